@@ -1,0 +1,116 @@
+// Edge list -> destination-major CSR on the device.
+//
+// Replaces, for the kernels below, what the reference does on every forward with
+// torch_sparse.SparseTensor(row=edge_index[1], col=edge_index[0]) (models/backbones.py:464) and what
+// torch_geometric.utils.coalesce does on the CPU (main_bridged_graph.py:75, 113, 193): sort by
+// (dst, src), optionally drop duplicate edges, emit rowptr/col plus the permutation back to the
+// caller's edge order.  The sort itself is CUB's radix sort (plumbing, run once per graph and cached
+// by the host layer); the rest is hand-written.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bgnn {
+
+// key = (dst << nb) | src with nb = bits needed for a node id, so the radix sort touches 2*nb bits only.
+__global__ void make_keys_kernel(const long long* __restrict__ src, const long long* __restrict__ dst, long long e, int nb,
+                                 unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= e) return;
+  keys[i] = ((unsigned long long)dst[i] << nb) | (unsigned long long)src[i];
+  vals[i] = (unsigned int)i;
+}
+
+__global__ void flag_heads_kernel(const unsigned long long* __restrict__ keys, long long e, int dedup,
+                                  unsigned int* __restrict__ flags) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= e) return;
+  flags[i] = (!dedup || i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+__global__ void compact_kernel(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ vals,
+                               const unsigned int* __restrict__ flags, const unsigned int* __restrict__ pos,
+                               long long e, int nb, int* __restrict__ col, long long* __restrict__ perm,
+                               unsigned long long* __restrict__ ckeys, long long* __restrict__ e_out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= e) return;
+  if (flags[i]) {
+    unsigned int p = pos[i];
+    col[p] = (int)(keys[i] & ((1ull << nb) - 1ull));
+    if (perm) perm[p] = (long long)vals[i];
+    ckeys[p] = keys[i];
+  }
+  if (i == e - 1) *e_out = (long long)pos[i] + (long long)flags[i];
+}
+
+// rowptr[r] = first position whose dst >= r  (r = 0..n)
+__global__ void rowptr_kernel(const unsigned long long* __restrict__ ckeys, const long long* __restrict__ e_out,
+                              long long n, int nb, int* __restrict__ rowptr) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n) return;
+  long long lo = 0, hi = *e_out;
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    if ((long long)(ckeys[mid] >> nb) < r) lo = mid + 1; else hi = mid;
+  }
+  rowptr[r] = (int)lo;
+}
+
+__global__ void zero_rowptr_kernel(long long n, int* rowptr, long long* e_out) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r <= n) rowptr[r] = 0;
+  if (r == 0) *e_out = 0;
+}
+
+static size_t cub_temp_bytes(long long e) {
+  size_t a = 0, b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const unsigned int*)nullptr, (unsigned int*)nullptr, e);
+  cub::DeviceScan::ExclusiveSum(nullptr, b, (const unsigned int*)nullptr, (unsigned int*)nullptr, e);
+  return a > b ? a : b;
+}
+
+size_t csr_build_workspace_bytes(long long e) {
+  if (e <= 0) return 256;
+  size_t per = 8 + 8 + 4 + 4 + 4 + 4;  // keys x2, vals x2, flags, pos
+  return (size_t)e * per + cub_temp_bytes(e) + 8 * 256;
+}
+
+int launch_edges_to_csr(const long long* src, const long long* dst, long long e, long long n, int dedup, int* rowptr,
+                        int* col, long long* perm, long long* e_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (n < 0 || e < 0 || n >= (1ll << 31) || e >= (1ll << 31)) return BGNN_ERR_INVALID_ARG;
+  const int T = 256;
+  if (e == 0) {
+    zero_rowptr_kernel<<<(unsigned)((n + 1 + T - 1) / T), T, 0, stream>>>(n, rowptr, e_out);
+    BGNN_LAUNCH_CHECK();
+    return BGNN_OK;
+  }
+  Workspace w(ws, ws_bytes);
+  auto* k0 = w.take<unsigned long long>(e);
+  auto* k1 = w.take<unsigned long long>(e);
+  auto* v0 = w.take<unsigned int>(e);
+  auto* v1 = w.take<unsigned int>(e);
+  auto* flags = w.take<unsigned int>(e);
+  auto* pos = w.take<unsigned int>(e);
+  size_t tb = cub_temp_bytes(e);
+  auto* temp = w.take<char>(tb);
+  if (!w.ok()) return BGNN_ERR_WORKSPACE;
+  unsigned blocks = (unsigned)((e + T - 1) / T);
+  int nb = 1;
+  while ((1ll << nb) < n) ++nb;
+  make_keys_kernel<<<blocks, T, 0, stream>>>(src, dst, e, nb, k0, v0);
+  BGNN_LAUNCH_CHECK();
+  BGNN_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, tb, k0, k1, v0, v1, e, 0, 2 * nb, stream));
+  flag_heads_kernel<<<blocks, T, 0, stream>>>(k1, e, dedup, flags);
+  BGNN_LAUNCH_CHECK();
+  BGNN_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, tb, flags, pos, e, stream));
+  compact_kernel<<<blocks, T, 0, stream>>>(k1, v1, flags, pos, e, nb, col, perm, k0, e_out);
+  BGNN_LAUNCH_CHECK();
+  rowptr_kernel<<<(unsigned)((n + 1 + T - 1) / T), T, 0, stream>>>(k0, e_out, n, nb, rowptr);
+  BGNN_LAUNCH_CHECK();
+  return BGNN_OK;
+}
+
+}  // namespace bgnn

@@ -1,0 +1,51 @@
+// Internal launcher declarations (C++).  The public surface is include/bgnn_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bgnn {
+
+// knn_simt.cu
+int launch_knn_simt(int mode, const float* Q, int nq, const float* DB, int ndb, int d, const float* w, float bias,
+                    int apply_sigmoid, int kc, int nsplit, int db_per_split, const int* row_list,
+                    const int* row_count, float* cand_val, int* cand_idx, cudaStream_t stream);
+int launch_normalize_split(const float* x, long long n, int d, int normalize, float* hi, float* lo, cudaStream_t stream);
+int launch_knn_merge(const float* cand_val, const int* cand_idx, int nlists, int kc, int nq, int k, int rescore,
+                     const float* qhi, const float* qlo, const float* dhi, const float* dlo, int d, int apply_sigmoid,
+                     float delta, const int* row_list, const int* row_count, long long* out_idx, float* out_val,
+                     float* out_gap, int* fb_rows, int* fb_count, cudaStream_t stream);
+
+// knn_cosine_sm100.cu  (tcgen05 / TMEM / TMA)
+struct TcPlan {
+  int bn;            // db rows per MMA tile (256, or 128 when k needs longer lists)
+  int nsplit;        // db splits (grid.y)
+  int tiles_per_split;
+  int kc;            // candidates kept per (row, list)
+  int nlists;        // lists per row = nsplit
+};
+TcPlan tc_plan(int nq, int ndb, int d, int k, int passes);
+int launch_knn_cosine_tc(const float* qhi, const float* qlo, int nq, const float* dhi, const float* dlo, int ndb, int d,
+                         int passes, const TcPlan& plan, float* cand_val, int* cand_idx, cudaStream_t stream);
+
+// csr_build.cu
+size_t csr_build_workspace_bytes(long long e);
+int launch_edges_to_csr(const long long* src, const long long* dst, long long e, long long n, int dedup, int* rowptr,
+                        int* col, long long* perm, long long* e_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// spmm_csr.cu
+int launch_spmm_csr(const int* rowptr, const int* col, const float* edge_w, const float* gather_scale,
+                    const float* out_scale, const float* X, long long n_rows, int f, int reduce_mean, float* Y,
+                    cudaStream_t stream);
+
+// gatv2_fused.cu
+int launch_gatv2_fwd(const int* rowptr, const int* col, const uint8_t* dst_is_src, const float* Hs, const float* Ht,
+                     const float* af_t2s, const float* af_s2t, float slope, long long n, int c, float* out,
+                     float* row_max, float* row_sum, cudaStream_t stream);
+size_t gatv2_bwd_workspace_bytes(long long n, int c);
+int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col,
+                     const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
+                     const float* af_s2t, float slope, long long n, int c, const float* out, const float* row_max,
+                     const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
+                     float* g_af_s2t, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace bgnn

@@ -1,0 +1,113 @@
+/* libbgnn_b200 -- C ABI of the B200-native Bridged-GNN hot path.
+ *
+ * The reference (wendongbi/Bridged-GNN) is pure Python on PyTorch/PyG and has no FFI; each entry
+ * point below names the reference call site(s) it replaces (paths relative to the reference
+ * checkout).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless stated otherwise; the library
+ *    allocates nothing persistent.  Scratch comes from a caller-provided workspace whose size is
+ *    returned by the matching *_workspace_bytes() query (pure host arithmetic, no GPU needed).
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream and does
+ *    no host synchronisation.
+ *  - return value: 0 = OK; negative = BGNN_ERR_* below; positive = cudaError_t of a failed launch.
+ *  - node indices are int64 at this boundary (PyG convention), int32 inside CSR (N, E < 2^31).
+ *  - sm_100a only: there is no CPU or other-architecture fallback.
+ */
+#ifndef BGNN_B200_H_
+#define BGNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGNN_ERR_INVALID_ARG (-1)
+#define BGNN_ERR_WORKSPACE (-2)
+#define BGNN_ERR_UNSUPPORTED (-3)
+#define BGNN_ERR_DRIVER (-4)
+
+/* kNN algorithms for the cosine head */
+#define BGNN_KNN_SIMT_F32 0   /* exact fp32 on CUDA cores                                    */
+#define BGNN_KNN_TC_3XTF32 1  /* tcgen05 3xTF32 split + exact fp32 re-score + certification */
+#define BGNN_KNN_TC_1XTF32 2  /* tcgen05 single TF32 pass + exact re-score + certification   */
+
+int bgnn_version(void);
+const char* bgnn_error_string(int code);
+
+/* ---- bridged-graph construction: fused all-pairs similarity + per-row top-k ------------------
+ *
+ * Replaces main_bridged_graph.py:45-67 and :90-111 (pair_enumeration models/models.py:265-282,
+ * similarity models/models.py:124-130 / 945-948 [cosine] and :949-954 [mlp], sim_mat.topk at
+ * main_bridged_graph.py:60,104).  The [nq, ndb] similarity matrix is never written to memory.
+ *
+ * Selection key (parity definition): post-sigmoid fp32 similarity descending, db index ascending.
+ * Outputs: out_idx[nq,k] int64 (db row of each neighbour, best first), out_val[nq,k] fp32 similarity,
+ * out_gap[nq] fp32 = sim_k - sim_(k+1) (+inf if ndb == k; rows with gap < 1e-6 are near-ties),
+ * out_stats[4] int32: [0] rows re-done by the exact fallback (tensor-core algorithms), [1..3] reserved.
+ * out_gap / out_stats may be NULL.  k > ndb is BGNN_ERR_INVALID_ARG (torch.topk raises there too).
+ */
+
+/* cosine head: sim = sigmoid( <q_i/max(|q_i|,1e-8), db_j/max(|db_j|,1e-8)> ).
+ * q [nq,d], db [ndb,d] row-major fp32 are the vectors fed to CosineSimilarity (u = z' + biasatt(z')).
+ * normalize=0 if rows are already unit length.  q == db (same pointer, nq == ndb) is the
+ * within-domain case; self matches are kept, as in the reference. */
+size_t bgnn_knn_cosine_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, int algo);
+int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb, int d, int k, int normalize,
+                        int apply_sigmoid, int algo, int64_t* out_idx, float* out_val, float* out_gap,
+                        int32_t* out_stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* v2 'mlp' head with eval-mode BatchNorm folded (models/models.py:918-925):
+ * sim = sigmoid( sum_h w2[h] * relu(Uq[i,h] + Udb[j,h]) + b2 ),  Uq [nq,h], Udb [ndb,h], w2 [h]. */
+size_t bgnn_knn_addrelu_workspace_bytes(int64_t nq, int64_t ndb, int h, int k);
+int bgnn_knn_addrelu_f32(const float* Uq, int64_t nq, const float* Udb, int64_t ndb, int h, const float* w2, float b2,
+                         int k, int apply_sigmoid, int64_t* out_idx, float* out_val, float* out_gap,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- graph format: edge list -> destination-major CSR ---------------------------------------
+ *
+ * Replaces torch_sparse.SparseTensor(row=edge_index[1], col=edge_index[0]) (models/backbones.py:464)
+ * and, with dedup=1, torch_geometric.utils.coalesce (main_bridged_graph.py:75,113,193) up to the
+ * (dst,src) instead of (src,dst) sort order.  rowptr [n+1] int32, col [e] int32 (source of each
+ * edge, rows sorted by destination then source), perm [e] int64 (position in the input edge list;
+ * may be NULL), e_out [1] int64 (number of edges kept). */
+size_t bgnn_edges_to_csr_workspace_bytes(int64_t e);
+int bgnn_edges_to_csr(const int64_t* src, const int64_t* dst, int64_t e, int64_t n, int dedup, int32_t* rowptr,
+                      int32_t* col, int64_t* perm, int64_t* e_out, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* ---- message passing ------------------------------------------------------------------------
+ *
+ * CSR SpMM:  Y[i,:] = out_scale[i] * (1/deg_i if reduce_mean) * sum_e edge_w[e] * gather_scale[col[e]] * X[col[e],:]
+ * Replaces torch_sparse.matmul(adj_t, x, reduce=...) under SAGEConv (models/backbones.py:464-468,
+ * models/models.py:250-253) and GCNConv's normalised propagate (models/backbones.py:272-274).
+ * edge_w [e], gather_scale [n_cols], out_scale [n_rows] may each be NULL (= 1).  The backward pass
+ * is the same call on the transposed CSR. */
+int bgnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* edge_w, const float* gather_scale,
+                      const float* out_scale, const float* X, int64_t n_rows, int f, int reduce_mean, float* Y,
+                      void* stream);
+
+/* Fused AdaptedConv aggregation (models/KTGNN.py:292-305, message :317-319; PyG softmax +
+ * propagate underneath).  Per destination row i: (H, a) = (Hs, af_t2s) if dst_is_src[i] else
+ * (Ht, af_s2t); score_j = a . leaky_relu(H[j] + H[i], slope); out[i] = sum_j softmax_j(score) H[j].
+ * Hs = lin_s(x_t2s), Ht = lin_t(x_s2t), both [n,c]; dst_is_src [n] bytes (central_mask);
+ * row_max / row_sum [n] are saved for the backward pass (may be NULL for inference). */
+int bgnn_gatv2_fwd_f32(const int32_t* rowptr, const int32_t* col, const uint8_t* dst_is_src, const float* Hs,
+                       const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n, int c,
+                       float* out, float* row_max, float* row_sum, void* stream);
+
+/* Backward of the above.  (rowptr,col) = CSR by destination, (t_rowptr,t_col) = CSR of the transposed
+ * graph (rows = sources, entries = destinations).  Writes gHs, gHt [n,c], g_af_t2s, g_af_s2t [c]. */
+size_t bgnn_gatv2_bwd_workspace_bytes(int64_t n, int c);
+int bgnn_gatv2_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
+                       const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
+                       const float* af_s2t, float slope, int64_t n, int c, const float* out, const float* row_max,
+                       const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
+                       float* g_af_s2t, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGNN_B200_H_ */

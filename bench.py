@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""Benchmark of the Bridged-GNN hot path on B200 (BASELINE.json metric:
+"bridged-graph kNN build ms & KT-GNN message-passing GEdges/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3]): synthetic Sync-RD_intra-and-inter, 2^20 nodes per GPU
+(786 432 source + 262 144 target), dim 128, 2 classes, k_cross = 20, 70 % homophily random edges.
+  phase A  bridged-graph build: cosine-head kNN of every target row against all source rows
+           (fused tcgen05 similarity + top-k, exact after re-scoring) + edge assembly      -> knn_build.ms
+  phase B  message passing: one KT-GNN (2 layers, hidden 64) training forward + backward over
+           the bridged graph (random edges U kNN edges, undirected, self loops)             -> value, GEdges/s
+A "step" is one phase-B pass; `value` = E_mp * 8 conv passes (4 forward + 4 backward) / step time.
+Multi-GPU (torchrun): weak scaling, every rank owns its own 2^20-node shard (target rows are sharded
+for the build, the kNN lists are all-gathered with NCCL); value sums the ranks' edges over the max time.
+
+--impl reference times the oracle restatement of the reference's own op sequence on the host CPU
+(PyG-free port; the reference itself needs torch_geometric, which is not installable here) on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NS, NT, DIM, K_CROSS, N_CLASS, HIDDEN = 786432, 262144, 128, 20, 2, 64
+RAND_EDGES_PER_NODE, HOMOPHILY = 5, 0.7
+METRIC = "bridged-graph kNN build ms & KT-GNN message-passing GEdges/s"
+
+
+# ----------------------------------------------------------------------------- synthetic workload
+def make_sync_embeddings(ns, nt, d, device, seed=0, n_class=N_CLASS, tar_seed=None):
+    """SURVEY 8d config 4 generator: class means mu_s[c] ~ N(0, I), mu_t[c] = 0.8 mu_s[c] + 0.3 + 0.2 N(0, I);
+    u = mu[y] + N(0, I).  Means come from `seed`, source rows from seed+1, target rows from `tar_seed`
+    (default seed+2) so that shards of target rows share one source set.
+    Returns (u_src [ns,d], u_tar [nt,d], y_src, y_tar)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    mu_s = torch.randn(n_class, d, generator=g, device=device)
+    mu_t = 0.8 * mu_s + 0.3 + 0.2 * torch.randn(n_class, d, generator=g, device=device)
+    gs = torch.Generator(device=device).manual_seed(seed + 1)
+    y_s = torch.randint(0, n_class, (ns,), generator=gs, device=device)
+    u_s = mu_s[y_s] + torch.randn(ns, d, generator=gs, device=device)
+    gt = torch.Generator(device=device).manual_seed(seed + 2 if tar_seed is None else tar_seed)
+    y_t = torch.randint(0, n_class, (nt,), generator=gt, device=device)
+    u_t = mu_t[y_t] + torch.randn(nt, d, generator=gt, device=device)
+    return u_s, u_t, y_s, y_t
+
+
+def make_random_edges(y, per_node, homophily, device, seed=1):
+    """per_node * N directed draws: dst uniform, src of the same class w.p. `homophily` else of another class."""
+    n = y.shape[0]
+    g = torch.Generator(device=device).manual_seed(seed)
+    e = per_node * n
+    dst = torch.randint(0, n, (e,), generator=g, device=device)
+    same = torch.rand(e, generator=g, device=device) < homophily
+    order = torch.argsort(y, stable=True)
+    counts = torch.bincount(y, minlength=N_CLASS)
+    starts = torch.cumsum(counts, 0) - counts
+    cls = torch.where(same, y[dst], (y[dst] + 1) % N_CLASS)
+    r = torch.rand(e, generator=g, device=device)
+    pos = starts[cls] + (r * counts[cls]).long().clamp(max=n - 1)
+    src = order[pos.clamp(max=n - 1)]
+    return torch.stack((src, dst), 0)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [t.strip() for t in line.split(",")]
+                if len(p) < 9:
+                    continue
+                sm.append(float(p[1])); mx.append(float(p[2]))
+                for nme, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_knn_sample(rows=12, seed=0):
+    """Oracle (reference op order: pair enumeration -> gather -> CosineSimilarity -> sigmoid -> top-k) on a
+    few target rows against the full 786 432-row source set."""
+    from oracle import build_oracle as bo
+    cores = bo.set_threads()
+    dev = torch.device("cpu")
+    u_s, u_t, _, _ = make_sync_embeddings(NS, rows, DIM, dev, seed)
+    t0 = time.perf_counter()
+    bo.cosine_knn_rows(u_s, u_t, K_CROSS, chunk=4)
+    dt = time.perf_counter() - t0
+    return {"gpairs_per_s": rows * NS / dt / 1e9, "seconds": dt, "cores": cores,
+            "sample": "%d target rows x %d source rows, d=%d (full build = %d rows)" % (rows, NS, DIM, NT),
+            "ms_full_build_extrapolated": dt / rows * NT * 1e3}
+
+
+def _oracle_ktgnn_params(model):
+    return {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+
+
+def cpu_mp_sample(n_nodes=1 << 15, seed=0, reps=2):
+    """Oracle KT-GNN (PyG-semantics gather / softmax / scatter-add, torch autograd) forward + backward on
+    the same generator at a reduced node count."""
+    from oracle import build_oracle as bo
+    from oracle import mp_oracle as mo
+    cores = bo.set_threads()
+    dev = torch.device("cpu")
+    ns, nt = n_nodes * 3 // 4, n_nodes // 4
+    u_s, u_t, y_s, y_t = make_sync_embeddings(ns, nt, DIM, dev, seed)
+    x = torch.cat((u_s, u_t), 0)
+    y = torch.cat((y_s, y_t), 0)
+    ei = make_random_edges(y, RAND_EDGES_PER_NODE, HOMOPHILY, dev)
+    # stand-in for the kNN edges at this size: K_CROSS random same-class source neighbours per target row
+    tar = torch.arange(ns, n_nodes).repeat_interleave(K_CROSS)
+    srcn = torch.randint(0, ns, (tar.numel(),), generator=torch.Generator().manual_seed(2))
+    ei = mo.to_undirected(torch.cat((ei, torch.stack((srcn, tar))), 1), n_nodes)
+    cm = torch.zeros(n_nodes, dtype=torch.bool)
+    cm[:ns] = True
+    torch.manual_seed(0)
+    P = _init_ktgnn_params(DIM, N_CLASS, HIDDEN)
+    e1, e2, eall = mo.graph_partition(ei, cm)
+    e_mp = eall.shape[1]
+    best = None
+    for _ in range(reps):
+        Pg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in P.items()}
+        t0 = time.perf_counter()
+        lb, lt, ltt = mo.ktgnn_no_complement(x, ei, cm, Pg, training=True)
+        loss = sum(torch.nn.functional.nll_loss(l[cm], y[cm]) for l in (lb, lt, ltt))
+        loss.backward()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": e_mp * 8 / best / 1e9, "unit": "GEdges/s", "cores": cores, "kind": "port", "seconds": best,
+            "sample": "same generator at N=%d nodes (E_mp=%d); oracle KT-GNN fwd+bwd, best of %d" % (n_nodes, e_mp, reps)}
+
+
+def _init_ktgnn_params(f_in, n_class, hidden):
+    """state_dict-shaped random parameters for the oracle (shapes of KTGNN_no_complement, layer_num=2)."""
+    g = torch.Generator().manual_seed(0)
+    P = {}
+
+    def conv(prefix, i, o):
+        for nme, shape in (("lin_s.weight", (o, i)), ("lin_s.bias", (o,)), ("lin_t.weight", (o, i)), ("lin_t.bias", (o,)),
+                           ("a_g_s2t.weight", (1, 2 * i)), ("a_g_t2s.weight", (1, 2 * i)), ("a_f_s2t.weight", (1, o)),
+                           ("a_f_t2s.weight", (1, o))):
+            P[prefix + nme] = torch.randn(shape, generator=g) * (1.0 / max(shape[-1], 1)) ** 0.5
+    conv("convs.0.", f_in, hidden)
+    conv("clf_base.", hidden, n_class)
+    conv("clf_target.", hidden, n_class)
+    for bn in ("bns.0", "clf_transformer.1"):
+        P[bn + ".weight"], P[bn + ".bias"] = torch.ones(hidden), torch.zeros(hidden)
+        P[bn + ".running_mean"], P[bn + ".running_var"] = torch.zeros(hidden), torch.ones(hidden)
+    for lin in ("clf_transformer.0", "clf_transformer.3"):
+        P[lin + ".weight"] = torch.randn(hidden, hidden, generator=g) / hidden ** 0.5
+        P[lin + ".bias"] = torch.zeros(hidden)
+    return P
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    mp_runs = [cpu_mp_sample(reps=1) for _ in range(max(1, min(args.steps, 3)))]
+    mp = max(mp_runs, key=lambda r: r["value"])
+    knn = cpu_knn_sample(rows=8)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mp["value"], "unit": "GEdges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mp["seconds"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "sync-1M (configs[3]) sampled for the CPU", "mp_sample": mp["sample"],
+                   "knn_sample": knn["sample"]},
+        "cpu_baseline": {"value": mp["value"], "unit": "GEdges/s", "cores": mp["cores"], "kind": "port",
+                         "sample": mp["sample"]},
+        "e2e": {"value": mp["value"], "unit": "GEdges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "knn_build": {"ms": knn["ms_full_build_extrapolated"], "gpairs_per_s": knn["gpairs_per_s"], "cores": knn["cores"],
+                      "sample": knn["sample"], "note": "ms extrapolated linearly in rows from the sample"},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from bridged_gnn_b200 import _lib, ops
+    from bridged_gnn_b200.data import Data, to_undirected
+    from bridged_gnn_b200.models import KTGNN_no_complement
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU oracle)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    peaks = load_peaks()
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) / steps
+
+    # ---- data: every rank owns one sync-1M shard (weak scaling); the source set is shared -------------
+    u_src, u_tar, y_src, y_tar = make_sync_embeddings(NS, NT, DIM, dev, seed=0, tar_seed=100 + rank)
+    u_src_h, u_tar_h = u_src.cpu().pin_memory(), u_tar.cpu().pin_memory()
+
+    # ---- phase A: bridged-graph build ------------------------------------------------------------------
+    def build(us, ut):
+        idx, val, gap, stats = ops.knn_cosine(ut, us, K_CROSS, normalize=True, apply_sigmoid=True, algo=args.knn_algo)
+        if world > 1:   # per-shard kNN lists -> every rank (NCCL all-gather over NVLink)
+            gi = torch.empty((world,) + idx.shape, dtype=idx.dtype, device=dev)
+            gv = torch.empty((world,) + val.shape, dtype=val.dtype, device=dev)
+            dist.all_gather_into_tensor(gi, idx)
+            dist.all_gather_into_tensor(gv, val)
+        to = torch.arange(NT, device=dev).unsqueeze(1).expand(NT, K_CROSS)
+        edges = torch.stack((idx.reshape(-1), to.reshape(-1)), 0)
+        return idx, val, gap, stats, edges
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = _lib.launches
+    _lib.start_timing()
+    knn_ms = timed(lambda: build(u_src, u_tar), K, W)
+    knn_calls = _lib.stop_timing()
+    knn_launches = (_lib.launches - launches0) * K // (K + W)
+    idx, val, gap, stats, cross_edges = build(u_src, u_tar)
+    n_fallback = int(stats[0].item())
+    near_ties = int((gap < 1e-6).sum().item())
+
+    def build_e2e():
+        us, ut = u_src_h.to(dev, non_blocking=True), u_tar_h.to(dev, non_blocking=True)
+        out = build(us, ut)
+        return out[4].cpu()
+    knn_e2e_ms = timed(build_e2e, max(2, K // 2), 1)
+    calls, tot = knn_calls.get("bgnn_knn_cosine_f32", (1, 0.0))
+    knn_call_ms = tot / max(calls, 1)
+    flops = 2.0 * NT * NS * DIM
+    tf32_peak = peaks["bf16_tflops"] / 2.0
+    knn_roof = {"bound": "tensor", "achieved": flops / (knn_call_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": flops / (knn_call_ms * 1e-3) / 1e12 / tf32_peak, "traffic": None,
+                "kernel": "knn_cosine_tc_kernel (timed: whole bgnn_knn_cosine_f32 call incl. prologue/merge)",
+                "peak_source": peaks["source"] + " bf16 dense / 2 (tcgen05 kind::tf32 runs at half the bf16 rate)",
+                "algorithmic_flops_per_launch": flops}
+
+    # ---- phase B: message passing over the bridged graph ------------------------------------------------
+    n = NS + NT
+    y = torch.cat((y_src, y_tar), 0)
+    rnd = make_random_edges(y, RAND_EDGES_PER_NODE, HOMOPHILY, dev, seed=1 + rank)
+    cross = cross_edges + torch.tensor([[0], [NS]], device=dev)
+    ei = to_undirected(torch.cat((rnd, cross), 1), n)
+    cm = torch.zeros(n, dtype=torch.bool, device=dev)
+    cm[:NS] = True
+    data = Data(x=torch.cat((u_src, u_tar), 0).contiguous(), edge_index=ei, y=y, central_mask=cm)
+    del rnd, cross, cross_edges, idx, val
+    torch.manual_seed(0)
+    model = KTGNN_no_complement(DIM, N_CLASS, 2, HIDDEN, root_weight=False, use_bn=True, dim_share=DIM,
+                                need_complement=False, dropout=0.0).to(dev)
+    model.train()
+    nll = torch.nn.functional.nll_loss
+
+    def train_step():
+        model.zero_grad(set_to_none=True)
+        lb, lt, ltt, _ = model(data)
+        loss = nll(lb[cm], y[cm]) + nll(lt[cm], y[cm]) + nll(ltt[cm], y[cm])
+        loss.backward()
+        return loss
+
+    def fwd_step():
+        with torch.no_grad():
+            return model(data)
+
+    train_step()                       # builds + caches partition / CSR / transposed CSR
+    e_mp = int(model.edge_index.shape[1])
+    launches0 = _lib.launches
+    _lib.start_timing()
+    step_ms = timed(train_step, K, W)
+    mp_calls = _lib.stop_timing()
+    mp_launches = (_lib.launches - launches0) * K // (K + W)
+    fwd_ms = timed(fwd_step, K, W)
+    clk = clocks.stop()
+    total_edges = e_mp * world
+    if world > 1:
+        t = torch.tensor([e_mp], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        total_edges = float(t.item())
+    value = total_edges * 8 / (step_ms * 1e-3) / 1e9
+
+    # e2e: host buffers in, log-probs out, through the public model API (fresh tensors -> CSR rebuilt too)
+    x_h, ei_h, cm_h = data.x.cpu().pin_memory(), ei.cpu().pin_memory(), cm.cpu().pin_memory()
+    h2d = x_h.numel() * 4 + ei_h.numel() * 8 + cm_h.numel()
+    d2h = 3 * n * N_CLASS * 4
+
+    def e2e_step():
+        d = Data(x=x_h.to(dev, non_blocking=True), edge_index=ei_h.to(dev, non_blocking=True),
+                 central_mask=cm_h.to(dev, non_blocking=True))
+        model.edge_index = None        # a new graph arrives: re-partition, rebuild CSR
+        model.zero_grad(set_to_none=True)
+        lb, lt, ltt, _ = model(d)
+        c = d.central_mask
+        loss = nll(lb[c], y[c]) + nll(lt[c], y[c]) + nll(ltt[c], y[c])
+        loss.backward()
+        return lb.detach().cpu(), lt.detach().cpu(), ltt.detach().cpu(), loss.item()
+    e2e_ms = timed(e2e_step, max(2, K // 2), 1)
+    e2e_value = total_edges * 8 / (e2e_ms * 1e-3) / 1e9
+
+    # roofline of the dominant message-passing kernel (largest share of the step among our kernels)
+    def gat_bytes(c, bwd):
+        fwd_b = e_mp * (4 + 4 * c) + n * (4 + 4 * c + 4 * c + 1 + 8)
+        return 2 * e_mp * (4 + 2 * 4 * c) + n * 8 * c if bwd else fwd_b
+    shares = {k: v[1] / (K + W) for k, v in mp_calls.items()}       # ms per step (events span warm-up + timed steps)
+    top = max(shares, key=shares.get) if shares else None
+    roof = None
+    if top:
+        c = int(top.split("c=")[1].rstrip("]")) if "c=" in top else HIDDEN
+        calls_per_step = mp_calls[top][0] / (K + W)
+        dur_ms = shares[top] / max(calls_per_step, 1e-9)
+        b = gat_bytes(c, "bwd" in top)
+        roof = {"bound": "hbm", "achieved": b / (dur_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": b / (dur_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "kernel": top,
+                "avg_launch_ms": dur_ms, "share_of_step": shares[top] / step_ms, "algorithmic_bytes_per_launch": b,
+                "peak_source": peaks["source"], "kernel_ms_per_step": {k: round(v, 4) for k, v in shares.items()}}
+
+    if rank == 0:
+        cpu = cpu_mp_sample() if world == 1 and not args.no_cpu_baseline else None
+        cpu_knn = cpu_knn_sample(rows=4) if world == 1 and not args.no_cpu_baseline else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "GEdges/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "sync-1M per GPU (BASELINE configs[3]): Ns=%d Nt=%d dim=%d k_cross=%d classes=%d hidden=%d"
+                                   % (NS, NT, DIM, K_CROSS, N_CLASS, HIDDEN),
+                       "E_mp": e_mp, "conv_passes_per_step": 8, "step": "KT-GNN train fwd+bwd (4 AdaptedConv fwd + 4 bwd)",
+                       "l2": "inputs exceed L2 (features %.0f MB, db %.0f MB)" % (n * DIM * 4 / 1e6, NS * DIM * 4 / 1e6),
+                       "knn_algo": args.knn_algo, "parallelism": "row-sharded x%d" % world},
+            "fwd_only": {"ms": fwd_ms, "gedges_per_s": total_edges * 4 / (fwd_ms * 1e-3) / 1e9},
+            "e2e": {"value": e2e_value, "unit": "GEdges/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "roofline": roof,
+            "knn_build": {"ms": knn_ms, "gpairs_per_s": NT * NS * world / (knn_ms * 1e-3) / 1e9,
+                          "tflops": flops * world / (knn_ms * 1e-3) / 1e12, "kernel_call_ms": knn_call_ms,
+                          "roofline": knn_roof, "exact_fallback_rows": n_fallback, "near_tie_rows": near_ties,
+                          "e2e": {"ms": knn_e2e_ms, "h2d_bytes_per_step": (NS + NT) * DIM * 4,
+                                  "d2h_bytes_per_step": 2 * NT * K_CROSS * 8},
+                          "cpu_baseline": cpu_knn, "gpu_launches": knn_launches},
+            "cpu_baseline": cpu, "gpu_launches": mp_launches, "clocks": clk,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--knn-algo", dest="knn_algo", default="tc3", choices=["tc3", "tc1", "simt"])
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

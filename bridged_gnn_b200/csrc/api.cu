@@ -1,0 +1,230 @@
+// C ABI of libbgnn_b200 (declared in include/bgnn_b200.h): argument checking, workspace carving and
+// the multi-kernel drivers.  No torch types, no allocation, no host synchronisation.
+#include "bgnn_b200.h"
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bgnn {
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+__global__ void copy_int_kernel(const int* src, int* dst) { *dst = *src; }
+
+// ---- cosine / add-ReLU kNN driver -------------------------------------------------------------
+struct SimtPlan {
+  int kc, nsplit, per_split;
+};
+
+static SimtPlan simt_plan(int nq, int ndb, int k, bool max_parallel) {
+  SimtPlan p;
+  p.kc = k + 1;                                    // the (k+1)-th value gives the near-tie gap
+  const int tiles = (ndb + 63) / 64;
+  const int qtiles = (nq + 63) / 64;
+  int ns = max_parallel ? tiles : (2 * kNumSMs + qtiles - 1) / qtiles;
+  ns = max(1, min(min(ns, tiles), BGNN_MERGE_MAX_CAND / p.kc));
+  const int tiles_per = (tiles + ns - 1) / ns;
+  p.per_split = tiles_per * 64;
+  p.nsplit = (tiles + tiles_per - 1) / tiles_per;
+  return p;
+}
+
+struct KnnPlan {
+  int algo;        // resolved algorithm
+  int passes;      // tensor-core passes (3 or 1), 0 for the CUDA-core sweep
+  int ld;          // row stride of the normalised planes
+  TcPlan tc;
+  SimtPlan simt;   // main sweep (SIMT algo) or exact fallback (tensor-core algos)
+  size_t cand_elems;
+};
+
+static bool knn_args_ok(int64_t nq, int64_t ndb, int d, int k) {
+  return nq >= 0 && ndb >= 1 && nq < (1ll << 31) && ndb < (1ll << 31) && d >= 1 && k >= 1 && k <= ndb && k <= 255;
+}
+
+static KnnPlan knn_plan(int64_t nq, int64_t ndb, int d, int k, int algo) {
+  KnnPlan p;
+  p.algo = algo;
+  p.passes = (algo == BGNN_KNN_TC_3XTF32) ? 3 : (algo == BGNN_KNN_TC_1XTF32 ? 1 : 0);
+  p.tc.bn = 0;
+  if (p.passes) {
+    p.tc = tc_plan((int)nq, (int)ndb, d, k, p.passes);
+    if (p.tc.bn == 0) { p.passes = 0; p.algo = BGNN_KNN_SIMT_F32; }   // k too large for the on-chip lists
+  }
+  p.ld = p.passes ? (d + 31) / 32 * 32 : d;
+  p.simt = simt_plan((int)nq, (int)ndb, k, /*max_parallel=*/p.passes != 0);
+  size_t simt_c = (size_t)p.simt.nsplit * nq * p.simt.kc;
+  size_t tc_c = p.passes ? (size_t)p.tc.nlists * nq * p.tc.kc : 0;
+  p.cand_elems = simt_c > tc_c ? simt_c : tc_c;
+  return p;
+}
+
+static size_t knn_ws_bytes(const KnnPlan& p, int64_t nq, int64_t ndb) {
+  size_t b = 0;
+  auto add = [&](size_t n) { b = align_up(b, 256) + n; };
+  const int planes = p.passes ? 2 : 1;
+  for (int i = 0; i < planes; ++i) { add((size_t)nq * p.ld * 4); add((size_t)ndb * p.ld * 4); }
+  add(p.cand_elems * 4);
+  add(p.cand_elems * 4);
+  add((size_t)nq * 4);   // fallback row list
+  add(256);              // fallback row count
+  return align_up(b, 256) + 256;
+}
+
+}  // namespace bgnn
+
+using namespace bgnn;
+
+extern "C" {
+
+int bgnn_version(void) { return 100; }
+
+const char* bgnn_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case BGNN_ERR_INVALID_ARG: return "invalid argument";
+    case BGNN_ERR_WORKSPACE: return "workspace too small";
+    case BGNN_ERR_UNSUPPORTED: return "unsupported size or option";
+    case BGNN_ERR_DRIVER: return "CUDA driver entry point unavailable";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+  }
+}
+
+size_t bgnn_knn_cosine_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, int algo) {
+  if (!knn_args_ok(nq, ndb, d, k)) return 0;
+  return knn_ws_bytes(knn_plan(nq, ndb, d, k, algo), nq, ndb);
+}
+
+int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb, int d, int k, int normalize,
+                        int apply_sigmoid, int algo, int64_t* out_idx, float* out_val, float* out_gap,
+                        int32_t* out_stats, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!knn_args_ok(nq, ndb, d, k) || !q || !db || !out_idx || !out_val) return BGNN_ERR_INVALID_ARG;
+  if (algo < BGNN_KNN_SIMT_F32 || algo > BGNN_KNN_TC_1XTF32) return BGNN_ERR_INVALID_ARG;
+  if (nq == 0) return BGNN_OK;
+  const KnnPlan p = knn_plan(nq, ndb, d, k, algo);
+  if (workspace_bytes < knn_ws_bytes(p, nq, ndb) || !workspace) return BGNN_ERR_WORKSPACE;
+  Workspace w(workspace, workspace_bytes);
+  const bool same = (q == db) && (nq == ndb);
+  float* qhi = w.take<float>((size_t)nq * p.ld);
+  float* dhi = w.take<float>((size_t)ndb * p.ld);
+  float *qlo = nullptr, *dlo = nullptr;
+  if (p.passes) { qlo = w.take<float>((size_t)nq * p.ld); dlo = w.take<float>((size_t)ndb * p.ld); }
+  float* cand_val = w.take<float>(p.cand_elems);
+  int* cand_idx = w.take<int>(p.cand_elems);
+  int* fb_rows = w.take<int>((size_t)nq);
+  int* fb_count = w.take<int>(64);
+  if (!w.ok()) return BGNN_ERR_WORKSPACE;
+  int rc;
+  // prologue: unit rows (and the tf32 hi/lo split for the tensor-core sweep)
+  if ((rc = launch_normalize_split(db, ndb, d, p.ld, normalize, dhi, dlo, stream)) != BGNN_OK) return rc;
+  if (same) { qhi = dhi; qlo = dlo; }
+  else if ((rc = launch_normalize_split(q, nq, d, p.ld, normalize, qhi, qlo, stream)) != BGNN_OK) return rc;
+
+  if (!p.passes) {
+    rc = launch_knn_simt(BGNN_PAIR_DOT, qhi, nullptr, (int)nq, dhi, nullptr, (int)ndb, d, p.ld, nullptr, 0.f,
+                         apply_sigmoid, p.simt.kc, p.simt.nsplit, p.simt.per_split, nullptr, nullptr, cand_val,
+                         cand_idx, stream);
+    if (rc != BGNN_OK) return rc;
+    rc = launch_knn_merge(cand_val, cand_idx, p.simt.nsplit, p.simt.kc, (int)nq, k, 0, nullptr, nullptr, nullptr,
+                          nullptr, d, p.ld, apply_sigmoid, -1.f, nullptr, nullptr, (long long*)out_idx, out_val,
+                          out_gap, nullptr, nullptr, stream);
+    if (rc != BGNN_OK) return rc;
+    if (out_stats) { set_int_kernel<<<1, 1, 0, stream>>>(out_stats, 0); BGNN_LAUNCH_CHECK(); }
+    return BGNN_OK;
+  }
+
+  // tensor-core sweep nominates, merge re-scores + certifies, CUDA-core sweep redoes uncertified rows
+  set_int_kernel<<<1, 1, 0, stream>>>(fb_count, 0);
+  BGNN_LAUNCH_CHECK();
+  rc = launch_knn_cosine_tc(qhi, qlo, (int)nq, dhi, dlo, (int)ndb, p.ld, p.passes, p.tc, cand_val, cand_idx, stream);
+  if (rc != BGNN_OK) return rc;
+  // error bound of the approximate dot product of two unit rows (see DESIGN.md "kNN exactness")
+  const float delta = (p.passes == 3) ? 3.0e-5f : 2.0e-3f;
+  rc = launch_knn_merge(cand_val, cand_idx, p.tc.nlists, p.tc.kc, (int)nq, k, 1, qhi, qlo, dhi, dlo, p.ld, p.ld,
+                        apply_sigmoid, delta, nullptr, nullptr, (long long*)out_idx, out_val, out_gap, fb_rows,
+                        fb_count, stream);
+  if (rc != BGNN_OK) return rc;
+  rc = launch_knn_simt(BGNN_PAIR_DOT, qhi, qlo, (int)nq, dhi, dlo, (int)ndb, p.ld, p.ld, nullptr, 0.f, apply_sigmoid,
+                       p.simt.kc, p.simt.nsplit, p.simt.per_split, fb_rows, fb_count, cand_val, cand_idx, stream);
+  if (rc != BGNN_OK) return rc;
+  rc = launch_knn_merge(cand_val, cand_idx, p.simt.nsplit, p.simt.kc, (int)nq, k, 0, nullptr, nullptr, nullptr,
+                        nullptr, p.ld, p.ld, apply_sigmoid, -1.f, fb_rows, fb_count, (long long*)out_idx, out_val,
+                        out_gap, nullptr, nullptr, stream);
+  if (rc != BGNN_OK) return rc;
+  if (out_stats) { copy_int_kernel<<<1, 1, 0, stream>>>(fb_count, out_stats); BGNN_LAUNCH_CHECK(); }
+  return BGNN_OK;
+}
+
+size_t bgnn_knn_addrelu_workspace_bytes(int64_t nq, int64_t ndb, int h, int k) {
+  if (!knn_args_ok(nq, ndb, h, k)) return 0;
+  const SimtPlan p = simt_plan((int)nq, (int)ndb, k, false);
+  return align_up((size_t)p.nsplit * nq * p.kc * 4, 256) * 2 + 512;
+}
+
+int bgnn_knn_addrelu_f32(const float* Uq, int64_t nq, const float* Udb, int64_t ndb, int h, const float* w2, float b2,
+                         int k, int apply_sigmoid, int64_t* out_idx, float* out_val, float* out_gap,
+                         void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!knn_args_ok(nq, ndb, h, k) || !Uq || !Udb || !w2 || !out_idx || !out_val) return BGNN_ERR_INVALID_ARG;
+  if (nq == 0) return BGNN_OK;
+  const SimtPlan p = simt_plan((int)nq, (int)ndb, k, false);
+  if (!workspace || workspace_bytes < bgnn_knn_addrelu_workspace_bytes(nq, ndb, h, k)) return BGNN_ERR_WORKSPACE;
+  Workspace w(workspace, workspace_bytes);
+  const size_t ce = (size_t)p.nsplit * nq * p.kc;
+  float* cand_val = w.take<float>(ce);
+  int* cand_idx = w.take<int>(ce);
+  if (!w.ok()) return BGNN_ERR_WORKSPACE;
+  int rc = launch_knn_simt(BGNN_PAIR_ADDRELU, Uq, nullptr, (int)nq, Udb, nullptr, (int)ndb, h, h, w2, b2, apply_sigmoid,
+                           p.kc, p.nsplit, p.per_split, nullptr, nullptr, cand_val, cand_idx, stream);
+  if (rc != BGNN_OK) return rc;
+  return launch_knn_merge(cand_val, cand_idx, p.nsplit, p.kc, (int)nq, k, 0, nullptr, nullptr, nullptr, nullptr, h, h,
+                          apply_sigmoid, -1.f, nullptr, nullptr, (long long*)out_idx, out_val, out_gap, nullptr,
+                          nullptr, stream);
+}
+
+size_t bgnn_edges_to_csr_workspace_bytes(int64_t e) { return e < 0 ? 0 : csr_build_workspace_bytes(e); }
+
+int bgnn_edges_to_csr(const int64_t* src, const int64_t* dst, int64_t e, int64_t n, int dedup, int32_t* rowptr,
+                      int32_t* col, int64_t* perm, int64_t* e_out, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  if (e < 0 || n < 0 || !rowptr || !e_out || (e > 0 && (!src || !dst || !col))) return BGNN_ERR_INVALID_ARG;
+  if (e > 0 && (!workspace || workspace_bytes < csr_build_workspace_bytes(e))) return BGNN_ERR_WORKSPACE;
+  return launch_edges_to_csr((const long long*)src, (const long long*)dst, e, n, dedup, rowptr, col, (long long*)perm,
+                             (long long*)e_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bgnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* edge_w, const float* gather_scale,
+                      const float* out_scale, const float* X, int64_t n_rows, int f, int reduce_mean, float* Y,
+                      void* stream) {
+  if (n_rows < 0 || f < 0 || (n_rows > 0 && f > 0 && (!rowptr || !X || !Y))) return BGNN_ERR_INVALID_ARG;
+  return launch_spmm_csr(rowptr, col, edge_w, gather_scale, out_scale, X, n_rows, f, reduce_mean, Y,
+                         (cudaStream_t)stream);
+}
+
+int bgnn_gatv2_fwd_f32(const int32_t* rowptr, const int32_t* col, const uint8_t* dst_is_src, const float* Hs,
+                       const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n, int c,
+                       float* out, float* row_max, float* row_sum, void* stream) {
+  if (n < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!rowptr || !col || !dst_is_src || !Hs || !Ht || !af_t2s || !af_s2t || !out)) return BGNN_ERR_INVALID_ARG;
+  return launch_gatv2_fwd(rowptr, col, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, c, out, row_max, row_sum,
+                          (cudaStream_t)stream);
+}
+
+size_t bgnn_gatv2_bwd_workspace_bytes(int64_t n, int c) { return (n < 0 || c <= 0) ? 0 : gatv2_bwd_workspace_bytes(n, c); }
+
+int bgnn_gatv2_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
+                       const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
+                       const float* af_s2t, float slope, int64_t n, int c, const float* out, const float* row_max,
+                       const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
+                       float* g_af_s2t, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!rowptr || !col || !t_rowptr || !t_col || !dst_is_src || !Hs || !Ht || !af_t2s || !af_s2t || !out ||
+                !row_max || !row_sum || !gout || !gHs || !gHt || !g_af_t2s || !g_af_s2t))
+    return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!workspace || workspace_bytes < gatv2_bwd_workspace_bytes(n, c))) return BGNN_ERR_WORKSPACE;
+  return launch_gatv2_bwd(rowptr, col, t_rowptr, t_col, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, c, out, row_max,
+                          row_sum, gout, gHs, gHt, g_af_t2s, g_af_s2t, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -75,7 +75,7 @@ __device__ __forceinline__ ListState list_init() {
 
 // Precondition: v > st.thr (always true while the list is not full).  Kept out of line: it runs
 // ~k*ln(N/k) times per row over a whole sweep, so it must not bloat the hot loop.
-__device__ __noinline__ ListState list_insert(float* val, int* idx, int stride, int kc, ListState st, float v, int j) {
+static __device__ __noinline__ ListState list_insert(float* val, int* idx, int stride, int kc, ListState st, float v, int j) {
   int slot = (st.cnt < kc) ? st.cnt : st.worst;
   val[slot * stride] = v;
   idx[slot * stride] = j;

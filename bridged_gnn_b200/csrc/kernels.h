@@ -6,14 +6,20 @@
 namespace bgnn {
 
 // knn_simt.cu
-int launch_knn_simt(int mode, const float* Q, int nq, const float* DB, int ndb, int d, const float* w, float bias,
-                    int apply_sigmoid, int kc, int nsplit, int db_per_split, const int* row_list,
-                    const int* row_count, float* cand_val, int* cand_idx, cudaStream_t stream);
-int launch_normalize_split(const float* x, long long n, int d, int normalize, float* hi, float* lo, cudaStream_t stream);
+#define BGNN_PAIR_DOT 0
+#define BGNN_PAIR_ADDRELU 1
+int launch_knn_simt(int mode, const float* Q, const float* Qlo, int nq, const float* DB, const float* DBlo, int ndb,
+                    int d, int ld, const float* w, float bias, int apply_sigmoid, int kc, int nsplit, int db_per_split,
+                    const int* row_list, const int* row_count, float* cand_val, int* cand_idx, cudaStream_t stream);
+
+// knn_select.cu
+#define BGNN_MERGE_MAX_CAND 1024
+int launch_normalize_split(const float* x, long long n, int d, int ld, int normalize, float* hi, float* lo,
+                           cudaStream_t stream);
 int launch_knn_merge(const float* cand_val, const int* cand_idx, int nlists, int kc, int nq, int k, int rescore,
-                     const float* qhi, const float* qlo, const float* dhi, const float* dlo, int d, int apply_sigmoid,
-                     float delta, const int* row_list, const int* row_count, long long* out_idx, float* out_val,
-                     float* out_gap, int* fb_rows, int* fb_count, cudaStream_t stream);
+                     const float* qhi, const float* qlo, const float* dhi, const float* dlo, int d, int ld,
+                     int apply_sigmoid, float delta, const int* row_list, const int* row_count, long long* out_idx,
+                     float* out_val, float* out_gap, int* fb_rows, int* fb_count, cudaStream_t stream);
 
 // knn_cosine_sm100.cu  (tcgen05 / TMEM / TMA)
 struct TcPlan {
@@ -21,6 +27,7 @@ struct TcPlan {
   int nsplit;        // db splits (grid.y)
   int tiles_per_split;
   int kc;            // candidates kept per (row, list)
+  int stages;        // depth of the TMA->MMA operand ring
   int nlists;        // lists per row = nsplit
 };
 TcPlan tc_plan(int nq, int ndb, int d, int k, int passes);

@@ -39,10 +39,10 @@ struct TcCfg {
   static constexpr int PLANES = (PASSES == 3) ? 2 : 1;
   static constexpr int B_PLANE = BN * TC_BK * 4;
   static constexpr int STAGE_BYTES = PLANES * (TC_A_PLANE + B_PLANE);
-  // BN=256 leaves 32 KB for the lists (kc = 32); BN=128 trades ring depth for lists up to kc = 96.
-  static constexpr int STAGES = (BN == 256 ? 196608 : 131072) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;   // 512 or 256: powers of two
 };
+constexpr int TC_SMEM_MAX = 232448;          // 227 KB opt-in limit per CTA
+constexpr int TC_SMEM_FIXED = 1024 + 512;    // alignment slack + barriers / tmem slot
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -131,10 +131,9 @@ template <int PASSES, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_cosine_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
                      const __grid_constant__ CUtensorMap map_dhi, const __grid_constant__ CUtensorMap map_dlo,
-                     int nq, int ndb, int kblocks, int tiles_total, int tiles_per_split, int kc,
+                     int nq, int ndb, int kblocks, int tiles_total, int tiles_per_split, int kc, int STAGES,
                      float* __restrict__ cand_val, int* __restrict__ cand_idx) {
   using Cfg = TcCfg<PASSES, BN>;
-  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* stage_base = smem;                                   // STAGES * STAGE_BYTES, 1024-aligned
@@ -325,16 +324,27 @@ static int make_map(CUtensorMap* m, const float* base, long long rows, int dpad,
   return r == CUDA_SUCCESS ? BGNN_OK : BGNN_ERR_DRIVER;
 }
 
+// Work decomposition.  Lists of kc > k nominees per (row, split) live in shared memory next to the
+// operand ring, so kc, the db tile width and the ring depth are traded against each other here.
 TcPlan tc_plan(int nq, int ndb, int d, int k, int passes) {
-  (void)d; (void)passes;
+  (void)d;
   TcPlan p;
-  const int bn = (k + 4 <= 32) ? 256 : 128;
-  p.bn = bn;
-  p.kc = (bn == 256) ? 32 : min(96, k + 8);
-  const int tiles = (ndb + bn - 1) / bn;
+  p.bn = 0;
+  int kc = (passes == 3) ? (k + 4) : max(k + 12, (3 * k) / 2 + 2);
+  kc = (kc + 3) / 4 * 4;
+  p.kc = kc;
+  const int planes = (passes == 3) ? 2 : 1;
+  const int list_bytes = kc * TC_BM * 8;
+  for (int bn = 256; bn >= 128; bn >>= 1) {
+    const int stage_bytes = planes * (TC_A_PLANE + bn * TC_BK * 4);
+    const int stages = (TC_SMEM_MAX - TC_SMEM_FIXED - list_bytes) / stage_bytes;
+    if (stages >= 2) { p.bn = bn; p.stages = min(stages, 8); break; }
+  }
+  if (p.bn == 0 || kc > BGNN_MERGE_MAX_CAND) { p.bn = 0; return p; }   // caller falls back to the CUDA-core sweep
+  const int tiles = (ndb + p.bn - 1) / p.bn;
   const int qblocks = (nq + TC_BM - 1) / TC_BM;
-  int ns = (2 * kNumSMs + qblocks - 1) / qblocks;
-  ns = max(1, min(min(ns, tiles), 8));
+  int ns = (2 * kNumSMs + qblocks - 1) / qblocks;      // aim for >= 2 CTAs per SM when nq is small
+  ns = max(1, min(min(ns, tiles), min(8, BGNN_MERGE_MAX_CAND / kc)));
   p.tiles_per_split = (tiles + ns - 1) / ns;
   p.nsplit = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.nlists = p.nsplit;
@@ -355,14 +365,14 @@ static int launch_cfg(const float* qhi, const float* qlo, int nq, const float* d
   } else {
     mq_lo = mq_hi; md_lo = md_hi;
   }
-  const size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + (size_t)plan.kc * TC_BM * 8 + 256;
-  if (smem > 232448) return BGNN_ERR_UNSUPPORTED;
+  const size_t smem = TC_SMEM_FIXED + (size_t)plan.stages * Cfg::STAGE_BYTES + (size_t)plan.kc * TC_BM * 8;
+  if (smem > (size_t)TC_SMEM_MAX || plan.stages < 2) return BGNN_ERR_UNSUPPORTED;
   auto kern = knn_cosine_tc_kernel<PASSES, BN>;
   BGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = (ndb + BN - 1) / BN;
   dim3 grid((nq + TC_BM - 1) / TC_BM, plan.nsplit);
   kern<<<grid, TC_THREADS, smem, stream>>>(mq_hi, mq_lo, md_hi, md_lo, nq, ndb, dpad / TC_BK, tiles,
-                                           plan.tiles_per_split, plan.kc, cand_val, cand_idx);
+                                           plan.tiles_per_split, plan.kc, plan.stages, cand_val, cand_idx);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }
@@ -372,6 +382,7 @@ int launch_knn_cosine_tc(const float* qhi, const float* qlo, int nq, const float
   if (nq <= 0) return BGNN_OK;
   if (d % TC_BK != 0) return BGNN_ERR_INVALID_ARG;   // caller pads to a multiple of 32
   const int bn = plan.bn;
+  if (bn != 128 && bn != 256) return BGNN_ERR_UNSUPPORTED;
   if (passes == 3) {
     return bn == 256 ? launch_cfg<3, 256>(qhi, qlo, nq, dhi, dlo, ndb, d, plan, cand_val, cand_idx, stream)
                      : launch_cfg<3, 128>(qhi, qlo, nq, dhi, dlo, ndb, d, plan, cand_val, cand_idx, stream);

@@ -1,0 +1,167 @@
+"""Bridged-graph construction with the reference's function surface (Bridged-GNN/main_bridged_graph.py).
+
+``add_topk_sim_cross_domain_edges`` / ``add_topk_sim_within_domain_edges`` keep the reference's names,
+argument meaning and return values (main_bridged_graph.py:33-75, 77-120) but never enumerate pairs:
+node embeddings and the node-wise operands of the similarity head are computed once, then one fused
+kernel scores every (query, db) pair on chip and keeps the top-k per row.  ``merge_graphs`` and
+``gen_bridged_graph`` assemble the merged graph on the device.
+"""
+import argparse
+import os
+
+import torch
+
+from . import ops
+from .data import Data, coalesce
+from .models.models import Adversarial_Learner, Adversarial_Learner_v2
+
+__all__ = ["add_topk_sim_cross_domain_edges", "add_topk_sim_within_domain_edges", "merge_graphs", "gen_bridged_graph"]
+
+
+def _homophily(y_from, y_to, edge_index):
+    lab = (y_from[edge_index[0]] != -1) & (y_to[edge_index[1]] != -1)
+    same = (y_from[edge_index[0]] == y_to[edge_index[1]]) & lab
+    return (same.sum() / lab.sum().clamp(min=1)).item()
+
+
+def _knn(sim_net, z_db, z_q, k, algo):
+    """Top-k db rows per query row under the head's similarity.  Returns idx [nq,k], val [nq,k], gap [nq]."""
+    if sim_net.mode == "cosine":
+        u_db = sim_net.cosine_operand(z_db)
+        u_q = u_db if z_q is z_db else sim_net.cosine_operand(z_q)
+        idx, val, gap, _ = ops.knn_cosine(u_q, u_db, k, normalize=True, apply_sigmoid=True, algo=algo)
+    else:
+        U_db, U_q, w2, b2 = sim_net.mlp_operands(z_db, z_q)
+        idx, val, gap = ops.knn_addrelu(U_q, U_db, w2, b2, k, apply_sigmoid=True)
+    return idx, val, gap
+
+
+def _edges_from_topk(idx):
+    """edge = (neighbour, query) for every kept neighbour, query-major like the reference's buckets."""
+    nq, k = idx.shape
+    to = torch.arange(nq, device=idx.device).unsqueeze(1).expand(nq, k)
+    return torch.stack((idx.reshape(-1), to.reshape(-1)), dim=0)
+
+
+def add_topk_sim_cross_domain_edges(data_src, data_tar, model, epsilon=0.5, k=3, batch_size=1000, apply_epsilon=False,
+                                    algo="auto", return_gap=False, verbose=True):
+    """For every target node, the k most similar source nodes (main_bridged_graph.py:33-75).
+
+    Returns ``(edge_index [2,E] int64 CPU coalesced (src, tar); e_sim_mat [Nt,k] fp32 CPU; idx_src_mat
+    [Nt,k] int64 CPU; probs_clf_src [Ns,C]; probs_clf_tar [Nt,C])`` like the reference.  Within a row the
+    neighbours come best first (the reference's ``topk(sorted=False)`` order is unspecified).
+    ``epsilon`` is accepted and, as in the reference (where the argument is never read), ignored unless
+    ``apply_epsilon=True``, which drops pairs with similarity <= epsilon.  ``batch_size`` is ignored:
+    nothing is materialised per batch.
+    """
+    with torch.no_grad():
+        model.eval()
+        z_src = model.embed_source(data_src)
+        z_tar = model.embed_target(data_tar)
+        probs_src, probs_tar = model.clf_probs(z_src), model.clf_probs(z_tar)
+        if probs_src is None:   # source_clf=False: the reference returns zeros.exp() == ones
+            probs_src = torch.ones((z_src.shape[0], int(data_src.y.max().item()) + 1))
+            probs_tar = torch.ones((z_tar.shape[0], int(data_tar.y.max().item()) + 1))
+        idx, val, gap = _knn(model.source_learner.sim_net, z_src, z_tar, k, algo)
+        edge_index = _edges_from_topk(idx)
+        if apply_epsilon:
+            edge_index = edge_index[:, val.reshape(-1) > epsilon]
+        if verbose:
+            print("Current homophily ratio:", _homophily(data_src.y, data_tar.y, edge_index))
+        edge_index = coalesce(edge_index)
+    out = (edge_index.cpu(), val.cpu(), idx.cpu(), probs_src, probs_tar)
+    return out + (gap.cpu(),) if return_gap else out
+
+
+def add_topk_sim_within_domain_edges(data_src, model, k=3, batch_size=1000, domain="source", algo="auto",
+                                     return_gap=False, verbose=True):
+    """k most similar nodes of the same domain for every node (main_bridged_graph.py:77-120); a node's
+    own row is not excluded, exactly as in the reference.  Returns ``(edge_index [2,E] (from, to)
+    coalesced, e_sim_mat [N,k], idx_mat [N,k])`` on the CPU."""
+    with torch.no_grad():
+        model.eval()
+        z = model.embed_source(data_src) if domain == "source" else model.embed_target(data_src)
+        idx, val, gap = _knn(model.source_learner.sim_net, z, z, k, algo)
+        edge_index = coalesce(_edges_from_topk(idx))
+        if verbose:
+            print("Current homophily ratio of Graph:", _homophily(data_src.y, data_src.y, edge_index))
+    out = (edge_index.cpu(), val.cpu(), idx.cpu())
+    return out + (gap.cpu(),) if return_gap else out
+
+
+def merge_graphs(data_src, data_tar, edge_index_cross_added, edge_index_added_src=None, edge_index_added_tar=None):
+    """main_bridged_graph.py:163-193 on the device: concatenate the two graphs and the added edges with
+    target ids offset by Ns, build the masks, coalesce.  Inputs are not modified."""
+    dev = data_src.x.device
+    n_src, n_tar = data_src.x.shape[0], data_tar.x.shape[0]
+    n = n_src + n_tar
+    off = torch.tensor([[0], [n_src]], device=dev)
+    parts = [data_src.edge_index.to(dev), data_tar.edge_index.to(dev) + n_src, edge_index_cross_added.to(dev) + off]
+    if edge_index_added_src is not None:
+        parts.append(edge_index_added_src.to(dev))
+    if edge_index_added_tar is not None:
+        parts.append(edge_index_added_tar.to(dev) + n_src)
+    edge_index = coalesce(torch.cat(parts, dim=1), n)
+    central = torch.zeros(n, dtype=torch.bool, device=dev)
+    central[:n_src] = True
+    train = central.clone()
+    train[:n_src] &= data_src.y.to(dev) != -1
+    train[n_src:] = data_tar.train_mask.to(dev)
+    val, test = torch.zeros_like(central), torch.zeros_like(central)
+    val[n_src:] = data_tar.val_mask.to(dev)
+    test[n_src:] = data_tar.test_mask.to(dev)
+    return Data(x=torch.cat((data_src.x, data_tar.x), 0), edge_index=edge_index, y=torch.cat((data_src.y, data_tar.y), 0),
+                train_mask=train, val_mask=val, test_mask=test, central_mask=central)
+
+
+def gen_bridged_graph(args, data_src, data_tar, device, path_ckpt, mapper_idx_src=None, mapper_idx_tar=None,
+                      epsilon=0.5, batch_size=1000):
+    """main_bridged_graph.py:267-321 without the optional validity filters and the id re-ordering
+    (SURVEY 8f "next" rows): load the similarity learner, add cross- and within-domain edges, merge."""
+    if args.version == "v1":
+        sim_model = Adversarial_Learner(data_src, data_tar, dim_hidden=args.hidden_dim, num_layer=args.num_layer,
+                                        source_clf=True, norm_mode=args.norm_mode, norm_scale=args.norm_scale)
+    else:
+        sim_model = Adversarial_Learner_v2(data_src, data_tar, dim_hidden=args.hidden_dim, num_layer=args.num_layer,
+                                           use_norm=True, source_clf=True, norm_mode=args.norm_mode,
+                                           norm_scale=args.norm_scale, sim_mode=args.sim_mode, backbone=args.backbone)
+    sim_model.load_state_dict(torch.load(path_ckpt, map_location="cpu"))
+    data_src, data_tar, sim_model = data_src.to(device), data_tar.to(device), sim_model.to(device)
+    if getattr(args, "check_cross", False) or getattr(args, "check_within", False):
+        raise NotImplementedError("edge-validity filters are not part of the accelerated path yet")
+    ei_cross, e_sim, idx_src, p_src, p_tar = add_topk_sim_cross_domain_edges(
+        data_src, data_tar, sim_model, epsilon=epsilon, k=args.k_cross, batch_size=batch_size)
+    ei_src = ei_tar = None
+    if args.k_within > 0:
+        ei_src, _, _ = add_topk_sim_within_domain_edges(data_src, sim_model, k=args.k_within, batch_size=100, domain="source")
+        ei_tar, _, _ = add_topk_sim_within_domain_edges(data_tar, sim_model, k=args.k_within, batch_size=100, domain="target")
+    data_merge = merge_graphs(data_src, data_tar, ei_cross, ei_src, ei_tar)
+    if getattr(args, "save", False):
+        os.makedirs("../data_bridged_graph", exist_ok=True)
+        torch.save({k: getattr(data_merge, k).cpu() for k in data_merge.keys()},
+                   f"../data_bridged_graph/{args.dataset_name}_bridged_graph.pt")
+    return data_merge
+
+
+def parse_args(argv=None):
+    """The reference's CLI flags that concern graph generation (main_bridged_graph.py:360-393)."""
+    p = argparse.ArgumentParser()
+    p.add_argument("--dataset_name", type=str, default="office_amazon2dslr")
+    p.add_argument("--version", type=str, default="v2", choices=["v1", "v2"])
+    p.add_argument("--backbone", type=str, default="mlp", choices=["mlp", "gnn"])
+    p.add_argument("--sim_mode", type=str, default="mlp", choices=["mlp", "cosine"])
+    p.add_argument("--hidden_dim", type=int, default=128)
+    p.add_argument("--num_layer", type=int, default=2)
+    p.add_argument("--norm_mode", type=str, default="None")
+    p.add_argument("--norm_scale", type=float, default=1.0)
+    p.add_argument("--k_cross", type=int, default=20)
+    p.add_argument("--k_within", type=int, default=3)
+    p.add_argument("--epsilon", type=float, default=0.5)
+    p.add_argument("--batch_size", type=int, default=1000)
+    p.add_argument("--check_cross", action="store_true")
+    p.add_argument("--check_within", action="store_true")
+    p.add_argument("--save", action="store_true")
+    p.add_argument("--gpu", type=int, default=0)
+    p.add_argument("--path_data", type=str, default=None, help="bridged-graph .dat to take features / split from")
+    p.add_argument("--path_ckpt", type=str, default=None)
+    return p.parse_args(argv)

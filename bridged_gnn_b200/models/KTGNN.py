@@ -1,0 +1,171 @@
+"""KT-GNN layers and models with the reference's constructor / forward / state_dict surface
+(models/KTGNN.py:218-328 AdaptedConv, :330-465 KTGNN_no_complement, :467-597 KTGNN_noDTC), running the
+edge part of every conv as one fused sm_100a kernel (ops.gat_aggregate) instead of PyG's
+gather -> softmax -> propagate chain.  Node-wise dense layers stay in torch (cuBLAS).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..data import add_self_loops, remove_self_loops
+
+
+class AdaptedConv(nn.Module):
+    """Domain-adaptive attention conv.  Parameters and their names match the reference
+    (lin_s, lin_t, a_g_s2t, a_g_t2s, a_f_s2t, a_f_t2s[, lin_r]) so its state_dicts load unchanged."""
+
+    def __init__(self, in_channels, out_channels, normalize=False, root_weight=True, activation_g=None,
+                 negative_slope=0.1, bias=True, **kwargs):
+        super().__init__()
+        if kwargs.get("aggr", "add") != "add":
+            raise NotImplementedError("AdaptedConv aggregates with 'add' (models/KTGNN.py:223)")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.normalize, self.root_weight = normalize, root_weight
+        self.activation_g, self.negative_slope = activation_g, negative_slope
+        cin = in_channels if isinstance(in_channels, int) else in_channels[0]
+        cin_r = in_channels if isinstance(in_channels, int) else in_channels[1]
+        if root_weight:
+            self.lin_r = nn.Linear(cin_r, out_channels, bias=False)
+        self.lin_s = nn.Linear(cin, out_channels, bias=bias)
+        self.lin_t = nn.Linear(cin, out_channels, bias=bias)
+        self.a_g_s2t = nn.Linear(cin * 2, 1, bias=False)
+        self.a_g_t2s = nn.Linear(cin * 2, 1, bias=False)
+        self.a_f_s2t = nn.Linear(out_channels, 1, bias=False)
+        self.a_f_t2s = nn.Linear(out_channels, 1, bias=False)
+        self._mask_key, self._mask_u8 = None, None
+
+    def reset_parameters(self):
+        for m in self.children():
+            m.reset_parameters()
+
+    def _dst_is_src(self, central_mask):
+        key = (central_mask.data_ptr(), central_mask._version, central_mask.shape[0])
+        if self._mask_key != key:
+            self._mask_key, self._mask_u8 = key, central_mask.to(torch.uint8).contiguous()
+        return self._mask_u8
+
+    def forward(self, x, edge_index, edge_index1=None, edge_index2=None, central_mask=None, size=None):
+        """edge_index must be cat(edge_index1, edge_index2) where edge_index1 / edge_index2 hold the edges
+        whose destination is a source- / target-domain node (KTGNN.graph_partition).  The fused kernel
+        picks the branch per destination row from ``central_mask``, so only ``edge_index`` is read."""
+        x_src, x_r = (x, x) if torch.is_tensor(x) else x
+        c = central_mask
+        # g: domain shift gates (models/KTGNN.py:275-280)
+        diff = x_src[c].mean(0, keepdim=True) - x_src[~c].mean(0, keepdim=True)
+        diff = diff.expand(x_src.shape)
+        cat = torch.cat((x_src, diff), dim=-1)
+        x_s2t = x_src - torch.tanh(self.a_g_s2t(cat)) * diff * c.unsqueeze(-1)
+        x_t2s = x_src + torch.tanh(self.a_g_t2s(cat)) * diff * (~c).unsqueeze(-1)
+        # f: per-domain transforms (:283-284)
+        h_t = self.lin_t(x_s2t)
+        h_s = self.lin_s(x_t2s)
+        # attention scores, softmax over destinations, weighted aggregation (:292-305) -- one kernel
+        graph = ops.cached_graph(edge_index, x_src.shape[0])
+        out = ops.gat_aggregate(h_s, h_t, self.a_f_t2s.weight, self.a_f_s2t.weight, graph, self._dst_is_src(c),
+                                self.negative_slope)
+        if self.root_weight and x_r is not None:
+            out = out + self.lin_r(x_r)
+        if self.normalize:
+            out = F.normalize(out, p=2.0, dim=-1)
+        return out
+
+    def __repr__(self):
+        return "{}({}, {})".format(self.__class__.__name__, self.in_channels, self.out_channels)
+
+
+def graph_partition(edge_index, central_mask, add_self_loop=True):
+    """models/KTGNN.py:385-398: rewrite self loops, then split edges by the domain of their destination."""
+    if add_self_loop:
+        edge_index = add_self_loops(remove_self_loops(edge_index), central_mask.shape[0])
+    m1 = central_mask[edge_index[1]]
+    e1, e2 = edge_index[:, m1], edge_index[:, ~m1]
+    return e1, e2, torch.cat((e1, e2), dim=-1)
+
+
+class _KTGNNBase(nn.Module):
+    def __init__(self, cached_edges, dropout, use_bn, need_complement):
+        super().__init__()
+        if need_complement:
+            # Adapted_complementor (models/KTGNN.py:138) is disabled in every shipped recipe
+            # (main_graph_knowledge_transfer.py:179, 332-333) and is outside the accelerated path.
+            raise NotImplementedError("need_complement=True is not part of the accelerated hot path")
+        self.cached_edges, self.dropout, self.use_bn, self.need_complement = cached_edges, dropout, use_bn, False
+        self.convs, self.bns = nn.ModuleList(), nn.ModuleList()
+        self.edge_index1 = self.edge_index2 = self.edge_index = None
+
+    graph_partition = staticmethod(graph_partition)
+
+    def _edges(self, data):
+        if not self.cached_edges:
+            return graph_partition(data.edge_index, data.central_mask)
+        if self.edge_index is None:
+            self.edge_index1, self.edge_index2, self.edge_index = graph_partition(data.edge_index, data.central_mask)
+        return self.edge_index1, self.edge_index2, self.edge_index
+
+    def _hidden(self, x, ei, ei1, ei2, c, n_convs):
+        for ind in range(n_convs):
+            x = self.convs[ind](x, ei, ei1, ei2, c)
+            if self.use_bn:
+                x = self.bns[ind](x)
+            x = F.dropout(F.relu(x), p=self.dropout, training=self.training)
+        return x
+
+
+class KTGNN_no_complement(_KTGNNBase):
+    def __init__(self, num_features, num_classes=2, layer_num=2, hidden=64, root_weight=False, dim_share=300, step=1,
+                 hidden_o=128, hidden_u=128, use_dist_loss=False, cached_edges=True, dropout=0.5, use_bn=False,
+                 need_complement=False):
+        super().__init__(cached_edges, dropout, use_bn, need_complement)
+        dim_in = dim_share
+        if layer_num == 1:
+            self.convs.append(AdaptedConv(dim_in, num_classes, root_weight=root_weight))
+        else:
+            for num in range(layer_num - 1):
+                self.convs.append(AdaptedConv(dim_in if num == 0 else hidden, hidden, root_weight=root_weight))
+                if use_bn:
+                    self.bns.append(nn.BatchNorm1d(hidden))
+        self.clf_base = AdaptedConv(hidden, num_classes, root_weight=root_weight)
+        self.clf_target = AdaptedConv(hidden, num_classes, root_weight=root_weight)
+        self.clf_transformer = nn.Sequential(nn.Linear(hidden, hidden), nn.BatchNorm1d(hidden), nn.ReLU(),
+                                             nn.Linear(hidden, hidden))
+
+    def get_emb(self, data):
+        ei1, ei2, ei = self._edges(data)
+        return self._hidden(data.x, ei, ei1, ei2, data.central_mask, len(self.convs))
+
+    def forward(self, data):
+        ei1, ei2, ei = self._edges(data)
+        c = data.central_mask
+        x = self._hidden(data.x, ei, ei1, ei2, c, len(self.convs))
+        logits_base = self.clf_base(x, ei, ei1, ei2, c)
+        logits_trans = self.clf_target(self.clf_transformer(x), ei, ei1, ei2, c)
+        logits_target = self.clf_target(x, ei, ei1, ei2, c)
+        return F.log_softmax(logits_base, 1), F.log_softmax(logits_target, 1), F.log_softmax(logits_trans, 1), None
+
+
+class KTGNN_noDTC(_KTGNNBase):
+    def __init__(self, num_features, num_classes=2, layer_num=2, hidden=64, root_weight=False, dim_share=300, step=1,
+                 hidden_o=128, hidden_u=128, use_dist_loss=False, cached_edges=True, dropout=0.5, use_bn=False,
+                 need_complement=False):
+        super().__init__(cached_edges, dropout, use_bn, need_complement)
+        dim_in = dim_share
+        if layer_num == 1:
+            self.convs.append(AdaptedConv(dim_in, num_classes, root_weight=root_weight))
+        else:
+            # the reference's loop runs range(layer_num-1), so its `num == layer_num-1` branch is never taken
+            for num in range(layer_num - 1):
+                self.convs.append(AdaptedConv(dim_in if num == 0 else hidden, hidden, root_weight=root_weight))
+                if use_bn:
+                    self.bns.append(nn.BatchNorm1d(hidden))
+
+    def get_emb(self, data):
+        ei1, ei2, ei = self._edges(data)
+        return self._hidden(data.x, ei, ei1, ei2, data.central_mask, len(self.convs) - 1)
+
+    def forward(self, data):
+        ei1, ei2, ei = self._edges(data)
+        c = data.central_mask
+        x = self._hidden(data.x, ei, ei1, ei2, c, len(self.convs) - 1)
+        x = self.convs[-1](x, ei, ei1, ei2, c)
+        return F.log_softmax(x, dim=1), None

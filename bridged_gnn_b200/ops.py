@@ -1,0 +1,251 @@
+"""Torch-facing operators over the C ABI: kNN build, CSR graphs, SpMM and the fused AdaptedConv
+aggregation (both differentiable).  Everything here runs hand-written sm_100a kernels on the current
+CUDA stream; nothing falls back to torch ops or the CPU.
+"""
+import torch
+
+from . import _lib
+from ._lib import KNN_SIMT_F32, KNN_TC_1XTF32, KNN_TC_3XTF32  # noqa: F401
+
+_ALGOS = {"simt": KNN_SIMT_F32, "tc3": KNN_TC_3XTF32, "tc1": KNN_TC_1XTF32}
+# below this many pairs the tensor-core sweep cannot fill the machine and the CUDA-core sweep is used
+_TC_MIN_PAIRS = 1 << 24
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ----------------------------------------------------------------------------------- kNN build
+def knn_cosine(q, db, k, normalize=True, apply_sigmoid=True, algo="auto"):
+    """Per-row top-k of sigmoid(cos(q_i, db_j)) without materialising the [nq, ndb] matrix.
+
+    Replaces the pair enumeration + ``Similar.similarity*`` + ``sim_mat.topk`` of the reference
+    (main_bridged_graph.py:45-67, 90-111; models/models.py:124-130, 945-948).  Selection key:
+    fp32 similarity desc, db index asc.  Returns ``(idx int64 [nq,k], val fp32 [nq,k] best first,
+    gap fp32 [nq] = v_k - v_(k+1), stats int32 [4])``; ``stats[0]`` = rows the tensor-core path
+    re-did exactly.  ``q is db`` is the within-domain case (self matches are kept).
+    """
+    lib = _lib.load()
+    q, db = _f32c(q), (_f32c(db) if db is not q else None)
+    if db is None:
+        db = q
+    nq, d = q.shape
+    ndb = db.shape[0]
+    if db.shape[1] != d:
+        raise ValueError("feature widths differ")
+    if algo == "auto":
+        algo = "tc3" if nq * ndb >= _TC_MIN_PAIRS else "simt"
+    a = _ALGOS[algo]
+    dev = q.device
+    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    val = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    gap = torch.empty((nq,), dtype=torch.float32, device=dev)
+    stats = torch.zeros((4,), dtype=torch.int32, device=dev)
+    nbytes = lib.bgnn_knn_cosine_workspace_bytes(nq, ndb, d, k, a)
+    if nbytes == 0:
+        raise ValueError("invalid kNN arguments (need 1 <= k <= min(ndb, 255))")
+    ws = _lib.workspace(nbytes, dev)
+    with _lib.call("bgnn_knn_cosine_f32", "bgnn_knn_cosine_f32[simt]" if a == KNN_SIMT_F32 else None):
+        _lib.check(lib.bgnn_knn_cosine_f32(_lib.ptr(q), nq, _lib.ptr(db), ndb, d, k, int(normalize),
+                                           int(apply_sigmoid), a, _lib.ptr(idx), _lib.ptr(val), _lib.ptr(gap),
+                                           _lib.ptr(stats), _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+    return idx, val, gap, stats
+
+
+def knn_addrelu(Uq, Udb, w2, b2, k, apply_sigmoid=True):
+    """Per-row top-k of sigmoid(sum_h w2[h] relu(Uq[i,h] + Udb[j,h]) + b2): the eval-mode fold of
+    ``Similar_v2(mode='mlp')`` (models/models.py:918-925, 949-954).  Same outputs as knn_cosine."""
+    lib = _lib.load()
+    Uq, w2 = _f32c(Uq), _f32c(w2).view(-1)
+    Udb = Uq if Udb is Uq else _f32c(Udb)
+    nq, h = Uq.shape
+    ndb = Udb.shape[0]
+    if Udb.shape[1] != h or w2.numel() != h:
+        raise ValueError("feature widths differ")
+    dev = Uq.device
+    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    val = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    gap = torch.empty((nq,), dtype=torch.float32, device=dev)
+    nbytes = lib.bgnn_knn_addrelu_workspace_bytes(nq, ndb, h, k)
+    if nbytes == 0:
+        raise ValueError("invalid kNN arguments (need 1 <= k <= min(ndb, 255))")
+    ws = _lib.workspace(nbytes, dev)
+    with _lib.call("bgnn_knn_addrelu_f32"):
+        _lib.check(lib.bgnn_knn_addrelu_f32(_lib.ptr(Uq), nq, _lib.ptr(Udb), ndb, h, _lib.ptr(w2), float(b2), k,
+                                            int(apply_sigmoid), _lib.ptr(idx), _lib.ptr(val), _lib.ptr(gap),
+                                            _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+    return idx, val, gap
+
+
+# ----------------------------------------------------------------------------------- graph format
+def edges_to_csr(src, dst, n, dedup=False, want_perm=True):
+    """(src[e], dst[e]) int64 -> destination-major CSR: rowptr int32 [n+1], col int32 [e'] (sources,
+    rows sorted by (dst, src)), perm int64 [e'] (position in the input list), e' (python int)."""
+    lib = _lib.load()
+    src, dst = src.contiguous(), dst.contiguous()
+    e = src.numel()
+    dev = src.device
+    rowptr = torch.empty((n + 1,), dtype=torch.int32, device=dev)
+    col = torch.empty((max(e, 1),), dtype=torch.int32, device=dev)
+    perm = torch.empty((max(e, 1),), dtype=torch.int64, device=dev) if want_perm else None
+    e_out = torch.zeros((1,), dtype=torch.int64, device=dev)
+    ws = _lib.workspace(lib.bgnn_edges_to_csr_workspace_bytes(e), dev)
+    with _lib.call("bgnn_edges_to_csr"):
+        _lib.check(lib.bgnn_edges_to_csr(_lib.ptr(src, torch.int64) if e else None,
+                                         _lib.ptr(dst, torch.int64) if e else None, e, n, int(dedup), _lib.ptr(rowptr),
+                                         _lib.ptr(col), _lib.ptr(perm, allow_none=True), _lib.ptr(e_out), _lib.ptr(ws),
+                                         ws.numel(), _lib.stream(dev)))
+    ne = int(e_out.item()) if dedup else e
+    return rowptr, col[:ne], (perm[:ne] if want_perm else None), ne
+
+
+def coalesce(edge_index, num_nodes=None):
+    """torch_geometric.utils.coalesce (main_bridged_graph.py:75, 113): sort by (row, col), drop duplicates."""
+    if edge_index.numel() == 0:
+        return edge_index
+    n = int(edge_index.max().item()) + 1 if num_nodes is None else num_nodes
+    rowptr, col, _, _ = edges_to_csr(edge_index[1], edge_index[0], n, dedup=True, want_perm=False)
+    counts = (rowptr[1:] - rowptr[:-1]).to(torch.int64)
+    row = torch.repeat_interleave(torch.arange(n, device=edge_index.device), counts)
+    return torch.stack((row, col.to(torch.int64)), 0)
+
+
+class CSRGraph:
+    """Destination-major CSR of an edge list plus, lazily, the CSR of the transposed graph (needed by
+    the backward passes).  Built once per graph and cached by the layers, where the reference rebuilds
+    a SparseTensor on every forward (models/backbones.py:464)."""
+
+    def __init__(self, edge_index, num_nodes):
+        self.n = int(num_nodes)
+        self.edge_index = edge_index
+        self.rowptr, self.col, self.perm, self.e = edges_to_csr(edge_index[0], edge_index[1], self.n)
+        self._t = None
+        self._deg = None
+
+    @property
+    def t(self):
+        if self._t is None:
+            self._t = edges_to_csr(self.edge_index[1], self.edge_index[0], self.n)[:3]
+        return self._t
+
+    @property
+    def deg(self):
+        if self._deg is None:
+            self._deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.float32)
+        return self._deg
+
+
+_graph_cache = {}
+
+
+def cached_graph(edge_index, num_nodes):
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device))
+    g = _graph_cache.get(key)
+    if g is None:
+        if len(_graph_cache) >= 4:      # a handful of live graphs; each entry pins its edge list and two CSRs
+            _graph_cache.pop(next(iter(_graph_cache)))
+        g = CSRGraph(edge_index, num_nodes)
+        _graph_cache[key] = g
+    return g
+
+
+# ----------------------------------------------------------------------------------- SpMM
+def _spmm_raw(rowptr, col, X, n_rows, reduce_mean=False, edge_w=None, gather_scale=None, out_scale=None):
+    lib = _lib.load()
+    X = X.contiguous()
+    f = X.shape[1]
+    Y = torch.empty((n_rows, f), dtype=torch.float32, device=X.device)
+    f32 = torch.float32
+    with _lib.call("bgnn_spmm_csr_f32"):
+        _lib.check(lib.bgnn_spmm_csr_f32(_lib.ptr(rowptr, torch.int32), _lib.ptr(col, torch.int32),
+                                         _lib.ptr(edge_w, f32, True), _lib.ptr(gather_scale, f32, True),
+                                         _lib.ptr(out_scale, f32, True), _lib.ptr(X, f32), n_rows, f, int(reduce_mean),
+                                         _lib.ptr(Y), _lib.stream(X.device)))
+    return Y
+
+
+class _SpmmFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, graph, reduce, edge_weight, gather_scale, out_scale):
+        ctx.graph, ctx.reduce, ctx.edge_weight = graph, reduce, edge_weight
+        ctx.gather_scale, ctx.out_scale = gather_scale, out_scale
+        ew = None if edge_weight is None else edge_weight[graph.perm].contiguous()
+        return _spmm_raw(graph.rowptr, graph.col, X.to(torch.float32), graph.n, reduce == "mean", ew, gather_scale,
+                         out_scale)
+
+    @staticmethod
+    def backward(ctx, gY):
+        # dX[j] = gather_scale[j] * sum_{i : j->i} w_ji * out_scale[i] * (1/deg_i) * dY[i]: the same kernel on
+        # the transposed CSR with the per-row factors moved to the gather side.
+        g = ctx.graph
+        t_rowptr, t_col, t_perm = g.t
+        ew = None if ctx.edge_weight is None else ctx.edge_weight[t_perm].contiguous()
+        gs = ctx.out_scale
+        if ctx.reduce == "mean":
+            inv = 1.0 / g.deg.clamp(min=1.0)
+            gs = inv if gs is None else gs * inv
+        gX = _spmm_raw(t_rowptr, t_col, gY.to(torch.float32).contiguous(), g.n, False, ew,
+                       None if gs is None else gs.contiguous(), ctx.gather_scale)
+        return gX, None, None, None, None, None
+
+
+def spmm(graph, X, reduce="sum", edge_weight=None, gather_scale=None, out_scale=None):
+    """Y[i] = out_scale[i] * reduce_{j->i} w_ji * gather_scale[j] * X[j] over a CSRGraph.  Replaces
+    torch_sparse.matmul(adj_t, x, reduce) (models/backbones.py:464-468) and the gather/scatter of
+    SAGEConv / GCNConv; differentiable in X.  ``edge_weight`` is given in the order of the graph's
+    original edge list; the scales are per node."""
+    return _SpmmFn.apply(X, graph, reduce, edge_weight, gather_scale, out_scale)
+
+
+# ----------------------------------------------------------------------------------- fused AdaptedConv aggregation
+class _GatAggFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope):
+        lib = _lib.load()
+        f32 = torch.float32
+        Hs, Ht = Hs.to(f32).contiguous(), Ht.to(f32).contiguous()
+        a1, a2 = af_t2s.to(f32).contiguous().view(-1), af_s2t.to(f32).contiguous().view(-1)
+        n, c = Hs.shape
+        dev = Hs.device
+        out = torch.empty((n, c), dtype=f32, device=dev)
+        row_max = torch.empty((n,), dtype=f32, device=dev)
+        row_sum = torch.empty((n,), dtype=f32, device=dev)
+        with _lib.call("bgnn_gatv2_fwd_f32", "bgnn_gatv2_fwd_f32[c=%d]" % c):
+            _lib.check(lib.bgnn_gatv2_fwd_f32(_lib.ptr(graph.rowptr), _lib.ptr(graph.col),
+                                              _lib.ptr(dst_is_src, torch.uint8), _lib.ptr(Hs), _lib.ptr(Ht),
+                                              _lib.ptr(a1), _lib.ptr(a2), float(slope), n, c, _lib.ptr(out),
+                                              _lib.ptr(row_max), _lib.ptr(row_sum), _lib.stream(dev)))
+        ctx.save_for_backward(Hs, Ht, a1, a2, out, row_max, row_sum)
+        ctx.graph, ctx.dst_is_src, ctx.slope = graph, dst_is_src, float(slope)
+        ctx.a_shapes = (af_t2s.shape, af_s2t.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        Hs, Ht, a1, a2, out, row_max, row_sum = ctx.saved_tensors
+        g = ctx.graph
+        t_rowptr, t_col, _ = g.t
+        n, c = Hs.shape
+        dev = Hs.device
+        gout = gout.to(torch.float32).contiguous()
+        gHs, gHt = torch.empty_like(Hs), torch.empty_like(Ht)
+        ga1, ga2 = torch.empty_like(a1), torch.empty_like(a2)
+        ws = _lib.workspace(lib.bgnn_gatv2_bwd_workspace_bytes(n, c), dev)
+        with _lib.call("bgnn_gatv2_bwd_f32", "bgnn_gatv2_bwd_f32[c=%d]" % c):
+            _lib.check(lib.bgnn_gatv2_bwd_f32(_lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(t_rowptr), _lib.ptr(t_col),
+                                              _lib.ptr(ctx.dst_is_src), _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(a1),
+                                              _lib.ptr(a2), ctx.slope, n, c, _lib.ptr(out), _lib.ptr(row_max),
+                                              _lib.ptr(row_sum), _lib.ptr(gout), _lib.ptr(gHs), _lib.ptr(gHt),
+                                              _lib.ptr(ga1), _lib.ptr(ga2), _lib.ptr(ws), ws.numel(),
+                                              _lib.stream(dev)))
+        return gHs, gHt, ga1.view(ctx.a_shapes[0]), ga2.view(ctx.a_shapes[1]), None, None, None
+
+
+def gat_aggregate(Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope=0.1):
+    """Edge part of AdaptedConv (models/KTGNN.py:292-305 + message :317-319) as one fused kernel per
+    direction of autograd: scores a.leaky_relu(H[src]+H[dst]), softmax over each destination's incoming
+    edges (PyG softmax, +1e-16), weighted sum of H[src]; (H, a) = (Hs, af_t2s) for destinations in the
+    source domain, (Ht, af_s2t) otherwise.  dst_is_src: uint8 [n]."""
+    return _GatAggFn.apply(Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope)

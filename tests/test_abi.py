@@ -1,0 +1,84 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/bgnn_b200.h declares, and the host-side argument validation that needs no GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from bridged_gnn_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build(verbose=False)
+    return _lib.load()
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "bgnn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bgnn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = _declared()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_ctypes_signatures_cover_header(lib):
+    from bridged_gnn_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+
+
+def test_version_and_error_strings(lib):
+    assert lib.bgnn_version() >= 100
+    assert lib.bgnn_error_string(0) == b"ok"
+    assert b"invalid" in lib.bgnn_error_string(-1)
+    assert b"workspace" in lib.bgnn_error_string(-2)
+
+
+def test_workspace_queries_are_host_only(lib):
+    # pure host arithmetic: callable without a GPU
+    assert lib.bgnn_knn_cosine_workspace_bytes(591, 2817, 128, 20, 0) > 0
+    assert lib.bgnn_knn_cosine_workspace_bytes(262144, 786432, 128, 20, 1) > 262144 * 128 * 4
+    assert lib.bgnn_knn_cosine_workspace_bytes(10, 5, 16, 6, 0) == 0      # k > ndb
+    assert lib.bgnn_knn_addrelu_workspace_bytes(591, 2817, 128, 20) > 0
+    assert lib.bgnn_edges_to_csr_workspace_bytes(37522) > 37522 * 8
+    assert lib.bgnn_gatv2_bwd_workspace_bytes(3408, 64) > 0
+
+
+def test_invalid_arguments_rejected_before_any_launch(lib):
+    null = ctypes.c_void_p(None)
+    # NULL inputs / k > ndb -> BGNN_ERR_INVALID_ARG (-1) without touching the device
+    assert lib.bgnn_knn_cosine_f32(null, 4, null, 4, 8, 2, 1, 1, 0, null, null, null, null, null, 0, null) == -1
+    assert lib.bgnn_knn_addrelu_f32(null, 4, null, 4, 8, null, 0.0, 9, 1, null, null, null, null, 0, null) == -1
+    assert lib.bgnn_gatv2_fwd_f32(null, null, null, null, null, null, null, 0.1, 5, 0, null, null, null, null) == -1
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "bridged_gnn_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from bridged_gnn_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_cpu_tensors_rejected():
+    import torch
+    from bridged_gnn_b200 import _lib
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        _lib.ptr(torch.zeros(4))

@@ -1,0 +1,281 @@
+"""GPU parity of message passing over the bridged graph (CSR build, SpMM, fused AdaptedConv
+aggregation, KT-GNN / SAGE / GCN models) against the oracle and the reference-generated golden
+vectors.  Integer outputs are bit-exact; fp32 features, logits and gradients within 1e-5 relative."""
+import pytest
+import torch
+
+from conftest import sub_state
+from oracle import build_oracle as bo
+from oracle import mp_oracle as mo
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+RTOL = 1e-5
+
+
+def relclose(a, b, tol=RTOL):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    return float((a - b).abs().max()) <= tol * float(b.abs().max()) + 1e-7
+
+
+def _ops():
+    from bridged_gnn_b200 import ops
+    return ops
+
+
+def _rand_graph(n, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, n, (2, e), generator=g)
+
+
+# ------------------------------------------------------------------ CSR build / coalesce (bit-exact)
+@pytest.mark.parametrize("n,e", [(1, 0), (10, 0), (7, 30), (1000, 20000), (3408, 37522), (100000, 1 << 20)])
+def test_edges_to_csr_exact(n, e):
+    ops = _ops()
+    ei = _rand_graph(n, e, 1)
+    rowptr, col, perm, ne = ops.edges_to_csr(ei[0].cuda(), ei[1].cuda(), n)
+    assert ne == e
+    key = ei[1] * n + ei[0]
+    _, order = torch.sort(key, stable=True)
+    assert torch.equal(col.cpu().long(), ei[0][order])
+    cnt = torch.bincount(ei[1], minlength=n)
+    assert torch.equal(rowptr.cpu().long(), torch.cat((torch.zeros(1, dtype=torch.long), cnt.cumsum(0))))
+    # perm maps CSR slots back to input edges (ties between duplicate edges may be permuted)
+    p = perm.cpu()
+    assert torch.equal(ei[0][p], ei[0][order]) and torch.equal(ei[1][p], ei[1][order])
+    assert sorted(p.tolist()) == list(range(e)) if e < 50000 else p.unique().numel() == e
+
+
+@pytest.mark.parametrize("n,e", [(5, 40), (300, 5000), (3408, 60000)])
+def test_coalesce_matches_pyg_semantics(n, e):
+    ops = _ops()
+    ei = _rand_graph(n, e, 2)
+    out = ops.coalesce(ei.cuda(), n).cpu()
+    assert torch.equal(out, bo.coalesce(ei, n))
+    from bridged_gnn_b200.data import to_undirected
+    assert torch.equal(to_undirected(ei.cuda(), n).cpu(), mo.to_undirected(ei, n))
+
+
+def test_office_undirected_and_partition(office_build, office_mp):
+    from bridged_gnn_b200.data import to_undirected
+    from bridged_gnn_b200.models import graph_partition
+    ei = to_undirected(T(office_build["edge_index"]).cuda(), 3408)
+    assert torch.equal(ei.cpu(), T(office_mp["edge_index_undirected"]))
+    e1, e2, e = graph_partition(ei, T(office_build["central_mask"]).cuda())
+    assert torch.equal(e1.cpu(), T(office_mp["ktgnn.ei1"])) and torch.equal(e2.cpu(), T(office_mp["ktgnn.ei2"]))
+
+
+# ------------------------------------------------------------------ SpMM
+@pytest.mark.parametrize("f", [1, 2, 31, 64, 100, 128, 256, 300, 512, 1685])
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+def test_spmm_forward_backward_random(f, reduce):
+    ops = _ops()
+    n, e = 500, 6000
+    ei = _rand_graph(n, e, 3)
+    ei[1, ei[1] == 7] = 8                       # node 7 has no incoming edge (empty row)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(n, f, generator=g)
+    w = torch.rand(e, generator=g) if reduce == "sum" else None
+    xr = x.clone().requires_grad_(True)
+    y_ref = mo.spmm(ei, xr, n, reduce, w)
+    gout = torch.randn(n, f, generator=g)
+    (y_ref * gout).sum().backward()
+    graph = ops.CSRGraph(ei.cuda(), n)
+    xg = x.cuda().requires_grad_(True)
+    y = ops.spmm(graph, xg, reduce, None if w is None else w.cuda())
+    assert relclose(y, y_ref)
+    assert bool((y[7] == 0).all())
+    (y * gout.cuda()).sum().backward()
+    assert relclose(xg.grad, xr.grad)
+
+
+def test_spmm_scales_equal_edge_weights():
+    """gather_scale / out_scale factorisation used by GCNConv == explicit per-edge weights."""
+    ops = _ops()
+    n, e, f = 400, 5000, 64
+    ei = _rand_graph(n, e, 5)
+    x = torch.randn(n, f)
+    a, b = torch.rand(n) + 0.5, torch.rand(n) + 0.5
+    graph = ops.CSRGraph(ei.cuda(), n)
+    y1 = ops.spmm(graph, x.cuda(), "sum", None, a.cuda(), b.cuda())
+    y2 = mo.spmm(ei, x, n, "sum", a[ei[0]] * b[ei[1]])
+    assert relclose(y1, y2)
+
+
+# ------------------------------------------------------------------ fused AdaptedConv aggregation
+def _agg_inputs(n, c, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    ei = _rand_graph(n, e, seed)
+    cm = torch.zeros(n, dtype=torch.bool)
+    cm[: (2 * n) // 3] = True
+    e1, e2, eall = mo.graph_partition(ei, cm)
+    Hs, Ht = torch.randn(n, c, generator=g), torch.randn(n, c, generator=g)
+    a1, a2 = torch.randn(c, generator=g) * 0.5, torch.randn(c, generator=g) * 0.5
+    gout = torch.randn(n, c, generator=g)
+    return eall, e1, e2, cm, Hs, Ht, a1, a2, gout
+
+
+@pytest.mark.parametrize("n,c,e", [(50, 1, 300), (300, 2, 3000), (1000, 31, 12000), (1000, 64, 12000), (700, 100, 5000),
+                                   (513, 128, 9000), (400, 256, 4000), (200, 300, 2000), (150, 512, 1500)])
+def test_gat_aggregate_forward_backward_random(n, c, e):
+    ops = _ops()
+    eall, e1, e2, cm, Hs, Ht, a1, a2, gout = _agg_inputs(n, c, e, 20 + c)
+    leaf = [t.clone().requires_grad_(True) for t in (Hs, Ht, a1, a2)]
+    y_ref = mo.adapted_conv_aggregate(leaf[0], leaf[1], e1, e2, cm, leaf[2], leaf[3])
+    (y_ref * gout).sum().backward()
+    graph = ops.CSRGraph(eall.cuda(), n)
+    dl = [t.clone().cuda().requires_grad_(True) for t in (Hs, Ht, a1, a2)]
+    y = ops.gat_aggregate(dl[0], dl[1], dl[2], dl[3], graph, cm.to(torch.uint8).cuda(), 0.1)
+    assert relclose(y, y_ref)
+    (y * gout.cuda()).sum().backward()
+    for got, ref, name in zip(dl, leaf, ("Hs", "Ht", "a_t2s", "a_s2t")):
+        assert relclose(got.grad, ref.grad, 2e-5), name
+
+
+def test_gat_aggregate_unsupported_width_fails_loudly():
+    ops = _ops()
+    eall, e1, e2, cm, Hs, Ht, a1, a2, gout = _agg_inputs(40, 1000, 200, 9)
+    graph = ops.CSRGraph(eall.cuda(), 40)
+    with pytest.raises(RuntimeError, match="unsupported"):
+        ops.gat_aggregate(Hs.cuda(), Ht.cuda(), a1.cuda(), a2.cuda(), graph, cm.to(torch.uint8).cuda(), 0.1)
+
+
+def test_gat_aggregate_single_edge_rows_and_large_scores():
+    """Rows whose only edge is the self loop give out = H[i]; huge scores must not overflow the softmax."""
+    ops = _ops()
+    n, c = 64, 32
+    cm = torch.zeros(n, dtype=torch.bool)
+    cm[:40] = True
+    e1, e2, eall = mo.graph_partition(torch.zeros((2, 0), dtype=torch.long), cm)
+    H = torch.randn(n, c) * 50
+    a = torch.randn(c) * 5
+    graph = ops.CSRGraph(eall.cuda(), n)
+    y = ops.gat_aggregate(H.cuda(), H.cuda() * 2, a.cuda(), a.cuda(), graph, cm.to(torch.uint8).cuda(), 0.1)
+    assert torch.allclose(y[:40].cpu(), H[:40], rtol=1e-6, atol=0)
+    assert torch.allclose(y[40:].cpu(), 2 * H[40:], rtol=1e-6, atol=0)
+    assert bool(torch.isfinite(y).all())
+
+
+# ------------------------------------------------------------------ golden: reference layers on the office bridged graph
+def test_adapted_conv_module_matches_reference(office_mp, office_build):
+    from bridged_gnn_b200.models import AdaptedConv
+    m = office_mp
+    conv = AdaptedConv(64, 31, root_weight=False)
+    conv.load_state_dict(sub_state(m, "conv.sd."))
+    conv.cuda()
+    c = T(office_build["central_mask"]).cuda()
+    e1, e2 = T(m["ktgnn.ei1"]).cuda(), T(m["ktgnn.ei2"]).cuda()
+    x = T(m["conv.x"]).cuda().requires_grad_(True)
+    y = conv(x, torch.cat((e1, e2), 1), e1, e2, c)
+    assert relclose(y, T(m["conv.y"]))
+    (y * T(m["conv.gout"]).cuda()).sum().backward()
+    assert relclose(x.grad, T(m["conv.gx"]), 2e-5)
+    for k, p in conv.named_parameters():
+        assert relclose(p.grad, T(m["conv.grad." + k]), 2e-5), k
+
+
+def _office_data(office_build, office_mp):
+    from bridged_gnn_b200.data import Data
+    return Data(x=T(office_build["x"]), edge_index=T(office_mp["edge_index_undirected"]), y=T(office_build["y"]),
+                central_mask=T(office_build["central_mask"]), train_mask=T(office_build["train_mask"])).to("cuda:0")
+
+
+def test_ktgnn_model_eval_and_train_match_reference(office_mp, office_build):
+    """Config 2: KT-GNN 2-layer hidden=64 on the office A->D bridged graph, to_undirected."""
+    from bridged_gnn_b200.models import KTGNN_no_complement
+    m = office_mp
+    data = _office_data(office_build, office_mp)
+    model = KTGNN_no_complement(256, 31, 2, 64, root_weight=False, use_bn=True, dim_share=256, need_complement=False)
+    model.load_state_dict(sub_state(m, "ktgnn.sd."))
+    model.cuda().eval()
+    with torch.no_grad():
+        lb, lt, ltt, _ = model(data)
+    assert relclose(lb, T(m["ktgnn.eval.logp_base"]))
+    assert relclose(lt, T(m["ktgnn.eval.logp_target"]))
+    assert relclose(ltt, T(m["ktgnn.eval.logp_trans"]))
+    assert model.edge_index1.shape[1] == 25055 and model.edge_index2.shape[1] == 12467
+    model.train()
+    model.dropout = 0.0
+    model.zero_grad()
+    lb, lt, ltt, _ = model(data)
+    tm = data.train_mask
+    nll = torch.nn.functional.nll_loss
+    loss = nll(lb[tm], data.y[tm]) + nll(lt[tm], data.y[tm]) + nll(ltt[tm], data.y[tm])
+    assert abs(loss.item() - float(m["ktgnn.train.loss"])) < 1e-5 * max(1.0, abs(float(m["ktgnn.train.loss"])))
+    loss.backward()
+    for k, p in model.named_parameters():
+        assert relclose(p.grad, T(m["ktgnn.train.grad." + k]), 5e-5), k
+
+
+def test_sage_gcn_models_match_reference(office_mp, office_build):
+    import types
+    from bridged_gnn_b200.models import GCNNet, GraphSAGE
+    from bridged_gnn_b200.models.models import GraphEncoder
+    m = office_mp
+    data = _office_data(office_build, office_mp)
+    ds = types.SimpleNamespace(num_features=256, num_classes=31)
+    sage = GraphSAGE(ds, layer_num=2, hidden=64)
+    sage.load_state_dict(sub_state(m, "sage.sd."))
+    gcn = GCNNet(ds, layer_num=2, hidden=64)
+    gcn.load_state_dict(sub_state(m, "gcn.sd."))
+    enc = GraphEncoder(256, 64, dim_hidden=64, layer_num=2, norm_mode="None")
+    enc.load_state_dict(sub_state(m, "enc.sd."))
+    with torch.no_grad():
+        assert relclose(sage.cuda().eval()(data), T(m["sage.logp"]))
+        assert relclose(gcn.cuda().eval()(data), T(m["gcn.logp"]))
+        assert relclose(enc.cuda().eval()(data.x, data.edge_index), T(m["enc.z"]))
+
+
+def test_sage_backward_matches_oracle(office_mp, office_build):
+    import types
+    from bridged_gnn_b200.models import GraphSAGE
+    m = office_mp
+    data = _office_data(office_build, office_mp)
+    ds = types.SimpleNamespace(num_features=256, num_classes=31)
+    sage = GraphSAGE(ds, layer_num=2, hidden=64)
+    sd = sub_state(m, "sage.sd.")
+    sage.load_state_dict(sd)
+    sage.cuda().train()
+    for mod in sage.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x, ei = T(office_build["x"]), T(m["edge_index_undirected"])
+    # oracle in train mode without dropout == eval graph
+    lp_ref = mo.graphsage(x, ei, P)
+    tm, y = T(office_build["train_mask"]), T(office_build["y"])
+    torch.nn.functional.nll_loss(lp_ref[tm], y[tm]).backward()
+    sage.eval()      # dropout off; no BN in GraphSAGE, so eval == train numerically
+    lp = sage(data)
+    torch.nn.functional.nll_loss(lp[data.train_mask], data.y[data.train_mask]).backward()
+    for k, p in sage.named_parameters():
+        assert relclose(p.grad, P[k].grad, 2e-5), k
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_large_graph_properties():
+    """Config-4-sized aggregation (2^20 nodes, ~1.6e7 edges): constant features must aggregate to the
+    constant (softmax weights sum to one; mean of ones is one), and SpMM is linear."""
+    ops = _ops()
+    n, c = 1 << 20, 64
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(0)
+    ei = torch.randint(0, n, (2, 15 * n), generator=g, device=dev)
+    loops = torch.arange(n, device=dev).unsqueeze(0).repeat(2, 1)
+    ei = torch.cat((ei, loops), 1)
+    graph = ops.CSRGraph(ei, n)
+    rp = graph.rowptr.long()
+    assert int(rp[-1]) == ei.shape[1] and bool((rp[1:] >= rp[:-1]).all())
+    assert torch.equal(torch.bincount(ei[1], minlength=n), rp[1:] - rp[:-1])
+    cm = (torch.arange(n, device=dev) % 4 != 0)
+    ones = torch.ones(n, c, device=dev)
+    a = torch.randn(c, generator=g, device=dev)
+    y = ops.gat_aggregate(ones * 0.5, ones * 2.0, a, -a, graph, cm.to(torch.uint8), 0.1)
+    assert torch.allclose(y[cm], ones[cm] * 0.5, rtol=2e-6) and torch.allclose(y[~cm], ones[~cm] * 2.0, rtol=2e-6)
+    x1, x2 = torch.randn(n, c, generator=g, device=dev), torch.randn(n, c, generator=g, device=dev)
+    lhs = ops.spmm(graph, x1 + 2 * x2, "mean")
+    rhs = ops.spmm(graph, x1, "mean") + 2 * ops.spmm(graph, x2, "mean")
+    assert float((lhs - rhs).abs().max()) < 1e-4
+    assert torch.allclose(ops.spmm(graph, ones, "mean"), ones, rtol=1e-6)
+    deg = ops.spmm(graph, ones[:, :1].contiguous(), "sum").view(-1)
+    assert torch.equal(deg.long(), rp[1:] - rp[:-1])

@@ -306,11 +306,14 @@ def run_ours(args):
     calls, tot = knn_calls.get("bgnn_knn_cosine_f32", (1, 0.0))
     knn_call_ms = tot / max(calls, 1)
     flops = 2.0 * NT * NS * DIM
-    tf32_peak = peaks["bf16_tflops"] / 2.0
-    knn_roof = {"bound": "tensor", "achieved": flops / (knn_call_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": flops / (knn_call_ms * 1e-3) / 1e12 / tf32_peak, "traffic": None,
-                "kernel": "knn_cosine_tc_kernel (timed: whole bgnn_knn_cosine_f32 call incl. prologue/merge)",
-                "peak_source": peaks["source"] + " bf16 dense / 2 (tcgen05 kind::tf32 runs at half the bf16 rate)",
+    half_rate = args.knn_algo in ("tc3", "tc1")
+    tc_peak = peaks["bf16_tflops"] / (2.0 if half_rate else 1.0)
+    knn_roof = {"bound": "tensor", "achieved": flops / (knn_call_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
+                "frac": flops / (knn_call_ms * 1e-3) / 1e12 / tc_peak, "traffic": None,
+                "kernel": ("knn_cosine_tc_kernel" if half_rate else "knn_cosine_f16_kernel")
+                + " (timed: whole bgnn_knn_cosine_f32 call incl. prologue, merge/re-score and exact fallback)",
+                "peak_source": peaks["source"] + (" bf16 dense / 2 (tcgen05 kind::tf32 runs at half the 16-bit rate)"
+                                                  if half_rate else " dense bf16 == fp16 rate of tcgen05 kind::f16"),
                 "algorithmic_flops_per_launch": flops}
 
     # ---- phase B: message passing over the bridged graph ------------------------------------------------
@@ -426,7 +429,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--knn-algo", dest="knn_algo", default="tc3", choices=["tc3", "tc1", "simt"])
+    ap.add_argument("--knn-algo", dest="knn_algo", default="f16", choices=["f16", "tc3", "tc1", "simt"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

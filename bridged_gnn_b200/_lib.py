@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libbgnn_b200.so")
 KNN_SIMT_F32 = 0
 KNN_TC_3XTF32 = 1
 KNN_TC_1XTF32 = 2
+KNN_TC_F16 = 3
 
 _c = ctypes
 _vp, _i64, _i32, _f32, _sz = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float, _c.c_size_t

@@ -30,8 +30,10 @@ static SimtPlan simt_plan(int nq, int ndb, int k, bool max_parallel) {
 
 struct KnnPlan {
   int algo;        // resolved algorithm
-  int passes;      // tensor-core passes (3 or 1), 0 for the CUDA-core sweep
-  int ld;          // row stride of the normalised planes
+  int passes;      // tf32 tensor-core passes (3 or 1), 0 otherwise
+  bool f16;        // single-pass fp16 tensor-core sweep
+  int ld;          // row stride of the normalised fp32 planes
+  int ldh;         // row stride of the fp16 plane (f16 sweep)
   TcPlan tc;
   SimtPlan simt;   // main sweep (SIMT algo) or exact fallback (tensor-core algos)
   size_t cand_elems;
@@ -46,14 +48,22 @@ static KnnPlan knn_plan(int64_t nq, int64_t ndb, int d, int k, int algo) {
   p.algo = algo;
   p.passes = (algo == BGNN_KNN_TC_3XTF32) ? 3 : (algo == BGNN_KNN_TC_1XTF32 ? 1 : 0);
   p.tc.bn = 0;
-  if (p.passes) {
+  p.f16 = false;
+  p.ldh = 0;
+  if (algo == BGNN_KNN_TC_F16) {
+    p.tc = tc_plan_f16((int)nq, (int)ndb, d, k);
+    p.f16 = p.tc.bn != 0;
+    if (!p.f16) p.algo = BGNN_KNN_SIMT_F32;                           // d or k too large for the on-chip budget
+  } else if (p.passes) {
     p.tc = tc_plan((int)nq, (int)ndb, d, k, p.passes);
     if (p.tc.bn == 0) { p.passes = 0; p.algo = BGNN_KNN_SIMT_F32; }   // k too large for the on-chip lists
   }
-  p.ld = p.passes ? (d + 31) / 32 * 32 : d;
-  p.simt = simt_plan((int)nq, (int)ndb, k, /*max_parallel=*/p.passes != 0);
+  p.ld = p.passes ? (d + 31) / 32 * 32 : (p.f16 ? (d + 3) / 4 * 4 : d);
+  if (p.f16) p.ldh = (d + 63) / 64 * 64;
+  const bool tcpath = p.passes != 0 || p.f16;
+  p.simt = simt_plan((int)nq, (int)ndb, k, /*max_parallel=*/tcpath);
   size_t simt_c = (size_t)p.simt.nsplit * nq * p.simt.kc;
-  size_t tc_c = p.passes ? (size_t)p.tc.nlists * nq * p.tc.kc : 0;
+  size_t tc_c = tcpath ? (size_t)p.tc.nlists * nq * p.tc.kc : 0;
   p.cand_elems = simt_c > tc_c ? simt_c : tc_c;
   return p;
 }
@@ -63,6 +73,7 @@ static size_t knn_ws_bytes(const KnnPlan& p, int64_t nq, int64_t ndb) {
   auto add = [&](size_t n) { b = align_up(b, 256) + n; };
   const int planes = p.passes ? 2 : 1;
   for (int i = 0; i < planes; ++i) { add((size_t)nq * p.ld * 4); add((size_t)ndb * p.ld * 4); }
+  if (p.f16) { add((size_t)nq * p.ldh * 2); add((size_t)ndb * p.ldh * 2); }
   add(p.cand_elems * 4);
   add(p.cand_elems * 4);
   add((size_t)nq * 4);   // fallback row list
@@ -99,7 +110,7 @@ int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb
                         int32_t* out_stats, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!knn_args_ok(nq, ndb, d, k) || !q || !db || !out_idx || !out_val) return BGNN_ERR_INVALID_ARG;
-  if (algo < BGNN_KNN_SIMT_F32 || algo > BGNN_KNN_TC_1XTF32) return BGNN_ERR_INVALID_ARG;
+  if (algo < BGNN_KNN_SIMT_F32 || algo > BGNN_KNN_TC_F16) return BGNN_ERR_INVALID_ARG;
   if (nq == 0) return BGNN_OK;
   const KnnPlan p = knn_plan(nq, ndb, d, k, algo);
   if (workspace_bytes < knn_ws_bytes(p, nq, ndb) || !workspace) return BGNN_ERR_WORKSPACE;
@@ -109,18 +120,26 @@ int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb
   float* dhi = w.take<float>((size_t)ndb * p.ld);
   float *qlo = nullptr, *dlo = nullptr;
   if (p.passes) { qlo = w.take<float>((size_t)nq * p.ld); dlo = w.take<float>((size_t)ndb * p.ld); }
+  unsigned short *qh = nullptr, *dh = nullptr;
+  if (p.f16) { qh = w.take<unsigned short>((size_t)nq * p.ldh); dh = w.take<unsigned short>((size_t)ndb * p.ldh); }
   float* cand_val = w.take<float>(p.cand_elems);
   int* cand_idx = w.take<int>(p.cand_elems);
   int* fb_rows = w.take<int>((size_t)nq);
   int* fb_count = w.take<int>(64);
   if (!w.ok()) return BGNN_ERR_WORKSPACE;
   int rc;
-  // prologue: unit rows (and the tf32 hi/lo split for the tensor-core sweep)
-  if ((rc = launch_normalize_split(db, ndb, d, p.ld, normalize, dhi, dlo, stream)) != BGNN_OK) return rc;
-  if (same) { qhi = dhi; qlo = dlo; }
-  else if ((rc = launch_normalize_split(q, nq, d, p.ld, normalize, qhi, qlo, stream)) != BGNN_OK) return rc;
+  // prologue: unit rows (plus the tf32 hi/lo split or the fp16 rounding for the tensor-core sweeps)
+  if (p.f16) {
+    if ((rc = launch_normalize_f16(db, ndb, d, p.ld, p.ldh, normalize, dhi, dh, stream)) != BGNN_OK) return rc;
+    if (same) { qhi = dhi; qh = dh; }
+    else if ((rc = launch_normalize_f16(q, nq, d, p.ld, p.ldh, normalize, qhi, qh, stream)) != BGNN_OK) return rc;
+  } else {
+    if ((rc = launch_normalize_split(db, ndb, d, p.ld, normalize, dhi, dlo, stream)) != BGNN_OK) return rc;
+    if (same) { qhi = dhi; qlo = dlo; }
+    else if ((rc = launch_normalize_split(q, nq, d, p.ld, normalize, qhi, qlo, stream)) != BGNN_OK) return rc;
+  }
 
-  if (!p.passes) {
+  if (!p.passes && !p.f16) {
     rc = launch_knn_simt(BGNN_PAIR_DOT, qhi, nullptr, (int)nq, dhi, nullptr, (int)ndb, d, p.ld, nullptr, 0.f,
                          apply_sigmoid, p.simt.kc, p.simt.nsplit, p.simt.per_split, nullptr, nullptr, cand_val,
                          cand_idx, stream);
@@ -136,10 +155,11 @@ int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb
   // tensor-core sweep nominates, merge re-scores + certifies, CUDA-core sweep redoes uncertified rows
   set_int_kernel<<<1, 1, 0, stream>>>(fb_count, 0);
   BGNN_LAUNCH_CHECK();
-  rc = launch_knn_cosine_tc(qhi, qlo, (int)nq, dhi, dlo, (int)ndb, p.ld, p.passes, p.tc, cand_val, cand_idx, stream);
+  if (p.f16) rc = launch_knn_cosine_f16(qh, (int)nq, dh, (int)ndb, p.ldh, p.tc, cand_val, cand_idx, stream);
+  else rc = launch_knn_cosine_tc(qhi, qlo, (int)nq, dhi, dlo, (int)ndb, p.ld, p.passes, p.tc, cand_val, cand_idx, stream);
   if (rc != BGNN_OK) return rc;
   // error bound of the approximate dot product of two unit rows (see DESIGN.md "kNN exactness")
-  const float delta = (p.passes == 3) ? 3.0e-5f : 2.0e-3f;
+  const float delta = p.f16 ? (9.7657e-4f + 5.97e-8f * sqrtf((float)d) + 4.0e-6f) : ((p.passes == 3) ? 3.0e-5f : 2.0e-3f);
   rc = launch_knn_merge(cand_val, cand_idx, p.tc.nlists, p.tc.kc, (int)nq, k, 1, qhi, qlo, dhi, dlo, p.ld, p.ld,
                         apply_sigmoid, delta, nullptr, nullptr, (long long*)out_idx, out_val, out_gap, fb_rows,
                         fb_count, stream);

@@ -34,6 +34,13 @@ TcPlan tc_plan(int nq, int ndb, int d, int k, int passes);
 int launch_knn_cosine_tc(const float* qhi, const float* qlo, int nq, const float* dhi, const float* dlo, int ndb, int d,
                          int passes, const TcPlan& plan, float* cand_val, int* cand_idx, cudaStream_t stream);
 
+// knn_cosine_f16_sm100.cu  (tcgen05 kind::f16, single pass)
+TcPlan tc_plan_f16(int nq, int ndb, int d, int k);
+int launch_normalize_f16(const float* x, long long n, int d, int ld, int ldh, int normalize, float* xn, void* xh,
+                         cudaStream_t stream);
+int launch_knn_cosine_f16(const void* qh, int nq, const void* dh, int ndb, int ldh, const TcPlan& plan, float* cand_val,
+                          int* cand_idx, cudaStream_t stream);
+
 // csr_build.cu
 size_t csr_build_workspace_bytes(long long e);
 int launch_edges_to_csr(const long long* src, const long long* dst, long long e, long long n, int dedup, int* rowptr,

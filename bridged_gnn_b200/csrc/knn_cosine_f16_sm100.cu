@@ -1,0 +1,315 @@
+// Cosine-similarity kNN sweep, single-pass fp16 tensor-core nomination (sm_100a):
+//   TMA -> shared memory -> tcgen05.mma kind::f16 (fp32 accumulators in TMEM) -> tcgen05.ld ->
+//   fused per-row top-KC selection.  The [nq, ndb] score matrix never leaves the SM.
+//
+// Replaces the pair-materialising similarity + sim_mat.topk of the reference for the cosine head
+// (models/models.py:124-130 / 945-948, main_bridged_graph.py:45-67, 90-111).
+//
+// Exactness.  The sweep scores unit rows rounded to fp16 (10 explicit mantissa bits, the same as tf32,
+// at half the operand bytes and twice the MMA rate).  For unit rows a, b with fp16 roundings ha, hb:
+//     |a.b - ha.hb| <= 2^-10 sum|a_i||b_i| + 2^-25 (sum|a_i| + sum|b_i|) + O(2^-22)  <=  2^-10 + 2^-24 sqrt(d)
+// so the approximate score is within delta_f16(d) of the exact fp32 cosine.  The kernel only NOMINATES
+// candidates (two lists of KC per row: one per epilogue warp of a lane quarter); knn_select.cu re-scores
+// them exactly in fp32 with the reference fmaf chain, selects under the parity key and certifies the row
+// against (largest discarded approximate score + delta); uncertified rows are redone exactly on CUDA cores.
+//
+// CTA = 10 warps, one (128-query block, db split) work unit, 1 CTA / SM:
+//   warp 0     TMA producer: the query block A [128 x dpad] once (resident), then a ring of B k-blocks
+//              [BN x 64] fp16, SWIZZLE_128B
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer; 128 x BN fp32 accumulator,
+//              double-buffered in TMEM: the epilogue of tile t overlaps the MMAs of tile t+1
+//   warps 2-9  epilogue: two warps per TMEM lane quarter, each taking every other 32-column chunk;
+//              thread <-> query row, running-threshold test on registers, rare insertion into a
+//              thread-private list in shared memory
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace bgnn {
+
+constexpr int F16_BM = 128;
+constexpr int F16_BK = 64;                          // fp16 elements per k-block = 128 B = one swizzle row
+constexpr int F16_UMMA_K = 16;
+constexpr int F16_THREADS = 320;
+constexpr int F16_A_KBLOCK = F16_BM * F16_BK * 2;   // 16 KB
+constexpr int F16_SMEM_MAX = 232448;
+constexpr int F16_SMEM_FIXED = 1024 + 512;          // alignment slack + barriers / tmem slot
+
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) [4,6), a/b format F16 (0)
+// [7,10)/[10,13), both K-major, N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// x -> unit row in fp32 (row stride ld, zero padded) and its fp16 rounding (row stride ldh, zero padded)
+__global__ void __launch_bounds__(256)
+normalize_f16_kernel(const float* __restrict__ x, long long n, int d, int ld, int ldh, int normalize,
+                     float* __restrict__ xn, __half* __restrict__ xh) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const float* p = x + row * d;
+  float denom = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) { float v = __ldg(p + c); ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    denom = fmaxf(sqrtf(ss), 1e-8f);
+  }
+  for (int c = lane; c < ldh; c += 32) {
+    float v = 0.f;
+    if (c < d) { v = __ldg(p + c); if (normalize) v = v / denom; }
+    if (c < ld) xn[row * ld + c] = v;
+    xh[row * ldh + c] = __float2half_rn(v);
+  }
+}
+
+int launch_normalize_f16(const float* x, long long n, int d, int ld, int ldh, int normalize, float* xn, void* xh,
+                         cudaStream_t stream) {
+  if (n <= 0) return BGNN_OK;
+  long long blocks = (n + 7) / 8;
+  normalize_f16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n, d, ld, ldh, normalize, xn, (__half*)xh);
+  BGNN_LAUNCH_CHECK();
+  return BGNN_OK;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(F16_THREADS, 1)
+knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
+                      int nq, int ndb, int kblocks, int tiles_total, int tiles_per_split, int kc, int stages,
+                      float* __restrict__ cand_val, int* __restrict__ cand_idx) {
+  constexpr int B_STAGE = BN * F16_BK * 2;
+  constexpr int TMEM_COLS = 2 * BN;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* a_base = smem;                                          // kblocks * 16 KB, resident
+  unsigned char* b_base = a_base + (size_t)kblocks * F16_A_KBLOCK;       // stages * B_STAGE ring
+  float* lval = reinterpret_cast<float*>(b_base + (size_t)stages * B_STAGE);   // [2][kc][128]
+  int* lidx = reinterpret_cast<int*>(lval + (size_t)2 * kc * F16_BM);           // [2][kc][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lidx + (size_t)2 * kc * F16_BM);
+  uint64_t* full_bar = bars;                      // [stages]
+  uint64_t* empty_bar = bars + stages;            // [stages]
+  uint64_t* tfull_bar = bars + 2 * stages;        // [2]
+  uint64_t* tempty_bar = bars + 2 * stages + 2;   // [2]
+  uint64_t* a_bar = bars + 2 * stages + 4;        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * F16_BM;
+  const int split = blockIdx.y;
+  const int tile_begin = split * tiles_per_split;
+  const int tile_end = min(tiles_total, tile_begin + tiles_per_split);
+  const int ntiles = tile_end - tile_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 8); }
+    mbar_init(smem_u32(a_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_db) : "memory");
+      const uint32_t ab = smem_u32(a_bar);
+      mbar_expect_tx(ab, (uint32_t)(kblocks * F16_A_KBLOCK));
+      for (int kb = 0; kb < kblocks; ++kb)
+        tma_load_2d(smem_u32(a_base + (size_t)kb * F16_A_KBLOCK), &map_q, ab, kb * F16_BK, q0);
+      int it = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int db0 = (tile_begin + t) * BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (uint32_t)(it / stages) & 1u;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, (uint32_t)B_STAGE);
+          tma_load_2d(smem_u32(b_base + (size_t)s * B_STAGE), &map_db, fb, kb * F16_BK, db0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(F16_BM, BN);
+      mbar_wait(smem_u32(a_bar), 0u);
+      tc_fence_after();
+      int it = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        const uint32_t tph = (uint32_t)(t >> 1) & 1u;
+        mbar_wait(smem_u32(&tempty_bar[buf]), tph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (uint32_t)(it / stages) & 1u;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          tc_fence_after();
+          const uint64_t ad = make_kmajor_sw128_desc(smem_u32(a_base + (size_t)kb * F16_A_KBLOCK));
+          const uint64_t bd = make_kmajor_sw128_desc(smem_u32(b_base + (size_t)s * B_STAGE));
+#pragma unroll
+          for (int k4 = 0; k4 < F16_BK / F16_UMMA_K; ++k4) {
+            // advance 32 B (= 16 fp16) inside the 128-B swizzle row: +2 in 16-B units
+            tc_mma_f16(d_tmem, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0 ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&empty_bar[s]));      // frees the ring slot when these MMAs retire
+        }
+        tc_commit(smem_u32(&tfull_bar[buf]));      // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue: thread <-> query row, warp pair <-> lane quarter =====================
+    const int quarter = warp & 3;                  // TMEM lanes this warp may read: 32*quarter ..
+    const int half = (warp - 2) >> 2;              // which of the two warps of the quarter
+    const int r_in_tile = quarter * 32 + lane;
+    const bool row_ok = q0 + r_in_tile < nq;
+    float* my_val = lval + (size_t)half * kc * F16_BM + r_in_tile;
+    int* my_idx = lidx + (size_t)half * kc * F16_BM + r_in_tile;
+    ListState st = list_init();
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const uint32_t tph = (uint32_t)(t >> 1) & 1u;
+      mbar_wait(smem_u32(&tfull_bar[buf]), tph);
+      tc_fence_after();
+      const int db0 = (tile_begin + t) * BN;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int ch = half; ch < BN / 32; ch += 2) {
+        float r[32];
+        tc_ld32(taddr0 + (uint32_t)(ch * 32), r);
+        tc_wait_ld();
+        float mx = r[0];
+#pragma unroll
+        for (int c = 1; c < 32; ++c) mx = fmaxf(mx, r[c]);
+        if (row_ok && mx > st.thr) {
+          float tmp[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) tmp[c] = r[c];
+          const int jb = db0 + ch * 32;
+          const int lim = min(32, ndb - jb);
+          for (int c = 0; c < lim; ++c) {
+            float v = tmp[c];
+            if (v > st.thr) st = list_insert(my_val, my_idx, F16_BM, kc, st, v, jb + c);
+          }
+        }
+      }
+      // this warp has read all of its columns of the buffer: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+    }
+    if (row_ok) {
+      const long long base = (((long long)split * 2 + half) * nq + (q0 + r_in_tile)) * kc;
+      for (int s = 0; s < kc; ++s) {
+        const bool f = s < st.cnt;
+        cand_val[base + s] = f ? my_val[s * F16_BM] : -INFINITY;
+        cand_idx[base + s] = f ? my_idx[s * F16_BM] : -1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+// Row-major [rows, ldh] fp16, box = [box_rows, 64 features], 128-B swizzle, zero fill out of bounds.
+static int make_map_f16(CUtensorMap* m, const void* base, long long rows, int ldh, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return BGNN_ERR_DRIVER;
+  cuuint64_t dims[2] = {(cuuint64_t)ldh, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ldh * 2};
+  cuuint32_t box[2] = {(cuuint32_t)F16_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? BGNN_OK : BGNN_ERR_DRIVER;
+}
+
+// Work decomposition: kc nominees per (row, half-list) next to the resident query block and the B ring.
+TcPlan tc_plan_f16(int nq, int ndb, int d, int k) {
+  TcPlan p;
+  p.bn = 0;
+  const int ldh = (d + F16_BK - 1) / F16_BK * F16_BK;
+  int kc = (k + 4 + 3) / 4 * 4;
+  p.kc = kc;
+  const int a_bytes = (ldh / F16_BK) * F16_A_KBLOCK;
+  const int list_bytes = 2 * kc * F16_BM * 8;
+  for (int bn = 256; bn >= 128; bn >>= 1) {
+    const int stage_bytes = bn * F16_BK * 2;
+    const int stages = (F16_SMEM_MAX - F16_SMEM_FIXED - a_bytes - list_bytes) / stage_bytes;
+    if (stages >= 3) { p.bn = bn; p.stages = min(stages, 8); break; }
+  }
+  if (p.bn == 0) return p;                                  // caller falls back to another sweep
+  const int tiles = (ndb + p.bn - 1) / p.bn;
+  const int qblocks = (nq + F16_BM - 1) / F16_BM;
+  int ns = (2 * kNumSMs + qblocks - 1) / qblocks;            // fill the machine when nq is small
+  ns = max(1, min(min(ns, tiles), min(8, BGNN_MERGE_MAX_CAND / (2 * kc))));
+  if (ns < 1) { p.bn = 0; return p; }
+  p.tiles_per_split = (tiles + ns - 1) / ns;
+  p.nsplit = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.nlists = 2 * p.nsplit;
+  if (p.nlists * kc > BGNN_MERGE_MAX_CAND) p.bn = 0;
+  return p;
+}
+
+template <int BN>
+static int launch_f16_cfg(const void* qh, int nq, const void* dh, int ndb, int ldh, const TcPlan& plan, float* cand_val,
+                          int* cand_idx, cudaStream_t stream) {
+  CUtensorMap mq, md;
+  int rc;
+  if ((rc = make_map_f16(&mq, qh, nq, ldh, F16_BM)) != BGNN_OK) return rc;
+  if ((rc = make_map_f16(&md, dh, ndb, ldh, BN)) != BGNN_OK) return rc;
+  const int kblocks = ldh / F16_BK;
+  const size_t smem = F16_SMEM_FIXED + (size_t)kblocks * F16_A_KBLOCK + (size_t)plan.stages * BN * F16_BK * 2 +
+                      (size_t)2 * plan.kc * F16_BM * 8;
+  if (smem > (size_t)F16_SMEM_MAX || plan.stages < 2) return BGNN_ERR_UNSUPPORTED;
+  auto kern = knn_cosine_f16_kernel<BN>;
+  BGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = (ndb + BN - 1) / BN;
+  dim3 grid((nq + F16_BM - 1) / F16_BM, plan.nsplit);
+  kern<<<grid, F16_THREADS, smem, stream>>>(mq, md, nq, ndb, kblocks, tiles, plan.tiles_per_split, plan.kc, plan.stages,
+                                            cand_val, cand_idx);
+  BGNN_LAUNCH_CHECK();
+  return BGNN_OK;
+}
+
+int launch_knn_cosine_f16(const void* qh, int nq, const void* dh, int ndb, int ldh, const TcPlan& plan, float* cand_val,
+                          int* cand_idx, cudaStream_t stream) {
+  if (nq <= 0) return BGNN_OK;
+  if (ldh % F16_BK != 0) return BGNN_ERR_INVALID_ARG;
+  if (plan.bn == 256) return launch_f16_cfg<256>(qh, nq, dh, ndb, ldh, plan, cand_val, cand_idx, stream);
+  if (plan.bn == 128) return launch_f16_cfg<128>(qh, nq, dh, ndb, ldh, plan, cand_val, cand_idx, stream);
+  return BGNN_ERR_UNSUPPORTED;
+}
+
+}  // namespace bgnn

@@ -34,10 +34,20 @@ class AdaptedConv(nn.Module):
         self.a_f_s2t = nn.Linear(out_channels, 1, bias=False)
         self.a_f_t2s = nn.Linear(out_channels, 1, bias=False)
         self._mask_key, self._mask_u8 = None, None
+        self._rows_key, self._rows = None, None
 
     def reset_parameters(self):
         for m in self.children():
             m.reset_parameters()
+
+    def _domain_rows(self, central_mask, dtype):
+        key = (central_mask.data_ptr(), central_mask._version, central_mask.shape[0], dtype)
+        if self._rows_key != key:
+            cf = central_mask.to(dtype)
+            ns = cf.sum().clamp(min=1.0)
+            nt = (central_mask.shape[0] - cf.sum()).clamp(min=1.0)
+            self._rows_key, self._rows = key, torch.stack((cf / ns, (1.0 - cf) / nt), 0).contiguous()
+        return self._rows
 
     def _dst_is_src(self, central_mask):
         key = (central_mask.data_ptr(), central_mask._version, central_mask.shape[0])
@@ -51,15 +61,28 @@ class AdaptedConv(nn.Module):
         picks the branch per destination row from ``central_mask``, so only ``edge_index`` is read."""
         x_src, x_r = (x, x) if torch.is_tensor(x) else x
         c = central_mask
-        # g: domain shift gates (models/KTGNN.py:275-280)
-        diff = x_src[c].mean(0, keepdim=True) - x_src[~c].mean(0, keepdim=True)
-        diff = diff.expand(x_src.shape)
-        cat = torch.cat((x_src, diff), dim=-1)
-        x_s2t = x_src - torch.tanh(self.a_g_s2t(cat)) * diff * c.unsqueeze(-1)
-        x_t2s = x_src + torch.tanh(self.a_g_t2s(cat)) * diff * (~c).unsqueeze(-1)
-        # f: per-domain transforms (:283-284)
-        h_t = self.lin_t(x_s2t)
-        h_s = self.lin_s(x_t2s)
+        n, d = x_src.shape
+        co = self.out_channels
+        # g + f (models/KTGNN.py:275-284) restructured so that x is read by ONE dense contraction and no
+        # [N, 2D] / [N, D] intermediate is materialised.  With Delta = mean_src(x) - mean_tar(x):
+        #   gate_s2t = tanh(a_g_s2t . [x, Delta]),  gate_t2s = tanh(a_g_t2s . [x, Delta])
+        #   h_t = lin_t(x - gate_s2t * Delta * c)      = x W_t^T + b_t - (gate_s2t * c)     (x) (W_t Delta)
+        #   h_s = lin_s(x + gate_t2s * Delta * (1-c))  = x W_s^T + b_s + (gate_t2s * (1-c)) (x) (W_s Delta)
+        cf = self._domain_rows(c, x_src.dtype)                       # [2, N]: 1/Ns on source rows, 1/Nt on target rows
+        means = cf @ x_src                                           # [2, D] (one pass over x)
+        delta = means[0:1] - means[1:2]                              # [1, D]
+        w_cat = torch.cat((self.lin_s.weight, self.lin_t.weight, self.a_g_s2t.weight[:, :d], self.a_g_t2s.weight[:, :d]), 0)
+        if self.lin_s.bias is not None:
+            b_cat = torch.cat((self.lin_s.bias, self.lin_t.bias, self.lin_s.bias.new_zeros(2)))
+            p = torch.addmm(b_cat, x_src, w_cat.t())                 # [N, 2*co + 2], biases folded into the GEMM
+        else:
+            p = x_src @ w_cat.t()
+        gate_s2t = torch.tanh(p[:, 2 * co] + (self.a_g_s2t.weight[:, d:] * delta).sum())
+        gate_t2s = torch.tanh(p[:, 2 * co + 1] + (self.a_g_t2s.weight[:, d:] * delta).sum())
+        cfl = c.to(x_src.dtype)
+        wd = delta @ torch.cat((self.lin_s.weight, self.lin_t.weight), 0).t()      # [1, 2*co]: W_s Delta, W_t Delta
+        h_s = torch.addcmul(p[:, :co], (gate_t2s * (1.0 - cfl)).unsqueeze(1), wd[:, :co])
+        h_t = torch.addcmul(p[:, co:2 * co], (gate_s2t * cfl).unsqueeze(1), wd[:, co:], value=-1.0)
         # attention scores, softmax over destinations, weighted aggregation (:292-305) -- one kernel
         graph = ops.cached_graph(edge_index, x_src.shape[0])
         out = ops.gat_aggregate(h_s, h_t, self.a_f_t2s.weight, self.a_f_s2t.weight, graph, self._dst_is_src(c),

@@ -5,9 +5,9 @@ CUDA stream; nothing falls back to torch ops or the CPU.
 import torch
 
 from . import _lib
-from ._lib import KNN_SIMT_F32, KNN_TC_1XTF32, KNN_TC_3XTF32  # noqa: F401
+from ._lib import KNN_SIMT_F32, KNN_TC_1XTF32, KNN_TC_3XTF32, KNN_TC_F16  # noqa: F401
 
-_ALGOS = {"simt": KNN_SIMT_F32, "tc3": KNN_TC_3XTF32, "tc1": KNN_TC_1XTF32}
+_ALGOS = {"simt": KNN_SIMT_F32, "tc3": KNN_TC_3XTF32, "tc1": KNN_TC_1XTF32, "f16": KNN_TC_F16}
 # below this many pairs the tensor-core sweep cannot fill the machine and the CUDA-core sweep is used
 _TC_MIN_PAIRS = 1 << 24
 
@@ -35,7 +35,7 @@ def knn_cosine(q, db, k, normalize=True, apply_sigmoid=True, algo="auto"):
     if db.shape[1] != d:
         raise ValueError("feature widths differ")
     if algo == "auto":
-        algo = "tc3" if nq * ndb >= _TC_MIN_PAIRS else "simt"
+        algo = "f16" if nq * ndb >= _TC_MIN_PAIRS else "simt"
     a = _ALGOS[algo]
     dev = q.device
     idx = torch.empty((nq, k), dtype=torch.int64, device=dev)

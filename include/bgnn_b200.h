@@ -33,6 +33,7 @@ extern "C" {
 #define BGNN_KNN_SIMT_F32 0   /* exact fp32 on CUDA cores                                    */
 #define BGNN_KNN_TC_3XTF32 1  /* tcgen05 3xTF32 split + exact fp32 re-score + certification */
 #define BGNN_KNN_TC_1XTF32 2  /* tcgen05 single TF32 pass + exact re-score + certification   */
+#define BGNN_KNN_TC_F16 3     /* tcgen05 single FP16 pass (resident query block) + exact re-score + certification */
 
 int bgnn_version(void);
 const char* bgnn_error_string(int code);

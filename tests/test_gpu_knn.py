@@ -132,7 +132,7 @@ def test_office_within_target_matches_reference(office_build):
     assert {e[1] for e in a ^ b} <= tie_rows
 
 
-@pytest.mark.parametrize("algo", ["simt", "tc3", "tc1"])
+@pytest.mark.parametrize("algo", ["simt", "tc3", "tc1", "f16"])
 def test_fb_cosine_head_matches_reference(fb_build, algo):
     """Config 3 stand-in: shipped fb_hamilton2caltech v1 cosine head on seeded embeddings, k=50 cross, k=5 within."""
     g = fb_build
@@ -160,7 +160,7 @@ def test_fb_cosine_head_matches_reference(fb_build, algo):
 # ------------------------------------------------------------------ seeded random inputs vs the oracle
 @pytest.mark.parametrize("nq,ndb,d,k", [(1, 1, 3, 1), (5, 7, 128, 7), (130, 1000, 100, 20), (257, 2049, 128, 3),
                                         (64, 4096, 256, 32), (33, 300, 17, 60)])
-@pytest.mark.parametrize("algo", ["simt", "tc3", "tc1"])
+@pytest.mark.parametrize("algo", ["simt", "tc3", "tc1", "f16"])
 def test_cosine_knn_random_vs_oracle(nq, ndb, d, k, algo):
     ops = _ops()
     gq = torch.Generator().manual_seed(1000 + nq + ndb)
@@ -176,7 +176,7 @@ def test_cosine_knn_random_vs_oracle(nq, ndb, d, k, algo):
         assert bool(torch.isinf(gap).all())
 
 
-@pytest.mark.parametrize("algo", ["tc3", "tc1"])
+@pytest.mark.parametrize("algo", ["tc3", "tc1", "f16"])
 @pytest.mark.parametrize("nq,ndb,d,k", [(700, 9000, 128, 20), (300, 5000, 96, 50), (129, 70000, 256, 8)])
 def test_tensor_core_path_is_bit_identical_to_cuda_core_path(algo, nq, ndb, d, k):
     """The tcgen05 sweep only nominates; after exact re-scoring + certification (+ exact fallback) its
@@ -206,7 +206,7 @@ def test_exact_ties_resolve_to_lowest_index():
     pairs = bo.pair_enumeration(torch.arange(600).unsqueeze(-1), torch.arange(50).unsqueeze(-1)).t()
     sim = torch.sigmoid(torch.nn.CosineSimilarity(dim=1)(db[pairs[0]], q[pairs[1]])).view(-1, 600)
     cv, ci = bo.canonical_topk(sim, 10)
-    for algo in ("simt", "tc3", "tc1"):
+    for algo in ("simt", "tc3", "tc1", "f16"):
         idx, val, gap, _ = ops.knn_cosine(q.cuda(), db.cuda(), 10, algo=algo)
         assert torch.equal(idx.cpu(), ci), algo
         assert bool((gap.cpu() >= 0).all())
@@ -216,7 +216,7 @@ def test_exact_ties_resolve_to_lowest_index():
 def test_within_domain_keeps_self_and_aliasing():
     ops = _ops()
     x = torch.randn(500, 128, generator=torch.Generator().manual_seed(5)).cuda()
-    for algo in ("simt", "tc3"):
+    for algo in ("simt", "tc3", "f16"):
         idx, val, _, _ = ops.knn_cosine(x, x, 4, algo=algo)
         assert torch.equal(idx[:, 0], torch.arange(500, device="cuda"))       # self is rank 1, not excluded
         idx2, val2, _, _ = ops.knn_cosine(x, x.clone(), 4, algo=algo)        # non-aliased path, same result
@@ -262,10 +262,12 @@ def test_sync_1m_shape_sampled_rows_exact():
     ops = _ops()
     from bench import make_sync_embeddings
     u_src, u_tar, _, _ = make_sync_embeddings(786432, 4096, 128, torch.device("cuda:0"), seed=0)
-    i1, v1, g1, st = ops.knn_cosine(u_tar, u_src, 20, algo="tc3")
     i0, v0, g0, _ = ops.knn_cosine(u_tar, u_src, 20, algo="simt")
-    assert torch.equal(i0, i1) and torch.equal(v0, v1) and torch.equal(g0, g1)
-    assert int(st[0]) < 4096 // 4          # certification must hold for the bulk of the rows
+    for algo in ("f16", "tc3"):
+        i1, v1, g1, st = ops.knn_cosine(u_tar, u_src, 20, algo=algo)
+        assert torch.equal(i0, i1) and torch.equal(v0, v1) and torch.equal(g0, g1), algo
+        print(algo, "exact-fallback rows:", int(st[0]), "of 4096")
+        assert int(st[0]) < 4096 // 4          # certification must hold for the bulk of the rows
     rows = torch.arange(0, 4096, 64)
     v, i, tie = bo.cosine_knn_rows(u_src.cpu(), u_tar.cpu(), 20, rows=rows, chunk=4)
     for n, r in enumerate(rows.tolist()):

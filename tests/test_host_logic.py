@@ -1,0 +1,163 @@
+"""CPU tests of the host-side logic around the kernels.  The CUDA operators are replaced by the oracle
+here (test infrastructure only) so that the algebra of the Python layers -- the restructured node-wise
+part of AdaptedConv, the BatchNorm fold of the mlp similarity head, model wiring and state_dict
+compatibility -- is checked against the reference-generated golden vectors without a GPU."""
+import types
+
+import pytest
+import torch
+
+from conftest import sub_state
+from oracle import build_oracle as bo
+from oracle import mp_oracle as mo
+
+T = torch.from_numpy
+
+
+def relclose(a, b, tol=1e-5):
+    a, b = a.detach(), b.detach()
+    return float((a - b).abs().max()) <= tol * float(b.abs().max()) + 1e-7
+
+
+class _FakeGraph:
+    def __init__(self, edge_index, n):
+        self.edge_index, self.n = edge_index, n
+        self.deg = torch.bincount(edge_index[1], minlength=n).to(torch.float32)
+
+
+@pytest.fixture()
+def oracle_backed_ops(monkeypatch):
+    """ops.gat_aggregate / ops.spmm / ops.cached_graph -> oracle implementations on the CPU."""
+    from bridged_gnn_b200 import ops
+
+    def cached_graph(edge_index, n):
+        return _FakeGraph(edge_index, n)
+
+    def gat_aggregate(Hs, Ht, a1, a2, graph, dst_is_src, slope=0.1):
+        cm = dst_is_src.bool()
+        ei = graph.edge_index
+        m1 = cm[ei[1]]
+        return mo.adapted_conv_aggregate(Hs, Ht, ei[:, m1], ei[:, ~m1], cm, a1.view(-1), a2.view(-1), slope)
+
+    def spmm(graph, X, reduce="sum", edge_weight=None, gather_scale=None, out_scale=None):
+        ei = graph.edge_index
+        w = edge_weight
+        if gather_scale is not None or out_scale is not None:
+            w = torch.ones(ei.shape[1]) if w is None else w
+            if gather_scale is not None:
+                w = w * gather_scale[ei[0]]
+            if out_scale is not None:
+                w = w * out_scale[ei[1]]
+        return mo.spmm(ei, X, graph.n, reduce, w)
+
+    monkeypatch.setattr(ops, "cached_graph", cached_graph)
+    monkeypatch.setattr(ops, "gat_aggregate", gat_aggregate)
+    monkeypatch.setattr(ops, "spmm", spmm)
+    monkeypatch.setattr(ops, "CSRGraph", _FakeGraph)
+    return ops
+
+
+def test_adapted_conv_algebra_matches_reference(oracle_backed_ops, office_mp, office_build):
+    from bridged_gnn_b200.models import AdaptedConv
+    m = office_mp
+    conv = AdaptedConv(64, 31, root_weight=False)
+    conv.load_state_dict(sub_state(m, "conv.sd."))
+    c = T(office_build["central_mask"])
+    e1, e2 = T(m["ktgnn.ei1"]), T(m["ktgnn.ei2"])
+    x = T(m["conv.x"]).clone().requires_grad_(True)
+    y = conv(x, torch.cat((e1, e2), 1), e1, e2, c)
+    assert relclose(y, T(m["conv.y"]))
+    (y * T(m["conv.gout"])).sum().backward()
+    assert relclose(x.grad, T(m["conv.gx"]), 2e-5)
+    for k, p in conv.named_parameters():
+        assert relclose(p.grad, T(m["conv.grad." + k]), 2e-5), k
+
+
+def test_ktgnn_wiring_matches_reference(oracle_backed_ops, office_mp, office_build):
+    from bridged_gnn_b200.data import Data
+    from bridged_gnn_b200.models import KTGNN_no_complement
+    m = office_mp
+    data = Data(x=T(office_build["x"]), edge_index=T(m["edge_index_undirected"]), y=T(office_build["y"]),
+                central_mask=T(office_build["central_mask"]), train_mask=T(office_build["train_mask"]))
+    model = KTGNN_no_complement(256, 31, 2, 64, root_weight=False, use_bn=True, dim_share=256, need_complement=False)
+    model.load_state_dict(sub_state(m, "ktgnn.sd."))
+    model.eval()
+    with torch.no_grad():
+        lb, lt, ltt, _ = model(data)
+    assert relclose(lb, T(m["ktgnn.eval.logp_base"])) and relclose(lt, T(m["ktgnn.eval.logp_target"]))
+    assert relclose(ltt, T(m["ktgnn.eval.logp_trans"]))
+    assert torch.equal(model.edge_index1, T(m["ktgnn.ei1"])) and torch.equal(model.edge_index2, T(m["ktgnn.ei2"]))
+    model.train()
+    model.dropout = 0.0
+    lb, lt, ltt, _ = model(data)
+    tm = data.train_mask
+    nll = torch.nn.functional.nll_loss
+    loss = nll(lb[tm], data.y[tm]) + nll(lt[tm], data.y[tm]) + nll(ltt[tm], data.y[tm])
+    assert abs(loss.item() - float(m["ktgnn.train.loss"])) < 2e-5
+    loss.backward()
+    for k, p in model.named_parameters():
+        assert relclose(p.grad, T(m["ktgnn.train.grad." + k]), 5e-5), k
+
+
+def test_sage_gcn_wiring_matches_reference(oracle_backed_ops, office_mp, office_build):
+    from bridged_gnn_b200.data import Data
+    from bridged_gnn_b200.models import GCNNet, GraphSAGE
+    m = office_mp
+    data = Data(x=T(office_build["x"]), edge_index=T(m["edge_index_undirected"]))
+    ds = types.SimpleNamespace(num_features=256, num_classes=31)
+    sage = GraphSAGE(ds, layer_num=2, hidden=64)
+    sage.load_state_dict(sub_state(m, "sage.sd."))
+    gcn = GCNNet(ds, layer_num=2, hidden=64)
+    gcn.load_state_dict(sub_state(m, "gcn.sd."))
+    with torch.no_grad():
+        assert relclose(sage.eval()(data), T(m["sage.logp"]))
+        assert relclose(gcn.eval()(data), T(m["gcn.logp"]))
+
+
+def test_mlp_head_fold_matches_pair_path(office_build):
+    """Eval-mode BatchNorm fold of Similar_v2(mode='mlp'): sum_h w2 relu(U_db + U_q) + b2 == the reference's
+    pair path logits (to fp32 rounding), on real checkpoint weights and embeddings."""
+    from bridged_gnn_b200.models import Similar_v2
+    g = office_build
+    W = sub_state(g, "ckpt.")
+    head = Similar_v2(128, 31, mode="mlp")
+    head.load_state_dict({k[len("source_learner.sim_net."):]: v for k, v in W.items() if k.startswith("source_learner.sim_net.")})
+    head.eval()
+    z_src, z_tar = T(g["z_src"]), T(g["z_tar"])
+    U_db, U_q, w2, b2 = head.mlp_operands(z_src, z_tar)
+    rows = T(g["sim_rows_idx"])
+    logit = (torch.relu(U_q[rows][:, None, :] + U_db[None, :, :]) * w2).sum(-1) + b2
+    sim = torch.sigmoid(logit)
+    assert float((sim - T(g["sim_rows"])).abs().max()) < 2e-6
+    with pytest.raises(RuntimeError):
+        head.train().mlp_operands(z_src, z_tar)
+
+
+def test_checkpoints_load_strict_shapes(office_build, fb_build):
+    """Module trees mirror the reference's: every golden checkpoint tensor finds its parameter."""
+    from bridged_gnn_b200.data import Data
+    from bridged_gnn_b200.models import Adversarial_Learner, Adversarial_Learner_v2
+    g = office_build
+    d = Data(x=torch.zeros(4, 256), y=torch.tensor([0, 30, 1, 2]))
+    m2 = Adversarial_Learner_v2(d, d, dim_hidden=128, num_layer=2, source_clf=True, use_norm=True, norm_mode="None",
+                                norm_scale=1.0, backbone="mlp", sim_mode="mlp")
+    res = m2.load_state_dict(sub_state(g, "ckpt."), strict=False)
+    assert not res.unexpected_keys
+    assert all(k.startswith(("target_learner.decoder", "discriminator")) for k in res.missing_keys)
+    z = m2.eval().embed_source(Data(x=T(g["x"])[:2817]))
+    assert relclose(z, T(g["z_src"]), 1e-5)
+    z = m2.embed_target(Data(x=T(g["x"])[2817:]))
+    assert relclose(z, T(g["z_tar"]), 1e-5)
+    d1 = Data(x=torch.zeros(4, 1685), y=torch.tensor([0, 1, 1, 0]))
+    m1 = Adversarial_Learner(d1, d1, dim_hidden=64, num_layer=2, source_clf=True, norm_mode="None", norm_scale=1.0)
+    res = m1.load_state_dict(sub_state(fb_build, "ckpt."), strict=False)
+    assert not res.unexpected_keys
+    u = m1.eval().source_learner.sim_net.cosine_operand(T(fb_build["z_src"]))
+    assert u.shape == (1200, 128)
+
+
+def test_graph_partition_and_self_loops(office_mp, office_build):
+    from bridged_gnn_b200.models import graph_partition
+    e1, e2, e = graph_partition(T(office_mp["edge_index_undirected"]), T(office_build["central_mask"]))
+    assert torch.equal(e1, T(office_mp["ktgnn.ei1"])) and torch.equal(e2, T(office_mp["ktgnn.ei2"]))
+    assert e.shape[1] == 37522

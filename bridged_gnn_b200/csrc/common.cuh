@@ -59,37 +59,63 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Thread-private top-KC list living in shared memory.  Thread t owns column t of val[KC][stride]
-// / idx[KC][stride] (bank-conflict-free).  Candidates must arrive in increasing index order, which
-// makes "strictly greater than the current worst" equivalent to the (value desc, index asc) key.
+// Thread-private top-KC list living in shared memory, organised as a binary min-heap whose root is the
+// WORST kept element.  Thread t owns column t of val[KC][stride] / idx[KC][stride] (bank-conflict-free).
+// Candidates must arrive in increasing index order, which makes "strictly greater than the current
+// worst" equivalent to the parity key (value desc, index asc): an equal value with a larger index loses.
 // ---------------------------------------------------------------------------------------------
 struct ListState {
   int cnt;      // filled slots
-  float thr;    // value of the worst kept element (-inf until full)
-  int worst;    // slot of the worst kept element
+  float thr;    // value of the worst kept element (-inf until the list is full)
 };
 
 __device__ __forceinline__ ListState list_init() {
-  ListState s; s.cnt = 0; s.thr = -INFINITY; s.worst = 0; return s;
+  ListState s; s.cnt = 0; s.thr = -INFINITY; return s;
 }
 
-// Precondition: v > st.thr (always true while the list is not full).  Kept out of line: it runs
-// ~k*ln(N/k) times per row over a whole sweep, so it must not bloat the hot loop.
-static __device__ __noinline__ ListState list_insert(float* val, int* idx, int stride, int kc, ListState st, float v, int j) {
-  int slot = (st.cnt < kc) ? st.cnt : st.worst;
-  val[slot * stride] = v;
-  idx[slot * stride] = j;
-  if (st.cnt < kc) ++st.cnt;
-  if (st.cnt == kc) {
-    float w = val[0];
-    int wi = idx[0], ws = 0;
-    for (int s = 1; s < kc; ++s) {
-      float x = val[s * stride];
-      int i = idx[s * stride];
-      if (x < w || (x == w && i > wi)) { w = x; wi = i; ws = s; }
+// a ranks below b under the parity key
+__device__ __forceinline__ bool list_worse(float av, int ai, float bv, int bi) {
+  return av < bv || (av == bv && ai > bi);
+}
+
+// Precondition: v > st.thr (always true while the list is not full).  O(log KC) shared-memory accesses.
+__device__ __forceinline__ void list_push(float* val, int* idx, int stride, int kc, ListState& st, float v, int j) {
+  if (st.cnt < kc) {
+    int pos = st.cnt++;
+    while (pos > 0) {                       // sift up: parents must be worse than children
+      const int par = (pos - 1) >> 1;
+      const float pv = val[par * stride];
+      const int pi = idx[par * stride];
+      if (!list_worse(v, j, pv, pi)) break;
+      val[pos * stride] = pv; idx[pos * stride] = pi;
+      pos = par;
     }
-    st.thr = w; st.worst = ws;
+    val[pos * stride] = v; idx[pos * stride] = j;
+    if (st.cnt == kc) st.thr = val[0];
+  } else {
+    int pos = 0;                            // replace the root, sift down
+    while (true) {
+      const int l = 2 * pos + 1;
+      if (l >= kc) break;
+      float cv = val[l * stride];
+      int ci = idx[l * stride], ch = l;
+      if (l + 1 < kc) {
+        const float rv = val[(l + 1) * stride];
+        const int ri = idx[(l + 1) * stride];
+        if (list_worse(rv, ri, cv, ci)) { cv = rv; ci = ri; ch = l + 1; }
+      }
+      if (!list_worse(cv, ci, v, j)) break;
+      val[pos * stride] = cv; idx[pos * stride] = ci;
+      pos = ch;
+    }
+    val[pos * stride] = v; idx[pos * stride] = j;
+    st.thr = val[0];
   }
+}
+
+// Out-of-line variant for call sites that must not grow (hot loops with many live registers).
+static __device__ __noinline__ ListState list_insert(float* val, int* idx, int stride, int kc, ListState st, float v, int j) {
+  list_push(val, idx, stride, kc, st, v, j);
   return st;
 }
 

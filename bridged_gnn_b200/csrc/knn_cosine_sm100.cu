@@ -174,6 +174,7 @@ knn_cosine_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
       tc_fence_after();
       const int db0 = (tile_begin + t) * BN;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
+      const bool partial = db0 + BN > ndb;          // only the last db tile has zero-filled columns
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         float r[32];
@@ -184,18 +185,40 @@ knn_cosine_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
           tc_fence_before();
           if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
         }
-        float mx = r[0];
+        const int jb = db0 + ch * 32;
+        if (partial) {
 #pragma unroll
-        for (int c = 1; c < 32; ++c) mx = fmaxf(mx, r[c]);
+          for (int c = 0; c < 32; ++c) r[c] = (jb + c < ndb) ? r[c] : -INFINITY;
+        }
+        float gm[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float m01 = fmaxf(r[g * 8 + 0], r[g * 8 + 1]), m23 = fmaxf(r[g * 8 + 2], r[g * 8 + 3]);
+          float m45 = fmaxf(r[g * 8 + 4], r[g * 8 + 5]), m67 = fmaxf(r[g * 8 + 6], r[g * 8 + 7]);
+          gm[g] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+        }
+        const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
         if (row_ok && mx > st.thr) {
-          float tmp[32];
+          // rare path, register-resident: per group of 8 columns, repeatedly pick the first column (index
+          // order) that still beats the running threshold and push it into the heap
 #pragma unroll
-          for (int c = 0; c < 32; ++c) tmp[c] = r[c];
-          const int jb = db0 + ch * 32;
-          const int lim = min(32, ndb - jb);
-          for (int c = 0; c < lim; ++c) {
-            float v = tmp[c];
-            if (v > st.thr) st = list_insert(my_val, my_idx, TC_BM, kc, st, v, jb + c);
+          for (int g = 0; g < 4; ++g) {
+            if (gm[g] > st.thr) {
+              int last = -1;
+              while (true) {
+                float cv = -INFINITY;
+                int cc = -1;
+#pragma unroll
+                for (int c = 7; c >= 0; --c) {
+                  const bool p = (c > last) && (r[g * 8 + c] > st.thr);
+                  cv = p ? r[g * 8 + c] : cv;
+                  cc = p ? c : cc;
+                }
+                if (cc < 0) break;
+                list_push(my_val, my_idx, TC_BM, kc, st, cv, jb + g * 8 + cc);
+                last = cc;
+              }
+            }
           }
         }
       }

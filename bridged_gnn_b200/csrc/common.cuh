@@ -78,44 +78,57 @@ __device__ __forceinline__ bool list_worse(float av, int ai, float bv, int bi) {
   return av < bv || (av == bv && ai > bi);
 }
 
+// explicit shared-window accessors: the lists live in dynamic shared memory and generic LD/ST would
+// cost an address-space check per access
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+  int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// val / idx: shared-window byte addresses of this thread's column; sb: byte stride between slots.
 // Precondition: v > st.thr (always true while the list is not full).  O(log KC) shared-memory accesses.
-__device__ __forceinline__ void list_push(float* val, int* idx, int stride, int kc, ListState& st, float v, int j) {
+__device__ __forceinline__ void list_push(uint32_t val, uint32_t idx, uint32_t sb, int kc, ListState& st, float v, int j) {
   if (st.cnt < kc) {
     int pos = st.cnt++;
     while (pos > 0) {                       // sift up: parents must be worse than children
       const int par = (pos - 1) >> 1;
-      const float pv = val[par * stride];
-      const int pi = idx[par * stride];
+      const float pv = lds_f32(val + par * sb);
+      const int pi = lds_s32(idx + par * sb);
       if (!list_worse(v, j, pv, pi)) break;
-      val[pos * stride] = pv; idx[pos * stride] = pi;
+      sts_f32(val + pos * sb, pv); sts_s32(idx + pos * sb, pi);
       pos = par;
     }
-    val[pos * stride] = v; idx[pos * stride] = j;
-    if (st.cnt == kc) st.thr = val[0];
+    sts_f32(val + pos * sb, v); sts_s32(idx + pos * sb, j);
+    if (st.cnt == kc) st.thr = lds_f32(val);
   } else {
     int pos = 0;                            // replace the root, sift down
     while (true) {
       const int l = 2 * pos + 1;
       if (l >= kc) break;
-      float cv = val[l * stride];
-      int ci = idx[l * stride], ch = l;
+      float cv = lds_f32(val + l * sb);
+      int ci = lds_s32(idx + l * sb), ch = l;
       if (l + 1 < kc) {
-        const float rv = val[(l + 1) * stride];
-        const int ri = idx[(l + 1) * stride];
+        const float rv = lds_f32(val + (l + 1) * sb);
+        const int ri = lds_s32(idx + (l + 1) * sb);
         if (list_worse(rv, ri, cv, ci)) { cv = rv; ci = ri; ch = l + 1; }
       }
       if (!list_worse(cv, ci, v, j)) break;
-      val[pos * stride] = cv; idx[pos * stride] = ci;
+      sts_f32(val + pos * sb, cv); sts_s32(idx + pos * sb, ci);
       pos = ch;
     }
-    val[pos * stride] = v; idx[pos * stride] = j;
-    st.thr = val[0];
+    sts_f32(val + pos * sb, v); sts_s32(idx + pos * sb, j);
+    st.thr = lds_f32(val);
   }
 }
 
 // Out-of-line variant for call sites that must not grow (hot loops with many live registers).
-static __device__ __noinline__ ListState list_insert(float* val, int* idx, int stride, int kc, ListState st, float v, int j) {
-  list_push(val, idx, stride, kc, st, v, j);
+static __device__ __noinline__ ListState list_insert(uint32_t val, uint32_t idx, uint32_t sb, int kc, ListState st, float v, int j) {
+  list_push(val, idx, sb, kc, st, v, j);
   return st;
 }
 

@@ -36,7 +36,7 @@ constexpr int F16_UMMA_K = 16;
 constexpr int F16_THREADS = 320;
 constexpr int F16_A_KBLOCK = F16_BM * F16_BK * 2;   // 16 KB
 constexpr int F16_SMEM_MAX = 232448;
-constexpr int F16_SMEM_FIXED = 1024 + 512;          // alignment slack + barriers / tmem slot
+constexpr int F16_SMEM_FIXED = 1024 + 512 + 1024;   // alignment slack + barriers / tmem slot + shared thresholds
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -98,7 +98,8 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   unsigned char* b_base = a_base + (size_t)kblocks * F16_A_KBLOCK;       // stages * B_STAGE ring
   float* lval = reinterpret_cast<float*>(b_base + (size_t)stages * B_STAGE);   // [2][kc][128]
   int* lidx = reinterpret_cast<int*>(lval + (size_t)2 * kc * F16_BM);           // [2][kc][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lidx + (size_t)2 * kc * F16_BM);
+  float* thr_sh = reinterpret_cast<float*>(lidx + (size_t)2 * kc * F16_BM);   // [2][128] list thresholds, shared by the warp pair
+  uint64_t* bars = reinterpret_cast<uint64_t*>(thr_sh + 2 * F16_BM);
   uint64_t* full_bar = bars;                      // [stages]
   uint64_t* empty_bar = bars + stages;            // [stages]
   uint64_t* tfull_bar = bars + 2 * stages;        // [2]
@@ -189,7 +190,16 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const bool row_ok = q0 + r_in_tile < nq;
     float* my_val = lval + (size_t)half * kc * F16_BM + r_in_tile;
     int* my_idx = lidx + (size_t)half * kc * F16_BM + r_in_tile;
+    const uint32_t my_val_s = smem_addr(my_val), my_idx_s = smem_addr(my_idx);
+    // The two warps of a lane quarter keep separate lists for the same rows but share their thresholds:
+    // a column is kept only if it beats max(own, partner) threshold.  Sound for the certification in
+    // knn_select.cu: every column either warp discards scores <= the larger of the two final list minima.
+    const uint32_t my_thr_s = smem_addr(thr_sh + half * F16_BM + r_in_tile);
+    const uint32_t other_thr_s = smem_addr(thr_sh + (half ^ 1) * F16_BM + r_in_tile);
+    sts_f32(my_thr_s, -INFINITY);
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only
     ListState st = list_init();
+    float thr = -INFINITY;                           // effective threshold = max(own list, partner list)
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const uint32_t tph = (uint32_t)(t >> 1) & 1u;
@@ -202,6 +212,7 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       for (int ch = half; ch < BN / 32; ch += 2) {
         float r[32];
         tc_ld32(taddr0 + (uint32_t)(ch * 32), r);
+        thr = fmaxf(thr, lds_f32(other_thr_s));
         tc_wait_ld();
         const int jb = db0 + ch * 32;
         if (partial) {
@@ -216,28 +227,30 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           gm[g] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
         }
         const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-        if (row_ok && mx > st.thr) {
+        if (row_ok && mx > thr) {
           // rare path, all register-resident: per group of 8 columns, repeatedly pick the first column
           // (index order) that still beats the running threshold and push it into the heap
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            if (gm[g] > st.thr) {
+            if (gm[g] > thr) {
               int last = -1;
               while (true) {
                 float cv = -INFINITY;
                 int cc = -1;
 #pragma unroll
                 for (int c = 7; c >= 0; --c) {
-                  const bool p = (c > last) && (r[g * 8 + c] > st.thr);
+                  const bool p = (c > last) && (r[g * 8 + c] > thr);
                   cv = p ? r[g * 8 + c] : cv;
                   cc = p ? c : cc;
                 }
                 if (cc < 0) break;
-                list_push(my_val, my_idx, F16_BM, kc, st, cv, jb + g * 8 + cc);
+                list_push(my_val_s, my_idx_s, F16_BM * 4, kc, st, cv, jb + g * 8 + cc);
+                thr = fmaxf(thr, st.thr);
                 last = cc;
               }
             }
           }
+          sts_f32(my_thr_s, st.thr);
         }
       }
       // this warp has read all of its columns of the buffer: hand it back to the MMA issuer

@@ -166,6 +166,7 @@ knn_cosine_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
     const bool row_ok = q0 + r_in_tile < nq;
     float* my_val = lval + r_in_tile;
     int* my_idx = lidx + r_in_tile;
+    const uint32_t my_val_s = smem_addr(my_val), my_idx_s = smem_addr(my_idx);
     ListState st = list_init();
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
@@ -215,7 +216,7 @@ knn_cosine_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
                   cc = p ? c : cc;
                 }
                 if (cc < 0) break;
-                list_push(my_val, my_idx, TC_BM, kc, st, cv, jb + g * 8 + cc);
+                list_push(my_val_s, my_idx_s, TC_BM * 4, kc, st, cv, jb + g * 8 + cc);
                 last = cc;
               }
             }

@@ -70,13 +70,13 @@ knn_simt_kernel(const float* __restrict__ Q, const float* __restrict__ Qlo, int 
 
   const int tid = threadIdx.x;
   const int nrows = row_list ? min(__ldg(row_count), nq) : nq;
-  const int q0 = blockIdx.x * ST_TQ;
-  if (q0 >= nrows) return;
   const int split = blockIdx.y;
   const int db_begin = split * db_per_split;
   const int db_end = min(ndb, db_begin + db_per_split);
   const int ty = tid >> 4, tx = tid & 15;
 
+  // grid-stride over query tiles: the exact-fallback launch does not know its row count on the host
+  for (int q0 = blockIdx.x * ST_TQ; q0 < nrows; q0 += gridDim.x * ST_TQ) {
   ListState st = list_init();
   for (int t0 = db_begin; t0 < db_end; t0 += ST_TD) {
     float acc[4][4];
@@ -125,7 +125,7 @@ knn_simt_kernel(const float* __restrict__ Q, const float* __restrict__ Qlo, int 
       int lim = min(ST_TD, db_end - t0);
       for (int c = 0; c < lim; ++c) {
         float s = stile[tid][c];
-        if (s > st.thr) st = list_insert(lval + tid, lidx + tid, ST_TQ, kc, st, s, t0 + c);
+        if (s > st.thr) st = list_insert(smem_addr(lval + tid), smem_addr(lidx + tid), ST_TQ * 4, kc, st, s, t0 + c);
       }
     }
   }
@@ -138,13 +138,17 @@ knn_simt_kernel(const float* __restrict__ Q, const float* __restrict__ Qlo, int 
       cand_idx[base + s] = f ? lidx[s * ST_TQ + tid] : -1;
     }
   }
+  __syncthreads();
+  }  // query tiles
 }
 
 int launch_knn_simt(int mode, const float* Q, const float* Qlo, int nq, const float* DB, const float* DBlo, int ndb,
                     int d, int ld, const float* w, float bias, int apply_sigmoid, int kc, int nsplit, int db_per_split,
                     const int* row_list, const int* row_count, float* cand_val, int* cand_idx, cudaStream_t stream) {
   if (nq <= 0 || nsplit <= 0) return BGNN_OK;
-  dim3 grid((nq + ST_TQ - 1) / ST_TQ, nsplit);
+  int qtiles = (nq + ST_TQ - 1) / ST_TQ;
+  if (row_list) qtiles = qtiles < 16 ? qtiles : 16;     // fallback rows are few; CTAs stride over the list
+  dim3 grid(qtiles, nsplit);
   size_t dyn = (size_t)kc * ST_TQ * (sizeof(float) + sizeof(int));
   if (dyn > 160 * 1024) return BGNN_ERR_UNSUPPORTED;
   auto aligned = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };

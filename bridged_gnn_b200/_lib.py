@@ -32,8 +32,8 @@ SIGNATURES = {
     "bgnn_edges_to_csr": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bgnn_spmm_csr_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "bgnn_gatv2_fwd_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp, _vp]),
-    "bgnn_gatv2_bwd_workspace_bytes": (_sz, [_i64, _i32]),
-    "bgnn_gatv2_bwd_f32": (_i32, [_vp] * 9 + [_f32, _i64, _i32] + [_vp] * 9 + [_sz, _vp]),
+    "bgnn_gatv2_bwd_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "bgnn_gatv2_bwd_f32": (_i32, [_vp] * 5 + [_i64] + [_vp] * 5 + [_f32, _i64, _i32] + [_vp] * 9 + [_sz, _vp]),
 }
 
 _lib = None

@@ -136,18 +136,27 @@ int launch_gatv2_fwd(const int* rowptr, const int* col, const uint8_t* dst_is_sr
 }
 
 // ------------------------------------------------------------------------------------------ backward
-// Pass A: per destination row.  Writes D[i] = gout_i . out_i, the destination-side gradient into
-// gHs/gHt (and zero into the other one), and per-CTA partial sums of d a_f into ga_part[cta][2][c].
+// Pass A: per destination row (CSR).  Recomputes the scores from the saved (max, sum), and writes
+//   * the destination-side gradient of row i into gHs (source-domain row) or gHt (target-domain row),
+//   * per-CTA partial sums of d a_f into ga_part[cta][2][c],
+//   * one record per edge, stored at the edge's slot in the TRANSPOSED CSR so that pass B streams them:
+//       ea   = alpha_ij with the destination's domain in the sign bit (negative: source-domain destination)
+//       eds  = d score_ij = alpha_ij (gout_i . H_j - gout_i . out_i)
+//       emask[CW] = bit c set iff H_j[c] + H_i[c] > 0 (the leaky-relu branch)
+// so that pass B needs neither H[dst] nor the softmax statistics again.
 template <int VEC, int G, int CH>
 __global__ void __launch_bounds__(256)
-gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const uint8_t* __restrict__ dst_is_src,
-                     const float* __restrict__ Hs, const float* __restrict__ Ht, const float* __restrict__ af_t2s,
-                     const float* __restrict__ af_s2t, float slope, long long n, int c, const float* __restrict__ out,
-                     const float* __restrict__ row_max, const float* __restrict__ row_sum,
-                     const float* __restrict__ gout, float* __restrict__ gHs, float* __restrict__ gHt,
-                     float* __restrict__ D, float* __restrict__ ga_part) {
+gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ csr_to_csc,
+                     const uint8_t* __restrict__ dst_is_src, const float* __restrict__ Hs, const float* __restrict__ Ht,
+                     const float* __restrict__ af_t2s, const float* __restrict__ af_s2t, float slope, long long n, int c,
+                     int cw, const float* __restrict__ out, const float* __restrict__ row_max,
+                     const float* __restrict__ row_sum, const float* __restrict__ gout, float* __restrict__ gHs,
+                     float* __restrict__ gHt, float* __restrict__ ea, float* __restrict__ eds,
+                     unsigned* __restrict__ emask, float* __restrict__ ga_part) {
   extern __shared__ float s_ga[];  // [groups][2][c]: every group owns a slice -> no atomics, fixed order
   constexpr int GROUPS = 256 / G;
+  constexpr int LPW = 32 / VEC;                    // lanes that share one 32-column mask word
+  constexpr int WG = (G < LPW) ? G : LPW;          // lanes of this group that share a word
   for (int t = threadIdx.x; t < GROUPS * 2 * c; t += blockDim.x) s_ga[t] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -182,9 +191,13 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
     const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     constexpr int U = 2;
     for (int e = beg; e < end; e += U) {
-      int j[U];
+      int j[U], pos[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) j[u] = (e + u < end) ? __ldg(col + e + u) : -1;
+      for (int u = 0; u < U; ++u) {
+        const bool ok = e + u < end;
+        j[u] = ok ? __ldg(col + e + u) : -1;
+        pos[u] = ok ? __ldg(csr_to_csc + e + u) : 0;
+      }
       Chunk<VEC> hj[U][CH];
 #pragma unroll
       for (int u = 0; u < U; ++u)
@@ -194,42 +207,53 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         float sp = 0.f, dp = 0.f;
+        unsigned bits[CH];
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch)
+        for (int ch = 0; ch < CH; ++ch) {
+          bits[ch] = 0u;
+          const int b0 = ((ch * G + lane_g) * VEC) & 31;
 #pragma unroll
           for (int i = 0; i < VEC; ++i) {
-            sp = fmaf(av[ch].v[i], lrelu(hj[u][ch].v[i] + hi[ch].v[i], slope), sp);
+            const float t = hj[u][ch].v[i] + hi[ch].v[i];
+            sp = fmaf(av[ch].v[i], lrelu(t, slope), sp);
             dp = fmaf(go[ch].v[i], hj[u][ch].v[i], dp);
+            bits[ch] |= (t > 0.f ? 1u : 0u) << (b0 + i);
           }
+        }
         sp = gsum<G>(sp, mask);
         dp = gsum<G>(dp, mask);
-        float alpha = (j[u] >= 0) ? expf(sp - m) * inv : 0.f;
-        float ds = alpha * (dp - Di);
+        const float alpha = (j[u] >= 0) ? expf(sp - m) * inv : 0.f;
+        const float ds = alpha * (dp - Di);
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch)
+        for (int ch = 0; ch < CH; ++ch) {
+#pragma unroll
+          for (int o = WG / 2; o > 0; o >>= 1) bits[ch] |= __shfl_xor_sync(mask, bits[ch], o);
+          const int w = ((ch * G + lane_g) * VEC) >> 5;
+          if (j[u] >= 0 && (lane_g % WG) == 0 && w < cw) emask[(long long)pos[u] * cw + w] = bits[ch];
 #pragma unroll
           for (int i = 0; i < VEC; ++i) {
-            float t = hj[u][ch].v[i] + hi[ch].v[i];
+            const float t = hj[u][ch].v[i] + hi[ch].v[i];
             gi[ch].v[i] = fmaf(ds * av[ch].v[i], t > 0.f ? 1.f : slope, gi[ch].v[i]);
             ga[ch].v[i] = fmaf(ds, lrelu(t, slope), ga[ch].v[i]);
           }
+        }
+        if (j[u] >= 0 && lane_g == 0) {
+          ea[pos[u]] = is_src ? -alpha : alpha;      // -0.0f keeps the sign for alpha == 0
+          eds[pos[u]] = ds;
+        }
       }
     }
-    Chunk<VEC> zero;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) zero.v[i] = 0.f;
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch) {
       int c0 = (ch * G + lane_g) * VEC;
       st_chunk<VEC>((is_src ? gHs : gHt) + row * c + c0, gi[ch], cok[ch]);
-      st_chunk<VEC>((is_src ? gHt : gHs) + row * c + c0, zero, cok[ch]);
       if (cok[ch]) {
         float* slot = s_ga + (size_t)(threadIdx.x / G) * 2 * c + (is_src ? 0 : c) + c0;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) slot[i] = ga[ch].v[i];
+        for (int i = 0; i < VEC; ++i)
+          if (c0 + i < c) slot[i] = ga[ch].v[i];
       }
     }
-    if (lane_g == 0) D[row] = Di;
   }
   __syncthreads();
   for (int t = threadIdx.x; t < 2 * c; t += blockDim.x) {
@@ -257,95 +281,101 @@ reduce_partials_kernel(const float* __restrict__ part, long long nparts, int wid
   if (threadIdx.x == 0) { if (t < c) o0[t] = red[0]; else o1[t - c] = red[0]; }
 }
 
-// Pass B: per source row j over its outgoing edges (CSC).  Adds the source-side gradient.
+// Pass B: per source row j over its outgoing edges (transposed CSR).  Streams the edge records of
+// pass A, gathers only gout[dst], and adds the source-side gradient
+//   dH[j] += alpha_ij gout_i + ds_ij a (.) lrelu'(H_j + H_i)
+// into gHs (edges into source-domain destinations) / gHt (target-domain destinations).
 template <int VEC, int G, int CH>
 __global__ void __launch_bounds__(256)
 gatv2_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restrict__ t_col,
-                     const uint8_t* __restrict__ dst_is_src, const float* __restrict__ Hs, const float* __restrict__ Ht,
-                     const float* __restrict__ af_t2s, const float* __restrict__ af_s2t, float slope, long long n, int c,
-                     const float* __restrict__ row_max, const float* __restrict__ row_sum, const float* __restrict__ D,
+                     const uint8_t* __restrict__ dst_is_src, const float* __restrict__ af_t2s,
+                     const float* __restrict__ af_s2t, float slope, long long n, int c, int cw,
+                     const float* __restrict__ ea, const float* __restrict__ eds, const unsigned* __restrict__ emask,
                      const float* __restrict__ gout, float* __restrict__ gHs, float* __restrict__ gHt) {
-  const int lane = threadIdx.x & 31;
   const int lane_g = threadIdx.x % G;
-  const unsigned mask = group_mask<G>(lane);
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
   if (row >= n) return;
-  Chunk<VEC> hs[CH], ht[CH], as_[CH], at_[CH], gs[CH], gt[CH];
+  Chunk<VEC> as_[CH], at_[CH], gs[CH], gt[CH];
   bool cok[CH];
+  int wsel[CH], bsel[CH];
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) {
     int c0 = (ch * G + lane_g) * VEC;
     cok[ch] = c0 < c;
-    hs[ch] = ld_chunk<VEC>(Hs + row * c + c0, cok[ch]);
-    ht[ch] = ld_chunk<VEC>(Ht + row * c + c0, cok[ch]);
+    wsel[ch] = min(c0 >> 5, cw - 1);
+    bsel[ch] = c0 & 31;
     as_[ch] = ld_chunk<VEC>(af_t2s + c0, cok[ch]);
     at_[ch] = ld_chunk<VEC>(af_s2t + c0, cok[ch]);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) { gs[ch].v[i] = 0.f; gt[ch].v[i] = 0.f; }
   }
   const int beg = __ldg(t_rowptr + row), end = __ldg(t_rowptr + row + 1);
-  for (int e = beg; e < end; ++e) {
-    const int i_dst = __ldg(t_col + e);
-    const bool dsrc = dst_is_src[i_dst] != 0;
-    const float* __restrict__ H = dsrc ? Hs : Ht;
-    Chunk<VEC> hd[CH], go[CH];
+  constexpr int U = 4;
+  for (int e = beg; e < end; e += U) {
+    int i_dst[U];
+    float al[U], ds[U];
+    unsigned mk[U][CH];
+    Chunk<VEC> go[U][CH];
 #pragma unroll
-    for (int ch = 0; ch < CH; ++ch) {
-      int c0 = (ch * G + lane_g) * VEC;
-      hd[ch] = ld_chunk<VEC>(H + (long long)i_dst * c + c0, cok[ch]);
-      go[ch] = ld_chunk<VEC>(gout + (long long)i_dst * c + c0, cok[ch]);
+    for (int u = 0; u < U; ++u) {
+      const bool ok = e + u < end;
+      i_dst[u] = ok ? __ldg(t_col + e + u) : -1;
+      al[u] = ok ? __ldg(ea + e + u) : 0.f;
+      ds[u] = ok ? __ldg(eds + e + u) : 0.f;
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) mk[u][ch] = ok ? __ldg(emask + (long long)(e + u) * cw + wsel[ch]) : 0u;
     }
-    const float m = __ldg(row_max + i_dst);
-    const float inv = 1.0f / (__ldg(row_sum + i_dst) + 1e-16f);
-    const float Di = __ldg(D + i_dst);
-    float sp = 0.f, dp = 0.f;
 #pragma unroll
-    for (int ch = 0; ch < CH; ++ch)
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float hj = dsrc ? hs[ch].v[i] : ht[ch].v[i];
-        float aa = dsrc ? as_[ch].v[i] : at_[ch].v[i];
-        sp = fmaf(aa, lrelu(hj + hd[ch].v[i], slope), sp);
-        dp = fmaf(go[ch].v[i], hj, dp);
-      }
-    sp = gsum<G>(sp, mask);
-    dp = gsum<G>(dp, mask);
-    const float alpha = expf(sp - m) * inv;
-    const float ds = alpha * (dp - Di);
+      for (int ch = 0; ch < CH; ++ch)
+        go[u][ch] = ld_chunk<VEC>(gout + (long long)(i_dst[u] < 0 ? 0 : i_dst[u]) * c + (ch * G + lane_g) * VEC,
+                                  cok[ch] && i_dst[u] >= 0);
 #pragma unroll
-    for (int ch = 0; ch < CH; ++ch)
+    for (int u = 0; u < U; ++u) {
+      const bool dsrc = signbit(al[u]);
+      const float alpha = fabsf(al[u]);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float hj = dsrc ? hs[ch].v[i] : ht[ch].v[i];
-        float aa = dsrc ? as_[ch].v[i] : at_[ch].v[i];
-        float t = hj + hd[ch].v[i];
-        float g = fmaf(ds * aa, t > 0.f ? 1.f : slope, alpha * go[ch].v[i]);
-        if (dsrc) gs[ch].v[i] += g; else gt[ch].v[i] += g;
-      }
+      for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float aa = dsrc ? as_[ch].v[i] : at_[ch].v[i];
+          const float dl = ((mk[u][ch] >> (bsel[ch] + i)) & 1u) ? 1.f : slope;
+          const float g = fmaf(ds[u] * aa, dl, alpha * go[u][ch].v[i]);
+          gs[ch].v[i] += dsrc ? g : 0.f;
+          gt[ch].v[i] += dsrc ? 0.f : g;
+        }
+    }
   }
+  const bool me_src = dst_is_src[row] != 0;
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) {
     int c0 = (ch * G + lane_g) * VEC;
     if (!cok[ch]) continue;
-    Chunk<VEC> ps = ld_chunk<VEC>(gHs + row * c + c0, true);   // destination-side part from pass A
-    Chunk<VEC> pt = ld_chunk<VEC>(gHt + row * c + c0, true);
+    // destination-side part of this row from pass A lives in the array of the row's own domain
+    Chunk<VEC> own = ld_chunk<VEC>((me_src ? gHs : gHt) + row * c + c0, true);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { ps.v[i] += gs[ch].v[i]; pt.v[i] += gt[ch].v[i]; }
-    st_chunk<VEC>(gHs + row * c + c0, ps, true);
-    st_chunk<VEC>(gHt + row * c + c0, pt, true);
+    for (int i = 0; i < VEC; ++i) {
+      gs[ch].v[i] += me_src ? own.v[i] : 0.f;
+      gt[ch].v[i] += me_src ? 0.f : own.v[i];
+    }
+    st_chunk<VEC>(gHs + row * c + c0, gs[ch], true);
+    st_chunk<VEC>(gHt + row * c + c0, gt[ch], true);
   }
 }
 
 static long long bwd_blocks(long long n, int g) { return (n * g + 255) / 256; }
 
-size_t gatv2_bwd_workspace_bytes(long long n, int c) {
+size_t gatv2_bwd_workspace_bytes(long long n, long long e, int c) {
   int vec, g, ch;
   if (!pick_row_config(c, vec, g, ch)) return 0;
-  return align_up((size_t)n * sizeof(float), 256) + align_up((size_t)bwd_blocks(n, g) * 2 * c * sizeof(float), 256) + 512;
+  const int cw = (c + 31) / 32;
+  return align_up((size_t)bwd_blocks(n, g) * 2 * c * sizeof(float), 256) + 2 * align_up((size_t)e * sizeof(float), 256) +
+         align_up((size_t)e * cw * sizeof(unsigned), 256) + 1024;
 }
 
-int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col,
-                     const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
+int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csr_to_csc,
+                     long long e, const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
                      const float* af_s2t, float slope, long long n, int c, const float* out, const float* row_max,
                      const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
                      float* g_af_s2t, void* ws, size_t ws_bytes, cudaStream_t stream) {
@@ -353,22 +383,25 @@ int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, con
   int vec, g, ch;
   if (!pick_row_config(c, vec, g, ch)) return BGNN_ERR_UNSUPPORTED;
   long long blocks = bwd_blocks(n, g);
+  const int cw = (c + 31) / 32;
   Workspace w(ws, ws_bytes);
-  float* D = w.take<float>(n);
   float* part = w.take<float>(blocks * 2 * c);
+  float* ea = w.take<float>(e);
+  float* eds = w.take<float>(e);
+  unsigned* emask = w.take<unsigned>(e * cw);
   if (!w.ok()) return BGNN_ERR_WORKSPACE;
   size_t dyn = (size_t)(256 / g) * 2 * c * sizeof(float);
 #define CALL(V, G_, C_)                                                                                            \
-  gatv2_bwd_dst_kernel<V, G_, C_><<<(unsigned)blocks, 256, dyn, stream>>>(rowptr, col, dst_is_src, Hs, Ht, af_t2s, \
-      af_s2t, slope, n, c, out, row_max, row_sum, gout, gHs, gHt, D, part)
+  gatv2_bwd_dst_kernel<V, G_, C_><<<(unsigned)blocks, 256, dyn, stream>>>(rowptr, col, csr_to_csc, dst_is_src, Hs, \
+      Ht, af_t2s, af_s2t, slope, n, c, cw, out, row_max, row_sum, gout, gHs, gHt, ea, eds, emask, part)
   BGNN_ROW_DISPATCH(vec, g, ch, CALL);
 #undef CALL
   BGNN_LAUNCH_CHECK();
   reduce_partials_kernel<<<2 * c, 256, 0, stream>>>(part, blocks, 2 * c, g_af_t2s, g_af_s2t, c);
   BGNN_LAUNCH_CHECK();
 #define CALL(V, G_, C_)                                                                                            \
-  gatv2_bwd_src_kernel<V, G_, C_><<<(unsigned)blocks, 256, 0, stream>>>(t_rowptr, t_col, dst_is_src, Hs, Ht,       \
-      af_t2s, af_s2t, slope, n, c, row_max, row_sum, D, gout, gHs, gHt)
+  gatv2_bwd_src_kernel<V, G_, C_><<<(unsigned)blocks, 256, 0, stream>>>(t_rowptr, t_col, dst_is_src, af_t2s,      \
+      af_s2t, slope, n, c, cw, ea, eds, emask, gout, gHs, gHt)
   BGNN_ROW_DISPATCH(vec, g, ch, CALL);
 #undef CALL
   BGNN_LAUNCH_CHECK();

@@ -122,12 +122,23 @@ class CSRGraph:
         self.rowptr, self.col, self.perm, self.e = edges_to_csr(edge_index[0], edge_index[1], self.n)
         self._t = None
         self._deg = None
+        self._csr_to_csc = None
 
     @property
     def t(self):
         if self._t is None:
             self._t = edges_to_csr(self.edge_index[1], self.edge_index[0], self.n)[:3]
         return self._t
+
+    @property
+    def csr_to_csc(self):
+        """int32 [e]: slot of every CSR edge in the transposed CSR (both index the same input edge list)."""
+        if self._csr_to_csc is None:
+            t_perm = self.t[2]
+            inv_t = torch.empty_like(t_perm)
+            inv_t[t_perm] = torch.arange(t_perm.numel(), device=t_perm.device)
+            self._csr_to_csc = inv_t[self.perm].to(torch.int32).contiguous()
+        return self._csr_to_csc
 
     @property
     def deg(self):
@@ -232,9 +243,10 @@ class _GatAggFn(torch.autograd.Function):
         gout = gout.to(torch.float32).contiguous()
         gHs, gHt = torch.empty_like(Hs), torch.empty_like(Ht)
         ga1, ga2 = torch.empty_like(a1), torch.empty_like(a2)
-        ws = _lib.workspace(lib.bgnn_gatv2_bwd_workspace_bytes(n, c), dev)
+        ws = _lib.workspace(lib.bgnn_gatv2_bwd_workspace_bytes(n, g.e, c), dev)
         with _lib.call("bgnn_gatv2_bwd_f32", "bgnn_gatv2_bwd_f32[c=%d]" % c):
             _lib.check(lib.bgnn_gatv2_bwd_f32(_lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(t_rowptr), _lib.ptr(t_col),
+                                              _lib.ptr(g.csr_to_csc, torch.int32), g.e,
                                               _lib.ptr(ctx.dst_is_src), _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(a1),
                                               _lib.ptr(a2), ctx.slope, n, c, _lib.ptr(out), _lib.ptr(row_max),
                                               _lib.ptr(row_sum), _lib.ptr(gout), _lib.ptr(gHs), _lib.ptr(gHt),

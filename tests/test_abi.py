@@ -49,7 +49,7 @@ def test_workspace_queries_are_host_only(lib):
     assert lib.bgnn_knn_cosine_workspace_bytes(10, 5, 16, 6, 0) == 0      # k > ndb
     assert lib.bgnn_knn_addrelu_workspace_bytes(591, 2817, 128, 20) > 0
     assert lib.bgnn_edges_to_csr_workspace_bytes(37522) > 37522 * 8
-    assert lib.bgnn_gatv2_bwd_workspace_bytes(3408, 64) > 0
+    assert lib.bgnn_gatv2_bwd_workspace_bytes(3408, 37522, 64) > 37522 * 16
 
 
 def test_invalid_arguments_rejected_before_any_launch(lib):

@@ -151,8 +151,8 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
                      const float* __restrict__ af_t2s, const float* __restrict__ af_s2t, float slope, long long n, int c,
                      int cw, const float* __restrict__ out, const float* __restrict__ row_max,
                      const float* __restrict__ row_sum, const float* __restrict__ gout, float* __restrict__ gHs,
-                     float* __restrict__ gHt, float* __restrict__ ea, float* __restrict__ eds,
-                     unsigned* __restrict__ emask, float* __restrict__ ga_part) {
+                     float* __restrict__ gHt, unsigned* __restrict__ erec, unsigned* __restrict__ emask,
+                     float* __restrict__ ga_part) {
   extern __shared__ float s_ga[];  // [groups][2][c]: every group owns a slice -> no atomics, fixed order
   constexpr int GROUPS = 256 / G;
   constexpr int LPW = 32 / VEC;                    // lanes that share one 32-column mask word
@@ -228,8 +228,6 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
         for (int ch = 0; ch < CH; ++ch) {
 #pragma unroll
           for (int o = WG / 2; o > 0; o >>= 1) bits[ch] |= __shfl_xor_sync(mask, bits[ch], o);
-          const int w = ((ch * G + lane_g) * VEC) >> 5;
-          if (j[u] >= 0 && (lane_g % WG) == 0 && w < cw) emask[(long long)pos[u] * cw + w] = bits[ch];
 #pragma unroll
           for (int i = 0; i < VEC; ++i) {
             const float t = hj[u][ch].v[i] + hi[ch].v[i];
@@ -237,9 +235,23 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
             ga[ch].v[i] = fmaf(ds, lrelu(t, slope), ga[ch].v[i]);
           }
         }
-        if (j[u] >= 0 && lane_g == 0) {
-          ea[pos[u]] = is_src ? -alpha : alpha;      // -0.0f keeps the sign for alpha == 0
-          eds[pos[u]] = ds;
+        const float ea = is_src ? -alpha : alpha;      // -0.0f keeps the sign for alpha == 0
+        if (cw <= 2) {
+          // c <= 64: the whole record is one 16-byte store by the group's first lane
+          unsigned w0 = bits[0], w1 = 0u;
+          if (CH == 1) { if (G * VEC > 32) w1 = __shfl_sync(mask, bits[0], (lane / G) * G + (G > LPW ? LPW : 0)); }
+          else w1 = bits[CH > 1 ? 1 : 0];
+          if (j[u] >= 0 && lane_g == 0)
+            *reinterpret_cast<uint4*>(erec + (long long)pos[u] * 4) =
+                make_uint4(__float_as_uint(ea), __float_as_uint(ds), w0, w1);
+        } else {
+          if (j[u] >= 0 && lane_g == 0)
+            *reinterpret_cast<float2*>(erec + (long long)pos[u] * 2) = make_float2(ea, ds);
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch) {
+            const int w = ((ch * G + lane_g) * VEC) >> 5;
+            if (j[u] >= 0 && (lane_g % WG) == 0 && w < cw) emask[(long long)pos[u] * cw + w] = bits[ch];
+          }
         }
       }
     }
@@ -290,7 +302,7 @@ __global__ void __launch_bounds__(256)
 gatv2_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restrict__ t_col,
                      const uint8_t* __restrict__ dst_is_src, const float* __restrict__ af_t2s,
                      const float* __restrict__ af_s2t, float slope, long long n, int c, int cw,
-                     const float* __restrict__ ea, const float* __restrict__ eds, const unsigned* __restrict__ emask,
+                     const unsigned* __restrict__ erec, const unsigned* __restrict__ emask,
                      const float* __restrict__ gout, float* __restrict__ gHs, float* __restrict__ gHt) {
   const int lane_g = threadIdx.x % G;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -320,10 +332,19 @@ gatv2_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restrict__ t
     for (int u = 0; u < U; ++u) {
       const bool ok = e + u < end;
       i_dst[u] = ok ? __ldg(t_col + e + u) : -1;
-      al[u] = ok ? __ldg(ea + e + u) : 0.f;
-      ds[u] = ok ? __ldg(eds + e + u) : 0.f;
+      if (cw <= 2) {
+        const uint4 r4 = ok ? __ldg(reinterpret_cast<const uint4*>(erec) + e + u) : make_uint4(0u, 0u, 0u, 0u);
+        al[u] = __uint_as_float(r4.x);
+        ds[u] = __uint_as_float(r4.y);
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch) mk[u][ch] = ok ? __ldg(emask + (long long)(e + u) * cw + wsel[ch]) : 0u;
+        for (int ch = 0; ch < CH; ++ch) mk[u][ch] = wsel[ch] ? r4.w : r4.z;
+      } else {
+        const float2 r2 = ok ? __ldg(reinterpret_cast<const float2*>(erec) + e + u) : make_float2(0.f, 0.f);
+        al[u] = r2.x;
+        ds[u] = r2.y;
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) mk[u][ch] = ok ? __ldg(emask + (long long)(e + u) * cw + wsel[ch]) : 0u;
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -370,8 +391,9 @@ size_t gatv2_bwd_workspace_bytes(long long n, long long e, int c) {
   int vec, g, ch;
   if (!pick_row_config(c, vec, g, ch)) return 0;
   const int cw = (c + 31) / 32;
-  return align_up((size_t)bwd_blocks(n, g) * 2 * c * sizeof(float), 256) + 2 * align_up((size_t)e * sizeof(float), 256) +
-         align_up((size_t)e * cw * sizeof(unsigned), 256) + 1024;
+  // records: 16 B per edge when the mask fits two words, else (alpha, dscore) pairs + a mask array
+  const size_t rec = cw <= 2 ? (size_t)e * 16 : (size_t)e * 8 + align_up((size_t)e * cw * sizeof(unsigned), 256);
+  return align_up((size_t)bwd_blocks(n, g) * 2 * c * sizeof(float), 256) + align_up(rec, 256) + 1024;
 }
 
 int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csr_to_csc,
@@ -386,14 +408,13 @@ int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, con
   const int cw = (c + 31) / 32;
   Workspace w(ws, ws_bytes);
   float* part = w.take<float>(blocks * 2 * c);
-  float* ea = w.take<float>(e);
-  float* eds = w.take<float>(e);
-  unsigned* emask = w.take<unsigned>(e * cw);
+  unsigned* erec = w.take<unsigned>(cw <= 2 ? e * 4 : e * 2);
+  unsigned* emask = cw <= 2 ? nullptr : w.take<unsigned>(e * cw);
   if (!w.ok()) return BGNN_ERR_WORKSPACE;
   size_t dyn = (size_t)(256 / g) * 2 * c * sizeof(float);
 #define CALL(V, G_, C_)                                                                                            \
   gatv2_bwd_dst_kernel<V, G_, C_><<<(unsigned)blocks, 256, dyn, stream>>>(rowptr, col, csr_to_csc, dst_is_src, Hs, \
-      Ht, af_t2s, af_s2t, slope, n, c, cw, out, row_max, row_sum, gout, gHs, gHt, ea, eds, emask, part)
+      Ht, af_t2s, af_s2t, slope, n, c, cw, out, row_max, row_sum, gout, gHs, gHt, erec, emask, part)
   BGNN_ROW_DISPATCH(vec, g, ch, CALL);
 #undef CALL
   BGNN_LAUNCH_CHECK();
@@ -401,7 +422,7 @@ int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, con
   BGNN_LAUNCH_CHECK();
 #define CALL(V, G_, C_)                                                                                            \
   gatv2_bwd_src_kernel<V, G_, C_><<<(unsigned)blocks, 256, 0, stream>>>(t_rowptr, t_col, dst_is_src, af_t2s,      \
-      af_s2t, slope, n, c, cw, ea, eds, emask, gout, gHs, gHt)
+      af_s2t, slope, n, c, cw, erec, emask, gout, gHs, gHt)
   BGNN_ROW_DISPATCH(vec, g, ch, CALL);
 #undef CALL
   BGNN_LAUNCH_CHECK();

@@ -231,6 +231,7 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     from bridged_gnn_b200 import _lib, ops
+    from bridged_gnn_b200 import dist as bdist
     from bridged_gnn_b200.data import Data, to_undirected
     from bridged_gnn_b200.models import KTGNN_no_complement
 
@@ -278,13 +279,10 @@ def run_ours(args):
     # ---- phase A: bridged-graph build ------------------------------------------------------------------
     def build(us, ut):
         idx, val, gap, stats = ops.knn_cosine(ut, us, K_CROSS, normalize=True, apply_sigmoid=True, algo=args.knn_algo)
-        if world > 1:   # per-shard kNN lists -> every rank (NCCL all-gather over NVLink)
-            gi = torch.empty((world,) + idx.shape, dtype=idx.dtype, device=dev)
-            gv = torch.empty((world,) + val.shape, dtype=val.dtype, device=dev)
-            dist.all_gather_into_tensor(gi, idx)
-            dist.all_gather_into_tensor(gv, val)
-        to = torch.arange(NT, device=dev).unsqueeze(1).expand(NT, K_CROSS)
-        edges = torch.stack((idx.reshape(-1), to.reshape(-1)), 0)
+        if world > 1:   # per-shard kNN lists -> every rank (one NCCL all-gather each, over NVLink)
+            bdist.all_gather_rows(idx, NT * world)
+            bdist.all_gather_rows(val, NT * world)
+        edges = bdist.edges_from_topk(idx)       # this rank's shard of the edge list (local target ids)
         return idx, val, gap, stats, edges
 
     clocks = ClockSampler(local)
@@ -331,11 +329,13 @@ def run_ours(args):
                                 need_complement=False, dropout=0.0).to(dev)
     model.train()
     nll = torch.nn.functional.nll_loss
+    # == nll_loss(out[train_mask], y[train_mask]) (main_graph_knowledge_transfer.py:57-59) without the boolean gathers
+    y_train = torch.where(cm, y, torch.full_like(y, -100))
 
     def train_step():
         model.zero_grad(set_to_none=True)
         lb, lt, ltt, _ = model(data)
-        loss = nll(lb[cm], y[cm]) + nll(lt[cm], y[cm]) + nll(ltt[cm], y[cm])
+        loss = nll(lb, y_train) + nll(lt, y_train) + nll(ltt, y_train)
         loss.backward()
         return loss
 
@@ -370,8 +370,7 @@ def run_ours(args):
         model.edge_index = None        # a new graph arrives: re-partition, rebuild CSR
         model.zero_grad(set_to_none=True)
         lb, lt, ltt, _ = model(d)
-        c = d.central_mask
-        loss = nll(lb[c], y[c]) + nll(lt[c], y[c]) + nll(ltt[c], y[c])
+        loss = nll(lb, y_train) + nll(lt, y_train) + nll(ltt, y_train)
         loss.backward()
         return lb.detach().cpu(), lt.detach().cpu(), ltt.detach().cpu(), loss.item()
     e2e_ms = timed(e2e_step, max(2, K // 2), 1)

@@ -200,6 +200,49 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only
     ListState st = list_init();
     float thr = -INFINITY;                           // effective threshold = max(own list, partner list)
+    bool partial = false;
+    // one 32-column chunk held in registers: group maxima vs the running threshold; the rare path stays in
+    // registers too -- per group of 8 columns, pick the first column (index order) that beats the threshold,
+    // push it into the heap, and rescan only if the group held more than one candidate
+    auto process_chunk = [&](float (&r)[32], int jb) {
+      if (partial) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) r[c] = (jb + c < ndb) ? r[c] : -INFINITY;
+      }
+      float gm[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float m01 = fmaxf(r[g * 8 + 0], r[g * 8 + 1]), m23 = fmaxf(r[g * 8 + 2], r[g * 8 + 3]);
+        float m45 = fmaxf(r[g * 8 + 4], r[g * 8 + 5]), m67 = fmaxf(r[g * 8 + 6], r[g * 8 + 7]);
+        gm[g] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+      }
+      const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+      if (row_ok && mx > thr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (gm[g] > thr) {
+            int last = -1;
+            while (true) {
+              float cv = -INFINITY;
+              int cc = -1, cnt = 0;
+#pragma unroll
+              for (int c = 7; c >= 0; --c) {
+                const bool p = (c > last) && (r[g * 8 + c] > thr);
+                cv = p ? r[g * 8 + c] : cv;
+                cc = p ? c : cc;
+                cnt += p ? 1 : 0;
+              }
+              if (cc < 0) break;
+              list_push(my_val_s, my_idx_s, F16_BM * 4, kc, st, cv, jb + g * 8 + cc);
+              thr = fmaxf(thr, st.thr);
+              if (cnt == 1) break;
+              last = cc;
+            }
+          }
+        }
+        sts_f32(my_thr_s, st.thr);
+      }
+    };
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const uint32_t tph = (uint32_t)(t >> 1) & 1u;
@@ -207,56 +250,31 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       tc_fence_after();
       const int db0 = (tile_begin + t) * BN;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
-      const bool partial = db0 + BN > ndb;          // only the last db tile has zero-filled columns
+      partial = db0 + BN > ndb;                     // only the last db tile has zero-filled columns
+      // Software pipeline over this warp's chunks (half, half+2, ...): the tcgen05.ld of the next chunk is
+      // in flight while the current one is reduced.  The TMEM buffer goes back to the MMA issuer as soon as
+      // the last chunk has landed in registers.
+      constexpr int NCH = BN / 64;                  // chunks per warp per tile (even)
+      float ra[32], rb[32];
+      tc_ld32(taddr0 + (uint32_t)(half * 32), ra);
 #pragma unroll 1
-      for (int ch = half; ch < BN / 32; ch += 2) {
-        float r[32];
-        tc_ld32(taddr0 + (uint32_t)(ch * 32), r);
-        thr = fmaxf(thr, lds_f32(other_thr_s));
+      for (int i = 0; i < NCH; i += 2) {
+        const int ch_a = half + 2 * i, ch_b = ch_a + 2;
         tc_wait_ld();
-        const int jb = db0 + ch * 32;
-        if (partial) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = (jb + c < ndb) ? r[c] : -INFINITY;
+        tc_ld32(taddr0 + (uint32_t)(ch_b * 32), rb);
+        thr = fmaxf(thr, lds_f32(other_thr_s));
+        process_chunk(ra, db0 + ch_a * 32);
+        tc_wait_ld();
+        if (i + 2 < NCH) {
+          tc_ld32(taddr0 + (uint32_t)((ch_b + 2) * 32), ra);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
         }
-        float gm[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float m01 = fmaxf(r[g * 8 + 0], r[g * 8 + 1]), m23 = fmaxf(r[g * 8 + 2], r[g * 8 + 3]);
-          float m45 = fmaxf(r[g * 8 + 4], r[g * 8 + 5]), m67 = fmaxf(r[g * 8 + 6], r[g * 8 + 7]);
-          gm[g] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
-        }
-        const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-        if (row_ok && mx > thr) {
-          // rare path, all register-resident: per group of 8 columns, repeatedly pick the first column
-          // (index order) that still beats the running threshold and push it into the heap
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (gm[g] > thr) {
-              int last = -1;
-              while (true) {
-                float cv = -INFINITY;
-                int cc = -1;
-#pragma unroll
-                for (int c = 7; c >= 0; --c) {
-                  const bool p = (c > last) && (r[g * 8 + c] > thr);
-                  cv = p ? r[g * 8 + c] : cv;
-                  cc = p ? c : cc;
-                }
-                if (cc < 0) break;
-                list_push(my_val_s, my_idx_s, F16_BM * 4, kc, st, cv, jb + g * 8 + cc);
-                thr = fmaxf(thr, st.thr);
-                last = cc;
-              }
-            }
-          }
-          sts_f32(my_thr_s, st.thr);
-        }
+        thr = fmaxf(thr, lds_f32(other_thr_s));
+        process_chunk(rb, db0 + ch_b * 32);
       }
-      // this warp has read all of its columns of the buffer: hand it back to the MMA issuer
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
     }
     if (row_ok) {
       const long long base = (((long long)split * 2 + half) * nq + (q0 + r_in_tile)) * kc;

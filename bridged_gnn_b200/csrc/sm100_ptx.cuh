@@ -17,11 +17,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug turns into a trap (sticky launch error) instead of a hung GPU.
+// Bounded wait: a protocol bug turns into a trap (sticky launch error) instead of a hung GPU.  try_wait
+// suspends the warp in hardware for a while before reporting failure, so the loop is short; the clock is
+// consulted only every 64 Ki failed probes to keep the spin path at a handful of instructions.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   long long t0 = 0;
-  for (uint32_t spins = 0;; ++spins) {
+  for (uint32_t spins = 1;; ++spins) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -30,8 +32,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
-    if (spins == 1024) t0 = clock64();
-    if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 8000000000ll) __trap();
+    if ((spins & 0xffffu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ll) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {

@@ -9,22 +9,20 @@
 // at half the operand bytes and twice the MMA rate).  For unit rows a, b with fp16 roundings ha, hb:
 //     |a.b - ha.hb| <= 2^-10 sum|a_i||b_i| + 2^-25 (sum|a_i| + sum|b_i|) + O(2^-22)  <=  2^-10 + 2^-24 sqrt(d)
 // so the approximate score is within delta_f16(d) of the exact fp32 cosine.  The kernel only NOMINATES
-// candidates (one list of KC per row and db split); knn_select.cu re-scores
+// candidates (two lists of KC per row: one per epilogue warp of a lane quarter); knn_select.cu re-scores
 // them exactly in fp32 with the reference fmaf chain, selects under the parity key and certifies the row
 // against (largest discarded approximate score + delta); uncertified rows are redone exactly on CUDA cores.
 //
-// CTA = 10 warps, one (256-query block, db split) work unit, 1 CTA / SM:
-//   warp 0     TMA producer: the query block A [256 x dpad] once (resident), then a ring of B k-blocks
-//              [128 x 64] fp16, SWIZZLE_128B
-//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer; two 128 x 128 fp32 accumulator halves
-//              (query rows 0..127 / 128..255) per step, double-buffered in TMEM (4 x 128 = 512 columns):
-//              the epilogue of step t overlaps the MMAs of step t+1
-//   warps 2-9  epilogue: warp <-> (accumulator half, TMEM lane quarter), thread <-> query row: one list
-//              per row; software-pipelined tcgen05.ld of 32 columns, FMNMX3 tree against the running
-//              threshold, register-resident rare path into a thread-private heap in shared memory
+// CTA = 10 warps, one (128-query block, db split) work unit, 1 CTA / SM:
+//   warp 0     TMA producer: the query block A [128 x dpad] once (resident), then a ring of B k-blocks
+//              [BN x 64] fp16, SWIZZLE_128B
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer; 128 x BN fp32 accumulator,
+//              double-buffered in TMEM: the epilogue of tile t overlaps the MMAs of tile t+1
+//   warps 2-9  epilogue: two warps per TMEM lane quarter, each taking every other 32-column chunk;
+//              thread <-> query row, running-threshold test on registers, rare insertion into a
+//              thread-private list in shared memory
 #include <cuda.h>
 #include <cuda_fp16.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -32,11 +30,13 @@
 
 namespace bgnn {
 
+constexpr int F16_BM = 128;
 constexpr int F16_BK = 64;                          // fp16 elements per k-block = 128 B = one swizzle row
 constexpr int F16_UMMA_K = 16;
 constexpr int F16_THREADS = 320;
+constexpr int F16_A_KBLOCK = F16_BM * F16_BK * 2;   // 16 KB
 constexpr int F16_SMEM_MAX = 232448;
-constexpr int F16_SMEM_FIXED = 1024 + 512;          // alignment slack + barriers / tmem slot
+constexpr int F16_SMEM_FIXED = 1024 + 512 + 1024;   // alignment slack + barriers / tmem slot + shared thresholds
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -85,26 +85,21 @@ int launch_normalize_f16(const float* x, long long n, int d, int ld, int ldh, in
   return BGNN_OK;
 }
 
-// CTA tile: 256 query rows (two 128-row accumulator halves, resident in smem) x 128 db rows per step.
-// Streaming 128 db rows per 2 x 128x128x128 MMA halves the L2->SM operand traffic per flop of a
-// 128 x 256 tile, which measured L2-bound (42 B/cycle/SM) on B200.
-constexpr int F16_BM2 = 256;                         // query rows per CTA
-constexpr int F16_BN = 128;                          // db rows per step
-constexpr int F16_A_KB2 = F16_BM2 * F16_BK * 2;      // 32 KB per k-block of the resident query block
-constexpr int F16_B_STAGE = F16_BN * F16_BK * 2;     // 16 KB per ring stage
-
+template <int BN>
 __global__ void __launch_bounds__(F16_THREADS, 1)
 knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
-                      int nq, int ndb, int kblocks, int tiles_total, int tiles_per_split, int kc, int stages, int dbg,
+                      int nq, int ndb, int kblocks, int tiles_total, int tiles_per_split, int kc, int stages,
                       float* __restrict__ cand_val, int* __restrict__ cand_idx) {
-  constexpr int TMEM_COLS = 512;                     // 2 buffers x 2 halves x 128 columns
+  constexpr int B_STAGE = BN * F16_BK * 2;
+  constexpr int TMEM_COLS = 2 * BN;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* a_base = smem;                                          // kblocks * 32 KB, resident
-  unsigned char* b_base = a_base + (size_t)kblocks * F16_A_KB2;          // stages * 16 KB ring
-  float* lval = reinterpret_cast<float*>(b_base + (size_t)stages * F16_B_STAGE);   // [kc][256]
-  int* lidx = reinterpret_cast<int*>(lval + (size_t)kc * F16_BM2);                  // [kc][256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lidx + (size_t)kc * F16_BM2);
+  unsigned char* a_base = smem;                                          // kblocks * 16 KB, resident
+  unsigned char* b_base = a_base + (size_t)kblocks * F16_A_KBLOCK;       // stages * B_STAGE ring
+  float* lval = reinterpret_cast<float*>(b_base + (size_t)stages * B_STAGE);   // [2][kc][128]
+  int* lidx = reinterpret_cast<int*>(lval + (size_t)2 * kc * F16_BM);           // [2][kc][128]
+  float* thr_sh = reinterpret_cast<float*>(lidx + (size_t)2 * kc * F16_BM);   // [2][128] list thresholds, shared by the warp pair
+  uint64_t* bars = reinterpret_cast<uint64_t*>(thr_sh + 2 * F16_BM);
   uint64_t* full_bar = bars;                      // [stages]
   uint64_t* empty_bar = bars + stages;            // [stages]
   uint64_t* tfull_bar = bars + 2 * stages;        // [2]
@@ -113,7 +108,7 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * F16_BM2;
+  const int q0 = blockIdx.x * F16_BM;
   const int split = blockIdx.y;
   const int tile_begin = split * tiles_per_split;
   const int tile_end = min(tiles_total, tile_begin + tiles_per_split);
@@ -141,26 +136,26 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_db) : "memory");
       const uint32_t ab = smem_u32(a_bar);
-      mbar_expect_tx(ab, (uint32_t)(kblocks * F16_A_KB2));
+      mbar_expect_tx(ab, (uint32_t)(kblocks * F16_A_KBLOCK));
       for (int kb = 0; kb < kblocks; ++kb)
-        tma_load_2d(smem_u32(a_base + (size_t)kb * F16_A_KB2), &map_q, ab, kb * F16_BK, q0);
+        tma_load_2d(smem_u32(a_base + (size_t)kb * F16_A_KBLOCK), &map_q, ab, kb * F16_BK, q0);
       int it = 0;
       for (int t = 0; t < ntiles; ++t) {
-        const int db0 = (tile_begin + t) * F16_BN;
+        const int db0 = (tile_begin + t) * BN;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t ph = (uint32_t)(it / stages) & 1u;
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
           const uint32_t fb = smem_u32(&full_bar[s]);
-          mbar_expect_tx(fb, (uint32_t)F16_B_STAGE);
-          tma_load_2d(smem_u32(b_base + (size_t)s * F16_B_STAGE), &map_db, fb, kb * F16_BK, db0);
+          mbar_expect_tx(fb, (uint32_t)B_STAGE);
+          tma_load_2d(smem_u32(b_base + (size_t)s * B_STAGE), &map_db, fb, kb * F16_BK, db0);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, F16_BN);
+      constexpr uint32_t idesc = make_idesc_f16(F16_BM, BN);
       mbar_wait(smem_u32(a_bar), 0u);
       tc_fence_after();
       int it = 0;
@@ -169,44 +164,47 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const uint32_t tph = (uint32_t)(t >> 1) & 1u;
         mbar_wait(smem_u32(&tempty_bar[buf]), tph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 2 * F16_BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t ph = (uint32_t)(it / stages) & 1u;
           mbar_wait(smem_u32(&full_bar[s]), ph);
           tc_fence_after();
-          const uint32_t a_kb = smem_u32(a_base + (size_t)kb * F16_A_KB2);
-          const uint64_t ad0 = make_kmajor_sw128_desc(a_kb);                      // query rows   0..127
-          const uint64_t ad1 = make_kmajor_sw128_desc(a_kb + 128 * 128);          // query rows 128..255
-          const uint64_t bd = make_kmajor_sw128_desc(smem_u32(b_base + (size_t)s * F16_B_STAGE));
+          const uint64_t ad = make_kmajor_sw128_desc(smem_u32(a_base + (size_t)kb * F16_A_KBLOCK));
+          const uint64_t bd = make_kmajor_sw128_desc(smem_u32(b_base + (size_t)s * B_STAGE));
 #pragma unroll
           for (int k4 = 0; k4 < F16_BK / F16_UMMA_K; ++k4) {
             // advance 32 B (= 16 fp16) inside the 128-B swizzle row: +2 in 16-B units
-            const uint32_t acc = (kb | k4) != 0 ? 1u : 0u;
-            tc_mma_f16(d_tmem, ad0 + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, acc);
-            tc_mma_f16(d_tmem + F16_BN, ad1 + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, acc);
+            tc_mma_f16(d_tmem, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0 ? 1u : 0u);
           }
           tc_commit(smem_u32(&empty_bar[s]));      // frees the ring slot when these MMAs retire
         }
-        tc_commit(smem_u32(&tfull_bar[buf]));      // both accumulator halves ready for the epilogue
+        tc_commit(smem_u32(&tfull_bar[buf]));      // accumulator ready for the epilogue
       }
     }
   } else {
-    // ===================== epilogue: thread <-> query row; warp <-> (accumulator half, lane quarter) ==========
+    // ===================== epilogue: thread <-> query row, warp pair <-> lane quarter =====================
     const int quarter = warp & 3;                  // TMEM lanes this warp may read: 32*quarter ..
-    const int half = (warp - 2) >> 2;              // accumulator half = query rows half*128 ..
-    const int r_in_tile = half * 128 + quarter * 32 + lane;
+    const int half = (warp - 2) >> 2;              // which of the two warps of the quarter
+    const int r_in_tile = quarter * 32 + lane;
     const bool row_ok = q0 + r_in_tile < nq;
-    float* my_val = lval + r_in_tile;
-    int* my_idx = lidx + r_in_tile;
+    float* my_val = lval + (size_t)half * kc * F16_BM + r_in_tile;
+    int* my_idx = lidx + (size_t)half * kc * F16_BM + r_in_tile;
     const uint32_t my_val_s = smem_addr(my_val), my_idx_s = smem_addr(my_idx);
+    // The two warps of a lane quarter keep separate lists for the same rows but share their thresholds:
+    // a column is kept only if it beats max(own, partner) threshold.  Sound for the certification in
+    // knn_select.cu: every column either warp discards scores <= the larger of the two final list minima.
+    const uint32_t my_thr_s = smem_addr(thr_sh + half * F16_BM + r_in_tile);
+    const uint32_t other_thr_s = smem_addr(thr_sh + (half ^ 1) * F16_BM + r_in_tile);
+    sts_f32(my_thr_s, -INFINITY);
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only
     ListState st = list_init();
+    float thr = -INFINITY;                           // effective threshold = max(own list, partner list)
     bool partial = false;
     // one 32-column chunk held in registers: group maxima vs the running threshold; the rare path stays in
     // registers too -- per group of 8 columns, pick the first column (index order) that beats the threshold,
     // push it into the heap, and rescan only if the group held more than one candidate
     auto process_chunk = [&](float (&r)[32], int jb) {
-      if (dbg == 2) { if (r[0] == 12345.f && r[17] == 3.f) st.thr = r[5]; return; }   // timing experiment: loads only
       if (partial) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) r[c] = (jb + c < ndb) ? r[c] : -INFINITY;
@@ -219,29 +217,30 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         gm[g] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
       }
       const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-      if (dbg == 1) { if (mx == 12345.f) st.thr = mx; return; }     // timing experiment: no insertions
-      if (row_ok && mx > st.thr) {
+      if (row_ok && mx > thr) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          if (gm[g] > st.thr) {
+          if (gm[g] > thr) {
             int last = -1;
             while (true) {
               float cv = -INFINITY;
               int cc = -1, cnt = 0;
 #pragma unroll
               for (int c = 7; c >= 0; --c) {
-                const bool p = (c > last) && (r[g * 8 + c] > st.thr);
+                const bool p = (c > last) && (r[g * 8 + c] > thr);
                 cv = p ? r[g * 8 + c] : cv;
                 cc = p ? c : cc;
                 cnt += p ? 1 : 0;
               }
               if (cc < 0) break;
-              list_push(my_val_s, my_idx_s, F16_BM2 * 4, kc, st, cv, jb + g * 8 + cc);
+              list_push(my_val_s, my_idx_s, F16_BM * 4, kc, st, cv, jb + g * 8 + cc);
+              thr = fmaxf(thr, st.thr);
               if (cnt == 1) break;
               last = cc;
             }
           }
         }
+        sts_f32(my_thr_s, st.thr);
       }
     };
     for (int t = 0; t < ntiles; ++t) {
@@ -249,42 +248,40 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       const uint32_t tph = (uint32_t)(t >> 1) & 1u;
       mbar_wait(smem_u32(&tfull_bar[buf]), tph);
       tc_fence_after();
-      const int db0 = (tile_begin + t) * F16_BN;
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 2 * F16_BN + half * F16_BN);
-      partial = db0 + F16_BN > ndb;                 // only the last db tile has zero-filled columns
-      if (dbg >= 3) {                               // timing experiment: no TMEM loads
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
-        continue;
-      }
-      // Software pipeline over the 4 chunks of 32 columns: the tcgen05.ld of the next chunk is in flight while
-      // the current one is reduced; the TMEM buffer goes back to the MMA issuer as soon as the last chunk has
-      // landed in registers.
+      const int db0 = (tile_begin + t) * BN;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
+      partial = db0 + BN > ndb;                     // only the last db tile has zero-filled columns
+      // Software pipeline over this warp's chunks (half, half+2, ...): the tcgen05.ld of the next chunk is
+      // in flight while the current one is reduced.  The TMEM buffer goes back to the MMA issuer as soon as
+      // the last chunk has landed in registers.
+      constexpr int NCH = BN / 64;                  // chunks per warp per tile (even)
       float ra[32], rb[32];
-      tc_ld32(taddr0, ra);
+      tc_ld32(taddr0 + (uint32_t)(half * 32), ra);
 #pragma unroll 1
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < NCH; i += 2) {
+        const int ch_a = half + 2 * i, ch_b = ch_a + 2;
         tc_wait_ld();
-        tc_ld32(taddr0 + (uint32_t)((2 * i + 1) * 32), rb);
-        process_chunk(ra, db0 + (2 * i) * 32);
+        tc_ld32(taddr0 + (uint32_t)(ch_b * 32), rb);
+        thr = fmaxf(thr, lds_f32(other_thr_s));
+        process_chunk(ra, db0 + ch_a * 32);
         tc_wait_ld();
-        if (i == 0) {
-          tc_ld32(taddr0 + 64u, ra);
+        if (i + 2 < NCH) {
+          tc_ld32(taddr0 + (uint32_t)((ch_b + 2) * 32), ra);
         } else {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
         }
-        process_chunk(rb, db0 + (2 * i + 1) * 32);
+        thr = fmaxf(thr, lds_f32(other_thr_s));
+        process_chunk(rb, db0 + ch_b * 32);
       }
     }
     if (row_ok) {
-      const long long base = ((long long)split * nq + (q0 + r_in_tile)) * kc;
+      const long long base = (((long long)split * 2 + half) * nq + (q0 + r_in_tile)) * kc;
       for (int s = 0; s < kc; ++s) {
         const bool f = s < st.cnt;
-        cand_val[base + s] = f ? my_val[s * F16_BM2] : -INFINITY;
-        cand_idx[base + s] = f ? my_idx[s * F16_BM2] : -1;
+        cand_val[base + s] = f ? my_val[s * F16_BM] : -INFINITY;
+        cand_idx[base + s] = f ? my_idx[s * F16_BM] : -1;
       }
     }
   }
@@ -312,52 +309,61 @@ static int make_map_f16(CUtensorMap* m, const void* base, long long rows, int ld
   return r == CUDA_SUCCESS ? BGNN_OK : BGNN_ERR_DRIVER;
 }
 
-// Work decomposition: kc nominees per row next to the resident 256-row query block and the B ring.
+// Work decomposition: kc nominees per (row, half-list) next to the resident query block and the B ring.
 TcPlan tc_plan_f16(int nq, int ndb, int d, int k) {
   TcPlan p;
   p.bn = 0;
   const int ldh = (d + F16_BK - 1) / F16_BK * F16_BK;
-  const int kblocks = ldh / F16_BK;
   int kc = (k + 4 + 3) / 4 * 4;
   p.kc = kc;
-  const int a_bytes = kblocks * F16_A_KB2;
-  const int list_bytes = kc * F16_BM2 * 8;
-  const int stages = (F16_SMEM_MAX - F16_SMEM_FIXED - a_bytes - list_bytes) / F16_B_STAGE;
-  if (stages < 3 || kc > BGNN_MERGE_MAX_CAND) return p;      // caller falls back to another sweep
-  p.bn = F16_BN;
-  p.stages = min(stages, 12);
-  const int tiles = (ndb + F16_BN - 1) / F16_BN;
-  const int qblocks = (nq + F16_BM2 - 1) / F16_BM2;
+  const int a_bytes = (ldh / F16_BK) * F16_A_KBLOCK;
+  const int list_bytes = 2 * kc * F16_BM * 8;
+  for (int bn = 256; bn >= 128; bn >>= 1) {
+    const int stage_bytes = bn * F16_BK * 2;
+    const int stages = (F16_SMEM_MAX - F16_SMEM_FIXED - a_bytes - list_bytes) / stage_bytes;
+    if (stages >= 3) { p.bn = bn; p.stages = min(stages, 8); break; }
+  }
+  if (p.bn == 0) return p;                                  // caller falls back to another sweep
+  const int tiles = (ndb + p.bn - 1) / p.bn;
+  const int qblocks = (nq + F16_BM - 1) / F16_BM;
   int ns = (2 * kNumSMs + qblocks - 1) / qblocks;            // fill the machine when nq is small
-  ns = max(1, min(min(ns, tiles), min(16, BGNN_MERGE_MAX_CAND / kc)));
+  ns = max(1, min(min(ns, tiles), min(8, BGNN_MERGE_MAX_CAND / (2 * kc))));
+  if (ns < 1) { p.bn = 0; return p; }
   p.tiles_per_split = (tiles + ns - 1) / ns;
   p.nsplit = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.nlists = p.nsplit;
+  p.nlists = 2 * p.nsplit;
+  if (p.nlists * kc > BGNN_MERGE_MAX_CAND) p.bn = 0;
   return p;
+}
+
+template <int BN>
+static int launch_f16_cfg(const void* qh, int nq, const void* dh, int ndb, int ldh, const TcPlan& plan, float* cand_val,
+                          int* cand_idx, cudaStream_t stream) {
+  CUtensorMap mq, md;
+  int rc;
+  if ((rc = make_map_f16(&mq, qh, nq, ldh, F16_BM)) != BGNN_OK) return rc;
+  if ((rc = make_map_f16(&md, dh, ndb, ldh, BN)) != BGNN_OK) return rc;
+  const int kblocks = ldh / F16_BK;
+  const size_t smem = F16_SMEM_FIXED + (size_t)kblocks * F16_A_KBLOCK + (size_t)plan.stages * BN * F16_BK * 2 +
+                      (size_t)2 * plan.kc * F16_BM * 8;
+  if (smem > (size_t)F16_SMEM_MAX || plan.stages < 2) return BGNN_ERR_UNSUPPORTED;
+  auto kern = knn_cosine_f16_kernel<BN>;
+  BGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = (ndb + BN - 1) / BN;
+  dim3 grid((nq + F16_BM - 1) / F16_BM, plan.nsplit);
+  kern<<<grid, F16_THREADS, smem, stream>>>(mq, md, nq, ndb, kblocks, tiles, plan.tiles_per_split, plan.kc, plan.stages,
+                                            cand_val, cand_idx);
+  BGNN_LAUNCH_CHECK();
+  return BGNN_OK;
 }
 
 int launch_knn_cosine_f16(const void* qh, int nq, const void* dh, int ndb, int ldh, const TcPlan& plan, float* cand_val,
                           int* cand_idx, cudaStream_t stream) {
   if (nq <= 0) return BGNN_OK;
   if (ldh % F16_BK != 0) return BGNN_ERR_INVALID_ARG;
-  if (plan.bn != F16_BN) return BGNN_ERR_UNSUPPORTED;
-  CUtensorMap mq, md;
-  int rc;
-  if ((rc = make_map_f16(&mq, qh, nq, ldh, F16_BM2)) != BGNN_OK) return rc;
-  if ((rc = make_map_f16(&md, dh, ndb, ldh, F16_BN)) != BGNN_OK) return rc;
-  const int kblocks = ldh / F16_BK;
-  const size_t smem = F16_SMEM_FIXED + (size_t)kblocks * F16_A_KB2 + (size_t)plan.stages * F16_B_STAGE +
-                      (size_t)plan.kc * F16_BM2 * 8;
-  if (smem > (size_t)F16_SMEM_MAX || plan.stages < 3) return BGNN_ERR_UNSUPPORTED;
-  auto kern = knn_cosine_f16_kernel;
-  BGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int tiles = (ndb + F16_BN - 1) / F16_BN;
-  dim3 grid((nq + F16_BM2 - 1) / F16_BM2, plan.nsplit);
-  static const int dbg = getenv("BGNN_KNN_DEBUG") ? atoi(getenv("BGNN_KNN_DEBUG")) : 0;   // timing experiments only
-  kern<<<grid, F16_THREADS, smem, stream>>>(mq, md, nq, ndb, kblocks, tiles, plan.tiles_per_split, plan.kc, plan.stages,
-                                            dbg, cand_val, cand_idx);
-  BGNN_LAUNCH_CHECK();
-  return BGNN_OK;
+  if (plan.bn == 256) return launch_f16_cfg<256>(qh, nq, dh, ndb, ldh, plan, cand_val, cand_idx, stream);
+  if (plan.bn == 128) return launch_f16_cfg<128>(qh, nq, dh, ndb, ldh, plan, cand_val, cand_idx, stream);
+  return BGNN_ERR_UNSUPPORTED;
 }
 
 }  // namespace bgnn

@@ -379,7 +379,10 @@ def run_ours(args):
     # roofline of the dominant message-passing kernel (largest share of the step among our kernels)
     def gat_bytes(c, bwd):
         fwd_b = e_mp * (4 + 4 * c) + n * (4 + 4 * c + 4 * c + 1 + 8)
-        return 2 * e_mp * (4 + 2 * 4 * c) + n * 8 * c if bwd else fwd_b
+        rec = 16 if c <= 64 else 8 + 4 * ((c + 31) // 32)
+        # pass A: col + H[src] gather + record write; pass B: t_col + slot map + record + gout[dst] gather; 7 row-sized node passes
+        bwd_b = e_mp * (4 + 4 * c + rec) + e_mp * (8 + rec + 4 * c) + n * 7 * 4 * c
+        return bwd_b if bwd else fwd_b
     shares = {k: v[1] / (K + W) for k, v in mp_calls.items()}       # ms per step (events span warm-up + timed steps)
     top = max(shares, key=shares.get) if shares else None
     roof = None

@@ -345,6 +345,8 @@ def run_ours(args):
 
     train_step()                       # builds + caches partition / CSR / transposed CSR
     e_mp = int(model.edge_index.shape[1])
+    deg = torch.bincount(model.edge_index[1], minlength=n)
+    deg_stats = {"mean": float(deg.float().mean()), "p99": int(torch.quantile(deg[::64].float(), 0.99)), "max": int(deg.max())}
     launches0 = _lib.launches
     _lib.start_timing()
     step_ms = timed(train_step, K, W)
@@ -405,7 +407,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "sync-1M per GPU (BASELINE configs[3]): Ns=%d Nt=%d dim=%d k_cross=%d classes=%d hidden=%d"
                                    % (NS, NT, DIM, K_CROSS, N_CLASS, HIDDEN),
-                       "E_mp": e_mp, "conv_passes_per_step": 8, "step": "KT-GNN train fwd+bwd (4 AdaptedConv fwd + 4 bwd)",
+                       "E_mp": e_mp, "in_degree": deg_stats, "conv_passes_per_step": 8, "step": "KT-GNN train fwd+bwd (4 AdaptedConv fwd + 4 bwd)",
                        "l2": "inputs exceed L2 (features %.0f MB, db %.0f MB)" % (n * DIM * 4 / 1e6, NS * DIM * 4 / 1e6),
                        "knn_algo": args.knn_algo, "parallelism": "row-sharded x%d" % world},
             "fwd_only": {"ms": fwd_ms, "gedges_per_s": total_edges * 4 / (fwd_ms * 1e-3) / 1e9},

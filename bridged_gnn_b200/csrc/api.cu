@@ -235,17 +235,17 @@ size_t bgnn_gatv2_bwd_workspace_bytes(int64_t n, int64_t e, int c) {
 }
 
 int bgnn_gatv2_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
-                       const int32_t* csc_to_csr, int64_t e, const uint8_t* dst_is_src, const float* Hs,
+                       const int32_t* csr_to_csc, int64_t e, const uint8_t* dst_is_src, const float* Hs,
                        const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n, int c,
                        const float* out, const float* row_max, const float* row_sum, const float* gout, float* gHs,
                        float* gHt, float* g_af_t2s, float* g_af_s2t, void* workspace, size_t workspace_bytes,
                        void* stream) {
   if (n < 0 || e < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
-  if (n > 0 && (!rowptr || !col || !t_rowptr || !t_col || !csc_to_csr || !dst_is_src || !Hs || !Ht || !af_t2s ||
+  if (n > 0 && (!rowptr || !col || !t_rowptr || !t_col || !csr_to_csc || !dst_is_src || !Hs || !Ht || !af_t2s ||
                 !af_s2t || !out || !row_max || !row_sum || !gout || !gHs || !gHt || !g_af_t2s || !g_af_s2t))
     return BGNN_ERR_INVALID_ARG;
   if (n > 0 && (!workspace || workspace_bytes < gatv2_bwd_workspace_bytes(n, e, c))) return BGNN_ERR_WORKSPACE;
-  return launch_gatv2_bwd(rowptr, col, t_rowptr, t_col, csc_to_csr, e, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, c,
+  return launch_gatv2_bwd(rowptr, col, t_rowptr, t_col, csr_to_csc, e, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, c,
                           out, row_max, row_sum, gout, gHs, gHt, g_af_t2s, g_af_s2t, workspace, workspace_bytes,
                           (cudaStream_t)stream);
 }

@@ -139,15 +139,14 @@ int launch_gatv2_fwd(const int* rowptr, const int* col, const uint8_t* dst_is_sr
 // Pass A: per destination row (CSR).  Recomputes the scores from the saved (max, sum), and writes
 //   * the destination-side gradient of row i into gHs (source-domain row) or gHt (target-domain row),
 //   * per-CTA partial sums of d a_f into ga_part[cta][2][c],
-//   * one record per edge, written in CSR order (streaming stores); pass B finds an edge's record through
-//     the transposed-CSR-slot -> CSR-slot map:
+//   * one record per edge, stored at the edge's slot in the TRANSPOSED CSR so that pass B streams them:
 //       ea   = alpha_ij with the destination's domain in the sign bit (negative: source-domain destination)
 //       eds  = d score_ij = alpha_ij (gout_i . H_j - gout_i . out_i)
 //       emask[CW] = bit c set iff H_j[c] + H_i[c] > 0 (the leaky-relu branch)
 // so that pass B needs neither H[dst] nor the softmax statistics again.
 template <int VEC, int G, int CH>
 __global__ void __launch_bounds__(256)
-gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ csr_to_csc,
                      const uint8_t* __restrict__ dst_is_src, const float* __restrict__ Hs, const float* __restrict__ Ht,
                      const float* __restrict__ af_t2s, const float* __restrict__ af_s2t, float slope, long long n, int c,
                      int cw, const float* __restrict__ out, const float* __restrict__ row_max,
@@ -197,7 +196,7 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
       for (int u = 0; u < U; ++u) {
         const bool ok = e + u < end;
         j[u] = ok ? __ldg(col + e + u) : -1;
-        pos[u] = e + u;                      // records are written in CSR order: streaming, full sectors
+        pos[u] = ok ? __ldg(csr_to_csc + e + u) : 0;
       }
       Chunk<VEC> hj[U][CH];
 #pragma unroll
@@ -300,7 +299,7 @@ reduce_partials_kernel(const float* __restrict__ part, long long nparts, int wid
 // into gHs (edges into source-domain destinations) / gHt (target-domain destinations).
 template <int VEC, int G, int CH>
 __global__ void __launch_bounds__(256)
-gatv2_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restrict__ t_col, const int* __restrict__ csc_to_csr,
+gatv2_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restrict__ t_col,
                      const uint8_t* __restrict__ dst_is_src, const float* __restrict__ af_t2s,
                      const float* __restrict__ af_s2t, float slope, long long n, int c, int cw,
                      const unsigned* __restrict__ erec, const unsigned* __restrict__ emask,
@@ -333,19 +332,18 @@ gatv2_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restrict__ t
     for (int u = 0; u < U; ++u) {
       const bool ok = e + u < end;
       i_dst[u] = ok ? __ldg(t_col + e + u) : -1;
-      const long long slot = ok ? (long long)__ldg(csc_to_csr + e + u) : 0;   // the edge's record (CSR order)
       if (cw <= 2) {
-        const uint4 r4 = ok ? __ldg(reinterpret_cast<const uint4*>(erec) + slot) : make_uint4(0u, 0u, 0u, 0u);
+        const uint4 r4 = ok ? __ldg(reinterpret_cast<const uint4*>(erec) + e + u) : make_uint4(0u, 0u, 0u, 0u);
         al[u] = __uint_as_float(r4.x);
         ds[u] = __uint_as_float(r4.y);
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) mk[u][ch] = wsel[ch] ? r4.w : r4.z;
       } else {
-        const float2 r2 = ok ? __ldg(reinterpret_cast<const float2*>(erec) + slot) : make_float2(0.f, 0.f);
+        const float2 r2 = ok ? __ldg(reinterpret_cast<const float2*>(erec) + e + u) : make_float2(0.f, 0.f);
         al[u] = r2.x;
         ds[u] = r2.y;
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch) mk[u][ch] = ok ? __ldg(emask + slot * cw + wsel[ch]) : 0u;
+        for (int ch = 0; ch < CH; ++ch) mk[u][ch] = ok ? __ldg(emask + (long long)(e + u) * cw + wsel[ch]) : 0u;
       }
     }
 #pragma unroll
@@ -398,7 +396,7 @@ size_t gatv2_bwd_workspace_bytes(long long n, long long e, int c) {
   return align_up((size_t)bwd_blocks(n, g) * 2 * c * sizeof(float), 256) + align_up(rec, 256) + 1024;
 }
 
-int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csc_to_csr,
+int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csr_to_csc,
                      long long e, const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
                      const float* af_s2t, float slope, long long n, int c, const float* out, const float* row_max,
                      const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
@@ -415,7 +413,7 @@ int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, con
   if (!w.ok()) return BGNN_ERR_WORKSPACE;
   size_t dyn = (size_t)(256 / g) * 2 * c * sizeof(float);
 #define CALL(V, G_, C_)                                                                                            \
-  gatv2_bwd_dst_kernel<V, G_, C_><<<(unsigned)blocks, 256, dyn, stream>>>(rowptr, col, dst_is_src, Hs, \
+  gatv2_bwd_dst_kernel<V, G_, C_><<<(unsigned)blocks, 256, dyn, stream>>>(rowptr, col, csr_to_csc, dst_is_src, Hs, \
       Ht, af_t2s, af_s2t, slope, n, c, cw, out, row_max, row_sum, gout, gHs, gHt, erec, emask, part)
   BGNN_ROW_DISPATCH(vec, g, ch, CALL);
 #undef CALL
@@ -423,7 +421,7 @@ int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, con
   reduce_partials_kernel<<<2 * c, 256, 0, stream>>>(part, blocks, 2 * c, g_af_t2s, g_af_s2t, c);
   BGNN_LAUNCH_CHECK();
 #define CALL(V, G_, C_)                                                                                            \
-  gatv2_bwd_src_kernel<V, G_, C_><<<(unsigned)blocks, 256, 0, stream>>>(t_rowptr, t_col, csc_to_csr, dst_is_src, af_t2s, \
+  gatv2_bwd_src_kernel<V, G_, C_><<<(unsigned)blocks, 256, 0, stream>>>(t_rowptr, t_col, dst_is_src, af_t2s,      \
       af_s2t, slope, n, c, cw, erec, emask, gout, gHs, gHt)
   BGNN_ROW_DISPATCH(vec, g, ch, CALL);
 #undef CALL

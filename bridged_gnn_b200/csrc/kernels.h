@@ -56,7 +56,7 @@ int launch_gatv2_fwd(const int* rowptr, const int* col, const uint8_t* dst_is_sr
                      const float* af_t2s, const float* af_s2t, float slope, long long n, int c, float* out,
                      float* row_max, float* row_sum, cudaStream_t stream);
 size_t gatv2_bwd_workspace_bytes(long long n, long long e, int c);
-int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csc_to_csr,
+int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csr_to_csc,
                      long long e, const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
                      const float* af_s2t, float slope, long long n, int c, const float* out, const float* row_max,
                      const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,

@@ -131,13 +131,13 @@ class CSRGraph:
         return self._t
 
     @property
-    def csc_to_csr(self):
-        """int32 [e]: CSR slot of every edge of the transposed CSR (both index the same input edge list)."""
+    def csr_to_csc(self):
+        """int32 [e]: slot of every CSR edge in the transposed CSR (both index the same input edge list)."""
         if self._csr_to_csc is None:
             t_perm = self.t[2]
-            inv = torch.empty_like(self.perm)
-            inv[self.perm] = torch.arange(self.perm.numel(), device=self.perm.device)
-            self._csr_to_csc = inv[t_perm].to(torch.int32).contiguous()
+            inv_t = torch.empty_like(t_perm)
+            inv_t[t_perm] = torch.arange(t_perm.numel(), device=t_perm.device)
+            self._csr_to_csc = inv_t[self.perm].to(torch.int32).contiguous()
         return self._csr_to_csc
 
     @property
@@ -246,7 +246,7 @@ class _GatAggFn(torch.autograd.Function):
         ws = _lib.workspace(lib.bgnn_gatv2_bwd_workspace_bytes(n, g.e, c), dev)
         with _lib.call("bgnn_gatv2_bwd_f32", "bgnn_gatv2_bwd_f32[c=%d]" % c):
             _lib.check(lib.bgnn_gatv2_bwd_f32(_lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(t_rowptr), _lib.ptr(t_col),
-                                              _lib.ptr(g.csc_to_csr, torch.int32), g.e,
+                                              _lib.ptr(g.csr_to_csc, torch.int32), g.e,
                                               _lib.ptr(ctx.dst_is_src), _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(a1),
                                               _lib.ptr(a2), ctx.slope, n, c, _lib.ptr(out), _lib.ptr(row_max),
                                               _lib.ptr(row_sum), _lib.ptr(gout), _lib.ptr(gHs), _lib.ptr(gHt),

@@ -100,11 +100,11 @@ int bgnn_gatv2_fwd_f32(const int32_t* rowptr, const int32_t* col, const uint8_t*
                        float* out, float* row_max, float* row_sum, void* stream);
 
 /* Backward of the above.  (rowptr,col) = CSR by destination with e edges, (t_rowptr,t_col) = CSR of the
- * transposed graph (rows = sources, entries = destinations), csc_to_csr [e] = CSR slot of every edge of the
+ * transposed graph (rows = sources, entries = destinations), csr_to_csc [e] = slot of every CSR edge in the
  * transposed CSR.  Writes gHs, gHt [n,c] (fully), g_af_t2s, g_af_s2t [c].  Deterministic, atomic-free. */
 size_t bgnn_gatv2_bwd_workspace_bytes(int64_t n, int64_t e, int c);
 int bgnn_gatv2_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
-                       const int32_t* csc_to_csr, int64_t e, const uint8_t* dst_is_src, const float* Hs,
+                       const int32_t* csr_to_csc, int64_t e, const uint8_t* dst_is_src, const float* Hs,
                        const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n, int c,
                        const float* out, const float* row_max, const float* row_sum, const float* gout, float* gHs,
                        float* gHt, float* g_af_t2s, float* g_af_s2t, void* workspace, size_t workspace_bytes,

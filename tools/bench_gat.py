@@ -28,7 +28,7 @@ def main():
     cm[:ns] = True
     _, _, eall = graph_partition(ei, cm)
     graph = ops.CSRGraph(eall, n)
-    _ = graph.t, graph.csc_to_csr
+    _ = graph.t, graph.csr_to_csc
     e = graph.e
     cm8 = cm.to(torch.uint8)
     peak = bench.load_peaks()["hbm_gbs"]

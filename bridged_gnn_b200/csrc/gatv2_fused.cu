@@ -45,6 +45,24 @@ gatv2_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, co
   const unsigned mask = group_mask<G>(lane);
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
   if (row >= n) return;  // a group leaves together; shuffles below use the group's own mask
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  if (beg == end) {
+    // no incoming edge (rows owned by another rank in the destination-partitioned multi-GPU layout):
+    // the aggregate is 0; skip every feature load
+    Chunk<VEC> z;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) z.v[i] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+      const int c0 = (ch * G + lane_g) * VEC;
+      st_chunk<VEC>(out + row * c + c0, z, c0 < c);
+    }
+    if (lane_g == 0) {
+      if (row_max) row_max[row] = -INFINITY;
+      if (row_sum) row_sum[row] = 0.f;
+    }
+    return;
+  }
   const bool is_src = dst_is_src[row] != 0;
   const float* __restrict__ H = is_src ? Hs : Ht;
   const float* __restrict__ a = is_src ? af_t2s : af_s2t;
@@ -59,7 +77,6 @@ gatv2_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, co
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[ch].v[i] = 0.f;
   }
-  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
   float m = -INFINITY, l = 0.f;
   constexpr int U = 4;
   for (int e = beg; e < end; e += U) {
@@ -163,7 +180,19 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
   const int lane_g = threadIdx.x % G;
   const unsigned mask = group_mask<G>(lane);
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  if (row < n) {
+  const int beg0 = row < n ? __ldg(rowptr + row) : 0, end0 = row < n ? __ldg(rowptr + row + 1) : 0;
+  if (row < n && beg0 == end0) {
+    // no incoming edge: the destination-side gradient is 0 (see the forward kernel)
+    Chunk<VEC> z;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) z.v[i] = 0.f;
+    const bool is_src = dst_is_src[row] != 0;
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+      const int c0 = (ch * G + lane_g) * VEC;
+      st_chunk<VEC>((is_src ? gHs : gHt) + row * c + c0, z, c0 < c);
+    }
+  } else if (row < n) {
     const bool is_src = dst_is_src[row] != 0;
     const float* __restrict__ H = is_src ? Hs : Ht;
     const float* __restrict__ a = is_src ? af_t2s : af_s2t;
@@ -188,7 +217,7 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
     const float Di = gsum<G>(dpart, mask);
     const float m = row_max[row];
     const float inv = 1.0f / (row_sum[row] + 1e-16f);
-    const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    const int beg = beg0, end = end0;
     constexpr int U = 2;
     for (int e = beg; e < end; e += U) {
       int j[U], pos[U];

@@ -63,3 +63,95 @@ def edges_from_topk(idx, row_offset=0):
     nq, k = idx.shape
     to = torch.arange(row_offset, row_offset + nq, device=idx.device).unsqueeze(1).expand(nq, k)
     return torch.stack((idx.reshape(-1), to.reshape(-1)), 0)
+
+
+# ----------------------------------------------------------------------------------- destination-partitioned aggregation
+class _AllGatherRows(torch.autograd.Function):
+    """[n_loc, C] per rank -> [world * n_loc, C] on every rank (the dense feature halo: kNN edges have no
+    locality, so a destination shard needs H of essentially every source).  Backward = reduce-scatter of the
+    gradients w.r.t. all rows, i.e. the transpose exchange of SURVEY 8e."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        world = dist.get_world_size(group)
+        out = x.new_empty((world * x.shape[0],) + tuple(x.shape[1:]))
+        dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        world = dist.get_world_size(ctx.group)
+        rank = dist.get_rank(ctx.group)
+        n_loc = g.shape[0] // world
+        g = g.contiguous()
+        if dist.get_backend(ctx.group) == "nccl":
+            gl = g.new_empty((n_loc,) + tuple(g.shape[1:]))
+            dist.reduce_scatter_tensor(gl, g, group=ctx.group)
+        else:                                   # gloo has no reduce-scatter: all-reduce, keep the own block
+            dist.all_reduce(g, group=ctx.group)
+            gl = g[rank * n_loc:(rank + 1) * n_loc].clone()
+        return gl, None
+
+
+class _AllReduceSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        y = x.clone()
+        dist.all_reduce(y, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.clone()
+        dist.all_reduce(g, group=ctx.group)
+        return g, None
+
+
+def all_gather_rows_autograd(x, group=None):
+    return _AllGatherRows.apply(x, group)
+
+
+def all_reduce_sum_autograd(x, group=None):
+    return _AllReduceSum.apply(x, group)
+
+
+class DstPartition:
+    """1-D partition of the node set by destination rows for message passing: rank r owns the
+    contiguous rows [r*n_loc, (r+1)*n_loc) of a node set padded to a multiple of the world size, keeps the
+    edges whose destination it owns (global source ids), and needs H of all nodes for the gather."""
+
+    def __init__(self, num_nodes, group=None):
+        self.group = group
+        self.rank, self.world = _world(group)
+        self.n = int(num_nodes)
+        self.n_loc = (self.n + self.world - 1) // self.world
+        self.n_pad = self.n_loc * self.world
+        self.r0 = self.rank * self.n_loc
+        self.r1 = min(self.n, self.r0 + self.n_loc)
+
+    def local_rows(self, t):
+        """Rows of a global per-node tensor owned by this rank, zero padded to n_loc."""
+        out = t.new_zeros((self.n_loc,) + tuple(t.shape[1:]))
+        if self.r1 > self.r0:
+            out[: self.r1 - self.r0] = t[self.r0:self.r1]
+        return out
+
+    def pad_rows(self, t, fill=0):
+        if t.shape[0] == self.n_pad:
+            return t
+        out = t.new_full((self.n_pad,) + tuple(t.shape[1:]), fill)
+        out[: t.shape[0]] = t
+        return out
+
+    def local_edges(self, edge_index):
+        """Edges whose destination this rank owns (ids stay global)."""
+        m = (edge_index[1] >= self.r0) & (edge_index[1] < self.r1)
+        return edge_index[:, m].contiguous()
+
+    def sync_grads(self, module):
+        """Sum parameter gradients over ranks (every rank back-propagated its own destination rows)."""
+        for p in module.parameters():
+            if p.grad is not None:
+                dist.all_reduce(p.grad, group=self.group)

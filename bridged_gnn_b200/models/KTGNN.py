@@ -55,10 +55,15 @@ class AdaptedConv(nn.Module):
             self._mask_key, self._mask_u8 = key, central_mask.to(torch.uint8).contiguous()
         return self._mask_u8
 
-    def forward(self, x, edge_index, edge_index1=None, edge_index2=None, central_mask=None, size=None):
+    def forward(self, x, edge_index, edge_index1=None, edge_index2=None, central_mask=None, size=None, part=None):
         """edge_index must be cat(edge_index1, edge_index2) where edge_index1 / edge_index2 hold the edges
         whose destination is a source- / target-domain node (KTGNN.graph_partition).  The fused kernel
-        picks the branch per destination row from ``central_mask``, so only ``edge_index`` is read."""
+        picks the branch per destination row from ``central_mask``, so only ``edge_index`` is read.
+
+        ``part`` (a ``dist.DstPartition``) switches to the multi-GPU layout: ``x`` holds this rank's rows only,
+        ``edge_index`` this rank's incoming edges (global ids), ``central_mask`` the padded global mask."""
+        if part is not None:
+            return self._forward_partitioned(x, edge_index, central_mask, part)
         x_src, x_r = (x, x) if torch.is_tensor(x) else x
         c = central_mask
         n, d = x_src.shape
@@ -77,12 +82,13 @@ class AdaptedConv(nn.Module):
             p = torch.addmm(b_cat, x_src, w_cat.t())                 # [N, 2*co + 2], biases folded into the GEMM
         else:
             p = x_src @ w_cat.t()
-        gate_s2t = torch.tanh(p[:, 2 * co] + (self.a_g_s2t.weight[:, d:] * delta).sum())
-        gate_t2s = torch.tanh(p[:, 2 * co + 1] + (self.a_g_t2s.weight[:, d:] * delta).sum())
+        p_s, p_t, p_g = p.split((co, co, 2), dim=1)                  # one backward (cat) instead of per-slice zero fills
+        k_g = torch.stack(((self.a_g_s2t.weight[:, d:] * delta).sum(), (self.a_g_t2s.weight[:, d:] * delta).sum()))
+        gates = torch.tanh(p_g + k_g)                                # [N, 2]: s2t, t2s
         cfl = c.to(x_src.dtype)
         wd = delta @ torch.cat((self.lin_s.weight, self.lin_t.weight), 0).t()      # [1, 2*co]: W_s Delta, W_t Delta
-        h_s = torch.addcmul(p[:, :co], (gate_t2s * (1.0 - cfl)).unsqueeze(1), wd[:, :co])
-        h_t = torch.addcmul(p[:, co:2 * co], (gate_s2t * cfl).unsqueeze(1), wd[:, co:], value=-1.0)
+        h_s = torch.addcmul(p_s, (gates[:, 1] * (1.0 - cfl)).unsqueeze(1), wd[:, :co])
+        h_t = torch.addcmul(p_t, (gates[:, 0] * cfl).unsqueeze(1), wd[:, co:], value=-1.0)
         # attention scores, softmax over destinations, weighted aggregation (:292-305) -- one kernel
         graph = ops.cached_graph(edge_index, x_src.shape[0])
         out = ops.gat_aggregate(h_s, h_t, self.a_f_t2s.weight, self.a_f_s2t.weight, graph, self._dst_is_src(c),
@@ -92,6 +98,40 @@ class AdaptedConv(nn.Module):
         if self.normalize:
             out = F.normalize(out, p=2.0, dim=-1)
         return out
+
+    def _forward_partitioned(self, x, edge_index, central_mask, part):
+        """Destination-partitioned forward: domain means by all-reduce, node-wise transforms on
+        the local rows, all-gather of H (dense halo), fused aggregation over the local destination rows;
+        autograd turns the all-gather into the reduce-scatter of dH."""
+        from .. import dist as bdist
+        if self.root_weight or self.normalize:
+            raise NotImplementedError("partitioned AdaptedConv supports root_weight=False, normalize=False (all recipes)")
+        d, co = x.shape[1], self.out_channels
+        c_loc = part.local_rows(central_mask[: part.n].to(x.dtype))           # [n_loc] (padding rows: 0)
+        valid = part.local_rows(torch.ones(part.n, dtype=x.dtype, device=x.device))
+        n_s = central_mask[: part.n].sum().clamp(min=1).to(x.dtype)
+        n_t = (part.n - central_mask[: part.n].sum()).clamp(min=1).to(x.dtype)
+        rows = torch.stack((c_loc / n_s, (valid - c_loc) / n_t), 0)           # [2, n_loc]
+        means = bdist.all_reduce_sum_autograd(rows @ x, part.group)
+        delta = means[0:1] - means[1:2]
+        w_cat = torch.cat((self.lin_s.weight, self.lin_t.weight, self.a_g_s2t.weight[:, :d], self.a_g_t2s.weight[:, :d]), 0)
+        if self.lin_s.bias is not None:
+            b_cat = torch.cat((self.lin_s.bias, self.lin_t.bias, self.lin_s.bias.new_zeros(2)))
+            p = torch.addmm(b_cat, x, w_cat.t())
+        else:
+            p = x @ w_cat.t()
+        p_s, p_t, p_g = p.split((co, co, 2), dim=1)
+        k_g = torch.stack(((self.a_g_s2t.weight[:, d:] * delta).sum(), (self.a_g_t2s.weight[:, d:] * delta).sum()))
+        gates = torch.tanh(p_g + k_g)
+        wd = delta @ torch.cat((self.lin_s.weight, self.lin_t.weight), 0).t()
+        h_s = torch.addcmul(p_s, (gates[:, 1] * (valid - c_loc)).unsqueeze(1), wd[:, :co])
+        h_t = torch.addcmul(p_t, (gates[:, 0] * c_loc).unsqueeze(1), wd[:, co:], value=-1.0)
+        H_s = bdist.all_gather_rows_autograd(h_s, part.group)                  # [n_pad, co]
+        H_t = bdist.all_gather_rows_autograd(h_t, part.group)
+        graph = ops.cached_graph(edge_index, part.n_pad)
+        out = ops.gat_aggregate(H_s, H_t, self.a_f_t2s.weight, self.a_f_s2t.weight, graph, self._dst_is_src(central_mask),
+                                self.negative_slope)
+        return out[part.r0:part.r0 + part.n_loc]
 
     def __repr__(self):
         return "{}({}, {})".format(self.__class__.__name__, self.in_channels, self.out_channels)
@@ -126,9 +166,12 @@ class _KTGNNBase(nn.Module):
             self.edge_index1, self.edge_index2, self.edge_index = graph_partition(data.edge_index, data.central_mask)
         return self.edge_index1, self.edge_index2, self.edge_index
 
-    def _hidden(self, x, ei, ei1, ei2, c, n_convs):
+    def _hidden(self, x, ei, ei1, ei2, c, n_convs, part=None):
+        if part is not None and self.use_bn and self.training and part.n_pad != part.n:
+            raise NotImplementedError("partitioned training with BatchNorm needs num_nodes % world_size == 0 "
+                                      "(padding rows would enter the batch statistics)")
         for ind in range(n_convs):
-            x = self.convs[ind](x, ei, ei1, ei2, c)
+            x = self.convs[ind](x, ei, ei1, ei2, c, part=part)
             if self.use_bn:
                 x = self.bns[ind](x)
             x = F.dropout(F.relu(x), p=self.dropout, training=self.training)
@@ -158,12 +201,21 @@ class KTGNN_no_complement(_KTGNNBase):
         return self._hidden(data.x, ei, ei1, ei2, data.central_mask, len(self.convs))
 
     def forward(self, data):
-        ei1, ei2, ei = self._edges(data)
+        """``data.part`` (a ``dist.DstPartition``), if present, selects the destination-partitioned multi-GPU
+        forward: ``data.x`` = this rank's rows [n_loc, F], ``data.edge_index`` = this rank's incoming edges
+        AFTER graph_partition's self-loop rewrite (global ids), ``data.central_mask`` = padded global mask.
+        BatchNorm layers must then be SyncBatchNorm (``torch.nn.SyncBatchNorm.convert_sync_batchnorm``)."""
+        part = getattr(data, "part", None)
+        if part is not None:
+            ei1 = ei2 = None
+            ei = data.edge_index
+        else:
+            ei1, ei2, ei = self._edges(data)
         c = data.central_mask
-        x = self._hidden(data.x, ei, ei1, ei2, c, len(self.convs))
-        logits_base = self.clf_base(x, ei, ei1, ei2, c)
-        logits_trans = self.clf_target(self.clf_transformer(x), ei, ei1, ei2, c)
-        logits_target = self.clf_target(x, ei, ei1, ei2, c)
+        x = self._hidden(data.x, ei, ei1, ei2, c, len(self.convs), part)
+        logits_base = self.clf_base(x, ei, ei1, ei2, c, part=part)
+        logits_trans = self.clf_target(self.clf_transformer(x), ei, ei1, ei2, c, part=part)
+        logits_target = self.clf_target(x, ei, ei1, ei2, c, part=part)
         return F.log_softmax(logits_base, 1), F.log_softmax(logits_target, 1), F.log_softmax(logits_trans, 1), None
 
 

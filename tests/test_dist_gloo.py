@@ -64,3 +64,93 @@ def test_row_shard_partitions_exactly():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [e - s for s, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ------------------------------------------------------------------ destination-partitioned message passing
+def _mp_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    from bridged_gnn_b200 import dist as bd
+    from bridged_gnn_b200 import ops
+    from bridged_gnn_b200.data import Data
+    from bridged_gnn_b200.models import KTGNN_no_complement, graph_partition
+    from oracle import mp_oracle as mo
+
+    # CUDA operators -> oracle on the CPU (test infrastructure, as in tests/test_host_logic.py)
+    class FakeGraph:
+        def __init__(self, ei, n):
+            self.edge_index, self.n = ei, n
+    ops.cached_graph = lambda ei, n: FakeGraph(ei, n)
+
+    def gat(Hs, Ht, a1, a2, graph, dst_is_src, slope=0.1):
+        cm = dst_is_src.bool()
+        ei = graph.edge_index
+        m1 = cm[ei[1]]
+        return mo.adapted_conv_aggregate(Hs, Ht, ei[:, m1], ei[:, ~m1], cm, a1.view(-1), a2.view(-1), slope)
+    ops.gat_aggregate = gat
+
+    gb = dict(np.load(os.path.join(ROOT, "tests", "golden", "office_a2d_build.npz")))
+    gm = dict(np.load(os.path.join(ROOT, "tests", "golden", "office_a2d_mp.npz")))
+    T = torch.from_numpy
+    x, y, cm, tm = T(gb["x"]), T(gb["y"]), T(gb["central_mask"]), T(gb["train_mask"])
+    ei_u = T(gm["edge_index_undirected"])
+    n = x.shape[0]
+    sd = {k[len("ktgnn.sd."):]: T(v) for k, v in gm.items() if k.startswith("ktgnn.sd.")}
+    part = bd.DstPartition(n)
+    _, _, ei_all = graph_partition(ei_u, cm)
+    data_loc = Data(x=part.local_rows(x), edge_index=part.local_edges(ei_all), central_mask=part.pad_rows(cm), part=part)
+
+    # (1) eval forward == reference logits
+    model = KTGNN_no_complement(256, 31, 2, 64, root_weight=False, use_bn=True, dim_share=256)
+    model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        lb, lt, ltt, _ = model(data_loc)
+    full = [bd.all_gather_rows(t[: part.r1 - part.r0].contiguous(), n) for t in (lb, lt, ltt)]
+
+    # (2) train-mode gradients (no BatchNorm: SyncBatchNorm is CUDA-only) == single-process gradients
+    torch.manual_seed(0)
+    m2 = KTGNN_no_complement(256, 31, 2, 64, root_weight=False, use_bn=False, dim_share=256, dropout=0.0)
+    ref = KTGNN_no_complement(256, 31, 2, 64, root_weight=False, use_bn=False, dim_share=256, dropout=0.0)
+    ref.load_state_dict(m2.state_dict())
+    nll = torch.nn.functional.nll_loss
+    cnt = int(tm.sum())
+    m2.train(), ref.train()
+    m2.clf_transformer[1].eval(), ref.clf_transformer[1].eval()      # batch statistics would need SyncBatchNorm (CUDA only)
+    out = m2(data_loc)
+    tm_loc, y_loc = part.local_rows(tm), part.local_rows(y)
+    loss = sum(nll(o[tm_loc], y_loc[tm_loc], reduction="sum") for o in out[:3]) / cnt
+    loss.backward()
+    part.sync_grads(m2)
+    out_r = ref(Data(x=x, edge_index=ei_u, central_mask=cm))
+    loss_r = sum(nll(o[tm], y[tm], reduction="sum") for o in out_r[:3]) / cnt
+    loss_r.backward()
+    errs = {k: float((p.grad - q.grad).abs().max() / (q.grad.abs().max() + 1e-12))
+            for (k, p), q in zip(m2.named_parameters(), ref.parameters())}
+    gerr = max(errs.values())
+    if rank == 0 and gerr > 5e-5:
+        print({k: "%.2e" % v for k, v in errs.items() if v > 5e-5}, file=sys.stderr)
+    ltot = loss.detach().clone()
+    dist.all_reduce(ltot)
+    ret[rank] = ([f.clone() for f in full], gerr, float(ltot), float(loss_r))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_partitioned_ktgnn_matches_single_rank():
+    import numpy as np
+    port = 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_mp_worker, args=(2, port, ret), nprocs=2, join=True)
+    gm = dict(np.load(os.path.join(ROOT, "tests", "golden", "office_a2d_mp.npz")))
+    for r in (0, 1):
+        full, gerr, ltot, lref = ret[r]
+        for got, key in zip(full, ("ktgnn.eval.logp_base", "ktgnn.eval.logp_target", "ktgnn.eval.logp_trans")):
+            want = torch.from_numpy(gm[key])
+            assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-7, key
+        assert gerr < 5e-5
+        assert abs(ltot - lref) < 1e-5 * max(1.0, abs(lref))

@@ -140,6 +140,32 @@ def test_gat_aggregate_unsupported_width_fails_loudly():
         ops.gat_aggregate(Hs.cuda(), Ht.cuda(), a1.cuda(), a2.cuda(), graph, cm.to(torch.uint8).cuda(), 0.1)
 
 
+def test_gat_aggregate_rows_without_edges():
+    """Rows with no incoming edge (other ranks' rows in the partitioned layout): zero output, zero gradient,
+    and the remaining rows unaffected."""
+    ops = _ops()
+    n, c = 300, 64
+    g = torch.Generator().manual_seed(12)
+    ei = torch.randint(0, n, (2, 4000), generator=g)
+    ei = ei[:, ei[1] < 150]                                  # only the first 150 rows receive edges
+    cm = torch.zeros(n, dtype=torch.bool)
+    cm[:200] = True
+    Hs, Ht = torch.randn(n, c, generator=g), torch.randn(n, c, generator=g)
+    a1, a2 = torch.randn(c, generator=g) * 0.3, torch.randn(c, generator=g) * 0.3
+    gout = torch.randn(n, c, generator=g)
+    leaf = [t.clone().requires_grad_(True) for t in (Hs, Ht, a1, a2)]
+    m1 = cm[ei[1]]
+    y_ref = mo.adapted_conv_aggregate(leaf[0], leaf[1], ei[:, m1], ei[:, ~m1], cm, leaf[2], leaf[3])
+    (y_ref * gout).sum().backward()
+    graph = ops.CSRGraph(ei.cuda(), n)
+    dl = [t.clone().cuda().requires_grad_(True) for t in (Hs, Ht, a1, a2)]
+    y = ops.gat_aggregate(dl[0], dl[1], dl[2], dl[3], graph, cm.to(torch.uint8).cuda(), 0.1)
+    assert bool((y[150:] == 0).all()) and relclose(y, y_ref)
+    (y * gout.cuda()).sum().backward()
+    for got, ref in zip(dl, leaf):
+        assert relclose(got.grad, ref.grad, 2e-5)
+
+
 def test_gat_aggregate_single_edge_rows_and_large_scores():
     """Rows whose only edge is the self loop give out = H[i]; huge scores must not overflow the softmax."""
     ops = _ops()

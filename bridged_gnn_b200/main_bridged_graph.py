@@ -15,7 +15,8 @@ from . import ops
 from .data import Data, coalesce
 from .models.models import Adversarial_Learner, Adversarial_Learner_v2
 
-__all__ = ["add_topk_sim_cross_domain_edges", "add_topk_sim_within_domain_edges", "merge_graphs", "gen_bridged_graph"]
+__all__ = ["add_topk_sim_cross_domain_edges", "add_topk_sim_within_domain_edges", "check_added_edges_cross_domain_validity",
+           "check_added_edges_within_domain_validity", "merge_graphs", "reorder", "gen_bridged_graph"]
 
 
 def _homophily(y_from, y_to, edge_index):
@@ -89,6 +90,84 @@ def add_topk_sim_within_domain_edges(data_src, model, k=3, batch_size=1000, doma
     return out + (gap.cpu(),) if return_gap else out
 
 
+def _quantile(v, q):
+    """torch.quantile (linear interpolation) without its 16 M-element cap: sort once, interpolate."""
+    v = v.float().sort().values
+    pos = q * (v.numel() - 1)
+    lo = int(pos)
+    hi = min(lo + 1, v.numel() - 1)
+    return v[lo] + (v[hi] - v[lo]) * (pos - lo)
+
+
+def _validity_mask(e_sim, rules, thres_conf_quantile):
+    e_sim = e_sim.reshape(-1)
+    remove = e_sim < _quantile(e_sim, thres_conf_quantile)      # 1. low similarity-net confidence
+    for r in rules:
+        remove = remove | r
+    return remove
+
+
+def check_added_edges_cross_domain_validity(edge_index_added, e_sim, data_src, data_tar, probs_clf_src, probs_clf_tar,
+                                            thres_conf_quantile=0.1, thres_feat_sim=0.0, verbose=True):
+    """The 4-rule filter of main_bridged_graph.py:225-264 as a handful of device-wide elementwise ops.
+    ``e_sim`` is matched positionally with the columns of ``edge_index_added``, as in the reference; pass
+    similarities in the edge order you want compared (the reference passes the [Nt, k] matrix flattened
+    against the re-sorted coalesced list)."""
+    dev = data_src.x.device
+    ei = edge_index_added.to(dev)
+    e0, e1 = ei[0], ei[1]
+    pred_s, pred_t = probs_clf_src.to(dev).argmax(dim=1), probs_clf_tar.to(dev).argmax(dim=1)
+    cos = torch.nn.functional.cosine_similarity(data_src.x[e0], data_tar.x[e1])
+    remove = _validity_mask(e_sim.to(dev), [
+        pred_s[e0] != data_src.y[e0],                                              # 2. wrong source prediction
+        (pred_t[e1] != data_tar.y[e1]) & data_tar.train_mask[e1],                  #    wrong labelled-target prediction
+        pred_s[e0] != pred_t[e1],                                                  # 3. end points disagree
+        cos < thres_feat_sim], thres_conf_quantile)                                # 4. raw features dissimilar
+    out = ei[:, ~remove]
+    if verbose:
+        print("[Done] Totally remove edges: {} | Current total edge num: {}".format(int(remove.sum()), out.shape[1]))
+        print("Current homophily ratio:", _homophily(data_src.y, data_tar.y, out))
+    return out.to(edge_index_added.device)
+
+
+def check_added_edges_within_domain_validity(edge_index_added, e_sim, data_in, probs_clf, thres_conf_quantile=0.1,
+                                             thres_feat_sim=0.0, verbose=True):
+    """main_bridged_graph.py:123-161 (both label rules gated by the train mask of the destination end)."""
+    dev = data_in.x.device
+    ei = edge_index_added.to(dev)
+    e0, e1 = ei[0], ei[1]
+    pred = probs_clf.to(dev).argmax(dim=1)
+    cos = torch.nn.functional.cosine_similarity(data_in.x[e0], data_in.x[e1])
+    tm = data_in.train_mask[e1]
+    remove = _validity_mask(e_sim.to(dev), [(pred[e0] != data_in.y[e0]) & tm, (pred[e1] != data_in.y[e1]) & tm,
+                                            pred[e0] != pred[e1], cos < thres_feat_sim], thres_conf_quantile)
+    out = ei[:, ~remove]
+    if verbose:
+        print("[Done] Totally remove edges: {} | Current total edge num: {}".format(int(remove.sum()), out.shape[1]))
+        print("Current homophily ratio:", _homophily(data_in.y, data_in.y, out))
+    return out.to(edge_index_added.device)
+
+
+def reorder(data_merge, data_src, mapper_idx_src, mapper_idx_tar):
+    """main_bridged_graph.py:195-222 without the per-edge Python dict lookups: the two id maps become one
+    permutation tensor, node arrays are gathered with it and edge ids are mapped by one index_select."""
+    n_src = data_src.x.shape[0]
+    dev = data_merge.x.device
+    keys = list(mapper_idx_src.keys()) + list(mapper_idx_tar.keys())
+    vals = list(mapper_idx_src.values()) + [v + n_src for v in mapper_idx_tar.values()]
+    if len(set(keys)) != len(keys):
+        raise AssertionError("source and target id maps overlap")
+    k = torch.tensor(keys, dtype=torch.long, device=dev)
+    v = torch.tensor(vals, dtype=torch.long, device=dev)
+    order = v[torch.argsort(k)]                      # merged id of the node with the i-th smallest original id
+    inverse = torch.empty(int(v.max()) + 1, dtype=torch.long, device=dev)
+    inverse[v] = k                                   # merged id -> original id
+    for name in ("train_mask", "val_mask", "test_mask", "central_mask", "x", "y"):
+        setattr(data_merge, name, getattr(data_merge, name)[order])
+    data_merge.edge_index = inverse[data_merge.edge_index]
+    return data_merge
+
+
 def merge_graphs(data_src, data_tar, edge_index_cross_added, edge_index_added_src=None, edge_index_added_tar=None):
     """main_bridged_graph.py:163-193 on the device: concatenate the two graphs and the added edges with
     target ids offset by Ns, build the masks, coalesce.  Inputs are not modified."""
@@ -116,8 +195,8 @@ def merge_graphs(data_src, data_tar, edge_index_cross_added, edge_index_added_sr
 
 def gen_bridged_graph(args, data_src, data_tar, device, path_ckpt, mapper_idx_src=None, mapper_idx_tar=None,
                       epsilon=0.5, batch_size=1000):
-    """main_bridged_graph.py:267-321 without the optional validity filters and the id re-ordering
-    (SURVEY 8f "next" rows): load the similarity learner, add cross- and within-domain edges, merge."""
+    """main_bridged_graph.py:267-321: load the similarity learner, add cross- and within-domain edges,
+    optionally filter them, merge and re-order (eval_homophily's dense N x N diagnostics are not run)."""
     if args.version == "v1":
         sim_model = Adversarial_Learner(data_src, data_tar, dim_hidden=args.hidden_dim, num_layer=args.num_layer,
                                         source_clf=True, norm_mode=args.norm_mode, norm_scale=args.norm_scale)
@@ -127,15 +206,22 @@ def gen_bridged_graph(args, data_src, data_tar, device, path_ckpt, mapper_idx_sr
                                            norm_scale=args.norm_scale, sim_mode=args.sim_mode, backbone=args.backbone)
     sim_model.load_state_dict(torch.load(path_ckpt, map_location="cpu"))
     data_src, data_tar, sim_model = data_src.to(device), data_tar.to(device), sim_model.to(device)
-    if getattr(args, "check_cross", False) or getattr(args, "check_within", False):
-        raise NotImplementedError("edge-validity filters are not part of the accelerated path yet")
     ei_cross, e_sim, idx_src, p_src, p_tar = add_topk_sim_cross_domain_edges(
         data_src, data_tar, sim_model, epsilon=epsilon, k=args.k_cross, batch_size=batch_size)
+    if getattr(args, "check_cross", False):
+        ei_cross = check_added_edges_cross_domain_validity(ei_cross, e_sim.view(-1), data_src, data_tar, p_src, p_tar,
+                                                           thres_conf_quantile=args.thres_conf_quantile,
+                                                           thres_feat_sim=args.thres_feat_sim)
     ei_src = ei_tar = None
     if args.k_within > 0:
-        ei_src, _, _ = add_topk_sim_within_domain_edges(data_src, sim_model, k=args.k_within, batch_size=100, domain="source")
-        ei_tar, _, _ = add_topk_sim_within_domain_edges(data_tar, sim_model, k=args.k_within, batch_size=100, domain="target")
+        ei_src, s_src, _ = add_topk_sim_within_domain_edges(data_src, sim_model, k=args.k_within, batch_size=100, domain="source")
+        ei_tar, s_tar, _ = add_topk_sim_within_domain_edges(data_tar, sim_model, k=args.k_within, batch_size=100, domain="target")
+        if getattr(args, "check_within", False):      # constants as hard-coded at main_bridged_graph.py:301-306
+            ei_src = check_added_edges_within_domain_validity(ei_src, s_src.view(-1), data_src, p_src, 0.1, 0.8)
+            ei_tar = check_added_edges_within_domain_validity(ei_tar, s_tar.view(-1), data_tar, p_tar, 0.1, 0.8)
     data_merge = merge_graphs(data_src, data_tar, ei_cross, ei_src, ei_tar)
+    if mapper_idx_src is not None and mapper_idx_tar is not None:
+        data_merge = reorder(data_merge, data_src, mapper_idx_src, mapper_idx_tar)
     if getattr(args, "save", False):
         os.makedirs("../data_bridged_graph", exist_ok=True)
         torch.save({k: getattr(data_merge, k).cpu() for k in data_merge.keys()},
@@ -160,6 +246,8 @@ def parse_args(argv=None):
     p.add_argument("--batch_size", type=int, default=1000)
     p.add_argument("--check_cross", action="store_true")
     p.add_argument("--check_within", action="store_true")
+    p.add_argument("--thres_conf_quantile", type=float, default=0.1)
+    p.add_argument("--thres_feat_sim", type=float, default=0.0)
     p.add_argument("--save", action="store_true")
     p.add_argument("--gpu", type=int, default=0)
     p.add_argument("--path_data", type=str, default=None, help="bridged-graph .dat to take features / split from")

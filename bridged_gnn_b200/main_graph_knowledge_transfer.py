@@ -1,0 +1,166 @@
+"""Step 2 of the reference pipeline with its entry-point surface (Bridged-GNN/main_graph_knowledge_transfer.py):
+train a GNN on a bridged graph.  The loops, losses and optimiser settings follow the reference
+(train :39-68, test :73-118, train_gnn :143-262, train_gnn_noDTC :302-396); every conv runs on the fused
+sm_100a kernels through ``bridged_gnn_b200.models``.
+
+    python -m bridged_gnn_b200.main_graph_knowledge_transfer --path_data <bridged_graph.dat> --model_name KTGNN \
+        --num_layer 2 --hidden_dim 64 --to_undirected
+"""
+import argparse
+import time
+import types
+
+import torch
+import torch.nn.functional as F
+
+from .data import Data, load_pyg_dat, to_undirected
+from .models import GCNNet, GraphSAGE, KTGNN_no_complement
+
+
+def _device(gpu=0):
+    if not torch.cuda.is_available():
+        raise RuntimeError("bridged_gnn_b200 needs a CUDA device (sm_100a); there is no CPU path")
+    return torch.device("cuda", gpu)
+
+
+def _f1_macro(y_true, y_pred, num_classes):
+    """Macro F1 over the classes present in y_true or y_pred (sklearn's f1_score(average='macro') semantics),
+    computed on the device from a confusion matrix."""
+    idx = y_true * num_classes + y_pred
+    cm = torch.bincount(idx, minlength=num_classes * num_classes).view(num_classes, num_classes).float()
+    tp = cm.diag()
+    fp, fn = cm.sum(0) - tp, cm.sum(1) - tp
+    present = (cm.sum(0) + cm.sum(1)) > 0
+    f1 = 2 * tp / (2 * tp + fp + fn).clamp(min=1)
+    return float(f1[present].mean()) if bool(present.any()) else 0.0
+
+
+def train(data, model, optimizer, clip_grad=False, gnn=None, Lambda=1.0, verbose=False):
+    """One optimisation step; the KT-GNN objective of :44-54: (2 L_s + L_t + L_t_hat)/4 + Lambda KL(p_t_hat || p_t)."""
+    model.train()
+    optimizer.zero_grad()
+    if gnn == "KTGNN":
+        lp_s, lp_t, lp_t_hat, loss_dist = model(data)
+        tr = data.train_mask
+        tr_t = data.train_mask & ~data.central_mask
+        loss_s = F.nll_loss(lp_s[tr], data.y[tr])
+        loss_t1 = F.nll_loss(lp_t[tr_t], data.y[tr_t])
+        loss_t2 = F.nll_loss(lp_t_hat[tr_t], data.y[tr_t])
+        loss_kl = F.kl_div(lp_t_hat, lp_t, log_target=True, reduction="batchmean")
+        loss = (loss_s * 2.0 + loss_t1 + loss_t2) / 4.0 + loss_kl * Lambda
+        if loss_dist is not None:
+            loss = loss + loss_dist
+        extras = (loss_t2.detach().item(), loss_t1.detach().item(), loss_kl.detach().item())
+    else:
+        lp = model(data)
+        lp = lp[0] if isinstance(lp, tuple) else lp
+        loss = F.nll_loss(lp[data.train_mask], data.y[data.train_mask])
+        extras = (0.0, 0.0, 0.0)
+    if verbose:
+        print("Loss:{:.4f}".format(loss.item()))
+    loss.backward()
+    optimizer.step()
+    return (loss.detach().item(),) + extras
+
+
+@torch.no_grad()
+def test(data, model, dataset_name=None, gnn=None, metric="f1", f1_average="macro"):
+    """[train, val, test] scores (:73-118): the base classifier on the train split, the transformed target
+    classifier on the target nodes of val / test for KT-GNN; plain log-probs otherwise."""
+    if metric not in ("f1", "acc") or f1_average != "macro":
+        raise NotImplementedError("device-side metrics: macro F1 and accuracy")
+    model.eval()
+    nc = int(data.y.max().item()) + 1
+    out = model(data)
+    scores = []
+    for i, mask in enumerate((data.train_mask, data.val_mask, data.test_mask)):
+        if gnn == "KTGNN":
+            lp = out[0] if i == 0 else out[2]
+            # as in the reference, val/test masks select target nodes only (central_mask is False there)
+            y, pred = data.y[mask], lp[mask].argmax(1)
+        else:
+            lp = out[0] if isinstance(out, tuple) else out
+            y, pred = data.y[mask], lp[mask].argmax(1)
+        scores.append(_f1_macro(y, pred, nc) if metric == "f1" else float((y == pred).float().mean()))
+    return scores
+
+
+@torch.no_grad()
+def get_each_clf_res(data, model, metric="f1", f1_average="macro"):
+    """Test-split score of each of KT-GNN's three classifiers (:119-142)."""
+    model.eval()
+    nc = int(data.y.max().item()) + 1
+    lp_s, lp_t, lp_t_hat, _ = model(data)
+    m = data.test_mask
+    y = data.y[m]
+    f = (lambda p: _f1_macro(y, p, nc)) if metric == "f1" else (lambda p: float((y == p).float().mean()))
+    return [f(lp_s[m].argmax(1)), f(lp_t[m].argmax(1)), f(lp_t_hat[m].argmax(1))]
+
+
+def train_gnn(data, gnn="KTGNN", num_layer=2, hidden=64, num_epoch=300, lr=1e-3, weight_decay=5e-3, Lambda=1.0,
+              metric="f1", device=None, verbose=True):
+    """:143-262: KTGNN_no_complement(F, C, layers, hidden, root_weight=False, use_bn=True), Adam + StepLR(100, 0.1),
+    model selection on the validation score."""
+    device = device or _device()
+    data = data.to(device)
+    nf, nc = data.x.shape[1], int(data.y.max().item()) + 1
+    if gnn == "KTGNN":
+        model = KTGNN_no_complement(nf, nc, num_layer, hidden, root_weight=False, use_bn=True, dim_share=nf,
+                                    need_complement=False)
+    else:
+        ds = types.SimpleNamespace(num_features=nf, num_classes=nc)
+        model = {"GraphSAGE": GraphSAGE, "GCN": GCNNet}[gnn](ds, layer_num=num_layer, hidden=hidden)
+    model = model.to(device)
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=100, gamma=0.1)
+    best = {"val": -1.0, "test": 0.0, "epoch": 0}
+    for epoch in range(1, num_epoch + 1):
+        t0 = time.time()
+        loss = train(data, model, opt, gnn=gnn, Lambda=Lambda)[0]
+        tr, va, te = test(data, model, gnn=gnn, metric=metric)
+        sched.step()
+        if va > best["val"]:
+            best = {"val": va, "test": te, "epoch": epoch}
+        if verbose and (epoch % 10 == 0 or epoch == 1):
+            print("Epoch {:03d} | loss {:.4f} | train {:.4f} val {:.4f} test {:.4f} | best test {:.4f} @ {} | {:.3f} s/epoch"
+                  .format(epoch, loss, tr, va, te, best["test"], best["epoch"], time.time() - t0))
+    return model, best
+
+
+def train_gnn_noDTC(data, gnn="GraphSAGE", **kw):
+    """``--no_dtc`` (:414-417): the reference hard-codes GraphSAGE here."""
+    return train_gnn(data, gnn="GraphSAGE", **kw)
+
+
+def main(args):
+    data = load_pyg_dat(args.path_data)
+    device = _device(args.gpu)
+    data = Data(**{k: getattr(data, k) for k in data.keys()}).to(device)
+    data.train_mask = data.train_mask & (data.y != -1)
+    if args.to_undirected:
+        # the reference discards ToUndirected's return value (:410-411, in place only on old PyG); BASELINE.json
+        # names the undirected graph, so it is applied here
+        data.edge_index = to_undirected(data.edge_index, data.x.shape[0])
+    kw = dict(num_layer=args.num_layer, hidden=args.hidden_dim, num_epoch=args.num_epoch, metric=args.metric, device=device)
+    if args.no_dtc:
+        return train_gnn_noDTC(data, **kw)
+    return train_gnn(data, gnn=args.model_name, Lambda=args.Lambda, **kw)
+
+
+def parse_args(argv=None):
+    p = argparse.ArgumentParser()
+    p.add_argument("--path_data", type=str, required=True)
+    p.add_argument("--model_name", type=str, default="KTGNN", choices=["KTGNN", "GraphSAGE", "GCN"])
+    p.add_argument("--num_layer", type=int, default=2)
+    p.add_argument("--hidden_dim", type=int, default=64)
+    p.add_argument("--num_epoch", type=int, default=300)
+    p.add_argument("--metric", type=str, default="f1", choices=["f1", "acc"])
+    p.add_argument("--Lambda", type=float, default=1.0)
+    p.add_argument("--to_undirected", action="store_true")
+    p.add_argument("--no_dtc", action="store_true")
+    p.add_argument("--gpu", type=int, default=0)
+    return p.parse_args(argv)
+
+
+if __name__ == "__main__":
+    main(parse_args())

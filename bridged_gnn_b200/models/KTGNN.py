@@ -49,6 +49,24 @@ class AdaptedConv(nn.Module):
             self._rows_key, self._rows = key, torch.stack((cf / ns, (1.0 - cf) / nt), 0).contiguous()
         return self._rows
 
+    def _padded_params(self):
+        """lin_s / lin_t / a_f with the output width padded to a multiple of 4 by zero rows when that lets the
+        gather kernels use 128-bit loads (e.g. 31 classes -> 32).  The zero columns of H contribute nothing to
+        the attention scores (their a_f entries are 0) and are sliced off the output."""
+        co = self.out_channels
+        cp = (co + 3) // 4 * 4 if (co % 4 != 0 and co > 8) else co
+        w_s, w_t, b_s, b_t = self.lin_s.weight, self.lin_t.weight, self.lin_s.bias, self.lin_t.bias
+        a1, a2 = self.a_f_t2s.weight, self.a_f_s2t.weight
+        if cp != co:
+            zw = w_s.new_zeros((cp - co, w_s.shape[1]))
+            w_s, w_t = torch.cat((w_s, zw), 0), torch.cat((w_t, zw), 0)
+            if b_s is not None:
+                zb = b_s.new_zeros(cp - co)
+                b_s, b_t = torch.cat((b_s, zb)), torch.cat((b_t, zb))
+            za = a1.new_zeros((1, cp - co))
+            a1, a2 = torch.cat((a1, za), 1), torch.cat((a2, za), 1)
+        return w_s, w_t, b_s, b_t, a1, a2, cp
+
     def _dst_is_src(self, central_mask):
         key = (central_mask.data_ptr(), central_mask._version, central_mask.shape[0])
         if self._mask_key != key:
@@ -76,23 +94,24 @@ class AdaptedConv(nn.Module):
         cf = self._domain_rows(c, x_src.dtype)                       # [2, N]: 1/Ns on source rows, 1/Nt on target rows
         means = cf @ x_src                                           # [2, D] (one pass over x)
         delta = means[0:1] - means[1:2]                              # [1, D]
-        w_cat = torch.cat((self.lin_s.weight, self.lin_t.weight, self.a_g_s2t.weight[:, :d], self.a_g_t2s.weight[:, :d]), 0)
-        if self.lin_s.bias is not None:
-            b_cat = torch.cat((self.lin_s.bias, self.lin_t.bias, self.lin_s.bias.new_zeros(2)))
-            p = torch.addmm(b_cat, x_src, w_cat.t())                 # [N, 2*co + 2], biases folded into the GEMM
+        w_s, w_t, b_s, b_t, a_t2s, a_s2t, cp = self._padded_params()
+        w_cat = torch.cat((w_s, w_t, self.a_g_s2t.weight[:, :d], self.a_g_t2s.weight[:, :d]), 0)
+        if b_s is not None:
+            p = torch.addmm(torch.cat((b_s, b_t, b_s.new_zeros(2))), x_src, w_cat.t())   # [N, 2*cp + 2], biases folded in
         else:
             p = x_src @ w_cat.t()
-        p_s, p_t, p_g = p.split((co, co, 2), dim=1)                  # one backward (cat) instead of per-slice zero fills
+        p_s, p_t, p_g = p.split((cp, cp, 2), dim=1)                  # one backward (cat) instead of per-slice zero fills
         k_g = torch.stack(((self.a_g_s2t.weight[:, d:] * delta).sum(), (self.a_g_t2s.weight[:, d:] * delta).sum()))
         gates = torch.tanh(p_g + k_g)                                # [N, 2]: s2t, t2s
         cfl = c.to(x_src.dtype)
-        wd = delta @ torch.cat((self.lin_s.weight, self.lin_t.weight), 0).t()      # [1, 2*co]: W_s Delta, W_t Delta
-        h_s = torch.addcmul(p_s, (gates[:, 1] * (1.0 - cfl)).unsqueeze(1), wd[:, :co])
-        h_t = torch.addcmul(p_t, (gates[:, 0] * cfl).unsqueeze(1), wd[:, co:], value=-1.0)
+        wd = delta @ torch.cat((w_s, w_t), 0).t()                    # [1, 2*cp]: W_s Delta, W_t Delta
+        h_s = torch.addcmul(p_s, (gates[:, 1] * (1.0 - cfl)).unsqueeze(1), wd[:, :cp])
+        h_t = torch.addcmul(p_t, (gates[:, 0] * cfl).unsqueeze(1), wd[:, cp:], value=-1.0)
         # attention scores, softmax over destinations, weighted aggregation (:292-305) -- one kernel
         graph = ops.cached_graph(edge_index, x_src.shape[0])
-        out = ops.gat_aggregate(h_s, h_t, self.a_f_t2s.weight, self.a_f_s2t.weight, graph, self._dst_is_src(c),
-                                self.negative_slope)
+        out = ops.gat_aggregate(h_s, h_t, a_t2s, a_s2t, graph, self._dst_is_src(c), self.negative_slope)
+        if cp != co:
+            out = out[:, :co]
         if self.root_weight and x_r is not None:
             out = out + self.lin_r(x_r)
         if self.normalize:
@@ -114,24 +133,23 @@ class AdaptedConv(nn.Module):
         rows = torch.stack((c_loc / n_s, (valid - c_loc) / n_t), 0)           # [2, n_loc]
         means = bdist.all_reduce_sum_autograd(rows @ x, part.group)
         delta = means[0:1] - means[1:2]
-        w_cat = torch.cat((self.lin_s.weight, self.lin_t.weight, self.a_g_s2t.weight[:, :d], self.a_g_t2s.weight[:, :d]), 0)
-        if self.lin_s.bias is not None:
-            b_cat = torch.cat((self.lin_s.bias, self.lin_t.bias, self.lin_s.bias.new_zeros(2)))
-            p = torch.addmm(b_cat, x, w_cat.t())
+        w_s, w_t, b_s, b_t, a_t2s, a_s2t, cp = self._padded_params()
+        w_cat = torch.cat((w_s, w_t, self.a_g_s2t.weight[:, :d], self.a_g_t2s.weight[:, :d]), 0)
+        if b_s is not None:
+            p = torch.addmm(torch.cat((b_s, b_t, b_s.new_zeros(2))), x, w_cat.t())
         else:
             p = x @ w_cat.t()
-        p_s, p_t, p_g = p.split((co, co, 2), dim=1)
+        p_s, p_t, p_g = p.split((cp, cp, 2), dim=1)
         k_g = torch.stack(((self.a_g_s2t.weight[:, d:] * delta).sum(), (self.a_g_t2s.weight[:, d:] * delta).sum()))
         gates = torch.tanh(p_g + k_g)
-        wd = delta @ torch.cat((self.lin_s.weight, self.lin_t.weight), 0).t()
-        h_s = torch.addcmul(p_s, (gates[:, 1] * (valid - c_loc)).unsqueeze(1), wd[:, :co])
-        h_t = torch.addcmul(p_t, (gates[:, 0] * c_loc).unsqueeze(1), wd[:, co:], value=-1.0)
-        H_s = bdist.all_gather_rows_autograd(h_s, part.group)                  # [n_pad, co]
+        wd = delta @ torch.cat((w_s, w_t), 0).t()
+        h_s = torch.addcmul(p_s, (gates[:, 1] * (valid - c_loc)).unsqueeze(1), wd[:, :cp])
+        h_t = torch.addcmul(p_t, (gates[:, 0] * c_loc).unsqueeze(1), wd[:, cp:], value=-1.0)
+        H_s = bdist.all_gather_rows_autograd(h_s, part.group)                  # [n_pad, cp]
         H_t = bdist.all_gather_rows_autograd(h_t, part.group)
         graph = ops.cached_graph(edge_index, part.n_pad)
-        out = ops.gat_aggregate(H_s, H_t, self.a_f_t2s.weight, self.a_f_s2t.weight, graph, self._dst_is_src(central_mask),
-                                self.negative_slope)
-        return out[part.r0:part.r0 + part.n_loc]
+        out = ops.gat_aggregate(H_s, H_t, a_t2s, a_s2t, graph, self._dst_is_src(central_mask), self.negative_slope)
+        return out[part.r0:part.r0 + part.n_loc, :co]
 
     def __repr__(self):
         return "{}({}, {})".format(self.__class__.__name__, self.in_channels, self.out_channels)

@@ -27,7 +27,14 @@ class SAGEConv(nn.Module):
 
     def forward(self, x, edge_index):
         graph = edge_index if isinstance(edge_index, ops.CSRGraph) else ops.cached_graph(edge_index, x.shape[0])
-        out = self.lin_l(ops.spmm(graph, x, "mean"))
+        if self.in_channels > self.out_channels:
+            # mean aggregation commutes with the linear map: transform first, gather the narrower rows
+            # (e.g. 1685 -> 64 one-hot inputs of the fb graphs: 26x less gather traffic)
+            out = ops.spmm(graph, torch.nn.functional.linear(x, self.lin_l.weight), "mean")
+            if self.lin_l.bias is not None:
+                out = out + self.lin_l.bias          # lin_l(mean) = W mean + b also for rows without in-edges
+        else:
+            out = self.lin_l(ops.spmm(graph, x, "mean"))
         if self.root_weight:
             out = out + self.lin_r(x)
         return out

@@ -248,3 +248,50 @@ def cosine_knn_rows(u_db, u_q, k, rows=None, chunk=128):
 def set_threads():
     torch.set_num_threads(os.cpu_count() or 1)
     return torch.get_num_threads()
+
+
+# ----------------------------------------------------------------------------- edge-validity filters / reorder
+def check_added_edges_cross_domain_validity(edge_index_added, e_sim, x_src, y_src, x_tar, y_tar, train_mask_tar,
+                                            probs_clf_src, probs_clf_tar, thres_conf_quantile=0.1, thres_feat_sim=0.0):
+    """main_bridged_graph.py:225-264, restated on plain tensors.  ``e_sim`` is indexed positionally against
+    the columns of ``edge_index_added`` exactly as the reference does (:237-239)."""
+    pred_s, pred_t = probs_clf_src.argmax(dim=1), probs_clf_tar.argmax(dim=1)
+    e0, e1 = edge_index_added[0], edge_index_added[1]
+    rm = torch.zeros(edge_index_added.shape[1], dtype=torch.bool)
+    e_sim = e_sim.view(-1)
+    rm[e_sim < e_sim.quantile(q=thres_conf_quantile)] = True
+    rm[pred_s[e0] != y_src[e0]] = True
+    rm[(pred_t[e1] != y_tar[e1]) * train_mask_tar[e1]] = True
+    rm[pred_s[e0] != pred_t[e1]] = True
+    rm[F.cosine_similarity(x_src[e0], x_tar[e1]) < thres_feat_sim] = True
+    return edge_index_added[:, ~rm]
+
+
+def check_added_edges_within_domain_validity(edge_index_added, e_sim, x, y, train_mask, probs_clf,
+                                             thres_conf_quantile=0.1, thres_feat_sim=0.0):
+    """main_bridged_graph.py:123-161 (note :141-142: both label rules are gated by train_mask of the
+    DESTINATION end, as in the reference)."""
+    pred = probs_clf.argmax(dim=1)
+    e0, e1 = edge_index_added[0], edge_index_added[1]
+    rm = torch.zeros(edge_index_added.shape[1], dtype=torch.bool)
+    e_sim = e_sim.view(-1)
+    rm[e_sim < e_sim.quantile(q=thres_conf_quantile)] = True
+    rm[(pred[e0] != y[e0]) * train_mask[e1]] = True
+    rm[(pred[e1] != y[e1]) * train_mask[e1]] = True
+    rm[pred[e0] != pred[e1]] = True
+    rm[F.cosine_similarity(x[e0], x[e1]) < thres_feat_sim] = True
+    return edge_index_added[:, ~rm]
+
+
+def reorder(x, y, masks, edge_index, n_src, mapper_idx_src, mapper_idx_tar):
+    """main_bridged_graph.py:195-222: put the merged graph back into the original node order.
+    ``mapper_*``: dict original id -> local id.  Returns (x, y, masks, edge_index) re-indexed."""
+    merge = dict(mapper_idx_src)
+    for k, v in mapper_idx_tar.items():
+        assert k not in merge
+        merge[k] = v + n_src
+    inv = {v: k for k, v in merge.items()}
+    items = torch.tensor(sorted(merge.items(), key=lambda t: t[0]), dtype=torch.long)
+    order = items[:, 1]
+    ei = torch.tensor([[inv[int(i)] for i in edge_index[0]], [inv[int(i)] for i in edge_index[1]]], dtype=torch.long)
+    return x[order], y[order], {k: m[order] for k, m in masks.items()}, ei

@@ -305,3 +305,20 @@ def test_large_graph_properties():
     assert torch.allclose(ops.spmm(graph, ones, "mean"), ones, rtol=1e-6)
     deg = ops.spmm(graph, ones[:, :1].contiguous(), "sum").view(-1)
     assert torch.equal(deg.long(), rp[1:] - rp[:-1])
+
+
+def test_train_gnn_entry_point_learns(office_mp, office_build):
+    """Config 2 through the reference-shaped entry point (main_graph_knowledge_transfer.train_gnn): KT-GNN
+    2-layer hidden 64 on the office A->D bridged graph, undirected; 40 epochs must fit the training split."""
+    from bridged_gnn_b200.data import Data
+    from bridged_gnn_b200.main_graph_knowledge_transfer import test as evaluate
+    from bridged_gnn_b200.main_graph_knowledge_transfer import train_gnn
+    g = office_build
+    torch.manual_seed(0)
+    data = Data(x=T(g["x"]), edge_index=T(office_mp["edge_index_undirected"]), y=T(g["y"]), central_mask=T(g["central_mask"]),
+                train_mask=T(g["train_mask"]), val_mask=T(g["val_mask"]), test_mask=T(g["test_mask"]))
+    model, best = train_gnn(data, gnn="KTGNN", num_layer=2, hidden=64, num_epoch=40, verbose=False)
+    tr, va, te = evaluate(data, model, gnn="KTGNN")
+    assert tr > 0.8 and te > 0.5, (tr, va, te)
+    model2, best2 = train_gnn(data, gnn="GraphSAGE", num_layer=2, hidden=64, num_epoch=30, verbose=False)
+    assert evaluate(data, model2, gnn="GraphSAGE")[0] > 0.8

@@ -161,3 +161,49 @@ def test_graph_partition_and_self_loops(office_mp, office_build):
     e1, e2, e = graph_partition(T(office_mp["edge_index_undirected"]), T(office_build["central_mask"]))
     assert torch.equal(e1, T(office_mp["ktgnn.ei1"])) and torch.equal(e2, T(office_mp["ktgnn.ei2"]))
     assert e.shape[1] == 37522
+
+
+def test_validity_filters_and_reorder_match_reference_semantics(office_build):
+    """§8(f) rows: the 4-rule edge filters (main_bridged_graph.py:123-161, 225-264) and reorder (:195-222) --
+    pure index / elementwise host logic, run on the CPU here against the oracle restatement."""
+    from bridged_gnn_b200.data import Data
+    from bridged_gnn_b200 import main_bridged_graph as mb
+    g = office_build
+    ns = 2817
+    x, y, tm = T(g["x"]), T(g["y"]), T(g["train_mask"])
+    src = Data(x=x[:ns], y=y[:ns], train_mask=tm[:ns])
+    tar = Data(x=x[ns:], y=y[ns:], train_mask=tm[ns:])
+    ei, sim = T(g["cross_edge_index"]), T(g["cross_sim"])
+    ps, pt = T(g["probs_clf_src"]), T(g["probs_clf_tar"])
+    for q, thr in ((0.1, 0.0), (0.25, 0.6)):
+        got = mb.check_added_edges_cross_domain_validity(ei, sim.view(-1), src, tar, ps, pt, q, thr, verbose=False)
+        want = bo.check_added_edges_cross_domain_validity(ei, sim.view(-1), src.x, src.y, tar.x, tar.y, tar.train_mask, ps, pt, q, thr)
+        assert torch.equal(got, want) and 0 < got.shape[1] < ei.shape[1]
+    eiw, simw = T(g["within_tar_edge_index"]), T(g["within_tar_sim"])
+    got = mb.check_added_edges_within_domain_validity(eiw, simw.view(-1), tar, pt, 0.1, 0.8, verbose=False)
+    want = bo.check_added_edges_within_domain_validity(eiw, simw.view(-1), tar.x, tar.y, tar.train_mask, pt, 0.1, 0.8)
+    assert torch.equal(got, want)
+    # reorder: random original ids
+    gen = torch.Generator().manual_seed(0)
+    perm = torch.randperm(40, generator=gen).tolist()
+    msrc = {perm[i]: i for i in range(25)}
+    mtar = {perm[25 + i]: i for i in range(15)}
+    xm, ym = torch.randn(40, 3, generator=gen), torch.arange(40)
+    eim = torch.randint(0, 40, (2, 100), generator=gen)
+    masks = {k: torch.rand(40, generator=gen) < 0.5 for k in ("train_mask", "val_mask", "test_mask", "central_mask")}
+    d = Data(x=xm.clone(), y=ym.clone(), edge_index=eim.clone(), **{k: v.clone() for k, v in masks.items()})
+    d = mb.reorder(d, Data(x=torch.zeros(25, 3)), msrc, mtar)
+    xr, yr, mr, er = bo.reorder(xm, ym, masks, eim, 25, msrc, mtar)
+    assert torch.equal(d.x, xr) and torch.equal(d.y, yr) and torch.equal(d.edge_index, er)
+    assert all(torch.equal(getattr(d, k), v) for k, v in mr.items())
+
+
+def test_device_f1_matches_sklearn():
+    from sklearn.metrics import f1_score
+    from bridged_gnn_b200.main_graph_knowledge_transfer import _f1_macro
+    g = torch.Generator().manual_seed(0)
+    for nc in (2, 5, 31):
+        y, p = torch.randint(0, nc, (500,), generator=g), torch.randint(0, nc, (500,), generator=g)
+        assert abs(_f1_macro(y, p, nc) - f1_score(y.numpy(), p.numpy(), average="macro")) < 1e-6
+    y, p = torch.tensor([0, 0, 3, 3]), torch.tensor([0, 3, 3, 3])      # classes 1, 2 absent from both
+    assert abs(_f1_macro(y, p, 5) - f1_score(y.numpy(), p.numpy(), average="macro")) < 1e-6

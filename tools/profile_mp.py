@@ -27,12 +27,17 @@ def main():
     data = Data(x=torch.cat((u_s, u_t)).contiguous(), edge_index=ei, y=y, central_mask=cm)
     model = KTGNN_no_complement(bench.DIM, bench.N_CLASS, 2, bench.HIDDEN, root_weight=False, use_bn=True,
                                 dim_share=bench.DIM, dropout=0.0).to(dev).train()
-    nll = torch.nn.functional.nll_loss
+
+    w_train = cm.to(torch.float32) / cm.sum()
+    y_col = y.unsqueeze(1)
+
+    def nll(lp):
+        return -(lp.gather(1, y_col).squeeze(1) * w_train).sum()
 
     def step():
         model.zero_grad(set_to_none=True)
         lb, lt, ltt, _ = model(data)
-        loss = nll(lb[cm], y[cm]) + nll(lt[cm], y[cm]) + nll(ltt[cm], y[cm])
+        loss = nll(lb) + nll(lt) + nll(ltt)
         loss.backward()
 
     for _ in range(3):
@@ -43,7 +48,7 @@ def main():
         for _ in range(3):
             step()
         torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
 
 
 if __name__ == "__main__":

@@ -145,7 +145,7 @@ def _oracle_ktgnn_params(model):
     return {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
 
 
-def cpu_mp_sample(n_nodes=1 << 15, seed=0, reps=2):
+def cpu_mp_sample(n_nodes=1 << 17, seed=0, reps=1):
     """Oracle KT-GNN (PyG-semantics gather / softmax / scatter-add, torch autograd) forward + backward on
     the same generator at a reduced node count."""
     from oracle import build_oracle as bo
@@ -208,9 +208,10 @@ def run_reference(args):
     if rank != 0:
         return
     t_all = time.perf_counter()
-    mp_runs = [cpu_mp_sample(reps=1) for _ in range(max(1, min(args.steps, 3)))]
+    # one bounded sample per step (N = 2^18 nodes, ~3 s each on 16 cores), at most 3 steps; then 48 kNN rows (~8 s)
+    mp_runs = [cpu_mp_sample(n_nodes=1 << 18, reps=1) for _ in range(max(1, min(args.steps, 3)))]
     mp = max(mp_runs, key=lambda r: r["value"])
-    knn = cpu_knn_sample(rows=8)
+    knn = cpu_knn_sample(rows=48)
     line = {
         "impl": "reference", "metric": METRIC, "value": mp["value"], "unit": "GEdges/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": mp["seconds"] * 1e3, "higher_is_better": True,
@@ -404,7 +405,7 @@ def run_ours(args):
 
     if rank == 0:
         cpu = cpu_mp_sample() if world == 1 and not args.no_cpu_baseline else None
-        cpu_knn = cpu_knn_sample(rows=4) if world == 1 and not args.no_cpu_baseline else None
+        cpu_knn = cpu_knn_sample(rows=24) if world == 1 and not args.no_cpu_baseline else None
         line = {
             "metric": METRIC, "value": value, "unit": "GEdges/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -23,6 +23,7 @@
 //              thread-private list in shared memory
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -91,7 +92,8 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                       int nq, int ndb, int kblocks, int tiles_total, int tiles_per_split, int kc, int stages,
                       float* __restrict__ cand_val, int* __restrict__ cand_idx) {
   constexpr int B_STAGE = BN * F16_BK * 2;
-  constexpr int TMEM_COLS = 2 * BN;
+  constexpr int NBUF = 512 / BN;                 // accumulator buffers in TMEM: 2 x 256 or 4 x 128 columns
+  constexpr int TMEM_COLS = 512;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* a_base = smem;                                          // kblocks * 16 KB, resident
@@ -102,10 +104,10 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(thr_sh + 2 * F16_BM);
   uint64_t* full_bar = bars;                      // [stages]
   uint64_t* empty_bar = bars + stages;            // [stages]
-  uint64_t* tfull_bar = bars + 2 * stages;        // [2]
-  uint64_t* tempty_bar = bars + 2 * stages + 2;   // [2]
-  uint64_t* a_bar = bars + 2 * stages + 4;        // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
+  uint64_t* tfull_bar = bars + 2 * stages;               // [NBUF]
+  uint64_t* tempty_bar = bars + 2 * stages + NBUF;       // [NBUF]
+  uint64_t* a_bar = bars + 2 * stages + 2 * NBUF;        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 2 * NBUF + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * F16_BM;
@@ -116,7 +118,7 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 8); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 8); }
     mbar_init(smem_u32(a_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -160,8 +162,8 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       tc_fence_after();
       int it = 0;
       for (int t = 0; t < ntiles; ++t) {
-        const int buf = t & 1;
-        const uint32_t tph = (uint32_t)(t >> 1) & 1u;
+        const int buf = t % NBUF;
+        const uint32_t tph = (uint32_t)(t / NBUF) & 1u;
         mbar_wait(smem_u32(&tempty_bar[buf]), tph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
@@ -244,8 +246,8 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       }
     };
     for (int t = 0; t < ntiles; ++t) {
-      const int buf = t & 1;
-      const uint32_t tph = (uint32_t)(t >> 1) & 1u;
+      const int buf = t % NBUF;
+      const uint32_t tph = (uint32_t)(t / NBUF) & 1u;
       mbar_wait(smem_u32(&tfull_bar[buf]), tph);
       tc_fence_after();
       const int db0 = (tile_begin + t) * BN;
@@ -318,7 +320,8 @@ TcPlan tc_plan_f16(int nq, int ndb, int d, int k) {
   p.kc = kc;
   const int a_bytes = (ldh / F16_BK) * F16_A_KBLOCK;
   const int list_bytes = 2 * kc * F16_BM * 8;
-  for (int bn = 256; bn >= 128; bn >>= 1) {
+  static const int force_bn = getenv("BGNN_F16_BN") ? atoi(getenv("BGNN_F16_BN")) : 0;   // tuning experiments
+  for (int bn = (force_bn == 128 ? 128 : 256); bn >= 128; bn >>= 1) {
     const int stage_bytes = bn * F16_BK * 2;
     const int stages = (F16_SMEM_MAX - F16_SMEM_FIXED - a_bytes - list_bytes) / stage_bytes;
     if (stages >= 3) { p.bn = bn; p.stages = min(stages, 8); break; }

@@ -274,3 +274,20 @@ def test_sync_1m_shape_sampled_rows_exact():
         if set(i[n].tolist()) != set(i1[r].tolist()):
             assert bool(tie[n]), r
     assert float((v - v1.cpu()[rows]).abs().max()) < 2e-6
+
+
+def test_sync_16m_shape_sampled_rows_exact():
+    """Config 5 shape: db = 12 582 912 source rows, d=256, k=32 (12.9 GB of fp32 embeddings on one GPU).
+    2048 sampled target rows: tensor-core path == exact CUDA-core path bit for bit."""
+    ops = _ops()
+    from bench import make_sync_embeddings
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * (1 << 30):
+        pytest.skip("needs ~45 GB of free HBM")
+    u_src, u_tar, _, _ = make_sync_embeddings(12582912, 2048, 256, torch.device("cuda:0"), seed=0)
+    i1, v1, g1, st = ops.knn_cosine(u_tar, u_src, 32, algo="f16")
+    i0, v0, g0, _ = ops.knn_cosine(u_tar, u_src, 32, algo="simt")
+    assert torch.equal(i0, i1) and torch.equal(v0, v1) and torch.equal(g0, g1)
+    assert int(st[0]) < 256
+    assert bool((i1 >= 0).all()) and int(i1.max()) < 12582912
+    assert bool((v1[:, :-1] >= v1[:, 1:]).all())

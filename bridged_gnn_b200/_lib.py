@@ -32,6 +32,9 @@ SIGNATURES = {
     "bgnn_edges_to_csr": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bgnn_spmm_csr_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "bgnn_gatv2_fwd_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "bgnn_adapted_transform_fwd_f32": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "bgnn_adapted_transform_bwd_workspace_bytes": (_sz, [_i32]),
+    "bgnn_adapted_transform_bwd_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "bgnn_gatv2_bwd_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "bgnn_gatv2_bwd_f32": (_i32, [_vp] * 5 + [_i64] + [_vp] * 5 + [_f32, _i64, _i32] + [_vp] * 9 + [_sz, _vp]),
 }
@@ -88,7 +91,8 @@ def workspace(nbytes, device):
 # kernels launched per C-ABI call (hand-written kernels of this library only; CUB's sort/scan inside
 # bgnn_edges_to_csr are not counted)
 KERNELS_PER_CALL = {"bgnn_knn_cosine_f32": 8, "bgnn_knn_cosine_f32[simt]": 4, "bgnn_knn_addrelu_f32": 2,
-                    "bgnn_edges_to_csr": 4, "bgnn_spmm_csr_f32": 1, "bgnn_gatv2_fwd_f32": 1, "bgnn_gatv2_bwd_f32": 3}
+                    "bgnn_edges_to_csr": 4, "bgnn_spmm_csr_f32": 1, "bgnn_gatv2_fwd_f32": 1, "bgnn_gatv2_bwd_f32": 3,
+                    "bgnn_adapted_transform_fwd_f32": 1, "bgnn_adapted_transform_bwd_f32": 2}
 launches = 0          # running count of kernels launched through the C ABI
 _timing = None        # None, or {name: [(start_event, end_event), ...]}
 

@@ -100,13 +100,9 @@ class AdaptedConv(nn.Module):
             p = torch.addmm(torch.cat((b_s, b_t, b_s.new_zeros(2))), x_src, w_cat.t())   # [N, 2*cp + 2], biases folded in
         else:
             p = x_src @ w_cat.t()
-        p_s, p_t, p_g = p.split((cp, cp, 2), dim=1)                  # one backward (cat) instead of per-slice zero fills
         k_g = torch.stack(((self.a_g_s2t.weight[:, d:] * delta).sum(), (self.a_g_t2s.weight[:, d:] * delta).sum()))
-        gates = torch.tanh(p_g + k_g)                                # [N, 2]: s2t, t2s
-        cfl = c.to(x_src.dtype)
         wd = delta @ torch.cat((w_s, w_t), 0).t()                    # [1, 2*cp]: W_s Delta, W_t Delta
-        h_s = torch.addcmul(p_s, (gates[:, 1] * (1.0 - cfl)).unsqueeze(1), wd[:, :cp])
-        h_t = torch.addcmul(p_t, (gates[:, 0] * cfl).unsqueeze(1), wd[:, cp:], value=-1.0)
+        h_s, h_t = ops.adapted_transform(p, wd, k_g, self._dst_is_src(c))   # gates + rank-1 corrections, one pass over P
         # attention scores, softmax over destinations, weighted aggregation (:292-305) -- one kernel
         graph = ops.cached_graph(edge_index, x_src.shape[0])
         out = ops.gat_aggregate(h_s, h_t, a_t2s, a_s2t, graph, self._dst_is_src(c), self.negative_slope)

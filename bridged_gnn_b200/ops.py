@@ -261,3 +261,55 @@ def gat_aggregate(Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope=0.1):
     edges (PyG softmax, +1e-16), weighted sum of H[src]; (H, a) = (Hs, af_t2s) for destinations in the
     source domain, (Ht, af_s2t) otherwise.  dst_is_src: uint8 [n]."""
     return _GatAggFn.apply(Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope)
+
+
+# ----------------------------------------------------------------------------------- AdaptedConv node-wise epilogue
+class _AdaptedTransformFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, P, wd, kg, is_src):
+        lib = _lib.load()
+        f32 = torch.float32
+        P = P.to(f32).contiguous()
+        wd_c, kg_c = wd.to(f32).contiguous().view(-1), kg.to(f32).contiguous().view(-1)
+        n = P.shape[0]
+        c = (P.shape[1] - 2) // 2
+        dev = P.device
+        Hs = torch.empty((n, c), dtype=f32, device=dev)
+        Ht = torch.empty((n, c), dtype=f32, device=dev)
+        gates = torch.empty((n, 2), dtype=f32, device=dev)
+        with _lib.call("bgnn_adapted_transform_fwd_f32"):
+            _lib.check(lib.bgnn_adapted_transform_fwd_f32(_lib.ptr(P), _lib.ptr(is_src, torch.uint8), _lib.ptr(wd_c),
+                                                          _lib.ptr(kg_c), n, c, _lib.ptr(Hs), _lib.ptr(Ht),
+                                                          _lib.ptr(gates), _lib.stream(dev)))
+        ctx.save_for_backward(gates, wd_c, is_src)
+        ctx.shapes = (wd.shape, kg.shape, c)
+        ctx.mark_non_differentiable(gates)
+        return Hs, Ht, gates
+
+    @staticmethod
+    def backward(ctx, gHs, gHt, _ggates):
+        lib = _lib.load()
+        gates, wd_c, is_src = ctx.saved_tensors
+        wd_shape, kg_shape, c = ctx.shapes
+        f32 = torch.float32
+        gHs, gHt = gHs.to(f32).contiguous(), gHt.to(f32).contiguous()
+        n = gHs.shape[0]
+        dev = gHs.device
+        gP = torch.empty((n, 2 * c + 2), dtype=f32, device=dev)
+        red = torch.empty((2 * c + 2,), dtype=f32, device=dev)
+        ws = _lib.workspace(lib.bgnn_adapted_transform_bwd_workspace_bytes(c), dev)
+        with _lib.call("bgnn_adapted_transform_bwd_f32"):
+            _lib.check(lib.bgnn_adapted_transform_bwd_f32(_lib.ptr(gHs), _lib.ptr(gHt), _lib.ptr(gates),
+                                                          _lib.ptr(is_src, torch.uint8), _lib.ptr(wd_c), n, c,
+                                                          _lib.ptr(gP), _lib.ptr(red), _lib.ptr(ws), ws.numel(),
+                                                          _lib.stream(dev)))
+        return gP, red[: 2 * c].view(wd_shape), red[2 * c:].view(kg_shape), None
+
+
+def adapted_transform(P, wd, kg, is_src):
+    """Fused node-wise epilogue of AdaptedConv (models/KTGNN.py:277-284 after the single contraction
+    P = x [W_s; W_t; a_g_s2t[:D]; a_g_t2s[:D]]^T + b): returns (Hs, Ht) = (lin_s(x_t2s), lin_t(x_s2t)).
+    P [n, 2c+2]; wd [2c] or [1, 2c] = (W_s Delta, W_t Delta); kg [2] = Delta part of the two gate logits;
+    is_src uint8 [n].  Differentiable in P, wd, kg."""
+    Hs, Ht, _ = _AdaptedTransformFn.apply(P, wd, kg, is_src)
+    return Hs, Ht

@@ -91,6 +91,7 @@ def _mp_worker(rank, world, port, ret):
         m1 = cm[ei[1]]
         return mo.adapted_conv_aggregate(Hs, Ht, ei[:, m1], ei[:, ~m1], cm, a1.view(-1), a2.view(-1), slope)
     ops.gat_aggregate = gat
+    ops.adapted_transform = mo.adapted_transform_epilogue
 
     gb = dict(np.load(os.path.join(ROOT, "tests", "golden", "office_a2d_build.npz")))
     gm = dict(np.load(os.path.join(ROOT, "tests", "golden", "office_a2d_mp.npz")))

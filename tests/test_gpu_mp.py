@@ -182,6 +182,25 @@ def test_gat_aggregate_single_edge_rows_and_large_scores():
     assert bool(torch.isfinite(y).all())
 
 
+@pytest.mark.parametrize("n,c", [(1, 1), (1000, 2), (777, 31), (5000, 32), (4096, 64), (3000, 100), (2000, 256), (300, 512)])
+def test_adapted_transform_forward_backward(n, c):
+    ops = _ops()
+    g = torch.Generator().manual_seed(40 + c)
+    P = torch.randn(n, 2 * c + 2, generator=g)
+    wd, kg = torch.randn(1, 2 * c, generator=g), torch.randn(2, generator=g)
+    cm = torch.rand(n, generator=g) < 0.7
+    go_s, go_t = torch.randn(n, c, generator=g), torch.randn(n, c, generator=g)
+    leaf = [t.clone().requires_grad_(True) for t in (P, wd, kg)]
+    Hs_r, Ht_r = mo.adapted_transform_epilogue(leaf[0], leaf[1], leaf[2], cm.to(torch.uint8))
+    ((Hs_r * go_s).sum() + (Ht_r * go_t).sum()).backward()
+    dl = [t.clone().cuda().requires_grad_(True) for t in (P, wd, kg)]
+    Hs, Ht = ops.adapted_transform(dl[0], dl[1], dl[2], cm.to(torch.uint8).cuda())
+    assert relclose(Hs, Hs_r, 2e-6) and relclose(Ht, Ht_r, 2e-6)
+    ((Hs * go_s.cuda()).sum() + (Ht * go_t.cuda()).sum()).backward()
+    for got, ref, name in zip(dl, leaf, ("P", "wd", "kg")):
+        assert got.grad.shape == ref.grad.shape and relclose(got.grad, ref.grad, 2e-5), name
+
+
 # ------------------------------------------------------------------ golden: reference layers on the office bridged graph
 def test_adapted_conv_module_matches_reference(office_mp, office_build):
     from bridged_gnn_b200.models import AdaptedConv

@@ -50,6 +50,7 @@ def oracle_backed_ops(monkeypatch):
                 w = w * out_scale[ei[1]]
         return mo.spmm(ei, X, graph.n, reduce, w)
 
+    monkeypatch.setattr(ops, "adapted_transform", mo.adapted_transform_epilogue)
     monkeypatch.setattr(ops, "cached_graph", cached_graph)
     monkeypatch.setattr(ops, "gat_aggregate", gat_aggregate)
     monkeypatch.setattr(ops, "spmm", spmm)

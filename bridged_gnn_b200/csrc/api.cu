@@ -35,6 +35,8 @@ struct KnnPlan {
   int ld;          // row stride of the normalised fp32 planes
   int ldh;         // row stride of the fp16 plane (f16 sweep)
   TcPlan tc;
+  int seed_rows;   // sampled db rows of the threshold-seeding sweep (f16 only; 0 = none)
+  TcPlan seed_tc;
   SimtPlan simt;   // main sweep (SIMT algo) or exact fallback (tensor-core algos)
   size_t cand_elems;
 };
@@ -48,12 +50,20 @@ static KnnPlan knn_plan(int64_t nq, int64_t ndb, int d, int k, int algo) {
   p.algo = algo;
   p.passes = (algo == BGNN_KNN_TC_3XTF32) ? 3 : (algo == BGNN_KNN_TC_1XTF32 ? 1 : 0);
   p.tc.bn = 0;
+  p.seed_rows = 0;
   p.f16 = false;
   p.ldh = 0;
   if (algo == BGNN_KNN_TC_F16) {
     p.tc = tc_plan_f16((int)nq, (int)ndb, d, k);
     p.f16 = p.tc.bn != 0;
     if (!p.f16) p.algo = BGNN_KNN_SIMT_F32;                           // d or k too large for the on-chip budget
+    if (p.f16) {
+      p.seed_rows = knn_seed_rows((int)ndb, k);
+      if (p.seed_rows) {
+        p.seed_tc = tc_plan_f16((int)nq, p.seed_rows, d, k, kSeedKc);
+        if (p.seed_tc.bn == 0) p.seed_rows = 0;
+      }
+    }
   } else if (p.passes) {
     p.tc = tc_plan((int)nq, (int)ndb, d, k, p.passes);
     if (p.tc.bn == 0) { p.passes = 0; p.algo = BGNN_KNN_SIMT_F32; }   // k too large for the on-chip lists
@@ -74,6 +84,12 @@ static size_t knn_ws_bytes(const KnnPlan& p, int64_t nq, int64_t ndb) {
   const int planes = p.passes ? 2 : 1;
   for (int i = 0; i < planes; ++i) { add((size_t)nq * p.ld * 4); add((size_t)ndb * p.ld * 4); }
   if (p.f16) { add((size_t)nq * p.ldh * 2); add((size_t)ndb * p.ldh * 2); }
+  if (p.seed_rows) {
+    add((size_t)p.seed_rows * p.ldh * 2);
+    add((size_t)p.seed_tc.nlists * nq * p.seed_tc.kc * 4);
+    add((size_t)p.seed_tc.nlists * nq * p.seed_tc.kc * 4);
+    add((size_t)nq * 4);
+  }
   add(p.cand_elems * 4);
   add(p.cand_elems * 4);
   add((size_t)nq * 4);   // fallback row list
@@ -122,6 +138,15 @@ int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb
   if (p.passes) { qlo = w.take<float>((size_t)nq * p.ld); dlo = w.take<float>((size_t)ndb * p.ld); }
   unsigned short *qh = nullptr, *dh = nullptr;
   if (p.f16) { qh = w.take<unsigned short>((size_t)nq * p.ldh); dh = w.take<unsigned short>((size_t)ndb * p.ldh); }
+  unsigned short* sample = nullptr;
+  float *seed_val = nullptr, *seed_thr = nullptr;
+  int* seed_idx = nullptr;
+  if (p.seed_rows) {
+    sample = w.take<unsigned short>((size_t)p.seed_rows * p.ldh);
+    seed_val = w.take<float>((size_t)p.seed_tc.nlists * nq * p.seed_tc.kc);
+    seed_idx = w.take<int>((size_t)p.seed_tc.nlists * nq * p.seed_tc.kc);
+    seed_thr = w.take<float>((size_t)nq);
+  }
   float* cand_val = w.take<float>(p.cand_elems);
   int* cand_idx = w.take<int>(p.cand_elems);
   int* fb_rows = w.take<int>((size_t)nq);
@@ -145,7 +170,7 @@ int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb
                          cand_idx, stream);
     if (rc != BGNN_OK) return rc;
     rc = launch_knn_merge(cand_val, cand_idx, p.simt.nsplit, p.simt.kc, (int)nq, k, 0, nullptr, nullptr, nullptr,
-                          nullptr, d, p.ld, apply_sigmoid, -1.f, nullptr, nullptr, (long long*)out_idx, out_val,
+                          nullptr, d, p.ld, apply_sigmoid, -1.f, nullptr, nullptr, nullptr, (long long*)out_idx, out_val,
                           out_gap, nullptr, nullptr, stream);
     if (rc != BGNN_OK) return rc;
     if (out_stats) { set_int_kernel<<<1, 1, 0, stream>>>(out_stats, 0); BGNN_LAUNCH_CHECK(); }
@@ -155,20 +180,26 @@ int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb
   // tensor-core sweep nominates, merge re-scores + certifies, CUDA-core sweep redoes uncertified rows
   set_int_kernel<<<1, 1, 0, stream>>>(fb_count, 0);
   BGNN_LAUNCH_CHECK();
-  if (p.f16) rc = launch_knn_cosine_f16(qh, (int)nq, dh, (int)ndb, p.ldh, p.tc, cand_val, cand_idx, stream);
-  else rc = launch_knn_cosine_tc(qhi, qlo, (int)nq, dhi, dlo, (int)ndb, p.ld, p.passes, p.tc, cand_val, cand_idx, stream);
+  if (p.f16) {
+    if (p.seed_rows) {
+      rc = launch_knn_seed_f16(qh, (int)nq, dh, (int)ndb, p.ldh, p.seed_rows, p.seed_tc, sample, seed_val, seed_idx,
+                               seed_thr, stream);
+      if (rc != BGNN_OK) return rc;
+    }
+    rc = launch_knn_cosine_f16(qh, (int)nq, dh, (int)ndb, p.ldh, p.tc, seed_thr, cand_val, cand_idx, stream);
+  } else rc = launch_knn_cosine_tc(qhi, qlo, (int)nq, dhi, dlo, (int)ndb, p.ld, p.passes, p.tc, cand_val, cand_idx, stream);
   if (rc != BGNN_OK) return rc;
   // error bound of the approximate dot product of two unit rows (see DESIGN.md "kNN exactness")
   const float delta = p.f16 ? (9.7657e-4f + 5.97e-8f * sqrtf((float)d) + 4.0e-6f) : ((p.passes == 3) ? 3.0e-5f : 2.0e-3f);
   rc = launch_knn_merge(cand_val, cand_idx, p.tc.nlists, p.tc.kc, (int)nq, k, 1, qhi, qlo, dhi, dlo, p.ld, p.ld,
-                        apply_sigmoid, delta, nullptr, nullptr, (long long*)out_idx, out_val, out_gap, fb_rows,
+                        apply_sigmoid, delta, seed_thr, nullptr, nullptr, (long long*)out_idx, out_val, out_gap, fb_rows,
                         fb_count, stream);
   if (rc != BGNN_OK) return rc;
   rc = launch_knn_simt(BGNN_PAIR_DOT, qhi, qlo, (int)nq, dhi, dlo, (int)ndb, p.ld, p.ld, nullptr, 0.f, apply_sigmoid,
                        p.simt.kc, p.simt.nsplit, p.simt.per_split, fb_rows, fb_count, cand_val, cand_idx, stream);
   if (rc != BGNN_OK) return rc;
   rc = launch_knn_merge(cand_val, cand_idx, p.simt.nsplit, p.simt.kc, (int)nq, k, 0, nullptr, nullptr, nullptr,
-                        nullptr, p.ld, p.ld, apply_sigmoid, -1.f, fb_rows, fb_count, (long long*)out_idx, out_val,
+                        nullptr, p.ld, p.ld, apply_sigmoid, -1.f, nullptr, fb_rows, fb_count, (long long*)out_idx, out_val,
                         out_gap, nullptr, nullptr, stream);
   if (rc != BGNN_OK) return rc;
   if (out_stats) { copy_int_kernel<<<1, 1, 0, stream>>>(fb_count, out_stats); BGNN_LAUNCH_CHECK(); }
@@ -198,7 +229,7 @@ int bgnn_knn_addrelu_f32(const float* Uq, int64_t nq, const float* Udb, int64_t 
                            p.kc, p.nsplit, p.per_split, nullptr, nullptr, cand_val, cand_idx, stream);
   if (rc != BGNN_OK) return rc;
   return launch_knn_merge(cand_val, cand_idx, p.nsplit, p.kc, (int)nq, k, 0, nullptr, nullptr, nullptr, nullptr, h, h,
-                          apply_sigmoid, -1.f, nullptr, nullptr, (long long*)out_idx, out_val, out_gap, nullptr,
+                          apply_sigmoid, -1.f, nullptr, nullptr, nullptr, (long long*)out_idx, out_val, out_gap, nullptr,
                           nullptr, stream);
 }
 

@@ -18,8 +18,8 @@ int launch_normalize_split(const float* x, long long n, int d, int ld, int norma
                            cudaStream_t stream);
 int launch_knn_merge(const float* cand_val, const int* cand_idx, int nlists, int kc, int nq, int k, int rescore,
                      const float* qhi, const float* qlo, const float* dhi, const float* dlo, int d, int ld,
-                     int apply_sigmoid, float delta, const int* row_list, const int* row_count, long long* out_idx,
-                     float* out_val, float* out_gap, int* fb_rows, int* fb_count, cudaStream_t stream);
+                     int apply_sigmoid, float delta, const float* seed_thr, const int* row_list, const int* row_count,
+                     long long* out_idx, float* out_val, float* out_gap, int* fb_rows, int* fb_count, cudaStream_t stream);
 
 // knn_cosine_sm100.cu  (tcgen05 / TMEM / TMA)
 struct TcPlan {
@@ -35,11 +35,15 @@ int launch_knn_cosine_tc(const float* qhi, const float* qlo, int nq, const float
                          int passes, const TcPlan& plan, float* cand_val, int* cand_idx, cudaStream_t stream);
 
 // knn_cosine_f16_sm100.cu  (tcgen05 kind::f16, single pass)
-TcPlan tc_plan_f16(int nq, int ndb, int d, int k);
+constexpr int kSeedKc = 4;    // list length of the threshold-seeding sweep over a db sample
+TcPlan tc_plan_f16(int nq, int ndb, int d, int k, int kc_fixed = 0);
+int knn_seed_rows(int ndb, int k);   // sampled db rows for threshold seeding (0 = no seeding)
+int launch_knn_seed_f16(const void* qh, int nq, const void* dh, int ndb, int ldh, int srows, const TcPlan& seed_plan,
+                        void* sample, float* cand_val, int* cand_idx, float* seed, cudaStream_t stream);
 int launch_normalize_f16(const float* x, long long n, int d, int ld, int ldh, int normalize, float* xn, void* xh,
                          cudaStream_t stream);
-int launch_knn_cosine_f16(const void* qh, int nq, const void* dh, int ndb, int ldh, const TcPlan& plan, float* cand_val,
-                          int* cand_idx, cudaStream_t stream);
+int launch_knn_cosine_f16(const void* qh, int nq, const void* dh, int ndb, int ldh, const TcPlan& plan,
+                          const float* thr_init, float* cand_val, int* cand_idx, cudaStream_t stream);
 
 // csr_build.cu
 size_t csr_build_workspace_bytes(long long e);

@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(MG_WARPS * 32)
 knn_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int nlists, int kc, int nq, int k,
                  int rescore, const float* __restrict__ qhi, const float* __restrict__ qlo,
                  const float* __restrict__ dhi, const float* __restrict__ dlo, int d, int ld, int apply_sigmoid,
-                 float delta, const int* __restrict__ row_list, const int* __restrict__ row_count,
-                 long long* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ out_gap,
+                 float delta, const float* __restrict__ seed_thr, const int* __restrict__ row_list,
+                 const int* __restrict__ row_count, long long* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ out_gap,
                  int* __restrict__ fb_rows, int* __restrict__ fb_count) {
   __shared__ float sv[MG_WARPS][MG_MAXC];
   __shared__ int si[MG_WARPS][MG_MAXC];
@@ -74,7 +74,8 @@ knn_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ can
   int* ix = si[wid];
   // Largest approximate score any list may have discarded: a full list dropped only columns scoring
   // <= its minimum; a list that is not full kept every column of its split.
-  float worst_thr = -INFINITY;
+  // A seeded sweep additionally dropped every column scoring <= the row's seed threshold.
+  float worst_thr = seed_thr ? __ldg(seed_thr + row) : -INFINITY;
   for (int l = 0; l < nlists; ++l) {
     const long long base = ((long long)l * nq + row) * kc;
     float lmin = INFINITY;
@@ -165,15 +166,16 @@ knn_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ can
 
 int launch_knn_merge(const float* cand_val, const int* cand_idx, int nlists, int kc, int nq, int k, int rescore,
                      const float* qhi, const float* qlo, const float* dhi, const float* dlo, int d, int ld,
-                     int apply_sigmoid, float delta, const int* row_list, const int* row_count, long long* out_idx,
-                     float* out_val, float* out_gap, int* fb_rows, int* fb_count, cudaStream_t stream) {
+                     int apply_sigmoid, float delta, const float* seed_thr, const int* row_list, const int* row_count,
+                     long long* out_idx, float* out_val, float* out_gap, int* fb_rows, int* fb_count,
+                     cudaStream_t stream) {
   if (nq <= 0) return BGNN_OK;
   if (nlists * kc > MG_MAXC) return BGNN_ERR_UNSUPPORTED;
   if (rescore && (ld % 4 != 0 || d % 4 != 0)) return BGNN_ERR_INVALID_ARG;
   size_t dyn = rescore ? (size_t)MG_WARPS * ld * sizeof(float) : 0;
   knn_merge_kernel<<<(nq + MG_WARPS - 1) / MG_WARPS, MG_WARPS * 32, dyn, stream>>>(
-      cand_val, cand_idx, nlists, kc, nq, k, rescore, qhi, qlo, dhi, dlo, d, ld, apply_sigmoid, delta, row_list,
-      row_count, out_idx, out_val, out_gap, fb_rows, fb_count);
+      cand_val, cand_idx, nlists, kc, nq, k, rescore, qhi, qlo, dhi, dlo, d, ld, apply_sigmoid, delta, seed_thr,
+      row_list, row_count, out_idx, out_val, out_gap, fb_rows, fb_count);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }

@@ -17,6 +17,9 @@ __device__ __forceinline__ Chunk<VEC> ld_chunk(const float* __restrict__ p, bool
   if (VEC == 4) {
     float4 t = ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
     c.v[0] = t.x; c.v[1 % VEC] = t.y; c.v[2 % VEC] = t.z; c.v[3 % VEC] = t.w;
+  } else if (VEC == 2) {
+    float2 t = ok ? __ldg(reinterpret_cast<const float2*>(p)) : make_float2(0.f, 0.f);
+    c.v[0] = t.x; c.v[1 % VEC] = t.y;
   } else {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) c.v[i] = ok ? __ldg(p + i) : 0.f;
@@ -29,6 +32,8 @@ __device__ __forceinline__ void st_chunk(float* __restrict__ p, const Chunk<VEC>
   if (!ok) return;
   if (VEC == 4) {
     *reinterpret_cast<float4*>(p) = make_float4(c.v[0], c.v[1 % VEC], c.v[2 % VEC], c.v[3 % VEC]);
+  } else if (VEC == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(c.v[0], c.v[1 % VEC]);
   } else {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) p[i] = c.v[i];

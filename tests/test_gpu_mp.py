@@ -115,7 +115,7 @@ def _agg_inputs(n, c, e, seed):
     return eall, e1, e2, cm, Hs, Ht, a1, a2, gout
 
 
-@pytest.mark.parametrize("n,c,e", [(50, 1, 300), (300, 2, 3000), (1000, 31, 12000), (1000, 64, 12000), (700, 100, 5000),
+@pytest.mark.parametrize("n,c,e", [(50, 1, 300), (300, 2, 3000), (300, 6, 3000), (500, 62, 6000), (1000, 31, 12000), (1000, 64, 12000), (700, 100, 5000),
                                    (513, 128, 9000), (400, 256, 4000), (200, 300, 2000), (150, 512, 1500)])
 def test_gat_aggregate_forward_backward_random(n, c, e):
     ops = _ops()

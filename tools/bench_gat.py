@@ -1,5 +1,5 @@
 """Kernel-level timing of the fused AdaptedConv aggregation (fwd / bwd) and SpMM on the bench graph.
-Usage: python tools/bench_gat.py [n_log2=20] [reps=10]"""
+Usage: python tools/bench_gat.py [n_log2=20] [reps=10] [widths=2,31,64,128,256]"""
 import os
 import sys
 
@@ -33,7 +33,8 @@ def main():
     cm8 = cm.to(torch.uint8)
     peak = bench.load_peaks()["hbm_gbs"]
     print("n=%d e=%d" % (n, e))
-    for c in (2, 31, 64, 128, 256):
+    widths = [int(t) for t in sys.argv[3].split(",")] if len(sys.argv) > 3 else [2, 31, 64, 128, 256]
+    for c in widths:
         Hs = torch.randn(n, c, device=dev, requires_grad=True)
         Ht = torch.randn(n, c, device=dev, requires_grad=True)
         a1 = torch.randn(c, device=dev, requires_grad=True)

@@ -23,6 +23,7 @@
 //              thread-private list in shared memory
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -55,6 +56,15 @@ __device__ __forceinline__ float max3f(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
+}
+
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) [4,6), a/b format F16 (0)
@@ -95,20 +105,91 @@ int launch_normalize_f16(const float* x, long long n, int d, int ld, int ldh, in
   return BGNN_OK;
 }
 
-template <int BN>
+// ---- epilogue slow path, out of line -------------------------------------------------------------------
+// The hot loop of an epilogue warp is the max tree of a chunk; everything a threshold hit needs (finding the
+// columns, the pending FIFO, the heap) lives in two __noinline__ functions so that the unrolled per-tile loop
+// stays a few hundred instructions (four inlined copies of it thrashed the instruction cache).
+struct EpiState {
+  int cnt;      // heap fill
+  int fcnt;     // pending FIFO fill
+  float lthr;   // worst kept heap value (-inf until the heap is full)
+  float thr;    // threshold the thread filters with = max(own heap, partner heap, seed), slightly stale
+};
+struct EpiAddr {                // shared-window byte addresses of this thread's columns
+  uint32_t val, idx;            // heap [kc][128]
+  uint32_t fv, fi;              // FIFO [F16_FCAP][128]
+  uint32_t thr;                 // this warp's published heap threshold of the row
+  int kc;
+};
+
+// FIFO -> heap (FIFO order = index order, which the heap's tie rule relies on)
+static __device__ __noinline__ EpiState epi_drain(EpiState e, EpiAddr a) {
+  ListState st;
+  st.cnt = e.cnt;
+  st.thr = e.lthr;
+  for (int s = 0; s < e.fcnt; ++s) {
+    const float v = lds_f32(a.fv + s * (F16_BM * 4));
+    const int j = lds_s32(a.fi + s * (F16_BM * 4));
+    if (v > st.thr) list_push(a.val, a.idx, F16_BM * 4, a.kc, st, v, j);
+  }
+  e.cnt = st.cnt;
+  e.lthr = st.thr;
+  e.fcnt = 0;
+  e.thr = fmaxf(e.thr, st.thr);
+  sts_f32(a.thr, st.thr);
+  return e;
+}
+
+// queue every column of one group of 8 that beats the threshold, in index order
+static __device__ __noinline__ EpiState epi_scan8(EpiState e, EpiAddr a, int jbase, float v0, float v1, float v2,
+                                                  float v3, float v4, float v5, float v6, float v7) {
+  const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+  int last = -1;
+  while (true) {
+    float cv = -INFINITY;
+    int cc = -1, cnt = 0;
+#pragma unroll
+    for (int c = 7; c >= 0; --c) {
+      const bool p = (c > last) && (v[c] > e.thr);
+      cv = p ? v[c] : cv;
+      cc = p ? c : cc;
+      cnt += p ? 1 : 0;
+    }
+    if (cc < 0) break;
+    if (e.fcnt == F16_FCAP) e = epi_drain(e, a);
+    if (cv > e.thr) {                               // the drain may have raised the threshold
+      sts_f32(a.fv + e.fcnt * (F16_BM * 4), cv);
+      sts_s32(a.fi + e.fcnt * (F16_BM * 4), jbase + cc);
+      ++e.fcnt;
+    }
+    if (cnt == 1) break;
+    last = cc;
+  }
+  return e;
+}
+
+// PAIR: two CTAs of a cluster (two neighbouring query blocks) share every db tile -- each loads HALF of it, and
+// the leader's tcgen05.mma.cta_group::2 (M = 256) reads both halves.  L2 -> shared-memory traffic and the
+// shared-memory fill rate per SM halve; both bounded the single-CTA kernel (profiles/README.md, r01g).
+// MODE: 0 = sweep, 1 = seed sweep over the db sample (segment maxima only), 2 = sweep with the BGNN_F16_DBG
+// bottleneck experiments / wait-cycle instrumentation compiled in (tools/diag_knn_*.sh).
+template <int BN, bool PAIR, int MODE>
 __global__ void __launch_bounds__(F16_THREADS, 1)
 knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
-                      int nq, int ndb, int kblocks, int tiles_total, int tiles_per_split, int kc, int stages,
+                      int nq, int ndb, int kblocks, int tiles_total, int tiles_per_split, int kc, int stages, int kps,
                       const float* __restrict__ thr_init, float* __restrict__ cand_val, int* __restrict__ cand_idx,
-                      int dbg) {
-  constexpr int B_STAGE = BN * F16_BK * 2;
+                      int seed_segs, int dbg_arg) {
+  constexpr bool SEED = MODE == 1;
+  const int dbg = (MODE == 2) ? dbg_arg : 0;       // folds every experiment branch away outside MODE 2
+  constexpr int B_ROWS = PAIR ? BN / 2 : BN;     // db rows of a tile this CTA loads
+  constexpr int B_STAGE = B_ROWS * F16_BK * 2;
   constexpr int NBUF = 512 / BN;                 // accumulator buffers in TMEM: 2 x 256 or 4 x 128 columns
   constexpr int TMEM_COLS = 512;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* a_base = smem;                                          // kblocks * 16 KB, resident
   unsigned char* b_base = a_base + (size_t)kblocks * F16_A_KBLOCK;       // stages * B_STAGE ring
-  float* lval = reinterpret_cast<float*>(b_base + (size_t)stages * B_STAGE);   // [2][kc][128]
+  float* lval = reinterpret_cast<float*>(b_base + (size_t)stages * kps * B_STAGE);   // [2][kc][128]
   int* lidx = reinterpret_cast<int*>(lval + (size_t)2 * kc * F16_BM);           // [2][kc][128]
   float* ffv = reinterpret_cast<float*>(lidx + (size_t)2 * kc * F16_BM);     // [2][FCAP][128] pending values
   int* ffi = reinterpret_cast<int*>(ffv + 2 * F16_FCAP * F16_BM);             // [2][FCAP][128] pending indices
@@ -122,6 +203,7 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 2 * NBUF + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader: issues the MMAs, owns full / tempty / a barriers
   const int q0 = blockIdx.x * F16_BM;
   const int split = blockIdx.y;
   const int tile_begin = split * tiles_per_split;
@@ -130,17 +212,23 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    for (int b = 0; b < NBUF; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 8); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), PAIR ? 16 : 8); }
     mbar_init(smem_u32(a_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {                                      // the same warp of both CTAs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();  // barrier inits visible to the peer before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -149,52 +237,89 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_db) : "memory");
+      // PAIR: both CTAs load (their query block, their half of every db tile) but the bytes are counted on the
+      // LEADER's barriers, which alone announces the totals
       const uint32_t ab = smem_u32(a_bar);
-      mbar_expect_tx(ab, (uint32_t)(kblocks * F16_A_KBLOCK));
-      for (int kb = 0; kb < kblocks; ++kb)
-        tma_load_2d(smem_u32(a_base + (size_t)kb * F16_A_KBLOCK), &map_q, ab, kb * F16_BK, q0);
-      int it = 0;
+      if (rank == 0) mbar_expect_tx(ab, (uint32_t)((PAIR ? 2 : 1) * kblocks * F16_A_KBLOCK));
+      const uint32_t ab_l = PAIR ? mapa_rank(ab, 0) : ab;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        if (PAIR) tma_load_2d_pair(smem_u32(a_base + (size_t)kb * F16_A_KBLOCK), &map_q, ab_l, kb * F16_BK, q0);
+        else tma_load_2d(smem_u32(a_base + (size_t)kb * F16_A_KBLOCK), &map_q, ab, kb * F16_BK, q0);
+      }
+      // Ring of `stages` slots; a slot holds `kps` consecutive k-blocks of one db tile and is announced by ONE
+      // barrier (per-slot bookkeeping of this thread, not L2 bandwidth, bounded the operand stream: r01g notes).
+      int s = 0, nloads = 0;
+      uint32_t ph = 0;
+      long long w_empty = 0, t_start = clock64();
       for (int t = 0; t < ntiles; ++t) {
-        const int db0 = (tile_begin + t) * BN;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        const int db0 = (tile_begin + t) * BN + (int)rank * B_ROWS;
+        for (int kb0 = 0; kb0 < kblocks; kb0 += kps) {
+          const long long c0 = (dbg & 8) ? clock64() : 0;
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          if (dbg & 8) w_empty += clock64() - c0;
           const uint32_t fb = smem_u32(&full_bar[s]);
-          mbar_expect_tx(fb, (uint32_t)B_STAGE);
-          tma_load_2d(smem_u32(b_base + (size_t)s * B_STAGE), &map_db, fb, kb * F16_BK, db0);
+          if (rank == 0) mbar_expect_tx(fb, (uint32_t)((PAIR ? 2 : 1) * kps * B_STAGE));
+          const uint32_t fb_l = PAIR ? mapa_rank(fb, 0) : fb;
+          const uint32_t dst = smem_u32(b_base + (size_t)s * kps * B_STAGE);
+          for (int kk = 0; kk < kps; ++kk) {
+            if (PAIR) tma_load_2d_pair(dst + kk * B_STAGE, &map_db, fb_l, (kb0 + kk) * F16_BK, db0);
+            else tma_load_2d(dst + kk * B_STAGE, &map_db, fb, (kb0 + kk) * F16_BK, db0);
+          }
+          ++nloads;
+          if (++s == stages) { s = 0; ph ^= 1u; }
         }
       }
+      if ((dbg & 8) && blockIdx.x < 2 && blockIdx.y == 0)
+        printf("cta %d producer: total %lld cyc, waiting for a free slot %lld cyc (%d slot loads)\n", (int)blockIdx.x,
+               clock64() - t_start, w_empty, nloads);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(F16_BM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * F16_BM : F16_BM, BN);
       mbar_wait(smem_u32(a_bar), 0u);
       tc_fence_after();
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      const uint64_t ad0 = make_kmajor_sw128_desc(smem_u32(a_base));
+      const uint64_t bd0 = make_kmajor_sw128_desc(smem_u32(b_base));
+      long long w_full = 0, w_tempty = 0, t_start = clock64();
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t % NBUF;
         const uint32_t tph = (uint32_t)(t / NBUF) & 1u;
+        long long c0 = (dbg & 8) ? clock64() : 0;
         mbar_wait(smem_u32(&tempty_bar[buf]), tph ^ 1u);
+        if (dbg & 8) w_tempty += clock64() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        for (int kb0 = 0; kb0 < kblocks; kb0 += kps) {
+          c0 = (dbg & 8) ? clock64() : 0;
           mbar_wait(smem_u32(&full_bar[s]), ph);
+          if (dbg & 8) w_full += clock64() - c0;
           tc_fence_after();
-          const uint64_t ad = make_kmajor_sw128_desc(smem_u32(a_base + (size_t)kb * F16_A_KBLOCK));
-          const uint64_t bd = make_kmajor_sw128_desc(smem_u32(b_base + (size_t)s * B_STAGE));
+          // descriptors advance in 16-byte units: a k-block of A is 16 KB, of B B_STAGE bytes; 16 fp16 (one MMA
+          // K step) are 32 B inside the 128-B swizzle row
+          uint64_t ad = ad0 + (uint64_t)(kb0 * (F16_A_KBLOCK >> 4));
+          uint64_t bd = bd0 + (uint64_t)(s * kps * (B_STAGE >> 4));
+          for (int kk = 0; kk < kps; ++kk, ad += (F16_A_KBLOCK >> 4), bd += (B_STAGE >> 4)) {
 #pragma unroll
-          for (int k4 = 0; k4 < F16_BK / F16_UMMA_K; ++k4) {
-            // advance 32 B (= 16 fp16) inside the 128-B swizzle row: +2 in 16-B units
-            if (!(dbg & 4)) tc_mma_f16(d_tmem, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0 ? 1u : 0u);
+            for (int k4 = 0; k4 < F16_BK / F16_UMMA_K; ++k4) {
+              if (dbg & 4) continue;
+              const uint32_t acc = (kb0 + kk + k4) != 0 ? 1u : 0u;
+              if (PAIR) tc_mma_f16_pair(d_tmem, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, acc);
+              else tc_mma_f16(d_tmem, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, acc);
+            }
           }
-          tc_commit(smem_u32(&empty_bar[s]));      // frees the ring slot when these MMAs retire
+          // frees the ring slot (in both CTAs of a pair) when these MMAs retire
+          if (PAIR) tc_commit_pair(smem_u32(&empty_bar[s])); else tc_commit(smem_u32(&empty_bar[s]));
+          if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        tc_commit(smem_u32(&tfull_bar[buf]));      // accumulator ready for the epilogue
+        // accumulator ready for the epilogue (of both CTAs)
+        if (PAIR) tc_commit_pair(smem_u32(&tfull_bar[buf])); else tc_commit(smem_u32(&tfull_bar[buf]));
       }
+      if ((dbg & 8) && blockIdx.x < 2 && blockIdx.y == 0)
+        printf("cta %d mma issuer: total %lld cyc, waiting for operands %lld cyc, for a free accumulator %lld cyc (%d tiles)\n",
+               (int)blockIdx.x, clock64() - t_start, w_full, w_tempty, ntiles);
     }
   } else {
     // ===================== epilogue: thread <-> query row, warp pair <-> lane quarter =====================
@@ -212,131 +337,141 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const uint32_t other_thr_s = smem_addr(thr_sh + (half ^ 1) * F16_BM + r_in_tile);
     sts_f32(my_thr_s, -INFINITY);
     asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only
-    ListState st = list_init();
-    // effective threshold = max(own list, partner list, seed): the seed is a score that at least kc_seed db
+    // effective threshold = max(own list, partner list, seed): the seed is a score that at least kSeedKc db
     // rows of a sample reach (knn_seed_thr_kernel), so the lists skip most of their start-up insertions
-    float thr = (thr_init && row_ok) ? __ldg(thr_init + q0 + r_in_tile) : -INFINITY;
-    bool partial = false;
+    EpiState es;
+    es.cnt = 0;
+    es.fcnt = 0;
+    es.lthr = -INFINITY;
+    es.thr = (thr_init && row_ok) ? __ldg(thr_init + q0 + r_in_tile) : -INFINITY;
     // Heap insertions are deferred: a column that beats the threshold is appended to a small per-thread
     // FIFO (two stores), and the FIFOs are drained into the heaps by ALL lanes of the warp together every
     // F16_DRAIN_TILES tiles (or by one lane alone when its FIFO is full).  In steady state a chunk holds a
     // candidate for one or two of the 32 rows only, so inline insertion ran the long heap code at 1/32 lane
     // occupancy (profiles/r01g); drained together it is shared by every row that has something pending.
     // The threshold a lane filters with is then slightly stale, which only lets a few more columns through.
-    const uint32_t my_fv_s = smem_addr(ffv + (size_t)half * F16_FCAP * F16_BM + r_in_tile);
-    const uint32_t my_fi_s = smem_addr(ffi + (size_t)half * F16_FCAP * F16_BM + r_in_tile);
-    int fcnt = 0;
-    auto drain = [&]() {
-      for (int s = 0; s < fcnt; ++s) {
-        const float v = lds_f32(my_fv_s + s * (F16_BM * 4));
-        const int j = lds_s32(my_fi_s + s * (F16_BM * 4));
-        if (v > st.thr) list_push(my_val_s, my_idx_s, F16_BM * 4, kc, st, v, j);   // FIFO order = index order
-      }
-      fcnt = 0;
-      thr = fmaxf(thr, st.thr);
-      sts_f32(my_thr_s, st.thr);
-    };
-    // one 32-column chunk held in registers: group maxima vs the running threshold; the rare path stays in
-    // registers too -- per group of 8 columns, pick the first column (index order) that beats the threshold,
-    // queue it, and rescan only if the group held more than one candidate
-    auto process_chunk = [&](float (&r)[32], int jb) {
-      if (partial) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) r[c] = (jb + c < ndb) ? r[c] : -INFINITY;
-      }
-      float gm[4];                                  // 3-input maxima (FMNMX3): 4 instructions per group of 8
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float m012 = max3f(r[g * 8 + 0], r[g * 8 + 1], r[g * 8 + 2]);
-        const float m345 = max3f(r[g * 8 + 3], r[g * 8 + 4], r[g * 8 + 5]);
-        gm[g] = max3f(m012, m345, fmaxf(r[g * 8 + 6], r[g * 8 + 7]));
-      }
-      const float mx = max3f(gm[0], gm[1], fmaxf(gm[2], gm[3]));
-      if (row_ok && mx > thr) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (gm[g] > thr) {
-            int last = -1;
-            while (true) {
-              float cv = -INFINITY;
-              int cc = -1, cnt = 0;
-#pragma unroll
-              for (int c = 7; c >= 0; --c) {
-                const bool p = (c > last) && (r[g * 8 + c] > thr);
-                cv = p ? r[g * 8 + c] : cv;
-                cc = p ? c : cc;
-                cnt += p ? 1 : 0;
-              }
-              if (cc < 0) break;
-              if (fcnt == F16_FCAP) drain();
-              if (cv > thr) {                       // the drain may have raised the threshold
-                sts_f32(my_fv_s + fcnt * (F16_BM * 4), cv);
-                sts_s32(my_fi_s + fcnt * (F16_BM * 4), jb + g * 8 + cc);
-                ++fcnt;
-              }
-              if (cnt == 1) break;
-              last = cc;
-            }
-          }
-        }
-      }
-    };
+    EpiAddr ea;
+    ea.val = my_val_s;
+    ea.idx = my_idx_s;
+    ea.fv = smem_addr(ffv + (size_t)half * F16_FCAP * F16_BM + r_in_tile);
+    ea.fi = smem_addr(ffi + (size_t)half * F16_FCAP * F16_BM + r_in_tile);
+    ea.thr = my_thr_s;
+    ea.kc = kc;
+    float seg_max = -INFINITY, seed_min = INFINITY;   // seed mode only (see below)
+    // Seed mode (the sweep over the db sample): no lists at all.  The tiles of this CTA are cut into seed_segs
+    // segments; the smallest of the segment maxima is a score that at least seed_segs sampled rows reach, which
+    // is all the seed has to guarantee -- maxima only instead of a top-k.
+    const int seg_tiles = SEED ? max(1, ntiles / max(seed_segs, 1)) : 0;
+    int seg_left = seg_tiles, segs_done = 0;
+    int drain_left = F16_DRAIN_TILES;
+    long long w_tfull = 0, w_ld = 0, w_proc = 0, e_start = clock64();
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t % NBUF;
       const uint32_t tph = (uint32_t)(t / NBUF) & 1u;
-      if ((t % F16_DRAIN_TILES) == F16_DRAIN_TILES - 1 && __any_sync(0xffffffffu, fcnt > 0)) drain();
+      if (!SEED && --drain_left == 0) {
+        drain_left = F16_DRAIN_TILES;
+        if (__any_sync(0xffffffffu, es.fcnt > 0)) es = epi_drain(es, ea);
+      }
+      long long c0 = (dbg & 8) ? clock64() : 0;
       mbar_wait(smem_u32(&tfull_bar[buf]), tph);
+      if (dbg & 8) { const long long c1 = clock64(); w_tfull += c1 - c0; c0 = c1; }
       tc_fence_after();
       const int db0 = (tile_begin + t) * BN;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
-      partial = db0 + BN > ndb;                     // only the last db tile has zero-filled columns
       if (dbg & 2) {                                // bottleneck experiments: hand the buffer straight back
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[buf]), 0)); else mbar_arrive(smem_u32(&tempty_bar[buf]));
+        }
         continue;
       }
-      // Software pipeline over this warp's chunks (half, half+2, ...): the tcgen05.ld of the next chunk is
-      // in flight while the current one is reduced.  The TMEM buffer goes back to the MMA issuer as soon as
-      // the last chunk has landed in registers.
-      constexpr int NCH = BN / 64;                  // chunks per warp per tile (even)
-      float ra[32], rb[32];
-      tc_ld32(taddr0 + (uint32_t)(half * 32), ra);
-#pragma unroll 1
-      for (int i = 0; i < NCH; i += 2) {
-        const int ch_a = half + 2 * i, ch_b = ch_a + 2;
-        tc_wait_ld();
-        tc_ld32(taddr0 + (uint32_t)(ch_b * 32), rb);
-        thr = fmaxf(thr, lds_f32(other_thr_s));
-        if (!(dbg & 1)) process_chunk(ra, db0 + ch_a * 32);
-        tc_wait_ld();
-        if (i + 2 < NCH) {
-          tc_ld32(taddr0 + (uint32_t)((ch_b + 2) * 32), ra);
-        } else {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
-        }
-        thr = fmaxf(thr, lds_f32(other_thr_s));
-        if (!(dbg & 1)) process_chunk(rb, db0 + ch_b * 32);
+      // All of this warp's chunks of the tile (half, half+2, ...) are pulled into registers up front and the
+      // TMEM buffer goes straight back to the MMA issuer: how long the selection below takes (it varies a lot
+      // from warp to warp and tile to tile) no longer decides when the MMAs of tile t+2 may start.
+      constexpr int NCH = BN / 64;                  // chunks per warp per tile
+      float rr[NCH][32];
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) tc_ld32(taddr0 + (uint32_t)((half + 2 * i) * 32), rr[i]);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {                               // the MMA issuer lives in the leader CTA
+        if (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[buf]), 0)); else mbar_arrive(smem_u32(&tempty_bar[buf]));
       }
+      if (dbg & 8) { const long long c1 = clock64(); w_ld += c1 - c0; c0 = c1; }
+      if (db0 + BN > ndb) {                          // only the last db tile has zero-filled columns
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+#pragma unroll
+          for (int c = 0; c < 32; ++c) rr[i][c] = (db0 + (half + 2 * i) * 32 + c < ndb) ? rr[i][c] : -INFINITY;
+      }
+      if (!(dbg & 1)) {
+        // group maxima of ALL chunks first (3-input maxima, 4 instructions per group of 8, independent of each
+        // other), then one test per tile; a hit hands the groups concerned to the out-of-line scan
+        float gm[NCH][4];
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float m012 = max3f(rr[i][g * 8 + 0], rr[i][g * 8 + 1], rr[i][g * 8 + 2]);
+            const float m345 = max3f(rr[i][g * 8 + 3], rr[i][g * 8 + 4], rr[i][g * 8 + 5]);
+            gm[i][g] = max3f(m012, m345, fmaxf(rr[i][g * 8 + 6], rr[i][g * 8 + 7]));
+          }
+        float mx = max3f(gm[0][0], gm[0][1], fmaxf(gm[0][2], gm[0][3]));
+#pragma unroll
+        for (int i = 1; i < NCH; ++i) mx = fmaxf(mx, max3f(gm[i][0], gm[i][1], fmaxf(gm[i][2], gm[i][3])));
+        if (SEED) {
+          seg_max = fmaxf(seg_max, mx);
+          if (--seg_left == 0) {                     // a segment is complete (tiles past the last full one are ignored)
+            seg_left = seg_tiles;
+            if (segs_done++ < seed_segs) seed_min = fminf(seed_min, seg_max);
+            seg_max = -INFINITY;
+          }
+        } else {
+          es.thr = fmaxf(es.thr, lds_f32(other_thr_s));
+          if (row_ok && mx > es.thr) {
+#pragma unroll
+            for (int i = 0; i < NCH; ++i)
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                if (gm[i][g] > es.thr)
+                  es = epi_scan8(es, ea, db0 + (half + 2 * i) * 32 + g * 8, rr[i][g * 8 + 0], rr[i][g * 8 + 1],
+                                 rr[i][g * 8 + 2], rr[i][g * 8 + 3], rr[i][g * 8 + 4], rr[i][g * 8 + 5], rr[i][g * 8 + 6],
+                                 rr[i][g * 8 + 7]);
+          }
+        }
+      }
+      if (dbg & 8) w_proc += clock64() - c0;
     }
-    drain();
+    if ((dbg & 8) && blockIdx.x < 1 && blockIdx.y == 0 && lane == 0)
+      printf("cta %d epilogue warp %d: total %lld cyc, waiting for a tile %lld, tmem loads %lld, selection %lld (%d tiles)\n",
+             (int)blockIdx.x, warp, clock64() - e_start, w_tfull, w_ld, w_proc, ntiles);
+    if (SEED) {
+      // one value per (list, row): -inf when this CTA saw no complete segment
+      if (row_ok) cand_val[((long long)split * 2 + half) * nq + (q0 + r_in_tile)] = (seed_min < INFINITY) ? seed_min : -INFINITY;
+    } else {
+    es = epi_drain(es, ea);
     if (row_ok) {
       const long long base = (((long long)split * 2 + half) * nq + (q0 + r_in_tile)) * kc;
       for (int s = 0; s < kc; ++s) {
-        const bool f = s < st.cnt;
+        const bool f = s < es.cnt;
         cand_val[base + s] = f ? my_val[s * F16_BM] : -INFINITY;
         cand_idx[base + s] = f ? my_idx[s * F16_BM] : -1;
       }
     }
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();  // nobody leaves while the peer may still signal or be read
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -365,14 +500,24 @@ TcPlan tc_plan_f16(int nq, int ndb, int d, int k, int kc_fixed) {
   const int a_bytes = (ldh / F16_BK) * F16_A_KBLOCK;
   const int list_bytes = 2 * kc * F16_BM * 8 + F16_FIFO_BYTES;
   static const int force_bn = getenv("BGNN_F16_BN") ? atoi(getenv("BGNN_F16_BN")) : 0;   // tuning experiments
+  static const int pair_env = getenv("BGNN_F16_PAIR") ? atoi(getenv("BGNN_F16_PAIR")) : 0;   // measured slower
+  const int qblocks = (nq + F16_BM - 1) / F16_BM;
+  p.pair = (pair_env && qblocks >= 2) ? 1 : 0;
   for (int bn = (force_bn == 128 ? 128 : 256); bn >= 128; bn >>= 1) {
-    const int stage_bytes = bn * F16_BK * 2;
-    const int stages = (F16_SMEM_MAX - F16_SMEM_FIXED - a_bytes - list_bytes) / stage_bytes;
-    if (stages >= 3) { p.bn = bn; p.stages = min(stages, 8); break; }
+    const int stage_bytes = (p.pair ? bn / 2 : bn) * F16_BK * 2;
+    const int units = (F16_SMEM_MAX - F16_SMEM_FIXED - a_bytes - list_bytes) / stage_bytes;   // k-blocks that fit
+    if (units < 3) continue;
+    // one barrier per slot of kps k-blocks: as many k-blocks of a tile per slot as still leave >= 2 slots
+    const int kblocks = ldh / F16_BK;
+    int kps = kblocks;
+    while (kps > 1 && (kblocks % kps != 0 || units / kps < 2)) --kps;
+    p.bn = bn;
+    p.kps = kps;
+    p.stages = min(units / kps, 8);
+    break;
   }
   if (p.bn == 0) return p;                                  // caller falls back to another sweep
   const int tiles = (ndb + p.bn - 1) / p.bn;
-  const int qblocks = (nq + F16_BM - 1) / F16_BM;
   int ns = (2 * kNumSMs + qblocks - 1) / qblocks;            // fill the machine when nq is small
   ns = max(1, min(min(ns, tiles), min(8, BGNN_MERGE_MAX_CAND / (2 * kc))));
   if (ns < 1) { p.bn = 0; return p; }
@@ -383,41 +528,69 @@ TcPlan tc_plan_f16(int nq, int ndb, int d, int k, int kc_fixed) {
   return p;
 }
 
-template <int BN>
+static int f16_dbg_env() {
+  static const int dbg = getenv("BGNN_F16_DBG") ? atoi(getenv("BGNN_F16_DBG")) : 0;   // bottleneck experiments only
+  return dbg;
+}
+
+template <int BN, bool PAIR, int MODE>
 static int launch_f16_cfg(const void* qh, int nq, const void* dh, int ndb, int ldh, const TcPlan& plan,
-                          const float* thr_init, float* cand_val, int* cand_idx, cudaStream_t stream) {
+                          const float* thr_init, float* cand_val, int* cand_idx, int seed_segs, cudaStream_t stream) {
   CUtensorMap mq, md;
   int rc;
+  constexpr int B_ROWS = PAIR ? BN / 2 : BN;
   if ((rc = make_map_f16(&mq, qh, nq, ldh, F16_BM)) != BGNN_OK) return rc;
-  if ((rc = make_map_f16(&md, dh, ndb, ldh, BN)) != BGNN_OK) return rc;
+  if ((rc = make_map_f16(&md, dh, ndb, ldh, B_ROWS)) != BGNN_OK) return rc;
   const int kblocks = ldh / F16_BK;
-  const size_t smem = F16_SMEM_FIXED + (size_t)kblocks * F16_A_KBLOCK + (size_t)plan.stages * BN * F16_BK * 2 +
+  const size_t smem = F16_SMEM_FIXED + (size_t)kblocks * F16_A_KBLOCK + (size_t)plan.stages * plan.kps * B_ROWS * F16_BK * 2 +
                       (size_t)2 * plan.kc * F16_BM * 8 + F16_FIFO_BYTES;
-  if (smem > (size_t)F16_SMEM_MAX || plan.stages < 2) return BGNN_ERR_UNSUPPORTED;
-  auto kern = knn_cosine_f16_kernel<BN>;
+  if (smem > (size_t)F16_SMEM_MAX || plan.stages < 2 || plan.kps < 1 || kblocks % plan.kps != 0) return BGNN_ERR_UNSUPPORTED;
+  auto kern = knn_cosine_f16_kernel<BN, PAIR, MODE>;
   BGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = (ndb + BN - 1) / BN;
-  dim3 grid((nq + F16_BM - 1) / F16_BM, plan.nsplit);
-  static const int dbg = getenv("BGNN_F16_DBG") ? atoi(getenv("BGNN_F16_DBG")) : 0;   // bottleneck experiments only
-  kern<<<grid, F16_THREADS, smem, stream>>>(mq, md, nq, ndb, kblocks, tiles, plan.tiles_per_split, plan.kc, plan.stages,
-                                            thr_init, cand_val, cand_idx, dbg);
-  BGNN_LAUNCH_CHECK();
+  const int qblocks = (nq + F16_BM - 1) / F16_BM;
+  const int dbg = f16_dbg_env();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(PAIR ? (qblocks + 1) / 2 * 2 : qblocks, plan.nsplit);   // a pair = two neighbouring query blocks
+  cfg.blockDim = dim3(F16_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BGNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mq, md, nq, ndb, kblocks, tiles, plan.tiles_per_split, plan.kc, plan.stages,
+                                   plan.kps, thr_init, cand_val, cand_idx, seed_segs, dbg));
   return BGNN_OK;
+}
+
+static int launch_f16_any(const void* qh, int nq, const void* dh, int ndb, int ldh, const TcPlan& plan,
+                          const float* thr_init, float* cand_val, int* cand_idx, int seed_segs, cudaStream_t stream) {
+  if (nq <= 0) return BGNN_OK;
+  if (ldh % F16_BK != 0) return BGNN_ERR_INVALID_ARG;
+  const int mode = seed_segs > 0 ? 1 : (f16_dbg_env() ? 2 : 0);
+#define F16_GO(BN_, PAIR_, MODE_) \
+  launch_f16_cfg<BN_, PAIR_, MODE_>(qh, nq, dh, ndb, ldh, plan, thr_init, cand_val, cand_idx, seed_segs, stream)
+#define F16_GO_MODE(BN_, PAIR_) (mode == 1 ? F16_GO(BN_, PAIR_, 1) : mode == 2 ? F16_GO(BN_, PAIR_, 2) : F16_GO(BN_, PAIR_, 0))
+  if (plan.bn == 256) return plan.pair ? F16_GO_MODE(256, true) : F16_GO_MODE(256, false);
+  if (plan.bn == 128) return plan.pair ? F16_GO_MODE(128, true) : F16_GO_MODE(128, false);
+#undef F16_GO_MODE
+#undef F16_GO
+  return BGNN_ERR_UNSUPPORTED;
 }
 
 int launch_knn_cosine_f16(const void* qh, int nq, const void* dh, int ndb, int ldh, const TcPlan& plan,
                           const float* thr_init, float* cand_val, int* cand_idx, cudaStream_t stream) {
-  if (nq <= 0) return BGNN_OK;
-  if (ldh % F16_BK != 0) return BGNN_ERR_INVALID_ARG;
-  if (plan.bn == 256) return launch_f16_cfg<256>(qh, nq, dh, ndb, ldh, plan, thr_init, cand_val, cand_idx, stream);
-  if (plan.bn == 128) return launch_f16_cfg<128>(qh, nq, dh, ndb, ldh, plan, thr_init, cand_val, cand_idx, stream);
-  return BGNN_ERR_UNSUPPORTED;
+  return launch_f16_any(qh, nq, dh, ndb, ldh, plan, thr_init, cand_val, cand_idx, 0, stream);
 }
 
 // ------------------------------------------------------------------------------------------ threshold seeding
 // A streaming top-KC list performs ~KC ln(n/KC) insertions, most of them while its threshold is still loose.
-// Seeding: sweep a strided SAMPLE of the db first (same kernel, tiny lists), take per query row a score that at
-// least kSeedKc sampled rows reach, and start the full sweep from that threshold.  Soundness is unchanged: the
+// Seeding: sweep a strided SAMPLE of the db first (same kernel in seed mode: segment maxima, no lists), take
+// per query row a score that at least kSeedKc sampled rows reach, and start the full sweep from that threshold.  Soundness is unchanged: the
 // merge kernel treats the seed as one more "largest discarded score" bound and certifies or falls back.
 int knn_seed_rows(int ndb, int k) {
   static const int off = getenv("BGNN_F16_NOSEED") ? atoi(getenv("BGNN_F16_NOSEED")) : 0;   // tuning experiments
@@ -440,24 +613,14 @@ gather_sample_f16_kernel(const uint4* __restrict__ src, long long ndb, int row_v
   dst[t] = __ldg(src + r * row_vecs + v);
 }
 
-// seed[row] = max over the FULL lists of the row of the list minimum (each full list holds kc sampled rows that
-// score at least its minimum); -inf when no list is full.
+// seed[row] = max over the row's lists of the list's segment-maxima minimum (each at least kSeedKc sampled
+// rows reach); -inf when no list saw a complete segment.
 __global__ void __launch_bounds__(256)
-knn_seed_thr_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int nlists, int kc, int nq,
-                    float* __restrict__ seed) {
+knn_seed_thr_kernel(const float* __restrict__ list_seed, int nlists, int nq, float* __restrict__ seed) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nq) return;
   float best = -INFINITY;
-  for (int l = 0; l < nlists; ++l) {
-    const long long base = ((long long)l * nq + row) * kc;
-    float lmin = INFINITY;
-    bool full = true;
-    for (int s = 0; s < kc; ++s) {
-      if (cand_idx[base + s] < 0) full = false;
-      lmin = fminf(lmin, cand_val[base + s]);
-    }
-    if (full) best = fmaxf(best, lmin);
-  }
+  for (int l = 0; l < nlists; ++l) best = fmaxf(best, list_seed[(long long)l * nq + row]);
   seed[row] = best;
 }
 
@@ -469,9 +632,9 @@ int launch_knn_seed_f16(const void* qh, int nq, const void* dh, int ndb, int ldh
   gather_sample_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const uint4*>(dh), ndb, row_vecs, srows, reinterpret_cast<uint4*>(sample));
   BGNN_LAUNCH_CHECK();
-  int rc = launch_knn_cosine_f16(qh, nq, sample, srows, ldh, seed_plan, nullptr, cand_val, cand_idx, stream);
+  int rc = launch_f16_any(qh, nq, sample, srows, ldh, seed_plan, nullptr, cand_val, cand_idx, kSeedKc, stream);
   if (rc != BGNN_OK) return rc;
-  knn_seed_thr_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(cand_val, cand_idx, seed_plan.nlists, seed_plan.kc, nq, seed);
+  knn_seed_thr_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(cand_val, seed_plan.nlists, nq, seed);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }

@@ -281,6 +281,8 @@ TcPlan tc_plan(int nq, int ndb, int d, int k, int passes) {
   p.tiles_per_split = (tiles + ns - 1) / ns;
   p.nsplit = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.nlists = p.nsplit;
+  p.pair = 0;
+  p.kps = 1;
   return p;
 }
 

@@ -32,11 +32,15 @@ SIGNATURES = {
     "bgnn_edges_to_csr": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bgnn_spmm_csr_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "bgnn_gatv2_fwd_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "bgnn_gatv2_fwd_ord_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "bgnn_rows_by_degree_workspace_bytes": (_sz, [_i64]),
+    "bgnn_rows_by_degree": (_i32, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     "bgnn_adapted_transform_fwd_f32": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "bgnn_adapted_transform_bwd_workspace_bytes": (_sz, [_i32]),
     "bgnn_adapted_transform_bwd_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "bgnn_gatv2_bwd_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "bgnn_gatv2_bwd_f32": (_i32, [_vp] * 5 + [_i64] + [_vp] * 5 + [_f32, _i64, _i32] + [_vp] * 9 + [_sz, _vp]),
+    "bgnn_gatv2_bwd_ord_f32": (_i32, [_vp] * 7 + [_i64] + [_vp] * 5 + [_f32, _i64, _i32] + [_vp] * 9 + [_sz, _vp]),
 }
 
 _lib = None
@@ -92,6 +96,7 @@ def workspace(nbytes, device):
 # bgnn_edges_to_csr are not counted)
 KERNELS_PER_CALL = {"bgnn_knn_cosine_f32": 8, "bgnn_knn_cosine_f32[simt]": 4, "bgnn_knn_addrelu_f32": 2,
                     "bgnn_edges_to_csr": 4, "bgnn_spmm_csr_f32": 1, "bgnn_gatv2_fwd_f32": 1, "bgnn_gatv2_bwd_f32": 3,
+                    "bgnn_gatv2_fwd_ord_f32": 1, "bgnn_gatv2_bwd_ord_f32": 3, "bgnn_rows_by_degree": 1,
                     "bgnn_adapted_transform_fwd_f32": 1, "bgnn_adapted_transform_bwd_f32": 2}
 launches = 0          # running count of kernels launched through the C ABI
 _timing = None        # None, or {name: [(start_event, end_event), ...]}

@@ -252,17 +252,49 @@ int bgnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* ed
                          (cudaStream_t)stream);
 }
 
+int bgnn_gatv2_fwd_ord_f32(const int32_t* rowptr, const int32_t* col, const int32_t* row_order, const uint8_t* dst_is_src,
+                           const float* Hs, const float* Ht, const float* af_t2s, const float* af_s2t, float slope,
+                           int64_t n, int c, float* out, float* row_max, float* row_sum, void* stream) {
+  if (n < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!rowptr || !col || !dst_is_src || !Hs || !Ht || !af_t2s || !af_s2t || !out)) return BGNN_ERR_INVALID_ARG;
+  return launch_gatv2_fwd(rowptr, col, row_order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, c, out, row_max, row_sum,
+                          (cudaStream_t)stream);
+}
+
 int bgnn_gatv2_fwd_f32(const int32_t* rowptr, const int32_t* col, const uint8_t* dst_is_src, const float* Hs,
                        const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n, int c,
                        float* out, float* row_max, float* row_sum, void* stream) {
-  if (n < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
-  if (n > 0 && (!rowptr || !col || !dst_is_src || !Hs || !Ht || !af_t2s || !af_s2t || !out)) return BGNN_ERR_INVALID_ARG;
-  return launch_gatv2_fwd(rowptr, col, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, c, out, row_max, row_sum,
-                          (cudaStream_t)stream);
+  return bgnn_gatv2_fwd_ord_f32(rowptr, col, nullptr, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, c, out, row_max,
+                                row_sum, stream);
+}
+
+size_t bgnn_rows_by_degree_workspace_bytes(int64_t n) { return n < 0 ? 0 : rows_by_degree_workspace_bytes(n); }
+
+int bgnn_rows_by_degree(const int32_t* rowptr, int64_t n, int min_degree, int32_t* order, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (n < 0 || min_degree < 0 || (n > 0 && (!rowptr || !order || !workspace))) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && workspace_bytes < rows_by_degree_workspace_bytes(n)) return BGNN_ERR_WORKSPACE;
+  return launch_rows_by_degree(rowptr, n, min_degree, order, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t bgnn_gatv2_bwd_workspace_bytes(int64_t n, int64_t e, int c) {
   return (n < 0 || e < 0 || c <= 0) ? 0 : gatv2_bwd_workspace_bytes(n, e, c);
+}
+
+int bgnn_gatv2_bwd_ord_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
+                           const int32_t* csr_to_csc, const int32_t* row_order, const int32_t* t_row_order, int64_t e,
+                           const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
+                           const float* af_s2t, float slope, int64_t n, int c, const float* out, const float* row_max,
+                           const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
+                           float* g_af_s2t, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 0 || e < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!rowptr || !col || !t_rowptr || !t_col || !csr_to_csc || !dst_is_src || !Hs || !Ht || !af_t2s ||
+                !af_s2t || !out || !row_max || !row_sum || !gout || !gHs || !gHt || !g_af_t2s || !g_af_s2t))
+    return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!workspace || workspace_bytes < gatv2_bwd_workspace_bytes(n, e, c))) return BGNN_ERR_WORKSPACE;
+  return launch_gatv2_bwd(rowptr, col, t_rowptr, t_col, csr_to_csc, row_order, t_row_order, e, dst_is_src, Hs, Ht, af_t2s,
+                          af_s2t, slope, n, c, out, row_max, row_sum, gout, gHs, gHt, g_af_t2s, g_af_s2t, workspace,
+                          workspace_bytes, (cudaStream_t)stream);
 }
 
 int bgnn_gatv2_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
@@ -271,14 +303,9 @@ int bgnn_gatv2_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t*
                        const float* out, const float* row_max, const float* row_sum, const float* gout, float* gHs,
                        float* gHt, float* g_af_t2s, float* g_af_s2t, void* workspace, size_t workspace_bytes,
                        void* stream) {
-  if (n < 0 || e < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
-  if (n > 0 && (!rowptr || !col || !t_rowptr || !t_col || !csr_to_csc || !dst_is_src || !Hs || !Ht || !af_t2s ||
-                !af_s2t || !out || !row_max || !row_sum || !gout || !gHs || !gHt || !g_af_t2s || !g_af_s2t))
-    return BGNN_ERR_INVALID_ARG;
-  if (n > 0 && (!workspace || workspace_bytes < gatv2_bwd_workspace_bytes(n, e, c))) return BGNN_ERR_WORKSPACE;
-  return launch_gatv2_bwd(rowptr, col, t_rowptr, t_col, csr_to_csc, e, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, c,
-                          out, row_max, row_sum, gout, gHs, gHt, g_af_t2s, g_af_s2t, workspace, workspace_bytes,
-                          (cudaStream_t)stream);
+  return bgnn_gatv2_bwd_ord_f32(rowptr, col, t_rowptr, t_col, csr_to_csc, nullptr, nullptr, e, dst_is_src, Hs, Ht, af_t2s,
+                                af_s2t, slope, n, c, out, row_max, row_sum, gout, gHs, gHt, g_af_t2s, g_af_s2t, workspace,
+                                workspace_bytes, stream);
 }
 
 int bgnn_adapted_transform_fwd_f32(const float* P, const uint8_t* is_src, const float* wd, const float* kg, int64_t n,

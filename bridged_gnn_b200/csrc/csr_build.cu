@@ -113,4 +113,48 @@ int launch_edges_to_csr(const long long* src, const long long* dst, long long e,
   return BGNN_OK;
 }
 
+// ---- rows by descending degree ---------------------------------------------------------------------------
+// The row-parallel gather kernels take an optional processing order: longest rows first, so that a hub row of
+// a kNN graph starts at once instead of forming the tail of the launch, and rows sharing a warp have similar
+// lengths.  Stable radix sort of (max_deg - deg, row): equal degrees keep ascending row order.
+// Rows shorter than min_degree all get the largest key: they follow the long rows in their natural order, which
+// keeps the row-level loads of narrow feature rows coalesced (min_degree = 0: full sort).
+__global__ void degree_keys_kernel(const int* __restrict__ rowptr, long long n, int min_degree,
+                                   unsigned int* __restrict__ keys, unsigned int* __restrict__ vals) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int deg = rowptr[i + 1] - rowptr[i];
+  keys[i] = deg >= min_degree ? 0x7ffffffeu - (unsigned int)deg : 0x7fffffffu;
+  vals[i] = (unsigned int)i;
+}
+
+static size_t degree_sort_temp_bytes(long long n) {
+  size_t a = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned int*)nullptr, (unsigned int*)nullptr,
+                                  (const unsigned int*)nullptr, (unsigned int*)nullptr, n);
+  return a;
+}
+
+size_t rows_by_degree_workspace_bytes(long long n) {
+  if (n <= 0) return 256;
+  return (size_t)n * 12 + degree_sort_temp_bytes(n) + 4 * 256;
+}
+
+int launch_rows_by_degree(const int* rowptr, long long n, int min_degree, int* order, void* ws, size_t ws_bytes,
+                          cudaStream_t stream) {
+  if (n < 0 || n >= (1ll << 31)) return BGNN_ERR_INVALID_ARG;
+  if (n == 0) return BGNN_OK;
+  Workspace w(ws, ws_bytes);
+  auto* k0 = w.take<unsigned int>(n);
+  auto* k1 = w.take<unsigned int>(n);
+  auto* v0 = w.take<unsigned int>(n);
+  size_t tb = degree_sort_temp_bytes(n);
+  auto* temp = w.take<char>(tb);
+  if (!w.ok()) return BGNN_ERR_WORKSPACE;
+  degree_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rowptr, n, min_degree, k0, v0);
+  BGNN_LAUNCH_CHECK();
+  BGNN_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, tb, k0, k1, v0, reinterpret_cast<unsigned int*>(order), n, 0, 31, stream));
+  return BGNN_OK;
+}
+
 }  // namespace bgnn

@@ -38,15 +38,19 @@ __device__ __forceinline__ float lrelu(float t, float slope) { return t > 0.f ? 
 // ------------------------------------------------------------------------------------------ forward
 template <int VEC, int G, int CH>
 __global__ void __launch_bounds__(256)
-gatv2_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const uint8_t* __restrict__ dst_is_src,
+gatv2_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ order,
+                 const uint8_t* __restrict__ dst_is_src,
                  const float* __restrict__ Hs, const float* __restrict__ Ht, const float* __restrict__ af_t2s,
                  const float* __restrict__ af_s2t, float slope, long long n, int c, float* __restrict__ out,
                  float* __restrict__ row_max, float* __restrict__ row_sum) {
   const int lane = threadIdx.x & 31;
   const int lane_g = threadIdx.x % G;
   const unsigned mask = group_mask<G>(lane);
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  if (row >= n) return;  // a group leaves together; shuffles below use the group's own mask
+  // `order` (optional): rows by descending degree -- hub rows start first instead of forming the tail of the
+  // launch, and the rows that share a warp have similar lengths
+  const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (slot >= n) return;  // a group leaves together; shuffles below use the group's own mask
+  const long long row = order ? (long long)__ldg(order + slot) : slot;
   const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
   if (beg == end) {
     // no incoming edge (rows owned by another rank in the destination-partitioned multi-GPU layout):
@@ -138,7 +142,7 @@ gatv2_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, co
   }
 }
 
-int launch_gatv2_fwd(const int* rowptr, const int* col, const uint8_t* dst_is_src, const float* Hs, const float* Ht,
+int launch_gatv2_fwd(const int* rowptr, const int* col, const int* order, const uint8_t* dst_is_src, const float* Hs, const float* Ht,
                      const float* af_t2s, const float* af_s2t, float slope, long long n, int c, float* out,
                      float* row_max, float* row_sum, cudaStream_t stream) {
   if (n <= 0) return BGNN_OK;
@@ -146,7 +150,7 @@ int launch_gatv2_fwd(const int* rowptr, const int* col, const uint8_t* dst_is_sr
   if (!pick_row_config(c, vec, g, ch)) return BGNN_ERR_UNSUPPORTED;
   long long blocks = (n * g + 255) / 256;
 #define CALL(V, G_, C_)                                                                                        \
-  gatv2_fwd_kernel<V, G_, C_><<<(unsigned)blocks, 256, 0, stream>>>(rowptr, col, dst_is_src, Hs, Ht, af_t2s,   \
+  gatv2_fwd_kernel<V, G_, C_><<<(unsigned)blocks, 256, 0, stream>>>(rowptr, col, order, dst_is_src, Hs, Ht, af_t2s,   \
                                                                       af_s2t, slope, n, c, out, row_max, row_sum)
   BGNN_ROW_DISPATCH(vec, g, ch, CALL);
 #undef CALL
@@ -171,21 +175,27 @@ int launch_gatv2_fwd(const int* rowptr, const int* col, const uint8_t* dst_is_sr
 // stores itself -- no cross-lane combination of mask words.  U edges are in flight per group; warps are
 // persistent over a static round-robin of row sets (no CTA barrier: a long row delays only its own warp, and
 // the d a_f summation order stays fixed).
-template <int VEC, int G, int CH, int U, int MINB>
+template <int VEC, int G, int CH, int U, int MINB, int ES>
 __global__ void __launch_bounds__(128, MINB)
 gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ csr_to_csc,
-                     const uint8_t* __restrict__ dst_is_src, const float* __restrict__ Hs, const float* __restrict__ Ht,
+                     const int* __restrict__ order, const uint8_t* __restrict__ dst_is_src, const float* __restrict__ Hs, const float* __restrict__ Ht,
                      const float* __restrict__ af_t2s, const float* __restrict__ af_s2t, float slope, long long n, int c,
                      int cw, const float* __restrict__ out, const float* __restrict__ row_max,
                      const float* __restrict__ row_sum, const float* __restrict__ gout, float* __restrict__ gHs,
                      float* __restrict__ gHt, unsigned* __restrict__ erec, unsigned* __restrict__ emask,
                      float* __restrict__ ga_part) {
-  constexpr int RPW = 32 / G;                      // rows per warp
+  // ES > 1 (narrow rows, G == 1): ES lanes share a row and split its EDGES (lane s takes edges s, s + ES, ...):
+  // consecutive lanes read consecutive col entries, and a hub row is no longer one lane's serial loop.
+  static_assert(ES == 1 || G == 1, "edge splitting is for rows a single lane can hold");
+  constexpr int RL = G * ES;                       // lanes per row
+  constexpr int RPW = 32 / RL;                     // rows per warp
   constexpr int EPL = VEC * CH;                    // contiguous features per lane
   static_assert(G == 1 || EPL == 8 || EPL == 16, "multi-lane rows own whole mask bytes");
   const int lane = threadIdx.x & 31;
   const int lane_g = lane % G;
+  const int sub = (lane / G) % ES;                 // which share of the row's edges
   const unsigned gmask = group_mask<G>(lane);
+  const unsigned rmask = group_mask<RL>(lane);
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int col0 = lane_g * EPL;
@@ -204,8 +214,9 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
   const bool mask_ok = col0 < c;
   const long long nsets = (n + RPW - 1) / RPW;
   for (long long set = wid; set < nsets; set += nwarps) {
-    const long long row = set * RPW + lane / G;
-    if (row >= n) continue;                        // whole groups leave together
+    const long long slot = set * RPW + lane / RL;
+    if (slot >= n) continue;                       // whole row groups leave together
+    const long long row = order ? (long long)__ldg(order + slot) : slot;
     const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     const bool is_src = dst_is_src[row] != 0;
     Chunk<VEC> gi[CH];
@@ -237,11 +248,12 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
       int nj[U], np[U];                            // (source, transposed slot) of the NEXT batch: its gathers start at once
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const bool ok = beg + u < end;
-        nj[u] = ok ? __ldg(col + beg + u) : -1;
-        np[u] = ok ? __ldg(csr_to_csc + beg + u) : 0;
+        const int ee = beg + u * ES + sub;
+        const bool ok = ee < end;
+        nj[u] = ok ? __ldg(col + ee) : -1;
+        np[u] = ok ? __ldg(csr_to_csc + ee) : 0;
       }
-      for (int e = beg; e < end; e += U) {
+      for (int e = beg; e < end; e += U * ES) {
         int j[U], pos[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) { j[u] = nj[u]; pos[u] = np[u]; }
@@ -253,9 +265,10 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
             hj[u][ch] = ld_chunk<VEC>(H + (long long)(j[u] < 0 ? 0 : j[u]) * c + col0 + ch * VEC, cok[ch] && j[u] >= 0);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const bool ok = e + U + u < end;
-          nj[u] = ok ? __ldg(col + e + U + u) : -1;
-          np[u] = ok ? __ldg(csr_to_csc + e + U + u) : 0;
+          const int ee = e + (U + u) * ES + sub;
+          const bool ok = ee < end;
+          nj[u] = ok ? __ldg(col + ee) : -1;
+          np[u] = ok ? __ldg(csr_to_csc + ee) : 0;
         }
         float sp[U], dp[U];
         unsigned bits[U];                          // leaky-relu branch bits of this lane's features (bit = feature)
@@ -317,17 +330,32 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
           }
         }
       }
+      if (ES > 1) {                                // combine the edge shares of the row (fixed butterfly)
+#pragma unroll
+        for (int o = G; o < RL; o <<= 1) {
+          dsum += __shfl_xor_sync(rmask, dsum, o);
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              gi[ch].v[i] += __shfl_xor_sync(rmask, gi[ch].v[i], o);
+              ga[ch].v[i] += __shfl_xor_sync(rmask, ga[ch].v[i], o);
+            }
+        }
+      }
       const float oms = 1.f - slope, sds = slope * dsum;
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           gi[ch].v[i] = av[ch].v[i] * fmaf(oms, gi[ch].v[i], sds);
-          s_ga[(is_src ? 0 : EPL) + ch * VEC + i][threadIdx.x] += ga[ch].v[i];
+          if (sub == 0) s_ga[(is_src ? 0 : EPL) + ch * VEC + i][threadIdx.x] += ga[ch].v[i];
         }
     }
+    if (sub == 0) {
 #pragma unroll
-    for (int ch = 0; ch < CH; ++ch) st_chunk<VEC>((is_src ? gHs : gHt) + row * c + col0 + ch * VEC, gi[ch], cok[ch]);
+      for (int ch = 0; ch < CH; ++ch) st_chunk<VEC>((is_src ? gHs : gHt) + row * c + col0 + ch * VEC, gi[ch], cok[ch]);
+    }
   }
   __syncwarp();
   // sum this warp's groups (fixed butterfly), then the first group writes the warp's partial
@@ -394,14 +422,15 @@ reduce_partials_kernel(const float* __restrict__ part, long long nparts, int wid
 // into gHs (edges into source-domain destinations) / gHt (target-domain destinations).
 template <int VEC, int G, int CH>
 __global__ void __launch_bounds__(256)
-gatv2_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restrict__ t_col,
+gatv2_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restrict__ t_col, const int* __restrict__ t_order,
                      const uint8_t* __restrict__ dst_is_src, const float* __restrict__ af_t2s,
                      const float* __restrict__ af_s2t, float slope, long long n, int c, int cw,
                      const unsigned* __restrict__ erec, const unsigned* __restrict__ emask,
                      const float* __restrict__ gout, float* __restrict__ gHs, float* __restrict__ gHt) {
   const int lane_g = threadIdx.x % G;
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  if (row >= n) return;
+  const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (slot >= n) return;
+  const long long row = t_order ? (long long)__ldg(t_order + slot) : slot;
   // per feature: the attention vector of either destination domain and its slope-scaled copy, so that the
   // leaky-relu branch of an edge is one select (a or slope * a) per domain
   Chunk<VEC> as_[CH], asl[CH], at_[CH], atl[CH], gs[CH], gt[CH];
@@ -508,7 +537,7 @@ size_t gatv2_bwd_workspace_bytes(long long n, long long e, int c) {
 }
 
 struct BwdDstArgs {
-  const int *rowptr, *col, *csr_to_csc;
+  const int *rowptr, *col, *csr_to_csc, *order;
   const uint8_t* dst_is_src;
   const float *Hs, *Ht, *af_t2s, *af_s2t;
   float slope;
@@ -520,9 +549,9 @@ struct BwdDstArgs {
   float* part;
 };
 
-template <int VEC, int G, int CH, int U, int MINB>
+template <int VEC, int G, int CH, int U, int MINB, int ES = 1>
 static int launch_bwd_dst_cfg(const BwdDstArgs& a, int& nwarps_out, cudaStream_t stream) {
-  auto kern = gatv2_bwd_dst_kernel<VEC, G, CH, U, MINB>;
+  auto kern = gatv2_bwd_dst_kernel<VEC, G, CH, U, MINB, ES>;
   static int occ = 0;                               // per instantiation
   if (occ == 0) {
     int o = 0;
@@ -530,11 +559,11 @@ static int launch_bwd_dst_cfg(const BwdDstArgs& a, int& nwarps_out, cudaStream_t
     occ = o < 1 ? 1 : (o > kBwdDstMaxCtasPerSm ? kBwdDstMaxCtasPerSm : o);
   }
   constexpr int WPC = kBwdDstThreads / 32;
-  const long long nsets = (a.n + (32 / G) - 1) / (32 / G);
+  const long long nsets = (a.n + (32 / (G * ES)) - 1) / (32 / (G * ES));
   long long ctas = (nsets + WPC - 1) / WPC;
   if (ctas > (long long)kNumSMs * occ) ctas = (long long)kNumSMs * occ;
   nwarps_out = (int)(ctas * WPC);
-  kern<<<(unsigned)ctas, kBwdDstThreads, 0, stream>>>(a.rowptr, a.col, a.csr_to_csc, a.dst_is_src, a.Hs, a.Ht, a.af_t2s,
+  kern<<<(unsigned)ctas, kBwdDstThreads, 0, stream>>>(a.rowptr, a.col, a.csr_to_csc, a.order, a.dst_is_src, a.Hs, a.Ht, a.af_t2s,
                                                       a.af_s2t, a.slope, a.n, a.c, a.cw, a.out, a.row_max, a.row_sum,
                                                       a.gout, a.gHs, a.gHt, a.erec, a.emask, a.part);
   BGNN_LAUNCH_CHECK();
@@ -550,9 +579,14 @@ static int launch_bwd_dst(const BwdDstArgs& a, int& nwarps_out, cudaStream_t str
     if (variant == 3) return launch_bwd_dst_cfg<VEC, G, CH, 2, 6>(a, nwarps_out, stream);
   }
   constexpr int EPL = VEC * CH;
-  constexpr int U = (EPL >= 8) ? 2 : 4;
-  constexpr int MINB = (EPL > 8) ? 3 : (EPL == 8 ? 5 : (EPL <= 2 ? 8 : 6));
-  return launch_bwd_dst_cfg<VEC, G, CH, U, MINB>(a, nwarps_out, stream);
+  if constexpr (G == 1) {                           // narrow rows: 8 lanes split the edges of a row
+    constexpr int MINB1 = (EPL <= 2) ? 8 : (EPL <= 4 ? 6 : 5);
+    return launch_bwd_dst_cfg<VEC, G, CH, 2, MINB1, 8>(a, nwarps_out, stream);
+  } else {
+    constexpr int U = (EPL >= 8) ? 2 : 4;
+    constexpr int MINB = (EPL > 8) ? 3 : 5;
+    return launch_bwd_dst_cfg<VEC, G, CH, U, MINB>(a, nwarps_out, stream);
+  }
 }
 
 template <int VEC>
@@ -576,7 +610,7 @@ static int dispatch_bwd_dst(int g, int ch, const BwdDstArgs& a, int& nwarps_out,
 }
 
 int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csr_to_csc,
-                     long long e, const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
+                     const int* order, const int* t_order, long long e, const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
                      const float* af_s2t, float slope, long long n, int c, const float* out, const float* row_max,
                      const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
                      float* g_af_s2t, void* ws, size_t ws_bytes, cudaStream_t stream) {
@@ -590,7 +624,7 @@ int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, con
   unsigned* erec = w.take<unsigned>(cw <= 2 ? e * 4 : e * 2);
   unsigned* emask = cw <= 2 ? nullptr : w.take<unsigned>(e * cw);
   if (!w.ok()) return BGNN_ERR_WORKSPACE;
-  const BwdDstArgs a{rowptr, col, csr_to_csc, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, c, cw,
+  const BwdDstArgs a{rowptr, col, csr_to_csc, order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, c, cw,
                      out, row_max, row_sum, gout, gHs, gHt, erec, emask, part};
   int nparts = 0;
   const int rc = dvec == 4 ? dispatch_bwd_dst<4>(dg, dch, a, nparts, stream)
@@ -600,7 +634,7 @@ int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, con
   reduce_partials_kernel<<<2 * c, 256, 0, stream>>>(part, nparts, 2 * c, g_af_t2s, g_af_s2t, c);
   BGNN_LAUNCH_CHECK();
 #define CALL(V, G_, C_)                                                                                            \
-  gatv2_bwd_src_kernel<V, G_, C_><<<(unsigned)blocks, 256, 0, stream>>>(t_rowptr, t_col, dst_is_src, af_t2s,      \
+  gatv2_bwd_src_kernel<V, G_, C_><<<(unsigned)blocks, 256, 0, stream>>>(t_rowptr, t_col, t_order, dst_is_src, af_t2s,      \
       af_s2t, slope, n, c, cw, erec, emask, gout, gHs, gHt)
   BGNN_ROW_DISPATCH(vec, g, ch, CALL);
 #undef CALL

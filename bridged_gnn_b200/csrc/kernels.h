@@ -52,18 +52,22 @@ size_t csr_build_workspace_bytes(long long e);
 int launch_edges_to_csr(const long long* src, const long long* dst, long long e, long long n, int dedup, int* rowptr,
                         int* col, long long* perm, long long* e_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+size_t rows_by_degree_workspace_bytes(long long n);
+int launch_rows_by_degree(const int* rowptr, long long n, int min_degree, int* order, void* ws, size_t ws_bytes,
+                          cudaStream_t stream);
+
 // spmm_csr.cu
 int launch_spmm_csr(const int* rowptr, const int* col, const float* edge_w, const float* gather_scale,
                     const float* out_scale, const float* X, long long n_rows, int f, int reduce_mean, float* Y,
                     cudaStream_t stream);
 
 // gatv2_fused.cu
-int launch_gatv2_fwd(const int* rowptr, const int* col, const uint8_t* dst_is_src, const float* Hs, const float* Ht,
+int launch_gatv2_fwd(const int* rowptr, const int* col, const int* order, const uint8_t* dst_is_src, const float* Hs, const float* Ht,
                      const float* af_t2s, const float* af_s2t, float slope, long long n, int c, float* out,
                      float* row_max, float* row_sum, cudaStream_t stream);
 size_t gatv2_bwd_workspace_bytes(long long n, long long e, int c);
 int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csr_to_csc,
-                     long long e, const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
+                     const int* order, const int* t_order, long long e, const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
                      const float* af_s2t, float slope, long long n, int c, const float* out, const float* row_max,
                      const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
                      float* g_af_s2t, void* ws, size_t ws_bytes, cudaStream_t stream);

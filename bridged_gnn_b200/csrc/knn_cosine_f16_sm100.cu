@@ -435,10 +435,24 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             for (int i = 0; i < NCH; ++i)
 #pragma unroll
               for (int g = 0; g < 4; ++g)
-                if (gm[i][g] > es.thr)
-                  es = epi_scan8(es, ea, db0 + (half + 2 * i) * 32 + g * 8, rr[i][g * 8 + 0], rr[i][g * 8 + 1],
-                                 rr[i][g * 8 + 2], rr[i][g * 8 + 3], rr[i][g * 8 + 4], rr[i][g * 8 + 5], rr[i][g * 8 + 6],
-                                 rr[i][g * 8 + 7]);
+                if (gm[i][g] > es.thr) {
+                  // the usual case inline: exactly one column of the group beats the threshold -- it is the
+                  // group maximum, only its position is missing -- and the FIFO has room
+                  int first = 8, last = -1;
+#pragma unroll
+                  for (int c = 7; c >= 0; --c) first = (rr[i][g * 8 + c] > es.thr) ? c : first;
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) last = (rr[i][g * 8 + c] > es.thr) ? c : last;
+                  const int jb = db0 + (half + 2 * i) * 32 + g * 8;
+                  if (first == last && es.fcnt < F16_FCAP) {
+                    sts_f32(ea.fv + es.fcnt * (F16_BM * 4), gm[i][g]);
+                    sts_s32(ea.fi + es.fcnt * (F16_BM * 4), jb + first);
+                    ++es.fcnt;
+                  } else {
+                    es = epi_scan8(es, ea, jb, rr[i][g * 8 + 0], rr[i][g * 8 + 1], rr[i][g * 8 + 2], rr[i][g * 8 + 3],
+                                   rr[i][g * 8 + 4], rr[i][g * 8 + 5], rr[i][g * 8 + 6], rr[i][g * 8 + 7]);
+                  }
+                }
           }
         }
       }

@@ -111,6 +111,23 @@ def coalesce(edge_index, num_nodes=None):
     return torch.stack((row, col.to(torch.int64)), 0)
 
 
+WIDE_ROW = 16         # feature widths from here on process rows in degree order
+
+
+def rows_by_degree(rowptr, n, min_degree=0):
+    """Row ids sorted by descending CSR row length (stable), int32 [n], on the device; rows shorter than
+    ``min_degree`` follow in natural order."""
+    lib = _lib.load()
+    order = torch.empty((n,), dtype=torch.int32, device=rowptr.device)
+    if n == 0:
+        return order
+    ws = _lib.workspace(lib.bgnn_rows_by_degree_workspace_bytes(n), rowptr.device)
+    with _lib.call("bgnn_rows_by_degree"):
+        _lib.check(lib.bgnn_rows_by_degree(_lib.ptr(rowptr, torch.int32), n, int(min_degree), _lib.ptr(order), _lib.ptr(ws), ws.numel(),
+                                           _lib.stream(rowptr.device)))
+    return order
+
+
 class CSRGraph:
     """Destination-major CSR of an edge list plus, lazily, the CSR of the transposed graph (needed by
     the backward passes).  Built once per graph and cached by the layers, where the reference rebuilds
@@ -123,6 +140,8 @@ class CSRGraph:
         self._t = None
         self._deg = None
         self._csr_to_csc = None
+        self._order = None
+        self._t_order = None
 
     @property
     def t(self):
@@ -139,6 +158,25 @@ class CSRGraph:
             inv_t[t_perm] = torch.arange(t_perm.numel(), device=t_perm.device)
             self._csr_to_csc = inv_t[self.perm].to(torch.int32).contiguous()
         return self._csr_to_csc
+
+    def order(self, c=WIDE_ROW):
+        """int32 [n] or None: processing order of the gather kernels for feature width c -- rows by descending
+        in-degree (hub rows first, rows of similar length share a warp).  Narrow rows keep the natural order:
+        measured on the sync-1M graph, the order lookup in front of every (short, latency-bound) row costs
+        more than the hub tail it removes."""
+        if c < WIDE_ROW:
+            return None
+        if self._order is None:
+            self._order = rows_by_degree(self.rowptr, self.n, 0)
+        return self._order
+
+    def t_order(self, c=WIDE_ROW):
+        """The same for the transposed CSR (rows = sources, by descending out-degree)."""
+        if c < WIDE_ROW:
+            return None
+        if self._t_order is None:
+            self._t_order = rows_by_degree(self.t[0], self.n, 0)
+        return self._t_order
 
     @property
     def deg(self):
@@ -222,8 +260,9 @@ class _GatAggFn(torch.autograd.Function):
         out = torch.empty((n, c), dtype=f32, device=dev)
         row_max = torch.empty((n,), dtype=f32, device=dev)
         row_sum = torch.empty((n,), dtype=f32, device=dev)
-        with _lib.call("bgnn_gatv2_fwd_f32", "bgnn_gatv2_fwd_f32[c=%d]" % c):
-            _lib.check(lib.bgnn_gatv2_fwd_f32(_lib.ptr(graph.rowptr), _lib.ptr(graph.col),
+        with _lib.call("bgnn_gatv2_fwd_ord_f32", "bgnn_gatv2_fwd_f32[c=%d]" % c):
+            _lib.check(lib.bgnn_gatv2_fwd_ord_f32(_lib.ptr(graph.rowptr), _lib.ptr(graph.col),
+                                              _lib.ptr(graph.order(c), torch.int32, True),
                                               _lib.ptr(dst_is_src, torch.uint8), _lib.ptr(Hs), _lib.ptr(Ht),
                                               _lib.ptr(a1), _lib.ptr(a2), float(slope), n, c, _lib.ptr(out),
                                               _lib.ptr(row_max), _lib.ptr(row_sum), _lib.stream(dev)))
@@ -244,9 +283,10 @@ class _GatAggFn(torch.autograd.Function):
         gHs, gHt = torch.empty_like(Hs), torch.empty_like(Ht)
         ga1, ga2 = torch.empty_like(a1), torch.empty_like(a2)
         ws = _lib.workspace(lib.bgnn_gatv2_bwd_workspace_bytes(n, g.e, c), dev)
-        with _lib.call("bgnn_gatv2_bwd_f32", "bgnn_gatv2_bwd_f32[c=%d]" % c):
-            _lib.check(lib.bgnn_gatv2_bwd_f32(_lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(t_rowptr), _lib.ptr(t_col),
-                                              _lib.ptr(g.csr_to_csc, torch.int32), g.e,
+        with _lib.call("bgnn_gatv2_bwd_ord_f32", "bgnn_gatv2_bwd_f32[c=%d]" % c):
+            _lib.check(lib.bgnn_gatv2_bwd_ord_f32(_lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(t_rowptr), _lib.ptr(t_col),
+                                              _lib.ptr(g.csr_to_csc, torch.int32), _lib.ptr(g.order(c), torch.int32, True),
+                                              _lib.ptr(g.t_order(c), torch.int32, True), g.e,
                                               _lib.ptr(ctx.dst_is_src), _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(a1),
                                               _lib.ptr(a2), ctx.slope, n, c, _lib.ptr(out), _lib.ptr(row_max),
                                               _lib.ptr(row_sum), _lib.ptr(gout), _lib.ptr(gHs), _lib.ptr(gHt),

@@ -99,6 +99,18 @@ int bgnn_gatv2_fwd_f32(const int32_t* rowptr, const int32_t* col, const uint8_t*
                        const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n, int c,
                        float* out, float* row_max, float* row_sum, void* stream);
 
+/* Same with an optional processing order of the rows (row_order [n] int32, a permutation of 0..n-1, or NULL):
+ * bgnn_rows_by_degree gives "longest rows first", which removes the tail a hub row of a kNN graph otherwise
+ * forms and evens out the rows that share a warp.  Rows shorter than min_degree keep their natural order after
+ * the long ones (use that for narrow feature rows, whose row-level accesses should stay coalesced; 0 = full
+ * sort).  Results do not depend on the order. */
+int bgnn_gatv2_fwd_ord_f32(const int32_t* rowptr, const int32_t* col, const int32_t* row_order, const uint8_t* dst_is_src,
+                           const float* Hs, const float* Ht, const float* af_t2s, const float* af_s2t, float slope,
+                           int64_t n, int c, float* out, float* row_max, float* row_sum, void* stream);
+size_t bgnn_rows_by_degree_workspace_bytes(int64_t n);
+int bgnn_rows_by_degree(const int32_t* rowptr, int64_t n, int min_degree, int32_t* order, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* Backward of the above.  (rowptr,col) = CSR by destination with e edges, (t_rowptr,t_col) = CSR of the
  * transposed graph (rows = sources, entries = destinations), csr_to_csc [e] = slot of every CSR edge in the
  * transposed CSR.  Writes gHs, gHt [n,c] (fully), g_af_t2s, g_af_s2t [c].  Deterministic, atomic-free. */
@@ -109,6 +121,15 @@ int bgnn_gatv2_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t*
                        const float* out, const float* row_max, const float* row_sum, const float* gout, float* gHs,
                        float* gHt, float* g_af_t2s, float* g_af_s2t, void* workspace, size_t workspace_bytes,
                        void* stream);
+
+/* Same with optional processing orders for the destination-major (row_order) and the transposed (t_row_order) CSR.
+ * g_af_* are summed in a fixed order for a given row_order, so results are reproducible run to run. */
+int bgnn_gatv2_bwd_ord_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
+                           const int32_t* csr_to_csc, const int32_t* row_order, const int32_t* t_row_order, int64_t e,
+                           const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
+                           const float* af_s2t, float slope, int64_t n, int c, const float* out, const float* row_max,
+                           const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
+                           float* g_af_s2t, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Node-wise epilogue of AdaptedConv's domain-shift transform (models/KTGNN.py:275-284).  The host computes
  * P [n, 2c+2] = x [W_s; W_t; a_g_s2t[:D]; a_g_t2s[:D]]^T (+ biases), wd [2c] = [W_s Delta; W_t Delta] and

@@ -132,6 +132,53 @@ def test_gat_aggregate_forward_backward_random(n, c, e):
         assert relclose(got.grad, ref.grad, 2e-5), name
 
 
+def test_rows_by_degree_is_a_stable_descending_permutation():
+    ops = _ops()
+    for n, e in ((1, 0), (7, 30), (1000, 20000), (4096, 100)):
+        ei = _rand_graph(n, e, 5 + n) if e else torch.zeros((2, 0), dtype=torch.long)
+        graph = ops.CSRGraph(ei.cuda(), n)
+        order = graph.order(64).cpu().long()
+        deg = (graph.rowptr[1:] - graph.rowptr[:-1]).cpu().long()
+        assert sorted(order.tolist()) == list(range(n))
+        ref = torch.sort(-deg, stable=True).indices            # descending degree, ties by ascending row id
+        assert torch.equal(order, ref)
+        hubs = ops.rows_by_degree(graph.rowptr, n, 20).cpu().long()   # only rows with >= 20 edges move to the front
+        key = torch.where(deg >= 20, -deg, torch.ones_like(deg))
+        assert torch.equal(hubs, torch.sort(key, stable=True).indices)
+
+
+def test_gat_aggregate_is_independent_of_the_row_order():
+    """The degree order only changes which warp processes which row: forward values and row gradients are
+    bit-identical to the natural order (C-ABI entry points without an order)."""
+    from bridged_gnn_b200 import _lib
+    ops = _ops()
+    lib = _lib.load()
+    n, c, e = 2000, 64, 30000
+    eall, e1, e2, cm, Hs, Ht, a1, a2, gout = _agg_inputs(n, c, e, 77)
+    graph = ops.CSRGraph(eall.cuda(), n)
+    cm8 = cm.to(torch.uint8).cuda()
+    dl = [t.clone().cuda().requires_grad_(True) for t in (Hs, Ht, a1, a2)]
+    y = ops.gat_aggregate(dl[0], dl[1], dl[2], dl[3], graph, cm8, 0.1)
+    y.backward(gout.cuda())
+    out = torch.empty_like(y)
+    rmax, rsum = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+    P = _lib.ptr
+    _lib.check(lib.bgnn_gatv2_fwd_f32(P(graph.rowptr), P(graph.col), P(cm8), P(dl[0].detach()), P(dl[1].detach()),
+                                      P(dl[2].detach()), P(dl[3].detach()), 0.1, n, c, P(out), P(rmax), P(rsum),
+                                      _lib.stream(out.device)))
+    assert torch.equal(out, y.detach())
+    gHs, gHt = torch.empty_like(out), torch.empty_like(out)
+    ga1, ga2 = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    ws = _lib.workspace(lib.bgnn_gatv2_bwd_workspace_bytes(n, graph.e, c), out.device)
+    t_rowptr, t_col, _ = graph.t
+    _lib.check(lib.bgnn_gatv2_bwd_f32(P(graph.rowptr), P(graph.col), P(t_rowptr), P(t_col), P(graph.csr_to_csc), graph.e,
+                                      P(cm8), P(dl[0].detach()), P(dl[1].detach()), P(dl[2].detach()), P(dl[3].detach()),
+                                      0.1, n, c, P(out), P(rmax), P(rsum), P(gout.cuda()), P(gHs), P(gHt), P(ga1), P(ga2),
+                                      P(ws), ws.numel(), _lib.stream(out.device)))
+    assert torch.equal(gHs, dl[0].grad) and torch.equal(gHt, dl[1].grad)
+    assert relclose(ga1, dl[2].grad, 1e-5) and relclose(ga2, dl[3].grad, 1e-5)
+
+
 def test_gat_aggregate_unsupported_width_fails_loudly():
     ops = _ops()
     eall, e1, e2, cm, Hs, Ht, a1, a2, gout = _agg_inputs(40, 1000, 200, 9)

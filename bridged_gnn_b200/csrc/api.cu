@@ -326,4 +326,36 @@ int bgnn_adapted_transform_bwd_f32(const float* gHs, const float* gHt, const flo
                                       (cudaStream_t)stream);
 }
 
+int bgnn_adapted_skinny_supported(int c, int d) { return adapted_skinny_supported(c, d) ? 1 : 0; }
+
+int bgnn_adapted_skinny_fwd_f32(const float* x, const uint8_t* is_src, const float* wcat, const float* bias,
+                                const float* wd, const float* kg, int64_t n, int d, int c, float* Hs, float* Ht,
+                                float* gates, void* stream) {
+  if (n < 0 || c <= 0 || d <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!x || !is_src || !wcat || !wd || !kg || !Hs || !Ht || !gates)) return BGNN_ERR_INVALID_ARG;
+  return launch_adapted_skinny_fwd(x, is_src, wcat, bias, wd, kg, n, d, c, Hs, Ht, gates, (cudaStream_t)stream);
+}
+
+size_t bgnn_adapted_skinny_bwd_workspace_bytes(int c, int d) {
+  return (c <= 0 || d <= 0) ? 0 : adapted_skinny_bwd_workspace_bytes(c, d);
+}
+
+int bgnn_adapted_skinny_bwd_f32(const float* x, const uint8_t* is_src, const float* wcat, const float* wd,
+                                const float* gates, const float* gHs, const float* gHt, int64_t n, int d, int c,
+                                float* gx, float* red, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 0 || c <= 0 || d <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!x || !is_src || !wcat || !wd || !gates || !gHs || !gHt || !gx || !red || !workspace))
+    return BGNN_ERR_INVALID_ARG;
+  return launch_adapted_skinny_bwd(x, is_src, wcat, wd, gates, gHs, gHt, n, d, c, gx, red, workspace, workspace_bytes,
+                                   (cudaStream_t)stream);
+}
+
+size_t bgnn_domain_colsum_workspace_bytes(int d) { return d <= 0 ? 0 : domain_colsum_workspace_bytes(d); }
+
+int bgnn_domain_colsum_f32(const float* x, const uint8_t* is_src, int64_t n, int d, float* sums, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (n < 0 || d <= 0 || !sums || !workspace || (n > 0 && (!x || !is_src))) return BGNN_ERR_INVALID_ARG;
+  return launch_domain_colsum(x, is_src, n, d, sums, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 }  // extern "C"

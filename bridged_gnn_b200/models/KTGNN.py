@@ -49,6 +49,15 @@ class AdaptedConv(nn.Module):
             self._rows_key, self._rows = key, torch.stack((cf / ns, (1.0 - cf) / nt), 0).contiguous()
         return self._rows
 
+    def _domain_counts(self, central_mask):
+        key = (central_mask.data_ptr(), central_mask._version, central_mask.shape[0])
+        if getattr(self, "_counts_key", None) != key:
+            ns = central_mask.sum().clamp(min=1).to(torch.float32)
+            nt = (central_mask.shape[0] - central_mask.sum()).clamp(min=1).to(torch.float32)
+            self._counts_key = key
+            self._counts = (torch.stack((1.0 / ns, 1.0 / nt)), (~central_mask.to(torch.bool)).to(torch.int64))
+        return self._counts
+
     def _padded_params(self):
         """lin_s / lin_t / a_f with the output width padded to a multiple of 4 by zero rows when that lets the
         gather kernels use 128-bit loads (e.g. 31 classes -> 32).  The zero columns of H contribute nothing to
@@ -91,18 +100,25 @@ class AdaptedConv(nn.Module):
         #   gate_s2t = tanh(a_g_s2t . [x, Delta]),  gate_t2s = tanh(a_g_t2s . [x, Delta])
         #   h_t = lin_t(x - gate_s2t * Delta * c)      = x W_t^T + b_t - (gate_s2t * c)     (x) (W_t Delta)
         #   h_s = lin_s(x + gate_t2s * Delta * (1-c))  = x W_s^T + b_s + (gate_t2s * (1-c)) (x) (W_s Delta)
-        cf = self._domain_rows(c, x_src.dtype)                       # [2, N]: 1/Ns on source rows, 1/Nt on target rows
-        means = cf @ x_src                                           # [2, D] (one pass over x)
+        on_gpu = x_src.is_cuda and x_src.dtype == torch.float32
+        if on_gpu and ops.domain_colsum_supported(d):
+            inv_counts, dom_index = self._domain_counts(c)
+            means = ops.domain_means(x_src, self._dst_is_src(c), inv_counts, dom_index)   # [2, D], one pass over x
+        else:
+            cf = self._domain_rows(c, x_src.dtype)                   # [2, N]: 1/Ns on source rows, 1/Nt on target rows
+            means = cf @ x_src
         delta = means[0:1] - means[1:2]                              # [1, D]
         w_s, w_t, b_s, b_t, a_t2s, a_s2t, cp = self._padded_params()
         w_cat = torch.cat((w_s, w_t, self.a_g_s2t.weight[:, :d], self.a_g_t2s.weight[:, :d]), 0)
-        if b_s is not None:
-            p = torch.addmm(torch.cat((b_s, b_t, b_s.new_zeros(2))), x_src, w_cat.t())   # [N, 2*cp + 2], biases folded in
-        else:
-            p = x_src @ w_cat.t()
+        b_cat = None if b_s is None else torch.cat((b_s, b_t, b_s.new_zeros(2)))
         k_g = torch.stack(((self.a_g_s2t.weight[:, d:] * delta).sum(), (self.a_g_t2s.weight[:, d:] * delta).sum()))
         wd = delta @ torch.cat((w_s, w_t), 0).t()                    # [1, 2*cp]: W_s Delta, W_t Delta
-        h_s, h_t = ops.adapted_transform(p, wd, k_g, self._dst_is_src(c))   # gates + rank-1 corrections, one pass over P
+        if on_gpu and ops.adapted_skinny_supported(cp, d):
+            # classifier heads (a few classes): contraction, gates and corrections in one pass over x
+            h_s, h_t = ops.adapted_skinny(x_src, w_cat, b_cat, wd, k_g, self._dst_is_src(c))
+        else:
+            p = x_src @ w_cat.t() if b_cat is None else torch.addmm(b_cat, x_src, w_cat.t())   # [N, 2*cp + 2]
+            h_s, h_t = ops.adapted_transform(p, wd, k_g, self._dst_is_src(c))   # gates + rank-1 corrections, one pass over P
         # attention scores, softmax over destinations, weighted aggregation (:292-305) -- one kernel
         graph = ops.cached_graph(edge_index, x_src.shape[0])
         out = ops.gat_aggregate(h_s, h_t, a_t2s, a_s2t, graph, self._dst_is_src(c), self.negative_slope)

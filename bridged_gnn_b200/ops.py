@@ -353,3 +353,93 @@ def adapted_transform(P, wd, kg, is_src):
     is_src uint8 [n].  Differentiable in P, wd, kg."""
     Hs, Ht, _ = _AdaptedTransformFn.apply(P, wd, kg, is_src)
     return Hs, Ht
+
+
+# ----------------------------------------------------------------------------------- narrow AdaptedConv transform
+class _AdaptedSkinnyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_cat, bias_cat, wd, kg, is_src):
+        lib = _lib.load()
+        f32 = torch.float32
+        x, w_cat = x.to(f32).contiguous(), w_cat.to(f32).contiguous()
+        wd_c, kg_c = wd.to(f32).contiguous().view(-1), kg.to(f32).contiguous().view(-1)
+        b_c = None if bias_cat is None else bias_cat.to(f32).contiguous()
+        n, d = x.shape
+        c = (w_cat.shape[0] - 2) // 2
+        dev = x.device
+        Hs = torch.empty((n, c), dtype=f32, device=dev)
+        Ht = torch.empty((n, c), dtype=f32, device=dev)
+        gates = torch.empty((n, 2), dtype=f32, device=dev)
+        with _lib.call("bgnn_adapted_skinny_fwd_f32"):
+            _lib.check(lib.bgnn_adapted_skinny_fwd_f32(_lib.ptr(x), _lib.ptr(is_src, torch.uint8), _lib.ptr(w_cat),
+                                                       _lib.ptr(b_c, f32, True), _lib.ptr(wd_c), _lib.ptr(kg_c), n, d, c,
+                                                       _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(gates), _lib.stream(dev)))
+        ctx.save_for_backward(x, w_cat, wd_c, gates, is_src)
+        ctx.meta = (wd.shape, kg.shape, c, d, bias_cat is not None)
+        return Hs, Ht
+
+    @staticmethod
+    def backward(ctx, gHs, gHt):
+        lib = _lib.load()
+        x, w_cat, wd_c, gates, is_src = ctx.saved_tensors
+        wd_shape, kg_shape, c, d, has_bias = ctx.meta
+        f32 = torch.float32
+        gHs, gHt = gHs.to(f32).contiguous(), gHt.to(f32).contiguous()
+        n, dev, o = x.shape[0], x.device, 2 * c + 2
+        gx = torch.empty_like(x)
+        red = torch.empty((o * d + o + 2 * c,), dtype=f32, device=dev)
+        ws = _lib.workspace(lib.bgnn_adapted_skinny_bwd_workspace_bytes(c, d), dev)
+        with _lib.call("bgnn_adapted_skinny_bwd_f32"):
+            _lib.check(lib.bgnn_adapted_skinny_bwd_f32(_lib.ptr(x), _lib.ptr(is_src, torch.uint8), _lib.ptr(w_cat),
+                                                       _lib.ptr(wd_c), _lib.ptr(gates), _lib.ptr(gHs), _lib.ptr(gHt), n, d,
+                                                       c, _lib.ptr(gx), _lib.ptr(red), _lib.ptr(ws), ws.numel(),
+                                                       _lib.stream(dev)))
+        g_w = red[: o * d].view(o, d)
+        colsum = red[o * d: o * d + o]
+        g_bias = colsum.clone() if has_bias else None
+        if g_bias is not None:
+            g_bias[2 * c:] = 0.0                       # the gate columns carry no bias parameter
+        return gx, g_w, g_bias, red[o * d + o:].view(wd_shape), colsum[2 * c:].view(kg_shape), None
+
+
+def adapted_skinny_supported(c, d):
+    return bool(_lib.load().bgnn_adapted_skinny_supported(int(c), int(d)))
+
+
+def adapted_skinny(x, w_cat, bias_cat, wd, kg, is_src):
+    """AdaptedConv's node-wise transform for narrow outputs (c <= 4 classes) straight from x: the contraction with
+    w_cat [2c+2, d] = [W_s; W_t; a_g_s2t[:d]; a_g_t2s[:d]], the gates and the rank-1 corrections in one pass over x
+    (models/KTGNN.py:275-284); returns (Hs, Ht).  Differentiable in x, w_cat, bias_cat, wd, kg."""
+    return _AdaptedSkinnyFn.apply(x, w_cat, bias_cat, wd, kg, is_src)
+
+
+class _DomainMeansFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, is_src, inv_counts, dom_index):
+        lib = _lib.load()
+        x = x.to(torch.float32).contiguous()
+        n, d = x.shape
+        sums = torch.empty((2, d), dtype=torch.float32, device=x.device)
+        ws = _lib.workspace(lib.bgnn_domain_colsum_workspace_bytes(d), x.device)
+        with _lib.call("bgnn_domain_colsum_f32"):
+            _lib.check(lib.bgnn_domain_colsum_f32(_lib.ptr(x), _lib.ptr(is_src, torch.uint8), n, d, _lib.ptr(sums),
+                                                  _lib.ptr(ws), ws.numel(), _lib.stream(x.device)))
+        ctx.save_for_backward(inv_counts, dom_index)
+        return sums * inv_counts.view(2, 1)
+
+    @staticmethod
+    def backward(ctx, gmeans):
+        inv_counts, dom_index = ctx.saved_tensors
+        return (gmeans * inv_counts.view(2, 1)).index_select(0, dom_index), None, None, None
+
+
+def domain_colsum_supported(d):
+    return d >= 4 and d % 4 == 0 and d <= 1024
+
+
+def domain_means(x, is_src, inv_counts, dom_index):
+    """[2, d]: mean of the source-domain rows and of the target-domain rows of x (models/KTGNN.py:275-276), one
+    pass over x.  is_src uint8 [n]; inv_counts float32 [2] = (1/Ns, 1/Nt); dom_index int64 [n] = 0 for source rows,
+    1 for target rows (used by the backward pass)."""
+    return _DomainMeansFn.apply(x, is_src, inv_counts, dom_index)
+

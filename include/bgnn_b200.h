@@ -146,6 +146,26 @@ int bgnn_adapted_transform_bwd_f32(const float* gHs, const float* gHt, const flo
                                    const float* wd, int64_t n, int c, float* gP, float* g_wd_kg, void* workspace,
                                    size_t workspace_bytes, void* stream);
 
+/* The same transform for NARROW outputs (classifier heads, c <= 4; d % 4 == 0, d <= 256), without the dense
+ * contraction on the host: reads x [n,d] once per direction.  wcat [2c+2, d] = [W_s; W_t; a_g_s2t[:d]; a_g_t2s[:d]],
+ * bias [2c+2] or NULL, wd / kg as above.  bgnn_adapted_skinny_supported tells whether (c, d) is covered. */
+int bgnn_adapted_skinny_supported(int c, int d);
+int bgnn_adapted_skinny_fwd_f32(const float* x, const uint8_t* is_src, const float* wcat, const float* bias,
+                                const float* wd, const float* kg, int64_t n, int d, int c, float* Hs, float* Ht,
+                                float* gates, void* stream);
+/* Backward: gx [n,d] (fully written), red [(2c+2)*d + (2c+2) + 2c] = (d wcat row-major, column sums of the
+ * pre-activation gradient = (d bias [2c], d kg [2]), d wd [2c]).  Deterministic two-stage reductions. */
+size_t bgnn_adapted_skinny_bwd_workspace_bytes(int c, int d);
+int bgnn_adapted_skinny_bwd_f32(const float* x, const uint8_t* is_src, const float* wcat, const float* wd,
+                                const float* gates, const float* gHs, const float* gHt, int64_t n, int d, int c,
+                                float* gx, float* red, void* workspace, size_t workspace_bytes, void* stream);
+
+/* sums [2,d]: column sums of x [n,d] over the source-domain rows (is_src != 0) and over the target-domain rows;
+ * Delta of models/KTGNN.py:275-276 is sums[0]/Ns - sums[1]/Nt.  d % 4 == 0, d <= 1024.  Deterministic. */
+size_t bgnn_domain_colsum_workspace_bytes(int d);
+int bgnn_domain_colsum_f32(const float* x, const uint8_t* is_src, int64_t n, int d, float* sums, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

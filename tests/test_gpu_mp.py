@@ -248,6 +248,57 @@ def test_adapted_transform_forward_backward(n, c):
         assert got.grad.shape == ref.grad.shape and relclose(got.grad, ref.grad, 2e-5), name
 
 
+@pytest.mark.parametrize("n,c,d,bias", [(1, 1, 4, True), (1000, 2, 64, True), (777, 3, 100, False), (5000, 4, 128, True),
+                                        (3000, 2, 256, True), (257, 4, 8, False)])
+def test_adapted_skinny_forward_backward(n, c, d, bias):
+    """Narrow-output transform straight from x == dense contraction + node-wise epilogue of the oracle."""
+    ops = _ops()
+    assert ops.adapted_skinny_supported(c, d) and not ops.adapted_skinny_supported(5, d) and not ops.adapted_skinny_supported(c, 260)
+    g = torch.Generator().manual_seed(70 + c + d)
+    x = torch.randn(n, d, generator=g)
+    w_cat = torch.randn(2 * c + 2, d, generator=g) * 0.3
+    b_cat = torch.cat((torch.randn(2 * c, generator=g), torch.zeros(2))) if bias else None
+    wd, kg = torch.randn(1, 2 * c, generator=g), torch.randn(2, generator=g)
+    cm = torch.rand(n, generator=g) < 0.7
+    go_s, go_t = torch.randn(n, c, generator=g), torch.randn(n, c, generator=g)
+    names = ["x", "w_cat", "wd", "kg"] + (["b_cat"] if bias else [])
+    vals = [x, w_cat, wd, kg] + ([b_cat] if bias else [])
+    leaf = [t.clone().requires_grad_(True) for t in vals]
+    P = leaf[0] @ leaf[1].t() + (leaf[4] if bias else 0.0)
+    Hs_r, Ht_r = mo.adapted_transform_epilogue(P, leaf[2], leaf[3], cm.to(torch.uint8))
+    ((Hs_r * go_s).sum() + (Ht_r * go_t).sum()).backward()
+    dl = [t.clone().cuda().requires_grad_(True) for t in vals]
+    Hs, Ht = ops.adapted_skinny(dl[0], dl[1], dl[4] if bias else None, dl[2], dl[3], cm.to(torch.uint8).cuda())
+    assert relclose(Hs, Hs_r, 5e-6) and relclose(Ht, Ht_r, 5e-6)
+    ((Hs * go_s.cuda()).sum() + (Ht * go_t.cuda()).sum()).backward()
+    for got, ref, name in zip(dl, leaf, names):
+        if name == "b_cat":      # the two gate columns have no bias parameter: their gradient is reported as 0
+            assert relclose(got.grad[: 2 * c], ref.grad[: 2 * c], 2e-5) and bool((got.grad[2 * c:] == 0).all())
+        else:
+            assert got.grad.shape == ref.grad.shape and relclose(got.grad, ref.grad, 2e-5), name
+
+
+@pytest.mark.parametrize("n,d", [(1, 4), (1000, 64), (4097, 256), (300, 1024)])
+def test_domain_means_forward_backward(n, d):
+    ops = _ops()
+    g = torch.Generator().manual_seed(90 + d)
+    x = torch.randn(n, d, generator=g)
+    cm = torch.rand(n, generator=g) < 0.6
+    if n > 1:
+        cm[0], cm[1] = True, False
+    ns, nt = cm.sum().clamp(min=1).float(), (n - cm.sum()).clamp(min=1).float()
+    gm = torch.randn(2, d, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = torch.stack(((xr * cm.float().unsqueeze(1)).sum(0) / ns, (xr * (~cm).float().unsqueeze(1)).sum(0) / nt))
+    (ref * gm).sum().backward()
+    xd = x.clone().cuda().requires_grad_(True)
+    inv = torch.stack((1.0 / ns, 1.0 / nt)).cuda()
+    got = ops.domain_means(xd, cm.to(torch.uint8).cuda(), inv, (~cm).long().cuda())
+    assert relclose(got, ref, 2e-6)
+    (got * gm.cuda()).sum().backward()
+    assert relclose(xd.grad, xr.grad, 2e-6)
+
+
 # ------------------------------------------------------------------ golden: reference layers on the office bridged graph
 def test_adapted_conv_module_matches_reference(office_mp, office_build):
     from bridged_gnn_b200.models import AdaptedConv

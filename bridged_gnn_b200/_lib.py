@@ -35,7 +35,7 @@ SIGNATURES = {
     "bgnn_gatv2_fwd_ord_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "bgnn_rows_by_degree_workspace_bytes": (_sz, [_i64]),
     "bgnn_rows_by_degree": (_i32, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
-    "bgnn_adapted_transform_fwd_f32": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "bgnn_adapted_transform_fwd_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "bgnn_adapted_transform_bwd_workspace_bytes": (_sz, [_i32]),
     "bgnn_adapted_transform_bwd_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "bgnn_adapted_skinny_supported": (_i32, [_i32, _i32]),

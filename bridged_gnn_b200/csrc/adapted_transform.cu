@@ -20,7 +20,7 @@ constexpr int AT_THREADS = 256;
 template <int G>
 __global__ void __launch_bounds__(AT_THREADS)
 adapted_transform_fwd_kernel(const float* __restrict__ P, const uint8_t* __restrict__ is_src, const float* __restrict__ wd,
-                             const float* __restrict__ kg, long long n, int c, float* __restrict__ Hs,
+                             const float* __restrict__ kg, const float* __restrict__ bias, long long n, int c, float* __restrict__ Hs,
                              float* __restrict__ Ht, float* __restrict__ gates) {
   const int lane_g = threadIdx.x % G;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -33,8 +33,9 @@ adapted_transform_fwd_kernel(const float* __restrict__ P, const uint8_t* __restr
   const float fs = src ? 0.f : g1;        // multiplies W_s Delta
   const float ft = src ? -g0 : 0.f;       // multiplies W_t Delta
   for (int j = lane_g; j < c; j += G) {
-    Hs[row * c + j] = fmaf(fs, __ldg(wd + j), __ldg(p + j));
-    Ht[row * c + j] = fmaf(ft, __ldg(wd + c + j), __ldg(p + c + j));
+    // bias (optional, [2c] = (b_s, b_t)): folded in here so that the contraction needs no separate bias pass
+    Hs[row * c + j] = fmaf(fs, __ldg(wd + j), __ldg(p + j) + (bias ? __ldg(bias + j) : 0.f));
+    Ht[row * c + j] = fmaf(ft, __ldg(wd + c + j), __ldg(p + c + j) + (bias ? __ldg(bias + c + j) : 0.f));
   }
   if (lane_g == 0) { gates[row * 2] = g0; gates[row * 2 + 1] = g1; }
 }
@@ -49,17 +50,18 @@ __global__ void __launch_bounds__(AT_THREADS)
 adapted_transform_bwd_kernel(const float* __restrict__ gHs, const float* __restrict__ gHt, const float* __restrict__ gates,
                              const uint8_t* __restrict__ is_src, const float* __restrict__ wd, long long n, int c,
                              float* __restrict__ gP, float* __restrict__ part) {
-  extern __shared__ float s_part[];       // [groups][2C+2]
+  extern __shared__ float s_part[];       // [groups][4C+2]: d wd (2C), d kg (2), column sums of dHs, dHt = d bias (2C)
   constexpr int GROUPS = AT_THREADS / G;
   const int lane_g = threadIdx.x % G, grp = threadIdx.x / G;
   const int ldp = 2 * c + 2;
-  float ws[CPL], wt[CPL], as_[CPL], at_[CPL];
+  const int lpart = 4 * c + 2;
+  float ws[CPL], wt[CPL], as_[CPL], at_[CPL], bs_[CPL], bt_[CPL];
 #pragma unroll
   for (int k = 0; k < CPL; ++k) {
     const int j = lane_g + k * G;
     ws[k] = j < c ? __ldg(wd + j) : 0.f;
     wt[k] = j < c ? __ldg(wd + c + j) : 0.f;
-    as_[k] = 0.f; at_[k] = 0.f;
+    as_[k] = 0.f; at_[k] = 0.f; bs_[k] = 0.f; bt_[k] = 0.f;
   }
   float k0 = 0.f, k1 = 0.f;
   const long long stride = (long long)gridDim.x * GROUPS;
@@ -83,6 +85,8 @@ adapted_transform_bwd_kernel(const float* __restrict__ gHs, const float* __restr
         dt = fmaf(b, wt[k], dt);
         as_[k] = fmaf(fs, a, as_[k]);
         at_[k] = fmaf(ft, b, at_[k]);
+        bs_[k] += a;
+        bt_[k] += b;
       }
     }
 #pragma unroll
@@ -98,18 +102,18 @@ adapted_transform_bwd_kernel(const float* __restrict__ gHs, const float* __restr
       k0 += d0; k1 += d1;
     }
   }
-  float* mine = s_part + (size_t)grp * ldp;
+  float* mine = s_part + (size_t)grp * lpart;
 #pragma unroll
   for (int k = 0; k < CPL; ++k) {
     const int j = lane_g + k * G;
-    if (j < c) { mine[j] = as_[k]; mine[c + j] = at_[k]; }
+    if (j < c) { mine[j] = as_[k]; mine[c + j] = at_[k]; mine[2 * c + 2 + j] = bs_[k]; mine[3 * c + 2 + j] = bt_[k]; }
   }
   if (lane_g == 0) { mine[2 * c] = k0; mine[2 * c + 1] = k1; }
   __syncthreads();
-  for (int t = threadIdx.x; t < ldp; t += blockDim.x) {
+  for (int t = threadIdx.x; t < lpart; t += blockDim.x) {
     float acc = 0.f;
-    for (int g = 0; g < GROUPS; ++g) acc += s_part[(size_t)g * ldp + t];
-    part[(long long)blockIdx.x * ldp + t] = acc;
+    for (int g = 0; g < GROUPS; ++g) acc += s_part[(size_t)g * lpart + t];
+    part[(long long)blockIdx.x * lpart + t] = acc;
   }
 }
 
@@ -135,12 +139,12 @@ static int pick_g(int c) {
   return g;
 }
 
-int launch_adapted_transform_fwd(const float* P, const uint8_t* is_src, const float* wd, const float* kg, long long n,
-                                 int c, float* Hs, float* Ht, float* gates, cudaStream_t stream) {
+int launch_adapted_transform_fwd(const float* P, const uint8_t* is_src, const float* wd, const float* kg, const float* bias,
+                                 long long n, int c, float* Hs, float* Ht, float* gates, cudaStream_t stream) {
   if (n <= 0) return BGNN_OK;
   const int g = pick_g(c);
   const long long blocks = (n * g + AT_THREADS - 1) / AT_THREADS;
-#define CALL(G_) adapted_transform_fwd_kernel<G_><<<(unsigned)blocks, AT_THREADS, 0, stream>>>(P, is_src, wd, kg, n, c, Hs, Ht, gates)
+#define CALL(G_) adapted_transform_fwd_kernel<G_><<<(unsigned)blocks, AT_THREADS, 0, stream>>>(P, is_src, wd, kg, bias, n, c, Hs, Ht, gates)
   switch (g) {
     case 1: CALL(1); break;
     case 2: CALL(2); break;
@@ -156,7 +160,7 @@ int launch_adapted_transform_fwd(const float* P, const uint8_t* is_src, const fl
 
 constexpr int AT_BWD_CTAS = kNumSMs * 4;
 
-size_t adapted_transform_bwd_workspace_bytes(int c) { return (size_t)AT_BWD_CTAS * (2 * c + 2) * sizeof(float) + 256; }
+size_t adapted_transform_bwd_workspace_bytes(int c) { return (size_t)AT_BWD_CTAS * (4 * c + 2) * sizeof(float) + 256; }
 
 int launch_adapted_transform_bwd(const float* gHs, const float* gHt, const float* gates, const uint8_t* is_src,
                                  const float* wd, long long n, int c, float* gP, float* g_wd_kg, void* ws, size_t ws_bytes,
@@ -167,8 +171,8 @@ int launch_adapted_transform_bwd(const float* gHs, const float* gHt, const float
   float* part = reinterpret_cast<float*>(ws);
   const int g = pick_g(c);
   const int cpl = (c + g - 1) / g;
-  const int ldp = 2 * c + 2;
-  const size_t dyn = (size_t)(AT_THREADS / g) * ldp * sizeof(float);
+  const int lpart = 4 * c + 2;
+  const size_t dyn = (size_t)(AT_THREADS / g) * lpart * sizeof(float);
   if (dyn > 200 * 1024) return BGNN_ERR_UNSUPPORTED;
 #define CALL(G_, CPL_)                                                                                              \
   do {                                                                                                              \
@@ -193,7 +197,7 @@ int launch_adapted_transform_bwd(const float* gHs, const float* gHt, const float
   }
 #undef CALL
   BGNN_LAUNCH_CHECK();
-  reduce_columns_kernel<<<ldp, 256, 0, stream>>>(part, AT_BWD_CTAS, ldp, g_wd_kg);
+  reduce_columns_kernel<<<lpart, 256, 0, stream>>>(part, AT_BWD_CTAS, lpart, g_wd_kg);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }

@@ -308,11 +308,11 @@ int bgnn_gatv2_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t*
                                 workspace_bytes, stream);
 }
 
-int bgnn_adapted_transform_fwd_f32(const float* P, const uint8_t* is_src, const float* wd, const float* kg, int64_t n,
-                                   int c, float* Hs, float* Ht, float* gates, void* stream) {
+int bgnn_adapted_transform_fwd_f32(const float* P, const uint8_t* is_src, const float* wd, const float* kg,
+                                   const float* bias, int64_t n, int c, float* Hs, float* Ht, float* gates, void* stream) {
   if (n < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
   if (n > 0 && (!P || !is_src || !wd || !kg || !Hs || !Ht || !gates)) return BGNN_ERR_INVALID_ARG;
-  return launch_adapted_transform_fwd(P, is_src, wd, kg, n, c, Hs, Ht, gates, (cudaStream_t)stream);
+  return launch_adapted_transform_fwd(P, is_src, wd, kg, bias, n, c, Hs, Ht, gates, (cudaStream_t)stream);
 }
 
 size_t bgnn_adapted_transform_bwd_workspace_bytes(int c) { return c <= 0 ? 0 : adapted_transform_bwd_workspace_bytes(c); }

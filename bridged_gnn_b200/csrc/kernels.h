@@ -73,8 +73,8 @@ int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, con
                      float* g_af_s2t, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // adapted_transform.cu
-int launch_adapted_transform_fwd(const float* P, const uint8_t* is_src, const float* wd, const float* kg, long long n,
-                                 int c, float* Hs, float* Ht, float* gates, cudaStream_t stream);
+int launch_adapted_transform_fwd(const float* P, const uint8_t* is_src, const float* wd, const float* kg, const float* bias,
+                                 long long n, int c, float* Hs, float* Ht, float* gates, cudaStream_t stream);
 size_t adapted_transform_bwd_workspace_bytes(int c);
 int launch_adapted_transform_bwd(const float* gHs, const float* gHt, const float* gates, const uint8_t* is_src,
                                  const float* wd, long long n, int c, float* gP, float* g_wd_kg, void* ws, size_t ws_bytes,

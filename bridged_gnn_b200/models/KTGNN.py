@@ -55,7 +55,7 @@ class AdaptedConv(nn.Module):
             ns = central_mask.sum().clamp(min=1).to(torch.float32)
             nt = (central_mask.shape[0] - central_mask.sum()).clamp(min=1).to(torch.float32)
             self._counts_key = key
-            self._counts = (torch.stack((1.0 / ns, 1.0 / nt)), (~central_mask.to(torch.bool)).to(torch.int64))
+            self._counts = torch.stack((1.0 / ns, 1.0 / nt))
         return self._counts
 
     def _padded_params(self):
@@ -102,8 +102,7 @@ class AdaptedConv(nn.Module):
         #   h_s = lin_s(x + gate_t2s * Delta * (1-c))  = x W_s^T + b_s + (gate_t2s * (1-c)) (x) (W_s Delta)
         on_gpu = x_src.is_cuda and x_src.dtype == torch.float32
         if on_gpu and ops.domain_colsum_supported(d):
-            inv_counts, dom_index = self._domain_counts(c)
-            means = ops.domain_means(x_src, self._dst_is_src(c), inv_counts, dom_index)   # [2, D], one pass over x
+            means = ops.domain_means(x_src, self._dst_is_src(c), self._domain_counts(c))   # [2, D], one pass over x
         else:
             cf = self._domain_rows(c, x_src.dtype)                   # [2, N]: 1/Ns on source rows, 1/Nt on target rows
             means = cf @ x_src
@@ -117,8 +116,9 @@ class AdaptedConv(nn.Module):
             # classifier heads (a few classes): contraction, gates and corrections in one pass over x
             h_s, h_t = ops.adapted_skinny(x_src, w_cat, b_cat, wd, k_g, self._dst_is_src(c))
         else:
-            p = x_src @ w_cat.t() if b_cat is None else torch.addmm(b_cat, x_src, w_cat.t())   # [N, 2*cp + 2]
-            h_s, h_t = ops.adapted_transform(p, wd, k_g, self._dst_is_src(c))   # gates + rank-1 corrections, one pass over P
+            p = x_src @ w_cat.t()                                    # [N, 2*cp + 2]
+            b2 = None if b_s is None else torch.cat((b_s, b_t))
+            h_s, h_t = ops.adapted_transform(p, wd, k_g, self._dst_is_src(c), b2)   # biases, gates, rank-1 corrections
         # attention scores, softmax over destinations, weighted aggregation (:292-305) -- one kernel
         graph = ops.cached_graph(edge_index, x_src.shape[0])
         out = ops.gat_aggregate(h_s, h_t, a_t2s, a_s2t, graph, self._dst_is_src(c), self.negative_slope)

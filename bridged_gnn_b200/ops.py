@@ -306,11 +306,12 @@ def gat_aggregate(Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope=0.1):
 # ----------------------------------------------------------------------------------- AdaptedConv node-wise epilogue
 class _AdaptedTransformFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, P, wd, kg, is_src):
+    def forward(ctx, P, wd, kg, is_src, bias):
         lib = _lib.load()
         f32 = torch.float32
         P = P.to(f32).contiguous()
         wd_c, kg_c = wd.to(f32).contiguous().view(-1), kg.to(f32).contiguous().view(-1)
+        b_c = None if bias is None else bias.to(f32).contiguous().view(-1)
         n = P.shape[0]
         c = (P.shape[1] - 2) // 2
         dev = P.device
@@ -319,10 +320,10 @@ class _AdaptedTransformFn(torch.autograd.Function):
         gates = torch.empty((n, 2), dtype=f32, device=dev)
         with _lib.call("bgnn_adapted_transform_fwd_f32"):
             _lib.check(lib.bgnn_adapted_transform_fwd_f32(_lib.ptr(P), _lib.ptr(is_src, torch.uint8), _lib.ptr(wd_c),
-                                                          _lib.ptr(kg_c), n, c, _lib.ptr(Hs), _lib.ptr(Ht),
-                                                          _lib.ptr(gates), _lib.stream(dev)))
+                                                          _lib.ptr(kg_c), _lib.ptr(b_c, f32, True), n, c, _lib.ptr(Hs),
+                                                          _lib.ptr(Ht), _lib.ptr(gates), _lib.stream(dev)))
         ctx.save_for_backward(gates, wd_c, is_src)
-        ctx.shapes = (wd.shape, kg.shape, c)
+        ctx.shapes = (wd.shape, kg.shape, c, None if bias is None else bias.shape)
         ctx.mark_non_differentiable(gates)
         return Hs, Ht, gates
 
@@ -330,28 +331,30 @@ class _AdaptedTransformFn(torch.autograd.Function):
     def backward(ctx, gHs, gHt, _ggates):
         lib = _lib.load()
         gates, wd_c, is_src = ctx.saved_tensors
-        wd_shape, kg_shape, c = ctx.shapes
+        wd_shape, kg_shape, c, bias_shape = ctx.shapes
         f32 = torch.float32
         gHs, gHt = gHs.to(f32).contiguous(), gHt.to(f32).contiguous()
         n = gHs.shape[0]
         dev = gHs.device
         gP = torch.empty((n, 2 * c + 2), dtype=f32, device=dev)
-        red = torch.empty((2 * c + 2,), dtype=f32, device=dev)
+        red = torch.empty((4 * c + 2,), dtype=f32, device=dev)
         ws = _lib.workspace(lib.bgnn_adapted_transform_bwd_workspace_bytes(c), dev)
         with _lib.call("bgnn_adapted_transform_bwd_f32"):
             _lib.check(lib.bgnn_adapted_transform_bwd_f32(_lib.ptr(gHs), _lib.ptr(gHt), _lib.ptr(gates),
                                                           _lib.ptr(is_src, torch.uint8), _lib.ptr(wd_c), n, c,
                                                           _lib.ptr(gP), _lib.ptr(red), _lib.ptr(ws), ws.numel(),
                                                           _lib.stream(dev)))
-        return gP, red[: 2 * c].view(wd_shape), red[2 * c:].view(kg_shape), None
+        g_bias = None if bias_shape is None else red[2 * c + 2:].view(bias_shape)
+        return gP, red[: 2 * c].view(wd_shape), red[2 * c: 2 * c + 2].view(kg_shape), None, g_bias
 
 
-def adapted_transform(P, wd, kg, is_src):
+def adapted_transform(P, wd, kg, is_src, bias=None):
     """Fused node-wise epilogue of AdaptedConv (models/KTGNN.py:277-284 after the single contraction
-    P = x [W_s; W_t; a_g_s2t[:D]; a_g_t2s[:D]]^T + b): returns (Hs, Ht) = (lin_s(x_t2s), lin_t(x_s2t)).
+    P = x [W_s; W_t; a_g_s2t[:D]; a_g_t2s[:D]]^T): returns (Hs, Ht) = (lin_s(x_t2s), lin_t(x_s2t)).
     P [n, 2c+2]; wd [2c] or [1, 2c] = (W_s Delta, W_t Delta); kg [2] = Delta part of the two gate logits;
-    is_src uint8 [n].  Differentiable in P, wd, kg."""
-    Hs, Ht, _ = _AdaptedTransformFn.apply(P, wd, kg, is_src)
+    is_src uint8 [n]; bias [2c] = (b_s, b_t) or None (added here rather than by a separate pass over P).
+    Differentiable in P, wd, kg, bias."""
+    Hs, Ht, _ = _AdaptedTransformFn.apply(P, wd, kg, is_src, bias)
     return Hs, Ht
 
 
@@ -415,7 +418,7 @@ def adapted_skinny(x, w_cat, bias_cat, wd, kg, is_src):
 
 class _DomainMeansFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, is_src, inv_counts, dom_index):
+    def forward(ctx, x, is_src, inv_counts):
         lib = _lib.load()
         x = x.to(torch.float32).contiguous()
         n, d = x.shape
@@ -424,22 +427,23 @@ class _DomainMeansFn(torch.autograd.Function):
         with _lib.call("bgnn_domain_colsum_f32"):
             _lib.check(lib.bgnn_domain_colsum_f32(_lib.ptr(x), _lib.ptr(is_src, torch.uint8), n, d, _lib.ptr(sums),
                                                   _lib.ptr(ws), ws.numel(), _lib.stream(x.device)))
-        ctx.save_for_backward(inv_counts, dom_index)
+        ctx.save_for_backward(inv_counts, is_src)
         return sums * inv_counts.view(2, 1)
 
     @staticmethod
     def backward(ctx, gmeans):
-        inv_counts, dom_index = ctx.saved_tensors
-        return (gmeans * inv_counts.view(2, 1)).index_select(0, dom_index), None, None, None
+        inv_counts, is_src = ctx.saved_tensors
+        g = gmeans * inv_counts.view(2, 1)
+        # every source row receives g[0], every target row g[1]: one elementwise pass, no gather
+        return torch.where(is_src.view(-1, 1) != 0, g[0:1], g[1:2]), None, None
 
 
 def domain_colsum_supported(d):
     return d >= 4 and d % 4 == 0 and d <= 1024
 
 
-def domain_means(x, is_src, inv_counts, dom_index):
+def domain_means(x, is_src, inv_counts):
     """[2, d]: mean of the source-domain rows and of the target-domain rows of x (models/KTGNN.py:275-276), one
-    pass over x.  is_src uint8 [n]; inv_counts float32 [2] = (1/Ns, 1/Nt); dom_index int64 [n] = 0 for source rows,
-    1 for target rows (used by the backward pass)."""
-    return _DomainMeansFn.apply(x, is_src, inv_counts, dom_index)
+    pass over x.  is_src uint8 [n]; inv_counts float32 [2] = (1/Ns, 1/Nt)."""
+    return _DomainMeansFn.apply(x, is_src, inv_counts)
 

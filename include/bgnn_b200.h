@@ -132,15 +132,16 @@ int bgnn_gatv2_bwd_ord_f32(const int32_t* rowptr, const int32_t* col, const int3
                            float* g_af_s2t, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Node-wise epilogue of AdaptedConv's domain-shift transform (models/KTGNN.py:275-284).  The host computes
- * P [n, 2c+2] = x [W_s; W_t; a_g_s2t[:D]; a_g_t2s[:D]]^T (+ biases), wd [2c] = [W_s Delta; W_t Delta] and
- * kg [2] = [a_g_s2t[D:].Delta, a_g_t2s[D:].Delta]; this call writes
- *   gates[i] = tanh(P[i, 2c:2c+2] + kg),  Hs[i] = P[i,0:c] + (1-c_i) gates[i,1] wd[0:c],
- *   Ht[i] = P[i,c:2c] - c_i gates[i,0] wd[c:2c]          (c_i = is_src[i]),
+ * P [n, 2c+2] = x [W_s; W_t; a_g_s2t[:D]; a_g_t2s[:D]]^T, wd [2c] = [W_s Delta; W_t Delta] and
+ * kg [2] = [a_g_s2t[D:].Delta, a_g_t2s[D:].Delta]; bias [2c] = (b_s, b_t) or NULL.  This call writes
+ *   gates[i] = tanh(P[i, 2c:2c+2] + kg),  Hs[i] = P[i,0:c] + b_s + (1-c_i) gates[i,1] wd[0:c],
+ *   Ht[i] = P[i,c:2c] + b_t - c_i gates[i,0] wd[c:2c]          (c_i = is_src[i]),
  * i.e. lin_s(x_t2s) and lin_t(x_s2t) of the reference without materialising the shifted copies of x. */
-int bgnn_adapted_transform_fwd_f32(const float* P, const uint8_t* is_src, const float* wd, const float* kg, int64_t n,
-                                   int c, float* Hs, float* Ht, float* gates, void* stream);
+int bgnn_adapted_transform_fwd_f32(const float* P, const uint8_t* is_src, const float* wd, const float* kg,
+                                   const float* bias, int64_t n, int c, float* Hs, float* Ht, float* gates, void* stream);
 
-/* Backward: gP [n, 2c+2] (fully written), g_wd_kg [2c+2] = (d wd, d kg).  Deterministic two-stage reductions. */
+/* Backward: gP [n, 2c+2] (fully written), red [4c+2] = (d wd [2c], d kg [2], d bias [2c]).  Deterministic
+ * two-stage reductions. */
 size_t bgnn_adapted_transform_bwd_workspace_bytes(int c);
 int bgnn_adapted_transform_bwd_f32(const float* gHs, const float* gHt, const float* gates, const uint8_t* is_src,
                                    const float* wd, int64_t n, int c, float* gP, float* g_wd_kg, void* workspace,

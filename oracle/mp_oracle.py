@@ -166,11 +166,13 @@ def gcn_net(x, edge_index, P, n_layers=2):
     return F.log_softmax(x, dim=1)
 
 
-def adapted_transform_epilogue(P, wd, kg, is_src):
+def adapted_transform_epilogue(P, wd, kg, is_src, bias=None):
     """Node-wise epilogue of AdaptedConv after the single contraction P = x [W_s; W_t; a_g_s2t[:D]; a_g_t2s[:D]]^T + b
     (algebraically equal to models/KTGNN.py:277-284; equality with the reference's own op order is checked in
     tests/test_host_logic.py::test_adapted_conv_algebra_matches_reference).  Returns (Hs, Ht)."""
     c = (P.shape[1] - 2) // 2
+    if bias is not None:            # (b_s, b_t) of lin_s / lin_t when the contraction was done without them
+        P = P + torch.cat((bias.reshape(-1), bias.new_zeros(2)))
     g = torch.tanh(P[:, 2 * c:] + kg.view(1, 2))
     cf = is_src.to(P.dtype)
     wd = wd.reshape(-1)

@@ -230,21 +230,25 @@ def test_gat_aggregate_single_edge_rows_and_large_scores():
 
 
 @pytest.mark.parametrize("n,c", [(1, 1), (1000, 2), (777, 31), (5000, 32), (4096, 64), (3000, 100), (2000, 256), (300, 512)])
-def test_adapted_transform_forward_backward(n, c):
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_adapted_transform_forward_backward(n, c, with_bias):
     ops = _ops()
     g = torch.Generator().manual_seed(40 + c)
     P = torch.randn(n, 2 * c + 2, generator=g)
     wd, kg = torch.randn(1, 2 * c, generator=g), torch.randn(2, generator=g)
+    bias = torch.randn(2 * c, generator=g)
     cm = torch.rand(n, generator=g) < 0.7
     go_s, go_t = torch.randn(n, c, generator=g), torch.randn(n, c, generator=g)
-    leaf = [t.clone().requires_grad_(True) for t in (P, wd, kg)]
-    Hs_r, Ht_r = mo.adapted_transform_epilogue(leaf[0], leaf[1], leaf[2], cm.to(torch.uint8))
+    vals = [P, wd, kg] + ([bias] if with_bias else [])
+    leaf = [t.clone().requires_grad_(True) for t in vals]
+    Pb = leaf[0] + torch.cat((leaf[3], torch.zeros(2))) if with_bias else leaf[0]
+    Hs_r, Ht_r = mo.adapted_transform_epilogue(Pb, leaf[1], leaf[2], cm.to(torch.uint8))
     ((Hs_r * go_s).sum() + (Ht_r * go_t).sum()).backward()
-    dl = [t.clone().cuda().requires_grad_(True) for t in (P, wd, kg)]
-    Hs, Ht = ops.adapted_transform(dl[0], dl[1], dl[2], cm.to(torch.uint8).cuda())
+    dl = [t.clone().cuda().requires_grad_(True) for t in vals]
+    Hs, Ht = ops.adapted_transform(dl[0], dl[1], dl[2], cm.to(torch.uint8).cuda(), dl[3] if with_bias else None)
     assert relclose(Hs, Hs_r, 2e-6) and relclose(Ht, Ht_r, 2e-6)
     ((Hs * go_s.cuda()).sum() + (Ht * go_t.cuda()).sum()).backward()
-    for got, ref, name in zip(dl, leaf, ("P", "wd", "kg")):
+    for got, ref, name in zip(dl, leaf, ("P", "wd", "kg", "bias")):
         assert got.grad.shape == ref.grad.shape and relclose(got.grad, ref.grad, 2e-5), name
 
 
@@ -293,7 +297,7 @@ def test_domain_means_forward_backward(n, d):
     (ref * gm).sum().backward()
     xd = x.clone().cuda().requires_grad_(True)
     inv = torch.stack((1.0 / ns, 1.0 / nt)).cuda()
-    got = ops.domain_means(xd, cm.to(torch.uint8).cuda(), inv, (~cm).long().cuda())
+    got = ops.domain_means(xd, cm.to(torch.uint8).cuda(), inv)
     assert relclose(got, ref, 2e-6)
     (got * gm.cuda()).sum().backward()
     assert relclose(xd.grad, xr.grad, 2e-6)

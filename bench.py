@@ -125,6 +125,16 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def load_traffic():
+    """DRAM bytes (read + write) per launch of the dominant kernels, from `ncu --set full` captures of this very
+    workload (tools/ncu_traffic.py -> profiles/traffic.json); {} when no capture has been summarised yet."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
 # ----------------------------------------------------------------------------- CPU baseline (oracle port)
 def cpu_knn_sample(rows=12, seed=0):
     """Oracle (reference op order: pair enumeration -> gather -> CosineSimilarity -> sigmoid -> top-k) on a
@@ -307,8 +317,11 @@ def run_ours(args):
     flops = 2.0 * NT * NS * DIM
     half_rate = args.knn_algo in ("tc3", "tc1")
     tc_peak = peaks["bf16_tflops"] / (2.0 if half_rate else 1.0)
+    traffic = load_traffic()
+    knn_tr = traffic.get("knn_cosine_f16_kernel" if not half_rate else "knn_cosine_tc_kernel", {})
     knn_roof = {"bound": "tensor", "achieved": flops / (knn_call_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s",
-                "frac": flops / (knn_call_ms * 1e-3) / 1e12 / tc_peak, "traffic": None,
+                "frac": flops / (knn_call_ms * 1e-3) / 1e12 / tc_peak, "traffic": knn_tr.get("bytes"),
+                "traffic_source": knn_tr.get("source"),
                 "kernel": ("knn_cosine_tc_kernel" if half_rate else "knn_cosine_f16_kernel")
                 + " (timed: whole bgnn_knn_cosine_f32 call incl. prologue, merge/re-score and exact fallback)",
                 "peak_source": peaks["source"] + (" bf16 dense / 2 (tcgen05 kind::tf32 runs at half the 16-bit rate)"
@@ -399,7 +412,8 @@ def run_ours(args):
         dur_ms = shares[top] / max(calls_per_step, 1e-9)
         b = gat_bytes(c, "bwd" in top)
         roof = {"bound": "hbm", "achieved": b / (dur_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": b / (dur_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "kernel": top,
+                "frac": b / (dur_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get(top, {}).get("bytes"),
+                "traffic_source": traffic.get(top, {}).get("source"), "kernel": top,
                 "avg_launch_ms": dur_ms, "share_of_step": shares[top] / step_ms, "algorithmic_bytes_per_launch": b,
                 "peak_source": peaks["source"], "kernel_ms_per_step": {k: round(v, 4) for k, v in shares.items()}}
 

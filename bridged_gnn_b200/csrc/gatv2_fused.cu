@@ -421,7 +421,7 @@ reduce_partials_kernel(const float* __restrict__ part, long long nparts, int wid
 //   dH[j] += alpha_ij gout_i + ds_ij a (.) lrelu'(H_j + H_i)
 // into gHs (edges into source-domain destinations) / gHt (target-domain destinations).
 template <int VEC, int G, int CH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (VEC * CH <= 4) ? 4 : 1)
 gatv2_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restrict__ t_col, const int* __restrict__ t_order,
                      const uint8_t* __restrict__ dst_is_src, const float* __restrict__ af_t2s,
                      const float* __restrict__ af_s2t, float slope, long long n, int c, int cw,

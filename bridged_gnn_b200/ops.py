@@ -111,7 +111,7 @@ def coalesce(edge_index, num_nodes=None):
     return torch.stack((row, col.to(torch.int64)), 0)
 
 
-WIDE_ROW = 16         # feature widths from here on process rows in degree order
+WIDE_ROW = 32         # feature widths from here on (rows of >= 128 B) process rows in degree order
 
 
 def rows_by_degree(rowptr, n, min_degree=0):

@@ -100,7 +100,7 @@ def workspace(nbytes, device):
 # ---- instrumentation used by bench.py (off by default; no effect on results) ----------------------
 # kernels launched per C-ABI call (hand-written kernels of this library only; CUB's sort/scan inside
 # bgnn_edges_to_csr are not counted)
-KERNELS_PER_CALL = {"bgnn_knn_cosine_f32": 11, "bgnn_knn_cosine_f32[simt]": 4, "bgnn_knn_addrelu_f32": 2,
+KERNELS_PER_CALL = {"bgnn_knn_cosine_f32": 13, "bgnn_knn_cosine_f32[simt]": 4, "bgnn_knn_addrelu_f32": 2,
                     "bgnn_edges_to_csr": 4, "bgnn_spmm_csr_f32": 1, "bgnn_gatv2_fwd_f32": 1, "bgnn_gatv2_bwd_f32": 3,
                     "bgnn_gatv2_fwd_ord_f32": 1, "bgnn_gatv2_bwd_ord_f32": 3, "bgnn_rows_by_degree": 1,
                     "bgnn_adapted_transform_fwd_f32": 1, "bgnn_adapted_transform_bwd_f32": 2,

@@ -94,6 +94,7 @@ static size_t knn_ws_bytes(const KnnPlan& p, int64_t nq, int64_t ndb) {
   add(p.cand_elems * 4);
   add((size_t)nq * 4);   // fallback row list
   add(256);              // fallback row count
+  add(knn_exact_rows_workspace_bytes(p.simt.kc - 1));   // per-slice lists of the few-rows exact sweep
   return align_up(b, 256) + 256;
 }
 
@@ -151,6 +152,7 @@ int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb
   int* cand_idx = w.take<int>(p.cand_elems);
   int* fb_rows = w.take<int>((size_t)nq);
   int* fb_count = w.take<int>(64);
+  char* xr_ws = w.take<char>(knn_exact_rows_workspace_bytes(k));
   if (!w.ok()) return BGNN_ERR_WORKSPACE;
   int rc;
   // prologue: unit rows (plus the tf32 hi/lo split or the fp16 rounding for the tensor-core sweeps)
@@ -166,11 +168,11 @@ int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb
 
   if (!p.passes && !p.f16) {
     rc = launch_knn_simt(BGNN_PAIR_DOT, qhi, nullptr, (int)nq, dhi, nullptr, (int)ndb, d, p.ld, nullptr, 0.f,
-                         apply_sigmoid, p.simt.kc, p.simt.nsplit, p.simt.per_split, nullptr, nullptr, cand_val,
+                         apply_sigmoid, p.simt.kc, p.simt.nsplit, p.simt.per_split, nullptr, nullptr, 0, cand_val,
                          cand_idx, stream);
     if (rc != BGNN_OK) return rc;
     rc = launch_knn_merge(cand_val, cand_idx, p.simt.nsplit, p.simt.kc, (int)nq, k, 0, nullptr, nullptr, nullptr,
-                          nullptr, d, p.ld, apply_sigmoid, -1.f, nullptr, nullptr, nullptr, (long long*)out_idx, out_val,
+                          nullptr, d, p.ld, apply_sigmoid, -1.f, nullptr, nullptr, nullptr, 0, (long long*)out_idx, out_val,
                           out_gap, nullptr, nullptr, stream);
     if (rc != BGNN_OK) return rc;
     if (out_stats) { set_int_kernel<<<1, 1, 0, stream>>>(out_stats, 0); BGNN_LAUNCH_CHECK(); }
@@ -192,15 +194,21 @@ int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb
   // error bound of the approximate dot product of two unit rows (see DESIGN.md "kNN exactness")
   const float delta = p.f16 ? (9.7657e-4f + 5.97e-8f * sqrtf((float)d) + 4.0e-6f) : ((p.passes == 3) ? 3.0e-5f : 2.0e-3f);
   rc = launch_knn_merge(cand_val, cand_idx, p.tc.nlists, p.tc.kc, (int)nq, k, 1, qhi, qlo, dhi, dlo, p.ld, p.ld,
-                        apply_sigmoid, delta, seed_thr, nullptr, nullptr, (long long*)out_idx, out_val, out_gap, fb_rows,
+                        apply_sigmoid, delta, seed_thr, nullptr, nullptr, 0, (long long*)out_idx, out_val, out_gap, fb_rows,
                         fb_count, stream);
   if (rc != BGNN_OK) return rc;
+  // uncertified rows, exactly: a handful -> one db slice per CTA (knn_exact_rows); more -> the tiled sweep + merge.
+  // The count lives on the device, so both are launched and each returns at once when it is not its case.
+  const int few = knn_exact_rows_max((int)ndb, p.ld, k);
+  rc = launch_knn_exact_rows(qhi, qlo, dhi, dlo, (int)ndb, p.ld, p.ld, apply_sigmoid, k, fb_rows, fb_count,
+                             (long long*)out_idx, out_val, out_gap, xr_ws, knn_exact_rows_workspace_bytes(k), stream);
+  if (rc != BGNN_OK) return rc;
   rc = launch_knn_simt(BGNN_PAIR_DOT, qhi, qlo, (int)nq, dhi, dlo, (int)ndb, p.ld, p.ld, nullptr, 0.f, apply_sigmoid,
-                       p.simt.kc, p.simt.nsplit, p.simt.per_split, fb_rows, fb_count, cand_val, cand_idx, stream);
+                       p.simt.kc, p.simt.nsplit, p.simt.per_split, fb_rows, fb_count, few, cand_val, cand_idx, stream);
   if (rc != BGNN_OK) return rc;
   rc = launch_knn_merge(cand_val, cand_idx, p.simt.nsplit, p.simt.kc, (int)nq, k, 0, nullptr, nullptr, nullptr,
-                        nullptr, p.ld, p.ld, apply_sigmoid, -1.f, nullptr, fb_rows, fb_count, (long long*)out_idx, out_val,
-                        out_gap, nullptr, nullptr, stream);
+                        nullptr, p.ld, p.ld, apply_sigmoid, -1.f, nullptr, fb_rows, fb_count, few, (long long*)out_idx,
+                        out_val, out_gap, nullptr, nullptr, stream);
   if (rc != BGNN_OK) return rc;
   if (out_stats) { copy_int_kernel<<<1, 1, 0, stream>>>(fb_count, out_stats); BGNN_LAUNCH_CHECK(); }
   return BGNN_OK;
@@ -226,10 +234,10 @@ int bgnn_knn_addrelu_f32(const float* Uq, int64_t nq, const float* Udb, int64_t 
   int* cand_idx = w.take<int>(ce);
   if (!w.ok()) return BGNN_ERR_WORKSPACE;
   int rc = launch_knn_simt(BGNN_PAIR_ADDRELU, Uq, nullptr, (int)nq, Udb, nullptr, (int)ndb, h, h, w2, b2, apply_sigmoid,
-                           p.kc, p.nsplit, p.per_split, nullptr, nullptr, cand_val, cand_idx, stream);
+                           p.kc, p.nsplit, p.per_split, nullptr, nullptr, 0, cand_val, cand_idx, stream);
   if (rc != BGNN_OK) return rc;
   return launch_knn_merge(cand_val, cand_idx, p.nsplit, p.kc, (int)nq, k, 0, nullptr, nullptr, nullptr, nullptr, h, h,
-                          apply_sigmoid, -1.f, nullptr, nullptr, nullptr, (long long*)out_idx, out_val, out_gap, nullptr,
+                          apply_sigmoid, -1.f, nullptr, nullptr, nullptr, 0, (long long*)out_idx, out_val, out_gap, nullptr,
                           nullptr, stream);
 }
 

@@ -10,7 +10,14 @@ namespace bgnn {
 #define BGNN_PAIR_ADDRELU 1
 int launch_knn_simt(int mode, const float* Q, const float* Qlo, int nq, const float* DB, const float* DBlo, int ndb,
                     int d, int ld, const float* w, float bias, int apply_sigmoid, int kc, int nsplit, int db_per_split,
-                    const int* row_list, const int* row_count, float* cand_val, int* cand_idx, cudaStream_t stream);
+                    const int* row_list, const int* row_count, int few_rows, float* cand_val, int* cand_idx,
+                    cudaStream_t stream);
+// exact sweep for a handful of listed rows (0 < *row_count <= knn_exact_rows_max(), decided on the device)
+int knn_exact_rows_max(int ndb, int ld, int k);
+size_t knn_exact_rows_workspace_bytes(int k);
+int launch_knn_exact_rows(const float* Q, const float* Qlo, const float* DB, const float* DBlo, int ndb, int d, int ld,
+                          int apply_sigmoid, int k, const int* row_list, const int* row_count, long long* out_idx,
+                          float* out_val, float* out_gap, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // knn_select.cu
 #define BGNN_MERGE_MAX_CAND 1024
@@ -19,7 +26,8 @@ int launch_normalize_split(const float* x, long long n, int d, int ld, int norma
 int launch_knn_merge(const float* cand_val, const int* cand_idx, int nlists, int kc, int nq, int k, int rescore,
                      const float* qhi, const float* qlo, const float* dhi, const float* dlo, int d, int ld,
                      int apply_sigmoid, float delta, const float* seed_thr, const int* row_list, const int* row_count,
-                     long long* out_idx, float* out_val, float* out_gap, int* fb_rows, int* fb_count, cudaStream_t stream);
+                     int few_rows, long long* out_idx, float* out_val, float* out_gap, int* fb_rows, int* fb_count,
+                     cudaStream_t stream);
 
 // knn_cosine_sm100.cu  (tcgen05 / TMEM / TMA)
 struct TcPlan {

@@ -59,13 +59,14 @@ knn_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ can
                  int rescore, const float* __restrict__ qhi, const float* __restrict__ qlo,
                  const float* __restrict__ dhi, const float* __restrict__ dlo, int d, int ld, int apply_sigmoid,
                  float delta, const float* __restrict__ seed_thr, const int* __restrict__ row_list,
-                 const int* __restrict__ row_count, long long* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ out_gap,
+                 const int* __restrict__ row_count, int few_rows, long long* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ out_gap,
                  int* __restrict__ fb_rows, int* __restrict__ fb_count) {
   __shared__ float sv[MG_WARPS][MG_MAXC];
   __shared__ int si[MG_WARPS][MG_MAXC];
   extern __shared__ __align__(16) float sqrow[];  // [MG_WARPS][ld] when rescoring
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nrows = row_list ? min(__ldg(row_count), nq) : nq;
+  if (row_list && nrows <= few_rows) return;        // a handful of rows went through knn_exact_rows_kernel
   const long long r = (long long)blockIdx.x * MG_WARPS + wid;
   if (r >= nrows) return;
   const long long row = row_list ? (long long)row_list[r] : r;
@@ -167,7 +168,7 @@ knn_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ can
 int launch_knn_merge(const float* cand_val, const int* cand_idx, int nlists, int kc, int nq, int k, int rescore,
                      const float* qhi, const float* qlo, const float* dhi, const float* dlo, int d, int ld,
                      int apply_sigmoid, float delta, const float* seed_thr, const int* row_list, const int* row_count,
-                     long long* out_idx, float* out_val, float* out_gap, int* fb_rows, int* fb_count,
+                     int few_rows, long long* out_idx, float* out_val, float* out_gap, int* fb_rows, int* fb_count,
                      cudaStream_t stream) {
   if (nq <= 0) return BGNN_OK;
   if (nlists * kc > MG_MAXC) return BGNN_ERR_UNSUPPORTED;
@@ -175,7 +176,7 @@ int launch_knn_merge(const float* cand_val, const int* cand_idx, int nlists, int
   size_t dyn = rescore ? (size_t)MG_WARPS * ld * sizeof(float) : 0;
   knn_merge_kernel<<<(nq + MG_WARPS - 1) / MG_WARPS, MG_WARPS * 32, dyn, stream>>>(
       cand_val, cand_idx, nlists, kc, nq, k, rescore, qhi, qlo, dhi, dlo, d, ld, apply_sigmoid, delta, seed_thr,
-      row_list, row_count, out_idx, out_val, out_gap, fb_rows, fb_count);
+      row_list, row_count, few_rows, out_idx, out_val, out_gap, fb_rows, fb_count);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(ST_THREADS)
 knn_simt_kernel(const float* __restrict__ Q, const float* __restrict__ Qlo, int nq, const float* __restrict__ DB,
                 const float* __restrict__ DBlo, int ndb, int d, int ld, int vec_ok, const float* __restrict__ w,
                 float bias, int apply_sigmoid, int kc, int db_per_split, const int* __restrict__ row_list,
-                const int* __restrict__ row_count, float* __restrict__ cand_val, int* __restrict__ cand_idx) {
+                const int* __restrict__ row_count, int few_rows, float* __restrict__ cand_val, int* __restrict__ cand_idx) {
   __shared__ __align__(16) float sq[ST_KB][ST_LD];
   __shared__ __align__(16) float sd[ST_KB][ST_LD];
   __shared__ float sw[ST_KB];
@@ -70,6 +70,7 @@ knn_simt_kernel(const float* __restrict__ Q, const float* __restrict__ Qlo, int 
 
   const int tid = threadIdx.x;
   const int nrows = row_list ? min(__ldg(row_count), nq) : nq;
+  if (row_list && nrows <= few_rows) return;      // a handful of rows: knn_exact_rows_kernel does them
   const int split = blockIdx.y;
   const int db_begin = split * db_per_split;
   const int db_end = min(ndb, db_begin + db_per_split);
@@ -144,7 +145,8 @@ knn_simt_kernel(const float* __restrict__ Q, const float* __restrict__ Qlo, int 
 
 int launch_knn_simt(int mode, const float* Q, const float* Qlo, int nq, const float* DB, const float* DBlo, int ndb,
                     int d, int ld, const float* w, float bias, int apply_sigmoid, int kc, int nsplit, int db_per_split,
-                    const int* row_list, const int* row_count, float* cand_val, int* cand_idx, cudaStream_t stream) {
+                    const int* row_list, const int* row_count, int few_rows, float* cand_val, int* cand_idx,
+                    cudaStream_t stream) {
   if (nq <= 0 || nsplit <= 0) return BGNN_OK;
   int qtiles = (nq + ST_TQ - 1) / ST_TQ;
   if (row_list) qtiles = qtiles < 16 ? qtiles : 16;     // fallback rows are few; CTAs stride over the list
@@ -157,13 +159,190 @@ int launch_knn_simt(int mode, const float* Q, const float* Qlo, int nq, const fl
     auto kern = knn_simt_kernel<BGNN_PAIR_DOT>;
     BGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     kern<<<grid, ST_THREADS, dyn, stream>>>(Q, Qlo, nq, DB, DBlo, ndb, d, ld, vec_ok, w, bias, apply_sigmoid, kc,
-                                            db_per_split, row_list, row_count, cand_val, cand_idx);
+                                            db_per_split, row_list, row_count, few_rows, cand_val, cand_idx);
   } else {
     auto kern = knn_simt_kernel<BGNN_PAIR_ADDRELU>;
     BGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     kern<<<grid, ST_THREADS, dyn, stream>>>(Q, Qlo, nq, DB, DBlo, ndb, d, ld, vec_ok, w, bias, apply_sigmoid, kc,
-                                            db_per_split, row_list, row_count, cand_val, cand_idx);
+                                            db_per_split, row_list, row_count, few_rows, cand_val, cand_idx);
   }
+  BGNN_LAUNCH_CHECK();
+  return BGNN_OK;
+}
+
+// ---- exact sweep for a HANDFUL of rows -----------------------------------------------------------------------
+// The tensor-core build leaves 0-2 uncertified rows out of 2.6e5; the tiled sweep above spends 3.9 ms on them
+// (64-row tiles with one live row, 48 CTAs).  Here every CTA takes a slice of the db for each listed row: one
+// thread per db row (the same fmaf chain over h, so similarities are bit-identical), the slice's scores staged
+// in shared memory, k1 rounds of block arg-best under the parity key; a second kernel merges the per-CTA lists.
+constexpr int XR_THREADS = 256;
+constexpr int XR_CTAS = kNumSMs * 2;
+constexpr int XR_MAX_ROWS = 8;
+
+__device__ __forceinline__ bool xr_better(float av, int ai, float bv, int bi) {   // a ranks above b
+  return av > bv || (av == bv && ai < bi);
+}
+
+// block arg-best over (val[i], idx[i]) for i in [0, m): result in all threads
+__device__ __forceinline__ void xr_block_best(const float* val, const int* idx, int m, float* s_v, int* s_i, int* s_p,
+                                              float& bv, int& bi, int& bp) {
+  bv = -INFINITY; bi = 0x7fffffff; bp = -1;
+  for (int i = threadIdx.x; i < m; i += XR_THREADS) {
+    const int j = idx[i];
+    if (j < 0) continue;
+    const float v = val[i];
+    if (bp < 0 || xr_better(v, j, bv, bi)) { bv = v; bi = j; bp = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+    if (op >= 0 && (bp < 0 || xr_better(ov, oi, bv, bi))) { bv = ov; bi = oi; bp = op; }
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s_v[w] = bv; s_i[w] = bi; s_p[w] = bp; }
+  __syncthreads();
+  bv = s_v[0]; bi = s_i[0]; bp = s_p[0];
+#pragma unroll
+  for (int k = 1; k < XR_THREADS / 32; ++k)
+    if (s_p[k] >= 0 && (bp < 0 || xr_better(s_v[k], s_i[k], bv, bi))) { bv = s_v[k]; bi = s_i[k]; bp = s_p[k]; }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(XR_THREADS)
+knn_exact_rows_kernel(const float* __restrict__ Q, const float* __restrict__ Qlo, const float* __restrict__ DB,
+                      const float* __restrict__ DBlo, int ndb, int d, int ld, int apply_sigmoid, int k1,
+                      const int* __restrict__ row_list, const int* __restrict__ row_count, float* __restrict__ part_val,
+                      int* __restrict__ part_idx) {
+  extern __shared__ __align__(16) float xr_smem[];   // q row [ld], slice scores [slice], slice ids [slice]
+  __shared__ float s_v[XR_THREADS / 32];
+  __shared__ int s_i[XR_THREADS / 32], s_p[XR_THREADS / 32];
+  const int count = __ldg(row_count);
+  if (count <= 0 || count > XR_MAX_ROWS) return;
+  const int slice = (ndb + gridDim.x - 1) / gridDim.x;
+  const int begin = blockIdx.x * slice, end = min(ndb, begin + slice);
+  float* sq = xr_smem;
+  float* sv = xr_smem + ld;
+  int* si = reinterpret_cast<int*>(sv + slice);
+  for (int r = 0; r < count; ++r) {
+    const long long row = row_list[r];
+    for (int c = threadIdx.x; c < ld; c += XR_THREADS) sq[c] = Q[row * ld + c] + (Qlo ? Qlo[row * ld + c] : 0.f);
+    __syncthreads();
+    for (int j = begin + threadIdx.x; j < end; j += XR_THREADS) {
+      const float4* ph = reinterpret_cast<const float4*>(DB + (long long)j * ld);
+      const float4* pl = DBlo ? reinterpret_cast<const float4*>(DBlo + (long long)j * ld) : nullptr;
+      float acc = 0.f;
+      for (int h4 = 0; h4 < d / 4; ++h4) {
+        float4 x = __ldg(ph + h4);
+        if (pl) { const float4 y = __ldg(pl + h4); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+        const float4 q = *reinterpret_cast<const float4*>(sq + 4 * h4);
+        acc = fmaf(q.x, x.x, acc);
+        acc = fmaf(q.y, x.y, acc);
+        acc = fmaf(q.z, x.z, acc);
+        acc = fmaf(q.w, x.w, acc);
+      }
+      sv[j - begin] = apply_sigmoid ? sigmoid_f32(acc) : acc;
+      si[j - begin] = j;
+    }
+    __syncthreads();
+    const int m = max(0, end - begin);
+    for (int round = 0; round < k1; ++round) {
+      float bv; int bi, bp;
+      xr_block_best(sv, si, m, s_v, s_i, s_p, bv, bi, bp);
+      if (threadIdx.x == 0) {
+        const long long o = ((long long)r * gridDim.x + blockIdx.x) * k1 + round;
+        part_val[o] = bp >= 0 ? bv : -INFINITY;
+        part_idx[o] = bp >= 0 ? bi : -1;
+        if (bp >= 0) si[bp] = -1;                 // consumed
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// one CTA per listed row: top-k (+1 for the gap) of the nparts * k1 per-slice winners
+__global__ void __launch_bounds__(XR_THREADS)
+knn_exact_rows_merge_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int nparts, int k1, int k,
+                            const int* __restrict__ row_list, const int* __restrict__ row_count,
+                            long long* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ out_gap) {
+  extern __shared__ __align__(16) float xm_smem[];   // values [nparts*k1], ids [nparts*k1]
+  __shared__ float s_v[XR_THREADS / 32];
+  __shared__ int s_i[XR_THREADS / 32], s_p[XR_THREADS / 32];
+  const int count = __ldg(row_count);
+  const int r = blockIdx.x;
+  if (count > XR_MAX_ROWS || r >= count) return;
+  const int m = nparts * k1;
+  float* sv = xm_smem;
+  int* si = reinterpret_cast<int*>(sv + m);
+  for (int i = threadIdx.x; i < m; i += XR_THREADS) {
+    sv[i] = part_val[(long long)r * m + i];
+    si[i] = part_idx[(long long)r * m + i];
+  }
+  __syncthreads();
+  const long long row = row_list[r];
+  float vk = -INFINITY;
+  for (int round = 0; round <= k; ++round) {
+    float bv; int bi, bp;
+    xr_block_best(sv, si, m, s_v, s_i, s_p, bv, bi, bp);
+    if (threadIdx.x == 0) {
+      if (round < k) {
+        out_idx[row * k + round] = bp >= 0 ? (long long)bi : -1LL;
+        out_val[row * k + round] = bp >= 0 ? bv : -INFINITY;
+        if (round == k - 1) vk = bp >= 0 ? bv : -INFINITY;
+        if (bp >= 0) si[bp] = -1;
+      } else if (out_gap) {
+        out_gap[row] = bp >= 0 ? (vk - bv) : INFINITY;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int XR_SMEM_MAX = 200 * 1024;
+
+// CTAs (= db slices) of the few-rows sweep: enough that a slice's scores fit in shared memory, few enough that
+// the merge kernel can hold all per-slice winners; 0 = this shape is left to the tiled sweep.
+static int xr_ctas(int ndb, int ld, int k) {
+  const int k1 = k + 1;
+  const int max_slice = (XR_SMEM_MAX - ld * 4) / 8;
+  int ctas = XR_CTAS;
+  while (ctas > 1 && (ndb + ctas - 1) / ctas < XR_THREADS) ctas >>= 1;   // at least one db row per thread
+  if ((ndb + ctas - 1) / ctas > max_slice) ctas = (ndb + max_slice - 1) / max_slice;
+  if ((size_t)2 * ctas * k1 * sizeof(float) > (size_t)XR_SMEM_MAX) return 0;
+  return ctas;
+}
+
+int knn_exact_rows_max(int ndb, int ld, int k) { return xr_ctas(ndb, ld, k) > 0 ? XR_MAX_ROWS : 0; }
+
+size_t knn_exact_rows_workspace_bytes(int k) {
+  // per-slice lists: at most XR_SMEM_MAX / 8 entries per listed row (the merge kernel's shared-memory bound)
+  return align_up((size_t)XR_MAX_ROWS * (XR_SMEM_MAX / 8) * sizeof(float), 256) * 2 + 256;
+}
+
+// Handles the listed rows iff 0 < *row_count <= knn_exact_rows_max(..) (decided on the device; no-op otherwise).
+int launch_knn_exact_rows(const float* Q, const float* Qlo, const float* DB, const float* DBlo, int ndb, int d, int ld,
+                          int apply_sigmoid, int k, const int* row_list, const int* row_count, long long* out_idx,
+                          float* out_val, float* out_gap, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (ld % 4 != 0 || d % 4 != 0) return BGNN_ERR_INVALID_ARG;
+  if (ws_bytes < knn_exact_rows_workspace_bytes(k)) return BGNN_ERR_WORKSPACE;
+  const int ctas = xr_ctas(ndb, ld, k);
+  if (ctas == 0) return BGNN_OK;                     // the caller passes few_rows = 0 to the tiled sweep
+  const int k1 = k + 1;
+  Workspace w(ws, ws_bytes);
+  float* pv = w.take<float>((size_t)XR_MAX_ROWS * ctas * k1);
+  int* pi = w.take<int>((size_t)XR_MAX_ROWS * ctas * k1);
+  if (!w.ok()) return BGNN_ERR_WORKSPACE;
+  const int slice = (ndb + ctas - 1) / ctas;
+  const size_t dyn1 = ((size_t)ld + 2 * (size_t)slice) * sizeof(float);
+  const size_t dyn2 = (size_t)2 * ctas * k1 * sizeof(float);
+  BGNN_CUDA_TRY(cudaFuncSetAttribute(knn_exact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn1));
+  BGNN_CUDA_TRY(cudaFuncSetAttribute(knn_exact_rows_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
+  knn_exact_rows_kernel<<<ctas, XR_THREADS, dyn1, stream>>>(Q, Qlo, DB, DBlo, ndb, d, ld, apply_sigmoid, k1, row_list,
+                                                           row_count, pv, pi);
+  BGNN_LAUNCH_CHECK();
+  knn_exact_rows_merge_kernel<<<XR_MAX_ROWS, XR_THREADS, dyn2, stream>>>(pv, pi, ctas, k1, k, row_list, row_count, out_idx,
+                                                                        out_val, out_gap);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }

@@ -195,6 +195,30 @@ def test_tensor_core_path_is_bit_identical_to_cuda_core_path(algo, nq, ndb, d, k
     assert int(st[0]) <= nq
 
 
+@pytest.mark.parametrize("algo", ["tc3", "f16"])
+@pytest.mark.parametrize("n_hard", [1, 5, 8, 9, 40])
+def test_uncertified_rows_few_and_many_take_the_exact_path(algo, n_hard):
+    """Rows whose neighbourhood is a tight cluster (hundreds of db rows within the approximation error of each
+    other) cannot be certified by the tensor-core sweep.  Up to 8 of them go through the few-rows exact sweep,
+    more through the tiled one; either way the output equals the CUDA-core path bit for bit."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11 + n_hard)
+    nq, ndb, d, k = 600, 40000, 128, 20
+    q = torch.randn(nq, d, generator=g)
+    db = torch.randn(ndb, d, generator=g)
+    v = torch.randn(d, generator=g)
+    db[1000:1400] = v + 1e-4 * torch.randn(400, d, generator=g)          # 400 near-duplicates
+    hard = torch.randperm(nq, generator=g)[:n_hard]
+    q[hard] = v + 1e-3 * torch.randn(n_hard, d, generator=g)             # queries sitting on the cluster
+    q, db = q.cuda(), db.cuda()
+    i0, v0, g0, _ = ops.knn_cosine(q, db, k, algo="simt")
+    i1, v1, g1, st = ops.knn_cosine(q, db, k, algo=algo)
+    assert int(st[0]) >= n_hard                                           # the hard rows were not certified
+    assert torch.equal(i0, i1) and torch.equal(v0, v1) and torch.equal(g0, g1)
+    if n_hard in (1, 5):      # (a stray random row may join the hard ones: leave room below the limit of 8)
+        assert int(st[0]) <= 8, "expected the few-rows path for this case (got %d uncertified rows)" % int(st[0])
+
+
 def test_exact_ties_resolve_to_lowest_index():
     """Duplicate db rows give exactly equal similarities (SURVEY F6: office has 52 duplicate source rows);
     the kept members of a tied group must be its lowest indices, i.e. the canonical order exactly."""

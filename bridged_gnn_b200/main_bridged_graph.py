@@ -14,6 +14,7 @@ import torch
 from . import ops
 from .data import Data, coalesce
 from .models.models import Adversarial_Learner, Adversarial_Learner_v2
+from .utils import eval_bridged_Graph, eval_homophily
 
 __all__ = ["add_topk_sim_cross_domain_edges", "add_topk_sim_within_domain_edges", "check_added_edges_cross_domain_validity",
            "check_added_edges_within_domain_validity", "merge_graphs", "reorder", "gen_bridged_graph"]
@@ -196,7 +197,8 @@ def merge_graphs(data_src, data_tar, edge_index_cross_added, edge_index_added_sr
 def gen_bridged_graph(args, data_src, data_tar, device, path_ckpt, mapper_idx_src=None, mapper_idx_tar=None,
                       epsilon=0.5, batch_size=1000):
     """main_bridged_graph.py:267-321: load the similarity learner, add cross- and within-domain edges,
-    optionally filter them, merge and re-order (eval_homophily's dense N x N diagnostics are not run)."""
+    optionally filter them, merge and re-order, print the homophily diagnostics (:315-316, without the dense
+    N x N matrix of the reference: bridged_gnn_b200.utils)."""
     if args.version == "v1":
         sim_model = Adversarial_Learner(data_src, data_tar, dim_hidden=args.hidden_dim, num_layer=args.num_layer,
                                         source_clf=True, norm_mode=args.norm_mode, norm_scale=args.norm_scale)
@@ -222,6 +224,9 @@ def gen_bridged_graph(args, data_src, data_tar, device, path_ckpt, mapper_idx_sr
     data_merge = merge_graphs(data_src, data_tar, ei_cross, ei_src, ei_tar)
     if mapper_idx_src is not None and mapper_idx_tar is not None:
         data_merge = reorder(data_merge, data_src, mapper_idx_src, mapper_idx_tar)
+    if getattr(args, "diagnostics", True):
+        eval_homophily(data_merge)
+        eval_bridged_Graph(data_merge)
     if getattr(args, "save", False):
         os.makedirs("../data_bridged_graph", exist_ok=True)
         torch.save({k: getattr(data_merge, k).cpu() for k in data_merge.keys()},

@@ -14,6 +14,7 @@ import torch
 import torch.nn.functional as F
 
 from .data import Data, load_pyg_dat, to_undirected
+from .utils import eval_bridged_Graph
 from .models import GCNNet, GraphSAGE, KTGNN_no_complement
 
 
@@ -136,6 +137,7 @@ def main(args):
     data = load_pyg_dat(args.path_data)
     device = _device(args.gpu)
     data = Data(**{k: getattr(data, k) for k in data.keys()}).to(device)
+    eval_bridged_Graph(data)                                   # main_graph_knowledge_transfer.py:403
     data.train_mask = data.train_mask & (data.y != -1)
     if args.to_undirected:
         # the reference discards ToUndirected's return value (:410-411, in place only on old PyG); BASELINE.json

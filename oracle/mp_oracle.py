@@ -179,3 +179,32 @@ def adapted_transform_epilogue(P, wd, kg, is_src, bias=None):
     Hs = P[:, :c] + ((1.0 - cf) * g[:, 1]).unsqueeze(1) * wd[:c]
     Ht = P[:, c:2 * c] - (cf * g[:, 0]).unsqueeze(1) * wd[c:]
     return Hs, Ht
+
+
+def eval_bridged_graph(edge_index, y, test_mask, n):
+    """utils.py:101-113: per node, the label histogram of its in-neighbours (unlabelled neighbours, y = -1, are
+    ignored), local homophily = share of the node's own label in it, and the fraction of test nodes whose local
+    homophily exceeds 0.5."""
+    adj = torch.zeros((n, n))
+    adj.index_put_((edge_index[1], edge_index[0]), torch.ones(edge_index.shape[1]), accumulate=True)   # SparseTensor(row=dst, col=src), duplicates add
+    y_onehot = F.one_hot(y + 1).float()[:, 1:]
+    lbl_dist = adj @ y_onehot
+    deg = lbl_dist.sum(1)
+    nonzero = (lbl_dist.sum(1) != 0) & (y != -1)
+    deg = deg + (~nonzero).float() * 1e-3
+    local = (lbl_dist * y_onehot).sum(1) / deg
+    return ((local[test_mask] > 0.5).sum() / test_mask.sum()).item(), local
+
+
+def eval_homophily(edge_index, y, n):
+    """utils.py:115-131: share of same-label pairs among the labelled edges, and among the labelled pairs of the
+    2-hop pattern nonzero(A A) with A = SparseTensor(row=edge_index[0], col=edge_index[1]) (dense here)."""
+    a = torch.zeros((n, n))
+    a.index_put_((edge_index[0], edge_index[1]), torch.ones(edge_index.shape[1]), accumulate=True)
+    two = torch.nonzero(a @ a, as_tuple=False).t()
+    m1 = (y[edge_index[0]] != -1) & (y[edge_index[1]] != -1)
+    r1 = ((y[edge_index[0]] == y[edge_index[1]]) & m1).sum() / m1.sum()
+    m2 = (y[two[0]] != -1) & (y[two[1]] != -1)
+    r2 = ((y[two[0]] == y[two[1]]) & m2).sum() / m2.sum()
+    return r1.item(), r2.item()
+

@@ -47,3 +47,8 @@ def office_mp():
 @pytest.fixture(scope="session")
 def fb_build():
     return load_golden("fb_h2c_cosine_build.npz")
+
+
+@pytest.fixture(scope="session")
+def diag_golden():
+    return load_golden("diagnostics.npz")

@@ -251,8 +251,40 @@ def office_mp(d):
     print("office mp: E_undirected", ei.shape[1], "E1", model.edge_index1.shape[1], "E2", model.edge_index2.shape[1])
 
 
+def diagnostics(d):
+    """utils.py:101-131 (eval_bridged_Graph, eval_homophily) on the shipped office bridged graph and on a seeded
+    random graph with unlabelled nodes and duplicate edges.  eval_homophily only prints: its output is parsed."""
+    import contextlib
+    import io
+    import utils as ref_utils  # noqa: E402  (reference, unmodified)
+    out = {}
+
+    def run(tag, data):
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            ratio = ref_utils.eval_bridged_Graph(data)
+            ref_utils.eval_homophily(data)
+        vals = [float(line.split(":")[1]) for line in buf.getvalue().splitlines() if line.startswith("homophily ratio")]
+        out[tag + ".local_ratio"] = np.float64(float(ratio))
+        out[tag + ".h1"], out[tag + ".h2"] = np.float64(vals[0]), np.float64(vals[1])
+        print(tag, float(ratio), vals)
+
+    run("office", Data(x=d["x"].clone(), edge_index=d["edge_index"].clone(), y=d["y"].clone(), test_mask=d["test_mask"].clone()))
+    g = torch.Generator().manual_seed(123)
+    n, e = 400, 3000
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei = torch.cat((ei, ei[:, :40]), 1)
+    y = torch.randint(0, 4, (n,), generator=g)
+    y[torch.rand(n, generator=g) < 0.25] = -1
+    tm = torch.rand(n, generator=g) < 0.5
+    out["rand.edge_index"], out["rand.y"], out["rand.test_mask"] = np_(ei), np_(y), np_(tm)
+    run("rand", Data(x=torch.zeros(n, 2), edge_index=ei, y=y, test_mask=tm))
+    np.savez_compressed(os.path.join(HERE, "diagnostics.npz"), **out)
+
+
 if __name__ == "__main__":
     d = office_build()
+    diagnostics(d)
     fb_cosine_build()
     office_mp(d)
     for f in sorted(os.listdir(HERE)):

@@ -134,6 +134,13 @@ class SparseTensor:
     def to(self, *a, **k):
         return self
 
+    def to_dense(self):
+        n, m = self.sparse_sizes
+        out = torch.zeros((n, m), dtype=self.value.dtype if self.value is not None else torch.float32)
+        v = self.value if self.value is not None else torch.ones(self.row.numel())
+        out.index_put_((self.row, self.col), v, accumulate=True)
+        return out
+
 
 def matmul(src, other, reduce="sum"):
     """torch_sparse.matmul(adj, x, reduce): out[row] = reduce_{(row,col)} value * x[col]."""

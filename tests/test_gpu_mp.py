@@ -303,6 +303,37 @@ def test_domain_means_forward_backward(n, d):
     assert relclose(xd.grad, xr.grad, 2e-6)
 
 
+# ------------------------------------------------------------------ diagnostics (utils.py:101-131) vs the dense restatement
+@pytest.mark.parametrize("n,e,classes", [(60, 300, 2), (500, 6000, 5), (1500, 9000, 31)])
+def test_homophily_diagnostics_match_the_dense_reference(n, e, classes):
+    from bridged_gnn_b200.data import Data
+    from bridged_gnn_b200.utils import eval_bridged_Graph, eval_homophily
+    g = torch.Generator().manual_seed(3 + n)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei = torch.cat((ei, ei[:, :20]), 1)                       # a few duplicate edges
+    y = torch.randint(0, classes, (n,), generator=g)
+    y[torch.rand(n, generator=g) < 0.2] = -1                  # unlabelled nodes
+    test_mask = torch.rand(n, generator=g) < 0.4
+    r_ref, _ = mo.eval_bridged_graph(ei, y, test_mask, n)
+    h1_ref, h2_ref = mo.eval_homophily(ei, y, n)
+    data = Data(x=torch.zeros(n, 4).cuda(), edge_index=ei.cuda(), y=y.cuda(), test_mask=test_mask.cuda())
+    r = eval_bridged_Graph(data, verbose=False)
+    assert abs(float(r) - r_ref) < 1e-6
+    for max_pairs in (1 << 26, 500):                          # one block / many blocks of start nodes
+        h1, h2 = eval_homophily(data, verbose=False, max_pairs=max_pairs)
+        assert abs(h1 - h1_ref) < 1e-6 and abs(h2 - h2_ref) < 1e-6
+
+
+def test_homophily_diagnostics_on_the_office_graph_match_the_reference(diag_golden, office_build):
+    from bridged_gnn_b200.data import Data
+    from bridged_gnn_b200.utils import eval_bridged_Graph, eval_homophily
+    g = office_build
+    data = Data(x=T(g["x"]).cuda(), edge_index=T(g["edge_index"]).cuda(), y=T(g["y"]).cuda(), test_mask=T(g["test_mask"]).cuda())
+    assert abs(float(eval_bridged_Graph(data, verbose=False)) - float(diag_golden["office.local_ratio"])) < 1e-6
+    h1, h2 = eval_homophily(data, verbose=False)
+    assert abs(h1 - float(diag_golden["office.h1"])) < 1e-6 and abs(h2 - float(diag_golden["office.h2"])) < 1e-6
+
+
 # ------------------------------------------------------------------ golden: reference layers on the office bridged graph
 def test_adapted_conv_module_matches_reference(office_mp, office_build):
     from bridged_gnn_b200.models import AdaptedConv

@@ -187,3 +187,18 @@ def test_sage_gcn_encoder(office_mp, office_build):
         assert torch.equal(mo.gcn_net(x, ei, sub_state(m, "gcn.sd.")), T(m["gcn.logp"]))
         W = {"e." + k: v for k, v in sub_state(m, "enc.sd.").items()}
         assert torch.equal(bo.graph_encoder(x, ei, W, "e"), T(m["enc.z"]))
+
+
+def test_homophily_diagnostics_match_reference(diag_golden, office_build):
+    """utils.py:101-131 run by the reference's own code (tests/golden/make_golden.py::diagnostics): the dense
+    restatements reproduce its three numbers on the shipped office bridged graph and on a seeded random graph."""
+    d, g = diag_golden, office_build
+    cases = {"office": (T(g["edge_index"]), T(g["y"]), T(g["test_mask"])),
+             "rand": (T(d["rand.edge_index"]), T(d["rand.y"]), T(d["rand.test_mask"]))}
+    for tag, (ei, y, tm) in cases.items():
+        n = y.shape[0]
+        ratio, _ = mo.eval_bridged_graph(ei, y, tm, n)
+        h1, h2 = mo.eval_homophily(ei, y, n)
+        assert abs(ratio - float(d[tag + ".local_ratio"])) < 1e-6, tag
+        assert abs(h1 - float(d[tag + ".h1"])) < 1e-6 and abs(h2 - float(d[tag + ".h2"])) < 1e-6, tag
+

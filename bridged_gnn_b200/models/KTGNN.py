@@ -142,21 +142,26 @@ class AdaptedConv(nn.Module):
         valid = part.local_rows(torch.ones(part.n, dtype=x.dtype, device=x.device))
         n_s = central_mask[: part.n].sum().clamp(min=1).to(x.dtype)
         n_t = (part.n - central_mask[: part.n].sum()).clamp(min=1).to(x.dtype)
-        rows = torch.stack((c_loc / n_s, (valid - c_loc) / n_t), 0)           # [2, n_loc]
-        means = bdist.all_reduce_sum_autograd(rows @ x, part.group)
+        is_src_loc = part.local_rows(self._dst_is_src(central_mask)[: part.n])
+        if x.is_cuda and x.dtype == torch.float32 and ops.domain_colsum_supported(d):
+            # padding rows of x are zero, so it does not matter which domain they are counted in
+            local = ops.domain_means(x, is_src_loc, torch.stack((1.0 / n_s, 1.0 / n_t)))
+        else:
+            local = torch.stack((c_loc / n_s, (valid - c_loc) / n_t), 0) @ x   # [2, n_loc] x [n_loc, d]
+        means = bdist.all_reduce_sum_autograd(local, part.group)
         delta = means[0:1] - means[1:2]
         w_s, w_t, b_s, b_t, a_t2s, a_s2t, cp = self._padded_params()
         w_cat = torch.cat((w_s, w_t, self.a_g_s2t.weight[:, :d], self.a_g_t2s.weight[:, :d]), 0)
-        if b_s is not None:
-            p = torch.addmm(torch.cat((b_s, b_t, b_s.new_zeros(2))), x, w_cat.t())
-        else:
-            p = x @ w_cat.t()
-        p_s, p_t, p_g = p.split((cp, cp, 2), dim=1)
         k_g = torch.stack(((self.a_g_s2t.weight[:, d:] * delta).sum(), (self.a_g_t2s.weight[:, d:] * delta).sum()))
-        gates = torch.tanh(p_g + k_g)
         wd = delta @ torch.cat((w_s, w_t), 0).t()
-        h_s = torch.addcmul(p_s, (gates[:, 1] * (valid - c_loc)).unsqueeze(1), wd[:, :cp])
-        h_t = torch.addcmul(p_t, (gates[:, 0] * c_loc).unsqueeze(1), wd[:, cp:], value=-1.0)
+        # node-wise transform of the local rows with the same fused kernels as the single-GPU path (padding rows
+        # count as target-domain rows there; nothing reads them and their gradients are zero)
+        b_cat = None if b_s is None else torch.cat((b_s, b_t, b_s.new_zeros(2)))
+        if x.is_cuda and x.dtype == torch.float32 and ops.adapted_skinny_supported(cp, d):
+            h_s, h_t = ops.adapted_skinny(x, w_cat, b_cat, wd, k_g, is_src_loc)
+        else:
+            b2 = None if b_s is None else torch.cat((b_s, b_t))
+            h_s, h_t = ops.adapted_transform(x @ w_cat.t(), wd, k_g, is_src_loc, b2)
         H_s = bdist.all_gather_rows_autograd(h_s, part.group)                  # [n_pad, cp]
         H_t = bdist.all_gather_rows_autograd(h_t, part.group)
         graph = ops.cached_graph(edge_index, part.n_pad)

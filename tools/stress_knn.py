@@ -18,6 +18,8 @@ with torch.no_grad():
     cases["fb"] = (head.cosine_operand(z_tar), head.cosine_operand(z_src), 50)
 cases["rnd"] = (torch.randn(700, 128, generator=gen).cuda(), torch.randn(9000, 128, generator=gen).cuda(), 20)
 cases["small"] = (torch.randn(33, 17, generator=gen).cuda(), torch.randn(300, 17, generator=gen).cuda(), 60)
+# large enough for the threshold-seeding sweep over a db sample (knn_seed_rows > 0)
+cases["seeded"] = (torch.randn(400, 128, generator=gen).cuda(), torch.randn(120000, 128, generator=gen).cuda(), 20)
 ref = {}
 bad = 0
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 40

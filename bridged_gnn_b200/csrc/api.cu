@@ -334,6 +334,38 @@ int bgnn_adapted_transform_bwd_f32(const float* gHs, const float* gHt, const flo
                                       (cudaStream_t)stream);
 }
 
+int bgnn_gatv2_heads_supported(int heads, int c) { return gatv2_heads_supported(heads, c) ? 1 : 0; }
+
+int bgnn_gatv2_heads_fwd_f32(const int32_t* rowptr, const int32_t* col, const uint8_t* dst_is_src, const float* Hs,
+                             const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n, int heads,
+                             int c, float* out, float* row_max, float* row_sum, void* stream) {
+  if (n < 0 || c <= 0 || heads <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!rowptr || !col || !dst_is_src || !Hs || !Ht || !af_t2s || !af_s2t || !out)) return BGNN_ERR_INVALID_ARG;
+  return launch_gatv2_heads_fwd(rowptr, col, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, heads, c, out, row_max, row_sum,
+                                (cudaStream_t)stream);
+}
+
+size_t bgnn_gatv2_heads_bwd_workspace_bytes(int64_t n, int64_t e, int heads, int c) {
+  return (n < 0 || e < 0 || c <= 0 || heads <= 0) ? 0 : gatv2_heads_bwd_workspace_bytes(n, e, heads, c);
+}
+
+int bgnn_gatv2_heads_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
+                             const int32_t* csr_to_csc, int64_t e, const uint8_t* dst_is_src, const float* Hs,
+                             const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n, int heads,
+                             int c, const float* out, const float* row_max, const float* row_sum, const float* gout,
+                             float* gHs, float* gHt, float* g_af_t2s, float* g_af_s2t, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (n < 0 || e < 0 || c <= 0 || heads <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!rowptr || !col || !t_rowptr || !t_col || !csr_to_csc || !dst_is_src || !Hs || !Ht || !af_t2s ||
+                !af_s2t || !out || !row_max || !row_sum || !gout || !gHs || !gHt || !g_af_t2s || !g_af_s2t))
+    return BGNN_ERR_INVALID_ARG;
+  if (!gatv2_heads_supported(heads, c)) return BGNN_ERR_UNSUPPORTED;
+  if (n > 0 && (!workspace || workspace_bytes < gatv2_heads_bwd_workspace_bytes(n, e, heads, c))) return BGNN_ERR_WORKSPACE;
+  return launch_gatv2_heads_bwd(rowptr, col, t_rowptr, t_col, csr_to_csc, e, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n,
+                                heads, c, out, row_max, row_sum, gout, gHs, gHt, g_af_t2s, g_af_s2t, workspace,
+                                workspace_bytes, (cudaStream_t)stream);
+}
+
 int bgnn_adapted_skinny_supported(int c, int d) { return adapted_skinny_supported(c, d) ? 1 : 0; }
 
 int bgnn_adapted_skinny_fwd_f32(const float* x, const uint8_t* is_src, const float* wcat, const float* bias,

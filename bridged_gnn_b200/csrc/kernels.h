@@ -88,6 +88,18 @@ int launch_adapted_transform_bwd(const float* gHs, const float* gHt, const float
                                  const float* wd, long long n, int c, float* gP, float* g_wd_kg, void* ws, size_t ws_bytes,
                                  cudaStream_t stream);
 
+// gatv2_heads.cu: 2-3 narrow aggregations over the same graph in one pass
+bool gatv2_heads_supported(int heads, int c);
+int launch_gatv2_heads_fwd(const int* rowptr, const int* col, const uint8_t* dst_is_src, const float* Hs, const float* Ht,
+                           const float* af_t2s, const float* af_s2t, float slope, long long n, int heads, int c,
+                           float* out, float* row_max, float* row_sum, cudaStream_t stream);
+size_t gatv2_heads_bwd_workspace_bytes(long long n, long long e, int heads, int c);
+int launch_gatv2_heads_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csr_to_csc,
+                           long long e, const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
+                           const float* af_s2t, float slope, long long n, int heads, int c, const float* out,
+                           const float* row_max, const float* row_sum, const float* gout, float* gHs, float* gHt,
+                           float* g_af_t2s, float* g_af_s2t, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 // adapted_skinny.cu
 bool adapted_skinny_supported(int c, int d);
 int launch_adapted_skinny_fwd(const float* x, const uint8_t* is_src, const float* wcat, const float* bias, const float* wd,

@@ -93,8 +93,26 @@ class AdaptedConv(nn.Module):
             return self._forward_partitioned(x, edge_index, central_mask, part)
         x_src, x_r = (x, x) if torch.is_tensor(x) else x
         c = central_mask
-        n, d = x_src.shape
+        h_s, h_t, a_t2s, a_s2t, cp = self.node_part(x_src, c)
+        # attention scores, softmax over destinations, weighted aggregation (:292-305) -- one kernel
+        graph = ops.cached_graph(edge_index, x_src.shape[0])
+        out = ops.gat_aggregate(h_s, h_t, a_t2s, a_s2t, graph, self._dst_is_src(c), self.negative_slope)
+        return self._finish(out, cp, x_r)
+
+    def _finish(self, out, cp, x_r):
         co = self.out_channels
+        if cp != co:
+            out = out[:, :co]
+        if self.root_weight and x_r is not None:
+            out = out + self.lin_r(x_r)
+        if self.normalize:
+            out = F.normalize(out, p=2.0, dim=-1)
+        return out
+
+    def node_part(self, x_src, c):
+        """The node-wise half of the conv (models/KTGNN.py:275-284): returns (lin_s(x_t2s), lin_t(x_s2t), a_f_t2s,
+        a_f_s2t, padded width) -- everything the edge part needs."""
+        n, d = x_src.shape
         # g + f (models/KTGNN.py:275-284) restructured so that x is read by ONE dense contraction and no
         # [N, 2D] / [N, D] intermediate is materialised.  With Delta = mean_src(x) - mean_tar(x):
         #   gate_s2t = tanh(a_g_s2t . [x, Delta]),  gate_t2s = tanh(a_g_t2s . [x, Delta])
@@ -119,16 +137,7 @@ class AdaptedConv(nn.Module):
             p = x_src @ w_cat.t()                                    # [N, 2*cp + 2]
             b2 = None if b_s is None else torch.cat((b_s, b_t))
             h_s, h_t = ops.adapted_transform(p, wd, k_g, self._dst_is_src(c), b2)   # biases, gates, rank-1 corrections
-        # attention scores, softmax over destinations, weighted aggregation (:292-305) -- one kernel
-        graph = ops.cached_graph(edge_index, x_src.shape[0])
-        out = ops.gat_aggregate(h_s, h_t, a_t2s, a_s2t, graph, self._dst_is_src(c), self.negative_slope)
-        if cp != co:
-            out = out[:, :co]
-        if self.root_weight and x_r is not None:
-            out = out + self.lin_r(x_r)
-        if self.normalize:
-            out = F.normalize(out, p=2.0, dim=-1)
-        return out
+        return h_s, h_t, a_t2s, a_s2t, cp
 
     def _forward_partitioned(self, x, edge_index, central_mask, part):
         """Destination-partitioned forward: domain means by all-reduce, node-wise transforms on
@@ -170,6 +179,29 @@ class AdaptedConv(nn.Module):
 
     def __repr__(self):
         return "{}({}, {})".format(self.__class__.__name__, self.in_channels, self.out_channels)
+
+
+def adapted_convs_shared_graph(convs, xs, edge_index, edge_index1, edge_index2, central_mask, part=None):
+    """[conv(x, ...) for conv, x in zip(convs, xs)] for AdaptedConvs over the SAME graph.  Narrow convs of equal
+    width (the classifier heads, models/KTGNN.py:432-434) share one aggregation pass: their node-wise parts run
+    one by one, the (lin_s, lin_t) outputs are laid side by side and a single multi-head kernel walks the edges."""
+    c = central_mask
+    widths = {conv.out_channels for conv in convs}
+    ok = (part is None and len(widths) == 1 and len(convs) in (2, 3) and all(torch.is_tensor(x) and x.is_cuda for x in xs)
+          and not any(conv.root_weight or conv.normalize for conv in convs)
+          and len({conv.negative_slope for conv in convs}) == 1)
+    if ok:
+        parts = [conv.node_part(x, c) for conv, x in zip(convs, xs)]
+        cp = parts[0][4]
+        ok = all(p[4] == cp for p in parts) and ops.gat_heads_supported(len(convs), cp)
+    if not ok:
+        return [conv(x, edge_index, edge_index1, edge_index2, c, part=part) for conv, x in zip(convs, xs)]
+    graph = ops.cached_graph(edge_index, xs[0].shape[0])
+    out = ops.gat_aggregate_heads(torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts], 1),
+                                  torch.cat([p[2].reshape(-1) for p in parts]), torch.cat([p[3].reshape(-1) for p in parts]),
+                                  graph, convs[0]._dst_is_src(c), convs[0].negative_slope, len(convs))
+    co = convs[0].out_channels
+    return [out[:, h * cp: h * cp + co] for h in range(len(convs))]
 
 
 def graph_partition(edge_index, central_mask, add_self_loop=True):
@@ -248,9 +280,8 @@ class KTGNN_no_complement(_KTGNNBase):
             ei1, ei2, ei = self._edges(data)
         c = data.central_mask
         x = self._hidden(data.x, ei, ei1, ei2, c, len(self.convs), part)
-        logits_base = self.clf_base(x, ei, ei1, ei2, c, part=part)
-        logits_trans = self.clf_target(self.clf_transformer(x), ei, ei1, ei2, c, part=part)
-        logits_target = self.clf_target(x, ei, ei1, ei2, c, part=part)
+        logits_base, logits_trans, logits_target = adapted_convs_shared_graph(
+            (self.clf_base, self.clf_target, self.clf_target), (x, self.clf_transformer(x), x), ei, ei1, ei2, c, part)
         return F.log_softmax(logits_base, 1), F.log_softmax(logits_target, 1), F.log_softmax(logits_trans, 1), None
 
 

@@ -303,6 +303,63 @@ def gat_aggregate(Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope=0.1):
     return _GatAggFn.apply(Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope)
 
 
+class _GatHeadsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope, heads):
+        lib = _lib.load()
+        f32 = torch.float32
+        Hs, Ht = Hs.to(f32).contiguous(), Ht.to(f32).contiguous()
+        a1, a2 = af_t2s.to(f32).contiguous().view(-1), af_s2t.to(f32).contiguous().view(-1)
+        n, f = Hs.shape
+        c = f // heads
+        dev = Hs.device
+        out = torch.empty((n, f), dtype=f32, device=dev)
+        row_max = torch.empty((n, heads), dtype=f32, device=dev)
+        row_sum = torch.empty((n, heads), dtype=f32, device=dev)
+        with _lib.call("bgnn_gatv2_heads_fwd_f32", "bgnn_gatv2_heads_fwd_f32[%dx%d]" % (heads, c)):
+            _lib.check(lib.bgnn_gatv2_heads_fwd_f32(_lib.ptr(graph.rowptr), _lib.ptr(graph.col),
+                                                    _lib.ptr(dst_is_src, torch.uint8), _lib.ptr(Hs), _lib.ptr(Ht),
+                                                    _lib.ptr(a1), _lib.ptr(a2), float(slope), n, heads, c, _lib.ptr(out),
+                                                    _lib.ptr(row_max), _lib.ptr(row_sum), _lib.stream(dev)))
+        ctx.save_for_backward(Hs, Ht, a1, a2, out, row_max, row_sum)
+        ctx.graph, ctx.dst_is_src, ctx.slope, ctx.heads = graph, dst_is_src, float(slope), heads
+        ctx.a_shapes = (af_t2s.shape, af_s2t.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        Hs, Ht, a1, a2, out, row_max, row_sum = ctx.saved_tensors
+        g, heads = ctx.graph, ctx.heads
+        t_rowptr, t_col, _ = g.t
+        n, f = Hs.shape
+        c = f // heads
+        dev = Hs.device
+        gout = gout.to(torch.float32).contiguous()
+        gHs, gHt = torch.empty_like(Hs), torch.empty_like(Ht)
+        ga1, ga2 = torch.empty_like(a1), torch.empty_like(a2)
+        ws = _lib.workspace(lib.bgnn_gatv2_heads_bwd_workspace_bytes(n, g.e, heads, c), dev)
+        with _lib.call("bgnn_gatv2_heads_bwd_f32", "bgnn_gatv2_heads_bwd_f32[%dx%d]" % (heads, c)):
+            _lib.check(lib.bgnn_gatv2_heads_bwd_f32(_lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(t_rowptr), _lib.ptr(t_col),
+                                                    _lib.ptr(g.csr_to_csc, torch.int32), g.e, _lib.ptr(ctx.dst_is_src),
+                                                    _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(a1), _lib.ptr(a2), ctx.slope, n,
+                                                    heads, c, _lib.ptr(out), _lib.ptr(row_max), _lib.ptr(row_sum),
+                                                    _lib.ptr(gout), _lib.ptr(gHs), _lib.ptr(gHt), _lib.ptr(ga1),
+                                                    _lib.ptr(ga2), _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+        return gHs, gHt, ga1.view(ctx.a_shapes[0]), ga2.view(ctx.a_shapes[1]), None, None, None, None
+
+
+def gat_heads_supported(heads, c):
+    return bool(_lib.load().bgnn_gatv2_heads_supported(int(heads), int(c)))
+
+
+def gat_aggregate_heads(Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope=0.1, heads=3):
+    """``heads`` narrow AdaptedConv aggregations over the same graph in one pass (KT-GNN's classifier convs,
+    models/KTGNN.py:432-434).  Hs, Ht [n, heads*c] with head h in columns h*c .. h*c+c-1, af_* [heads*c]; per head
+    identical to ``gat_aggregate`` (scores, softmax and sums never mix heads).  heads in {2, 3}, c <= 4."""
+    return _GatHeadsFn.apply(Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope, heads)
+
+
 # ----------------------------------------------------------------------------------- AdaptedConv node-wise epilogue
 class _AdaptedTransformFn(torch.autograd.Function):
     @staticmethod

@@ -131,6 +131,24 @@ int bgnn_gatv2_bwd_ord_f32(const int32_t* rowptr, const int32_t* col, const int3
                            const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
                            float* g_af_s2t, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Two or three NARROW aggregations (heads) over the same graph in one pass -- KT-GNN's classifier convs
+ * clf_base(x), clf_target(clf_transformer(x)), clf_target(x) (models/KTGNN.py:432-434).  Hs, Ht, out, gout, gHs,
+ * gHt are [n, heads*c] with head h in columns h*c .. h*c+c-1; af_*, g_af_* are [heads*c]; row_max / row_sum are
+ * [n, heads].  Per head the semantics are exactly bgnn_gatv2_fwd_f32 / _bwd_f32 (scores, softmax and sums never mix
+ * heads); an edge costs one index load, one gather and one 32-byte record for all heads.  heads in {2, 3}, c <= 4
+ * (bgnn_gatv2_heads_supported). */
+int bgnn_gatv2_heads_supported(int heads, int c);
+int bgnn_gatv2_heads_fwd_f32(const int32_t* rowptr, const int32_t* col, const uint8_t* dst_is_src, const float* Hs,
+                             const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n, int heads,
+                             int c, float* out, float* row_max, float* row_sum, void* stream);
+size_t bgnn_gatv2_heads_bwd_workspace_bytes(int64_t n, int64_t e, int heads, int c);
+int bgnn_gatv2_heads_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
+                             const int32_t* csr_to_csc, int64_t e, const uint8_t* dst_is_src, const float* Hs,
+                             const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n, int heads,
+                             int c, const float* out, const float* row_max, const float* row_sum, const float* gout,
+                             float* gHs, float* gHt, float* g_af_t2s, float* g_af_s2t, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* Node-wise epilogue of AdaptedConv's domain-shift transform (models/KTGNN.py:275-284).  The host computes
  * P [n, 2c+2] = x [W_s; W_t; a_g_s2t[:D]; a_g_t2s[:D]]^T, wd [2c] = [W_s Delta; W_t Delta] and
  * kg [2] = [a_g_s2t[D:].Delta, a_g_t2s[D:].Delta]; bias [2c] = (b_s, b_t) or NULL.  This call writes

@@ -132,6 +132,78 @@ def test_gat_aggregate_forward_backward_random(n, c, e):
         assert relclose(got.grad, ref.grad, 2e-5), name
 
 
+@pytest.mark.parametrize("heads,c,n,e", [(3, 2, 1000, 12000), (2, 1, 300, 2000), (3, 4, 700, 9000), (2, 3, 64, 900), (3, 1, 2000, 30000)])
+def test_gat_aggregate_heads_equals_one_aggregation_per_head(heads, c, n, e):
+    """Several narrow aggregations in one pass: per head identical to the single-head op (forward and gradients)."""
+    ops = _ops()
+    assert ops.gat_heads_supported(heads, c) and not ops.gat_heads_supported(4, c) and not ops.gat_heads_supported(heads, 5)
+    g = torch.Generator().manual_seed(31 + heads * 7 + c)
+    ei = _rand_graph(n, e, 40 + c)
+    ei = torch.cat((ei, torch.stack((torch.randint(0, n, (400,), generator=g), torch.zeros(400, dtype=torch.long)))), 1)   # a hub row
+    cm = torch.zeros(n, dtype=torch.bool)
+    cm[: (2 * n) // 3] = True
+    _, _, eall = mo.graph_partition(ei, cm)
+    graph = ops.CSRGraph(eall.cuda(), n)
+    cm8 = cm.to(torch.uint8).cuda()
+    f = heads * c
+    vals = [torch.randn(n, f, generator=g), torch.randn(n, f, generator=g), torch.randn(f, generator=g) * 0.5,
+            torch.randn(f, generator=g) * 0.5]
+    gout = torch.randn(n, f, generator=g).cuda()
+    one = [t.clone().cuda().requires_grad_(True) for t in vals]
+    ys = [ops.gat_aggregate(one[0][:, h * c:(h + 1) * c].contiguous(), one[1][:, h * c:(h + 1) * c].contiguous(),
+                            one[2][h * c:(h + 1) * c], one[3][h * c:(h + 1) * c], graph, cm8, 0.1) for h in range(heads)]
+    y_ref = torch.cat(ys, 1)
+    (y_ref * gout).sum().backward()
+    mh = [t.clone().cuda().requires_grad_(True) for t in vals]
+    y = ops.gat_aggregate_heads(mh[0], mh[1], mh[2], mh[3], graph, cm8, 0.1, heads)
+    assert relclose(y, y_ref.detach().cpu(), 2e-6)
+    (y * gout).sum().backward()
+    for got, ref, name in zip(mh, one, ("Hs", "Ht", "a_t2s", "a_s2t")):
+        assert relclose(got.grad, ref.grad.cpu(), 1e-5), name
+
+
+def test_ktgnn_classifier_heads_batched_equals_unbatched(monkeypatch):
+    """KTGNN_no_complement with a few classes runs its three classifier convs as one multi-head pass; logits and
+    gradients equal the conv-by-conv path."""
+    ops = _ops()
+    from bridged_gnn_b200.data import Data, to_undirected
+    from bridged_gnn_b200.models import KTGNN_no_complement
+    g = torch.Generator().manual_seed(5)
+    n, d, classes = 1500, 32, 3
+    ei = to_undirected(_rand_graph(n, 14000, 8).cuda(), n)
+    cm = torch.zeros(n, dtype=torch.bool)
+    cm[:1000] = True
+    x = torch.randn(n, d, generator=g)
+    y = torch.randint(0, classes, (n,), generator=g).cuda()
+    data = Data(x=x.cuda(), edge_index=ei, central_mask=cm.cuda())
+    torch.manual_seed(0)
+    model = KTGNN_no_complement(d, classes, 2, 16, root_weight=False, use_bn=True, dim_share=d, dropout=0.0).cuda().train()
+
+    def run():
+        model.zero_grad(set_to_none=True)
+        lb, lt, ltt, _ = model(data)
+        loss = sum(torch.nn.functional.nll_loss(t, y) for t in (lb, lt, ltt))
+        loss.backward()
+        return [t.detach().clone() for t in (lb, lt, ltt)], [p.grad.detach().clone() for p in model.parameters()]
+
+    calls = {"n": 0}
+    real = ops.gat_aggregate_heads
+
+    def counted(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+    monkeypatch.setattr(ops, "gat_aggregate_heads", counted)
+    out_b, grads_b = run()
+    assert calls["n"] == 1                                    # the batched path was taken
+    monkeypatch.setattr(ops, "gat_heads_supported", lambda h, c: False)
+    out_u, grads_u = run()
+    assert calls["n"] == 1
+    for a, b in zip(out_b, out_u):
+        assert relclose(a, b.cpu(), 2e-6)
+    for a, b in zip(grads_b, grads_u):
+        assert relclose(a, b.cpu(), 2e-5)
+
+
 def test_rows_by_degree_is_a_stable_descending_permutation():
     ops = _ops()
     for n, e in ((1, 0), (7, 30), (1000, 20000), (4096, 100)):

@@ -109,9 +109,16 @@ class AdaptedConv(nn.Module):
             out = F.normalize(out, p=2.0, dim=-1)
         return out
 
-    def node_part(self, x_src, c):
+    def domain_means(self, x_src, c):
+        """[2, D]: mean of the source-domain rows and of the target-domain rows of x (models/KTGNN.py:275-276)."""
+        if x_src.is_cuda and x_src.dtype == torch.float32 and ops.domain_colsum_supported(x_src.shape[1]):
+            return ops.domain_means(x_src, self._dst_is_src(c), self._domain_counts(c))    # one pass over x
+        return self._domain_rows(c, x_src.dtype) @ x_src             # [2, N]: 1/Ns on source rows, 1/Nt on target rows
+
+    def node_part(self, x_src, c, means=None):
         """The node-wise half of the conv (models/KTGNN.py:275-284): returns (lin_s(x_t2s), lin_t(x_s2t), a_f_t2s,
-        a_f_s2t, padded width) -- everything the edge part needs."""
+        a_f_s2t, padded width) -- everything the edge part needs.  ``means`` ([2, D] domain means of x_src) may be
+        passed in when another conv over the same input has computed them already."""
         n, d = x_src.shape
         # g + f (models/KTGNN.py:275-284) restructured so that x is read by ONE dense contraction and no
         # [N, 2D] / [N, D] intermediate is materialised.  With Delta = mean_src(x) - mean_tar(x):
@@ -119,11 +126,8 @@ class AdaptedConv(nn.Module):
         #   h_t = lin_t(x - gate_s2t * Delta * c)      = x W_t^T + b_t - (gate_s2t * c)     (x) (W_t Delta)
         #   h_s = lin_s(x + gate_t2s * Delta * (1-c))  = x W_s^T + b_s + (gate_t2s * (1-c)) (x) (W_s Delta)
         on_gpu = x_src.is_cuda and x_src.dtype == torch.float32
-        if on_gpu and ops.domain_colsum_supported(d):
-            means = ops.domain_means(x_src, self._dst_is_src(c), self._domain_counts(c))   # [2, D], one pass over x
-        else:
-            cf = self._domain_rows(c, x_src.dtype)                   # [2, N]: 1/Ns on source rows, 1/Nt on target rows
-            means = cf @ x_src
+        if means is None:
+            means = self.domain_means(x_src, c)
         delta = means[0:1] - means[1:2]                              # [1, D]
         w_s, w_t, b_s, b_t, a_t2s, a_s2t, cp = self._padded_params()
         w_cat = torch.cat((w_s, w_t, self.a_g_s2t.weight[:, :d], self.a_g_t2s.weight[:, :d]), 0)
@@ -191,7 +195,12 @@ def adapted_convs_shared_graph(convs, xs, edge_index, edge_index1, edge_index2, 
           and not any(conv.root_weight or conv.normalize for conv in convs)
           and len({conv.negative_slope for conv in convs}) == 1)
     if ok:
-        parts = [conv.node_part(x, c) for conv, x in zip(convs, xs)]
+        shared = {}                                  # domain means per distinct input (two heads read the same x)
+        parts = []
+        for conv, x in zip(convs, xs):
+            if id(x) not in shared:
+                shared[id(x)] = conv.domain_means(x, c)
+            parts.append(conv.node_part(x, c, shared[id(x)]))
         cp = parts[0][4]
         ok = all(p[4] == cp for p in parts) and ops.gat_heads_supported(len(convs), cp)
     if not ok:

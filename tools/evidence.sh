@@ -10,7 +10,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_bench_reference.
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${T}_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" --csv --log-file $O/${T}_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${T}_ncu_launches.log 2>&1
-ncu --set full --import-source on --clock-control none -k 'regex:gatv2_(fwd|bwd_dst|bwd_src)_kernel' -c 12 -o $O/${T}_prof_gat \
+ncu --set full --import-source on --clock-control none -k 'regex:gatv2_(heads_)?(fwd|bwd_dst|bwd_src)_kernel' -c 6 -o $O/${T}_prof_gat \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/${T}_ncu_gat.log 2>&1
 python tools/profile_knn.py f16 262144 786432 128 20 2 > $O/${T}_knn_plain.log 2>&1 || exit 1
 ncu --set full --import-source on --clock-control none -k regex:knn_cosine_f16_kernel -s 3 -c 1 -o $O/${T}_prof_knn \

@@ -437,20 +437,25 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
               for (int g = 0; g < 4; ++g)
                 if (gm[i][g] > es.thr) {
                   // the usual case inline: exactly one column of the group beats the threshold -- it is the
-                  // group maximum, only its position is missing -- and the FIFO has room
+                  // group maximum, only its position is missing -- and the FIFO has room.  The copies below are
+                  // made opaque to the compiler INSIDE the branch: without that it if-converts the select chains
+                  // of all 16 groups of a tile into every hit (290 instructions per hit at one active lane,
+                  // profiles/r01p_knn_f16_ncu.txt)
+                  float v[8];
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) { v[c] = rr[i][g * 8 + c]; asm volatile("" : "+f"(v[c])); }
                   int first = 8, last = -1;
 #pragma unroll
-                  for (int c = 7; c >= 0; --c) first = (rr[i][g * 8 + c] > es.thr) ? c : first;
+                  for (int c = 7; c >= 0; --c) first = (v[c] > es.thr) ? c : first;
 #pragma unroll
-                  for (int c = 0; c < 8; ++c) last = (rr[i][g * 8 + c] > es.thr) ? c : last;
+                  for (int c = 0; c < 8; ++c) last = (v[c] > es.thr) ? c : last;
                   const int jb = db0 + (half + 2 * i) * 32 + g * 8;
                   if (first == last && es.fcnt < F16_FCAP) {
                     sts_f32(ea.fv + es.fcnt * (F16_BM * 4), gm[i][g]);
                     sts_s32(ea.fi + es.fcnt * (F16_BM * 4), jb + first);
                     ++es.fcnt;
                   } else {
-                    es = epi_scan8(es, ea, jb, rr[i][g * 8 + 0], rr[i][g * 8 + 1], rr[i][g * 8 + 2], rr[i][g * 8 + 3],
-                                   rr[i][g * 8 + 4], rr[i][g * 8 + 5], rr[i][g * 8 + 6], rr[i][g * 8 + 7]);
+                    es = epi_scan8(es, ea, jb, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
                   }
                 }
           }

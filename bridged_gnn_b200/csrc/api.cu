@@ -326,11 +326,11 @@ int bgnn_adapted_transform_fwd_f32(const float* P, const uint8_t* is_src, const 
 size_t bgnn_adapted_transform_bwd_workspace_bytes(int c) { return c <= 0 ? 0 : adapted_transform_bwd_workspace_bytes(c); }
 
 int bgnn_adapted_transform_bwd_f32(const float* gHs, const float* gHt, const float* gates, const uint8_t* is_src,
-                                   const float* wd, int64_t n, int c, float* gP, float* g_wd_kg, void* workspace,
+                                   const float* wd, int64_t n, int c, int ldp, float* gP, float* g_wd_kg, void* workspace,
                                    size_t workspace_bytes, void* stream) {
-  if (n < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n < 0 || c <= 0 || ldp < 2 * c + 2) return BGNN_ERR_INVALID_ARG;
   if (n > 0 && (!gHs || !gHt || !gates || !is_src || !wd || !gP || !g_wd_kg || !workspace)) return BGNN_ERR_INVALID_ARG;
-  return launch_adapted_transform_bwd(gHs, gHt, gates, is_src, wd, n, c, gP, g_wd_kg, workspace, workspace_bytes,
+  return launch_adapted_transform_bwd(gHs, gHt, gates, is_src, wd, n, c, ldp, gP, g_wd_kg, workspace, workspace_bytes,
                                       (cudaStream_t)stream);
 }
 
@@ -396,6 +396,42 @@ int bgnn_domain_colsum_f32(const float* x, const uint8_t* is_src, int64_t n, int
                            size_t workspace_bytes, void* stream) {
   if (n < 0 || d <= 0 || !sums || !workspace || (n > 0 && (!x || !is_src))) return BGNN_ERR_INVALID_ARG;
   return launch_domain_colsum(x, is_src, n, d, sums, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bgnn_rowpanel_gemm_supported(int k, int ld_a, int no) { return rowpanel_gemm_supported(k, ld_a, no) ? 1 : 0; }
+
+int bgnn_rowpanel_gemm_f32(const float* A, int64_t n, int k, int ld_a, const float* b_hi, const float* b_lo,
+                           const float* bias, int no, float* Y, int ldy, void* stream) {
+  if (n < 0 || k <= 0 || no <= 0 || ld_a < k || ldy < no) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!A || !b_hi || !b_lo || !Y)) return BGNN_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo)) & 15)
+    return BGNN_ERR_INVALID_ARG;
+  return launch_rowpanel_gemm(A, n, k, ld_a, b_hi, b_lo, bias, no, Y, ldy, (cudaStream_t)stream);
+}
+
+int bgnn_adapted_wide_supported(int c, int d) { return adapted_wide_supported(c, d) ? 1 : 0; }
+
+int bgnn_adapted_wide_fwd_f32(const float* x, int64_t n, int d, const float* wcat_hi, const float* wcat_lo, int c,
+                              const uint8_t* is_src, const float* wd, const float* kg, const float* bias, float* Hs,
+                              float* Ht, float* gates, void* stream) {
+  if (n < 0 || c <= 0 || d <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!x || !wcat_hi || !wcat_lo || !is_src || !wd || !kg || !Hs || !Ht || !gates)) return BGNN_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wcat_hi) | reinterpret_cast<uintptr_t>(wcat_lo) |
+       reinterpret_cast<uintptr_t>(Hs) | reinterpret_cast<uintptr_t>(Ht)) & 15)
+    return BGNN_ERR_INVALID_ARG;
+  return launch_adapted_wide_fwd(x, n, d, wcat_hi, wcat_lo, c, is_src, wd, kg, bias, Hs, Ht, gates, (cudaStream_t)stream);
+}
+
+int bgnn_wgrad_gemm_supported(int d, int ld_x, int no, int ld_g) { return wgrad_gemm_supported(d, ld_x, no, ld_g) ? 1 : 0; }
+
+size_t bgnn_wgrad_gemm_workspace_bytes(int no) { return no <= 0 ? 0 : wgrad_gemm_workspace_bytes(no); }
+
+int bgnn_wgrad_gemm_f32(const float* G, int ld_g, int no, const float* X, int ld_x, int d, int64_t n, float* W, int ldw,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 0 || no <= 0 || d <= 0 || ld_g < no || ld_x < d || ldw < d || !W || !workspace) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!G || !X)) return BGNN_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(X)) & 15) return BGNN_ERR_INVALID_ARG;
+  return launch_wgrad_gemm(G, ld_g, no, X, ld_x, d, n, W, ldw, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

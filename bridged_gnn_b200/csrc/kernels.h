@@ -85,8 +85,8 @@ int launch_adapted_transform_fwd(const float* P, const uint8_t* is_src, const fl
                                  long long n, int c, float* Hs, float* Ht, float* gates, cudaStream_t stream);
 size_t adapted_transform_bwd_workspace_bytes(int c);
 int launch_adapted_transform_bwd(const float* gHs, const float* gHt, const float* gates, const uint8_t* is_src,
-                                 const float* wd, long long n, int c, float* gP, float* g_wd_kg, void* ws, size_t ws_bytes,
-                                 cudaStream_t stream);
+                                 const float* wd, long long n, int c, int ldp, float* gP, float* g_wd_kg, void* ws,
+                                 size_t ws_bytes, cudaStream_t stream);
 
 // gatv2_heads.cu: 2-3 narrow aggregations over the same graph in one pass
 bool gatv2_heads_supported(int heads, int c);
@@ -113,5 +113,20 @@ bool domain_colsum_supported(int d);
 size_t domain_colsum_workspace_bytes(int d);
 int launch_domain_colsum(const float* x, const uint8_t* is_src, long long n, int d, float* sums, void* ws, size_t ws_bytes,
                          cudaStream_t stream);
+
+// rowpanel_gemm_sm100.cu
+bool rowpanel_gemm_supported(int k, int ld_a, int no);
+int launch_rowpanel_gemm(const float* A, long long n, int k, int ld_a, const float* bhi, const float* blo, const float* bias,
+                         int no, float* Y, int ldy, cudaStream_t stream);
+bool adapted_wide_supported(int c, int d);
+int launch_adapted_wide_fwd(const float* x, long long n, int d, const float* wcat_hi, const float* wcat_lo, int c,
+                            const uint8_t* is_src, const float* wd, const float* kg, const float* bias, float* Hs, float* Ht,
+                            float* gates, cudaStream_t stream);
+
+// wgrad_gemm_sm100.cu
+bool wgrad_gemm_supported(int d, int ld_x, int no, int ld_g);
+size_t wgrad_gemm_workspace_bytes(int no);
+int launch_wgrad_gemm(const float* G, int ld_g, int no, const float* X, int ld_x, int d, long long n, float* W, int ldw,
+                      void* ws, size_t ws_bytes, cudaStream_t stream);
 
 }  // namespace bgnn

@@ -1,0 +1,257 @@
+// Weight-gradient contraction on the 5th-gen tensor cores with fp32-grade accuracy (3 x TF32), sm_100a:
+//     W[j, f] = sum_i G[i, j] X[i, f]          i over ~1e6 node rows, j < no <= 256, f < d <= 128
+// = g_w_cat = dP^T x of AdaptedConv's node-wise part (models/KTGNN.py:277-284) and the weight gradient of the
+// Linear layers of the classifier transformer (models/KTGNN.py:363).  cuBLAS
+// runs these as fp32 SIMT "NT" GEMMs with a tiny output and a 1e6-long reduction (1.2 ms + 2 x 0.6 ms of the
+// KT-GNN training step on one B200); here both operands cross HBM once and the reduction runs on tcgen05.
+//
+// The reduction index is the ROW index of both operands, so both are MN-major in shared memory.  For 32-bit
+// operands tcgen05 takes MN-major tiles only in the "128-byte swizzle with 32-byte atomicity" layout
+// (UMMA layout type 1, cute::UMMA::Layout_MN_SW128_32B_Atom: 4 rows x 128 B, 32-byte chunks XOR row mod 4) --
+// measured here: with the ordinary SWIZZLE_128B descriptor and a transposed tf32 operand the MMA completes and
+// writes NOTHING.  TMA has the matching mode (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): a box [32 columns x 32 rows]
+// is a column of eight such atoms, so LBO = 4096 B (next box = next 32 columns), SBO = 512 B (next 4 rows), and one
+// tf32 MMA (K = 8) eats two atoms = 1024 B.
+// Both streamed operands are split on chip (hi = tf32(a), lo = tf32(a - hi)) by four warps, element-wise and
+// therefore layout-agnostic;  D[f, j] (128 TMEM lanes x nop columns) += lo.hi + hi.lo + hi.hi.
+//
+// Persistent CTAs stride over the 32-row blocks and keep ONE accumulator for the whole kernel; each CTA then writes
+// its partial [128, nop] and a second kernel adds the partials in CTA order (deterministic) into W (transposed).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace bgnn {
+
+constexpr int WG_BK = 32;              // rows per stage
+constexpr int WG_BOX = 32 * WG_BK * 4; // one TMA box: 32 columns x 32 rows fp32 = 4 KB
+constexpr int WG_MBOX = 4;             // X boxes per stage = 128 features (UMMA M)
+constexpr int WG_THREADS = 320;
+constexpr int WG_SMEM_MAX = 232448;
+constexpr int WG_SMEM_FIXED = 1024 + 512;
+
+__host__ __device__ constexpr uint32_t wg_idesc_tf32_mn(int m, int n) {
+  // D fp32, A/B tf32, both MN-major (bits 15, 16)
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// MN-major fp32/tf32 operand, 128-byte swizzle with 32-byte atomicity: LBO = stride between 32-column atoms,
+// SBO = stride between 4-row groups
+__device__ __forceinline__ uint64_t wg_mn_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+  d |= (uint64_t)(WG_BOX >> 4) << 16;       // LBO: next 32-column atom column = next TMA box
+  d |= (uint64_t)(512 >> 4) << 32;          // SBO: next 4-row atom
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                   // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+__device__ __forceinline__ float wg_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+
+// stage layout: hi plane [G: nb boxes][X: 4 boxes] then the lo plane, same order.  TMA fills the first nb + mb boxes
+// of the hi plane with the raw data; X boxes mb..3 (features >= d) are zeroed once and never touched again.
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, long long nblocks,
+                  int mb, int nb, int stages, float* __restrict__ part) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int plane = (nb + WG_MBOX) * WG_BOX;
+  const int stage_bytes = 2 * plane;
+  const int nop = nb * 32;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* ready_bar = bars + stages;
+  uint64_t* empty_bar = bars + 2 * stages;
+  uint64_t* done_bar = bars + 3 * stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&ready_bar[s]), 4);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(done_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (mb < WG_MBOX) {        // zero the X boxes no TMA ever writes (both planes, every stage)
+    const int zero_f4 = (WG_MBOX - mb) * WG_BOX / 16;
+    for (int s = 0; s < stages; ++s)
+      for (int pl = 0; pl < 2; ++pl) {
+        float4* z = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + (size_t)pl * plane + (size_t)(nb + mb) * WG_BOX);
+        for (int i = threadIdx.x; i < zero_f4; i += WG_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g) : "memory");
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        mbar_expect_tx(fb, (uint32_t)((nb + mb) * WG_BOX));
+        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+        const int row0 = (int)(b * WG_BK);
+        for (int j = 0; j < nb; ++j) tma_load_2d(st + j * WG_BOX, &map_g, fb, j * 32, row0);
+        for (int j = 0; j < mb; ++j) tma_load_2d(st + (nb + j) * WG_BOX, &map_x, fb, j * 32, row0);
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = wg_idesc_tf32_mn(128, nop);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t acc = 0;
+      for (long long b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        mbar_wait(smem_u32(&ready_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t g_hi = wg_mn_desc(st), x_hi = wg_mn_desc(st + nb * WG_BOX);
+        const uint64_t g_lo = wg_mn_desc(st + plane), x_lo = wg_mn_desc(st + plane + nb * WG_BOX);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const uint64_t ad = (p == 0) ? x_lo : x_hi;      // A = X (M = features), B = G (N = output columns)
+          const uint64_t bd = (p == 1) ? g_lo : g_hi;
+#pragma unroll
+          for (int ks = 0; ks < WG_BK / 8; ++ks) {
+            tc_mma_tf32(tmem_base, ad + (uint64_t)(ks * (1024 >> 4)), bd + (uint64_t)(ks * (1024 >> 4)), idesc, acc);
+            acc = 1u;
+          }
+        }
+        tc_commit(smem_u32(&empty_bar[s]));
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+      tc_commit(smem_u32(done_bar));
+    }
+  } else if (warp < 6) {
+    // ===================== split raw -> (hi, lo) =====================
+    const int tid = threadIdx.x - 64;
+    const int n_f4 = (nb + mb) * WG_BOX / 16;
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long b = blockIdx.x; b < nblocks; b += gridDim.x) {
+      mbar_wait(smem_u32(&full_bar[s]), ph);
+      float4* a = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+      float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + plane);
+#pragma unroll 4
+      for (int i = tid; i < n_f4; i += 128) {
+        const float4 v = a[i];
+        float4 h, l;
+        h.x = wg_tf32(v.x); h.y = wg_tf32(v.y); h.z = wg_tf32(v.z); h.w = wg_tf32(v.w);
+        l.x = wg_tf32(v.x - h.x); l.y = wg_tf32(v.y - h.y); l.z = wg_tf32(v.z - h.z); l.w = wg_tf32(v.w - h.w);
+        a[i] = h;
+        lo[i] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ready_bar[s]));
+      if (++s == stages) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    // ===================== epilogue: the CTA's partial, thread <-> feature row =====================
+    const int quarter = warp & 3;
+    const int f = quarter * 32 + lane;
+    float* out = part + ((size_t)blockIdx.x * 128 + f) * nop;
+    if ((long long)blockIdx.x < nblocks) {
+      mbar_wait(smem_u32(done_bar), 0u);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      float r[32];
+      for (int c0 = 0; c0 < nop; c0 += 32) {
+        tc_ld32(taddr0 + (uint32_t)c0, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) reinterpret_cast<float4*>(out + c0)[k] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// W[j * ldw + f] = sum over CTAs (in order) of part[cta][f][j]
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int nop, int no, int d, float* __restrict__ W, int ldw) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // f * no + j: consecutive threads read consecutive j
+  if (idx >= d * no) return;
+  const int f = idx / no, j = idx - f * no;
+  float acc = 0.f;
+  for (int p = 0; p < nparts; ++p) acc += part[((size_t)p * 128 + f) * nop + j];
+  W[(size_t)j * ldw + f] = acc;
+}
+
+static int wg_make_map(CUtensorMap* m, const float* base, long long rows, int cols, int ld) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return BGNN_ERR_DRIVER;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)WG_BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? BGNN_OK : BGNN_ERR_DRIVER;
+}
+
+static int wg_stages(int nb) {
+  int st = (WG_SMEM_MAX - WG_SMEM_FIXED) / (2 * (nb + WG_MBOX) * WG_BOX);
+  return st > 6 ? 6 : st;
+}
+
+bool wgrad_gemm_supported(int d, int ld_x, int no, int ld_g) {
+  return d >= 1 && d <= 128 && no >= 1 && no <= 256 && ld_x % 4 == 0 && ld_g % 4 == 0 && wg_stages((no + 31) / 32) >= 2;
+}
+
+size_t wgrad_gemm_workspace_bytes(int no) { return (size_t)kNumSMs * 128 * ((no + 31) / 32 * 32) * sizeof(float) + 256; }
+
+int launch_wgrad_gemm(const float* G, int ld_g, int no, const float* X, int ld_x, int d, long long n, float* W, int ldw,
+                      void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (!wgrad_gemm_supported(d, ld_x, no, ld_g) || n >= (1ll << 31)) return BGNN_ERR_UNSUPPORTED;
+  if (ws_bytes < wgrad_gemm_workspace_bytes(no)) return BGNN_ERR_WORKSPACE;
+  const int nb = (no + 31) / 32, mb = (d + 31) / 32;
+  const int nop = nb * 32;
+  float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  const long long nblocks = (n + WG_BK - 1) / WG_BK;
+  const unsigned grid = (unsigned)(nblocks < kNumSMs ? (nblocks > 0 ? nblocks : 1) : kNumSMs);
+  if (n > 0) {
+    CUtensorMap mx, mg;
+    int rc;
+    if ((rc = wg_make_map(&mx, X, n, d, ld_x)) != BGNN_OK) return rc;
+    if ((rc = wg_make_map(&mg, G, n, no, ld_g)) != BGNN_OK) return rc;
+    const int stages = wg_stages(nb);
+    const size_t smem = WG_SMEM_FIXED + (size_t)stages * 2 * (nb + WG_MBOX) * WG_BOX;
+    BGNN_CUDA_TRY(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_gemm_kernel<<<grid, WG_THREADS, smem, stream>>>(mx, mg, nblocks, mb, nb, stages, part);
+    BGNN_LAUNCH_CHECK();
+  }
+  wgrad_reduce_kernel<<<(d * no + 255) / 256, 256, 0, stream>>>(part, n > 0 ? (int)grid : 0, nop, no, d, W, ldw);
+  BGNN_LAUNCH_CHECK();
+  return BGNN_OK;
+}
+
+}  // namespace bgnn

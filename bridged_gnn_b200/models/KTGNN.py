@@ -11,6 +11,17 @@ from .. import ops
 from ..data import add_self_loops, remove_self_loops
 
 
+class NodeLinear(nn.Linear):
+    """nn.Linear over the node-feature matrix (same parameters and state_dict keys); on the GPU in fp32 the forward,
+    input-gradient and weight-gradient GEMMs run on this library's 3 x TF32 tensor-core kernels instead of cuBLAS'
+    fp32 SIMT GEMMs (the Linear layers of clf_transformer, models/KTGNN.py:363)."""
+
+    def forward(self, x):
+        if ops.linear_supported(x, self.weight):
+            return ops.linear(x, self.weight, self.bias)
+        return F.linear(x, self.weight, self.bias)
+
+
 class AdaptedConv(nn.Module):
     """Domain-adaptive attention conv.  Parameters and their names match the reference
     (lin_s, lin_t, a_g_s2t, a_g_t2s, a_f_s2t, a_f_t2s[, lin_r]) so its state_dicts load unchanged."""
@@ -137,6 +148,11 @@ class AdaptedConv(nn.Module):
         if on_gpu and ops.adapted_skinny_supported(cp, d):
             # classifier heads (a few classes): contraction, gates and corrections in one pass over x
             h_s, h_t = ops.adapted_skinny(x_src, w_cat, b_cat, wd, k_g, self._dst_is_src(c))
+        elif on_gpu and ops.adapted_wide_supported(cp, d):
+            # hidden layers: the contraction on the tensor cores (3 x TF32) with the node-wise epilogue applied to
+            # the accumulator tile -- x is read once, P is never written
+            b2 = None if b_s is None else torch.cat((b_s, b_t))
+            h_s, h_t = ops.adapted_wide(x_src, w_cat, b2, wd, k_g, self._dst_is_src(c))
         else:
             p = x_src @ w_cat.t()                                    # [N, 2*cp + 2]
             b2 = None if b_s is None else torch.cat((b_s, b_t))
@@ -172,6 +188,9 @@ class AdaptedConv(nn.Module):
         b_cat = None if b_s is None else torch.cat((b_s, b_t, b_s.new_zeros(2)))
         if x.is_cuda and x.dtype == torch.float32 and ops.adapted_skinny_supported(cp, d):
             h_s, h_t = ops.adapted_skinny(x, w_cat, b_cat, wd, k_g, is_src_loc)
+        elif x.is_cuda and x.dtype == torch.float32 and ops.adapted_wide_supported(cp, d):
+            b2 = None if b_s is None else torch.cat((b_s, b_t))
+            h_s, h_t = ops.adapted_wide(x, w_cat, b2, wd, k_g, is_src_loc)
         else:
             b2 = None if b_s is None else torch.cat((b_s, b_t))
             h_s, h_t = ops.adapted_transform(x @ w_cat.t(), wd, k_g, is_src_loc, b2)
@@ -269,8 +288,8 @@ class KTGNN_no_complement(_KTGNNBase):
                     self.bns.append(nn.BatchNorm1d(hidden))
         self.clf_base = AdaptedConv(hidden, num_classes, root_weight=root_weight)
         self.clf_target = AdaptedConv(hidden, num_classes, root_weight=root_weight)
-        self.clf_transformer = nn.Sequential(nn.Linear(hidden, hidden), nn.BatchNorm1d(hidden), nn.ReLU(),
-                                             nn.Linear(hidden, hidden))
+        self.clf_transformer = nn.Sequential(NodeLinear(hidden, hidden), nn.BatchNorm1d(hidden), nn.ReLU(),
+                                             NodeLinear(hidden, hidden))
 
     def get_emb(self, data):
         ei1, ei2, ei = self._edges(data)

@@ -2,6 +2,8 @@
 aggregation (both differentiable).  Everything here runs hand-written sm_100a kernels on the current
 CUDA stream; nothing falls back to torch ops or the CPU.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -398,7 +400,7 @@ class _AdaptedTransformFn(torch.autograd.Function):
         ws = _lib.workspace(lib.bgnn_adapted_transform_bwd_workspace_bytes(c), dev)
         with _lib.call("bgnn_adapted_transform_bwd_f32"):
             _lib.check(lib.bgnn_adapted_transform_bwd_f32(_lib.ptr(gHs), _lib.ptr(gHt), _lib.ptr(gates),
-                                                          _lib.ptr(is_src, torch.uint8), _lib.ptr(wd_c), n, c,
+                                                          _lib.ptr(is_src, torch.uint8), _lib.ptr(wd_c), n, c, 2 * c + 2,
                                                           _lib.ptr(gP), _lib.ptr(red), _lib.ptr(ws), ws.numel(),
                                                           _lib.stream(dev)))
         g_bias = None if bias_shape is None else red[2 * c + 2:].view(bias_shape)
@@ -413,6 +415,177 @@ def adapted_transform(P, wd, kg, is_src, bias=None):
     Differentiable in P, wd, kg, bias."""
     Hs, Ht, _ = _AdaptedTransformFn.apply(P, wd, kg, is_src, bias)
     return Hs, Ht
+
+
+# ----------------------------------------------------------------------------------- wide AdaptedConv transform
+def tf32_planes(w, rows_to=16, cols_to=32):
+    """(hi, lo) planes of a small fp32 matrix for the 3 x TF32 contractions: hi = w rounded to tf32, lo = w - hi
+    rounded to tf32 (the tensor core would truncate), both zero padded to multiples of (16, 32)."""
+    w = w.detach().to(torch.float32)
+    r, c = w.shape
+    rp, cp = -(-r // rows_to) * rows_to, -(-c // cols_to) * cols_to
+    wp = torch.zeros((rp, cp), dtype=torch.float32, device=w.device)
+    wp[:r, :c] = w
+    def tf32(t):
+        return ((t.view(torch.int32) + 4096) & -8192).view(torch.float32)
+    hi = tf32(wp)
+    return hi.contiguous(), tf32(wp - hi).contiguous()
+
+
+def rowpanel_gemm_supported(k, ld_a, no):
+    return bool(_lib.load().bgnn_rowpanel_gemm_supported(int(k), int(ld_a), int(no)))
+
+
+def rowpanel_gemm(A, B, bias=None):
+    """A [n, k] @ B [no, k]^T (+ bias [no]) on the tcgen05 tensor cores with fp32-grade accuracy (3 x TF32; A is split on chip and
+    streamed from HBM once).  Stands in for the fp32 SIMT GEMMs of AdaptedConv's node-wise part
+    (models/KTGNN.py:277-284).  A may be a row-strided view (stride % 4 == 0).  Not differentiable."""
+    lib = _lib.load()
+    f32 = torch.float32
+    A = A.detach().to(f32)
+    n, k = A.shape
+    if A.stride(1) != 1 or A.stride(0) % 4 != 0 or A.stride(0) < k or A.data_ptr() % 16 != 0:
+        buf = torch.zeros((n, k + (-k) % 4), dtype=f32, device=A.device)     # TMA needs 16-byte row strides
+        buf[:, :k] = A
+        A = buf[:, :k]
+    no = B.shape[0]
+    hi, lo = tf32_planes(B)
+    b_c = None if bias is None else bias.detach().to(f32).contiguous()
+    Y = torch.empty((n, no), dtype=f32, device=A.device)
+    with _lib.call("bgnn_rowpanel_gemm_f32"):
+        _lib.ptr(A[:1])          # device / dtype checks; A itself may be a row-strided view
+        _lib.check(lib.bgnn_rowpanel_gemm_f32(A.data_ptr(), n, k, max(A.stride(0), k + (-k) % 4), _lib.ptr(hi), _lib.ptr(lo),
+                                              _lib.ptr(b_c, f32, True), no, _lib.ptr(Y), no, _lib.stream(A.device)))
+    return Y
+
+
+def _tma_rows(t):
+    """Row-strided fp32 matrix a TMA descriptor can address in place (unit column stride, 16-byte rows and base)."""
+    return (t.dim() == 2 and t.dtype == torch.float32 and t.is_cuda and t.stride(1) == 1 and t.stride(0) % 4 == 0
+            and t.stride(0) >= t.shape[1] and t.data_ptr() % 16 == 0)
+
+
+def wgrad_gemm_supported(G, X):
+    return (_tma_rows(G) and _tma_rows(X) and G.shape[0] == X.shape[0]
+            and bool(_lib.load().bgnn_wgrad_gemm_supported(X.shape[1], X.stride(0), G.shape[1], G.stride(0))))
+
+
+def wgrad_gemm(G, X):
+    """G [n, no]^T @ X [n, d] -> [no, d] on the tcgen05 tensor cores with fp32-grade accuracy (3 x TF32, both
+    operands split on chip and read from HBM once, deterministic): the weight gradients of AdaptedConv's dense
+    contraction (models/KTGNN.py:277-284) and of the Linear layers of clf_transformer (models/KTGNN.py:363).
+    Both operands may be row-strided views (see ``_tma_rows``).  Not differentiable."""
+    lib = _lib.load()
+    G, X = G.detach(), X.detach()
+    if not wgrad_gemm_supported(G, X):
+        raise ValueError("wgrad_gemm: unsupported operands (need fp32 CUDA, d <= 128, no <= 256, 16-byte rows)")
+    n, no = G.shape
+    d = X.shape[1]
+    W = torch.empty((no, d), dtype=torch.float32, device=G.device)
+    ws = _lib.workspace(lib.bgnn_wgrad_gemm_workspace_bytes(no), G.device)
+    with _lib.call("bgnn_wgrad_gemm_f32"):
+        _lib.check(lib.bgnn_wgrad_gemm_f32(G.data_ptr(), G.stride(0), no, X.data_ptr(), X.stride(0), d, n, _lib.ptr(W), d,
+                                           _lib.ptr(ws), ws.numel(), _lib.stream(G.device)))
+    return W
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return rowpanel_gemm(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.to(torch.float32).contiguous()
+        g_x = rowpanel_gemm(gy, weight.t()) if ctx.needs_input_grad[0] else None
+        g_w = None
+        if ctx.needs_input_grad[1]:
+            xd = x.detach()
+            g_w = wgrad_gemm(gy, xd) if wgrad_gemm_supported(gy, xd) else gy.t() @ xd
+        g_b = gy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return g_x, g_w, g_b
+
+
+def linear_supported(x, weight):
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and not os.environ.get("BGNN_NO_WIDE")
+            and rowpanel_gemm_supported(weight.shape[1], weight.shape[1] + (-weight.shape[1]) % 4, weight.shape[0])
+            and rowpanel_gemm_supported(weight.shape[0], weight.shape[0] + (-weight.shape[0]) % 4, weight.shape[1]))
+
+
+def linear(x, weight, bias=None):
+    """torch.nn.functional.linear for a tall node-feature matrix (n ~ 1e6 rows, <= 256 features in and out): forward
+    and input gradient on the row-panel 3 x TF32 tensor-core GEMM (bias fused), weight gradient on ``wgrad_gemm``.
+    The Linear layers of KT-GNN's clf_transformer (models/KTGNN.py:363).  Differentiable in x, weight, bias."""
+    return _LinearFn.apply(x, weight, bias)
+
+
+class _AdaptedWideFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_cat, bias, wd, kg, is_src):
+        lib = _lib.load()
+        f32 = torch.float32
+        x, w_cat = x.to(f32).contiguous(), w_cat.to(f32).contiguous()
+        wd_c, kg_c = wd.to(f32).contiguous().view(-1), kg.to(f32).contiguous().view(-1)
+        b_c = None if bias is None else bias.to(f32).contiguous().view(-1)
+        n, d = x.shape
+        c = (w_cat.shape[0] - 2) // 2
+        dev = x.device
+        hi, lo = tf32_planes(w_cat)
+        Hs = torch.empty((n, c), dtype=f32, device=dev)
+        Ht = torch.empty((n, c), dtype=f32, device=dev)
+        gates = torch.empty((n, 2), dtype=f32, device=dev)
+        with _lib.call("bgnn_adapted_wide_fwd_f32"):
+            _lib.check(lib.bgnn_adapted_wide_fwd_f32(_lib.ptr(x), n, d, _lib.ptr(hi), _lib.ptr(lo), c,
+                                                     _lib.ptr(is_src, torch.uint8), _lib.ptr(wd_c), _lib.ptr(kg_c),
+                                                     _lib.ptr(b_c, f32, True), _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(gates),
+                                                     _lib.stream(dev)))
+        ctx.save_for_backward(x, w_cat, wd_c, gates, is_src)
+        ctx.meta = (wd.shape, kg.shape, c, None if bias is None else bias.shape)
+        return Hs, Ht
+
+    @staticmethod
+    def backward(ctx, gHs, gHt):
+        lib = _lib.load()
+        x, w_cat, wd_c, gates, is_src = ctx.saved_tensors
+        wd_shape, kg_shape, c, bias_shape = ctx.meta
+        f32 = torch.float32
+        gHs, gHt = gHs.to(f32).contiguous(), gHt.to(f32).contiguous()
+        n = gHs.shape[0]
+        dev = gHs.device
+        ldp = 2 * c + 4                     # 2c+2 rounded up to 4: the two GEMMs below read gP in place through TMA
+        gP_buf = torch.empty((n, ldp), dtype=f32, device=dev)
+        gP = gP_buf[:, : 2 * c + 2]
+        red = torch.empty((4 * c + 2,), dtype=f32, device=dev)
+        ws = _lib.workspace(lib.bgnn_adapted_transform_bwd_workspace_bytes(c), dev)
+        with _lib.call("bgnn_adapted_transform_bwd_f32"):
+            _lib.check(lib.bgnn_adapted_transform_bwd_f32(_lib.ptr(gHs), _lib.ptr(gHt), _lib.ptr(gates),
+                                                          _lib.ptr(is_src, torch.uint8), _lib.ptr(wd_c), n, c, ldp,
+                                                          _lib.ptr(gP_buf), _lib.ptr(red), _lib.ptr(ws), ws.numel(),
+                                                          _lib.stream(dev)))
+        g_x = g_w = None
+        if ctx.needs_input_grad[0]:
+            g_x = rowpanel_gemm(gP, w_cat.t()) if rowpanel_gemm_supported(2 * c + 2, ldp, x.shape[1]) else gP @ w_cat
+        if ctx.needs_input_grad[1]:
+            g_w = wgrad_gemm(gP, x) if wgrad_gemm_supported(gP, x) else gP.t() @ x
+        g_bias = None if bias_shape is None else red[2 * c + 2:].view(bias_shape)
+        return g_x, g_w, g_bias, red[: 2 * c].view(wd_shape), red[2 * c: 2 * c + 2].view(kg_shape), None
+
+
+def adapted_wide_supported(c, d):
+    if os.environ.get("BGNN_NO_WIDE"):       # A/B switch for tools/profile_mp.py
+        return False
+    return bool(_lib.load().bgnn_adapted_wide_supported(int(c), int(d)))
+
+
+def adapted_wide(x, w_cat, bias, wd, kg, is_src):
+    """AdaptedConv's node-wise transform for wide outputs (c a multiple of 32) straight from x: the contraction with
+    w_cat [2c+2, d] on the tensor cores (3 x TF32) with the gates, biases and rank-1 corrections applied to the
+    accumulator tile (models/KTGNN.py:275-284); returns (Hs, Ht).  bias [2c] or None.
+    Differentiable in x, w_cat, bias, wd, kg."""
+    return _AdaptedWideFn.apply(x, w_cat, bias, wd, kg, is_src)
 
 
 # ----------------------------------------------------------------------------------- narrow AdaptedConv transform

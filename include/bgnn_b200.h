@@ -158,12 +158,13 @@ int bgnn_gatv2_heads_bwd_f32(const int32_t* rowptr, const int32_t* col, const in
 int bgnn_adapted_transform_fwd_f32(const float* P, const uint8_t* is_src, const float* wd, const float* kg,
                                    const float* bias, int64_t n, int c, float* Hs, float* Ht, float* gates, void* stream);
 
-/* Backward: gP [n, 2c+2] (fully written), red [4c+2] = (d wd [2c], d kg [2], d bias [2c]).  Deterministic
- * two-stage reductions. */
+/* Backward: gP [n, 2c+2] with row stride ldp >= 2c+2 (columns [0, 2c+2) fully written; a stride that is a multiple
+ * of 4 lets bgnn_wgrad_gemm_f32 / bgnn_rowpanel_gemm_f32 read gP in place), red [4c+2] = (d wd [2c], d kg [2],
+ * d bias [2c]).  Deterministic two-stage reductions. */
 size_t bgnn_adapted_transform_bwd_workspace_bytes(int c);
 int bgnn_adapted_transform_bwd_f32(const float* gHs, const float* gHt, const float* gates, const uint8_t* is_src,
-                                   const float* wd, int64_t n, int c, float* gP, float* g_wd_kg, void* workspace,
-                                   size_t workspace_bytes, void* stream);
+                                   const float* wd, int64_t n, int c, int ldp, float* gP, float* g_wd_kg,
+                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* The same transform for NARROW outputs (classifier heads, c <= 4; d % 4 == 0, d <= 256), without the dense
  * contraction on the host: reads x [n,d] once per direction.  wcat [2c+2, d] = [W_s; W_t; a_g_s2t[:d]; a_g_t2s[:d]],
@@ -184,6 +185,33 @@ int bgnn_adapted_skinny_bwd_f32(const float* x, const uint8_t* is_src, const flo
 size_t bgnn_domain_colsum_workspace_bytes(int d);
 int bgnn_domain_colsum_f32(const float* x, const uint8_t* is_src, int64_t n, int d, float* sums, void* workspace,
                            size_t workspace_bytes, void* stream);
+
+/* Row-panel GEMM on the tcgen05 tensor cores with fp32-grade accuracy (3 x TF32, the streamed operand split on
+ * chip):  Y [n, no] (row stride ldy) = A [n, k] (row stride ld_a, ld_a % 4 == 0, 16-byte aligned) . B^T, with B
+ * given as two planes b_hi / b_lo [nop, kp] row-major, nop = no rounded up to 16, kp = k rounded up to 32, zero
+ * padded, b_hi = B rounded to tf32 (low 13 mantissa bits zero) and b_lo = B - b_hi rounded likewise.  no <= 256.
+ * bias [no] (added to every row) or NULL.  Replaces the fp32 SIMT
+ * GEMMs torch runs for x @ w_cat.t() and dP @ w_cat in AdaptedConv (models/KTGNN.py:277-284). */
+int bgnn_rowpanel_gemm_supported(int k, int ld_a, int no);
+int bgnn_rowpanel_gemm_f32(const float* A, int64_t n, int k, int ld_a, const float* b_hi, const float* b_lo,
+                           const float* bias, int no, float* Y, int ldy, void* stream);
+/* The same contraction for a WIDE AdaptedConv (c % 32 == 0, 2c+2 <= 256, d % 4 == 0, d <= 256) with the node-wise
+ * epilogue of bgnn_adapted_transform_fwd_f32 fused in: x [n,d] is read once, P is never written.
+ * wcat_hi / wcat_lo: planes of [W_s; W_t; a_g_s2t[:d]; a_g_t2s[:d]] as above; bias [2c] or NULL. */
+int bgnn_adapted_wide_supported(int c, int d);
+int bgnn_adapted_wide_fwd_f32(const float* x, int64_t n, int d, const float* wcat_hi, const float* wcat_lo, int c,
+                              const uint8_t* is_src, const float* wd, const float* kg, const float* bias, float* Hs,
+                              float* Ht, float* gates, void* stream);
+
+/* Weight-gradient contraction W [no, d] (row stride ldw) = G^T X = sum_i G[i, :]^T X[i, :] over n rows, on the tcgen05
+ * tensor cores with fp32-grade accuracy (3 x TF32, both operands split on chip, each read from HBM once; per-CTA
+ * partials are added in a fixed order: deterministic).  G [n, no] row stride ld_g, X [n, d] row stride ld_x, both
+ * strides multiples of 4 and both bases 16-byte aligned; d <= 128, no <= 256.  This is g_w_cat = dP^T x of AdaptedConv
+ * (models/KTGNN.py:277-284) and the weight gradient of the Linear layers of clf_transformer (models/KTGNN.py:363). */
+int bgnn_wgrad_gemm_supported(int d, int ld_x, int no, int ld_g);
+size_t bgnn_wgrad_gemm_workspace_bytes(int no);
+int bgnn_wgrad_gemm_f32(const float* G, int ld_g, int no, const float* X, int ld_x, int d, int64_t n, float* W, int ldw,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -324,6 +324,111 @@ def test_adapted_transform_forward_backward(n, c, with_bias):
         assert got.grad.shape == ref.grad.shape and relclose(got.grad, ref.grad, 2e-5), name
 
 
+@pytest.mark.parametrize("n,k,no", [(1, 4, 1), (127, 32, 32), (128, 128, 130), (1000, 130, 128), (4099, 100, 96),
+                                    (20000, 256, 256), (300, 36, 7), (150 * 128 + 5, 64, 64)])
+def test_rowpanel_gemm_matches_float64(n, k, no):
+    """3 x TF32 row-panel GEMM (tcgen05, the streamed operand split on chip) == float64 product to fp32 accuracy,
+    for resident and streamed B planes, ragged n / k / no and more tiles than CTAs."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + k + no)
+    A = torch.randn(n, k, generator=g) * torch.exp(torch.randn(n, 1, generator=g))
+    B = torch.randn(no, k, generator=g)
+    ref = A.double() @ B.double().t()
+    scale = (A.double().abs() @ B.double().abs().t()).clamp(min=1e-30)     # the error bound of a dot product
+    Y = ops.rowpanel_gemm(A.cuda(), B.cuda())
+    assert Y.shape == (n, no)
+    bias = torch.randn(no, generator=g)
+    assert torch.allclose(ops.rowpanel_gemm(A.cuda(), B.cuda(), bias.cuda()), Y + bias.cuda(), rtol=0, atol=1e-6 * float(Y.abs().max()))
+    err = float(((Y.cpu().double() - ref).abs() / scale).max())
+    assert err < 2e-6, err
+    if k % 4 == 0 and n > 1:      # a row-strided view is read in place
+        big = torch.zeros(n, k + 8)
+        big[:, :k] = A
+        Y2 = ops.rowpanel_gemm(big.cuda()[:, :k], B.cuda())
+        assert torch.equal(Y2, Y)
+
+
+@pytest.mark.parametrize("n,no,d", [(1, 1, 4), (31, 32, 32), (32, 130, 128), (1000, 64, 64), (4099, 130, 128), (70000, 256, 100),
+                                    (5000, 7, 36), (148 * 32 * 3 + 17, 96, 128)])
+def test_wgrad_gemm_matches_float64(n, no, d):
+    """G^T X on tcgen05 (both operands MN-major in shared memory, split into tf32 planes on chip) == float64 product
+    to fp32 accuracy; ragged n / no / d, fewer row blocks than CTAs and several per CTA; bit-reproducible."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + no + d)
+    G = torch.randn(n, no, generator=g) * torch.exp(torch.randn(n, 1, generator=g))
+    X = torch.randn(n, d, generator=g)
+    ldg, ldx = no + (-no) % 4 + 4, d + (-d) % 4
+    Gd = torch.zeros(n, ldg).cuda()
+    Gd[:, :no] = G.cuda()
+    Xd = torch.zeros(n, ldx).cuda()
+    Xd[:, :d] = X.cuda()
+    Gv, Xv = Gd[:, :no], Xd[:, :d]
+    assert ops.wgrad_gemm_supported(Gv, Xv)
+    W = ops.wgrad_gemm(Gv, Xv)
+    ref = G.double().t() @ X.double()
+    scale = (G.double().abs().t() @ X.double().abs()).clamp(min=1e-30)
+    assert W.shape == (no, d)
+    err = float(((W.cpu().double() - ref).abs() / scale).max())
+    assert err < 2e-6, err
+    assert torch.equal(W, ops.wgrad_gemm(Gv, Xv))
+
+
+def test_wgrad_gemm_rejects_what_tma_cannot_address():
+    ops = _ops()
+    G, X = torch.randn(64, 10).cuda(), torch.randn(64, 16).cuda()
+    assert not ops.wgrad_gemm_supported(G, X)            # 40-byte rows
+    assert not ops.wgrad_gemm_supported(X, torch.randn(64, 132).cuda())     # d > 128
+    with pytest.raises(ValueError):
+        ops.wgrad_gemm(G, X)
+
+
+@pytest.mark.parametrize("n,din,dout,bias", [(1, 4, 4, True), (1000, 64, 64, True), (4097, 100, 36, False), (20000, 128, 256, True)])
+def test_node_linear_forward_backward(n, din, dout, bias):
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + din)
+    x, w, b = torch.randn(n, din, generator=g), torch.randn(dout, din, generator=g) * 0.2, torch.randn(dout, generator=g)
+    go = torch.randn(n, dout, generator=g)
+    vals = [x, w] + ([b] if bias else [])
+    leaf = [t.clone().double().requires_grad_(True) for t in vals]
+    y_r = torch.nn.functional.linear(leaf[0], leaf[1], leaf[2] if bias else None)
+    (y_r * go).sum().backward()
+    dl = [t.clone().cuda().requires_grad_(True) for t in vals]
+    assert ops.linear_supported(dl[0], dl[1])
+    y = ops.linear(dl[0], dl[1], dl[2] if bias else None)
+    assert relclose(y, y_r.float(), 3e-6)
+    (y * go.cuda()).sum().backward()
+    for got, ref, name in zip(dl, leaf, ("x", "weight", "bias")):
+        assert got.grad.shape == ref.grad.shape and relclose(got.grad, ref.grad.float(), 1e-5), name
+
+
+@pytest.mark.parametrize("n,c,d,bias", [(1, 32, 4, True), (1000, 64, 128, True), (777, 32, 100, False), (5000, 64, 64, True),
+                                        (20000, 96, 256, True), (129, 64, 36, False)])
+def test_adapted_wide_forward_backward(n, c, d, bias):
+    """Wide-output transform straight from x (tensor-core contraction with the node-wise epilogue fused) == dense
+    contraction + node-wise epilogue of the oracle."""
+    ops = _ops()
+    assert ops.adapted_wide_supported(c, d) and not ops.adapted_wide_supported(c + 1, d) and not ops.adapted_wide_supported(160, d)
+    g = torch.Generator().manual_seed(90 + c + d)
+    x = torch.randn(n, d, generator=g)
+    w_cat = torch.randn(2 * c + 2, d, generator=g) * 0.3
+    b2 = torch.randn(2 * c, generator=g) if bias else None
+    wd, kg = torch.randn(1, 2 * c, generator=g), torch.randn(2, generator=g)
+    cm = torch.rand(n, generator=g) < 0.7
+    go_s, go_t = torch.randn(n, c, generator=g), torch.randn(n, c, generator=g)
+    names = ["x", "w_cat", "wd", "kg"] + (["bias"] if bias else [])
+    vals = [x, w_cat, wd, kg] + ([b2] if bias else [])
+    leaf = [t.clone().double().requires_grad_(True) for t in vals]
+    P = leaf[0] @ leaf[1].t() + (torch.cat((leaf[4], torch.zeros(2, dtype=torch.float64))) if bias else 0.0)
+    Hs_r, Ht_r = mo.adapted_transform_epilogue(P, leaf[2], leaf[3], cm.to(torch.uint8))
+    ((Hs_r * go_s).sum() + (Ht_r * go_t).sum()).backward()
+    dl = [t.clone().cuda().requires_grad_(True) for t in vals]
+    Hs, Ht = ops.adapted_wide(dl[0], dl[1], dl[4] if bias else None, dl[2], dl[3], cm.to(torch.uint8).cuda())
+    assert relclose(Hs, Hs_r.float(), 3e-6) and relclose(Ht, Ht_r.float(), 3e-6)
+    ((Hs * go_s.cuda()).sum() + (Ht * go_t.cuda()).sum()).backward()
+    for got, ref, name in zip(dl, leaf, names):
+        assert got.grad.shape == ref.grad.shape and relclose(got.grad, ref.grad.float(), 2e-5), name
+
+
 @pytest.mark.parametrize("n,c,d,bias", [(1, 1, 4, True), (1000, 2, 64, True), (777, 3, 100, False), (5000, 4, 128, True),
                                         (3000, 2, 256, True), (257, 4, 8, False)])
 def test_adapted_skinny_forward_backward(n, c, d, bias):

@@ -427,11 +427,37 @@ int bgnn_wgrad_gemm_supported(int d, int ld_x, int no, int ld_g) { return wgrad_
 size_t bgnn_wgrad_gemm_workspace_bytes(int no) { return no <= 0 ? 0 : wgrad_gemm_workspace_bytes(no); }
 
 int bgnn_wgrad_gemm_f32(const float* G, int ld_g, int no, const float* X, int ld_x, int d, int64_t n, float* W, int ldw,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+                        float* colsum, void* workspace, size_t workspace_bytes, void* stream) {
   if (n < 0 || no <= 0 || d <= 0 || ld_g < no || ld_x < d || ldw < d || !W || !workspace) return BGNN_ERR_INVALID_ARG;
   if (n > 0 && (!G || !X)) return BGNN_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(X)) & 15) return BGNN_ERR_INVALID_ARG;
-  return launch_wgrad_gemm(G, ld_g, no, X, ld_x, d, n, W, ldw, workspace, workspace_bytes, (cudaStream_t)stream);
+  return launch_wgrad_gemm(G, ld_g, no, X, ld_x, d, n, W, ldw, colsum, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bgnn_bn_relu_supported(int c) { return bn_relu_supported(c) ? 1 : 0; }
+
+size_t bgnn_bn_relu_workspace_bytes(int c) { return c <= 0 ? 0 : bn_relu_workspace_bytes(c); }
+
+int bgnn_bn_relu_fwd_f32(const float* x, int64_t n, int c, const float* weight, const float* bias, float eps, float momentum,
+                         float* running_mean, float* running_var, int relu, float* y, float* stats, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (n < 0 || c <= 0 || !stats || !workspace) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!x || !y)) return BGNN_ERR_INVALID_ARG;
+  return launch_bn_relu_fwd(x, n, c, weight, bias, eps, momentum, running_mean, running_var, relu, y, stats, workspace,
+                            workspace_bytes, (cudaStream_t)stream);
+}
+
+int bgnn_bn_relu_apply_f32(const float* x, int64_t n, int c, const float* stats, int relu, float* y, void* stream) {
+  if (n < 0 || c <= 0 || !stats) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!x || !y)) return BGNN_ERR_INVALID_ARG;
+  return launch_bn_relu_apply(x, n, c, stats, relu, y, (cudaStream_t)stream);
+}
+
+int bgnn_bn_relu_bwd_f32(const float* gy, const float* x, int64_t n, int c, const float* stats, int relu, float* gx,
+                         float* gwb, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 0 || c <= 0 || !stats || !gwb || !workspace) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!gy || !x || !gx)) return BGNN_ERR_INVALID_ARG;
+  return launch_bn_relu_bwd(gy, x, n, c, stats, relu, gx, gwb, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

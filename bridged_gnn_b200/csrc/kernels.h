@@ -127,6 +127,16 @@ int launch_adapted_wide_fwd(const float* x, long long n, int d, const float* wca
 bool wgrad_gemm_supported(int d, int ld_x, int no, int ld_g);
 size_t wgrad_gemm_workspace_bytes(int no);
 int launch_wgrad_gemm(const float* G, int ld_g, int no, const float* X, int ld_x, int d, long long n, float* W, int ldw,
-                      void* ws, size_t ws_bytes, cudaStream_t stream);
+                      float* colsum, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// bn_relu.cu
+bool bn_relu_supported(int c);
+size_t bn_relu_workspace_bytes(int c);
+int launch_bn_relu_fwd(const float* x, long long n, int c, const float* w, const float* b, float eps, float momentum,
+                       float* running_mean, float* running_var, int relu, float* y, float* stats, void* ws, size_t ws_bytes,
+                       cudaStream_t stream);
+int launch_bn_relu_apply(const float* x, long long n, int c, const float* stats, int relu, float* y, cudaStream_t stream);
+int launch_bn_relu_bwd(const float* gy, const float* x, long long n, int c, const float* stats, int relu, float* gx, float* gwb,
+                       void* ws, size_t ws_bytes, cudaStream_t stream);
 
 }  // namespace bgnn

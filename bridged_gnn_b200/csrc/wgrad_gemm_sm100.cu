@@ -55,7 +55,7 @@ __device__ __forceinline__ float wg_tf32(float v) { return __uint_as_float((__fl
 // of the hi plane with the raw data; X boxes mb..3 (features >= d) are zeroed once and never touched again.
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, long long nblocks,
-                  int mb, int nb, int stages, float* __restrict__ part) {
+                  int mb, int nb, int stages, int ones_col, float* __restrict__ part) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int plane = (nb + WG_MBOX) * WG_BOX;
@@ -91,6 +91,14 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         float4* z = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + (size_t)pl * plane + (size_t)(nb + mb) * WG_BOX);
         for (int i = threadIdx.x; i < zero_f4; i += WG_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    if (ones_col) {          // feature mb*32 := 1 in every row, so that row mb*32 of D collects the column sums of G
+      __syncthreads();
+      if (threadIdx.x < WG_BK)
+        for (int s = 0; s < stages; ++s) {
+          float* z = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + (size_t)(nb + mb) * WG_BOX);
+          z[threadIdx.x * 32 + ((threadIdx.x & 3) << 3)] = 1.0f;      // column 0 of row r sits in 32-byte chunk r & 3
+        }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
@@ -194,15 +202,20 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   }
 }
 
-// W[j * ldw + f] = sum over CTAs (in order) of part[cta][f][j]
+// W[j * ldw + f] = sum over CTAs (in order) of part[cta][f][j];  colsum[j] = the same for the all-ones feature row
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int nop, int no, int d, float* __restrict__ W, int ldw) {
+wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int nop, int no, int d, float* __restrict__ W, int ldw,
+                    float* __restrict__ colsum, int f_ones) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // f * no + j: consecutive threads read consecutive j
-  if (idx >= d * no) return;
-  const int f = idx / no, j = idx - f * no;
+  if (idx >= (d + (colsum ? 1 : 0)) * no) return;
+  int f = idx / no;
+  const int j = idx - f * no;
+  const bool extra = f == d;
+  if (extra) f = f_ones;
   float acc = 0.f;
   for (int p = 0; p < nparts; ++p) acc += part[((size_t)p * 128 + f) * nop + j];
-  W[(size_t)j * ldw + f] = acc;
+  if (extra) colsum[j] = acc;
+  else W[(size_t)j * ldw + f] = acc;
 }
 
 static int wg_make_map(CUtensorMap* m, const float* base, long long rows, int cols, int ld) {
@@ -230,8 +243,9 @@ bool wgrad_gemm_supported(int d, int ld_x, int no, int ld_g) {
 size_t wgrad_gemm_workspace_bytes(int no) { return (size_t)kNumSMs * 128 * ((no + 31) / 32 * 32) * sizeof(float) + 256; }
 
 int launch_wgrad_gemm(const float* G, int ld_g, int no, const float* X, int ld_x, int d, long long n, float* W, int ldw,
-                      void* ws, size_t ws_bytes, cudaStream_t stream) {
+                      float* colsum, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (!wgrad_gemm_supported(d, ld_x, no, ld_g) || n >= (1ll << 31)) return BGNN_ERR_UNSUPPORTED;
+  if (colsum && d > 96) return BGNN_ERR_UNSUPPORTED;      // the all-ones feature needs a spare box
   if (ws_bytes < wgrad_gemm_workspace_bytes(no)) return BGNN_ERR_WORKSPACE;
   const int nb = (no + 31) / 32, mb = (d + 31) / 32;
   const int nop = nb * 32;
@@ -246,10 +260,10 @@ int launch_wgrad_gemm(const float* G, int ld_g, int no, const float* X, int ld_x
     const int stages = wg_stages(nb);
     const size_t smem = WG_SMEM_FIXED + (size_t)stages * 2 * (nb + WG_MBOX) * WG_BOX;
     BGNN_CUDA_TRY(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_gemm_kernel<<<grid, WG_THREADS, smem, stream>>>(mx, mg, nblocks, mb, nb, stages, part);
+    wgrad_gemm_kernel<<<grid, WG_THREADS, smem, stream>>>(mx, mg, nblocks, mb, nb, stages, colsum ? 1 : 0, part);
     BGNN_LAUNCH_CHECK();
   }
-  wgrad_reduce_kernel<<<(d * no + 255) / 256, 256, 0, stream>>>(part, n > 0 ? (int)grid : 0, nop, no, d, W, ldw);
+  wgrad_reduce_kernel<<<((d + 1) * no + 255) / 256, 256, 0, stream>>>(part, n > 0 ? (int)grid : 0, nop, no, d, W, ldw, colsum, mb * 32);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }

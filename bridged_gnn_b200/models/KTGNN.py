@@ -11,6 +11,29 @@ from .. import ops
 from ..data import add_self_loops, remove_self_loops
 
 
+def bn_relu(bn, x):
+    """relu(bn(x)) (models/KTGNN.py:425-429); plain nn.BatchNorm1d on the GPU goes through the fused two-pass kernels,
+    anything else (SyncBatchNorm of the partitioned path, CPU, other dtypes) through the module itself."""
+    if type(bn) is nn.BatchNorm1d and ops.batch_norm_relu_supported(x, bn):
+        return ops.batch_norm_relu(x, bn)
+    return F.relu(bn(x))
+
+
+def run_sequential(seq, x):
+    """``seq(x)`` for an nn.Sequential, with every BatchNorm1d -> ReLU pair taken by ``bn_relu``
+    (clf_transformer, models/KTGNN.py:363-366)."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        if isinstance(mods[i], nn.modules.batchnorm._BatchNorm) and i + 1 < len(mods) and type(mods[i + 1]) is nn.ReLU:
+            x = bn_relu(mods[i], x)
+            i += 2
+        else:
+            x = mods[i](x)
+            i += 1
+    return x
+
+
 class NodeLinear(nn.Linear):
     """nn.Linear over the node-feature matrix (same parameters and state_dict keys); on the GPU in fp32 the forward,
     input-gradient and weight-gradient GEMMs run on this library's 3 x TF32 tensor-core kernels instead of cuBLAS'
@@ -267,9 +290,8 @@ class _KTGNNBase(nn.Module):
                                       "(padding rows would enter the batch statistics)")
         for ind in range(n_convs):
             x = self.convs[ind](x, ei, ei1, ei2, c, part=part)
-            if self.use_bn:
-                x = self.bns[ind](x)
-            x = F.dropout(F.relu(x), p=self.dropout, training=self.training)
+            x = bn_relu(self.bns[ind], x) if self.use_bn else F.relu(x)
+            x = F.dropout(x, p=self.dropout, training=self.training)
         return x
 
 
@@ -309,7 +331,7 @@ class KTGNN_no_complement(_KTGNNBase):
         c = data.central_mask
         x = self._hidden(data.x, ei, ei1, ei2, c, len(self.convs), part)
         logits_base, logits_trans, logits_target = adapted_convs_shared_graph(
-            (self.clf_base, self.clf_target, self.clf_target), (x, self.clf_transformer(x), x), ei, ei1, ei2, c, part)
+            (self.clf_base, self.clf_target, self.clf_target), (x, run_sequential(self.clf_transformer, x), x), ei, ei1, ei2, c, part)
         return F.log_softmax(logits_base, 1), F.log_softmax(logits_target, 1), F.log_softmax(logits_trans, 1), None
 
 

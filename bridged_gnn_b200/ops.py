@@ -470,23 +470,27 @@ def wgrad_gemm_supported(G, X):
             and bool(_lib.load().bgnn_wgrad_gemm_supported(X.shape[1], X.stride(0), G.shape[1], G.stride(0))))
 
 
-def wgrad_gemm(G, X):
+def wgrad_gemm(G, X, colsum=False):
     """G [n, no]^T @ X [n, d] -> [no, d] on the tcgen05 tensor cores with fp32-grade accuracy (3 x TF32, both
     operands split on chip and read from HBM once, deterministic): the weight gradients of AdaptedConv's dense
     contraction (models/KTGNN.py:277-284) and of the Linear layers of clf_transformer (models/KTGNN.py:363).
-    Both operands may be row-strided views (see ``_tma_rows``).  Not differentiable."""
+    Both operands may be row-strided views (see ``_tma_rows``).  ``colsum=True`` (d <= 96) also returns G.sum(0),
+    collected by the same pass through an all-ones feature.  Not differentiable."""
     lib = _lib.load()
     G, X = G.detach(), X.detach()
     if not wgrad_gemm_supported(G, X):
         raise ValueError("wgrad_gemm: unsupported operands (need fp32 CUDA, d <= 128, no <= 256, 16-byte rows)")
     n, no = G.shape
     d = X.shape[1]
+    if colsum and d > 96:
+        raise ValueError("wgrad_gemm: colsum needs d <= 96")
     W = torch.empty((no, d), dtype=torch.float32, device=G.device)
+    cs = torch.empty((no,), dtype=torch.float32, device=G.device) if colsum else None
     ws = _lib.workspace(lib.bgnn_wgrad_gemm_workspace_bytes(no), G.device)
     with _lib.call("bgnn_wgrad_gemm_f32"):
         _lib.check(lib.bgnn_wgrad_gemm_f32(G.data_ptr(), G.stride(0), no, X.data_ptr(), X.stride(0), d, n, _lib.ptr(W), d,
-                                           _lib.ptr(ws), ws.numel(), _lib.stream(G.device)))
-    return W
+                                           _lib.ptr(cs, allow_none=True), _lib.ptr(ws), ws.numel(), _lib.stream(G.device)))
+    return (W, cs) if colsum else W
 
 
 class _LinearFn(torch.autograd.Function):
@@ -501,11 +505,19 @@ class _LinearFn(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         gy = gy.to(torch.float32).contiguous()
         g_x = rowpanel_gemm(gy, weight.t()) if ctx.needs_input_grad[0] else None
-        g_w = None
+        g_w = g_b = None
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
             xd = x.detach()
-            g_w = wgrad_gemm(gy, xd) if wgrad_gemm_supported(gy, xd) else gy.t() @ xd
-        g_b = gy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+            if wgrad_gemm_supported(gy, xd):
+                if want_b and xd.shape[1] <= 96:
+                    g_w, g_b = wgrad_gemm(gy, xd, colsum=True)      # bias gradient from the same pass
+                else:
+                    g_w = wgrad_gemm(gy, xd)
+            else:
+                g_w = gy.t() @ xd
+        if want_b and g_b is None:
+            g_b = gy.sum(0)
         return g_x, g_w, g_b
 
 
@@ -586,6 +598,83 @@ def adapted_wide(x, w_cat, bias, wd, kg, is_src):
     accumulator tile (models/KTGNN.py:275-284); returns (Hs, Ht).  bias [2c] or None.
     Differentiable in x, w_cat, bias, wd, kg."""
     return _AdaptedWideFn.apply(x, w_cat, bias, wd, kg, is_src)
+
+
+# ----------------------------------------------------------------------------------- BatchNorm1d + ReLU
+class _BnReluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu):
+        lib = _lib.load()
+        f32 = torch.float32
+        x = x.to(f32).contiguous()
+        n, c = x.shape
+        dev = x.device
+        y = torch.empty_like(x)
+        stats = torch.empty((4 * c,), dtype=f32, device=dev)
+        ws = _lib.workspace(lib.bgnn_bn_relu_workspace_bytes(c), dev)
+        w_c = None if weight is None else weight.detach().to(f32).contiguous()
+        b_c = None if bias is None else bias.detach().to(f32).contiguous()
+        with _lib.call("bgnn_bn_relu_fwd_f32"):
+            _lib.check(lib.bgnn_bn_relu_fwd_f32(_lib.ptr(x), n, c, _lib.ptr(w_c, f32, True), _lib.ptr(b_c, f32, True), float(eps),
+                                                float(momentum), _lib.ptr(running_mean, f32, True),
+                                                _lib.ptr(running_var, f32, True), int(relu), _lib.ptr(y), _lib.ptr(stats),
+                                                _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+        ctx.save_for_backward(x, stats)
+        ctx.meta = (int(relu), weight is not None, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, stats = ctx.saved_tensors
+        relu, has_w, has_b = ctx.meta
+        f32 = torch.float32
+        gy = gy.to(f32).contiguous()
+        n, c = x.shape
+        dev = x.device
+        gx = torch.empty_like(x)
+        gwb = torch.empty((2 * c,), dtype=f32, device=dev)
+        ws = _lib.workspace(lib.bgnn_bn_relu_workspace_bytes(c), dev)
+        with _lib.call("bgnn_bn_relu_bwd_f32"):
+            _lib.check(lib.bgnn_bn_relu_bwd_f32(_lib.ptr(gy), _lib.ptr(x), n, c, _lib.ptr(stats), relu, _lib.ptr(gx),
+                                                _lib.ptr(gwb), _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+        return gx, (gwb[:c] if has_w else None), (gwb[c:] if has_b else None), None, None, None, None, None
+
+
+def batch_norm_relu_supported(x, bn):
+    """Whether ``batch_norm_relu`` covers this call: fp32 CUDA [n, c] input, c % 4 == 0; training mode with batch
+    statistics and a fixed momentum, or inference (no autograd) with running statistics."""
+    if os.environ.get("BGNN_NO_WIDE") or not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 1):
+        return False
+    if not bool(_lib.load().bgnn_bn_relu_supported(x.shape[1])):
+        return False
+    if bn.training:
+        return bn.momentum is not None or not bn.track_running_stats
+    return bn.track_running_stats and not (torch.is_grad_enabled() and (x.requires_grad or (bn.affine and bn.weight.requires_grad)))
+
+
+def batch_norm_relu(x, bn, relu=True):
+    """relu(bn(x)) for an ``nn.BatchNorm1d`` over the node-feature matrix (models/KTGNN.py:363-366, 425-429) in two
+    passes over x each way (statistics; normalise + affine + ReLU), against ATen's six forward and four backward.
+    Training mode updates bn.running_mean / running_var / num_batches_tracked like torch."""
+    lib = _lib.load()
+    f32 = torch.float32
+    if bn.training:
+        track = bn.track_running_stats and bn.running_mean is not None
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        return _BnReluFn.apply(x, bn.weight, bn.bias, bn.running_mean if track else None, bn.running_var if track else None,
+                               bn.momentum if bn.momentum is not None else 0.0, bn.eps, relu)
+    x = x.detach().to(f32).contiguous()
+    n, c = x.shape
+    w = bn.weight.detach() if bn.affine else torch.ones(c, dtype=f32, device=x.device)
+    b = bn.bias.detach() if bn.affine else torch.zeros(c, dtype=f32, device=x.device)
+    scale = w * torch.rsqrt(bn.running_var + bn.eps)
+    stats = torch.cat((bn.running_mean, scale, scale, b)).to(f32).contiguous()
+    y = torch.empty_like(x)
+    with _lib.call("bgnn_bn_relu_apply_f32"):
+        _lib.check(lib.bgnn_bn_relu_apply_f32(_lib.ptr(x), n, c, _lib.ptr(stats), int(relu), _lib.ptr(y), _lib.stream(x.device)))
+    return y
 
 
 # ----------------------------------------------------------------------------------- narrow AdaptedConv transform

@@ -206,12 +206,31 @@ int bgnn_adapted_wide_fwd_f32(const float* x, int64_t n, int d, const float* wca
 /* Weight-gradient contraction W [no, d] (row stride ldw) = G^T X = sum_i G[i, :]^T X[i, :] over n rows, on the tcgen05
  * tensor cores with fp32-grade accuracy (3 x TF32, both operands split on chip, each read from HBM once; per-CTA
  * partials are added in a fixed order: deterministic).  G [n, no] row stride ld_g, X [n, d] row stride ld_x, both
- * strides multiples of 4 and both bases 16-byte aligned; d <= 128, no <= 256.  This is g_w_cat = dP^T x of AdaptedConv
+ * strides multiples of 4 and both bases 16-byte aligned; d <= 128, no <= 256.  colsum [no] (NULL to skip; needs
+ * d <= 96) receives the column sums of G from the same pass (a bias gradient).  This is g_w_cat = dP^T x of AdaptedConv
  * (models/KTGNN.py:277-284) and the weight gradient of the Linear layers of clf_transformer (models/KTGNN.py:363). */
 int bgnn_wgrad_gemm_supported(int d, int ld_x, int no, int ld_g);
 size_t bgnn_wgrad_gemm_workspace_bytes(int no);
 int bgnn_wgrad_gemm_f32(const float* G, int ld_g, int no, const float* X, int ld_x, int d, int64_t n, float* W, int ldw,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        float* colsum, void* workspace, size_t workspace_bytes, void* stream);
+
+/* BatchNorm1d (+ ReLU) over x [n, c] in training mode (models/KTGNN.py:363-366, 425-429: nn.BatchNorm1d followed by
+ * ReLU), c % 4 == 0, c <= 1024; two passes over x each way, deterministic.
+ * fwd: batch statistics (biased variance for the normalisation), y = [relu]((x - mean) * weight * invstd + bias);
+ *      weight / bias [c] or NULL (= 1 / 0); running_mean / running_var [c] or NULL are updated in place with
+ *      `momentum` (unbiased variance), like torch;  stats [4c] = (mean, invstd, weight * invstd, bias) is what apply
+ *      and bwd take.
+ * apply: y = [relu]((x - stats.mean) * stats.scale + stats.bias) only -- the eval-mode forward with
+ *      stats = (running_mean, -, weight / sqrt(running_var + eps), bias).
+ * bwd: gx [n, c] and gwb [2c] = (d weight, d bias) from gy = dL/dy; the ReLU mask is recomputed from x. */
+int bgnn_bn_relu_supported(int c);
+size_t bgnn_bn_relu_workspace_bytes(int c);
+int bgnn_bn_relu_fwd_f32(const float* x, int64_t n, int c, const float* weight, const float* bias, float eps, float momentum,
+                         float* running_mean, float* running_var, int relu, float* y, float* stats, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int bgnn_bn_relu_apply_f32(const float* x, int64_t n, int c, const float* stats, int relu, float* y, void* stream);
+int bgnn_bn_relu_bwd_f32(const float* gy, const float* x, int64_t n, int c, const float* stats, int relu, float* gx,
+                         float* gwb, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

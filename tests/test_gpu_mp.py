@@ -371,6 +371,11 @@ def test_wgrad_gemm_matches_float64(n, no, d):
     err = float(((W.cpu().double() - ref).abs() / scale).max())
     assert err < 2e-6, err
     assert torch.equal(W, ops.wgrad_gemm(Gv, Xv))
+    if d <= 96:                # column sums of G ride along on an all-ones feature
+        W2, cs = ops.wgrad_gemm(Gv, Xv, colsum=True)
+        assert torch.equal(W2, W)
+        ref_cs = G.double().sum(0)
+        assert float(((cs.cpu().double() - ref_cs).abs() / G.double().abs().sum(0).clamp(min=1e-30)).max()) < 2e-6
 
 
 def test_wgrad_gemm_rejects_what_tma_cannot_address():
@@ -399,6 +404,49 @@ def test_node_linear_forward_backward(n, din, dout, bias):
     (y * go.cuda()).sum().backward()
     for got, ref, name in zip(dl, leaf, ("x", "weight", "bias")):
         assert got.grad.shape == ref.grad.shape and relclose(got.grad, ref.grad.float(), 1e-5), name
+
+
+@pytest.mark.parametrize("n,c", [(16, 4), (1000, 64), (4099, 100), (50000, 64), (3000, 256), (700, 1024)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_batch_norm_relu_matches_torch(n, c, relu):
+    """Fused BatchNorm1d (+ ReLU), training and inference mode, against nn.BatchNorm1d / F.relu in float64: outputs,
+    all three gradients, running statistics; the backward recomputes the ReLU mask from x."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + c)
+    x = torch.randn(n, c, generator=g) * (1.0 + torch.rand(c, generator=g)) + 3.0 * torch.randn(c, generator=g)
+    go = torch.randn(n, c, generator=g)
+    ref = torch.nn.BatchNorm1d(c).double()
+    with torch.no_grad():
+        ref.weight.copy_(torch.randn(c, generator=g))
+        ref.bias.copy_(torch.randn(c, generator=g))
+    bn = torch.nn.BatchNorm1d(c).cuda()
+    bn.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr)
+    yr = torch.relu(yr) if relu else yr
+    (yr * go).sum().backward()
+    xd = x.cuda().requires_grad_(True)
+    assert ops.batch_norm_relu_supported(xd, bn)
+    y = ops.batch_norm_relu(xd, bn, relu=relu)
+    (y * go.cuda()).sum().backward()
+    assert relclose(y, yr.float(), 3e-6)
+    assert relclose(xd.grad, xr.grad.float(), 2e-5)
+    assert relclose(bn.weight.grad, ref.weight.grad.float(), 2e-5) and relclose(bn.bias.grad, ref.bias.grad.float(), 2e-5)
+    assert relclose(bn.running_mean, ref.running_mean.float(), 2e-6) and relclose(bn.running_var, ref.running_var.float(), 2e-6)
+    assert int(bn.num_batches_tracked) == 1
+    y2 = ops.batch_norm_relu(xd, bn, relu=relu)          # deterministic
+    assert torch.equal(y2, y)
+    with torch.no_grad():
+        ref(x.double())                                  # second momentum update on the reference side too
+    bn.eval()
+    ref.eval()
+    with torch.no_grad():
+        assert ops.batch_norm_relu_supported(xd, bn)
+        ye = ops.batch_norm_relu(xd, bn, relu=relu)
+        yre = ref(x.double())
+        yre = torch.relu(yre) if relu else yre
+    assert relclose(ye, yre.float(), 3e-6)
+    assert not ops.batch_norm_relu_supported(xd, bn)     # inference statistics with autograd on: left to torch
 
 
 @pytest.mark.parametrize("n,c,d,bias", [(1, 32, 4, True), (1000, 64, 128, True), (777, 32, 100, False), (5000, 64, 64, True),

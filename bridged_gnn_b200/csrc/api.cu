@@ -373,11 +373,11 @@ int bgnn_adapted_skinny_fwd_f32(const float* x, const uint8_t* is_src, const flo
                                 float* gates, void* stream) {
   if (n < 0 || c <= 0 || d <= 0) return BGNN_ERR_INVALID_ARG;
   if (n > 0 && (!x || !is_src || !wcat || !wd || !kg || !Hs || !Ht || !gates)) return BGNN_ERR_INVALID_ARG;
-  return launch_adapted_skinny_fwd(x, is_src, wcat, bias, wd, kg, n, d, c, Hs, Ht, gates, (cudaStream_t)stream);
+  return launch_adapted_skinny_fwd(x, is_src, wcat, bias, wd, kg, n, d, c, 1, Hs, Ht, gates, (cudaStream_t)stream);
 }
 
 size_t bgnn_adapted_skinny_bwd_workspace_bytes(int c, int d) {
-  return (c <= 0 || d <= 0) ? 0 : adapted_skinny_bwd_workspace_bytes(c, d);
+  return (c <= 0 || d <= 0) ? 0 : adapted_skinny_bwd_workspace_bytes(c, d, 1);
 }
 
 int bgnn_adapted_skinny_bwd_f32(const float* x, const uint8_t* is_src, const float* wcat, const float* wd,
@@ -386,8 +386,8 @@ int bgnn_adapted_skinny_bwd_f32(const float* x, const uint8_t* is_src, const flo
   if (n < 0 || c <= 0 || d <= 0) return BGNN_ERR_INVALID_ARG;
   if (n > 0 && (!x || !is_src || !wcat || !wd || !gates || !gHs || !gHt || !gx || !red || !workspace))
     return BGNN_ERR_INVALID_ARG;
-  return launch_adapted_skinny_bwd(x, is_src, wcat, wd, gates, gHs, gHt, n, d, c, gx, red, workspace, workspace_bytes,
-                                   (cudaStream_t)stream);
+  return launch_adapted_skinny_bwd(x, is_src, wcat, wd, gates, gHs, gHt, nullptr, n, d, c, 1, gx, red, workspace,
+                                   workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t bgnn_domain_colsum_workspace_bytes(int d) { return d <= 0 ? 0 : domain_colsum_workspace_bytes(d); }
@@ -458,6 +458,42 @@ int bgnn_bn_relu_bwd_f32(const float* gy, const float* x, int64_t n, int c, cons
   if (n < 0 || c <= 0 || !stats || !gwb || !workspace) return BGNN_ERR_INVALID_ARG;
   if (n > 0 && (!gy || !x || !gx)) return BGNN_ERR_INVALID_ARG;
   return launch_bn_relu_bwd(gy, x, n, c, stats, relu, gx, gwb, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bgnn_adapted_skinny_heads_supported(int c, int d, int heads) { return adapted_skinny_heads_supported(c, d, heads) ? 1 : 0; }
+
+int bgnn_adapted_skinny_heads_fwd_f32(const float* x, const uint8_t* is_src, const float* wcat, const float* bias,
+                                      const float* wd, const float* kg, int64_t n, int d, int c, int heads, float* Hs,
+                                      float* Ht, float* gates, void* stream) {
+  if (n < 0 || c <= 0 || d <= 0 || heads <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!x || !is_src || !wcat || !wd || !kg || !Hs || !Ht || !gates)) return BGNN_ERR_INVALID_ARG;
+  return launch_adapted_skinny_fwd(x, is_src, wcat, bias, wd, kg, n, d, c, heads, Hs, Ht, gates, (cudaStream_t)stream);
+}
+
+size_t bgnn_adapted_skinny_heads_bwd_workspace_bytes(int c, int d, int heads) {
+  if (c <= 0 || d <= 0 || heads <= 0) return 0;
+  const size_t a = adapted_skinny_bwd_workspace_bytes(c, d, heads), b = adapted_skinny_pre_workspace_bytes(c, heads);
+  return a > b ? a : b;
+}
+
+int bgnn_adapted_skinny_heads_pre_f32(const uint8_t* is_src, const float* wd, const float* gates, const float* gHs,
+                                      const float* gHt, int64_t n, int c, int heads, float* pre, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  if (n < 0 || c <= 0 || heads <= 0 || !pre || !workspace) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!is_src || !wd || !gates || !gHs || !gHt)) return BGNN_ERR_INVALID_ARG;
+  return launch_adapted_skinny_pre(is_src, wd, gates, gHs, gHt, n, c, heads, pre, workspace, workspace_bytes,
+                                   (cudaStream_t)stream);
+}
+
+int bgnn_adapted_skinny_heads_bwd_f32(const float* x, const uint8_t* is_src, const float* wcat, const float* wd,
+                                      const float* gates, const float* gHs, const float* gHt, const float* gm, int64_t n,
+                                      int d, int c, int heads, float* gx, float* red, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  if (n < 0 || c <= 0 || d <= 0 || heads <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!x || !is_src || !wcat || !wd || !gates || !gHs || !gHt || !gx || !red || !workspace))
+    return BGNN_ERR_INVALID_ARG;
+  return launch_adapted_skinny_bwd(x, is_src, wcat, wd, gates, gHs, gHt, gm, n, d, c, heads, gx, red, workspace,
+                                   workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

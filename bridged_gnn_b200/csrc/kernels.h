@@ -102,13 +102,17 @@ int launch_gatv2_heads_bwd(const int* rowptr, const int* col, const int* t_rowpt
 
 // adapted_skinny.cu
 bool adapted_skinny_supported(int c, int d);
+bool adapted_skinny_heads_supported(int c, int d, int heads);
 int launch_adapted_skinny_fwd(const float* x, const uint8_t* is_src, const float* wcat, const float* bias, const float* wd,
-                              const float* kg, long long n, int d, int c, float* Hs, float* Ht, float* gates,
+                              const float* kg, long long n, int d, int c, int heads, float* Hs, float* Ht, float* gates,
                               cudaStream_t stream);
-size_t adapted_skinny_bwd_workspace_bytes(int c, int d);
+size_t adapted_skinny_bwd_workspace_bytes(int c, int d, int heads);
 int launch_adapted_skinny_bwd(const float* x, const uint8_t* is_src, const float* wcat, const float* wd, const float* gates,
-                              const float* gHs, const float* gHt, long long n, int d, int c, float* gx, float* red,
-                              void* ws, size_t ws_bytes, cudaStream_t stream);
+                              const float* gHs, const float* gHt, const float* gm, long long n, int d, int c, int heads,
+                              float* gx, float* red, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t adapted_skinny_pre_workspace_bytes(int c, int heads);
+int launch_adapted_skinny_pre(const uint8_t* is_src, const float* wd, const float* gates, const float* gHs, const float* gHt,
+                              long long n, int c, int heads, float* pre, void* ws, size_t ws_bytes, cudaStream_t stream);
 bool domain_colsum_supported(int d);
 size_t domain_colsum_workspace_bytes(int d);
 int launch_domain_colsum(const float* x, const uint8_t* is_src, long long n, int d, float* sums, void* ws, size_t ws_bytes,

@@ -236,23 +236,54 @@ def adapted_convs_shared_graph(convs, xs, edge_index, edge_index1, edge_index2, 
     ok = (part is None and len(widths) == 1 and len(convs) in (2, 3) and all(torch.is_tensor(x) and x.is_cuda for x in xs)
           and not any(conv.root_weight or conv.normalize for conv in convs)
           and len({conv.negative_slope for conv in convs}) == 1)
+    order = list(range(len(convs)))
     if ok:
-        shared = {}                                  # domain means per distinct input (two heads read the same x)
-        parts = []
-        for conv, x in zip(convs, xs):
-            if id(x) not in shared:
-                shared[id(x)] = conv.domain_means(x, c)
-            parts.append(conv.node_part(x, c, shared[id(x)]))
-        cp = parts[0][4]
-        ok = all(p[4] == cp for p in parts) and ops.gat_heads_supported(len(convs), cp)
+        cps = {conv._padded_params()[6] for conv in convs}
+        ok = len(cps) == 1 and ops.gat_heads_supported(len(convs), next(iter(cps)))
+    if ok:
+        cp = next(iter(cps))
+        # convs that read the same tensor form a group: one pass over x for the whole group (means included)
+        groups = {}
+        for i, x in enumerate(xs):
+            groups.setdefault(id(x), []).append(i)
+        order, hs, ht, af1, af2 = [], [], [], [], []
+        for idxs in groups.values():
+            x = xs[idxs[0]]
+            for j in range(0, len(idxs), 2):
+                sub = idxs[j: j + 2]
+                if ops.adapted_skinny_group_supported(x, cp, len(sub)):
+                    d = x.shape[1]
+                    hp = []
+                    for i in sub:
+                        w_s, w_t, b_s, b_t, _, _, _ = convs[i]._padded_params()
+                        a1, a2 = convs[i].a_g_s2t.weight, convs[i].a_g_t2s.weight
+                        hp.append((torch.cat((w_s, w_t, a1[:, :d], a2[:, :d]), 0),
+                                   None if b_s is None else torch.cat((b_s, b_t, b_s.new_zeros(2))),
+                                   torch.cat((a1[:, d:], a2[:, d:]), 0)))
+                    h_s, h_t = ops.adapted_skinny_group(x, convs[sub[0]]._dst_is_src(c), convs[sub[0]]._domain_counts(c), hp)
+                    hs.append(h_s)
+                    ht.append(h_t)
+                else:
+                    means = convs[sub[0]].domain_means(x, c)
+                    for i in sub:
+                        p = convs[i].node_part(x, c, means)
+                        hs.append(p[0])
+                        ht.append(p[1])
+                for i in sub:
+                    _, _, _, _, a_t2s, a_s2t, _ = convs[i]._padded_params()
+                    af1.append(a_t2s.reshape(-1))
+                    af2.append(a_s2t.reshape(-1))
+                    order.append(i)
     if not ok:
         return [conv(x, edge_index, edge_index1, edge_index2, c, part=part) for conv, x in zip(convs, xs)]
     graph = ops.cached_graph(edge_index, xs[0].shape[0])
-    out = ops.gat_aggregate_heads(torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts], 1),
-                                  torch.cat([p[2].reshape(-1) for p in parts]), torch.cat([p[3].reshape(-1) for p in parts]),
-                                  graph, convs[0]._dst_is_src(c), convs[0].negative_slope, len(convs))
+    out = ops.gat_aggregate_heads(torch.cat(hs, 1), torch.cat(ht, 1), torch.cat(af1), torch.cat(af2), graph,
+                                  convs[0]._dst_is_src(c), convs[0].negative_slope, len(convs))
     co = convs[0].out_channels
-    return [out[:, h * cp: h * cp + co] for h in range(len(convs))]
+    res = [None] * len(convs)
+    for pos, i in enumerate(order):                 # heads were laid out group by group
+        res[i] = out[:, pos * cp: pos * cp + co]
+    return res
 
 
 def graph_partition(edge_index, central_mask, add_self_loop=True):

@@ -735,6 +735,109 @@ def adapted_skinny(x, w_cat, bias_cat, wd, kg, is_src):
     return _AdaptedSkinnyFn.apply(x, w_cat, bias_cat, wd, kg, is_src)
 
 
+class _SkinnyGroupFn(torch.autograd.Function):
+    """Domain means + narrow node-wise transform of 1 or 2 heads over the same x, as ONE autograd node: x is read
+    by one pass each way (plus the column-sum pass of the means) and receives ONE gradient -- the part that flows
+    through the means (Delta -> wd, kg) is added inside the backward kernel instead of by a [n, d] ``where`` and an
+    accumulation pass per consumer."""
+
+    @staticmethod
+    def forward(ctx, x, is_src, inv_counts, heads, *params):
+        lib = _lib.load()
+        f32 = torch.float32
+        x = x.to(f32).contiguous()
+        n, d = x.shape
+        dev = x.device
+        ws_ = [params[3 * h].to(f32) for h in range(heads)]
+        bs_ = [params[3 * h + 1] for h in range(heads)]
+        as_ = [params[3 * h + 2].to(f32) for h in range(heads)]
+        o = ws_[0].shape[0]
+        c = (o - 2) // 2
+        sums = torch.empty((2, d), dtype=f32, device=dev)
+        wsp = _lib.workspace(lib.bgnn_domain_colsum_workspace_bytes(d), dev)
+        with _lib.call("bgnn_domain_colsum_f32"):
+            _lib.check(lib.bgnn_domain_colsum_f32(_lib.ptr(x), _lib.ptr(is_src, torch.uint8), n, d, _lib.ptr(sums),
+                                                  _lib.ptr(wsp), wsp.numel(), _lib.stream(dev)))
+        means = sums * inv_counts.view(2, 1)
+        delta = means[0] - means[1]                                        # [d]
+        wcat = torch.cat(ws_, 0).contiguous()                              # [heads*o, d]
+        atail = torch.cat(as_, 0).contiguous()                             # [heads*2, d]
+        has_bias = [b is not None for b in bs_]
+        bias = None
+        if any(has_bias):
+            bias = torch.cat([b.to(f32) if b is not None else torch.zeros(o, dtype=f32, device=dev) for b in bs_]).contiguous()
+        wd = (wcat.view(heads, o, d)[:, : 2 * c, :] @ delta).reshape(-1).contiguous()      # [heads*2c]
+        kg = (atail @ delta).contiguous()                                  # [heads*2]
+        Hs = torch.empty((n, heads * c), dtype=f32, device=dev)
+        Ht = torch.empty((n, heads * c), dtype=f32, device=dev)
+        gates = torch.empty((n, heads * 2), dtype=f32, device=dev)
+        with _lib.call("bgnn_adapted_skinny_heads_fwd_f32"):
+            _lib.check(lib.bgnn_adapted_skinny_heads_fwd_f32(_lib.ptr(x), _lib.ptr(is_src, torch.uint8), _lib.ptr(wcat),
+                                                             _lib.ptr(bias, f32, True), _lib.ptr(wd), _lib.ptr(kg), n, d, c,
+                                                             heads, _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(gates),
+                                                             _lib.stream(dev)))
+        ctx.save_for_backward(x, wcat, atail, wd, gates, is_src, delta, inv_counts)
+        ctx.meta = (heads, c, d, has_bias)
+        return Hs, Ht
+
+    @staticmethod
+    def backward(ctx, gHs, gHt):
+        lib = _lib.load()
+        x, wcat, atail, wd, gates, is_src, delta, inv_counts = ctx.saved_tensors
+        heads, c, d, has_bias = ctx.meta
+        f32 = torch.float32
+        gHs, gHt = gHs.to(f32).contiguous(), gHt.to(f32).contiguous()
+        n, dev, o = x.shape[0], x.device, 2 * c + 2
+        ws = _lib.workspace(lib.bgnn_adapted_skinny_heads_bwd_workspace_bytes(c, d, heads), dev)
+        pre = torch.empty((heads * o,), dtype=f32, device=dev)
+        with _lib.call("bgnn_adapted_skinny_heads_pre_f32"):
+            _lib.check(lib.bgnn_adapted_skinny_heads_pre_f32(_lib.ptr(is_src, torch.uint8), _lib.ptr(wd), _lib.ptr(gates),
+                                                             _lib.ptr(gHs), _lib.ptr(gHt), n, c, heads, _lib.ptr(pre),
+                                                             _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+        pre = pre.view(heads, o)
+        g_wd, g_kg = pre[:, : 2 * c], pre[:, 2 * c:]                        # [heads, 2c], [heads, 2]
+        w3, a3 = wcat.view(heads, o, d), atail.view(heads, 2, d)
+        # wd_h = W_h[:2c] delta, kg_h = A_h delta  ->  d delta, and through the two means into every row of x
+        g_delta = torch.einsum("hj,hjd->d", g_wd, w3[:, : 2 * c, :]) + torch.einsum("hk,hkd->d", g_kg, a3)
+        gm = torch.stack((g_delta * inv_counts[0], -g_delta * inv_counts[1])).contiguous()
+        gx = torch.empty_like(x)
+        red = torch.empty((heads * (o * d + o + 2 * c),), dtype=f32, device=dev)
+        with _lib.call("bgnn_adapted_skinny_heads_bwd_f32"):
+            _lib.check(lib.bgnn_adapted_skinny_heads_bwd_f32(_lib.ptr(x), _lib.ptr(is_src, torch.uint8), _lib.ptr(wcat),
+                                                             _lib.ptr(wd), _lib.ptr(gates), _lib.ptr(gHs), _lib.ptr(gHt),
+                                                             _lib.ptr(gm), n, d, c, heads, _lib.ptr(gx), _lib.ptr(red),
+                                                             _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+        g_w = red[: heads * o * d].view(heads, o, d).clone()
+        g_w[:, : 2 * c, :] += g_wd.unsqueeze(2) * delta.view(1, 1, d)       # wd = W[:2c] delta
+        colsum = red[heads * o * d: heads * o * d + heads * o].view(heads, o)
+        g_a = g_kg.unsqueeze(2) * delta.view(1, 1, d)                       # [heads, 2, d]
+        out = [gx, None, None, None]
+        for h in range(heads):
+            g_b = None
+            if has_bias[h]:
+                g_b = colsum[h].clone()
+                g_b[2 * c:] = 0.0                                           # the gate columns carry no bias parameter
+            out += [g_w[h], g_b, g_a[h]]
+        return tuple(out)
+
+
+def adapted_skinny_group_supported(x, c, heads):
+    return (x.is_cuda and x.dtype == torch.float32 and not os.environ.get("BGNN_NO_WIDE")
+            and bool(_lib.load().bgnn_adapted_skinny_heads_supported(int(c), int(x.shape[1]), int(heads)))
+            and domain_colsum_supported(x.shape[1]))
+
+
+def adapted_skinny_group(x, is_src, inv_counts, head_params):
+    """Node-wise part (models/KTGNN.py:275-284) of 1 or 2 narrow AdaptedConvs over the SAME input x, domain means
+    included.  ``head_params``: per head (w_cat [2c+2, d] = [W_s; W_t; a_g_s2t[:d]; a_g_t2s[:d]], b_cat [2c+2] or
+    None, a_tail [2, d] = [a_g_s2t[d:]; a_g_t2s[d:]]); ``inv_counts`` = (1/Ns, 1/Nt).  Returns (Hs, Ht), each
+    [n, heads*c] with the heads side by side.  Differentiable in x and every parameter."""
+    flat = []
+    for w, b, a in head_params:
+        flat += [w, b, a]
+    return _SkinnyGroupFn.apply(x, is_src, inv_counts, len(head_params), *flat)
+
+
 class _DomainMeansFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, is_src, inv_counts):

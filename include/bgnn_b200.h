@@ -232,6 +232,26 @@ int bgnn_bn_relu_apply_f32(const float* x, int64_t n, int c, const float* stats,
 int bgnn_bn_relu_bwd_f32(const float* gy, const float* x, int64_t n, int c, const float* stats, int relu, float* gx,
                          float* gwb, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The narrow transform for `heads` (1 or 2) convs that read the SAME x (the classifier heads clf_base / clf_target,
+ * models/KTGNN.py:432-434): parameters stacked per head (wcat [heads*(2c+2), d], bias [heads*(2c+2)] or NULL,
+ * wd [heads*2c], kg [heads*2]), outputs side by side (Hs, Ht [n, heads*c], gates [n, heads*2]) -- x is read once.
+ * Backward in two calls: _pre (no pass over x) gives pre [heads*(2c+2)] = per head (d wd [2c], d kg [2]); the host
+ * turns that into gm [2, d], the gradient reaching x through the source / target domain means, and _bwd adds
+ * gm[0] (source rows) / gm[1] (target rows) into gx in its single pass over x (gm may be NULL).
+ * red [heads*((2c+2)*d + (2c+2) + 2c)] = (d wcat, per head column sums (d bias, d kg), d wd). */
+int bgnn_adapted_skinny_heads_supported(int c, int d, int heads);
+int bgnn_adapted_skinny_heads_fwd_f32(const float* x, const uint8_t* is_src, const float* wcat, const float* bias,
+                                      const float* wd, const float* kg, int64_t n, int d, int c, int heads, float* Hs,
+                                      float* Ht, float* gates, void* stream);
+size_t bgnn_adapted_skinny_heads_bwd_workspace_bytes(int c, int d, int heads);
+int bgnn_adapted_skinny_heads_pre_f32(const uint8_t* is_src, const float* wd, const float* gates, const float* gHs,
+                                      const float* gHt, int64_t n, int c, int heads, float* pre, void* workspace,
+                                      size_t workspace_bytes, void* stream);
+int bgnn_adapted_skinny_heads_bwd_f32(const float* x, const uint8_t* is_src, const float* wcat, const float* wd,
+                                      const float* gates, const float* gHs, const float* gHt, const float* gm, int64_t n,
+                                      int d, int c, int heads, float* gx, float* red, void* workspace,
+                                      size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -406,6 +406,57 @@ def test_node_linear_forward_backward(n, din, dout, bias):
         assert got.grad.shape == ref.grad.shape and relclose(got.grad, ref.grad.float(), 1e-5), name
 
 
+@pytest.mark.parametrize("n,c,d,heads,bias", [(50, 1, 4, 1, True), (1000, 2, 64, 2, True), (777, 3, 100, 2, False),
+                                              (5000, 4, 128, 1, True), (3000, 2, 256, 2, True)])
+def test_adapted_skinny_group_forward_backward(n, c, d, heads, bias):
+    """Domain means + narrow transform of 1-2 heads over the same x as one autograd node == the oracle's chain
+    (means -> Delta -> wd, kg -> epilogue) differentiated by torch in float64, gradient through the means included."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(300 + n + c)
+    x = torch.randn(n, d, generator=g) + 0.5
+    cm = torch.rand(n, generator=g) < 0.7
+    cm[0], cm[1] = True, False
+    inv = torch.tensor([1.0 / float(cm.sum()), 1.0 / float((~cm).sum())])
+    hp = []
+    for _ in range(heads):
+        w = torch.randn(2 * c + 2, d, generator=g) * 0.3
+        b = torch.cat((torch.randn(2 * c, generator=g), torch.zeros(2))) if bias else None
+        a = torch.randn(2, d, generator=g) * 0.3
+        hp.append((w, b, a))
+    go_s, go_t = torch.randn(n, heads * c, generator=g), torch.randn(n, heads * c, generator=g)
+
+    xr = x.double().requires_grad_(True)
+    hpr = [tuple(None if t is None else t.double().requires_grad_(True) for t in h) for h in hp]
+    cf = cm.double()
+    means = torch.stack(((cf * inv[0].double()) @ xr, ((1 - cf) * inv[1].double()) @ xr))
+    delta = means[0] - means[1]
+    outs_s, outs_t = [], []
+    for w, b, a in hpr:
+        P = xr @ w.t() + (b if b is not None else 0.0)
+        Hs_r, Ht_r = mo.adapted_transform_epilogue(P, w[: 2 * c] @ delta, a @ delta, cm.to(torch.uint8))
+        outs_s.append(Hs_r)
+        outs_t.append(Ht_r)
+    Hs_r, Ht_r = torch.cat(outs_s, 1), torch.cat(outs_t, 1)
+    ((Hs_r * go_s).sum() + (Ht_r * go_t).sum()).backward()
+
+    xd = x.cuda().requires_grad_(True)
+    hpd = [tuple(None if t is None else t.clone().cuda().requires_grad_(True) for t in h) for h in hp]
+    assert ops.adapted_skinny_group_supported(xd, c, heads)
+    Hs, Ht = ops.adapted_skinny_group(xd, cm.to(torch.uint8).cuda(), inv.cuda(), hpd)
+    assert relclose(Hs, Hs_r.float(), 5e-6) and relclose(Ht, Ht_r.float(), 5e-6)
+    ((Hs * go_s.cuda()).sum() + (Ht * go_t.cuda()).sum()).backward()
+    assert relclose(xd.grad, xr.grad.float(), 2e-5)
+    for h in range(heads):
+        for got, ref, name in zip(hpd[h], hpr[h], ("w_cat", "b_cat", "a_tail")):
+            if got is None:
+                continue
+            rg = ref.grad.float()
+            if name == "b_cat":
+                rg = rg.clone()
+                rg[2 * c:] = 0.0
+            assert relclose(got.grad, rg, 2e-5), (h, name)
+
+
 @pytest.mark.parametrize("n,c", [(16, 4), (1000, 64), (4099, 100), (50000, 64), (3000, 256), (700, 1024)])
 @pytest.mark.parametrize("relu", [True, False])
 def test_batch_norm_relu_matches_torch(n, c, relu):

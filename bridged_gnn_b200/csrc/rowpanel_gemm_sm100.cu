@@ -10,16 +10,17 @@
 //     a.b ~= lo.b_hi + hi.b_lo + hi.b_hi       (b_hi / b_lo planes of the small operand prepared by the host)
 // so every row of A crosses HBM once and the work is bound by that stream, not by the MMAs.
 //
-// CTA = 10 warps, persistent over 128-row tiles:
+// CTA = 14 warps, persistent over 128-row tiles:
 //   warp 0     TMA producer: per k-block of 32 features the raw A tile [128 x 32] and the B_hi / B_lo planes
 //              [NOP x 32] into a ring of SWIZZLE_128B stages
-//   warps 2-5  split: rewrite the A tile in place as hi, write lo next to it (element-wise, layout-agnostic),
+//   warps 2-9  split: rewrite the A tile in place as hi, write lo next to it (element-wise, layout-agnostic),
 //              fence.proxy.async, signal the MMA issuer
 //   warp 1     TMEM allocator + single-thread tcgen05.mma (kind::tf32) issuer, 128 x NOP fp32 accumulator
 //              double-buffered in TMEM
-//   warps 6-9  epilogue: thread <-> row, tcgen05.ld 32 columns at a time, store (EPI 0) or AdaptedConv node-wise
+//   warps 10-13 epilogue: thread <-> row, tcgen05.ld 32 columns at a time, store (EPI 0) or AdaptedConv node-wise
 //              epilogue (EPI 1)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -30,7 +31,8 @@ namespace bgnn {
 constexpr int RG_BM = 128;
 constexpr int RG_BK = 32;            // fp32 elements per k-block = 128 B = one swizzle atom row
 constexpr int RG_UMMA_K = 8;         // tf32
-constexpr int RG_THREADS = 320;
+constexpr int RG_SPLIT_WARPS = 8;
+constexpr int RG_THREADS = (2 + RG_SPLIT_WARPS + 4) * 32;   // TMA, MMA, split warps, 4 epilogue warps
 constexpr int RG_A_PLANE = RG_BM * RG_BK * 4;   // 16 KB
 constexpr int RG_SMEM_MAX = 232448;
 constexpr int RG_SMEM_FIXED = 1024 + 512;
@@ -39,8 +41,8 @@ __host__ __device__ constexpr uint32_t rg_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// nearest tf32 (ties away from zero in magnitude): the tensor core truncates its fp32 inputs to 19 bits, so both
-// planes are rounded here and |a - hi| <= 2^-12 |a|, |(a - hi) - lo| <= 2^-23 |a|
+// nearest tf32 (ties away from zero in magnitude): the tensor core truncates its fp32 inputs to 19 bits, so hi is
+// rounded here (|a - hi| <= 2^-12 |a|) and lo = a - hi is left to the hardware's truncation (error <= 2^-22 |a|)
 __device__ __forceinline__ float rg_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 
 struct RgEpi {                 // EPI 1: AdaptedConv node-wise epilogue (adapted_transform.cu, fused)
@@ -82,7 +84,7 @@ rowpanel_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&ready_bar[s]), 4);
+      mbar_init(smem_u32(&ready_bar[s]), RG_SPLIT_WARPS);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 4); }
@@ -168,9 +170,10 @@ rowpanel_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         tc_commit(smem_u32(&tfull_bar[buf]));
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + RG_SPLIT_WARPS) {
     // ===================== split: a -> (hi, lo), element-wise on the swizzled tile =====================
-    const int tid = threadIdx.x - 64;               // 0..127
+    constexpr int ST = RG_SPLIT_WARPS * 32;
+    const int tid = threadIdx.x - 64;               // 0..ST-1
     int s = 0;
     uint32_t ph = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -179,13 +182,14 @@ rowpanel_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         float4* a = reinterpret_cast<float4*>(stage_base + (size_t)s * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(stage_base + (size_t)s * stage_bytes + RG_A_PLANE);
 #pragma unroll
-        for (int i = 0; i < RG_A_PLANE / 16 / 128; ++i) {
-          const float4 v = a[tid + i * 128];
+        for (int i = 0; i < RG_A_PLANE / 16 / ST; ++i) {
+          const float4 v = a[tid + i * ST];
           float4 h, l;
           h.x = rg_tf32(v.x); h.y = rg_tf32(v.y); h.z = rg_tf32(v.z); h.w = rg_tf32(v.w);
-          l.x = rg_tf32(v.x - h.x); l.y = rg_tf32(v.y - h.y); l.z = rg_tf32(v.z - h.z); l.w = rg_tf32(v.w - h.w);
-          a[tid + i * 128] = h;
-          lo[tid + i * 128] = l;
+          // a - hi is exact in fp32 and at most 2^-12 |a|; the tensor core drops its low 13 bits: <= 2^-22 |a|
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          a[tid + i * ST] = h;
+          lo[tid + i * ST] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
         __syncwarp();
@@ -292,6 +296,8 @@ static int rg_plan(int k, int no, int& nop, int& kblocks, bool& bres) {
   const int b_all = kblocks * 2 * nop * RG_BK * 4;
   int stages = (RG_SMEM_MAX - RG_SMEM_FIXED - b_all) / (2 * RG_A_PLANE);
   bres = stages >= 2;
+  static const int force_stream = getenv("BGNN_RG_STREAM") ? atoi(getenv("BGNN_RG_STREAM")) : 0;
+  if (force_stream && (RG_SMEM_MAX - RG_SMEM_FIXED) / (2 * RG_A_PLANE + 2 * nop * RG_BK * 4) > stages) bres = false;
   if (!bres) stages = (RG_SMEM_MAX - RG_SMEM_FIXED) / (2 * RG_A_PLANE + 2 * nop * RG_BK * 4);
   if (stages > 6) stages = 6;
   return stages >= 2 ? stages : 0;

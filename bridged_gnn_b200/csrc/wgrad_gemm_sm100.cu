@@ -12,7 +12,7 @@
 // writes NOTHING.  TMA has the matching mode (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): a box [32 columns x 32 rows]
 // is a column of eight such atoms, so LBO = 4096 B (next box = next 32 columns), SBO = 512 B (next 4 rows), and one
 // tf32 MMA (K = 8) eats two atoms = 1024 B.
-// Both streamed operands are split on chip (hi = tf32(a), lo = tf32(a - hi)) by four warps, element-wise and
+// Both streamed operands are split on chip (hi = tf32(a), lo = a - hi) by eight warps, element-wise and
 // therefore layout-agnostic;  D[f, j] (128 TMEM lanes x nop columns) += lo.hi + hi.lo + hi.hi.
 //
 // Persistent CTAs stride over the 32-row blocks and keep ONE accumulator for the whole kernel; each CTA then writes
@@ -28,7 +28,8 @@ namespace bgnn {
 constexpr int WG_BK = 32;              // rows per stage
 constexpr int WG_BOX = 32 * WG_BK * 4; // one TMA box: 32 columns x 32 rows fp32 = 4 KB
 constexpr int WG_MBOX = 4;             // X boxes per stage = 128 features (UMMA M)
-constexpr int WG_THREADS = 320;
+constexpr int WG_SPLIT_WARPS = 8;
+constexpr int WG_THREADS = (2 + WG_SPLIT_WARPS + 4) * 32;   // TMA, MMA, split warps, 4 epilogue warps
 constexpr int WG_SMEM_MAX = 232448;
 constexpr int WG_SMEM_FIXED = 1024 + 512;
 
@@ -73,7 +74,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&ready_bar[s]), 4);
+      mbar_init(smem_u32(&ready_bar[s]), WG_SPLIT_WARPS);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(done_bar), 1);
@@ -152,7 +153,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       }
       tc_commit(smem_u32(done_bar));
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + WG_SPLIT_WARPS) {
     // ===================== split raw -> (hi, lo) =====================
     const int tid = threadIdx.x - 64;
     const int n_f4 = (nb + mb) * WG_BOX / 16;
@@ -163,11 +164,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       float4* a = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
       float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + plane);
 #pragma unroll 4
-      for (int i = tid; i < n_f4; i += 128) {
+      for (int i = tid; i < n_f4; i += WG_SPLIT_WARPS * 32) {
         const float4 v = a[i];
         float4 h, l;
         h.x = wg_tf32(v.x); h.y = wg_tf32(v.y); h.z = wg_tf32(v.z); h.w = wg_tf32(v.w);
-        l.x = wg_tf32(v.x - h.x); l.y = wg_tf32(v.y - h.y); l.z = wg_tf32(v.z - h.z); l.w = wg_tf32(v.w - h.w);
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;      // the tensor core truncates: <= 2^-22 |a|
         a[i] = h;
         lo[i] = l;
       }

@@ -10,14 +10,14 @@
 //     a.b ~= lo.b_hi + hi.b_lo + hi.b_hi       (b_hi / b_lo planes of the small operand prepared by the host)
 // so every row of A crosses HBM once and the work is bound by that stream, not by the MMAs.
 //
-// CTA = 14 warps, persistent over 128-row tiles:
+// CTA = 10 warps, persistent over 128-row tiles:
 //   warp 0     TMA producer: per k-block of 32 features the raw A tile [128 x 32] and the B_hi / B_lo planes
 //              [NOP x 32] into a ring of SWIZZLE_128B stages
-//   warps 2-9  split: rewrite the A tile in place as hi, write lo next to it (element-wise, layout-agnostic),
+//   warps 2-5  split: rewrite the A tile in place as hi, write lo next to it (element-wise, layout-agnostic),
 //              fence.proxy.async, signal the MMA issuer
 //   warp 1     TMEM allocator + single-thread tcgen05.mma (kind::tf32) issuer, 128 x NOP fp32 accumulator
 //              double-buffered in TMEM
-//   warps 10-13 epilogue: thread <-> row, tcgen05.ld 32 columns at a time, store (EPI 0) or AdaptedConv node-wise
+//   warps 6-9  epilogue: thread <-> row, tcgen05.ld 32 columns at a time, store (EPI 0) or AdaptedConv node-wise
 //              epilogue (EPI 1)
 #include <cuda.h>
 #include <stdlib.h>
@@ -31,11 +31,12 @@ namespace bgnn {
 constexpr int RG_BM = 128;
 constexpr int RG_BK = 32;            // fp32 elements per k-block = 128 B = one swizzle atom row
 constexpr int RG_UMMA_K = 8;         // tf32
-constexpr int RG_SPLIT_WARPS = 8;
+constexpr int RG_SPLIT_WARPS = 4;
 constexpr int RG_THREADS = (2 + RG_SPLIT_WARPS + 4) * 32;   // TMA, MMA, split warps, 4 epilogue warps
 constexpr int RG_A_PLANE = RG_BM * RG_BK * 4;   // 16 KB
 constexpr int RG_SMEM_MAX = 232448;
-constexpr int RG_SMEM_FIXED = 1024 + 512;
+constexpr int RG_EPI_STAGE = 4 * 32 * 32 * 4;      // epilogue staging tiles
+constexpr int RG_SMEM_FIXED = 1024 + 512 + RG_EPI_STAGE;
 
 __host__ __device__ constexpr uint32_t rg_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -56,6 +57,38 @@ struct RgEpi {                 // EPI 1: AdaptedConv node-wise epilogue (adapted
   int c;
 };
 
+// Epilogue store of one 32 x 32 block: the thread <-> row registers go through a 4 KB per-warp staging tile (16-byte
+// chunks XOR row & 7: conflict-free both ways) so that every global store instruction writes four full 128-byte row
+// segments instead of 32 scattered 16-byte pieces.
+__device__ __forceinline__ void rg_store_block(float* stg, const float* r, int lane, float* __restrict__ out, long long row0,
+                                               long long n, int ld, int col0, int ncols) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+  __syncwarp();
+  const int q = lane & 7, sub = lane >> 3;
+  const int col = col0 + q * 4;
+  const bool vec = (ld & 3) == 0 && col + 4 <= ncols;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + sub;
+    const float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((q ^ (rr & 7)) << 2));
+    const long long row = row0 + rr;
+    if (row < n) {
+      float* y = out + row * ld + col;
+      if (vec) {
+        *reinterpret_cast<float4*>(y) = v;
+      } else {
+        if (col < ncols) y[0] = v.x;
+        if (col + 1 < ncols) y[1] = v.y;
+        if (col + 2 < ncols) y[2] = v.z;
+        if (col + 3 < ncols) y[3] = v.w;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // BRES: the B planes of ALL k-blocks stay resident in shared memory (loaded once per CTA); otherwise they travel with
 // every stage.
 template <int EPI, bool BRES>
@@ -69,7 +102,8 @@ rowpanel_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int stage_bytes = 2 * RG_A_PLANE + (BRES ? 0 : 2 * b_plane);   // A (-> hi), A lo [, B hi, B lo]; multiples of 1024
   unsigned char* stage_base = smem;
   unsigned char* bres_base = smem + (size_t)stages * stage_bytes;       // BRES: [kblocks][hi, lo]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bres_base + (BRES ? (size_t)kblocks * 2 * b_plane : 0));
+  float* epi_stage = reinterpret_cast<float*>(bres_base + (BRES ? (size_t)kblocks * 2 * b_plane : 0));   // 4 warps x 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(epi_stage) + RG_EPI_STAGE);
   uint64_t* full_bar = bars;                    // [stages] TMA landed
   uint64_t* ready_bar = bars + stages;          // [stages] split done (4 warps)
   uint64_t* empty_bar = bars + 2 * stages;      // [stages] MMAs retired
@@ -208,8 +242,10 @@ rowpanel_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       mbar_wait(smem_u32(&tfull_bar[buf]), tph);
       tc_fence_after();
       const long long row = t * RG_BM + r_in_tile;
+      const long long row0 = t * RG_BM + quarter * 32;
       const bool row_ok = row < n;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256);
+      float* stg = epi_stage + quarter * (32 * 32);
       float r[32];
       if (EPI == 0) {
         for (int c0 = 0; c0 < nop; c0 += 32) {
@@ -219,16 +255,7 @@ rowpanel_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
             for (int k = 0; k < 32; ++k) r[k] += (c0 + k < no) ? __ldg(ep.bias + c0 + k) : 0.f;
           }
-          if (row_ok) {
-            float* y = Y + row * ldy + c0;
-            if ((ldy & 3) == 0 && c0 + 32 <= no) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) reinterpret_cast<float4*>(y)[k] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 32; ++k) if (c0 + k < no) y[k] = r[k];
-            }
-          }
+          rg_store_block(stg, r, lane, Y, row0, n, ldy, c0, no);
         }
       } else {
         // columns [0,C) = x W_s^T, [C,2C) = x W_t^T, 2C / 2C+1 = gate logits (C a multiple of 32)
@@ -238,25 +265,16 @@ rowpanel_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const bool src = row_ok ? (ep.is_src[row] != 0) : false;
         const float g0 = tanhf(r[0] + __ldg(ep.kg)), g1 = tanhf(r[1] + __ldg(ep.kg + 1));
         const float fs = src ? 0.f : g1, ft = src ? -g0 : 0.f;
-        if (row_ok) { ep.gates[row * 2] = g0; ep.gates[row * 2 + 1] = g1; }
+        if (row_ok) *reinterpret_cast<float2*>(ep.gates + row * 2) = make_float2(g0, g1);
         for (int c0 = 0; c0 < 2 * c; c0 += 32) {
           tc_ld32(taddr0 + (uint32_t)c0, r);
           tc_wait_ld();
-          if (row_ok) {
-            const bool second = c0 >= c;
-            const float f = second ? ft : fs;
-            float* y = (second ? ep.Ht + row * c + (c0 - c) : ep.Hs + row * c + c0);
+          const bool second = c0 >= c;
+          const float f = second ? ft : fs;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              float o[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int col = c0 + 4 * k + q;     // column of P = index into wd / bias
-                o[q] = fmaf(f, __ldg(ep.wd + col), r[4 * k + q] + (ep.bias ? __ldg(ep.bias + col) : 0.f));
-              }
-              reinterpret_cast<float4*>(y)[k] = make_float4(o[0], o[1], o[2], o[3]);
-            }
-          }
+          for (int k = 0; k < 32; ++k)      // c0 + k = column of P = index into wd / bias
+            r[k] = fmaf(f, __ldg(ep.wd + c0 + k), r[k] + (ep.bias ? __ldg(ep.bias + c0 + k) : 0.f));
+          rg_store_block(stg, r, lane, second ? ep.Ht : ep.Hs, row0, n, c, second ? c0 - c : c0, c);
         }
       }
       tc_fence_before();

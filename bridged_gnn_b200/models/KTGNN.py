@@ -315,6 +315,18 @@ class _KTGNNBase(nn.Module):
             self.edge_index1, self.edge_index2, self.edge_index = graph_partition(data.edge_index, data.central_mask)
         return self.edge_index1, self.edge_index2, self.edge_index
 
+    def prepare_graph(self, data):
+        """Everything of a forward / backward pass that depends on the graph alone (models/KTGNN.py:385-398
+        graph_partition, then the CSR, transposed CSR and row orders of the aggregation kernels), cached for the
+        calls that follow.  ``data`` needs ``edge_index`` and ``central_mask`` only: a serving loop can call this
+        while ``data.x`` is still being copied to the device on another stream."""
+        _, _, ei = self._edges(data)
+        ops.cached_graph(ei, data.central_mask.shape[0]).prepare(training=self.training and torch.is_grad_enabled())
+        for conv in list(self.convs) + [m for m in self.children() if isinstance(m, AdaptedConv)]:
+            conv._dst_is_src(data.central_mask)
+            conv._domain_counts(data.central_mask)
+        return self
+
     def _hidden(self, x, ei, ei1, ei2, c, n_convs, part=None):
         if part is not None and self.use_bn and self.training and part.n_pad != part.n:
             raise NotImplementedError("partitioned training with BatchNorm needs num_nodes % world_size == 0 "

@@ -180,6 +180,18 @@ class CSRGraph:
             self._t_order = rows_by_degree(self.t[0], self.n, 0)
         return self._t_order
 
+    def prepare(self, training=True, wide=True):
+        """Builds now what the aggregation kernels would build lazily on first use: the processing orders and, for
+        training, the transposed CSR and the CSR -> CSC slot map.  Needs only the edge list, so a caller can run it
+        while the node features are still on their way to the device."""
+        if wide:
+            self.order(WIDE_ROW)
+        if training:
+            self.csr_to_csc          # builds self.t too
+            if wide:
+                self.t_order(WIDE_ROW)
+        return self
+
     @property
     def deg(self):
         if self._deg is None:

@@ -651,7 +651,12 @@ def test_ktgnn_model_eval_and_train_match_reference(office_mp, office_build):
     model.train()
     model.dropout = 0.0
     model.zero_grad()
+    model.edge_index = None
+    model.prepare_graph(data)             # partition + CSR / transposed CSR / row orders ahead of the forward
+    graph = _ops().cached_graph(model.edge_index, data.x.shape[0])
+    assert graph._t is not None and graph._csr_to_csc is not None and graph._order is not None
     lb, lt, ltt, _ = model(data)
+    assert _ops().cached_graph(model.edge_index, data.x.shape[0]) is graph
     tm = data.train_mask
     nll = torch.nn.functional.nll_loss
     loss = nll(lb[tm], data.y[tm]) + nll(lt[tm], data.y[tm]) + nll(ltt[tm], data.y[tm])

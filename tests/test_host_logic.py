@@ -208,3 +208,33 @@ def test_device_f1_matches_sklearn():
         assert abs(_f1_macro(y, p, nc) - f1_score(y.numpy(), p.numpy(), average="macro")) < 1e-6
     y, p = torch.tensor([0, 0, 3, 3]), torch.tensor([0, 3, 3, 3])      # classes 1, 2 absent from both
     assert abs(_f1_macro(y, p, 5) - f1_score(y.numpy(), p.numpy(), average="macro")) < 1e-6
+
+
+def test_tf32_planes_reconstruct_the_matrix():
+    """Host-side operand split of the 3 x TF32 GEMMs: both planes are exactly representable in tf32 (low 13 mantissa
+    bits zero), zero padded to (16, 32) multiples, and hi + lo reproduces w to 2^-22 relative."""
+    from bridged_gnn_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(130, 100, generator=g) * torch.exp(3 * torch.randn(130, 1, generator=g))
+    hi, lo = ops.tf32_planes(w)
+    assert hi.shape == (144, 128) and lo.shape == (144, 128)
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0 and int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert float(hi[130:].abs().max()) == 0.0 and float(hi[:, 100:].abs().max()) == 0.0
+    rec = (hi.double() + lo.double())[:130, :100]
+    assert float(((rec - w.double()).abs() / w.double().abs()).max()) <= 2.0 ** -22
+    assert float(((hi[:130, :100].double() - w.double()).abs() / w.double().abs()).max()) <= 2.0 ** -11
+
+
+def test_run_sequential_pairs_batchnorm_with_relu_on_cpu():
+    """clf_transformer on CPU tensors goes through the modules themselves (no CUDA library involved) and equals
+    nn.Sequential's own forward; NodeLinear keeps nn.Linear's parameters and state_dict keys."""
+    from bridged_gnn_b200.models.KTGNN import NodeLinear, run_sequential
+    torch.manual_seed(0)
+    seq = torch.nn.Sequential(NodeLinear(8, 8), torch.nn.BatchNorm1d(8), torch.nn.ReLU(), NodeLinear(8, 8))
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.BatchNorm1d(8), torch.nn.ReLU(), torch.nn.Linear(8, 8))
+    assert list(seq.state_dict().keys()) == list(ref.state_dict().keys())
+    ref.load_state_dict(seq.state_dict())
+    x = torch.randn(50, 8)
+    assert torch.allclose(run_sequential(seq, x), ref(x), atol=1e-6)
+    seq.eval(), ref.eval()
+    assert torch.allclose(run_sequential(seq, x), ref(x), atol=1e-6)

@@ -12,11 +12,12 @@
 // writes NOTHING.  TMA has the matching mode (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): a box [32 columns x 32 rows]
 // is a column of eight such atoms, so LBO = 4096 B (next box = next 32 columns), SBO = 512 B (next 4 rows), and one
 // tf32 MMA (K = 8) eats two atoms = 1024 B.
-// Both streamed operands are split on chip (hi = tf32(a), lo = a - hi) by eight warps, element-wise and
+// Both streamed operands are split on chip (hi = tf32(a), lo = tf32(a - hi)) by eight warps, element-wise and
 // therefore layout-agnostic;  D[f, j] (128 TMEM lanes x nop columns) += lo.hi + hi.lo + hi.hi.
 //
-// Persistent CTAs stride over the 32-row blocks and keep ONE accumulator for the whole kernel; each CTA then writes
-// its partial [128, nop] and a second kernel adds the partials in CTA order (deterministic) into W (transposed).
+// Persistent CTAs stride over the 32-row blocks; the 128 x nop accumulator is double-buffered in TMEM and flushed
+// every WG_FLUSH blocks into the CTA's fp32 partial [128, nop] (see the epilogue), and a second kernel adds the
+// partials in CTA order, in double, into W (transposed).  Deterministic.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -32,6 +33,7 @@ constexpr int WG_SPLIT_WARPS = 8;
 constexpr int WG_THREADS = (2 + WG_SPLIT_WARPS + 4) * 32;   // TMA, MMA, split warps, 4 epilogue warps
 constexpr int WG_SMEM_MAX = 232448;
 constexpr int WG_SMEM_FIXED = 1024 + 512;
+constexpr int WG_FLUSH = 16;            // K-blocks (512 rows) accumulated in TMEM before the tile is added to the CTA's fp32 partial
 
 __host__ __device__ constexpr uint32_t wg_idesc_tf32_mn(int m, int n) {
   // D fp32, A/B tf32, both MN-major (bits 15, 16)
@@ -66,8 +68,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   uint64_t* full_bar = bars;
   uint64_t* ready_bar = bars + stages;
   uint64_t* empty_bar = bars + 2 * stages;
-  uint64_t* done_bar = bars + 3 * stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 1);
+  uint64_t* tfull_bar = bars + 3 * stages;       // [2] accumulator buffer ready for the epilogue
+  uint64_t* tempty_bar = bars + 3 * stages + 2;  // [2] drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -77,12 +80,12 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       mbar_init(smem_u32(&ready_bar[s]), WG_SPLIT_WARPS);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(done_bar), 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(256u) : "memory");
+                 "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (mb < WG_MBOX) {        // zero the X boxes no TMA ever writes (both planes, every stage)
@@ -131,27 +134,35 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       const uint32_t idesc = wg_idesc_tf32_mn(128, nop);
       int s = 0;
       uint32_t ph = 0;
-      uint32_t acc = 0;
-      for (long long b = blockIdx.x; b < nblocks; b += gridDim.x) {
+      int lb = 0;                       // this CTA's block counter; WG_FLUSH blocks share one accumulator buffer
+      for (long long b = blockIdx.x; b < nblocks; b += gridDim.x, ++lb) {
+        const int grp = lb / WG_FLUSH, buf = grp & 1;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+        const bool first = lb % WG_FLUSH == 0;
+        if (first) {
+          mbar_wait(smem_u32(&tempty_bar[buf]), (((uint32_t)(grp >> 1)) & 1u) ^ 1u);
+          tc_fence_after();
+        }
         mbar_wait(smem_u32(&ready_bar[s]), ph);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
         const uint64_t g_hi = wg_mn_desc(st), x_hi = wg_mn_desc(st + nb * WG_BOX);
         const uint64_t g_lo = wg_mn_desc(st + plane), x_lo = wg_mn_desc(st + plane + nb * WG_BOX);
+        uint32_t acc = first ? 0u : 1u;
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
           const uint64_t ad = (p == 0) ? x_lo : x_hi;      // A = X (M = features), B = G (N = output columns)
           const uint64_t bd = (p == 1) ? g_lo : g_hi;
 #pragma unroll
           for (int ks = 0; ks < WG_BK / 8; ++ks) {
-            tc_mma_tf32(tmem_base, ad + (uint64_t)(ks * (1024 >> 4)), bd + (uint64_t)(ks * (1024 >> 4)), idesc, acc);
+            tc_mma_tf32(d_tmem, ad + (uint64_t)(ks * (1024 >> 4)), bd + (uint64_t)(ks * (1024 >> 4)), idesc, acc);
             acc = 1u;
           }
         }
         tc_commit(smem_u32(&empty_bar[s]));
+        if (lb % WG_FLUSH == WG_FLUSH - 1 || b + gridDim.x >= nblocks) tc_commit(smem_u32(&tfull_bar[buf]));
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
-      tc_commit(smem_u32(done_bar));
     }
   } else if (warp < 2 + WG_SPLIT_WARPS) {
     // ===================== split raw -> (hi, lo) =====================
@@ -168,7 +179,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const float4 v = a[i];
         float4 h, l;
         h.x = wg_tf32(v.x); h.y = wg_tf32(v.y); h.z = wg_tf32(v.z); h.w = wg_tf32(v.w);
-        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;      // the tensor core truncates: <= 2^-22 |a|
+        l.x = wg_tf32(v.x - h.x); l.y = wg_tf32(v.y - h.y); l.z = wg_tf32(v.z - h.z); l.w = wg_tf32(v.w - h.w);
         a[i] = h;
         lo[i] = l;
       }
@@ -179,31 +190,51 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
   } else {
     // ===================== epilogue: the CTA's partial, thread <-> feature row =====================
+    // The tensor core's fp32 accumulation is not round-to-nearest: over the ~2700 accumulations a CTA would chain at
+    // n = 1e6 the error grew to 3e-7 of sum |g||x| (20 x an fp32 FMA chain).  Every WG_FLUSH blocks the tile is
+    // therefore added (fp32, round to nearest, fixed order) to the CTA's partial in global memory -- L2-resident --
+    // while the MMAs continue in the other TMEM buffer.
     const int quarter = warp & 3;
     const int f = quarter * 32 + lane;
-    float* out = part + ((size_t)blockIdx.x * 128 + f) * nop;
-    if ((long long)blockIdx.x < nblocks) {
-      mbar_wait(smem_u32(done_bar), 0u);
+    // partial layout [cta][column quad q = j / 4][feature f][4]: the 128 epilogue threads (one per f) touch 2 KB
+    // contiguous per quad, so the read-modify-write of a flush is coalesced
+    float4* out4 = reinterpret_cast<float4*>(part + (size_t)blockIdx.x * 128 * nop) + f;
+    const long long mine = (long long)blockIdx.x < nblocks ? (nblocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int ngroups = (int)((mine + WG_FLUSH - 1) / WG_FLUSH);
+    for (int grp = 0; grp < ngroups; ++grp) {
+      const int buf = grp & 1;
+      mbar_wait(smem_u32(&tfull_bar[buf]), ((uint32_t)(grp >> 1)) & 1u);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256);
       float r[32];
       for (int c0 = 0; c0 < nop; c0 += 32) {
         tc_ld32(taddr0 + (uint32_t)c0, r);
         tc_wait_ld();
+        float4* o4 = out4 + (size_t)(c0 >> 2) * 128;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) reinterpret_cast<float4*>(out + c0)[k] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+        for (int k = 0; k < 8; ++k) {
+          float4 v = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+          if (grp > 0) {
+            const float4 old = o4[k * 128];
+            v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+          }
+          o4[k * 128] = v;
+        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
-// W[j * ldw + f] = sum over CTAs (in order) of part[cta][f][j];  colsum[j] = the same for the all-ones feature row
+// W[j * ldw + f] = sum over CTAs (in order, in double) of part[cta](f, j);  colsum[j] = the same for the all-ones feature row
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int nop, int no, int d, float* __restrict__ W, int ldw,
                     float* __restrict__ colsum, int f_ones) {
@@ -213,10 +244,11 @@ wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int nop, int no,
   const int j = idx - f * no;
   const bool extra = f == d;
   if (extra) f = f_ones;
-  float acc = 0.f;
-  for (int p = 0; p < nparts; ++p) acc += part[((size_t)p * 128 + f) * nop + j];
-  if (extra) colsum[j] = acc;
-  else W[(size_t)j * ldw + f] = acc;
+  double acc = 0.0;
+  const size_t at = ((size_t)(j >> 2) * 128 + f) * 4 + (j & 3);       // [quad][feature][4] inside a CTA's partial
+  for (int p = 0; p < nparts; ++p) acc += (double)part[(size_t)p * 128 * nop + at];
+  if (extra) colsum[j] = (float)acc;
+  else W[(size_t)j * ldw + f] = (float)acc;
 }
 
 static int wg_make_map(CUtensorMap* m, const float* base, long long rows, int cols, int ld) {

@@ -378,6 +378,24 @@ def test_wgrad_gemm_matches_float64(n, no, d):
         assert float(((cs.cpu().double() - ref_cs).abs() / G.double().abs().sum(0).clamp(min=1e-30)).max()) < 2e-6
 
 
+def test_wgrad_gemm_long_reduction_keeps_fp32_accuracy():
+    """1e6-row reduction with heavy cancellation (the training shape): the tensor core's fp32 accumulation is not
+    round-to-nearest, so the kernel flushes its TMEM accumulator into an fp32 partial every 512 rows; the result has
+    to stay at the accuracy of an fp32 FMA GEMM (measured 1.9e-8 of sum |g||x| against cuBLAS' 1.4e-8; one
+    accumulator for the whole kernel gave 2.7e-7) and within 1e-5 of max |ref|."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 1 << 20
+    G = torch.randn(n, 64, device="cuda", generator=g) * 1e-3
+    X = torch.randn(n, 64, device="cuda", generator=g)
+    W = ops.wgrad_gemm(G, X)
+    ref = G.double().t() @ X.double()
+    scale = G.double().abs().t() @ X.double().abs()
+    err = (W.double() - ref).abs()
+    assert float((err / scale).max()) < 6e-8
+    assert float(err.max() / ref.abs().max()) < 1e-5
+
+
 def test_wgrad_gemm_rejects_what_tma_cannot_address():
     ops = _ops()
     G, X = torch.randn(64, 10).cuda(), torch.randn(64, 16).cuda()

@@ -32,6 +32,31 @@ __device__ __forceinline__ unsigned sk_group_mask(int lane) {
   return G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
 }
 
+// Transposed reduction: V values per lane, G lanes per row.  Each step halves both the lane distance and the number of
+// values a lane still carries (the upper lanes keep the upper half), so V - 1 + log2(G / V) shuffles do what a
+// butterfly per value does with V log2(G); afterwards lane l of the group holds the complete sum of value l / (G / V).
+template <int S, int CNT>
+__device__ __forceinline__ void sk_tr_step(float* a, int lane_g, unsigned mask) {
+  if constexpr (S >= 1) {
+    if constexpr (CNT > 1) {
+      constexpr int H = CNT / 2;
+      const bool upper = (lane_g & S) != 0;
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const float send = upper ? a[i] : a[i + H];
+        const float keep = upper ? a[i + H] : a[i];
+        a[i] = keep + __shfl_xor_sync(mask, send, S);
+      }
+      sk_tr_step<S / 2, H>(a, lane_g, mask);
+    } else {
+      a[0] += __shfl_xor_sync(mask, a[0], S);
+      sk_tr_step<S / 2, 1>(a, lane_g, mask);
+    }
+  }
+}
+
+__host__ __device__ constexpr int sk_pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
 // HEADS convs that read the SAME x (classifier heads, models/KTGNN.py:432-434) are served by one pass: their weight
 // rows are stacked (wcat [HEADS*O, d], bias [HEADS*O], wd [HEADS*2C], kg [HEADS*2]) and the outputs lie side by side
 // (Hs, Ht [n, HEADS*C], gates [n, HEADS*2]) -- the layout the multi-head aggregation kernel takes.
@@ -65,9 +90,10 @@ adapted_skinny_fwd_kernel(const float* __restrict__ x, const uint8_t* __restrict
       xc[k] = xn[k];
       if (row + groups < n && c0 < d) xn[k] = __ldg(reinterpret_cast<const float4*>(x + (row + groups) * d + c0));
     }
-    float acc[OT];
+    constexpr int V = sk_pow2_ceil(OT);
+    float acc[V];
 #pragma unroll
-    for (int o = 0; o < OT; ++o) acc[o] = 0.f;
+    for (int o = 0; o < V; ++o) acc[o] = 0.f;
 #pragma unroll
     for (int k = 0; k < CHD; ++k) {
       const int c0 = (lane_g + k * G) * 4;
@@ -80,24 +106,48 @@ adapted_skinny_fwd_kernel(const float* __restrict__ x, const uint8_t* __restrict
         }
       }
     }
-#pragma unroll
-    for (int o = 0; o < OT; ++o)
-#pragma unroll
-      for (int s = G / 2; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(mask, acc[o], s);
-    if (lane_g == 0) {
-      const bool src = is_src[row] != 0;
-#pragma unroll
-      for (int h = 0; h < HEADS; ++h) {
-        const float* a = acc + h * O;
-        const float g0 = tanhf(a[2 * C] + __ldg(kg + 2 * h)), g1 = tanhf(a[2 * C + 1] + __ldg(kg + 2 * h + 1));
-        const float fs = src ? 0.f : g1, ft = src ? -g0 : 0.f;
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-          Hs[(row * HEADS + h) * C + j] = fmaf(fs, __ldg(wd + h * 2 * C + j), a[j] + (bias ? __ldg(bias + h * O + j) : 0.f));
-          Ht[(row * HEADS + h) * C + j] = fmaf(ft, __ldg(wd + h * 2 * C + C + j), a[C + j] + (bias ? __ldg(bias + h * O + C + j) : 0.f));
+    if constexpr (V <= G && G >= 8) {
+      // one value per lane after the transposed reduction; the lane that owns an output computes and stores it
+      sk_tr_step<G / 2, V>(acc, lane_g, mask);
+      constexpr int R = G / V;
+      const int v = lane_g / R;                        // index of the value this lane holds
+      const int h = v < OT ? v / O : 0, o = v - h * O;
+      const int base = lane - lane_g;                  // first lane of the group inside the warp
+      const float g0raw = __shfl_sync(mask, acc[0], base + (h * O + 2 * C) * R);
+      const float g1raw = __shfl_sync(mask, acc[0], base + (h * O + 2 * C + 1) * R);
+      if (v < OT && lane_g % R == 0) {
+        const bool src = is_src[row] != 0;
+        if (o < C) {
+          const float fs = src ? 0.f : tanhf(g1raw + __ldg(kg + 2 * h + 1));
+          Hs[(row * HEADS + h) * C + o] = fmaf(fs, __ldg(wd + h * 2 * C + o), acc[0] + (bias ? __ldg(bias + h * O + o) : 0.f));
+        } else if (o < 2 * C) {
+          const float ft = src ? -tanhf(g0raw + __ldg(kg + 2 * h)) : 0.f;
+          Ht[(row * HEADS + h) * C + o - C] = fmaf(ft, __ldg(wd + h * 2 * C + o), acc[0] + (bias ? __ldg(bias + h * O + o) : 0.f));
+        } else {
+          gates[(row * HEADS + h) * 2 + (o - 2 * C)] = tanhf(acc[0] + __ldg(kg + 2 * h + (o - 2 * C)));
         }
-        gates[(row * HEADS + h) * 2] = g0;
-        gates[(row * HEADS + h) * 2 + 1] = g1;
+      }
+    } else {
+      // few lanes per row or more values than lanes: a butterfly per value, lane 0 of the group finishes the row
+#pragma unroll
+      for (int o = 0; o < OT; ++o)
+#pragma unroll
+        for (int s = G / 2; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(mask, acc[o], s);
+      if (lane_g == 0) {
+        const bool src = is_src[row] != 0;
+#pragma unroll
+        for (int h = 0; h < HEADS; ++h) {
+          const float* a = acc + h * O;
+          const float g0 = tanhf(a[2 * C] + __ldg(kg + 2 * h)), g1 = tanhf(a[2 * C + 1] + __ldg(kg + 2 * h + 1));
+          const float fs = src ? 0.f : g1, ft = src ? -g0 : 0.f;
+#pragma unroll
+          for (int j = 0; j < C; ++j) {
+            Hs[(row * HEADS + h) * C + j] = fmaf(fs, __ldg(wd + h * 2 * C + j), a[j] + (bias ? __ldg(bias + h * O + j) : 0.f));
+            Ht[(row * HEADS + h) * C + j] = fmaf(ft, __ldg(wd + h * 2 * C + C + j), a[C + j] + (bias ? __ldg(bias + h * O + C + j) : 0.f));
+          }
+          gates[(row * HEADS + h) * 2] = g0;
+          gates[(row * HEADS + h) * 2 + 1] = g1;
+        }
       }
     }
   }

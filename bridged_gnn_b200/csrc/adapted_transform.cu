@@ -49,7 +49,7 @@ template <int G, int CPL>   // CPL = columns per lane = ceil(C / G)
 __global__ void __launch_bounds__(AT_THREADS)
 adapted_transform_bwd_kernel(const float* __restrict__ gHs, const float* __restrict__ gHt, const float* __restrict__ gates,
                              const uint8_t* __restrict__ is_src, const float* __restrict__ wd, long long n, int c, int ldp,
-                             float* __restrict__ gP, float* __restrict__ part) {
+                             int copy, float* __restrict__ gP, float* __restrict__ part) {
   extern __shared__ float s_part[];       // [groups][4C+2]: d wd (2C), d kg (2), column sums of dHs, dHt = d bias (2C)
   constexpr int GROUPS = AT_THREADS / G;
   const int lane_g = threadIdx.x % G, grp = threadIdx.x / G;
@@ -78,8 +78,10 @@ adapted_transform_bwd_kernel(const float* __restrict__ gHs, const float* __restr
       const int j = lane_g + k * G;
       if (valid && j < c) {
         const float a = __ldg(gHs + row * c + j), b = __ldg(gHt + row * c + j);
-        gP[row * ldp + j] = a;
-        gP[row * ldp + c + j] = b;
+        if (copy) {
+          gP[row * ldp + j] = a;
+          gP[row * ldp + c + j] = b;
+        }
         ds = fmaf(a, ws[k], ds);
         dt = fmaf(b, wt[k], dt);
         as_[k] = fmaf(fs, a, as_[k]);
@@ -96,8 +98,9 @@ adapted_transform_bwd_kernel(const float* __restrict__ gHs, const float* __restr
     if (valid && lane_g == 0) {
       const float d0 = (src ? -dt : 0.f) * (1.f - g0 * g0);
       const float d1 = (src ? 0.f : ds) * (1.f - g1 * g1);
-      gP[row * ldp + 2 * c] = d0;
-      gP[row * ldp + 2 * c + 1] = d1;
+      const int goff = copy ? 2 * c : 0;       // gates only: gP is a compact [n, ldp] buffer with (d0, d1) in front
+      gP[row * ldp + goff] = d0;
+      gP[row * ldp + goff + 1] = d1;
       k0 += d0; k1 += d1;
     }
   }
@@ -162,11 +165,11 @@ constexpr int AT_BWD_CTAS = kNumSMs * 4;
 size_t adapted_transform_bwd_workspace_bytes(int c) { return (size_t)AT_BWD_CTAS * (4 * c + 2) * sizeof(float) + 256; }
 
 int launch_adapted_transform_bwd(const float* gHs, const float* gHt, const float* gates, const uint8_t* is_src,
-                                 const float* wd, long long n, int c, int ldp, float* gP, float* g_wd_kg, void* ws,
-                                 size_t ws_bytes, cudaStream_t stream) {
+                                 const float* wd, long long n, int c, int ldp, int copy, float* gP, float* g_wd_kg,
+                                 void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (n <= 0) return BGNN_OK;
   if (c > 512) return BGNN_ERR_UNSUPPORTED;
-  if (ldp < 2 * c + 2) return BGNN_ERR_INVALID_ARG;
+  if (ldp < (copy ? 2 * c + 2 : 2)) return BGNN_ERR_INVALID_ARG;
   if (ws_bytes < adapted_transform_bwd_workspace_bytes(c)) return BGNN_ERR_WORKSPACE;
   float* part = reinterpret_cast<float*>(ws);
   const int g = pick_g(c);
@@ -178,7 +181,7 @@ int launch_adapted_transform_bwd(const float* gHs, const float* gHt, const float
   do {                                                                                                              \
     auto kern = adapted_transform_bwd_kernel<G_, CPL_>;                                                             \
     BGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));               \
-    kern<<<AT_BWD_CTAS, AT_THREADS, dyn, stream>>>(gHs, gHt, gates, is_src, wd, n, c, ldp, gP, part);                    \
+    kern<<<AT_BWD_CTAS, AT_THREADS, dyn, stream>>>(gHs, gHt, gates, is_src, wd, n, c, ldp, copy, gP, part);                    \
   } while (0)
   if (g < 32) {
     switch (g) {

@@ -330,7 +330,7 @@ int bgnn_adapted_transform_bwd_f32(const float* gHs, const float* gHt, const flo
                                    size_t workspace_bytes, void* stream) {
   if (n < 0 || c <= 0 || ldp < 2 * c + 2) return BGNN_ERR_INVALID_ARG;
   if (n > 0 && (!gHs || !gHt || !gates || !is_src || !wd || !gP || !g_wd_kg || !workspace)) return BGNN_ERR_INVALID_ARG;
-  return launch_adapted_transform_bwd(gHs, gHt, gates, is_src, wd, n, c, ldp, gP, g_wd_kg, workspace, workspace_bytes,
+  return launch_adapted_transform_bwd(gHs, gHt, gates, is_src, wd, n, c, ldp, 1, gP, g_wd_kg, workspace, workspace_bytes,
                                       (cudaStream_t)stream);
 }
 
@@ -494,6 +494,29 @@ int bgnn_adapted_skinny_heads_bwd_f32(const float* x, const uint8_t* is_src, con
     return BGNN_ERR_INVALID_ARG;
   return launch_adapted_skinny_bwd(x, is_src, wcat, wd, gates, gHs, gHt, gm, n, d, c, heads, gx, red, workspace,
                                    workspace_bytes, (cudaStream_t)stream);
+}
+
+int bgnn_adapted_transform_bwd_gates_f32(const float* gHs, const float* gHt, const float* gates, const uint8_t* is_src,
+                                         const float* wd, int64_t n, int c, float* dg, float* g_wd_kg, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  if (n < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!gHs || !gHt || !gates || !is_src || !wd || !dg || !g_wd_kg || !workspace)) return BGNN_ERR_INVALID_ARG;
+  return launch_adapted_transform_bwd(gHs, gHt, gates, is_src, wd, n, c, 4, 0, dg, g_wd_kg, workspace, workspace_bytes,
+                                      (cudaStream_t)stream);
+}
+
+int bgnn_wgrad_gemm_cat_f32(const float* G0, int ld0, int no0, const float* G1, int ld1, int no1, const float* G2, int ld2,
+                            int no2, const float* X, int ld_x, int d, int64_t n, float* W, int ldw, float* colsum,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  const float* G[3] = {G0, G1, G2};
+  const int ld[3] = {ld0, ld1, ld2}, no[3] = {no0, no1, no2};
+  const int nblk = G2 ? 3 : (G1 ? 2 : 1);
+  if (n < 0 || d <= 0 || ld_x < d || ldw < d || !G0 || !W || !workspace || (G2 && !G1)) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && !X) return BGNN_ERR_INVALID_ARG;
+  uintptr_t bits = reinterpret_cast<uintptr_t>(X);
+  for (int i = 0; i < nblk; ++i) bits |= reinterpret_cast<uintptr_t>(G[i]);
+  if (bits & 15) return BGNN_ERR_INVALID_ARG;
+  return launch_wgrad_gemm_cat(G, ld, no, nblk, X, ld_x, d, n, W, ldw, colsum, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -85,8 +85,8 @@ int launch_adapted_transform_fwd(const float* P, const uint8_t* is_src, const fl
                                  long long n, int c, float* Hs, float* Ht, float* gates, cudaStream_t stream);
 size_t adapted_transform_bwd_workspace_bytes(int c);
 int launch_adapted_transform_bwd(const float* gHs, const float* gHt, const float* gates, const uint8_t* is_src,
-                                 const float* wd, long long n, int c, int ldp, float* gP, float* g_wd_kg, void* ws,
-                                 size_t ws_bytes, cudaStream_t stream);
+                                 const float* wd, long long n, int c, int ldp, int copy, float* gP, float* g_wd_kg,
+                                 void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // gatv2_heads.cu: 2-3 narrow aggregations over the same graph in one pass
 bool gatv2_heads_supported(int heads, int c);
@@ -132,6 +132,8 @@ bool wgrad_gemm_supported(int d, int ld_x, int no, int ld_g);
 size_t wgrad_gemm_workspace_bytes(int no);
 int launch_wgrad_gemm(const float* G, int ld_g, int no, const float* X, int ld_x, int d, long long n, float* W, int ldw,
                       float* colsum, void* ws, size_t ws_bytes, cudaStream_t stream);
+int launch_wgrad_gemm_cat(const float* const* G, const int* ld_g, const int* no, int nblk, const float* X, int ld_x, int d,
+                          long long n, float* W, int ldw, float* colsum, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // bn_relu.cu
 bool bn_relu_supported(int c);

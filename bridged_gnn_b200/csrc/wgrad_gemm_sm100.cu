@@ -57,8 +57,9 @@ __device__ __forceinline__ float wg_tf32(float v) { return __uint_as_float((__fl
 // stage layout: hi plane [G: nb boxes][X: 4 boxes] then the lo plane, same order.  TMA fills the first nb + mb boxes
 // of the hi plane with the raw data; X boxes mb..3 (features >= d) are zeroed once and never touched again.
 __global__ void __launch_bounds__(WG_THREADS, 1)
-wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, long long nblocks,
-                  int mb, int nb, int stages, int ones_col, float* __restrict__ part) {
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
+                  const __grid_constant__ CUtensorMap map_g1, const __grid_constant__ CUtensorMap map_g2, int nb0, int nb1,
+                  long long nblocks, int mb, int nb, int stages, int ones_col, float* __restrict__ part) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int plane = (nb + WG_MBOX) * WG_BOX;
@@ -115,6 +116,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g) : "memory");
+      if (nb0 < nb) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g1) : "memory");
+      if (nb0 + nb1 < nb) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g2) : "memory");
       int s = 0;
       uint32_t ph = 0;
       for (long long b = blockIdx.x; b < nblocks; b += gridDim.x) {
@@ -123,7 +126,12 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         mbar_expect_tx(fb, (uint32_t)((nb + mb) * WG_BOX));
         const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
         const int row0 = (int)(b * WG_BK);
-        for (int j = 0; j < nb; ++j) tma_load_2d(st + j * WG_BOX, &map_g, fb, j * 32, row0);
+        // G = up to three column blocks side by side (each from its own matrix: [dHs | dHt | d gates] without a copy)
+        for (int j = 0; j < nb; ++j) {
+          const CUtensorMap* m = j < nb0 ? &map_g : (j < nb0 + nb1 ? &map_g1 : &map_g2);
+          const int jj = j < nb0 ? j : (j < nb0 + nb1 ? j - nb0 : j - nb0 - nb1);
+          tma_load_2d(st + j * WG_BOX, m, fb, jj * 32, row0);
+        }
         for (int j = 0; j < mb; ++j) tma_load_2d(st + (nb + j) * WG_BOX, &map_x, fb, j * 32, row0);
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
@@ -275,30 +283,48 @@ bool wgrad_gemm_supported(int d, int ld_x, int no, int ld_g) {
 
 size_t wgrad_gemm_workspace_bytes(int no) { return (size_t)kNumSMs * 128 * ((no + 31) / 32 * 32) * sizeof(float) + 256; }
 
-int launch_wgrad_gemm(const float* G, int ld_g, int no, const float* X, int ld_x, int d, long long n, float* W, int ldw,
-                      float* colsum, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  if (!wgrad_gemm_supported(d, ld_x, no, ld_g) || n >= (1ll << 31)) return BGNN_ERR_UNSUPPORTED;
+int launch_wgrad_gemm_cat(const float* const* G, const int* ld_g, const int* no_blk, int nblk, const float* X, int ld_x, int d,
+                          long long n, float* W, int ldw, float* colsum, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (nblk < 1 || nblk > 3) return BGNN_ERR_INVALID_ARG;
+  int no = 0, nbs[3] = {0, 0, 0};
+  for (int i = 0; i < nblk; ++i) {
+    if (no_blk[i] < 1 || ld_g[i] % 4 != 0 || ld_g[i] < no_blk[i]) return BGNN_ERR_UNSUPPORTED;
+    if (i + 1 < nblk && no_blk[i] % 32 != 0) return BGNN_ERR_UNSUPPORTED;      // W rows must stay contiguous
+    no += no_blk[i];
+    nbs[i] = (no_blk[i] + 31) / 32;
+  }
+  if (!wgrad_gemm_supported(d, ld_x, no, 4) || n >= (1ll << 31)) return BGNN_ERR_UNSUPPORTED;
   if (colsum && d > 96) return BGNN_ERR_UNSUPPORTED;      // the all-ones feature needs a spare box
   if (ws_bytes < wgrad_gemm_workspace_bytes(no)) return BGNN_ERR_WORKSPACE;
-  const int nb = (no + 31) / 32, mb = (d + 31) / 32;
+  const int nb = nbs[0] + nbs[1] + nbs[2], mb = (d + 31) / 32;
   const int nop = nb * 32;
   float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   const long long nblocks = (n + WG_BK - 1) / WG_BK;
   const unsigned grid = (unsigned)(nblocks < kNumSMs ? (nblocks > 0 ? nblocks : 1) : kNumSMs);
   if (n > 0) {
-    CUtensorMap mx, mg;
+    CUtensorMap mx, mg[3];
     int rc;
     if ((rc = wg_make_map(&mx, X, n, d, ld_x)) != BGNN_OK) return rc;
-    if ((rc = wg_make_map(&mg, G, n, no, ld_g)) != BGNN_OK) return rc;
+    for (int i = 0; i < 3; ++i) {
+      const int k = i < nblk ? i : 0;
+      if ((rc = wg_make_map(&mg[i], G[k], n, no_blk[k], ld_g[k])) != BGNN_OK) return rc;
+    }
     const int stages = wg_stages(nb);
     const size_t smem = WG_SMEM_FIXED + (size_t)stages * 2 * (nb + WG_MBOX) * WG_BOX;
     BGNN_CUDA_TRY(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_gemm_kernel<<<grid, WG_THREADS, smem, stream>>>(mx, mg, nblocks, mb, nb, stages, colsum ? 1 : 0, part);
+    wgrad_gemm_kernel<<<grid, WG_THREADS, smem, stream>>>(mx, mg[0], mg[1], mg[2], nbs[0], nbs[1], nblocks, mb, nb, stages,
+                                                          colsum ? 1 : 0, part);
     BGNN_LAUNCH_CHECK();
   }
-  wgrad_reduce_kernel<<<((d + 1) * no + 255) / 256, 256, 0, stream>>>(part, n > 0 ? (int)grid : 0, nop, no, d, W, ldw, colsum, mb * 32);
+  wgrad_reduce_kernel<<<((d + 1) * no + 255) / 256, 256, 0, stream>>>(part, n > 0 ? (int)grid : 0, nop, no, d, W, ldw, colsum,
+                                                                      mb * 32);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
+}
+
+int launch_wgrad_gemm(const float* G, int ld_g, int no, const float* X, int ld_x, int d, long long n, float* W, int ldw,
+                      float* colsum, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  return launch_wgrad_gemm_cat(&G, &ld_g, &no, 1, X, ld_x, d, n, W, ldw, colsum, ws, ws_bytes, stream);
 }
 
 }  // namespace bgnn

@@ -505,6 +505,39 @@ def wgrad_gemm(G, X, colsum=False):
     return (W, cs) if colsum else W
 
 
+def wgrad_gemm_cat_supported(blocks, X):
+    if not (1 <= len(blocks) <= 3 and _tma_rows(X) and all(_tma_rows(g) and g.shape[0] == X.shape[0] for g in blocks)):
+        return False
+    if any(g.shape[1] % 32 != 0 for g in blocks[:-1]):
+        return False
+    no = sum(g.shape[1] for g in blocks)
+    return bool(_lib.load().bgnn_wgrad_gemm_supported(X.shape[1], X.stride(0), no, 4))
+
+
+def wgrad_gemm_cat(blocks, X):
+    """``torch.cat(blocks, 1).t() @ X`` without the concatenation: up to three column blocks [n, no_i] (all but the
+    last a multiple of 32 wide), each read in place through its own TMA descriptor by the ``wgrad_gemm`` kernel."""
+    lib = _lib.load()
+    blocks = [g.detach() for g in blocks]
+    X = X.detach()
+    if not wgrad_gemm_cat_supported(blocks, X):
+        raise ValueError("wgrad_gemm_cat: unsupported operands")
+    n, d = X.shape
+    no = sum(g.shape[1] for g in blocks)
+    W = torch.empty((no, d), dtype=torch.float32, device=X.device)
+    ws = _lib.workspace(lib.bgnn_wgrad_gemm_workspace_bytes(no), X.device)
+    args = []
+    for i in range(3):
+        if i < len(blocks):
+            args += [blocks[i].data_ptr(), blocks[i].stride(0), blocks[i].shape[1]]
+        else:
+            args += [None, 0, 0]
+    with _lib.call("bgnn_wgrad_gemm_cat_f32"):
+        _lib.check(lib.bgnn_wgrad_gemm_cat_f32(*args, X.data_ptr(), X.stride(0), d, n, _lib.ptr(W), d, None, _lib.ptr(ws),
+                                               ws.numel(), _lib.stream(X.device)))
+    return W
+
+
 class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -579,6 +612,22 @@ class _AdaptedWideFn(torch.autograd.Function):
         gHs, gHt = gHs.to(f32).contiguous(), gHt.to(f32).contiguous()
         n = gHs.shape[0]
         dev = gHs.device
+        if not ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
+            # first layer (x is data): dP = [dHs | dHt | d gates] is never materialised -- one pass over (dHs, dHt)
+            # for the reductions and the two gate columns, then the weight-gradient GEMM reads the three blocks in place
+            dg = torch.empty((n, 4), dtype=f32, device=dev)
+            red = torch.empty((4 * c + 2,), dtype=f32, device=dev)
+            ws = _lib.workspace(lib.bgnn_adapted_transform_bwd_workspace_bytes(c), dev)
+            blocks = [gHs, gHt, dg[:, :2]]
+            if wgrad_gemm_cat_supported(blocks, x):
+                with _lib.call("bgnn_adapted_transform_bwd_gates_f32"):
+                    _lib.check(lib.bgnn_adapted_transform_bwd_gates_f32(_lib.ptr(gHs), _lib.ptr(gHt), _lib.ptr(gates),
+                                                                        _lib.ptr(is_src, torch.uint8), _lib.ptr(wd_c), n, c,
+                                                                        _lib.ptr(dg), _lib.ptr(red), _lib.ptr(ws), ws.numel(),
+                                                                        _lib.stream(dev)))
+                g_w = wgrad_gemm_cat(blocks, x)
+                g_bias = None if bias_shape is None else red[2 * c + 2:].view(bias_shape)
+                return None, g_w, g_bias, red[: 2 * c].view(wd_shape), red[2 * c: 2 * c + 2].view(kg_shape), None
         ldp = 2 * c + 4                     # 2c+2 rounded up to 4: the two GEMMs below read gP in place through TMA
         gP_buf = torch.empty((n, ldp), dtype=f32, device=dev)
         gP = gP_buf[:, : 2 * c + 2]

@@ -165,6 +165,12 @@ size_t bgnn_adapted_transform_bwd_workspace_bytes(int c);
 int bgnn_adapted_transform_bwd_f32(const float* gHs, const float* gHt, const float* gates, const uint8_t* is_src,
                                    const float* wd, int64_t n, int c, int ldp, float* gP, float* g_wd_kg,
                                    void* workspace, size_t workspace_bytes, void* stream);
+/* The same reductions, writing only the two gate columns of gP: dg [n, 4] = (gP[:, 2c], gP[:, 2c+1], -, -).  For a
+ * conv whose input needs no gradient (the first layer) the other 2c columns of gP are gHs and gHt themselves, and
+ * bgnn_wgrad_gemm_cat_f32 reads them in place: gP is never materialised. */
+int bgnn_adapted_transform_bwd_gates_f32(const float* gHs, const float* gHt, const float* gates, const uint8_t* is_src,
+                                         const float* wd, int64_t n, int c, float* dg, float* g_wd_kg, void* workspace,
+                                         size_t workspace_bytes, void* stream);
 
 /* The same transform for NARROW outputs (classifier heads, c <= 4; d % 4 == 0, d <= 256), without the dense
  * contraction on the host: reads x [n,d] once per direction.  wcat [2c+2, d] = [W_s; W_t; a_g_s2t[:d]; a_g_t2s[:d]],
@@ -213,6 +219,12 @@ int bgnn_wgrad_gemm_supported(int d, int ld_x, int no, int ld_g);
 size_t bgnn_wgrad_gemm_workspace_bytes(int no);
 int bgnn_wgrad_gemm_f32(const float* G, int ld_g, int no, const float* X, int ld_x, int d, int64_t n, float* W, int ldw,
                         float* colsum, void* workspace, size_t workspace_bytes, void* stream);
+/* The same with G given as up to three column blocks side by side, G = [G0 | G1 | G2] (G1 / G2 may be NULL; every
+ * block but the last a multiple of 32 columns wide; no = no0 + no1 + no2 sizes the workspace): each block is read
+ * from its own matrix through its own TMA descriptor. */
+int bgnn_wgrad_gemm_cat_f32(const float* G0, int ld0, int no0, const float* G1, int ld1, int no1, const float* G2, int ld2,
+                            int no2, const float* X, int ld_x, int d, int64_t n, float* W, int ldw, float* colsum,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* BatchNorm1d (+ ReLU) over x [n, c] in training mode (models/KTGNN.py:363-366, 425-429: nn.BatchNorm1d followed by
  * ReLU), c % 4 == 0, c <= 1024; two passes over x each way, deterministic.

@@ -544,6 +544,28 @@ def test_adapted_wide_forward_backward(n, c, d, bias):
     ((Hs * go_s.cuda()).sum() + (Ht * go_t.cuda()).sum()).backward()
     for got, ref, name in zip(dl, leaf, names):
         assert got.grad.shape == ref.grad.shape and relclose(got.grad, ref.grad.float(), 2e-5), name
+    # first-layer case: x is data (no gradient) -- dP is never materialised, the weight-gradient GEMM reads
+    # [dHs | dHt | d gates] in place
+    dl2 = [t.clone().cuda().requires_grad_(i > 0) for i, t in enumerate(vals)]
+    Hs2, Ht2 = ops.adapted_wide(dl2[0], dl2[1], dl2[4] if bias else None, dl2[2], dl2[3], cm.to(torch.uint8).cuda())
+    assert torch.equal(Hs2, Hs) and torch.equal(Ht2, Ht)
+    ((Hs2 * go_s.cuda()).sum() + (Ht2 * go_t.cuda()).sum()).backward()
+    assert dl2[0].grad is None
+    for got, ref, name in list(zip(dl2, leaf, names))[1:]:
+        assert got.grad.shape == ref.grad.shape and relclose(got.grad, ref.grad.float(), 2e-5), name
+
+
+def test_wgrad_gemm_cat_equals_concatenation():
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    n = 3000
+    A, B, C = torch.randn(n, 64, generator=g).cuda(), torch.randn(n, 32, generator=g).cuda(), torch.randn(n, 4, generator=g).cuda()
+    X = torch.randn(n, 100, generator=g).cuda()
+    W = ops.wgrad_gemm_cat([A, B, C[:, :2]], X)
+    ref = torch.cat((A, B, C[:, :2]), 1).double().t() @ X.double()
+    assert W.shape == (98, 100) and relclose(W, ref.float(), 2e-6)
+    assert relclose(ops.wgrad_gemm_cat([A, B], X), ref[:96].float(), 2e-6)
+    assert not ops.wgrad_gemm_cat_supported([C[:, :2], A], X)          # only the last block may be ragged
 
 
 @pytest.mark.parametrize("n,c,d,bias", [(1, 1, 4, True), (1000, 2, 64, True), (777, 3, 100, False), (5000, 4, 128, True),

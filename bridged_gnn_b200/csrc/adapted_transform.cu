@@ -65,10 +65,35 @@ adapted_transform_bwd_kernel(const float* __restrict__ gHs, const float* __restr
   float k0 = 0.f, k1 = 0.f;
   const long long stride = (long long)gridDim.x * GROUPS;
   const long long iters = (n + stride - 1) / stride;      // uniform trip count: the shuffles below use the full mask
+  // the next row's slices are in flight while this row is reduced (4-byte loads: latency-bound otherwise)
+  float an[CPL], bn[CPL];
+  {
+    const long long r0 = (long long)blockIdx.x * GROUPS + grp;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int j = lane_g + k * G;
+      const bool ok = r0 < n && j < c;
+      an[k] = ok ? __ldg(gHs + r0 * c + j) : 0.f;
+      bn[k] = ok ? __ldg(gHt + r0 * c + j) : 0.f;
+    }
+  }
   for (long long it = 0; it < iters; ++it) {
     const long long row_raw = (long long)blockIdx.x * GROUPS + grp + it * stride;
     const bool valid = row_raw < n;
     const long long row = valid ? row_raw : 0;
+    float av[CPL], bv[CPL];
+    {
+      const long long rn = row_raw + stride;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const int j = lane_g + k * G;
+        av[k] = an[k];
+        bv[k] = bn[k];
+        const bool ok = rn < n && j < c;
+        an[k] = ok ? __ldg(gHs + rn * c + j) : 0.f;
+        bn[k] = ok ? __ldg(gHt + rn * c + j) : 0.f;
+      }
+    }
     const bool src = is_src[row] != 0;
     const float g0 = __ldg(gates + row * 2), g1 = __ldg(gates + row * 2 + 1);
     const float fs = src ? 0.f : g1, ft = src ? -g0 : 0.f;
@@ -76,14 +101,14 @@ adapted_transform_bwd_kernel(const float* __restrict__ gHs, const float* __restr
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
       const int j = lane_g + k * G;
-      if (valid && j < c) {
-        const float a = __ldg(gHs + row * c + j), b = __ldg(gHt + row * c + j);
-        if (copy) {
-          gP[row * ldp + j] = a;
-          gP[row * ldp + c + j] = b;
-        }
-        ds = fmaf(a, ws[k], ds);
-        dt = fmaf(b, wt[k], dt);
+      const float a = av[k], b = bv[k];        // zero outside the matrix
+      if (copy && valid && j < c) {
+        gP[row * ldp + j] = a;
+        gP[row * ldp + c + j] = b;
+      }
+      ds = fmaf(a, ws[k], ds);
+      dt = fmaf(b, wt[k], dt);
+      if (valid) {
         as_[k] = fmaf(fs, a, as_[k]);
         at_[k] = fmaf(ft, b, at_[k]);
         bs_[k] += a;

@@ -242,21 +242,29 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   }
 }
 
-// W[j * ldw + f] = sum over CTAs (in order, in double) of part[cta](f, j);  colsum[j] = the same for the all-ones feature row
+// W[j * ldw + f] = sum over CTAs of part[cta](f, j), in double: eight lanes per element each add every eighth partial
+// in order, then a fixed butterfly combines them (deterministic);  colsum[j] = the same for the all-ones feature row
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int nop, int no, int d, float* __restrict__ W, int ldw,
                     float* __restrict__ colsum, int f_ones) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // f * no + j: consecutive threads read consecutive j
-  if (idx >= (d + (colsum ? 1 : 0)) * no) return;
-  int f = idx / no;
-  const int j = idx - f * no;
+  const int sub = threadIdx.x & 7;
+  const int idx = blockIdx.x * 32 + (threadIdx.x >> 3);     // f * no + j: consecutive groups read consecutive j
+  const int total = (d + (colsum ? 1 : 0)) * no;
+  const bool live = idx < total;
+  int f = live ? idx / no : 0;
+  const int j = live ? idx - f * no : 0;
   const bool extra = f == d;
   if (extra) f = f_ones;
-  double acc = 0.0;
   const size_t at = ((size_t)(j >> 2) * 128 + f) * 4 + (j & 3);       // [quad][feature][4] inside a CTA's partial
-  for (int p = 0; p < nparts; ++p) acc += (double)part[(size_t)p * 128 * nop + at];
-  if (extra) colsum[j] = (float)acc;
-  else W[(size_t)j * ldw + f] = (float)acc;
+  double acc = 0.0;
+  if (live)
+    for (int p = sub; p < nparts; p += 8) acc += (double)part[(size_t)p * 128 * nop + at];
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (live && sub == 0) {
+    if (extra) colsum[j] = (float)acc;
+    else W[(size_t)j * ldw + f] = (float)acc;
+  }
 }
 
 static int wg_make_map(CUtensorMap* m, const float* base, long long rows, int cols, int ld) {
@@ -316,7 +324,7 @@ int launch_wgrad_gemm_cat(const float* const* G, const int* ld_g, const int* no_
                                                           colsum ? 1 : 0, part);
     BGNN_LAUNCH_CHECK();
   }
-  wgrad_reduce_kernel<<<((d + 1) * no + 255) / 256, 256, 0, stream>>>(part, n > 0 ? (int)grid : 0, nop, no, d, W, ldw, colsum,
+  wgrad_reduce_kernel<<<((d + 1) * no + 31) / 32, 256, 0, stream>>>(part, n > 0 ? (int)grid : 0, nop, no, d, W, ldw, colsum,
                                                                       mb * 32);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;

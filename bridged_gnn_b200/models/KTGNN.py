@@ -1,7 +1,9 @@
 """KT-GNN layers and models with the reference's constructor / forward / state_dict surface
 (models/KTGNN.py:218-328 AdaptedConv, :330-465 KTGNN_no_complement, :467-597 KTGNN_noDTC), running the
-edge part of every conv as one fused sm_100a kernel (ops.gat_aggregate) instead of PyG's
-gather -> softmax -> propagate chain.  Node-wise dense layers stay in torch (cuBLAS).
+edge part of every conv as one fused sm_100a kernel (ops.gat_aggregate, ops.gat_aggregate_heads) instead of PyG's
+gather -> softmax -> propagate chain, and the node-wise dense part (AdaptedConv's contraction with its gates,
+clf_transformer's Linear layers, BatchNorm1d + ReLU) on this library's tensor-core / two-pass kernels when the input
+is an fp32 CUDA matrix of a supported width (torch's own modules otherwise: CPU tensors, SyncBatchNorm, odd widths).
 """
 import torch
 import torch.nn as nn

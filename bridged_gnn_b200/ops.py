@@ -1,6 +1,8 @@
-"""Torch-facing operators over the C ABI: kNN build, CSR graphs, SpMM and the fused AdaptedConv
-aggregation (both differentiable).  Everything here runs hand-written sm_100a kernels on the current
-CUDA stream; nothing falls back to torch ops or the CPU.
+"""Torch-facing operators over the C ABI: kNN build, CSR graphs, SpMM, the fused AdaptedConv aggregation
+(single conv and multi-head), the node-wise transforms (CUDA-core for classifier heads, tcgen05 3 x TF32 for wide
+outputs), row-panel / weight-gradient GEMMs and BatchNorm1d + ReLU -- all differentiable.  Everything here runs
+hand-written sm_100a kernels on the current CUDA stream; nothing falls back to the CPU, and an operator given a
+shape it does not cover raises (the ``*_supported`` predicates tell callers beforehand).
 """
 import os
 

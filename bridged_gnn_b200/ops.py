@@ -2,7 +2,9 @@
 (single conv and multi-head), the node-wise transforms (CUDA-core for classifier heads, tcgen05 3 x TF32 for wide
 outputs), row-panel / weight-gradient GEMMs and BatchNorm1d + ReLU -- all differentiable.  Everything here runs
 hand-written sm_100a kernels on the current CUDA stream; nothing falls back to the CPU, and an operator given a
-shape it does not cover raises (the ``*_supported`` predicates tell callers beforehand).
+shape it does not cover raises (the ``*_supported`` predicates tell callers beforehand).  The one exception: the
+backward contractions of ``linear`` / ``adapted_wide`` use ``torch.matmul`` on the GPU when an operand's row stride
+is not a multiple of 16 bytes (TMA cannot address it) -- never the case for the widths KT-GNN uses.
 """
 import os
 

@@ -519,4 +519,17 @@ int bgnn_wgrad_gemm_cat_f32(const float* G0, int ld0, int no0, const float* G1, 
   return launch_wgrad_gemm_cat(G, ld, no, nblk, X, ld_x, d, n, W, ldw, colsum, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int bgnn_adapted_skinny_tc_supported(int c, int d, int heads) { return adapted_skinny_tc_supported(c, d, heads) ? 1 : 0; }
+
+int bgnn_adapted_skinny_heads_tc_fwd_f32(const float* x, int64_t n, int d, const float* wcat_hi, const float* wcat_lo, int c,
+                                         int heads, const uint8_t* is_src, const float* wd, const float* kg,
+                                         const float* bias, float* Hs, float* Ht, float* gates, void* stream) {
+  if (n < 0 || c <= 0 || d <= 0 || heads <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!x || !wcat_hi || !wcat_lo || !is_src || !wd || !kg || !Hs || !Ht || !gates)) return BGNN_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wcat_hi) | reinterpret_cast<uintptr_t>(wcat_lo)) & 15)
+    return BGNN_ERR_INVALID_ARG;
+  return launch_adapted_skinny_tc_fwd(x, n, d, wcat_hi, wcat_lo, c, heads, is_src, wd, kg, bias, Hs, Ht, gates,
+                                      (cudaStream_t)stream);
+}
+
 }  // extern "C"

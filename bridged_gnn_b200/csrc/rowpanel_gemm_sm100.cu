@@ -53,8 +53,9 @@ struct RgEpi {                 // EPI 1: AdaptedConv node-wise epilogue (adapted
   const float* bias;           // [2C] or null
   float* Hs;                   // [n, C]
   float* Ht;                   // [n, C]
-  float* gates;                // [n, 2]
+  float* gates;                // [n, 2]  (EPI 2: [n, heads * 2])
   int c;
+  int heads;                   // EPI 2: narrow convs side by side, columns h * (2c+2) + [0, 2c+2) of the accumulator
 };
 
 // Epilogue store of one 32 x 32 block: the thread <-> row registers go through a 4 KB per-warp staging tile (16-byte
@@ -257,6 +258,34 @@ rowpanel_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           }
           rg_store_block(stg, r, lane, Y, row0, n, ldy, c0, no);
         }
+      } else if (EPI == 2) {
+        // classifier heads (C <= 4, 1-2 heads): all heads * (2C+2) <= 32 columns of a row sit in one tcgen05.ld; they
+        // go through the staging tile (word k of row l at k ^ l: conflict-free) so that the head / column loops can
+        // index them at run time
+        const int c = ep.c, o = 2 * c + 2;
+        tc_ld32(taddr0, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) stg[lane * 32 + (k ^ lane)] = r[k];
+        __syncwarp();
+        if (row_ok) {
+          const float* mine = stg + lane * 32;
+          const bool src = ep.is_src[row] != 0;
+          for (int h = 0; h < ep.heads; ++h) {
+            const float g0 = tanhf(mine[(h * o + 2 * c) ^ lane] + __ldg(ep.kg + 2 * h));
+            const float g1 = tanhf(mine[(h * o + 2 * c + 1) ^ lane] + __ldg(ep.kg + 2 * h + 1));
+            const float fs = src ? 0.f : g1, ft = src ? -g0 : 0.f;
+            for (int j = 0; j < c; ++j) {
+              const float ps = mine[(h * o + j) ^ lane] + (ep.bias ? __ldg(ep.bias + h * o + j) : 0.f);
+              const float pt = mine[(h * o + c + j) ^ lane] + (ep.bias ? __ldg(ep.bias + h * o + c + j) : 0.f);
+              ep.Hs[(row * ep.heads + h) * c + j] = fmaf(fs, __ldg(ep.wd + h * 2 * c + j), ps);
+              ep.Ht[(row * ep.heads + h) * c + j] = fmaf(ft, __ldg(ep.wd + h * 2 * c + c + j), pt);
+            }
+            ep.gates[(row * ep.heads + h) * 2] = g0;
+            ep.gates[(row * ep.heads + h) * 2 + 1] = g1;
+          }
+        }
+        __syncwarp();
       } else {
         // columns [0,C) = x W_s^T, [C,2C) = x W_t^T, 2C / 2C+1 = gate logits (C a multiple of 32)
         const int c = ep.c;
@@ -361,6 +390,20 @@ int launch_rowpanel_gemm(const float* A, long long n, int k, int ld_a, const flo
   return rg_launch<0>(A, n, k, ld_a, bhi, blo, no, Y, ldy, ep, stream);
 }
 
+bool adapted_skinny_tc_supported(int c, int d, int heads) {
+  return c >= 1 && c <= 4 && heads >= 1 && heads <= 2 && d % 4 == 0 && d >= 4 && d <= 256 &&
+         rowpanel_gemm_supported(d, d, heads * (2 * c + 2));
+}
+
+int launch_adapted_skinny_tc_fwd(const float* x, long long n, int d, const float* wcat_hi, const float* wcat_lo, int c, int heads,
+                                 const uint8_t* is_src, const float* wd, const float* kg, const float* bias, float* Hs,
+                                 float* Ht, float* gates, cudaStream_t stream) {
+  if (!adapted_skinny_tc_supported(c, d, heads)) return BGNN_ERR_UNSUPPORTED;
+  RgEpi ep;
+  ep.is_src = is_src; ep.wd = wd; ep.kg = kg; ep.bias = bias; ep.Hs = Hs; ep.Ht = Ht; ep.gates = gates; ep.c = c; ep.heads = heads;
+  return rg_launch<2>(x, n, d, d, wcat_hi, wcat_lo, heads * (2 * c + 2), nullptr, 0, ep, stream);
+}
+
 bool adapted_wide_supported(int c, int d) { return c >= 32 && c % 32 == 0 && 2 * c + 2 <= 256 && d % 4 == 0 && d >= 4 && d <= 256 && rowpanel_gemm_supported(d, d, 2 * c + 2); }
 
 int launch_adapted_wide_fwd(const float* x, long long n, int d, const float* wcat_hi, const float* wcat_lo, int c,
@@ -368,7 +411,7 @@ int launch_adapted_wide_fwd(const float* x, long long n, int d, const float* wca
                             float* gates, cudaStream_t stream) {
   if (!adapted_wide_supported(c, d)) return BGNN_ERR_UNSUPPORTED;
   RgEpi ep;
-  ep.is_src = is_src; ep.wd = wd; ep.kg = kg; ep.bias = bias; ep.Hs = Hs; ep.Ht = Ht; ep.gates = gates; ep.c = c;
+  ep.is_src = is_src; ep.wd = wd; ep.kg = kg; ep.bias = bias; ep.Hs = Hs; ep.Ht = Ht; ep.gates = gates; ep.c = c; ep.heads = 1;
   return rg_launch<1>(x, n, d, d, wcat_hi, wcat_lo, 2 * c + 2, nullptr, 0, ep, stream);
 }
 

@@ -836,11 +836,20 @@ class _SkinnyGroupFn(torch.autograd.Function):
         Hs = torch.empty((n, heads * c), dtype=f32, device=dev)
         Ht = torch.empty((n, heads * c), dtype=f32, device=dev)
         gates = torch.empty((n, heads * 2), dtype=f32, device=dev)
-        with _lib.call("bgnn_adapted_skinny_heads_fwd_f32"):
-            _lib.check(lib.bgnn_adapted_skinny_heads_fwd_f32(_lib.ptr(x), _lib.ptr(is_src, torch.uint8), _lib.ptr(wcat),
-                                                             _lib.ptr(bias, f32, True), _lib.ptr(wd), _lib.ptr(kg), n, d, c,
-                                                             heads, _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(gates),
-                                                             _lib.stream(dev)))
+        if not os.environ.get("BGNN_NO_SKINNY_TC") and lib.bgnn_adapted_skinny_tc_supported(c, d, heads):
+            # the heads * (2c+2) dot products per row on the tensor cores (3 x TF32), gates applied to the accumulator
+            hi, lo = tf32_planes(wcat)
+            with _lib.call("bgnn_adapted_skinny_heads_tc_fwd_f32"):
+                _lib.check(lib.bgnn_adapted_skinny_heads_tc_fwd_f32(_lib.ptr(x), n, d, _lib.ptr(hi), _lib.ptr(lo), c, heads,
+                                                                    _lib.ptr(is_src, torch.uint8), _lib.ptr(wd), _lib.ptr(kg),
+                                                                    _lib.ptr(bias, f32, True), _lib.ptr(Hs), _lib.ptr(Ht),
+                                                                    _lib.ptr(gates), _lib.stream(dev)))
+        else:
+            with _lib.call("bgnn_adapted_skinny_heads_fwd_f32"):
+                _lib.check(lib.bgnn_adapted_skinny_heads_fwd_f32(_lib.ptr(x), _lib.ptr(is_src, torch.uint8), _lib.ptr(wcat),
+                                                                 _lib.ptr(bias, f32, True), _lib.ptr(wd), _lib.ptr(kg), n, d,
+                                                                 c, heads, _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(gates),
+                                                                 _lib.stream(dev)))
         ctx.save_for_backward(x, wcat, atail, wd, gates, is_src, delta, inv_counts)
         ctx.meta = (heads, c, d, has_bias)
         return Hs, Ht

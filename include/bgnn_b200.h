@@ -264,6 +264,15 @@ int bgnn_adapted_skinny_heads_bwd_f32(const float* x, const uint8_t* is_src, con
                                       int d, int c, int heads, float* gx, float* red, void* workspace,
                                       size_t workspace_bytes, void* stream);
 
+/* Forward of bgnn_adapted_skinny_heads_fwd_f32 on the tensor cores: the heads * (2c+2) <= 20 dot products per row run
+ * as a 3 x TF32 row-panel GEMM (x streamed by TMA, split on chip) and the gates / corrections are applied to the
+ * accumulator row; same outputs and layouts.  wcat_hi / wcat_lo: tf32 planes of the stacked weight rows, padded to
+ * (16, 32) multiples as for bgnn_rowpanel_gemm_f32. */
+int bgnn_adapted_skinny_tc_supported(int c, int d, int heads);
+int bgnn_adapted_skinny_heads_tc_fwd_f32(const float* x, int64_t n, int d, const float* wcat_hi, const float* wcat_lo, int c,
+                                         int heads, const uint8_t* is_src, const float* wd, const float* kg,
+                                         const float* bias, float* Hs, float* Ht, float* gates, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,7 @@ SIGNATURES = {
     "bgnn_bn_relu_bwd_f32": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "bgnn_adapted_skinny_tc_supported": (_i32, [_i32, _i32, _i32]),
     "bgnn_adapted_skinny_heads_tc_fwd_f32": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _i32] + [_vp] * 8),
+    "bgnn_tf32_planes_f32": (_i32, [_vp, _i32, _i32, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     "bgnn_adapted_wide_supported": (_i32, [_i32, _i32]),
     "bgnn_adapted_wide_fwd_f32": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32] + [_vp] * 8),
     "bgnn_adapted_skinny_heads_supported": (_i32, [_i32, _i32, _i32]),
@@ -129,7 +130,7 @@ KERNELS_PER_CALL = {"bgnn_knn_cosine_f32": 13, "bgnn_knn_cosine_f32[simt]": 4, "
                     "bgnn_edges_to_csr": 4, "bgnn_spmm_csr_f32": 1, "bgnn_gatv2_fwd_f32": 1, "bgnn_gatv2_bwd_f32": 3,
                     "bgnn_gatv2_fwd_ord_f32": 1, "bgnn_gatv2_bwd_ord_f32": 3, "bgnn_rows_by_degree": 1,
                     "bgnn_adapted_transform_fwd_f32": 1, "bgnn_adapted_transform_bwd_f32": 2,
-                    "bgnn_gatv2_heads_fwd_f32": 1, "bgnn_gatv2_heads_bwd_f32": 3, "bgnn_adapted_skinny_fwd_f32": 1, "bgnn_adapted_skinny_bwd_f32": 2, "bgnn_domain_colsum_f32": 2, "bgnn_rowpanel_gemm_f32": 1, "bgnn_adapted_skinny_heads_tc_fwd_f32": 1, "bgnn_wgrad_gemm_cat_f32": 2, "bgnn_adapted_transform_bwd_gates_f32": 2, "bgnn_adapted_skinny_heads_fwd_f32": 1, "bgnn_adapted_skinny_heads_pre_f32": 2,
+                    "bgnn_gatv2_heads_fwd_f32": 1, "bgnn_gatv2_heads_bwd_f32": 3, "bgnn_adapted_skinny_fwd_f32": 1, "bgnn_adapted_skinny_bwd_f32": 2, "bgnn_domain_colsum_f32": 2, "bgnn_rowpanel_gemm_f32": 1, "bgnn_tf32_planes_f32": 1, "bgnn_adapted_skinny_heads_tc_fwd_f32": 1, "bgnn_wgrad_gemm_cat_f32": 2, "bgnn_adapted_transform_bwd_gates_f32": 2, "bgnn_adapted_skinny_heads_fwd_f32": 1, "bgnn_adapted_skinny_heads_pre_f32": 2,
                     "bgnn_adapted_skinny_heads_bwd_f32": 2, "bgnn_bn_relu_fwd_f32": 3, "bgnn_bn_relu_apply_f32": 1, "bgnn_bn_relu_bwd_f32": 3, "bgnn_wgrad_gemm_f32": 2,
                     "bgnn_adapted_wide_fwd_f32": 1}
 launches = 0          # running count of kernels launched through the C ABI

@@ -532,4 +532,10 @@ int bgnn_adapted_skinny_heads_tc_fwd_f32(const float* x, int64_t n, int d, const
                                       (cudaStream_t)stream);
 }
 
+int bgnn_tf32_planes_f32(const float* w, int rows, int cols, int64_t stride_r, int64_t stride_c, int rows_p, int cols_p,
+                         float* hi, float* lo, void* stream) {
+  if (!hi || !lo || (rows > 0 && cols > 0 && !w)) return BGNN_ERR_INVALID_ARG;
+  return launch_tf32_planes(w, rows, cols, stride_r, stride_c, rows_p, cols_p, hi, lo, (cudaStream_t)stream);
+}
+
 }  // extern "C"

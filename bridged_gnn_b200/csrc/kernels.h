@@ -122,6 +122,8 @@ int launch_domain_colsum(const float* x, const uint8_t* is_src, long long n, int
 bool rowpanel_gemm_supported(int k, int ld_a, int no);
 int launch_rowpanel_gemm(const float* A, long long n, int k, int ld_a, const float* bhi, const float* blo, const float* bias,
                          int no, float* Y, int ldy, cudaStream_t stream);
+int launch_tf32_planes(const float* w, int rows, int cols, long long stride_r, long long stride_c, int rows_p, int cols_p, float* hi,
+                       float* lo, cudaStream_t stream);
 bool adapted_wide_supported(int c, int d);
 bool adapted_skinny_tc_supported(int c, int d, int heads);
 int launch_adapted_skinny_tc_fwd(const float* x, long long n, int d, const float* wcat_hi, const float* wcat_lo, int c, int heads,

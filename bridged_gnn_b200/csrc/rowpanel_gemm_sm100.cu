@@ -390,6 +390,31 @@ int launch_rowpanel_gemm(const float* A, long long n, int k, int ld_a, const flo
   return rg_launch<0>(A, n, k, ld_a, bhi, blo, no, Y, ldy, ep, stream);
 }
 
+// hi / lo tf32 planes of a small fp32 matrix (any strides: a transposed view costs nothing), zero padded to
+// [rows_p, cols_p]: the host-side operand preparation of the kernels above in one launch
+__global__ void __launch_bounds__(256)
+tf32_planes_kernel(const float* __restrict__ w, int rows, int cols, long long stride_r, long long stride_c, int rows_p, int cols_p,
+                   float* __restrict__ hi, float* __restrict__ lo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_p * cols_p) return;
+  const int r = idx / cols_p, c = idx - r * cols_p;
+  const float v = (r < rows && c < cols) ? __ldg(w + r * stride_r + c * stride_c) : 0.f;
+  const float h = rg_tf32(v);
+  hi[idx] = h;
+  lo[idx] = rg_tf32(v - h);
+}
+
+int launch_tf32_planes(const float* w, int rows, int cols, long long stride_r, long long stride_c, int rows_p, int cols_p, float* hi,
+                       float* lo, cudaStream_t stream) {
+  if (rows < 0 || cols < 0 || rows_p < rows || cols_p < cols) return BGNN_ERR_INVALID_ARG;
+  const long long total = (long long)rows_p * cols_p;
+  if (total == 0) return BGNN_OK;
+  if (total > (1ll << 30)) return BGNN_ERR_UNSUPPORTED;
+  tf32_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(w, rows, cols, stride_r, stride_c, rows_p, cols_p, hi, lo);
+  BGNN_LAUNCH_CHECK();
+  return BGNN_OK;
+}
+
 bool adapted_skinny_tc_supported(int c, int d, int heads) {
   return c >= 1 && c <= 4 && heads >= 1 && heads <= 2 && d % 4 == 0 && d >= 4 && d <= 256 &&
          rowpanel_gemm_supported(d, d, heads * (2 * c + 2));

@@ -436,12 +436,22 @@ def adapted_transform(P, wd, kg, is_src, bias=None):
 # ----------------------------------------------------------------------------------- wide AdaptedConv transform
 def tf32_planes(w, rows_to=16, cols_to=32):
     """(hi, lo) planes of a small fp32 matrix for the 3 x TF32 contractions: hi = w rounded to tf32, lo = w - hi
-    rounded to tf32 (the tensor core would truncate), both zero padded to multiples of (16, 32)."""
+    rounded to tf32 (the tensor core would truncate), both zero padded to multiples of (16, 32).  One kernel launch on
+    the GPU (any strides, e.g. ``weight.t()``); plain torch ops for CPU tensors (tests)."""
     w = w.detach().to(torch.float32)
     r, c = w.shape
     rp, cp = -(-r // rows_to) * rows_to, -(-c // cols_to) * cols_to
+    if w.is_cuda:
+        lib = _lib.load()
+        hi = torch.empty((rp, cp), dtype=torch.float32, device=w.device)
+        lo = torch.empty((rp, cp), dtype=torch.float32, device=w.device)
+        with _lib.call("bgnn_tf32_planes_f32"):
+            _lib.check(lib.bgnn_tf32_planes_f32(w.data_ptr(), r, c, w.stride(0), w.stride(1), rp, cp, _lib.ptr(hi), _lib.ptr(lo),
+                                                _lib.stream(w.device)))
+        return hi, lo
     wp = torch.zeros((rp, cp), dtype=torch.float32, device=w.device)
     wp[:r, :c] = w
+
     def tf32(t):
         return ((t.view(torch.int32) + 4096) & -8192).view(torch.float32)
     hi = tf32(wp)

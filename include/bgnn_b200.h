@@ -273,6 +273,12 @@ int bgnn_adapted_skinny_heads_tc_fwd_f32(const float* x, int64_t n, int d, const
                                          int heads, const uint8_t* is_src, const float* wd, const float* kg,
                                          const float* bias, float* Hs, float* Ht, float* gates, void* stream);
 
+/* Operand preparation for the 3 x TF32 kernels above: hi [rows_p, cols_p] = w rounded to tf32, lo = (w - hi) rounded
+ * to tf32, zero outside [rows, cols].  w is addressed as w[r * stride_r + c * stride_c] (elements), so a transposed
+ * view needs no copy. */
+int bgnn_tf32_planes_f32(const float* w, int rows, int cols, int64_t stride_r, int64_t stride_c, int rows_p, int cols_p,
+                         float* hi, float* lo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -555,6 +555,18 @@ def test_adapted_wide_forward_backward(n, c, d, bias):
         assert got.grad.shape == ref.grad.shape and relclose(got.grad, ref.grad.float(), 2e-5), name
 
 
+def test_tf32_planes_kernel_equals_host_restatement():
+    """The one-launch operand preparation == the torch restatement (tests/test_host_logic.py pins that one), bit for
+    bit, for contiguous and transposed inputs."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(130, 100, generator=g) * torch.exp(3 * torch.randn(130, 1, generator=g))
+    for view_cpu, view_gpu in ((w, w.cuda()), (w.t(), w.cuda().t())):
+        hi_r, lo_r = ops.tf32_planes(view_cpu)
+        hi, lo = ops.tf32_planes(view_gpu)
+        assert hi.shape == hi_r.shape and torch.equal(hi.cpu(), hi_r) and torch.equal(lo.cpu(), lo_r)
+
+
 def test_wgrad_gemm_cat_equals_concatenation():
     ops = _ops()
     g = torch.Generator().manual_seed(11)

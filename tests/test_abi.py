@@ -82,3 +82,37 @@ def test_cpu_tensors_rejected():
     from bridged_gnn_b200 import _lib
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         _lib.ptr(torch.zeros(4))
+
+
+def test_dense_kernel_plans_are_host_only(lib):
+    """Shape predicates and workspace sizes of the node-wise dense kernels: host arithmetic, no GPU needed."""
+    # row-panel GEMM: K, NO <= 256, 16-byte rows
+    assert lib.bgnn_rowpanel_gemm_supported(128, 128, 130) == 1
+    assert lib.bgnn_rowpanel_gemm_supported(130, 132, 128) == 1
+    assert lib.bgnn_rowpanel_gemm_supported(128, 130, 64) == 0        # 520-byte rows: TMA cannot address them
+    assert lib.bgnn_rowpanel_gemm_supported(64, 64, 257) == 0
+    # wide / narrow AdaptedConv transforms
+    assert lib.bgnn_adapted_wide_supported(64, 128) == 1 and lib.bgnn_adapted_wide_supported(32, 256) == 1
+    assert lib.bgnn_adapted_wide_supported(48, 128) == 0 and lib.bgnn_adapted_wide_supported(160, 128) == 0
+    assert lib.bgnn_adapted_wide_supported(64, 130) == 0
+    assert lib.bgnn_adapted_skinny_heads_supported(2, 64, 2) == 1 and lib.bgnn_adapted_skinny_heads_supported(2, 64, 3) == 0
+    assert lib.bgnn_adapted_skinny_heads_supported(5, 64, 1) == 0
+    assert lib.bgnn_adapted_skinny_tc_supported(2, 64, 2) == 1 and lib.bgnn_adapted_skinny_tc_supported(4, 256, 2) == 1
+    assert lib.bgnn_adapted_skinny_tc_supported(2, 66, 1) == 0
+    # weight-gradient GEMM: d <= 128, no <= 256, workspace = one [128, nop] partial per SM
+    assert lib.bgnn_wgrad_gemm_supported(128, 128, 130, 132) == 1 and lib.bgnn_wgrad_gemm_supported(129, 132, 64, 64) == 0
+    assert lib.bgnn_wgrad_gemm_supported(64, 64, 64, 66) == 0
+    assert lib.bgnn_wgrad_gemm_workspace_bytes(130) >= 148 * 128 * 160 * 4
+    assert lib.bgnn_wgrad_gemm_workspace_bytes(64) < lib.bgnn_wgrad_gemm_workspace_bytes(130)
+    # BatchNorm + ReLU: c % 4 == 0, c <= 1024
+    assert lib.bgnn_bn_relu_supported(64) == 1 and lib.bgnn_bn_relu_supported(6) == 0 and lib.bgnn_bn_relu_supported(2048) == 0
+    assert lib.bgnn_bn_relu_workspace_bytes(64) > 148 * 8 * 128 * 4
+
+
+def test_dense_kernels_reject_invalid_arguments(lib):
+    null = ctypes.c_void_p(None)
+    assert lib.bgnn_rowpanel_gemm_f32(null, 4, 8, 8, null, null, null, 8, null, 8, null) == -1
+    assert lib.bgnn_wgrad_gemm_f32(null, 8, 8, null, 8, 8, 4, null, 8, null, null, 0, null) == -1
+    assert lib.bgnn_bn_relu_fwd_f32(null, 4, 8, null, null, 1e-5, 0.1, null, null, 1, null, null, null, 0, null) == -1
+    assert lib.bgnn_adapted_wide_fwd_f32(null, 4, 8, null, null, 32, null, null, null, null, null, null, null, null) == -1
+    assert lib.bgnn_tf32_planes_f32(null, 4, 4, 4, 1, 16, 32, null, null, null) == -1

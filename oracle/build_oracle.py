@@ -295,3 +295,28 @@ def reorder(x, y, masks, edge_index, n_src, mapper_idx_src, mapper_idx_tar):
     order = items[:, 1]
     ei = torch.tensor([[inv[int(i)] for i in edge_index[0]], [inv[int(i)] for i in edge_index[1]]], dtype=torch.long)
     return x[order], y[order], {k: m[order] for k, m in masks.items()}, ei
+
+
+def merge_graphs(x_src, y_src, ei_src, x_tar, y_tar, ei_tar, train_mask_tar, val_mask_tar, test_mask_tar,
+                 edge_index_cross_added, edge_index_added_src=None, edge_index_added_tar=None):
+    """main_bridged_graph.py:163-193 on plain tensors: concatenate the two graphs and the added edges (target ids
+    offset by N_src), build the masks (:181-189), ``Data(...).coalesce()`` (:191-193).  Returns a dict."""
+    n_src, n_tar = x_src.shape[0], x_tar.shape[0]
+    n = n_src + n_tar
+    cross = edge_index_cross_added.clone()
+    cross[1, :] += n_src
+    parts = [ei_src, ei_tar + n_src, cross]
+    if edge_index_added_src is not None:
+        parts.append(edge_index_added_src)
+    if edge_index_added_tar is not None:
+        parts.append(edge_index_added_tar + n_src)
+    central = torch.zeros(n, dtype=torch.bool)
+    central[:n_src] = True
+    train, val, test = torch.zeros(n, dtype=torch.bool), torch.zeros(n, dtype=torch.bool), torch.zeros(n, dtype=torch.bool)
+    train[central] = True
+    train[torch.where(y_src == -1)] = False
+    train[torch.where(train_mask_tar)[0] + n_src] = True
+    val[torch.where(val_mask_tar)[0] + n_src] = True
+    test[torch.where(test_mask_tar)[0] + n_src] = True
+    return dict(x=torch.cat((x_src, x_tar), 0), edge_index=coalesce(torch.cat(parts, dim=1), n), y=torch.cat((y_src, y_tar), 0),
+                train_mask=train, val_mask=val, test_mask=test, central_mask=central)

@@ -52,3 +52,8 @@ def fb_build():
 @pytest.fixture(scope="session")
 def diag_golden():
     return load_golden("diagnostics.npz")
+
+
+@pytest.fixture(scope="session")
+def office_assemble():
+    return load_golden("office_a2d_assemble.npz")

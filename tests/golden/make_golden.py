@@ -282,8 +282,62 @@ def diagnostics(d):
     np.savez_compressed(os.path.join(HERE, "diagnostics.npz"), **out)
 
 
+def office_assemble(d):
+    """The reference's own check_added_edges_{cross,within}_domain_validity (main_bridged_graph.py:225-264,
+    123-161), merge_graphs (:163-193) and reorder (:195-222), run on the office fixture with the edge lists /
+    similarities / classifier outputs the reference's build produced (stored in office_a2d_build.npz)."""
+    import contextlib
+    import copy
+    import io
+    g = dict(np.load(os.path.join(HERE, "office_a2d_build.npz")))
+    T = torch.from_numpy
+    src, tar, ns = split_domains(d)
+    ei_c, sim_c = T(g["cross_edge_index"]), T(g["cross_sim"])
+    ei_s, sim_s = T(g["within_src_edge_index"]), T(g["within_src_sim"])
+    ei_t, sim_t = T(g["within_tar_edge_index"]), T(g["within_tar_sim"])
+    p_src, p_tar = T(g["probs_clf_src"]), T(g["probs_clf_tar"])
+    out = {}
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        # cross filter at the CLI defaults (q = 0.1, thres_feat_sim = 0) and with rule 4 active / another quantile
+        for tag, q, thr in (("cross_q10_f0", 0.1, 0.0), ("cross_q25_f30", 0.25, 0.3), ("cross_q0_f0", 0.0, 0.0)):
+            out[tag] = np_(ref_build.check_added_edges_cross_domain_validity(ei_c.clone(), sim_c.view(-1), src, tar, p_src, p_tar,
+                                                                            thres_conf_quantile=q, thres_feat_sim=thr))
+        # within filters with the constants hard-coded at :301-306
+        out["within_src_q10_f80"] = np_(ref_build.check_added_edges_within_domain_validity(ei_s.clone(), sim_s.view(-1), src, p_src, 0.1, 0.8))
+        out["within_tar_q10_f80"] = np_(ref_build.check_added_edges_within_domain_validity(ei_t.clone(), sim_t.view(-1), tar, p_tar, 0.1, 0.8))
+        out["within_tar_q50_f0"] = np_(ref_build.check_added_edges_within_domain_validity(ei_t.clone(), sim_t.view(-1), tar, p_tar, 0.5, 0.0))
+        # merge (:163-193) with the filtered cross edges and both within-domain lists, exactly like gen_bridged_graph :312-313
+        src_u = copy.deepcopy(src)
+        src_u.y[torch.arange(0, ns, 97)] = -1          # a few unlabelled source nodes exercise train_mask[y == -1] = False
+        merged = ref_build.merge_graphs(src_u, tar, copy.deepcopy(T(out["cross_q10_f0"])), copy.deepcopy(ei_s), copy.deepcopy(ei_t))
+        out["merge.unlabelled_src"] = np_(torch.arange(0, ns, 97))
+        for k in ("edge_index", "y", "train_mask", "val_mask", "test_mask", "central_mask"):
+            out["merge." + k] = np_(getattr(merged, k))
+        out["merge.x_checksum"] = np_(merged.x.double().sum(1))
+        merged_x = merged.x.clone()
+        # merge without within-domain edges (k_within = 0 recipes)
+        merged0 = ref_build.merge_graphs(src, tar, copy.deepcopy(ei_c))
+        out["merge0.edge_index"] = np_(merged0.edge_index)
+        # reorder (:195-222): original ids = a seeded permutation of 0..N-1 split over the two domains
+        gen = torch.Generator().manual_seed(7)
+        n = merged.x.shape[0]
+        orig = torch.randperm(n, generator=gen)
+        m_src = {int(orig[i]): i for i in range(ns)}
+        m_tar = {int(orig[ns + i]): i for i in range(n - ns)}
+        out["reorder.orig_ids"] = np_(orig)
+        re = ref_build.reorder(merged, src_u, m_src, m_tar)
+        for k in ("edge_index", "y", "train_mask", "val_mask", "test_mask", "central_mask"):
+            out["reorder." + k] = np_(getattr(re, k))
+        out["reorder.x_checksum"] = np_(re.x.double().sum(1))
+        assert torch.equal(re.x, merged_x[torch.argsort(orig)])
+    np.savez_compressed(os.path.join(HERE, "office_a2d_assemble.npz"), **out)
+    print("office assemble:", {k: v.shape for k, v in out.items() if v.ndim == 2})
+
+
 if __name__ == "__main__":
     d = office_build()
+    office_assemble(d)
     diagnostics(d)
     fb_cosine_build()
     office_mp(d)

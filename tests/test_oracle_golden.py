@@ -202,3 +202,47 @@ def test_homophily_diagnostics_match_reference(diag_golden, office_build):
         assert abs(ratio - float(d[tag + ".local_ratio"])) < 1e-6, tag
         assert abs(h1 - float(d[tag + ".h1"])) < 1e-6 and abs(h2 - float(d[tag + ".h2"])) < 1e-6, tag
 
+
+
+def _assemble_inputs(g):
+    x, y, c, ei = T(g["x"]), T(g["y"]), T(g["central_mask"]), T(g["edge_index"])
+    ms, mt = c[ei[0]] & c[ei[1]], (~c[ei[0]]) & (~c[ei[1]])
+    tm, vm, sm = T(g["train_mask"]), T(g["val_mask"]), T(g["test_mask"])
+    return dict(xs=x[:NS], ys=y[:NS], es=ei[:, ms], tms=tm[:NS], xt=x[NS:], yt=y[NS:], et=ei[:, mt] - NS, tmt=tm[NS:],
+                vmt=vm[NS:], smt=sm[NS:])
+
+
+def test_filters_merge_reorder_pinned_on_reference(office_build, office_assemble):
+    """the oracle's check_added_edges_* / merge_graphs / reorder against the outputs of the
+    reference's own functions (main_bridged_graph.py:225-264, 123-161, 163-193, 195-222) on the office fixture."""
+    g, a = office_build, office_assemble
+    p = _assemble_inputs(g)
+    ei_c, sim_c = T(g["cross_edge_index"]), T(g["cross_sim"])
+    ps, pt = T(g["probs_clf_src"]), T(g["probs_clf_tar"])
+    for tag, q, thr in (("cross_q10_f0", 0.1, 0.0), ("cross_q25_f30", 0.25, 0.3), ("cross_q0_f0", 0.0, 0.0)):
+        got = bo.check_added_edges_cross_domain_validity(ei_c, sim_c.view(-1), p["xs"], p["ys"], p["xt"], p["yt"], p["tmt"], ps, pt, q, thr)
+        assert torch.equal(got, T(a[tag])), tag
+    ei_s, sim_s = T(g["within_src_edge_index"]), T(g["within_src_sim"])
+    ei_t, sim_t = T(g["within_tar_edge_index"]), T(g["within_tar_sim"])
+    got = bo.check_added_edges_within_domain_validity(ei_s, sim_s.view(-1), p["xs"], p["ys"], p["tms"], ps, 0.1, 0.8)
+    assert torch.equal(got, T(a["within_src_q10_f80"]))
+    for tag, q, thr in (("within_tar_q10_f80", 0.1, 0.8), ("within_tar_q50_f0", 0.5, 0.0)):
+        got = bo.check_added_edges_within_domain_validity(ei_t, sim_t.view(-1), p["xt"], p["yt"], p["tmt"], pt, q, thr)
+        assert torch.equal(got, T(a[tag])), tag
+    ys = p["ys"].clone()
+    ys[T(a["merge.unlabelled_src"])] = -1
+    m = bo.merge_graphs(p["xs"], ys, p["es"], p["xt"], p["yt"], p["et"], p["tmt"], p["vmt"], p["smt"], T(a["cross_q10_f0"]), ei_s, ei_t)
+    for k in ("edge_index", "y", "train_mask", "val_mask", "test_mask", "central_mask"):
+        assert torch.equal(m[k], T(a["merge." + k])), k
+    assert torch.equal(m["x"].double().sum(1), T(a["merge.x_checksum"]))
+    m0 = bo.merge_graphs(p["xs"], p["ys"], p["es"], p["xt"], p["yt"], p["et"], p["tmt"], p["vmt"], p["smt"], ei_c)
+    assert torch.equal(m0["edge_index"], T(a["merge0.edge_index"]))
+    orig = T(a["reorder.orig_ids"])
+    n = orig.numel()
+    m_src = {int(orig[i]): i for i in range(NS)}
+    m_tar = {int(orig[NS + i]): i for i in range(n - NS)}
+    masks = {k: m[k] for k in ("train_mask", "val_mask", "test_mask", "central_mask")}
+    xr, yr, mr, er = bo.reorder(m["x"], m["y"], masks, m["edge_index"], NS, m_src, m_tar)
+    assert torch.equal(er, T(a["reorder.edge_index"])) and torch.equal(yr, T(a["reorder.y"]))
+    assert all(torch.equal(mr[k], T(a["reorder." + k])) for k in masks)
+    assert torch.equal(xr.double().sum(1), T(a["reorder.x_checksum"]))

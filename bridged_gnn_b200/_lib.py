@@ -26,8 +26,13 @@ SIGNATURES = {
     "bgnn_error_string": (_c.c_char_p, [_i32]),
     "bgnn_knn_cosine_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "bgnn_knn_cosine_f32": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bgnn_knn_cosine_eps_f32": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bgnn_knn_addrelu_eps_f32": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _f32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bgnn_knn_addrelu_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "bgnn_knn_addrelu_f32": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bgnn_quantile_workspace_bytes": (_sz, []),
+    "bgnn_quantile_f32": (_i32, [_vp, _i64, _i64, _f32, _vp, _vp, _sz, _vp]),
+    "bgnn_edge_validity_f32": (_i32, [_vp, _vp, _i64] + [_vp] * 10 + [_i32, _f32, _vp, _vp, _vp]),
     "bgnn_edges_to_csr_workspace_bytes": (_sz, [_i64]),
     "bgnn_edges_to_csr": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bgnn_spmm_csr_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
@@ -126,8 +131,8 @@ def workspace(nbytes, device):
 # ---- instrumentation used by bench.py (off by default; no effect on results) ----------------------
 # kernels launched per C-ABI call (hand-written kernels of this library only; CUB's sort/scan inside
 # bgnn_edges_to_csr are not counted)
-KERNELS_PER_CALL = {"bgnn_knn_cosine_f32": 13, "bgnn_knn_cosine_f32[simt]": 4, "bgnn_knn_addrelu_f32": 2,
-                    "bgnn_edges_to_csr": 4, "bgnn_spmm_csr_f32": 1, "bgnn_gatv2_fwd_f32": 1, "bgnn_gatv2_bwd_f32": 3,
+KERNELS_PER_CALL = {"bgnn_knn_cosine_f32": 13, "bgnn_knn_cosine_eps_f32": 13, "bgnn_knn_addrelu_eps_f32": 2, "bgnn_knn_cosine_f32[simt]": 4, "bgnn_knn_addrelu_f32": 2,
+                    "bgnn_edges_to_csr": 4, "bgnn_quantile_f32": 11, "bgnn_edge_validity_f32": 2, "bgnn_spmm_csr_f32": 1, "bgnn_gatv2_fwd_f32": 1, "bgnn_gatv2_bwd_f32": 3,
                     "bgnn_gatv2_fwd_ord_f32": 1, "bgnn_gatv2_bwd_ord_f32": 3, "bgnn_rows_by_degree": 1,
                     "bgnn_adapted_transform_fwd_f32": 1, "bgnn_adapted_transform_bwd_f32": 2,
                     "bgnn_gatv2_heads_fwd_f32": 1, "bgnn_gatv2_heads_bwd_f32": 3, "bgnn_adapted_skinny_fwd_f32": 1, "bgnn_adapted_skinny_bwd_f32": 2, "bgnn_domain_colsum_f32": 2, "bgnn_rowpanel_gemm_f32": 1, "bgnn_tf32_planes_f32": 1, "bgnn_adapted_skinny_heads_tc_fwd_f32": 1, "bgnn_wgrad_gemm_cat_f32": 2, "bgnn_adapted_transform_bwd_gates_f32": 2, "bgnn_adapted_skinny_heads_fwd_f32": 1, "bgnn_adapted_skinny_heads_pre_f32": 2,

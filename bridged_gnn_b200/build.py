@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libbgnn_b200.so")
-SOURCES = ["api.cu", "adapted_skinny.cu", "gatv2_heads.cu", "knn_simt.cu", "knn_select.cu", "knn_cosine_sm100.cu", "knn_cosine_f16_sm100.cu", "csr_build.cu", "spmm_csr.cu",
+SOURCES = ["api.cu", "adapted_skinny.cu", "gatv2_heads.cu", "knn_simt.cu", "knn_select.cu", "knn_cosine_sm100.cu", "knn_cosine_f16_sm100.cu", "csr_build.cu", "edge_filter.cu", "spmm_csr.cu",
            "gatv2_fused.cu", "adapted_transform.cu", "rowpanel_gemm_sm100.cu", "wgrad_gemm_sm100.cu", "bn_relu.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

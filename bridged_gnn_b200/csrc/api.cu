@@ -125,6 +125,14 @@ size_t bgnn_knn_cosine_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, in
 int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb, int d, int k, int normalize,
                         int apply_sigmoid, int algo, int64_t* out_idx, float* out_val, float* out_gap,
                         int32_t* out_stats, void* workspace, size_t workspace_bytes, void* stream_) {
+  return bgnn_knn_cosine_eps_f32(q, nq, db, ndb, d, k, normalize, apply_sigmoid, algo, nanf(""), out_idx, out_val, out_gap,
+                                 nullptr, out_stats, workspace, workspace_bytes, stream_);
+}
+
+int bgnn_knn_cosine_eps_f32(const float* q, int64_t nq, const float* db, int64_t ndb, int d, int k, int normalize,
+                            int apply_sigmoid, int algo, float eps, int64_t* out_idx, float* out_val, float* out_gap,
+                            int32_t* out_count, int32_t* out_stats, void* workspace, size_t workspace_bytes,
+                            void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!knn_args_ok(nq, ndb, d, k) || !q || !db || !out_idx || !out_val) return BGNN_ERR_INVALID_ARG;
   if (algo < BGNN_KNN_SIMT_F32 || algo > BGNN_KNN_TC_F16) return BGNN_ERR_INVALID_ARG;
@@ -173,7 +181,7 @@ int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb
     if (rc != BGNN_OK) return rc;
     rc = launch_knn_merge(cand_val, cand_idx, p.simt.nsplit, p.simt.kc, (int)nq, k, 0, nullptr, nullptr, nullptr,
                           nullptr, d, p.ld, apply_sigmoid, -1.f, nullptr, nullptr, nullptr, 0, (long long*)out_idx, out_val,
-                          out_gap, nullptr, nullptr, stream);
+                          out_gap, nullptr, nullptr, eps, out_count, stream);
     if (rc != BGNN_OK) return rc;
     if (out_stats) { set_int_kernel<<<1, 1, 0, stream>>>(out_stats, 0); BGNN_LAUNCH_CHECK(); }
     return BGNN_OK;
@@ -195,20 +203,21 @@ int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb
   const float delta = p.f16 ? (9.7657e-4f + 5.97e-8f * sqrtf((float)d) + 4.0e-6f) : ((p.passes == 3) ? 3.0e-5f : 2.0e-3f);
   rc = launch_knn_merge(cand_val, cand_idx, p.tc.nlists, p.tc.kc, (int)nq, k, 1, qhi, qlo, dhi, dlo, p.ld, p.ld,
                         apply_sigmoid, delta, seed_thr, nullptr, nullptr, 0, (long long*)out_idx, out_val, out_gap, fb_rows,
-                        fb_count, stream);
+                        fb_count, eps, out_count, stream);
   if (rc != BGNN_OK) return rc;
   // uncertified rows, exactly: a handful -> one db slice per CTA (knn_exact_rows); more -> the tiled sweep + merge.
   // The count lives on the device, so both are launched and each returns at once when it is not its case.
   const int few = knn_exact_rows_max((int)ndb, p.ld, k);
   rc = launch_knn_exact_rows(qhi, qlo, dhi, dlo, (int)ndb, p.ld, p.ld, apply_sigmoid, k, fb_rows, fb_count,
-                             (long long*)out_idx, out_val, out_gap, xr_ws, knn_exact_rows_workspace_bytes(k), stream);
+                             (long long*)out_idx, out_val, out_gap, eps, out_count, xr_ws,
+                             knn_exact_rows_workspace_bytes(k), stream);
   if (rc != BGNN_OK) return rc;
   rc = launch_knn_simt(BGNN_PAIR_DOT, qhi, qlo, (int)nq, dhi, dlo, (int)ndb, p.ld, p.ld, nullptr, 0.f, apply_sigmoid,
                        p.simt.kc, p.simt.nsplit, p.simt.per_split, fb_rows, fb_count, few, cand_val, cand_idx, stream);
   if (rc != BGNN_OK) return rc;
   rc = launch_knn_merge(cand_val, cand_idx, p.simt.nsplit, p.simt.kc, (int)nq, k, 0, nullptr, nullptr, nullptr,
                         nullptr, p.ld, p.ld, apply_sigmoid, -1.f, nullptr, fb_rows, fb_count, few, (long long*)out_idx,
-                        out_val, out_gap, nullptr, nullptr, stream);
+                        out_val, out_gap, nullptr, nullptr, eps, out_count, stream);
   if (rc != BGNN_OK) return rc;
   if (out_stats) { copy_int_kernel<<<1, 1, 0, stream>>>(fb_count, out_stats); BGNN_LAUNCH_CHECK(); }
   return BGNN_OK;
@@ -223,6 +232,13 @@ size_t bgnn_knn_addrelu_workspace_bytes(int64_t nq, int64_t ndb, int h, int k) {
 int bgnn_knn_addrelu_f32(const float* Uq, int64_t nq, const float* Udb, int64_t ndb, int h, const float* w2, float b2,
                          int k, int apply_sigmoid, int64_t* out_idx, float* out_val, float* out_gap,
                          void* workspace, size_t workspace_bytes, void* stream_) {
+  return bgnn_knn_addrelu_eps_f32(Uq, nq, Udb, ndb, h, w2, b2, k, apply_sigmoid, nanf(""), out_idx, out_val, out_gap, nullptr,
+                                  workspace, workspace_bytes, stream_);
+}
+
+int bgnn_knn_addrelu_eps_f32(const float* Uq, int64_t nq, const float* Udb, int64_t ndb, int h, const float* w2, float b2,
+                             int k, int apply_sigmoid, float eps, int64_t* out_idx, float* out_val, float* out_gap,
+                             int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!knn_args_ok(nq, ndb, h, k) || !Uq || !Udb || !w2 || !out_idx || !out_val) return BGNN_ERR_INVALID_ARG;
   if (nq == 0) return BGNN_OK;
@@ -238,7 +254,27 @@ int bgnn_knn_addrelu_f32(const float* Uq, int64_t nq, const float* Udb, int64_t 
   if (rc != BGNN_OK) return rc;
   return launch_knn_merge(cand_val, cand_idx, p.nsplit, p.kc, (int)nq, k, 0, nullptr, nullptr, nullptr, nullptr, h, h,
                           apply_sigmoid, -1.f, nullptr, nullptr, nullptr, 0, (long long*)out_idx, out_val, out_gap, nullptr,
-                          nullptr, stream);
+                          nullptr, eps, out_count, stream);
+}
+
+size_t bgnn_quantile_workspace_bytes(void) { return quantile_workspace_bytes(); }
+
+int bgnn_quantile_f32(const float* v, int64_t n, int64_t rank_lo, float weight, float* out3, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (!v || !out3 || n <= 0 || rank_lo < 0 || rank_lo >= n || !(weight >= 0.f && weight <= 1.f)) return BGNN_ERR_INVALID_ARG;
+  if (!workspace || workspace_bytes < quantile_workspace_bytes()) return BGNN_ERR_WORKSPACE;
+  return launch_quantile(v, n, rank_lo, weight, out3, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bgnn_edge_validity_f32(const int64_t* e0, const int64_t* e1, int64_t e, const float* e_sim, const float* thr_conf,
+                           const int64_t* pred_a, const int64_t* y_a, const int64_t* pred_b, const int64_t* y_b,
+                           const uint8_t* gate_a, const uint8_t* gate_b, const float* x_a, const float* x_b, int d,
+                           float thres_feat_sim, uint8_t* keep, int64_t* counts, void* stream) {
+  if (e < 0 || d <= 0 || !counts) return BGNN_ERR_INVALID_ARG;
+  if (e > 0 && (!e0 || !e1 || !e_sim || !pred_a || !y_a || !pred_b || !y_b || !x_a || !x_b || !keep)) return BGNN_ERR_INVALID_ARG;
+  return launch_edge_validity((const long long*)e0, (const long long*)e1, e, e_sim, thr_conf, (const long long*)pred_a,
+                              (const long long*)y_a, (const long long*)pred_b, (const long long*)y_b, gate_a, gate_b, x_a, x_b,
+                              d, thres_feat_sim, keep, (long long*)counts, (cudaStream_t)stream);
 }
 
 size_t bgnn_edges_to_csr_workspace_bytes(int64_t e) { return e < 0 ? 0 : csr_build_workspace_bytes(e); }

@@ -15,11 +15,20 @@
 namespace bgnn {
 
 // key = (dst << nb) | src with nb = bits needed for a node id, so the radix sort touches 2*nb bits only.
-__global__ void make_keys_kernel(const long long* __restrict__ src, const long long* __restrict__ dst, long long e, int nb,
-                                 unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals) {
+// An edge with a node id outside [0, n) would spill into the other half of the key and later serve as a gather index:
+// it is counted in *bad and parked under destination n, behind the last row, where no kernel reads it.
+__global__ void make_keys_kernel(const long long* __restrict__ src, const long long* __restrict__ dst, long long e, long long n,
+                                 int nb, unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals,
+                                 unsigned long long* __restrict__ bad) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= e) return;
-  keys[i] = ((unsigned long long)dst[i] << nb) | (unsigned long long)src[i];
+  long long s = src[i], d = dst[i];
+  if (s < 0 || s >= n || d < 0 || d >= n) {
+    atomicAdd(bad, 1ull);
+    s = 0;
+    d = n;
+  }
+  keys[i] = ((unsigned long long)d << nb) | (unsigned long long)s;
   vals[i] = (unsigned int)i;
 }
 
@@ -61,8 +70,10 @@ __global__ void rowptr_kernel(const unsigned long long* __restrict__ ckeys, cons
 __global__ void zero_rowptr_kernel(long long n, int* rowptr, long long* e_out) {
   long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r <= n) rowptr[r] = 0;
-  if (r == 0) *e_out = 0;
+  if (r == 0) { e_out[0] = 0; e_out[1] = 0; }
 }
+
+__global__ void zero_bad_kernel(long long* e_out) { e_out[1] = 0; }
 
 static size_t cub_temp_bytes(long long e) {
   size_t a = 0, b = 0;
@@ -100,9 +111,12 @@ int launch_edges_to_csr(const long long* src, const long long* dst, long long e,
   unsigned blocks = (unsigned)((e + T - 1) / T);
   int nb = 1;
   while ((1ll << nb) < n) ++nb;
-  make_keys_kernel<<<blocks, T, 0, stream>>>(src, dst, e, nb, k0, v0);
+  zero_bad_kernel<<<1, 1, 0, stream>>>(e_out);
   BGNN_LAUNCH_CHECK();
-  BGNN_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, tb, k0, k1, v0, v1, e, 0, 2 * nb, stream));
+  make_keys_kernel<<<blocks, T, 0, stream>>>(src, dst, e, n, nb, k0, v0, reinterpret_cast<unsigned long long*>(e_out + 1));
+  BGNN_LAUNCH_CHECK();
+  // 2 nb + 1 key bits: destination n (the parking row of invalid edges) needs one bit more than a node id when n = 2^nb
+  BGNN_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, tb, k0, k1, v0, v1, e, 0, 2 * nb + 1, stream));
   flag_heads_kernel<<<blocks, T, 0, stream>>>(k1, e, dedup, flags);
   BGNN_LAUNCH_CHECK();
   BGNN_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, tb, flags, pos, e, stream));

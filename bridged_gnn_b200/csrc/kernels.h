@@ -17,7 +17,8 @@ int knn_exact_rows_max(int ndb, int ld, int k);
 size_t knn_exact_rows_workspace_bytes(int k);
 int launch_knn_exact_rows(const float* Q, const float* Qlo, const float* DB, const float* DBlo, int ndb, int d, int ld,
                           int apply_sigmoid, int k, const int* row_list, const int* row_count, long long* out_idx,
-                          float* out_val, float* out_gap, void* ws, size_t ws_bytes, cudaStream_t stream);
+                          float* out_val, float* out_gap, float eps, int* out_count, void* ws, size_t ws_bytes,
+                          cudaStream_t stream);
 
 // knn_select.cu
 #define BGNN_MERGE_MAX_CAND 1024
@@ -27,7 +28,7 @@ int launch_knn_merge(const float* cand_val, const int* cand_idx, int nlists, int
                      const float* qhi, const float* qlo, const float* dhi, const float* dlo, int d, int ld,
                      int apply_sigmoid, float delta, const float* seed_thr, const int* row_list, const int* row_count,
                      int few_rows, long long* out_idx, float* out_val, float* out_gap, int* fb_rows, int* fb_count,
-                     cudaStream_t stream);
+                     float eps, int* out_count, cudaStream_t stream);
 
 // knn_cosine_sm100.cu  (tcgen05 / TMEM / TMA)
 struct TcPlan {
@@ -54,6 +55,15 @@ int launch_normalize_f16(const float* x, long long n, int d, int ld, int ldh, in
                          cudaStream_t stream);
 int launch_knn_cosine_f16(const void* qh, int nq, const void* dh, int ndb, int ldh, const TcPlan& plan,
                           const float* thr_init, float* cand_val, int* cand_idx, cudaStream_t stream);
+
+// edge_filter.cu
+size_t quantile_workspace_bytes();
+int launch_quantile(const float* v, long long n, long long rank_lo, float weight, float* out3, void* ws, size_t ws_bytes,
+                    cudaStream_t stream);
+int launch_edge_validity(const long long* e0, const long long* e1, long long e, const float* e_sim, const float* thr_conf,
+                         const long long* pred_a, const long long* y_a, const long long* pred_b, const long long* y_b,
+                         const uint8_t* gate_a, const uint8_t* gate_b, const float* x_a, const float* x_b, int d,
+                         float thres_feat_sim, uint8_t* keep, long long* counts, cudaStream_t stream);
 
 // csr_build.cu
 size_t csr_build_workspace_bytes(long long e);

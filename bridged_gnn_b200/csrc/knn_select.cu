@@ -60,7 +60,7 @@ knn_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ can
                  const float* __restrict__ dhi, const float* __restrict__ dlo, int d, int ld, int apply_sigmoid,
                  float delta, const float* __restrict__ seed_thr, const int* __restrict__ row_list,
                  const int* __restrict__ row_count, int few_rows, long long* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ out_gap,
-                 int* __restrict__ fb_rows, int* __restrict__ fb_count) {
+                 int* __restrict__ fb_rows, int* __restrict__ fb_count, float eps, int* __restrict__ out_count) {
   __shared__ float sv[MG_WARPS][MG_MAXC];
   __shared__ int si[MG_WARPS][MG_MAXC];
   extern __shared__ __align__(16) float sqrow[];  // [MG_WARPS][ld] when rescoring
@@ -120,6 +120,11 @@ knn_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ can
   // index appears at most once.
   float vk = -INFINITY, vk1 = -INFINITY;
   bool have_k1 = false;
+  // epsilon threshold of the bridge matching (main_bridged_graph.py:33 `epsilon`), fused into the selection: a
+  // neighbour is emitted only if its similarity exceeds eps (NaN = off); values are best first, so the kept
+  // neighbours of a row are a prefix whose length goes to out_count
+  const bool use_eps = eps == eps;
+  int kept = 0;
   for (int round = 0; round <= k; ++round) {
     float bv = -INFINITY;
     int bi = 0x7fffffff, bs = -1;
@@ -137,8 +142,10 @@ knn_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ can
       if (os >= 0 && (bs < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; bs = os; }
     }
     if (round < k) {
+      const bool emit = bs >= 0 && (!use_eps || bv > eps);
+      kept += emit ? 1 : 0;
       if (lane == 0) {
-        out_idx[row * k + round] = (bs >= 0) ? (long long)bi : -1LL;
+        out_idx[row * k + round] = emit ? (long long)bi : -1LL;
         out_val[row * k + round] = (bs >= 0) ? bv : -INFINITY;
       }
       if (round == k - 1) vk = (bs >= 0) ? bv : -INFINITY;
@@ -150,6 +157,7 @@ knn_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ can
     }
   }
   if (lane == 0) {
+    if (out_count) out_count[row] = kept;
     if (out_gap) out_gap[row] = have_k1 ? (vk - vk1) : INFINITY;
     if (delta >= 0.f && fb_rows && worst_thr > -INFINITY) {
       // every discarded column scores, exactly, at most f(worst_thr + delta); the row is final only if
@@ -169,14 +177,14 @@ int launch_knn_merge(const float* cand_val, const int* cand_idx, int nlists, int
                      const float* qhi, const float* qlo, const float* dhi, const float* dlo, int d, int ld,
                      int apply_sigmoid, float delta, const float* seed_thr, const int* row_list, const int* row_count,
                      int few_rows, long long* out_idx, float* out_val, float* out_gap, int* fb_rows, int* fb_count,
-                     cudaStream_t stream) {
+                     float eps, int* out_count, cudaStream_t stream) {
   if (nq <= 0) return BGNN_OK;
   if (nlists * kc > MG_MAXC) return BGNN_ERR_UNSUPPORTED;
   if (rescore && (ld % 4 != 0 || d % 4 != 0)) return BGNN_ERR_INVALID_ARG;
   size_t dyn = rescore ? (size_t)MG_WARPS * ld * sizeof(float) : 0;
   knn_merge_kernel<<<(nq + MG_WARPS - 1) / MG_WARPS, MG_WARPS * 32, dyn, stream>>>(
       cand_val, cand_idx, nlists, kc, nq, k, rescore, qhi, qlo, dhi, dlo, d, ld, apply_sigmoid, delta, seed_thr,
-      row_list, row_count, few_rows, out_idx, out_val, out_gap, fb_rows, fb_count);
+      row_list, row_count, few_rows, out_idx, out_val, out_gap, fb_rows, fb_count, eps, out_count);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }

@@ -265,7 +265,8 @@ knn_exact_rows_kernel(const float* __restrict__ Q, const float* __restrict__ Qlo
 __global__ void __launch_bounds__(XR_THREADS)
 knn_exact_rows_merge_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int nparts, int k1, int k,
                             const int* __restrict__ row_list, const int* __restrict__ row_count,
-                            long long* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ out_gap) {
+                            long long* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ out_gap,
+                            float eps, int* __restrict__ out_count) {
   extern __shared__ __align__(16) float xm_smem[];   // values [nparts*k1], ids [nparts*k1]
   __shared__ float s_v[XR_THREADS / 32];
   __shared__ int s_i[XR_THREADS / 32], s_p[XR_THREADS / 32];
@@ -282,17 +283,22 @@ knn_exact_rows_merge_kernel(const float* __restrict__ part_val, const int* __res
   __syncthreads();
   const long long row = row_list[r];
   float vk = -INFINITY;
+  const bool use_eps = eps == eps;                  // epsilon threshold fused into the selection (NaN = off)
+  int kept = 0;
   for (int round = 0; round <= k; ++round) {
     float bv; int bi, bp;
     xr_block_best(sv, si, m, s_v, s_i, s_p, bv, bi, bp);
     if (threadIdx.x == 0) {
       if (round < k) {
-        out_idx[row * k + round] = bp >= 0 ? (long long)bi : -1LL;
+        const bool emit = bp >= 0 && (!use_eps || bv > eps);
+        kept += emit ? 1 : 0;
+        out_idx[row * k + round] = emit ? (long long)bi : -1LL;
         out_val[row * k + round] = bp >= 0 ? bv : -INFINITY;
         if (round == k - 1) vk = bp >= 0 ? bv : -INFINITY;
         if (bp >= 0) si[bp] = -1;
-      } else if (out_gap) {
-        out_gap[row] = bp >= 0 ? (vk - bv) : INFINITY;
+      } else {
+        if (out_gap) out_gap[row] = bp >= 0 ? (vk - bv) : INFINITY;
+        if (out_count) out_count[row] = kept;
       }
     }
     __syncthreads();
@@ -323,7 +329,8 @@ size_t knn_exact_rows_workspace_bytes(int k) {
 // Handles the listed rows iff 0 < *row_count <= knn_exact_rows_max(..) (decided on the device; no-op otherwise).
 int launch_knn_exact_rows(const float* Q, const float* Qlo, const float* DB, const float* DBlo, int ndb, int d, int ld,
                           int apply_sigmoid, int k, const int* row_list, const int* row_count, long long* out_idx,
-                          float* out_val, float* out_gap, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                          float* out_val, float* out_gap, float eps, int* out_count, void* ws, size_t ws_bytes,
+                          cudaStream_t stream) {
   if (ld % 4 != 0 || d % 4 != 0) return BGNN_ERR_INVALID_ARG;
   if (ws_bytes < knn_exact_rows_workspace_bytes(k)) return BGNN_ERR_WORKSPACE;
   const int ctas = xr_ctas(ndb, ld, k);
@@ -342,7 +349,7 @@ int launch_knn_exact_rows(const float* Q, const float* Qlo, const float* DB, con
                                                            row_count, pv, pi);
   BGNN_LAUNCH_CHECK();
   knn_exact_rows_merge_kernel<<<XR_MAX_ROWS, XR_THREADS, dyn2, stream>>>(pv, pi, ctas, k1, k, row_list, row_count, out_idx,
-                                                                        out_val, out_gap);
+                                                                        out_val, out_gap, eps, out_count);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }

@@ -90,3 +90,23 @@ def load_pyg_dat(path):
                 sys.modules.pop(k, None)
     store = obj.__dict__["_store"].__dict__["_mapping"]
     return Data(**{k: v for k, v in store.items()})
+
+
+def save_graph(data, path):
+    """Write a bridged graph (the artefact of step 1, main_bridged_graph.py:317-320) as a plain dict of CPU tensors.
+    The reference pickles a torch_geometric Data object, which cannot be produced without PyG; ``load_graph`` reads
+    both forms."""
+    torch.save({"format": "bridged_gnn_b200.graph.v1", **{k: getattr(data, k).cpu() for k in data.keys()
+                                                           if torch.is_tensor(getattr(data, k))}}, path)
+
+
+def load_graph(path):
+    """Read a bridged graph written either by ``save_graph`` (dict of tensors) or by the reference (pickled
+    torch_geometric Data, ``data_bridged_graph/*.dat``)."""
+    try:
+        obj = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:
+        return load_pyg_dat(path)                 # a pickled PyG object needs the attribute-bag unpickler
+    if isinstance(obj, dict) and "x" in obj and "edge_index" in obj:
+        return Data(**{k: v for k, v in obj.items() if torch.is_tensor(v)})
+    raise ValueError("%s: neither a bridged_gnn_b200 graph dict nor a pickled PyG Data" % path)

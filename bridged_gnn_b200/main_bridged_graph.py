@@ -12,12 +12,12 @@ import os
 import torch
 
 from . import ops
-from .data import Data, coalesce
+from .data import Data, coalesce, load_graph, save_graph
 from .models.models import Adversarial_Learner, Adversarial_Learner_v2
 from .utils import eval_bridged_Graph, eval_homophily
 
 __all__ = ["add_topk_sim_cross_domain_edges", "add_topk_sim_within_domain_edges", "check_added_edges_cross_domain_validity",
-           "check_added_edges_within_domain_validity", "merge_graphs", "reorder", "gen_bridged_graph"]
+           "check_added_edges_within_domain_validity", "merge_graphs", "reorder", "gen_bridged_graph", "split_domains", "main"]
 
 
 def _homophily(y_from, y_to, edge_index):
@@ -26,23 +26,25 @@ def _homophily(y_from, y_to, edge_index):
     return (same.sum() / lab.sum().clamp(min=1)).item()
 
 
-def _knn(sim_net, z_db, z_q, k, algo):
-    """Top-k db rows per query row under the head's similarity.  Returns idx [nq,k], val [nq,k], gap [nq]."""
+def _knn(sim_net, z_db, z_q, k, algo, eps=None):
+    """Top-k db rows per query row under the head's similarity.  Returns idx [nq,k], val [nq,k], gap [nq].
+    ``eps``: threshold applied inside the selection epilogue (neighbours with similarity <= eps get idx -1)."""
     if sim_net.mode == "cosine":
         u_db = sim_net.cosine_operand(z_db)
         u_q = u_db if z_q is z_db else sim_net.cosine_operand(z_q)
-        idx, val, gap, _ = ops.knn_cosine(u_q, u_db, k, normalize=True, apply_sigmoid=True, algo=algo)
+        idx, val, gap = ops.knn_cosine(u_q, u_db, k, normalize=True, apply_sigmoid=True, algo=algo, eps=eps)[:3]
     else:
         U_db, U_q, w2, b2 = sim_net.mlp_operands(z_db, z_q)
-        idx, val, gap = ops.knn_addrelu(U_q, U_db, w2, b2, k, apply_sigmoid=True)
+        idx, val, gap = ops.knn_addrelu(U_q, U_db, w2, b2, k, apply_sigmoid=True, eps=eps)[:3]
     return idx, val, gap
 
 
 def _edges_from_topk(idx):
-    """edge = (neighbour, query) for every kept neighbour, query-major like the reference's buckets."""
+    """edge = (neighbour, query) for every kept neighbour (idx >= 0), query-major like the reference's buckets."""
     nq, k = idx.shape
     to = torch.arange(nq, device=idx.device).unsqueeze(1).expand(nq, k)
-    return torch.stack((idx.reshape(-1), to.reshape(-1)), dim=0)
+    edges = torch.stack((idx.reshape(-1), to.reshape(-1)), dim=0)
+    return edges[:, edges[0] >= 0]
 
 
 def add_topk_sim_cross_domain_edges(data_src, data_tar, model, epsilon=0.5, k=3, batch_size=1000, apply_epsilon=False,
@@ -53,8 +55,8 @@ def add_topk_sim_cross_domain_edges(data_src, data_tar, model, epsilon=0.5, k=3,
     [Nt,k] int64 CPU; probs_clf_src [Ns,C]; probs_clf_tar [Nt,C])`` like the reference.  Within a row the
     neighbours come best first (the reference's ``topk(sorted=False)`` order is unspecified).
     ``epsilon`` is accepted and, as in the reference (where the argument is never read), ignored unless
-    ``apply_epsilon=True``, which drops pairs with similarity <= epsilon.  ``batch_size`` is ignored:
-    nothing is materialised per batch.
+    ``apply_epsilon=True``, which drops pairs with similarity <= epsilon inside the kernel's selection epilogue
+    (``idx_src_mat`` then holds -1 at the dropped places).  ``batch_size`` is ignored: nothing is materialised per batch.
     """
     with torch.no_grad():
         model.eval()
@@ -62,12 +64,10 @@ def add_topk_sim_cross_domain_edges(data_src, data_tar, model, epsilon=0.5, k=3,
         z_tar = model.embed_target(data_tar)
         probs_src, probs_tar = model.clf_probs(z_src), model.clf_probs(z_tar)
         if probs_src is None:   # source_clf=False: the reference returns zeros.exp() == ones
-            probs_src = torch.ones((z_src.shape[0], int(data_src.y.max().item()) + 1))
-            probs_tar = torch.ones((z_tar.shape[0], int(data_tar.y.max().item()) + 1))
-        idx, val, gap = _knn(model.source_learner.sim_net, z_src, z_tar, k, algo)
-        edge_index = _edges_from_topk(idx)
-        if apply_epsilon:
-            edge_index = edge_index[:, val.reshape(-1) > epsilon]
+            probs_src = torch.ones((z_src.shape[0], int(data_src.y.max().item()) + 1), device=z_src.device)
+            probs_tar = torch.ones((z_tar.shape[0], int(data_tar.y.max().item()) + 1), device=z_tar.device)
+        idx, val, gap = _knn(model.source_learner.sim_net, z_src, z_tar, k, algo, eps=epsilon if apply_epsilon else None)
+        edge_index = _edges_from_topk(idx)      # the threshold was applied by the kernel's selection epilogue
         if verbose:
             print("Current homophily ratio:", _homophily(data_src.y, data_tar.y, edge_index))
         edge_index = coalesce(edge_index)
@@ -91,61 +91,46 @@ def add_topk_sim_within_domain_edges(data_src, model, k=3, batch_size=1000, doma
     return out + (gap.cpu(),) if return_gap else out
 
 
-def _quantile(v, q):
-    """torch.quantile (linear interpolation) without its 16 M-element cap: sort once, interpolate."""
-    v = v.float().sort().values
-    pos = q * (v.numel() - 1)
-    lo = int(pos)
-    hi = min(lo + 1, v.numel() - 1)
-    return v[lo] + (v[hi] - v[lo]) * (pos - lo)
-
-
-def _validity_mask(e_sim, rules, thres_conf_quantile):
-    e_sim = e_sim.reshape(-1)
-    remove = e_sim < _quantile(e_sim, thres_conf_quantile)      # 1. low similarity-net confidence
-    for r in rules:
-        remove = remove | r
-    return remove
+def _report(counts, n_out, y_from, y_to, out, verbose):
+    if verbose:
+        c = counts.tolist()
+        print("1. remove low SimNet Confidence edges:", c[0])
+        print("2. remove edges that include node with wrong pred label compared with training label (ground truth):", c[1])
+        print("3. remove edges that the clf predicted label of two nodes (end points) are different:", c[2])
+        print("4. remove low raw_feat_sim edges:", c[3])
+        print("[Done] Totally remove edges: {} | Current total edge num: {}".format(sum(c[:4]), n_out))
+        print("Current homophily ratio:", _homophily(y_from, y_to, out))
 
 
 def check_added_edges_cross_domain_validity(edge_index_added, e_sim, data_src, data_tar, probs_clf_src, probs_clf_tar,
                                             thres_conf_quantile=0.1, thres_feat_sim=0.0, verbose=True):
-    """The 4-rule filter of main_bridged_graph.py:225-264 as a handful of device-wide elementwise ops.
-    ``e_sim`` is matched positionally with the columns of ``edge_index_added``, as in the reference; pass
-    similarities in the edge order you want compared (the reference passes the [Nt, k] matrix flattened
-    against the re-sorted coalesced list)."""
+    """The 4-rule filter of main_bridged_graph.py:225-264 on the device: the similarity quantile by radix select
+    (``ops.quantile``: no sort, no 16 M-element cap) and the four rules -- the per-edge raw-feature cosine included --
+    in one kernel (``ops.edge_validity``).  ``e_sim`` is matched positionally with the columns of
+    ``edge_index_added``, as in the reference; pass similarities in the edge order you want compared (the reference
+    passes the [Nt, k] matrix flattened against the re-sorted coalesced list)."""
     dev = data_src.x.device
     ei = edge_index_added.to(dev)
-    e0, e1 = ei[0], ei[1]
+    e_sim = e_sim.to(dev).reshape(-1).float()
     pred_s, pred_t = probs_clf_src.to(dev).argmax(dim=1), probs_clf_tar.to(dev).argmax(dim=1)
-    cos = torch.nn.functional.cosine_similarity(data_src.x[e0], data_tar.x[e1])
-    remove = _validity_mask(e_sim.to(dev), [
-        pred_s[e0] != data_src.y[e0],                                              # 2. wrong source prediction
-        (pred_t[e1] != data_tar.y[e1]) & data_tar.train_mask[e1],                  #    wrong labelled-target prediction
-        pred_s[e0] != pred_t[e1],                                                  # 3. end points disagree
-        cos < thres_feat_sim], thres_conf_quantile)                                # 4. raw features dissimilar
-    out = ei[:, ~remove]
-    if verbose:
-        print("[Done] Totally remove edges: {} | Current total edge num: {}".format(int(remove.sum()), out.shape[1]))
-        print("Current homophily ratio:", _homophily(data_src.y, data_tar.y, out))
+    keep, counts = ops.edge_validity(ei, e_sim, ops.quantile(e_sim, thres_conf_quantile), pred_s, data_src.y, pred_t, data_tar.y,
+                                     None, data_tar.train_mask, data_src.x, data_tar.x, thres_feat_sim)
+    out = ei[:, keep]
+    _report(counts, out.shape[1], data_src.y, data_tar.y, out, verbose)
     return out.to(edge_index_added.device)
 
 
 def check_added_edges_within_domain_validity(edge_index_added, e_sim, data_in, probs_clf, thres_conf_quantile=0.1,
                                              thres_feat_sim=0.0, verbose=True):
-    """main_bridged_graph.py:123-161 (both label rules gated by the train mask of the destination end)."""
+    """main_bridged_graph.py:123-161 (both label rules gated by the train mask of the destination end), same kernels."""
     dev = data_in.x.device
     ei = edge_index_added.to(dev)
-    e0, e1 = ei[0], ei[1]
+    e_sim = e_sim.to(dev).reshape(-1).float()
     pred = probs_clf.to(dev).argmax(dim=1)
-    cos = torch.nn.functional.cosine_similarity(data_in.x[e0], data_in.x[e1])
-    tm = data_in.train_mask[e1]
-    remove = _validity_mask(e_sim.to(dev), [(pred[e0] != data_in.y[e0]) & tm, (pred[e1] != data_in.y[e1]) & tm,
-                                            pred[e0] != pred[e1], cos < thres_feat_sim], thres_conf_quantile)
-    out = ei[:, ~remove]
-    if verbose:
-        print("[Done] Totally remove edges: {} | Current total edge num: {}".format(int(remove.sum()), out.shape[1]))
-        print("Current homophily ratio:", _homophily(data_in.y, data_in.y, out))
+    keep, counts = ops.edge_validity(ei, e_sim, ops.quantile(e_sim, thres_conf_quantile), pred, data_in.y, pred, data_in.y,
+                                     data_in.train_mask, data_in.train_mask, data_in.x, data_in.x, thres_feat_sim)
+    out = ei[:, keep]
+    _report(counts, out.shape[1], data_in.y, data_in.y, out, verbose)
     return out.to(edge_index_added.device)
 
 
@@ -228,10 +213,45 @@ def gen_bridged_graph(args, data_src, data_tar, device, path_ckpt, mapper_idx_sr
         eval_homophily(data_merge)
         eval_bridged_Graph(data_merge)
     if getattr(args, "save", False):
-        os.makedirs("../data_bridged_graph", exist_ok=True)
-        torch.save({k: getattr(data_merge, k).cpu() for k in data_merge.keys()},
-                   f"../data_bridged_graph/{args.dataset_name}_bridged_graph.pt")
+        out_dir = getattr(args, "out_dir", None) or "../data_bridged_graph"
+        os.makedirs(out_dir, exist_ok=True)
+        # (the reference pickles a PyG Data here, :317-320; data.load_graph reads both that and this dict form)
+        save_graph(data_merge, os.path.join(out_dir, f"{args.dataset_name}_bridged_graph.pt"))
     return data_merge
+
+
+def split_domains(data):
+    """(data_src, data_tar) of a merged graph by ``central_mask``, with local ids and the intra-domain edges only --
+    what utils.dataset_conversion (utils.py:41-99) hands to gen_bridged_graph -- plus the id maps
+    {original id: local id} that ``reorder`` takes."""
+    c = data.central_mask
+    ids_s, ids_t = torch.nonzero(c).view(-1), torch.nonzero(~c).view(-1)
+    local = torch.empty(c.shape[0], dtype=torch.long, device=c.device)
+    local[ids_s] = torch.arange(ids_s.numel(), device=c.device)
+    local[ids_t] = torch.arange(ids_t.numel(), device=c.device)
+    ei = data.edge_index
+    ms, mt = c[ei[0]] & c[ei[1]], (~c[ei[0]]) & (~c[ei[1]])
+    parts = []
+    for ids, m in ((ids_s, ms), (ids_t, mt)):
+        kw = {k: getattr(data, k)[ids] for k in ("x", "y", "train_mask", "val_mask", "test_mask") if hasattr(data, k)}
+        parts.append(Data(edge_index=local[ei[:, m]], **kw))
+    maps = [{int(o): i for i, o in enumerate(ids.tolist())} for ids in (ids_s, ids_t)]
+    return parts[0], parts[1], maps[0], maps[1]
+
+
+def main(args):
+    """Step 1 from a graph file and a trained similarity learner (main_bridged_graph.py:325-357 without the
+    adversarial training of the learner, which is outside the accelerated path): ``--path_data`` holds the two
+    domains in one graph (``central_mask`` marks the source nodes; only intra-domain edges are used),
+    ``--path_ckpt`` the learner's state_dict."""
+    if not args.path_data or not args.path_ckpt:
+        raise SystemExit("--path_data and --path_ckpt are required")
+    if not torch.cuda.is_available():
+        raise RuntimeError("bridged_gnn_b200 needs a CUDA device (sm_100a); there is no CPU path")
+    device = torch.device("cuda", args.gpu)
+    data_src, data_tar, m_src, m_tar = split_domains(load_graph(args.path_data))
+    return gen_bridged_graph(args, data_src, data_tar, device, args.path_ckpt, m_src, m_tar, epsilon=args.epsilon,
+                             batch_size=args.batch_size)
 
 
 def parse_args(argv=None):
@@ -257,4 +277,9 @@ def parse_args(argv=None):
     p.add_argument("--gpu", type=int, default=0)
     p.add_argument("--path_data", type=str, default=None, help="bridged-graph .dat to take features / split from")
     p.add_argument("--path_ckpt", type=str, default=None)
+    p.add_argument("--out_dir", type=str, default=None, help="where --save writes (default ../data_bridged_graph)")
     return p.parse_args(argv)
+
+
+if __name__ == "__main__":
+    main(parse_args())

@@ -13,7 +13,9 @@ import types
 import torch
 import torch.nn.functional as F
 
-from .data import Data, load_pyg_dat, to_undirected
+import os
+
+from .data import Data, load_graph, to_undirected
 from .utils import eval_bridged_Graph
 from .models import GCNNet, GraphSAGE, KTGNN_no_complement
 
@@ -99,9 +101,16 @@ def get_each_clf_res(data, model, metric="f1", f1_average="macro"):
 
 
 def train_gnn(data, gnn="KTGNN", num_layer=2, hidden=64, num_epoch=300, lr=1e-3, weight_decay=5e-3, Lambda=1.0,
-              metric="f1", device=None, verbose=True):
-    """:143-262: KTGNN_no_complement(F, C, layers, hidden, root_weight=False, use_bn=True), Adam + StepLR(100, 0.1),
-    model selection on the validation score."""
+              metric="f1", device=None, verbose=True, select="loss_target", save=False, dataset_name="graph",
+              ckpt_dir="../ckpt", track_each_clf=False):
+    """:143-262: KTGNN_no_complement(F, C, layers, hidden, root_weight=False, use_bn=True), Adam + StepLR(100, 0.1).
+    Model selection follows the reference (:238-245): the epoch with the lowest ``loss_target`` (train-split NLL of the
+    transformed target classifier, ``train()[1]``; for the non-KT-GNN models of the noDTC loop, :374-380, the training
+    loss) is reported, and its state_dict is written to ``{ckpt_dir}/model_{gnn}_{dataset_name}_best.ckpt`` when
+    ``save``.  ``select="val"`` picks the highest validation score instead (not what the reference does).
+    ``track_each_clf`` also records get_each_clf_res per epoch (:227-230), returned in ``best["each_clf"]``."""
+    if select not in ("loss_target", "val"):
+        raise ValueError("select must be 'loss_target' (reference) or 'val'")
     device = device or _device()
     data = data.to(device)
     nf, nc = data.x.shape[1], int(data.y.max().item()) + 1
@@ -114,17 +123,27 @@ def train_gnn(data, gnn="KTGNN", num_layer=2, hidden=64, num_epoch=300, lr=1e-3,
     model = model.to(device)
     opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
     sched = torch.optim.lr_scheduler.StepLR(opt, step_size=100, gamma=0.1)
-    best = {"val": -1.0, "test": 0.0, "epoch": 0}
+    best = {"train": 0.0, "val": -1.0 if select == "val" else 0.0, "test": 0.0, "loss": 666.0, "epoch": 0}   # :209-214
+    each = []
     for epoch in range(1, num_epoch + 1):
         t0 = time.time()
-        loss = train(data, model, opt, gnn=gnn, Lambda=Lambda)[0]
+        losses = train(data, model, opt, gnn=gnn, Lambda=Lambda)
+        loss = losses[0]
+        crit = losses[1] if gnn == "KTGNN" else loss
         tr, va, te = test(data, model, gnn=gnn, metric=metric)
+        if track_each_clf and gnn == "KTGNN":
+            each.append(get_each_clf_res(data, model, metric="f1"))
         sched.step()
-        if va > best["val"]:
-            best = {"val": va, "test": te, "epoch": epoch}
+        if (crit < best["loss"]) if select == "loss_target" else (va > best["val"]):
+            best = {"train": tr, "val": va, "test": te, "loss": crit, "epoch": epoch}
+            if save:
+                os.makedirs(ckpt_dir, exist_ok=True)
+                torch.save(model.state_dict(), os.path.join(ckpt_dir, "model_{}_{}_best.ckpt".format(gnn, dataset_name)))
         if verbose and (epoch % 10 == 0 or epoch == 1):
             print("Epoch {:03d} | loss {:.4f} | train {:.4f} val {:.4f} test {:.4f} | best test {:.4f} @ {} | {:.3f} s/epoch"
                   .format(epoch, loss, tr, va, te, best["test"], best["epoch"], time.time() - t0))
+    if track_each_clf:
+        best["each_clf"] = each
     return model, best
 
 
@@ -134,7 +153,7 @@ def train_gnn_noDTC(data, gnn="GraphSAGE", **kw):
 
 
 def main(args):
-    data = load_pyg_dat(args.path_data)
+    data = load_graph(args.path_data)
     device = _device(args.gpu)
     data = Data(**{k: getattr(data, k) for k in data.keys()}).to(device)
     eval_bridged_Graph(data)                                   # main_graph_knowledge_transfer.py:403
@@ -143,7 +162,8 @@ def main(args):
         # the reference discards ToUndirected's return value (:410-411, in place only on old PyG); BASELINE.json
         # names the undirected graph, so it is applied here
         data.edge_index = to_undirected(data.edge_index, data.x.shape[0])
-    kw = dict(num_layer=args.num_layer, hidden=args.hidden_dim, num_epoch=args.num_epoch, metric=args.metric, device=device)
+    kw = dict(num_layer=args.num_layer, hidden=args.hidden_dim, num_epoch=args.num_epoch, metric=args.metric, device=device,
+              select=args.select, save=args.save, dataset_name=args.dataset_name)
     if args.no_dtc:
         return train_gnn_noDTC(data, **kw)
     return train_gnn(data, gnn=args.model_name, Lambda=args.Lambda, **kw)
@@ -161,6 +181,10 @@ def parse_args(argv=None):
     p.add_argument("--to_undirected", action="store_true")
     p.add_argument("--no_dtc", action="store_true")
     p.add_argument("--gpu", type=int, default=0)
+    p.add_argument("--dataset_name", type=str, default="graph")
+    p.add_argument("--save", action="store_true", help="write the selected epoch's state_dict to ../ckpt (reference :244-245)")
+    p.add_argument("--select", type=str, default="loss_target", choices=["loss_target", "val"],
+                   help="model selection: lowest loss_target (the reference's criterion) or highest validation score")
     return p.parse_args(argv)
 
 

@@ -76,9 +76,15 @@ class AdaptedConv(nn.Module):
         for m in self.children():
             m.reset_parameters()
 
+    # The caches below are keyed on the mask TENSOR (held in the key, compared by identity) and its version: an
+    # address alone could be recycled by the allocator for a new mask of the same length.
+    @staticmethod
+    def _same(key, mask, *extra):
+        return key is not None and key[0] is mask and key[1] == mask._version and key[2:] == extra
+
     def _domain_rows(self, central_mask, dtype):
-        key = (central_mask.data_ptr(), central_mask._version, central_mask.shape[0], dtype)
-        if self._rows_key != key:
+        key = (central_mask, central_mask._version, dtype)
+        if not self._same(self._rows_key, central_mask, dtype):
             cf = central_mask.to(dtype)
             ns = cf.sum().clamp(min=1.0)
             nt = (central_mask.shape[0] - cf.sum()).clamp(min=1.0)
@@ -86,8 +92,8 @@ class AdaptedConv(nn.Module):
         return self._rows
 
     def _domain_counts(self, central_mask):
-        key = (central_mask.data_ptr(), central_mask._version, central_mask.shape[0])
-        if getattr(self, "_counts_key", None) != key:
+        key = (central_mask, central_mask._version)
+        if not self._same(getattr(self, "_counts_key", None), central_mask):
             ns = central_mask.sum().clamp(min=1).to(torch.float32)
             nt = (central_mask.shape[0] - central_mask.sum()).clamp(min=1).to(torch.float32)
             self._counts_key = key
@@ -113,8 +119,8 @@ class AdaptedConv(nn.Module):
         return w_s, w_t, b_s, b_t, a1, a2, cp
 
     def _dst_is_src(self, central_mask):
-        key = (central_mask.data_ptr(), central_mask._version, central_mask.shape[0])
-        if self._mask_key != key:
+        key = (central_mask, central_mask._version)
+        if not self._same(self._mask_key, central_mask):
             self._mask_key, self._mask_u8 = key, central_mask.to(torch.uint8).contiguous()
         return self._mask_u8
 

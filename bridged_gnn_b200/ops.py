@@ -23,7 +23,7 @@ def _f32c(t):
 
 
 # ----------------------------------------------------------------------------------- kNN build
-def knn_cosine(q, db, k, normalize=True, apply_sigmoid=True, algo="auto"):
+def knn_cosine(q, db, k, normalize=True, apply_sigmoid=True, algo="auto", eps=None):
     """Per-row top-k of sigmoid(cos(q_i, db_j)) without materialising the [nq, ndb] matrix.
 
     Replaces the pair enumeration + ``Similar.similarity*`` + ``sim_mat.topk`` of the reference
@@ -31,6 +31,10 @@ def knn_cosine(q, db, k, normalize=True, apply_sigmoid=True, algo="auto"):
     fp32 similarity desc, db index asc.  Returns ``(idx int64 [nq,k], val fp32 [nq,k] best first,
     gap fp32 [nq] = v_k - v_(k+1), stats int32 [4])``; ``stats[0]`` = rows the tensor-core path
     re-did exactly.  ``q is db`` is the within-domain case (self matches are kept).
+
+    ``eps`` (float): the bridge-matching threshold fused into the selection epilogue -- neighbours whose similarity
+    is not > eps get ``idx = -1`` (their similarity stays in ``val``) and a fifth output ``count int32 [nq]`` gives
+    the number of neighbours kept per row (a prefix: rows are best first).
     """
     lib = _lib.load()
     q, db = _f32c(q), (_f32c(db) if db is not q else None)
@@ -52,16 +56,19 @@ def knn_cosine(q, db, k, normalize=True, apply_sigmoid=True, algo="auto"):
     if nbytes == 0:
         raise ValueError("invalid kNN arguments (need 1 <= k <= min(ndb, 255))")
     ws = _lib.workspace(nbytes, dev)
+    count = None if eps is None else torch.empty((nq,), dtype=torch.int32, device=dev)
     with _lib.call("bgnn_knn_cosine_f32", "bgnn_knn_cosine_f32[simt]" if a == KNN_SIMT_F32 else None):
-        _lib.check(lib.bgnn_knn_cosine_f32(_lib.ptr(q), nq, _lib.ptr(db), ndb, d, k, int(normalize),
-                                           int(apply_sigmoid), a, _lib.ptr(idx), _lib.ptr(val), _lib.ptr(gap),
-                                           _lib.ptr(stats), _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
-    return idx, val, gap, stats
+        _lib.check(lib.bgnn_knn_cosine_eps_f32(_lib.ptr(q), nq, _lib.ptr(db), ndb, d, k, int(normalize),
+                                               int(apply_sigmoid), a, float("nan") if eps is None else float(eps),
+                                               _lib.ptr(idx), _lib.ptr(val), _lib.ptr(gap), _lib.ptr(count, allow_none=True),
+                                               _lib.ptr(stats), _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+    return (idx, val, gap, stats) if eps is None else (idx, val, gap, stats, count)
 
 
-def knn_addrelu(Uq, Udb, w2, b2, k, apply_sigmoid=True):
+def knn_addrelu(Uq, Udb, w2, b2, k, apply_sigmoid=True, eps=None):
     """Per-row top-k of sigmoid(sum_h w2[h] relu(Uq[i,h] + Udb[j,h]) + b2): the eval-mode fold of
-    ``Similar_v2(mode='mlp')`` (models/models.py:918-925, 949-954).  Same outputs as knn_cosine."""
+    ``Similar_v2(mode='mlp')`` (models/models.py:918-925, 949-954).  Returns (idx, val, gap), plus ``count`` when
+    ``eps`` is given (see knn_cosine)."""
     lib = _lib.load()
     Uq, w2 = _f32c(Uq), _f32c(w2).view(-1)
     Udb = Uq if Udb is Uq else _f32c(Udb)
@@ -77,11 +84,13 @@ def knn_addrelu(Uq, Udb, w2, b2, k, apply_sigmoid=True):
     if nbytes == 0:
         raise ValueError("invalid kNN arguments (need 1 <= k <= min(ndb, 255))")
     ws = _lib.workspace(nbytes, dev)
+    count = None if eps is None else torch.empty((nq,), dtype=torch.int32, device=dev)
     with _lib.call("bgnn_knn_addrelu_f32"):
-        _lib.check(lib.bgnn_knn_addrelu_f32(_lib.ptr(Uq), nq, _lib.ptr(Udb), ndb, h, _lib.ptr(w2), float(b2), k,
-                                            int(apply_sigmoid), _lib.ptr(idx), _lib.ptr(val), _lib.ptr(gap),
-                                            _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
-    return idx, val, gap
+        _lib.check(lib.bgnn_knn_addrelu_eps_f32(_lib.ptr(Uq), nq, _lib.ptr(Udb), ndb, h, _lib.ptr(w2), float(b2), k,
+                                                int(apply_sigmoid), float("nan") if eps is None else float(eps),
+                                                _lib.ptr(idx), _lib.ptr(val), _lib.ptr(gap),
+                                                _lib.ptr(count, allow_none=True), _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+    return (idx, val, gap) if eps is None else (idx, val, gap, count)
 
 
 # ----------------------------------------------------------------------------------- graph format
@@ -95,14 +104,16 @@ def edges_to_csr(src, dst, n, dedup=False, want_perm=True):
     rowptr = torch.empty((n + 1,), dtype=torch.int32, device=dev)
     col = torch.empty((max(e, 1),), dtype=torch.int32, device=dev)
     perm = torch.empty((max(e, 1),), dtype=torch.int64, device=dev) if want_perm else None
-    e_out = torch.zeros((1,), dtype=torch.int64, device=dev)
+    e_out = torch.zeros((2,), dtype=torch.int64, device=dev)
     ws = _lib.workspace(lib.bgnn_edges_to_csr_workspace_bytes(e), dev)
     with _lib.call("bgnn_edges_to_csr"):
         _lib.check(lib.bgnn_edges_to_csr(_lib.ptr(src, torch.int64) if e else None,
                                          _lib.ptr(dst, torch.int64) if e else None, e, n, int(dedup), _lib.ptr(rowptr),
                                          _lib.ptr(col), _lib.ptr(perm, allow_none=True), _lib.ptr(e_out), _lib.ptr(ws),
                                          ws.numel(), _lib.stream(dev)))
-    ne = int(e_out.item()) if dedup else e
+    ne, bad = e_out.tolist()      # one sync per graph build (graphs are cached by the layers)
+    if bad:
+        raise IndexError("edge_index holds %d edge(s) with a node id outside [0, %d)" % (bad, n))
     return rowptr, col[:ne], (perm[:ne] if want_perm else None), ne
 
 
@@ -115,6 +126,61 @@ def coalesce(edge_index, num_nodes=None):
     counts = (rowptr[1:] - rowptr[:-1]).to(torch.int64)
     row = torch.repeat_interleave(torch.arange(n, device=edge_index.device), counts)
     return torch.stack((row, col.to(torch.int64)), 0)
+
+
+# ----------------------------------------------------------------------------------- edge-validity filters
+def quantile(v, q):
+    """``v.quantile(q)`` (linear interpolation, torch's float32 rank arithmetic) for a 1-D fp32 CUDA tensor by radix
+    select: no sort and none of torch.quantile's 16 M-element cap (main_bridged_graph.py:134, 236).  Returns a
+    0-dim device tensor; no host synchronisation."""
+    import numpy as np
+    lib = _lib.load()
+    v = _f32c(v).view(-1)
+    n = v.numel()
+    if n == 0:
+        raise ValueError("quantile of an empty tensor")
+    if n - 1 < (1 << 24):      # torch: ranks = q * (n - 1) in the input's dtype
+        rank = np.float32(q) * np.float32(n - 1)
+        lo = int(np.floor(rank))
+        w = float(np.float32(rank - np.float32(lo)))
+    else:                      # beyond torch.quantile's own limit: double arithmetic
+        rank = float(q) * (n - 1)
+        lo = int(rank)
+        w = rank - lo
+    lo = min(max(lo, 0), n - 1)
+    out = torch.empty((3,), dtype=torch.float32, device=v.device)
+    ws = _lib.workspace(lib.bgnn_quantile_workspace_bytes(), v.device)
+    with _lib.call("bgnn_quantile_f32"):
+        _lib.check(lib.bgnn_quantile_f32(_lib.ptr(v), n, lo, w, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream(v.device)))
+    return out[2]
+
+
+def edge_validity(edge_index, e_sim, thr_conf, pred_a, y_a, pred_b, y_b, gate_a, gate_b, x_a, x_b, thres_feat_sim):
+    """The four removal rules of check_added_edges_{cross,within}_domain_validity (main_bridged_graph.py:225-264,
+    123-161) in one kernel, warp per edge.  Returns (keep bool [E], counts int64 [5] = newly removed by rule 1..4,
+    kept).  ``thr_conf``: 0-dim device tensor (``quantile``); gates: bool [n_b] or None."""
+    lib = _lib.load()
+    dev = x_a.device
+    ei = edge_index.to(torch.int64).contiguous()
+    e = ei.shape[1]
+    i64, u8 = torch.int64, torch.uint8
+    keep = torch.empty((max(e, 1),), dtype=u8, device=dev)
+    counts = torch.empty((5,), dtype=i64, device=dev)
+    x_a, x_b = _f32c(x_a), (_f32c(x_b) if x_b is not x_a else None)
+    if x_b is None:
+        x_b = x_a
+    g_a = None if gate_a is None else gate_a.to(u8).contiguous()
+    g_b = None if gate_b is None else gate_b.to(u8).contiguous()
+    thr = None if thr_conf is None else thr_conf.to(torch.float32).reshape(1).contiguous()
+    with _lib.call("bgnn_edge_validity_f32"):
+        _lib.check(lib.bgnn_edge_validity_f32(_lib.ptr(ei[0].contiguous()) if e else None, _lib.ptr(ei[1].contiguous()) if e else None, e,
+                                              _lib.ptr(_f32c(e_sim).view(-1)) if e else None, _lib.ptr(thr, allow_none=True),
+                                              _lib.ptr(pred_a.to(i64).contiguous()), _lib.ptr(y_a.to(i64).contiguous()),
+                                              _lib.ptr(pred_b.to(i64).contiguous()), _lib.ptr(y_b.to(i64).contiguous()),
+                                              _lib.ptr(g_a, u8, True), _lib.ptr(g_b, u8, True), _lib.ptr(x_a), _lib.ptr(x_b),
+                                              x_a.shape[1], float(thres_feat_sim), _lib.ptr(keep), _lib.ptr(counts),
+                                              _lib.stream(dev)))
+    return keep[:e].bool(), counts
 
 
 WIDE_ROW = 32         # feature widths from here on (rows of >= 128 B) process rows in degree order

@@ -60,6 +60,15 @@ int bgnn_knn_cosine_f32(const float* q, int64_t nq, const float* db, int64_t ndb
                         int apply_sigmoid, int algo, int64_t* out_idx, float* out_val, float* out_gap,
                         int32_t* out_stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same with the bridge-matching threshold `epsilon` (main_bridged_graph.py:33; the reference accepts the argument
+ * and never reads it) fused into the selection epilogue: a neighbour is emitted only if its similarity is > eps
+ * (eps = NaN: off, identical to bgnn_knn_cosine_f32).  Dropped places keep their similarity in out_val and get
+ * out_idx = -1; rows are best first, so the kept neighbours are a prefix of length out_count[row] (int32 [nq],
+ * may be NULL).  out_gap is unaffected. */
+int bgnn_knn_cosine_eps_f32(const float* q, int64_t nq, const float* db, int64_t ndb, int d, int k, int normalize,
+                            int apply_sigmoid, int algo, float eps, int64_t* out_idx, float* out_val, float* out_gap,
+                            int32_t* out_count, int32_t* out_stats, void* workspace, size_t workspace_bytes, void* stream);
+
 /* v2 'mlp' head with eval-mode BatchNorm folded (models/models.py:918-925):
  * sim = sigmoid( sum_h w2[h] * relu(Uq[i,h] + Udb[j,h]) + b2 ),  Uq [nq,h], Udb [ndb,h], w2 [h]. */
 size_t bgnn_knn_addrelu_workspace_bytes(int64_t nq, int64_t ndb, int h, int k);
@@ -67,13 +76,43 @@ int bgnn_knn_addrelu_f32(const float* Uq, int64_t nq, const float* Udb, int64_t 
                          int k, int apply_sigmoid, int64_t* out_idx, float* out_val, float* out_gap,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+int bgnn_knn_addrelu_eps_f32(const float* Uq, int64_t nq, const float* Udb, int64_t ndb, int h, const float* w2, float b2,
+                             int k, int apply_sigmoid, float eps, int64_t* out_idx, float* out_val, float* out_gap,
+                             int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- edge-validity filters of the build -----------------------------------------------------
+ *
+ * bgnn_quantile_f32: order statistics of v[n] by radix select (no sort, no size cap).  rank_lo = floor(q (n-1)),
+ * weight = q (n-1) - rank_lo; out3 = (v_(rank_lo), v_(rank_lo+1), their linear interpolation as torch.quantile
+ * computes it).  Replaces e_sim.quantile(q) at main_bridged_graph.py:134, 236.
+ *
+ * bgnn_edge_validity_f32: the four removal rules of check_added_edges_cross_domain_validity /
+ * check_added_edges_within_domain_validity (main_bridged_graph.py:225-264, 123-161) in one pass over the edges:
+ *   1. e_sim[i] < *thr_conf (device scalar; NULL = rule off)
+ *   2. pred_a[e0] != y_a[e0] (only where gate_a[e1] != 0 when gate_a is given), or pred_b[e1] != y_b[e1] where
+ *      gate_b[e1] != 0 (gate_b NULL = everywhere)
+ *   3. pred_a[e0] != pred_b[e1]
+ *   4. cosine_similarity(x_a[e0], x_b[e1]) < thres_feat_sim   (x_a, x_b [*, d] raw features, ATen's formula)
+ * keep [e] bytes: 1 = edge survives.  counts [5] int64: edges newly removed by rule 1, 2, 3, 4 in that order
+ * (the numbers the reference prints) and the number kept.  cross-domain: a = source side, b = target side,
+ * gate_a = NULL, gate_b = target train_mask; within-domain: a = b, gate_a = gate_b = train_mask. */
+size_t bgnn_quantile_workspace_bytes(void);
+int bgnn_quantile_f32(const float* v, int64_t n, int64_t rank_lo, float weight, float* out3, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int bgnn_edge_validity_f32(const int64_t* e0, const int64_t* e1, int64_t e, const float* e_sim, const float* thr_conf,
+                           const int64_t* pred_a, const int64_t* y_a, const int64_t* pred_b, const int64_t* y_b,
+                           const uint8_t* gate_a, const uint8_t* gate_b, const float* x_a, const float* x_b, int d,
+                           float thres_feat_sim, uint8_t* keep, int64_t* counts, void* stream);
+
 /* ---- graph format: edge list -> destination-major CSR ---------------------------------------
  *
  * Replaces torch_sparse.SparseTensor(row=edge_index[1], col=edge_index[0]) (models/backbones.py:464)
  * and, with dedup=1, torch_geometric.utils.coalesce (main_bridged_graph.py:75,113,193) up to the
  * (dst,src) instead of (src,dst) sort order.  rowptr [n+1] int32, col [e] int32 (source of each
  * edge, rows sorted by destination then source), perm [e] int64 (position in the input edge list;
- * may be NULL), e_out [1] int64 (number of edges kept). */
+ * may be NULL), e_out [2] int64: [0] = number of edges kept, [1] = number of edges with a node id outside [0, n)
+ * (PyG raises an index error on those; here they are parked behind the last row where no kernel reads them, and the
+ * host layer turns a non-zero count into an error). */
 size_t bgnn_edges_to_csr_workspace_bytes(int64_t e);
 int bgnn_edges_to_csr(const int64_t* src, const int64_t* dst, int64_t e, int64_t n, int dedup, int32_t* rowptr,
                       int32_t* col, int64_t* perm, int64_t* e_out, void* workspace, size_t workspace_bytes,

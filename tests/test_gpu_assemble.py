@@ -1,0 +1,203 @@
+"""GPU parity of everything around the kNN sweep in the bridged-graph build: the within-domain entry points, the fused
+epsilon threshold, the edge-validity filters (radix-select quantile + one rule kernel), merge_graphs and reorder --
+against the golden vectors produced by the reference's own functions (tests/golden/make_golden.py) and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import sub_state
+from oracle import build_oracle as bo
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+NS = 2817
+DEV = "cuda:0"
+
+
+def _data(g, dev=DEV):
+    from bridged_gnn_b200.data import Data
+    x, y, c, ei = T(g["x"]), T(g["y"]), T(g["central_mask"]), T(g["edge_index"])
+    ms, mt = c[ei[0]] & c[ei[1]], (~c[ei[0]]) & (~c[ei[1]])
+    tm, vm, sm = T(g["train_mask"]), T(g["val_mask"]), T(g["test_mask"])
+    src = Data(x=x[:NS].clone(), y=y[:NS].clone(), edge_index=ei[:, ms].clone(), train_mask=tm[:NS].clone(),
+               val_mask=vm[:NS].clone(), test_mask=sm[:NS].clone())
+    tar = Data(x=x[NS:].clone(), y=y[NS:].clone(), edge_index=(ei[:, mt] - NS).clone(), train_mask=tm[NS:].clone(),
+               val_mask=vm[NS:].clone(), test_mask=sm[NS:].clone())
+    return src.to(dev), tar.to(dev)
+
+
+def _office_model(g, src, tar):
+    from bridged_gnn_b200.models import Adversarial_Learner_v2
+    model = Adversarial_Learner_v2(src, tar, dim_hidden=128, num_layer=2, source_clf=True, use_norm=True,
+                                   norm_mode="None", norm_scale=1.0, backbone="mlp", sim_mode="mlp")
+    model.load_state_dict(sub_state(g, "ckpt."), strict=False)
+    return model.eval().to(DEV)
+
+
+# ------------------------------------------------------------------ a7: within-domain entry points
+@pytest.mark.parametrize("domain", ["source", "target"])
+def test_within_domain_entry_point_matches_reference(office_build, domain):
+    """add_topk_sim_within_domain_edges (main_bridged_graph.py:77-120) on the office fixture, k_within = 3, both
+    domains (2817 x 2817 and 591 x 591): neighbour sets equal the reference's except in near-tie rows, similarities
+    within 2e-5 (embeddings are recomputed on the GPU), self matches kept, edge list coalesced (from, to)."""
+    from bridged_gnn_b200.main_bridged_graph import add_topk_sim_within_domain_edges
+    g = office_build
+    src, tar = _data(g)
+    model = _office_model(g, src, tar)
+    data, tag, z = (src, "within_src", T(g["z_src"])) if domain == "source" else (tar, "within_tar", T(g["z_tar"]))
+    n = data.x.shape[0]
+    ei, sim, idx, gap = add_topk_sim_within_domain_edges(data, model, k=3, batch_size=100, domain=domain, return_gap=True,
+                                                         verbose=False)
+    assert ei.device.type == "cpu" and ei.dtype == torch.int64 and sim.shape == (n, 3) and idx.shape == (n, 3)
+    full = bo.full_sim_matrix(z, z, sub_state(g, "ckpt."), "mlp")
+    cv, ci = bo.canonical_topk(full, 3)
+    tie_rows = set(torch.nonzero(bo.near_tie_rows(full, 3, 1e-5)).view(-1).tolist())
+    differ = {r for r in range(n) if set(ci[r].tolist()) != set(idx[r].tolist())}
+    assert differ <= tie_rows, sorted(differ - tie_rows)[:10]
+    assert float((sim - cv).abs().max()) < 2e-5
+    # against the reference's own outputs: torch.topk(sorted=False) picks other members only inside exact / near ties
+    ref_sets = [set(r.tolist()) for r in g[tag + "_idx"]]
+    differ_ref = {r for r in range(n) if ref_sets[r] != set(idx[r].tolist())}
+    assert differ_ref <= tie_rows
+    a, b = set(map(tuple, ei.t().tolist())), set(map(tuple, T(g[tag + "_edge_index"]).t().tolist()))
+    assert {e[1] for e in a ^ b} <= tie_rows
+    key = ei[0] * n + ei[1]
+    assert bool((key[1:] > key[:-1]).all())                       # coalesced: sorted by (from, to), no duplicates
+    assert ei.shape[1] == 3 * n                                   # k distinct neighbours per query row, nothing lost
+
+
+# ------------------------------------------------------------------ N1: epsilon inside the selection epilogue
+@pytest.mark.parametrize("algo", ["simt", "f16", "tc3"])
+def test_epsilon_threshold_fused_in_the_epilogue(algo):
+    from bridged_gnn_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    q, db = torch.randn(300, 128, generator=g).to(DEV), torch.randn(20000, 128, generator=g).to(DEV)
+    idx0, val0, gap0, _ = ops.knn_cosine(q, db, 20, algo=algo)
+    eps = float(val0[:, 9].median())                               # cuts inside most rows
+    idx1, val1, gap1, _, cnt = ops.knn_cosine(q, db, 20, algo=algo, eps=eps)
+    keep = val0 > eps
+    assert torch.equal(val0, val1) and torch.equal(gap0, gap1)
+    assert torch.equal(idx1, torch.where(keep, idx0, torch.full_like(idx0, -1)))
+    assert torch.equal(cnt.long(), keep.sum(1))
+    assert 0 < int(cnt.sum()) < idx0.numel()
+
+
+def test_apply_epsilon_entry_point(office_build):
+    """add_topk_sim_cross_domain_edges(..., epsilon=0.5, apply_epsilon=True): the edge list is the unthresholded one
+    minus the pairs with similarity <= 0.5 (0.7 % of the office top-20); default stays = reference."""
+    from bridged_gnn_b200.main_bridged_graph import add_topk_sim_cross_domain_edges
+    g = office_build
+    src, tar = _data(g)
+    model = _office_model(g, src, tar)
+    ei0, sim0, idx0, _, _ = add_topk_sim_cross_domain_edges(src, tar, model, epsilon=0.5, k=20, verbose=False)
+    ei1, sim1, idx1, _, _ = add_topk_sim_cross_domain_edges(src, tar, model, epsilon=0.5, k=20, apply_epsilon=True, verbose=False)
+    assert ei0.shape[1] == 591 * 20 and torch.equal(sim0, sim1)
+    keep = sim0 > 0.5
+    assert torch.equal(idx1, torch.where(keep, idx0, torch.full_like(idx0, -1)))
+    want = set(map(tuple, torch.stack((idx0[keep], torch.arange(591).unsqueeze(1).expand(591, 20)[keep])).t().tolist()))
+    assert set(map(tuple, ei1.t().tolist())) == want
+    assert 0 < ei0.shape[1] - ei1.shape[1] < 0.05 * ei0.shape[1]
+
+
+# ------------------------------------------------------------------ f1: quantile by radix select
+@pytest.mark.parametrize("n", [1, 2, 7, 1000, 11820, 300001])
+def test_quantile_matches_torch(n):
+    from bridged_gnn_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    v = torch.sigmoid(torch.randn(n, generator=g))
+    if n > 100:
+        v[torch.randint(0, n, (n // 3,), generator=g)] = v[0]     # a large tied group
+        v[::17] *= -1.0                                           # negative keys
+    vd = v.to(DEV)
+    for q in (0.0, 0.1, 0.25, 0.5, 0.9, 1.0):
+        got = ops.quantile(vd, q)
+        want = v.quantile(q=q)
+        assert float(got) == float(want), (n, q, float(got), float(want))
+
+
+def _near(x_a, x_b, ei, thr):
+    cos = torch.nn.functional.cosine_similarity(x_a[ei[0]], x_b[ei[1]])
+    return ((cos - thr).abs() < 1e-6)
+
+
+def _same_edges_up_to_threshold_ties(got, want, near_edges):
+    a, b = set(map(tuple, got.t().tolist())), set(map(tuple, want.t().tolist()))
+    assert (a ^ b) <= near_edges, sorted((a ^ b) - near_edges)[:5]
+
+
+def test_validity_filters_match_reference(office_build, office_assemble):
+    """check_added_edges_{cross,within}_domain_validity (main_bridged_graph.py:225-264, 123-161) on the device against
+    the reference's own outputs.  Edges whose raw-feature cosine lies within 1e-6 of thres_feat_sim may flip with the
+    summation order of the cosine; everything else is exact."""
+    from bridged_gnn_b200 import main_bridged_graph as mb
+    g, a = office_build, office_assemble
+    src, tar = _data(g)
+    ei_c, sim_c = T(g["cross_edge_index"]), T(g["cross_sim"])
+    ps, pt = T(g["probs_clf_src"]).to(DEV), T(g["probs_clf_tar"]).to(DEV)
+    xs, xt = T(g["x"])[:NS], T(g["x"])[NS:]
+    for tag, q, thr in (("cross_q10_f0", 0.1, 0.0), ("cross_q25_f30", 0.25, 0.3), ("cross_q0_f0", 0.0, 0.0)):
+        got = mb.check_added_edges_cross_domain_validity(ei_c, sim_c.view(-1), src, tar, ps, pt, q, thr, verbose=False)
+        assert got.device.type == "cpu"
+        m = _near(xs, xt, ei_c, thr)
+        _same_edges_up_to_threshold_ties(got, T(a[tag]), set(map(tuple, ei_c[:, m].t().tolist())))
+        if thr == 0.0:
+            assert torch.equal(got, T(a[tag]))
+    ei_s, sim_s = T(g["within_src_edge_index"]), T(g["within_src_sim"])
+    ei_t, sim_t = T(g["within_tar_edge_index"]), T(g["within_tar_sim"])
+    got = mb.check_added_edges_within_domain_validity(ei_s, sim_s.view(-1), src, ps, 0.1, 0.8, verbose=False)
+    _same_edges_up_to_threshold_ties(got, T(a["within_src_q10_f80"]), set(map(tuple, ei_s[:, _near(xs, xs, ei_s, 0.8)].t().tolist())))
+    for tag, q, thr in (("within_tar_q10_f80", 0.1, 0.8), ("within_tar_q50_f0", 0.5, 0.0)):
+        got = mb.check_added_edges_within_domain_validity(ei_t, sim_t.view(-1), tar, pt, q, thr, verbose=False)
+        _same_edges_up_to_threshold_ties(got, T(a[tag]), set(map(tuple, ei_t[:, _near(xt, xt, ei_t, thr)].t().tolist())))
+    # printed per-rule counts: same numbers as the sequential masks of the reference
+    from bridged_gnn_b200 import ops
+    pred_s, pred_t = ps.argmax(1), pt.argmax(1)
+    e_sim = sim_c.view(-1).to(DEV)
+    keep, counts = ops.edge_validity(ei_c.to(DEV), e_sim, ops.quantile(e_sim, 0.1), pred_s, src.y, pred_t, tar.y, None,
+                                     tar.train_mask, src.x, tar.x, 0.0)
+    e0, e1 = ei_c[0].to(DEV), ei_c[1].to(DEV)
+    r1 = e_sim < e_sim.quantile(q=0.1)
+    r2 = r1 | (pred_s[e0] != src.y[e0]) | ((pred_t[e1] != tar.y[e1]) & tar.train_mask[e1])
+    r3 = r2 | (pred_s[e0] != pred_t[e1])
+    assert counts.tolist()[:3] == [int(r1.sum()), int(r2.sum() - r1.sum()), int(r3.sum() - r2.sum())]
+    assert int(counts[4]) == int(keep.sum()) and int(counts.sum()) == ei_c.shape[1]
+
+
+def test_merge_graphs_and_reorder_match_reference(office_build, office_assemble):
+    """merge_graphs (main_bridged_graph.py:163-193) and reorder (:195-222) on the device, bit-exact against the
+    reference's outputs; the caller's edge lists are left untouched (the reference adds N_src in place)."""
+    from bridged_gnn_b200 import main_bridged_graph as mb
+    g, a = office_build, office_assemble
+    src, tar = _data(g)
+    src.y[T(a["merge.unlabelled_src"]).to(DEV)] = -1
+    ei_c = T(a["cross_q10_f0"]).to(DEV)
+    ei_s, ei_t = T(g["within_src_edge_index"]).to(DEV), T(g["within_tar_edge_index"]).to(DEV)
+    keep = ei_c.clone()
+    m = mb.merge_graphs(src, tar, ei_c, ei_s, ei_t)
+    assert torch.equal(ei_c, keep)
+    for k in ("edge_index", "y", "train_mask", "val_mask", "test_mask", "central_mask"):
+        assert torch.equal(getattr(m, k).cpu(), T(a["merge." + k])), k
+    assert torch.equal(m.x.double().sum(1).cpu(), T(a["merge.x_checksum"]))
+    src0, tar0 = _data(g)
+    m0 = mb.merge_graphs(src0, tar0, T(g["cross_edge_index"]).to(DEV))
+    assert torch.equal(m0.edge_index.cpu(), T(a["merge0.edge_index"]))
+    orig = T(a["reorder.orig_ids"])
+    n = orig.numel()
+    m_src = {int(orig[i]): i for i in range(NS)}
+    m_tar = {int(orig[NS + i]): i for i in range(n - NS)}
+    r = mb.reorder(m, src, m_src, m_tar)
+    for k in ("edge_index", "y", "train_mask", "val_mask", "test_mask", "central_mask"):
+        assert torch.equal(getattr(r, k).cpu(), T(a["reorder." + k])), k
+    assert torch.equal(r.x.double().sum(1).cpu(), T(a["reorder.x_checksum"]))
+
+
+def test_edge_ids_out_of_range_raise():
+    """a node id outside [0, n) must not reach the gather kernels (PyG raises an index error there)."""
+    from bridged_gnn_b200 import ops
+    ei = torch.tensor([[0, 1, 7, 2], [1, 2, 0, 0]], device=DEV)
+    with pytest.raises(IndexError):
+        ops.CSRGraph(ei, 4)
+    with pytest.raises(IndexError):
+        ops.coalesce(torch.tensor([[0, -1], [1, 0]], device=DEV), 4)
+    g = ops.CSRGraph(torch.tensor([[0, 1, 3, 2], [1, 2, 0, 0]], device=DEV), 4)       # n = 2^nb: the parking row is unused
+    assert g.rowptr.tolist() == [0, 2, 3, 4, 4] and g.col.tolist() == [2, 3, 0, 1]

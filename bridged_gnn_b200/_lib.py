@@ -36,6 +36,13 @@ SIGNATURES = {
     "bgnn_edges_to_csr_workspace_bytes": (_sz, [_i64]),
     "bgnn_edges_to_csr": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bgnn_spmm_csr_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "bgnn_spmm_csr_ld_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),
+    "bgnn_gatv2_fwd_part_f32": (_i32, [_vp] * 8 + [_f32, _i64, _i64, _i32] + [_vp] * 5),
+    "bgnn_gatv2_bwd_part_f32": (_i32, [_vp] * 7 + [_i64] + [_vp] * 5 + [_f32, _i64, _i64, _i64, _i32] + [_vp] * 10 + [_sz, _vp]),
+    "bgnn_gatv2_heads_fwd_part_f32": (_i32, [_vp] * 7 + [_f32, _i64, _i64, _i32, _i32] + [_vp] * 4),
+    "bgnn_gatv2_heads_bwd_part_f32": (_i32, [_vp] * 5 + [_i64] + [_vp] * 5 + [_f32, _i64, _i64, _i64, _i32, _i32] + [_vp] * 9 + [_sz, _vp]),
+    "bgnn_bn_relu_bwd_reduce_f32": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "bgnn_bn_relu_bwd_apply_f32": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "bgnn_gatv2_fwd_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "bgnn_gatv2_fwd_ord_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "bgnn_rows_by_degree_workspace_bytes": (_sz, [_i64]),
@@ -133,7 +140,9 @@ def workspace(nbytes, device):
 # bgnn_edges_to_csr are not counted)
 KERNELS_PER_CALL = {"bgnn_knn_cosine_f32": 13, "bgnn_knn_cosine_eps_f32": 13, "bgnn_knn_addrelu_eps_f32": 2, "bgnn_knn_cosine_f32[simt]": 4, "bgnn_knn_addrelu_f32": 2,
                     "bgnn_edges_to_csr": 4, "bgnn_quantile_f32": 11, "bgnn_edge_validity_f32": 2, "bgnn_spmm_csr_f32": 1, "bgnn_gatv2_fwd_f32": 1, "bgnn_gatv2_bwd_f32": 3,
-                    "bgnn_gatv2_fwd_ord_f32": 1, "bgnn_gatv2_bwd_ord_f32": 3, "bgnn_rows_by_degree": 1,
+                    "bgnn_gatv2_fwd_ord_f32": 1, "bgnn_gatv2_bwd_ord_f32": 3, "bgnn_gatv2_fwd_part_f32": 1, "bgnn_gatv2_bwd_part_f32": 3,
+                    "bgnn_gatv2_heads_fwd_part_f32": 1, "bgnn_gatv2_heads_bwd_part_f32": 3, "bgnn_spmm_csr_ld_f32": 1,
+                    "bgnn_bn_relu_bwd_reduce_f32": 2, "bgnn_bn_relu_bwd_apply_f32": 1, "bgnn_rows_by_degree": 1,
                     "bgnn_adapted_transform_fwd_f32": 1, "bgnn_adapted_transform_bwd_f32": 2,
                     "bgnn_gatv2_heads_fwd_f32": 1, "bgnn_gatv2_heads_bwd_f32": 3, "bgnn_adapted_skinny_fwd_f32": 1, "bgnn_adapted_skinny_bwd_f32": 2, "bgnn_domain_colsum_f32": 2, "bgnn_rowpanel_gemm_f32": 1, "bgnn_tf32_planes_f32": 1, "bgnn_adapted_skinny_heads_tc_fwd_f32": 1, "bgnn_wgrad_gemm_cat_f32": 2, "bgnn_adapted_transform_bwd_gates_f32": 2, "bgnn_adapted_skinny_heads_fwd_f32": 1, "bgnn_adapted_skinny_heads_pre_f32": 2,
                     "bgnn_adapted_skinny_heads_bwd_f32": 2, "bgnn_bn_relu_fwd_f32": 3, "bgnn_bn_relu_apply_f32": 1, "bgnn_bn_relu_bwd_f32": 3, "bgnn_wgrad_gemm_f32": 2,

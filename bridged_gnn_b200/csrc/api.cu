@@ -288,21 +288,35 @@ int bgnn_edges_to_csr(const int64_t* src, const int64_t* dst, int64_t e, int64_t
                              (long long*)e_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int bgnn_spmm_csr_ld_f32(const int32_t* rowptr, const int32_t* col, const float* edge_w, const float* gather_scale,
+                         const float* out_scale, const float* X, int64_t ldx, int64_t n_rows, int f, int reduce_mean,
+                         float* Y, int64_t ldy, void* stream) {
+  if (n_rows < 0 || f < 0 || ldx < f || ldy < f || (n_rows > 0 && f > 0 && (!rowptr || !X || !Y))) return BGNN_ERR_INVALID_ARG;
+  return launch_spmm_csr(rowptr, col, edge_w, gather_scale, out_scale, X, ldx, n_rows, f, reduce_mean, Y, ldy,
+                         (cudaStream_t)stream);
+}
+
 int bgnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* edge_w, const float* gather_scale,
                       const float* out_scale, const float* X, int64_t n_rows, int f, int reduce_mean, float* Y,
                       void* stream) {
-  if (n_rows < 0 || f < 0 || (n_rows > 0 && f > 0 && (!rowptr || !X || !Y))) return BGNN_ERR_INVALID_ARG;
-  return launch_spmm_csr(rowptr, col, edge_w, gather_scale, out_scale, X, n_rows, f, reduce_mean, Y,
-                         (cudaStream_t)stream);
+  return bgnn_spmm_csr_ld_f32(rowptr, col, edge_w, gather_scale, out_scale, X, f, n_rows, f, reduce_mean, Y, f, stream);
+}
+
+int bgnn_gatv2_fwd_part_f32(const int32_t* rowptr, const int32_t* col, const int32_t* row_order, const uint8_t* dst_is_src,
+                            const float* Hs, const float* Ht, const float* af_t2s, const float* af_s2t, float slope,
+                            int64_t n_rows, int64_t row_off, int c, float* out, float* row_max, float* row_sum, float* score,
+                            void* stream) {
+  if (n_rows < 0 || row_off < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n_rows > 0 && (!rowptr || !col || !dst_is_src || !Hs || !Ht || !af_t2s || !af_s2t || !out)) return BGNN_ERR_INVALID_ARG;
+  return launch_gatv2_fwd(rowptr, col, row_order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n_rows, row_off, c, out, row_max,
+                          row_sum, score, 0, (cudaStream_t)stream);
 }
 
 int bgnn_gatv2_fwd_ord_f32(const int32_t* rowptr, const int32_t* col, const int32_t* row_order, const uint8_t* dst_is_src,
                            const float* Hs, const float* Ht, const float* af_t2s, const float* af_s2t, float slope,
                            int64_t n, int c, float* out, float* row_max, float* row_sum, void* stream) {
-  if (n < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
-  if (n > 0 && (!rowptr || !col || !dst_is_src || !Hs || !Ht || !af_t2s || !af_s2t || !out)) return BGNN_ERR_INVALID_ARG;
-  return launch_gatv2_fwd(rowptr, col, row_order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, c, out, row_max, row_sum,
-                          (cudaStream_t)stream);
+  return bgnn_gatv2_fwd_part_f32(rowptr, col, row_order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, 0, c, out, row_max,
+                                 row_sum, nullptr, stream);
 }
 
 int bgnn_gatv2_fwd_f32(const int32_t* rowptr, const int32_t* col, const uint8_t* dst_is_src, const float* Hs,
@@ -325,20 +339,36 @@ size_t bgnn_gatv2_bwd_workspace_bytes(int64_t n, int64_t e, int c) {
   return (n < 0 || e < 0 || c <= 0) ? 0 : gatv2_bwd_workspace_bytes(n, e, c);
 }
 
+int bgnn_gatv2_bwd_part_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
+                            const int32_t* csr_to_csc, const int32_t* row_order, const int32_t* t_row_order, int64_t e,
+                            const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
+                            const float* af_s2t, float slope, int64_t n_rows, int64_t row_off, int64_t n_src, int c,
+                            const float* out, const float* row_max, const float* row_sum, const float* score,
+                            const float* gout, float* gHs, float* gHt, float* g_af_t2s, float* g_af_s2t, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  if (n_rows < 0 || n_src < 0 || row_off < 0 || row_off + n_rows > n_src || e < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n_src > 0 && (!t_rowptr || !dst_is_src || !Hs || !Ht || !af_t2s || !af_s2t || !g_af_t2s || !g_af_s2t || (!gHs && !gHt)))
+    return BGNN_ERR_INVALID_ARG;
+  if (n_rows > 0 && (!rowptr || !out || !row_max || !row_sum || !gout)) return BGNN_ERR_INVALID_ARG;
+  if (e > 0 && (!col || !t_col || !csr_to_csc)) return BGNN_ERR_INVALID_ARG;
+  const size_t need = gatv2_bwd_workspace_bytes(n_src, e, c);
+  if (need == 0) return BGNN_ERR_UNSUPPORTED;
+  if (n_src > 0 && (!workspace || workspace_bytes < need)) return BGNN_ERR_WORKSPACE;
+  return launch_gatv2_bwd(rowptr, col, t_rowptr, t_col, csr_to_csc, row_order, t_row_order, e, dst_is_src, Hs, Ht, af_t2s,
+                          af_s2t, slope, n_rows, row_off, n_src, c, out, row_max, row_sum, score, gout, gHs, gHt, g_af_t2s,
+                          g_af_s2t, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int bgnn_gatv2_bwd_ord_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
                            const int32_t* csr_to_csc, const int32_t* row_order, const int32_t* t_row_order, int64_t e,
                            const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
                            const float* af_s2t, float slope, int64_t n, int c, const float* out, const float* row_max,
                            const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
                            float* g_af_s2t, void* workspace, size_t workspace_bytes, void* stream) {
-  if (n < 0 || e < 0 || c <= 0) return BGNN_ERR_INVALID_ARG;
-  if (n > 0 && (!rowptr || !col || !t_rowptr || !t_col || !csr_to_csc || !dst_is_src || !Hs || !Ht || !af_t2s ||
-                !af_s2t || !out || !row_max || !row_sum || !gout || !gHs || !gHt || !g_af_t2s || !g_af_s2t))
-    return BGNN_ERR_INVALID_ARG;
-  if (n > 0 && (!workspace || workspace_bytes < gatv2_bwd_workspace_bytes(n, e, c))) return BGNN_ERR_WORKSPACE;
-  return launch_gatv2_bwd(rowptr, col, t_rowptr, t_col, csr_to_csc, row_order, t_row_order, e, dst_is_src, Hs, Ht, af_t2s,
-                          af_s2t, slope, n, c, out, row_max, row_sum, gout, gHs, gHt, g_af_t2s, g_af_s2t, workspace,
-                          workspace_bytes, (cudaStream_t)stream);
+  if (n > 0 && (!gHs || !gHt)) return BGNN_ERR_INVALID_ARG;
+  return bgnn_gatv2_bwd_part_f32(rowptr, col, t_rowptr, t_col, csr_to_csc, row_order, t_row_order, e, dst_is_src, Hs, Ht,
+                                 af_t2s, af_s2t, slope, n, 0, n, c, out, row_max, row_sum, nullptr, gout, gHs, gHt, g_af_t2s,
+                                 g_af_s2t, workspace, workspace_bytes, stream);
 }
 
 int bgnn_gatv2_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
@@ -372,17 +402,42 @@ int bgnn_adapted_transform_bwd_f32(const float* gHs, const float* gHt, const flo
 
 int bgnn_gatv2_heads_supported(int heads, int c) { return gatv2_heads_supported(heads, c) ? 1 : 0; }
 
+int bgnn_gatv2_heads_fwd_part_f32(const int32_t* rowptr, const int32_t* col, const uint8_t* dst_is_src, const float* Hs,
+                                  const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n_rows,
+                                  int64_t row_off, int heads, int c, float* out, float* row_max, float* row_sum, void* stream) {
+  if (n_rows < 0 || row_off < 0 || c <= 0 || heads <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n_rows > 0 && (!rowptr || !col || !dst_is_src || !Hs || !Ht || !af_t2s || !af_s2t || !out)) return BGNN_ERR_INVALID_ARG;
+  return launch_gatv2_heads_fwd(rowptr, col, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n_rows, row_off, heads, c, out, row_max,
+                                row_sum, (cudaStream_t)stream);
+}
+
 int bgnn_gatv2_heads_fwd_f32(const int32_t* rowptr, const int32_t* col, const uint8_t* dst_is_src, const float* Hs,
                              const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n, int heads,
                              int c, float* out, float* row_max, float* row_sum, void* stream) {
-  if (n < 0 || c <= 0 || heads <= 0) return BGNN_ERR_INVALID_ARG;
-  if (n > 0 && (!rowptr || !col || !dst_is_src || !Hs || !Ht || !af_t2s || !af_s2t || !out)) return BGNN_ERR_INVALID_ARG;
-  return launch_gatv2_heads_fwd(rowptr, col, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, heads, c, out, row_max, row_sum,
-                                (cudaStream_t)stream);
+  return bgnn_gatv2_heads_fwd_part_f32(rowptr, col, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, 0, heads, c, out, row_max,
+                                       row_sum, stream);
 }
 
 size_t bgnn_gatv2_heads_bwd_workspace_bytes(int64_t n, int64_t e, int heads, int c) {
   return (n < 0 || e < 0 || c <= 0 || heads <= 0) ? 0 : gatv2_heads_bwd_workspace_bytes(n, e, heads, c);
+}
+
+int bgnn_gatv2_heads_bwd_part_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
+                                  const int32_t* csr_to_csc, int64_t e, const uint8_t* dst_is_src, const float* Hs,
+                                  const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n_rows,
+                                  int64_t row_off, int64_t n_src, int heads, int c, const float* out, const float* row_max,
+                                  const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
+                                  float* g_af_s2t, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_rows < 0 || n_src < 0 || row_off < 0 || row_off + n_rows > n_src || e < 0 || c <= 0 || heads <= 0) return BGNN_ERR_INVALID_ARG;
+  if (n_src > 0 && (!t_rowptr || !dst_is_src || !Hs || !Ht || !af_t2s || !af_s2t || !g_af_t2s || !g_af_s2t || (!gHs && !gHt)))
+    return BGNN_ERR_INVALID_ARG;
+  if (n_rows > 0 && (!rowptr || !out || !row_max || !row_sum || !gout)) return BGNN_ERR_INVALID_ARG;
+  if (e > 0 && (!col || !t_col || !csr_to_csc)) return BGNN_ERR_INVALID_ARG;
+  if (!gatv2_heads_supported(heads, c)) return BGNN_ERR_UNSUPPORTED;
+  if (n_src > 0 && (!workspace || workspace_bytes < gatv2_heads_bwd_workspace_bytes(n_src, e, heads, c))) return BGNN_ERR_WORKSPACE;
+  return launch_gatv2_heads_bwd(rowptr, col, t_rowptr, t_col, csr_to_csc, e, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n_rows,
+                                row_off, n_src, heads, c, out, row_max, row_sum, gout, gHs, gHt, g_af_t2s, g_af_s2t, workspace,
+                                workspace_bytes, (cudaStream_t)stream);
 }
 
 int bgnn_gatv2_heads_bwd_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
@@ -391,15 +446,10 @@ int bgnn_gatv2_heads_bwd_f32(const int32_t* rowptr, const int32_t* col, const in
                              int c, const float* out, const float* row_max, const float* row_sum, const float* gout,
                              float* gHs, float* gHt, float* g_af_t2s, float* g_af_s2t, void* workspace,
                              size_t workspace_bytes, void* stream) {
-  if (n < 0 || e < 0 || c <= 0 || heads <= 0) return BGNN_ERR_INVALID_ARG;
-  if (n > 0 && (!rowptr || !col || !t_rowptr || !t_col || !csr_to_csc || !dst_is_src || !Hs || !Ht || !af_t2s ||
-                !af_s2t || !out || !row_max || !row_sum || !gout || !gHs || !gHt || !g_af_t2s || !g_af_s2t))
-    return BGNN_ERR_INVALID_ARG;
-  if (!gatv2_heads_supported(heads, c)) return BGNN_ERR_UNSUPPORTED;
-  if (n > 0 && (!workspace || workspace_bytes < gatv2_heads_bwd_workspace_bytes(n, e, heads, c))) return BGNN_ERR_WORKSPACE;
-  return launch_gatv2_heads_bwd(rowptr, col, t_rowptr, t_col, csr_to_csc, e, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n,
-                                heads, c, out, row_max, row_sum, gout, gHs, gHt, g_af_t2s, g_af_s2t, workspace,
-                                workspace_bytes, (cudaStream_t)stream);
+  if (n > 0 && (!gHs || !gHt)) return BGNN_ERR_INVALID_ARG;
+  return bgnn_gatv2_heads_bwd_part_f32(rowptr, col, t_rowptr, t_col, csr_to_csc, e, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope,
+                                       n, 0, n, heads, c, out, row_max, row_sum, gout, gHs, gHt, g_af_t2s, g_af_s2t, workspace,
+                                       workspace_bytes, stream);
 }
 
 int bgnn_adapted_skinny_supported(int c, int d) { return adapted_skinny_supported(c, d) ? 1 : 0; }
@@ -478,7 +528,7 @@ int bgnn_bn_relu_fwd_f32(const float* x, int64_t n, int c, const float* weight, 
                          float* running_mean, float* running_var, int relu, float* y, float* stats, void* workspace,
                          size_t workspace_bytes, void* stream) {
   if (n < 0 || c <= 0 || !stats || !workspace) return BGNN_ERR_INVALID_ARG;
-  if (n > 0 && (!x || !y)) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && !x) return BGNN_ERR_INVALID_ARG;     // y may be NULL: statistics only
   return launch_bn_relu_fwd(x, n, c, weight, bias, eps, momentum, running_mean, running_var, relu, y, stats, workspace,
                             workspace_bytes, (cudaStream_t)stream);
 }
@@ -487,6 +537,20 @@ int bgnn_bn_relu_apply_f32(const float* x, int64_t n, int c, const float* stats,
   if (n < 0 || c <= 0 || !stats) return BGNN_ERR_INVALID_ARG;
   if (n > 0 && (!x || !y)) return BGNN_ERR_INVALID_ARG;
   return launch_bn_relu_apply(x, n, c, stats, relu, y, (cudaStream_t)stream);
+}
+
+int bgnn_bn_relu_bwd_reduce_f32(const float* gy, const float* x, int64_t n, int c, const float* stats, int relu, float* gwb,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 0 || c <= 0 || !stats || !gwb || !workspace) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!gy || !x)) return BGNN_ERR_INVALID_ARG;
+  return launch_bn_relu_bwd_reduce(gy, x, n, c, stats, relu, gwb, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bgnn_bn_relu_bwd_apply_f32(const float* gy, const float* x, int64_t n, int c, const float* stats, int relu,
+                               const float* coef, float* gx, void* stream) {
+  if (n < 0 || c <= 0 || !stats || !coef) return BGNN_ERR_INVALID_ARG;
+  if (n > 0 && (!gy || !x || !gx)) return BGNN_ERR_INVALID_ARG;
+  return launch_bn_relu_bwd_apply(gy, x, n, c, stats, relu, coef, gx, (cudaStream_t)stream);
 }
 
 int bgnn_bn_relu_bwd_f32(const float* gy, const float* x, int64_t n, int c, const float* stats, int relu, float* gx,

@@ -210,8 +210,10 @@ int launch_bn_relu_fwd(const float* x, long long n, int c, const float* w, const
   BGNN_LAUNCH_CHECK();
   bn_fwd_finalize_kernel<<<c, BN_THREADS, 0, stream>>>(part, ctas, x, w, b, n, c, eps, momentum, stats, running_mean, running_var);
   BGNN_LAUNCH_CHECK();
-  bn_apply_kernel<0><<<ctas, BN_THREADS, 0, stream>>>(x, nullptr, stats, nullptr, relu, n, c, g.tpr, g.rows, y);
-  BGNN_LAUNCH_CHECK();
+  if (y) {                                            // y == NULL: statistics only (the multi-GPU path combines them first)
+    bn_apply_kernel<0><<<ctas, BN_THREADS, 0, stream>>>(x, nullptr, stats, nullptr, relu, n, c, g.tpr, g.rows, y);
+    BGNN_LAUNCH_CHECK();
+  }
   return BGNN_OK;
 }
 
@@ -244,6 +246,38 @@ int launch_bn_relu_bwd(const float* gy, const float* x, long long n, int c, cons
     bn_apply_kernel<1><<<ctas, BN_THREADS, 0, stream>>>(x, gy, stats, coef, relu, n, c, g.tpr, g.rows, gx);
     BGNN_LAUNCH_CHECK();
   }
+  return BGNN_OK;
+}
+
+// The two halves of the backward for the destination-partitioned (multi-GPU) path, where the column sums are
+// all-reduced in between: `reduce` gives this rank's sums (d weight | d bias) = (sum g xhat | sum g) under the GLOBAL
+// statistics; `apply` takes coef = (mean g | mean g xhat) over ALL ranks' rows.
+int launch_bn_relu_bwd_reduce(const float* gy, const float* x, long long n, int c, const float* stats, int relu, float* gwb,
+                              void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (!bn_relu_supported(c)) return BGNN_ERR_UNSUPPORTED;
+  if (ws_bytes < bn_relu_workspace_bytes(c)) return BGNN_ERR_WORKSPACE;
+  float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  float* coef = part + (size_t)BN_CTAS * 2 * c;
+  const BnGeom g = bn_geom(c);
+  const int ctas = n > 0 ? bn_ctas(n, g.rows) : 0;
+  if (n > 0) {
+    const size_t dyn = (size_t)g.rows * 2 * c * sizeof(float);
+    BGNN_CUDA_TRY(cudaFuncSetAttribute(bn_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    bn_reduce_kernel<1><<<ctas, BN_THREADS, dyn, stream>>>(x, gy, stats, relu, n, c, g.tpr, g.rows, part);
+    BGNN_LAUNCH_CHECK();
+  }
+  bn_bwd_finalize_kernel<<<c, BN_THREADS, 0, stream>>>(part, ctas, 1, c, gwb, coef);
+  BGNN_LAUNCH_CHECK();
+  return BGNN_OK;
+}
+
+int launch_bn_relu_bwd_apply(const float* gy, const float* x, long long n, int c, const float* stats, int relu,
+                             const float* coef, float* gx, cudaStream_t stream) {
+  if (!bn_relu_supported(c)) return BGNN_ERR_UNSUPPORTED;
+  if (n <= 0) return BGNN_OK;
+  const BnGeom g = bn_geom(c);
+  bn_apply_kernel<1><<<bn_ctas(n, g.rows), BN_THREADS, 0, stream>>>(x, gy, stats, coef, relu, n, c, g.tpr, g.rows, gx);
+  BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }
 

@@ -8,12 +8,24 @@
 //     out[dst] = sum alpha * H[src]
 // The two edge sets have disjoint destinations, so per destination row i one picks (H, a) by the
 // domain of i and does a single online-softmax pass over the row's incoming edges: one gather of
-// H[src] per edge, no [E,C] intermediates, no atomics.
+// H[src] per edge, no [E,C] intermediates, no atomics.  In training the forward also streams out the
+// per-edge score (4 B per edge, CSR order) so that the backward never recomputes a score.
 //
-// Backward (K3b) recomputes the scores from the saved per-row (max, sum):
-//   pass A (CSR by dst):  D_i = gout_i . out_i ;  dH[dst] part, d a_f partials (per-CTA, reduced after)
-//   pass B (CSC by src):  dH[src] part = sum alpha*gout_i + ds * a (.) lrelu'(H_j+H_i)
-// Both passes are atomic-free and deterministic.
+// Backward (K3b), two atomic-free, deterministic passes.  With t = H_j + H_i, p = [t > 0],
+// lrelu(t) = slope t + (1 - slope) p t and ds_ij = alpha_ij (gout_i . H_j - gout_i . out_i):
+//   pass A (CSR by dst, gathers H[src]):   ds, the leaky-relu branch bits p (packed from sign bits),
+//        T_i[f] = sum_j p ds, S_i = sum_j ds;   dH[i] += a (.) (slope S_i + (1-slope) T_i)     [destination side]
+//        d a += H_i (.) (slope S_i + (1-slope) T_i);   one 16-byte record (alpha, ds, p bits) per edge
+//   pass B (CSC by src, gathers gout[dst], streams the records):
+//        G_j = sum_i alpha gout_i,  T_j[f] = sum_i p ds,  S_j = sum_i ds   (per destination domain)
+//        dH[j] += G_j + a (.) (slope S_j + (1-slope) T_j);   d a += H_j (.) (slope S_j + (1-slope) T_j)
+// i.e. per edge and feature pass A costs one FMA (the dot product), one subtraction + one funnel shift (branch bit)
+// and one predicated add; everything that involves `a` or the leaky-relu values happens once per ROW.
+//
+// Destination-partitioned (multi-GPU) layout: a rank processes n_rows destination rows with LOCAL row ids
+// (rowptr, out, gout, row statistics) whose global node id is row + row_off; H, dst_is_src and the gradients
+// w.r.t. H are indexed by global id (col entries are global); the transposed CSR has n_src rows (all sources)
+// whose entries are local destination ids.  Single GPU: row_off = 0, n_src = n_rows.
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -36,13 +48,14 @@ __device__ __forceinline__ float gsum(float v, unsigned mask) {
 __device__ __forceinline__ float lrelu(float t, float slope) { return t > 0.f ? t : t * slope; }
 
 // ------------------------------------------------------------------------------------------ forward
-template <int VEC, int G, int CH>
+// SCORE_ONLY: only the per-edge scores are produced (for callers of the backward that did not keep them).
+template <int VEC, int G, int CH, bool SCORE_ONLY>
 __global__ void __launch_bounds__(256)
 gatv2_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ order,
                  const uint8_t* __restrict__ dst_is_src,
                  const float* __restrict__ Hs, const float* __restrict__ Ht, const float* __restrict__ af_t2s,
-                 const float* __restrict__ af_s2t, float slope, long long n, int c, float* __restrict__ out,
-                 float* __restrict__ row_max, float* __restrict__ row_sum) {
+                 const float* __restrict__ af_s2t, float slope, long long n, long long row_off, int c, float* __restrict__ out,
+                 float* __restrict__ row_max, float* __restrict__ row_sum, float* __restrict__ score) {
   const int lane = threadIdx.x & 31;
   const int lane_g = threadIdx.x % G;
   const unsigned mask = group_mask<G>(lane);
@@ -51,10 +64,11 @@ gatv2_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, co
   const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
   if (slot >= n) return;  // a group leaves together; shuffles below use the group's own mask
   const long long row = order ? (long long)__ldg(order + slot) : slot;
+  const long long grow = row + row_off;              // global node id of the destination
   const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
   if (beg == end) {
-    // no incoming edge (rows owned by another rank in the destination-partitioned multi-GPU layout):
-    // the aggregate is 0; skip every feature load
+    // no incoming edge: the aggregate is 0; skip every feature load
+    if (SCORE_ONLY) return;
     Chunk<VEC> z;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) z.v[i] = 0.f;
@@ -69,7 +83,7 @@ gatv2_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, co
     }
     return;
   }
-  const bool is_src = dst_is_src[row] != 0;
+  const bool is_src = dst_is_src[grow] != 0;
   const float* __restrict__ H = is_src ? Hs : Ht;
   const float* __restrict__ a = is_src ? af_t2s : af_s2t;
   Chunk<VEC> hi[CH], av[CH], acc[CH];
@@ -78,7 +92,7 @@ gatv2_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, co
   for (int ch = 0; ch < CH; ++ch) {
     int c0 = (ch * G + lane_g) * VEC;
     cok[ch] = c0 < c;
-    hi[ch] = ld_chunk<VEC>(H + row * c + c0, cok[ch]);
+    hi[ch] = ld_chunk<VEC>(H + grow * c + c0, cok[ch]);
     av[ch] = ld_chunk<VEC>(a + c0, cok[ch]);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[ch].v[i] = 0.f;
@@ -110,6 +124,18 @@ gatv2_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, co
       s[u] = gsum<G>(s[u], mask);
       if (j[u] < 0) s[u] = -INFINITY;
     }
+    if (score) {
+      // the scores of the batch go out as one contiguous run: lane u of the group stores edge e + u
+      if (G >= U) {
+        const float sv = lane_g == 0 ? s[0] : (lane_g == 1 ? s[1] : (lane_g == 2 ? s[2] : s[3]));
+        if (lane_g < U && e + lane_g < end) score[e + lane_g] = sv;
+      } else if (lane_g == 0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (e + u < end) score[e + u] = s[u];
+      }
+    }
+    if (SCORE_ONLY) continue;
     float mb = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
     float mn = fmaxf(m, mb);          // finite: the batch has at least one valid edge
     float sc = expf(m - mn);          // exp(-inf) = 0 on the first batch
@@ -129,6 +155,7 @@ gatv2_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, co
     }
     m = mn;
   }
+  if (SCORE_ONLY) return;
   const float inv = 1.0f / (l + 1e-16f);   // PyG softmax denominator
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) {
@@ -143,15 +170,21 @@ gatv2_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, co
 }
 
 int launch_gatv2_fwd(const int* rowptr, const int* col, const int* order, const uint8_t* dst_is_src, const float* Hs, const float* Ht,
-                     const float* af_t2s, const float* af_s2t, float slope, long long n, int c, float* out,
-                     float* row_max, float* row_sum, cudaStream_t stream) {
+                     const float* af_t2s, const float* af_s2t, float slope, long long n, long long row_off, int c, float* out,
+                     float* row_max, float* row_sum, float* score, int score_only, cudaStream_t stream) {
   if (n <= 0) return BGNN_OK;
   int vec, g, ch;
   if (!pick_row_config(c, vec, g, ch)) return BGNN_ERR_UNSUPPORTED;
   long long blocks = (n * g + 255) / 256;
-#define CALL(V, G_, C_)                                                                                        \
-  gatv2_fwd_kernel<V, G_, C_><<<(unsigned)blocks, 256, 0, stream>>>(rowptr, col, order, dst_is_src, Hs, Ht, af_t2s,   \
-                                                                      af_s2t, slope, n, c, out, row_max, row_sum)
+#define CALL(V, G_, C_)                                                                                                  \
+  do {                                                                                                                   \
+    if (score_only)                                                                                                      \
+      gatv2_fwd_kernel<V, G_, C_, true><<<(unsigned)blocks, 256, 0, stream>>>(rowptr, col, order, dst_is_src, Hs, Ht,   \
+          af_t2s, af_s2t, slope, n, row_off, c, out, row_max, row_sum, score);                                           \
+    else                                                                                                                 \
+      gatv2_fwd_kernel<V, G_, C_, false><<<(unsigned)blocks, 256, 0, stream>>>(rowptr, col, order, dst_is_src, Hs, Ht,  \
+          af_t2s, af_s2t, slope, n, row_off, c, out, row_max, row_sum, score);                                           \
+  } while (0)
   BGNN_ROW_DISPATCH(vec, g, ch, CALL);
 #undef CALL
   BGNN_LAUNCH_CHECK();
@@ -159,35 +192,36 @@ int launch_gatv2_fwd(const int* rowptr, const int* col, const int* order, const 
 }
 
 // ------------------------------------------------------------------------------------------ backward
-// Pass A: per destination row (CSR).  Recomputes the scores from the saved (max, sum), and writes
-//   * the destination-side gradient of row i into gHs (source-domain row) or gHt (target-domain row),
-//   * per-WARP partial sums of d a_f into ga_part[warp][2][c] (reduced by reduce_partials_kernel),
+// Pass A: per destination row (CSR), scores read back from the forward.  Writes
+//   * the destination-side gradient of row i into gHs (source-domain row) or gHt (target-domain row) at row + row_off,
+//   * per-WARP partial sums of the destination-side part of d a_f into ga_part[warp][2][c],
 //   * one record per edge, stored at the edge's slot in the TRANSPOSED CSR so that pass B streams them:
 //       ea   = alpha_ij with the destination's domain in the sign bit (negative: source-domain destination)
 //       eds  = d score_ij = alpha_ij (gout_i . H_j - gout_i . out_i)
-//       emask[CW] = bit c set iff H_j[c] + H_i[c] > 0 (the leaky-relu branch)
+//       emask[CW] = bit f set iff H_j[f] + H_i[f] > 0 (the leaky-relu branch)
 // so that pass B needs neither H[dst] nor the softmax statistics again.
 //
-// The pass is bound by instruction issue and latency, not by memory (profiles/r01e, r01h), so its row mapping
-// differs from the forward kernel's: a group of G lanes owns a row and every lane owns EPL = VEC*CH CONTIGUOUS
-// features (8, or 16 for c > 256).  Fewer lanes per row means fewer shuffle steps and less per-edge bookkeeping
-// per feature, and a lane's leaky-relu bits are exactly byte(s) lane_g*EPL/8.. of the edge's mask, which it
-// stores itself -- no cross-lane combination of mask words.  U edges are in flight per group; warps are
-// persistent over a static round-robin of row sets (no CTA barrier: a long row delays only its own warp, and
-// the d a_f summation order stays fixed).
+// Row mapping: a group of G lanes owns a row and every lane owns EPL = VEC*CH CONTIGUOUS features (8, or 16 for
+// c > 256).  Few lanes per row means few shuffle steps per edge, and a lane's branch bits are exactly byte(s)
+// lane_g*EPL/8.. of the edge's mask, which it stores itself.  The branch bit of a feature is the SIGN bit of
+// (-H_i) - H_j, which is set exactly when H_j + H_i > 0 (+0 when the sum is 0, like the reference's t > 0), so
+// the bits of a lane are packed by one funnel shift per feature.  U edges are in flight per group; warps are
+// persistent over a static round-robin of row sets (no CTA barrier: a long row delays only its own warp, and the
+// d a_f summation order stays fixed).
 template <int VEC, int G, int CH, int U, int MINB, int ES>
 __global__ void __launch_bounds__(128, MINB)
 gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ csr_to_csc,
                      const int* __restrict__ order, const uint8_t* __restrict__ dst_is_src, const float* __restrict__ Hs, const float* __restrict__ Ht,
-                     const float* __restrict__ af_t2s, const float* __restrict__ af_s2t, float slope, long long n, int c,
-                     int cw, const float* __restrict__ out, const float* __restrict__ row_max,
-                     const float* __restrict__ row_sum, const float* __restrict__ gout, float* __restrict__ gHs,
-                     float* __restrict__ gHt, unsigned* __restrict__ erec, unsigned* __restrict__ emask,
+                     const float* __restrict__ af_t2s, const float* __restrict__ af_s2t, float slope, long long n, long long slot_off,
+                     long long row_off, int c, int cw, const float* __restrict__ out, const float* __restrict__ row_max,
+                     const float* __restrict__ row_sum, const float* __restrict__ score, const float* __restrict__ gout,
+                     float* __restrict__ gHs, float* __restrict__ gHt, unsigned* __restrict__ erec, unsigned* __restrict__ emask,
                      float* __restrict__ ga_part) {
-  // ES > 1 (narrow rows, G == 1): ES lanes share a row and split its EDGES (lane s takes edges s, s + ES, ...):
-  // consecutive lanes read consecutive col entries, and a hub row is no longer one lane's serial loop.
-  static_assert(ES == 1 || G == 1, "edge splitting is for rows a single lane can hold");
+  // ES > 1: ES groups of G lanes share a row and split its EDGES (group s takes edges s, s + ES, ...).  Used for
+  // narrow rows (G == 1: consecutive lanes read consecutive col entries) and for the HUB rows of wide ones (the
+  // longest rows of the degree order get a whole warp each, so that a 2000-edge row is not one group's serial loop).
   constexpr int RL = G * ES;                       // lanes per row
+  static_assert(RL <= 32, "a row is owned by at most one warp");
   constexpr int RPW = 32 / RL;                     // rows per warp
   constexpr int EPL = VEC * CH;                    // contiguous features per lane
   static_assert(G == 1 || EPL == 8 || EPL == 16, "multi-lane rows own whole mask bytes");
@@ -199,9 +233,10 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int col0 = lane_g * EPL;
+  const float oms = 1.f - slope;
   bool cok[CH];
   // running d a_f sums of this lane, per destination domain: thread-private columns of shared memory
-  // (kept out of the register file, which bounds this kernel's occupancy)
+  // (kept out of the register file; touched once per ROW)
   __shared__ float s_ga[2 * EPL][128];
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) cok[ch] = col0 + ch * VEC < c;
@@ -216,48 +251,51 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
   for (long long set = wid; set < nsets; set += nwarps) {
     const long long slot = set * RPW + lane / RL;
     if (slot >= n) continue;                       // whole row groups leave together
-    const long long row = order ? (long long)__ldg(order + slot) : slot;
+    const long long row = order ? (long long)__ldg(order + slot_off + slot) : slot_off + slot;
+    const long long grow = row + row_off;
     const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-    const bool is_src = dst_is_src[row] != 0;
-    Chunk<VEC> gi[CH];
+    const bool is_src = dst_is_src[grow] != 0;
+    float* __restrict__ gdst = is_src ? gHs : gHt;
+    Chunk<VEC> gi[CH];                             // sum over the row's edges of [t > 0] ds, per feature
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) gi[ch].v[i] = 0.f;
     if (beg < end) {                               // no incoming edge: the destination-side gradient is 0
       const float* __restrict__ H = is_src ? Hs : Ht;
-      const float* __restrict__ a = is_src ? af_t2s : af_s2t;
-      Chunk<VEC> hi[CH], av[CH], go[CH], ga[CH];
+      Chunk<VEC> nhi[CH], go[CH];
       float dpart = 0.f;
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
-        hi[ch] = ld_chunk<VEC>(H + row * c + col0 + ch * VEC, cok[ch]);
-        av[ch] = ld_chunk<VEC>(a + col0 + ch * VEC, cok[ch]);
+        nhi[ch] = ld_chunk<VEC>(H + grow * c + col0 + ch * VEC, cok[ch]);
         go[ch] = ld_chunk<VEC>(gout + row * c + col0 + ch * VEC, cok[ch]);
         const Chunk<VEC> oi = ld_chunk<VEC>(out + row * c + col0 + ch * VEC, cok[ch]);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           dpart = fmaf(go[ch].v[i], oi.v[i], dpart);
-          ga[ch].v[i] = 0.f;
+          nhi[ch].v[i] = 0.f - nhi[ch].v[i];      // never -0: (-H_i) - H_j is then +0 whenever the sum is 0
         }
       }
       const float Di = gsum<G>(dpart, gmask);
       const float m = row_max[row];
       const float inv = 1.0f / (row_sum[row] + 1e-16f);
       float dsum = 0.f;                            // sum of d score over the row's edges
-      int nj[U], np[U];                            // (source, transposed slot) of the NEXT batch: its gathers start at once
+      int nj[U], np[U];                            // (source, transposed slot, score) of the NEXT batch: its gathers start at once
+      float nsc[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int ee = beg + u * ES + sub;
         const bool ok = ee < end;
         nj[u] = ok ? __ldg(col + ee) : -1;
         np[u] = ok ? __ldg(csr_to_csc + ee) : 0;
+        nsc[u] = ok ? __ldg(score + ee) : -INFINITY;
       }
       for (int e = beg; e < end; e += U * ES) {
         int j[U], pos[U];
+        float sc[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { j[u] = nj[u]; pos[u] = np[u]; }
-        Chunk<VEC> hj[U][CH];                      // H[src]; overwritten by lrelu(H[src] + H[dst]) below
+        for (int u = 0; u < U; ++u) { j[u] = nj[u]; pos[u] = np[u]; sc[u] = nsc[u]; }
+        Chunk<VEC> hj[U][CH];                      // H[src]; overwritten by (-H[dst]) - H[src] below
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -269,49 +307,37 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
           const bool ok = ee < end;
           nj[u] = ok ? __ldg(col + ee) : -1;
           np[u] = ok ? __ldg(csr_to_csc + ee) : 0;
+          nsc[u] = ok ? __ldg(score + ee) : -INFINITY;
         }
-        float sp[U], dp[U];
+        float dp[U];
         unsigned bits[U];                          // leaky-relu branch bits of this lane's features (bit = feature)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          float s = 0.f, d = 0.f;
+          float d = 0.f;
           unsigned b = 0u;
 #pragma unroll
-          for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-              const float x = hj[u][ch].v[i];
-              const float t = x + hi[ch].v[i];
-              const bool p = t > 0.f;
-              const float l = p ? t : t * slope;
-              s = fmaf(av[ch].v[i], l, s);
-              d = fmaf(go[ch].v[i], x, d);
-              b |= p ? (1u << (ch * VEC + i)) : 0u;
-              hj[u][ch].v[i] = l;
-            }
-          sp[u] = s;
+          for (int k = EPL - 1; k >= 0; --k) {     // descending: the funnel shift leaves feature k in bit k
+            const int ch = k / VEC, i = k % VEC;
+            const float x = hj[u][ch].v[i];
+            d = fmaf(go[ch].v[i], x, d);
+            const float tn = nhi[ch].v[i] - x;     // sign bit set  <=>  H_j + H_i > 0
+            b = __funnelshift_l(__float_as_uint(tn), b, 1);
+            hj[u][ch].v[i] = tn;
+          }
           dp[u] = d;
           bits[u] = b;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          sp[u] = gsum<G>(sp[u], gmask);
-          dp[u] = gsum<G>(dp[u], gmask);
-        }
+        for (int u = 0; u < U; ++u) dp[u] = gsum<G>(dp[u], gmask);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const float alpha = (j[u] >= 0) ? expf(sp[u] - m) * inv : 0.f;
+          const float alpha = (j[u] >= 0) ? expf(sc[u] - m) * inv : 0.f;
           const float ds = alpha * (dp[u] - Di);
           dsum += ds;
-          // d H[dst] = a (.) sum_j ds_j lrelu'(t_j) = a (.) (slope * sum_j ds_j + (1 - slope) * sum_{t_j > 0} ds_j):
-          // only the second sum is per feature
 #pragma unroll
           for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-              gi[ch].v[i] += ((bits[u] >> (ch * VEC + i)) & 1u) ? ds : 0.f;
-              ga[ch].v[i] = fmaf(ds, hj[u][ch].v[i], ga[ch].v[i]);
-            }
+            for (int i = 0; i < VEC; ++i) gi[ch].v[i] += (hj[u][ch].v[i] < 0.f) ? ds : 0.f;
           if (j[u] >= 0) {
             const float ea = is_src ? -alpha : alpha;      // -0.0f keeps the sign for alpha == 0
             if (G == 1 && cw <= 2) {
@@ -337,24 +363,27 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
 #pragma unroll
           for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-              gi[ch].v[i] += __shfl_xor_sync(rmask, gi[ch].v[i], o);
-              ga[ch].v[i] += __shfl_xor_sync(rmask, ga[ch].v[i], o);
-            }
+            for (int i = 0; i < VEC; ++i) gi[ch].v[i] += __shfl_xor_sync(rmask, gi[ch].v[i], o);
         }
       }
-      const float oms = 1.f - slope, sds = slope * dsum;
+      // sum_j ds_j lrelu'(t_j) = slope sum_j ds_j + (1 - slope) sum_{t_j > 0} ds_j, per feature: times a -> d H[dst],
+      // times H[dst] -> destination-side part of d a
+      const float sds = slope * dsum;
+      const float* __restrict__ a = is_src ? af_t2s : af_s2t;
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
+      for (int ch = 0; ch < CH; ++ch) {
+        const Chunk<VEC> av = ld_chunk<VEC>(a + col0 + ch * VEC, cok[ch]);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-          gi[ch].v[i] = av[ch].v[i] * fmaf(oms, gi[ch].v[i], sds);
-          if (sub == 0) s_ga[(is_src ? 0 : EPL) + ch * VEC + i][threadIdx.x] += ga[ch].v[i];
+          const float w = fmaf(oms, gi[ch].v[i], sds);
+          gi[ch].v[i] = av.v[i] * w;
+          if (sub == 0) s_ga[(is_src ? 0 : EPL) + ch * VEC + i][threadIdx.x] -= nhi[ch].v[i] * w;   // nhi = -H[dst]
         }
+      }
     }
-    if (sub == 0) {
+    if (sub == 0 && gdst) {
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch) st_chunk<VEC>((is_src ? gHs : gHt) + row * c + col0 + ch * VEC, gi[ch], cok[ch]);
+      for (int ch = 0; ch < CH; ++ch) st_chunk<VEC>(gdst + grow * c + col0 + ch * VEC, gi[ch], cok[ch]);
     }
   }
   __syncwarp();
@@ -396,9 +425,10 @@ static bool pick_dst_config(int c, int& vec, int& g, int& ch) {
 }
 constexpr int kBwdDstThreads = 128;
 constexpr int kBwdDstMaxCtasPerSm = 16;
+constexpr int kBwdSrcThreads = 256;
 static long long bwd_dst_max_warps() { return (long long)kNumSMs * kBwdDstMaxCtasPerSm * (kBwdDstThreads / 32); }
 
-// Column-wise reduction of the per-CTA partials: one CTA per column, strided partial sums then a
+// Column-wise reduction of the per-warp partials: one CTA per column, strided partial sums then a
 // fixed-shape tree -> deterministic.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ part, long long nparts, int width, float* __restrict__ o0,
@@ -416,24 +446,30 @@ reduce_partials_kernel(const float* __restrict__ part, long long nparts, int wid
   if (threadIdx.x == 0) { if (t < c) o0[t] = red[0]; else o1[t - c] = red[0]; }
 }
 
-// Pass B: per source row j over its outgoing edges (transposed CSR).  Streams the edge records of
-// pass A, gathers only gout[dst], and adds the source-side gradient
-//   dH[j] += alpha_ij gout_i + ds_ij a (.) lrelu'(H_j + H_i)
-// into gHs (edges into source-domain destinations) / gHt (target-domain destinations).
-template <int VEC, int G, int CH>
-__global__ void __launch_bounds__(256, (VEC * CH <= 4) ? 4 : 1)
+// Pass B: per source row j over its outgoing edges (transposed CSR); one row per group of G lanes, CTAs scheduled
+// by the hardware in degree order (hub rows first, no tail).  Streams the edge records of pass A and gathers only
+// gout[dst].  Per destination domain it accumulates
+//   G = sum alpha gout_i,  T[f] = sum_{branch bit f} ds,  S = sum ds
+// and finishes the row with   dH[j] = own + G + a (.) (slope S + (1-slope) T),   d a += H_j (.) (slope S + (1-slope) T)
+// (own = the destination-side part pass A left in the array of the row's own domain, for rows this rank owns).
+// The d a contributions of the CTA's rows are summed in a fixed order (warp butterfly, then over the warps in shared
+// memory) into ONE partial per CTA: deterministic.
+template <int VEC, int G, int CH, int MINB>
+__global__ void __launch_bounds__(kBwdSrcThreads, MINB)
 gatv2_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restrict__ t_col, const int* __restrict__ t_order,
-                     const uint8_t* __restrict__ dst_is_src, const float* __restrict__ af_t2s,
-                     const float* __restrict__ af_s2t, float slope, long long n, int c, int cw,
+                     const uint8_t* __restrict__ dst_is_src, const float* __restrict__ Hs, const float* __restrict__ Ht,
+                     const float* __restrict__ af_t2s, const float* __restrict__ af_s2t, float slope, long long n_src,
+                     long long own_lo, long long own_n, int c, int cw,
                      const unsigned* __restrict__ erec, const unsigned* __restrict__ emask,
-                     const float* __restrict__ gout, float* __restrict__ gHs, float* __restrict__ gHt) {
+                     const float* __restrict__ gout, float* __restrict__ gHs, float* __restrict__ gHt,
+                     float* __restrict__ ga_part) {
+  extern __shared__ float s_da[];                    // [warps][2c]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lane_g = threadIdx.x % G;
   const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  if (slot >= n) return;
-  const long long row = t_order ? (long long)__ldg(t_order + slot) : slot;
-  // per feature: the attention vector of either destination domain and its slope-scaled copy, so that the
-  // leaky-relu branch of an edge is one select (a or slope * a) per domain
-  Chunk<VEC> as_[CH], asl[CH], at_[CH], atl[CH], gs[CH], gt[CH];
+  const bool live = slot < n_src;                    // whole groups are live or not
+  const float oms = 1.f - slope;
+  Chunk<VEC> das[CH], dat[CH];
   bool cok[CH];
   int wsel[CH], bsel[CH];
 #pragma unroll
@@ -442,98 +478,155 @@ gatv2_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restrict__ t
     cok[ch] = c0 < c;
     wsel[ch] = min(c0 >> 5, cw - 1);
     bsel[ch] = c0 & 31;
-    as_[ch] = ld_chunk<VEC>(af_t2s + c0, cok[ch]);
-    at_[ch] = ld_chunk<VEC>(af_s2t + c0, cok[ch]);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      asl[ch].v[i] = as_[ch].v[i] * slope;
-      atl[ch].v[i] = at_[ch].v[i] * slope;
-      gs[ch].v[i] = 0.f;
-      gt[ch].v[i] = 0.f;
-    }
+    for (int i = 0; i < VEC; ++i) { das[ch].v[i] = 0.f; dat[ch].v[i] = 0.f; }
   }
-  const int beg = __ldg(t_rowptr + row), end = __ldg(t_rowptr + row + 1);
-  constexpr int U = 4;
-  int nxt[U];                                        // destination ids of the NEXT batch: their gathers start at once
+  if (live) {
+    const long long row = t_order ? (long long)__ldg(t_order + slot) : slot;
+    const int beg = __ldg(t_rowptr + row), end = __ldg(t_rowptr + row + 1);
+    const bool owned = row >= own_lo && row < own_lo + own_n;
+    const bool me_src = dst_is_src[row] != 0;
+    Chunk<VEC> gs[CH], gt[CH], ts[CH], tt[CH];
 #pragma unroll
-  for (int u = 0; u < U; ++u) nxt[u] = (beg + u < end) ? __ldg(t_col + beg + u) : -1;
-  for (int e = beg; e < end; e += U) {
-    int i_dst[U];
-    Chunk<VEC> go[U][CH];
+    for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
-    for (int u = 0; u < U; ++u) i_dst[u] = nxt[u];
+      for (int i = 0; i < VEC; ++i) { gs[ch].v[i] = 0.f; gt[ch].v[i] = 0.f; ts[ch].v[i] = 0.f; tt[ch].v[i] = 0.f; }
+    float ss = 0.f, st = 0.f;
+    constexpr int U = 4;
+    int nxt[U];                                      // destination ids of the NEXT batch: their gathers start at once
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int u = 0; u < U; ++u) nxt[u] = (beg + u < end) ? __ldg(t_col + beg + u) : -1;
+    for (int e = beg; e < end; e += U) {
+      int i_dst[U];
+      Chunk<VEC> go[U][CH];
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
-        go[u][ch] = ld_chunk<VEC>(gout + (long long)(i_dst[u] < 0 ? 0 : i_dst[u]) * c + (ch * G + lane_g) * VEC,
-                                  cok[ch] && i_dst[u] >= 0);
+      for (int u = 0; u < U; ++u) i_dst[u] = nxt[u];
 #pragma unroll
-    for (int u = 0; u < U; ++u) nxt[u] = (e + U + u < end) ? __ldg(t_col + e + U + u) : -1;
-    float dss[U], dst_[U], als[U], alt[U];           // (d score, alpha) routed to the destination's domain
-    unsigned mk[U][CH];
+      for (int u = 0; u < U; ++u)
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const bool ok = e + u < end;
-      float al, ds;
-      if (cw <= 2) {
-        const uint4 r4 = ok ? __ldg(reinterpret_cast<const uint4*>(erec) + e + u) : make_uint4(0u, 0u, 0u, 0u);
-        al = __uint_as_float(r4.x);
-        ds = __uint_as_float(r4.y);
+        for (int ch = 0; ch < CH; ++ch)
+          go[u][ch] = ld_chunk<VEC>(gout + (long long)(i_dst[u] < 0 ? 0 : i_dst[u]) * c + (ch * G + lane_g) * VEC,
+                                    cok[ch] && i_dst[u] >= 0);
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch) mk[u][ch] = wsel[ch] ? r4.w : r4.z;
-      } else {
-        const float2 r2 = ok ? __ldg(reinterpret_cast<const float2*>(erec) + e + u) : make_float2(0.f, 0.f);
-        al = r2.x;
-        ds = r2.y;
+      for (int u = 0; u < U; ++u) nxt[u] = (e + U + u < end) ? __ldg(t_col + e + U + u) : -1;
+      float dss[U], dst_[U], als[U], alt[U];           // (d score, alpha) routed to the destination's domain
+      unsigned mk[U][CH];
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch) mk[u][ch] = ok ? __ldg(emask + (long long)(e + u) * cw + wsel[ch]) : 0u;
+      for (int u = 0; u < U; ++u) {
+        const bool ok = e + u < end;
+        float al, ds;
+        if (cw <= 2) {
+          const uint4 r4 = ok ? __ldg(reinterpret_cast<const uint4*>(erec) + e + u) : make_uint4(0u, 0u, 0u, 0u);
+          al = __uint_as_float(r4.x);
+          ds = __uint_as_float(r4.y);
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch) mk[u][ch] = wsel[ch] ? r4.w : r4.z;
+        } else {
+          const float2 r2 = ok ? __ldg(reinterpret_cast<const float2*>(erec) + e + u) : make_float2(0.f, 0.f);
+          al = r2.x;
+          ds = r2.y;
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch) mk[u][ch] = ok ? __ldg(emask + (long long)(e + u) * cw + wsel[ch]) : 0u;
+        }
+        const bool dsrc = signbit(al);
+        const float alpha = fabsf(al);
+        dss[u] = dsrc ? ds : 0.f;
+        dst_[u] = dsrc ? 0.f : ds;
+        als[u] = dsrc ? alpha : 0.f;
+        alt[u] = dsrc ? 0.f : alpha;
+        ss += dss[u];
+        st += dst_[u];
       }
-      const bool dsrc = signbit(al);
-      const float alpha = fabsf(al);
-      dss[u] = dsrc ? ds : 0.f;
-      dst_[u] = dsrc ? 0.f : ds;
-      als[u] = dsrc ? alpha : 0.f;
-      alt[u] = dsrc ? 0.f : alpha;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            const bool pos = (mk[u][ch] >> (bsel[ch] + i)) & 1u;
+            const float g0 = go[u][ch].v[i];
+            gs[ch].v[i] = fmaf(als[u], g0, gs[ch].v[i]);
+            gt[ch].v[i] = fmaf(alt[u], g0, gt[ch].v[i]);
+            ts[ch].v[i] += pos ? dss[u] : 0.f;
+            tt[ch].v[i] += pos ? dst_[u] : 0.f;
+          }
     }
+    const float sls = slope * ss, slt = slope * st;
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
+    for (int ch = 0; ch < CH; ++ch) {
+      const int c0 = (ch * G + lane_g) * VEC;
+      if (!cok[ch]) continue;
+      if (beg < end) {
+        const Chunk<VEC> hs = ld_chunk<VEC>(Hs + row * c + c0, true), ht = ld_chunk<VEC>(Ht + row * c + c0, true);
+        const Chunk<VEC> as_ = ld_chunk<VEC>(af_t2s + c0, true), at_ = ld_chunk<VEC>(af_s2t + c0, true);   // L1-resident
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-          const bool pos = (mk[u][ch] >> (bsel[ch] + i)) & 1u;
-          const float g0 = go[u][ch].v[i];
-          gs[ch].v[i] = fmaf(dss[u], pos ? as_[ch].v[i] : asl[ch].v[i], fmaf(als[u], g0, gs[ch].v[i]));
-          gt[ch].v[i] = fmaf(dst_[u], pos ? at_[ch].v[i] : atl[ch].v[i], fmaf(alt[u], g0, gt[ch].v[i]));
+          const float us = fmaf(oms, ts[ch].v[i], sls), ut = fmaf(oms, tt[ch].v[i], slt);
+          gs[ch].v[i] = fmaf(as_.v[i], us, gs[ch].v[i]);
+          gt[ch].v[i] = fmaf(at_.v[i], ut, gt[ch].v[i]);
+          das[ch].v[i] = hs.v[i] * us;
+          dat[ch].v[i] = ht.v[i] * ut;
         }
-  }
-  const bool me_src = dst_is_src[row] != 0;
+      }
+      if (owned) {
+        // destination-side part of this row from pass A lives in the array of the row's own domain
+        const float* ownp = me_src ? gHs : gHt;
+        if (ownp) {
+          const Chunk<VEC> own = ld_chunk<VEC>(ownp + row * c + c0, true);
 #pragma unroll
-  for (int ch = 0; ch < CH; ++ch) {
-    int c0 = (ch * G + lane_g) * VEC;
-    if (!cok[ch]) continue;
-    // destination-side part of this row from pass A lives in the array of the row's own domain
-    Chunk<VEC> own = ld_chunk<VEC>((me_src ? gHs : gHt) + row * c + c0, true);
+          for (int i = 0; i < VEC; ++i) {
+            gs[ch].v[i] += me_src ? own.v[i] : 0.f;
+            gt[ch].v[i] += me_src ? 0.f : own.v[i];
+          }
+        }
+      }
+      if (gHs) st_chunk<VEC>(gHs + row * c + c0, gs[ch], true);
+      if (gHt) st_chunk<VEC>(gHt + row * c + c0, gt[ch], true);
+    }
+  }
+  // source-side part of d a_f: the warp's groups (fixed butterfly), then the CTA's warps in order -> one partial per CTA
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      gs[ch].v[i] += me_src ? own.v[i] : 0.f;
-      gt[ch].v[i] += me_src ? 0.f : own.v[i];
+      float vs = das[ch].v[i], vt = dat[ch].v[i];
+#pragma unroll
+      for (int o = G; o < 32; o <<= 1) {
+        vs += __shfl_xor_sync(0xffffffffu, vs, o);
+        vt += __shfl_xor_sync(0xffffffffu, vt, o);
+      }
+      const int cc = (ch * G + lane_g) * VEC + i;
+      if (lane < G && cc < c) {
+        s_da[warp * 2 * c + cc] = vs;
+        s_da[warp * 2 * c + c + cc] = vt;
+      }
     }
-    st_chunk<VEC>(gHs + row * c + c0, gs[ch], true);
-    st_chunk<VEC>(gHt + row * c + c0, gt[ch], true);
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * c; j += kBwdSrcThreads) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kBwdSrcThreads / 32; ++w) acc += s_da[w * 2 * c + j];
+    ga_part[(long long)blockIdx.x * 2 * c + j] = acc;
   }
 }
 
-static long long bwd_blocks(long long n, int g) { return (n * g + 255) / 256; }
+static long long bwd_src_blocks(long long n_src, int c) {
+  int vec, g, ch;
+  if (!pick_row_config(c, vec, g, ch)) return 0;
+  const long long b = (n_src * g + kBwdSrcThreads - 1) / kBwdSrcThreads;
+  return b < 1 ? 1 : b;
+}
 
 size_t gatv2_bwd_workspace_bytes(long long n, long long e, int c) {
   int vec, g, ch;
   if (!pick_row_config(c, vec, g, ch) || !pick_dst_config(c, vec, g, ch)) return 0;
   const int cw = (c + 31) / 32;
-  // records: 16 B per edge when the mask fits two words, else (alpha, dscore) pairs + a mask array
+  // records: 16 B per edge when the mask fits two words, else (alpha, dscore) pairs + a mask array;
+  // + e floats of scores for callers that did not keep the forward's; d a_f partials: one per warp of the two pass-A
+  // launches (hub rows, the rest) and one per CTA of pass B
   const size_t rec = cw <= 2 ? (size_t)e * 16 : (size_t)e * 8 + align_up((size_t)e * cw * sizeof(unsigned), 256);
-  return align_up((size_t)bwd_dst_max_warps() * 2 * c * sizeof(float), 256) + align_up(rec, 256) + 1024;
+  return align_up((size_t)(2 * bwd_dst_max_warps() + bwd_src_blocks(n, c)) * 2 * c * sizeof(float), 256) + align_up(rec, 256) +
+         align_up((size_t)e * sizeof(float), 256) + 1024;
 }
 
 struct BwdDstArgs {
@@ -541,9 +634,9 @@ struct BwdDstArgs {
   const uint8_t* dst_is_src;
   const float *Hs, *Ht, *af_t2s, *af_s2t;
   float slope;
-  long long n;
+  long long n, slot_off, row_off;
   int c, cw;
-  const float *out, *row_max, *row_sum, *gout;
+  const float *out, *row_max, *row_sum, *score, *gout;
   float *gHs, *gHt;
   unsigned *erec, *emask;
   float* part;
@@ -564,8 +657,8 @@ static int launch_bwd_dst_cfg(const BwdDstArgs& a, int& nwarps_out, cudaStream_t
   if (ctas > (long long)kNumSMs * occ) ctas = (long long)kNumSMs * occ;
   nwarps_out = (int)(ctas * WPC);
   kern<<<(unsigned)ctas, kBwdDstThreads, 0, stream>>>(a.rowptr, a.col, a.csr_to_csc, a.order, a.dst_is_src, a.Hs, a.Ht, a.af_t2s,
-                                                      a.af_s2t, a.slope, a.n, a.c, a.cw, a.out, a.row_max, a.row_sum,
-                                                      a.gout, a.gHs, a.gHt, a.erec, a.emask, a.part);
+                                                      a.af_s2t, a.slope, a.n, a.slot_off, a.row_off, a.c, a.cw, a.out, a.row_max, a.row_sum,
+                                                      a.score, a.gout, a.gHs, a.gHt, a.erec, a.emask, a.part);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }
@@ -574,18 +667,33 @@ template <int VEC, int G, int CH>
 static int launch_bwd_dst(const BwdDstArgs& a, int& nwarps_out, cudaStream_t stream) {
   if constexpr (VEC == 4 && G == 8 && CH == 2) {    // tuning experiments on the c = 64 mapping
     static const int variant = getenv("BGNN_GAT_VARIANT") ? atoi(getenv("BGNN_GAT_VARIANT")) : 0;
-    if (variant == 1) return launch_bwd_dst_cfg<VEC, G, CH, 4, 4>(a, nwarps_out, stream);
-    if (variant == 2) return launch_bwd_dst_cfg<VEC, G, CH, 2, 4>(a, nwarps_out, stream);
-    if (variant == 3) return launch_bwd_dst_cfg<VEC, G, CH, 2, 6>(a, nwarps_out, stream);
+    if (variant == 1) return launch_bwd_dst_cfg<VEC, G, CH, 2, 5>(a, nwarps_out, stream);
+    if (variant == 2) return launch_bwd_dst_cfg<VEC, G, CH, 2, 8>(a, nwarps_out, stream);
+    if (variant == 3) return launch_bwd_dst_cfg<VEC, G, CH, 4, 5>(a, nwarps_out, stream);
+    if (variant == 4) return launch_bwd_dst_cfg<VEC, G, CH, 3, 5>(a, nwarps_out, stream);
+    if (variant == 5) return launch_bwd_dst_cfg<VEC, G, CH, 4, 4>(a, nwarps_out, stream);
   }
   constexpr int EPL = VEC * CH;
   if constexpr (G == 1) {                           // narrow rows: 8 lanes split the edges of a row
     constexpr int MINB1 = (EPL <= 2) ? 8 : (EPL <= 4 ? 6 : 5);
     return launch_bwd_dst_cfg<VEC, G, CH, 2, MINB1, 8>(a, nwarps_out, stream);
   } else {
-    constexpr int U = (EPL >= 8) ? 2 : 4;
-    constexpr int MINB = (EPL > 8) ? 3 : 5;
+    constexpr int U = 2;
+    constexpr int MINB = (EPL > 8) ? 3 : 6;
     return launch_bwd_dst_cfg<VEC, G, CH, U, MINB>(a, nwarps_out, stream);
+  }
+}
+
+// The longest rows of the degree order, one WARP per row (ES = 32 / G groups split the row's edges).
+template <int VEC, int G, int CH>
+static int launch_bwd_dst_hubs(const BwdDstArgs& a, int& nwarps_out, cudaStream_t stream) {
+  if constexpr (G > 1 && G < 32) {
+    constexpr int EPL = VEC * CH;
+    // 4 edges in flight per group: the single longest row bounds this launch
+    return launch_bwd_dst_cfg<VEC, G, CH, (EPL > 8) ? 2 : 4, (EPL > 8) ? 3 : 4, 32 / G>(a, nwarps_out, stream);
+  } else {
+    nwarps_out = 0;
+    return BGNN_OK;
   }
 }
 
@@ -609,35 +717,112 @@ static int dispatch_bwd_dst(int g, int ch, const BwdDstArgs& a, int& nwarps_out,
   }
 }
 
+template <int VEC>
+static int dispatch_bwd_dst_hubs(int g, const BwdDstArgs& a, int& nwarps_out, cudaStream_t stream) {
+  constexpr int CHW = 8 / VEC;
+  switch (g) {
+    case 2: return launch_bwd_dst_hubs<VEC, 2, CHW>(a, nwarps_out, stream);
+    case 4: return launch_bwd_dst_hubs<VEC, 4, CHW>(a, nwarps_out, stream);
+    case 8: return launch_bwd_dst_hubs<VEC, 8, CHW>(a, nwarps_out, stream);
+    case 16: return launch_bwd_dst_hubs<VEC, 16, CHW>(a, nwarps_out, stream);
+    default: nwarps_out = 0; return BGNN_OK;
+  }
+}
+
+// rows at the head of the degree order that get a warp each in pass A (only with a row order; G in 2..16)
+constexpr long long kHubRows = 4096;
+
+template <int VEC, int G, int CH, int MINB>
+static int launch_bwd_src_min(const int* t_rowptr, const int* t_col, const int* t_order, const uint8_t* dst_is_src, const float* Hs,
+                              const float* Ht, const float* af_t2s, const float* af_s2t, float slope, long long n_src,
+                              long long own_lo, long long own_n, int c, int cw, const unsigned* erec, const unsigned* emask,
+                              const float* gout, float* gHs, float* gHt, float* part, int& nparts_out, cudaStream_t stream) {
+  auto kern = gatv2_bwd_src_kernel<VEC, G, CH, MINB>;
+  const long long ctas = (n_src * G + kBwdSrcThreads - 1) / kBwdSrcThreads;
+  const size_t dyn = (size_t)(kBwdSrcThreads / 32) * 2 * c * sizeof(float);
+  nparts_out = (int)ctas;
+  kern<<<(unsigned)ctas, kBwdSrcThreads, dyn, stream>>>(t_rowptr, t_col, t_order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n_src,
+                                                        own_lo, own_n, c, cw, erec, emask, gout, gHs, gHt, part);
+  BGNN_LAUNCH_CHECK();
+  return BGNN_OK;
+}
+
+template <int VEC, int G, int CH>
+static int launch_bwd_src_cfg(const int* t_rowptr, const int* t_col, const int* t_order, const uint8_t* dst_is_src, const float* Hs,
+                              const float* Ht, const float* af_t2s, const float* af_s2t, float slope, long long n_src,
+                              long long own_lo, long long own_n, int c, int cw, const unsigned* erec, const unsigned* emask,
+                              const float* gout, float* gHs, float* gHt, float* part, int& nwarps_out, cudaStream_t stream) {
+#define BGNN_SRC_GO(M)                                                                                                          \
+  launch_bwd_src_min<VEC, G, CH, M>(t_rowptr, t_col, t_order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n_src, own_lo, own_n, c, \
+                                    cw, erec, emask, gout, gHs, gHt, part, nwarps_out, stream)
+  if constexpr (VEC == 4 && G == 16 && CH == 1) {   // tuning experiments on the c = 64 mapping
+    static const int variant = getenv("BGNN_GAT_BVARIANT") ? atoi(getenv("BGNN_GAT_BVARIANT")) : 0;
+    if (variant == 1) return BGNN_SRC_GO(2);
+    if (variant == 2) return BGNN_SRC_GO(3);
+  }
+  if constexpr (VEC * CH <= 4) return BGNN_SRC_GO(4);
+  else return BGNN_SRC_GO(1);
+#undef BGNN_SRC_GO
+}
+
 int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csr_to_csc,
                      const int* order, const int* t_order, long long e, const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
-                     const float* af_s2t, float slope, long long n, int c, const float* out, const float* row_max,
-                     const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
-                     float* g_af_s2t, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  if (n <= 0) return BGNN_OK;
+                     const float* af_s2t, float slope, long long n, long long row_off, long long n_src, int c, const float* out,
+                     const float* row_max, const float* row_sum, const float* score, const float* gout, float* gHs, float* gHt,
+                     float* g_af_t2s, float* g_af_s2t, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (n_src <= 0) return BGNN_OK;
   int vec, g, ch, dvec, dg, dch;
   if (!pick_row_config(c, vec, g, ch) || !pick_dst_config(c, dvec, dg, dch)) return BGNN_ERR_UNSUPPORTED;
-  long long blocks = bwd_blocks(n, g);
   const int cw = (c + 31) / 32;
   Workspace w(ws, ws_bytes);
-  float* part = w.take<float>(bwd_dst_max_warps() * 2 * c);
+  float* part = w.take<float>((2 * bwd_dst_max_warps() + bwd_src_blocks(n_src, c)) * 2 * c);
   unsigned* erec = w.take<unsigned>(cw <= 2 ? e * 4 : e * 2);
   unsigned* emask = cw <= 2 ? nullptr : w.take<unsigned>(e * cw);
+  float* score_ws = w.take<float>(e);
   if (!w.ok()) return BGNN_ERR_WORKSPACE;
-  const BwdDstArgs a{rowptr, col, csr_to_csc, order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, c, cw,
-                     out, row_max, row_sum, gout, gHs, gHt, erec, emask, part};
-  int nparts = 0;
-  const int rc = dvec == 4 ? dispatch_bwd_dst<4>(dg, dch, a, nparts, stream)
-               : dvec == 2 ? dispatch_bwd_dst<2>(dg, dch, a, nparts, stream)
-                           : dispatch_bwd_dst<1>(dg, dch, a, nparts, stream);
-  if (rc != BGNN_OK) return rc;
-  reduce_partials_kernel<<<2 * c, 256, 0, stream>>>(part, nparts, 2 * c, g_af_t2s, g_af_s2t, c);
-  BGNN_LAUNCH_CHECK();
-#define CALL(V, G_, C_)                                                                                            \
-  gatv2_bwd_src_kernel<V, G_, C_><<<(unsigned)blocks, 256, 0, stream>>>(t_rowptr, t_col, t_order, dst_is_src, af_t2s,      \
-      af_s2t, slope, n, c, cw, erec, emask, gout, gHs, gHt)
+  if (!score && n > 0) {
+    // the caller did not keep the forward's scores: one score-only sweep of the forward kernel
+    const int rc = launch_gatv2_fwd(rowptr, col, order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, row_off, c, nullptr,
+                                    nullptr, nullptr, score_ws, 1, stream);
+    if (rc != BGNN_OK) return rc;
+    score = score_ws;
+  }
+  int npa = 0, npb = 0;
+  if (n > 0) {
+    BwdDstArgs a{rowptr, col, csr_to_csc, order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, 0, row_off, c, cw,
+                 out, row_max, row_sum, score, gout, gHs, gHt, erec, emask, part};
+    // the head of the degree order: one warp per row, so that a hub row is not a single group's serial loop
+    const long long n_hub = (order && dg >= 2 && dg <= 16) ? (n < kHubRows ? n : kHubRows) : 0;
+    if (n_hub > 0) {
+      a.n = n_hub;
+      int nh = 0;
+      const int rc = dvec == 4 ? dispatch_bwd_dst_hubs<4>(dg, a, nh, stream)
+                   : dvec == 2 ? dispatch_bwd_dst_hubs<2>(dg, a, nh, stream)
+                               : dispatch_bwd_dst_hubs<1>(dg, a, nh, stream);
+      if (rc != BGNN_OK) return rc;
+      npa = nh;
+    }
+    if (n > n_hub) {
+      a.n = n - n_hub;
+      a.slot_off = n_hub;
+      a.part = part + (size_t)npa * 2 * c;
+      int nr = 0;
+      const int rc = dvec == 4 ? dispatch_bwd_dst<4>(dg, dch, a, nr, stream)
+                   : dvec == 2 ? dispatch_bwd_dst<2>(dg, dch, a, nr, stream)
+                               : dispatch_bwd_dst<1>(dg, dch, a, nr, stream);
+      if (rc != BGNN_OK) return rc;
+      npa += nr;
+    }
+  }
+  float* part_b = part + (size_t)npa * 2 * c;
+  int rcb = BGNN_OK;
+#define CALL(V, G_, C_)                                                                                                   \
+  rcb = launch_bwd_src_cfg<V, G_, C_>(t_rowptr, t_col, t_order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n_src, row_off, n, c, \
+                                      cw, erec, emask, gout, gHs, gHt, part_b, npb, stream)
   BGNN_ROW_DISPATCH(vec, g, ch, CALL);
 #undef CALL
+  if (rcb != BGNN_OK) return rcb;
+  reduce_partials_kernel<<<2 * c, 256, 0, stream>>>(part, (long long)npa + npb, 2 * c, g_af_t2s, g_af_s2t, c);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }

@@ -64,18 +64,19 @@ template <int HD, int C>
 __global__ void __launch_bounds__(MH_THREADS)
 gatv2_heads_fwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const uint8_t* __restrict__ dst_is_src,
                        const float* __restrict__ Hs, const float* __restrict__ Ht, const float* __restrict__ af_t2s,
-                       const float* __restrict__ af_s2t, float slope, long long n, float* __restrict__ out,
+                       const float* __restrict__ af_s2t, float slope, long long n, long long row_off, float* __restrict__ out,
                        float* __restrict__ row_max, float* __restrict__ row_sum) {
   constexpr int F = HD * C;
   const int lane = threadIdx.x & 31, sub = lane % MH_ES;
   const unsigned rmask = mh_row_mask(lane);
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / MH_ES;
   if (row >= n) return;                       // the 8 lanes of a row leave together
+  const long long grow = row + row_off;       // global node id (destination-partitioned layout; 0 offset otherwise)
   const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-  const bool is_src = dst_is_src[row] != 0;
+  const bool is_src = dst_is_src[grow] != 0;
   const float* __restrict__ H = is_src ? Hs : Ht;
   float hi[F], av[F], acc[F], m[HD], l[HD];
-  mh_load<F>(H + row * F, hi);
+  mh_load<F>(H + grow * F, hi);
   mh_load<F>((is_src ? af_t2s : af_s2t), av);
 #pragma unroll
   for (int f = 0; f < F; ++f) acc[f] = 0.f;
@@ -141,7 +142,8 @@ __global__ void __launch_bounds__(128, 6)
 gatv2_heads_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ csr_to_csc,
                            const uint8_t* __restrict__ dst_is_src, const float* __restrict__ Hs,
                            const float* __restrict__ Ht, const float* __restrict__ af_t2s,
-                           const float* __restrict__ af_s2t, float slope, long long n, const float* __restrict__ out,
+                           const float* __restrict__ af_s2t, float slope, long long n, long long row_off,
+                           const float* __restrict__ out,
                            const float* __restrict__ row_max, const float* __restrict__ row_sum,
                            const float* __restrict__ gout, float* __restrict__ gHs, float* __restrict__ gHt,
                            unsigned* __restrict__ erec, float* __restrict__ ga_part) {
@@ -158,15 +160,16 @@ gatv2_heads_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict
   for (long long set = wid; set < nsets; set += nwarps) {
     const long long row = set * RPW + lane / MH_ES;
     if (row >= n) continue;
+    const long long grow = row + row_off;
     const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-    const bool is_src = dst_is_src[row] != 0;
+    const bool is_src = dst_is_src[grow] != 0;
     float gi[F];
 #pragma unroll
     for (int f = 0; f < F; ++f) gi[f] = 0.f;
     if (beg < end) {
       const float* __restrict__ H = is_src ? Hs : Ht;
       float hi[F], av[F], go[F], oi[F], ga[F], D[HD], m[HD], inv[HD], dsum[HD];
-      mh_load<F>(H + row * F, hi);
+      mh_load<F>(H + grow * F, hi);
       mh_load<F>((is_src ? af_t2s : af_s2t), av);
       mh_load<F>(gout + row * F, go);
       mh_load<F>(out + row * F, oi);
@@ -245,7 +248,8 @@ gatv2_heads_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict
           if (sub == 0) s_ga[(is_src ? 0 : F) + h * C + c][threadIdx.x] += ga[h * C + c];
         }
     }
-    if (sub == 0) mh_store<F>((is_src ? gHs : gHt) + row * F, gi);
+    float* gdst = is_src ? gHs : gHt;
+    if (sub == 0 && gdst) mh_store<F>(gdst + grow * F, gi);
   }
   __syncwarp();
 #pragma unroll
@@ -286,7 +290,8 @@ template <int HD, int C>
 __global__ void __launch_bounds__(MH_THREADS)
 gatv2_heads_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restrict__ t_col,
                            const uint8_t* __restrict__ dst_is_src, const float* __restrict__ af_t2s,
-                           const float* __restrict__ af_s2t, float slope, long long n, const unsigned* __restrict__ erec,
+                           const float* __restrict__ af_s2t, float slope, long long n, long long own_lo, long long own_n,
+                           const unsigned* __restrict__ erec,
                            const float* __restrict__ gout, float* __restrict__ gHs, float* __restrict__ gHt) {
   constexpr int F = HD * C;
   const int lane = threadIdx.x & 31, sub = lane % MH_ES;
@@ -335,15 +340,18 @@ gatv2_heads_bwd_src_kernel(const int* __restrict__ t_rowptr, const int* __restri
   if (sub == 0) {
     // destination-side part of this row from pass A lives in the array of the row's own domain
     const bool me_src = dst_is_src[row] != 0;
-    float own[F];
-    mh_load<F>((me_src ? gHs : gHt) + row * F, own);
+    const float* ownp = me_src ? gHs : gHt;
+    if (ownp && row >= own_lo && row < own_lo + own_n) {     // rows this rank owns as destinations
+      float own[F];
+      mh_load<F>(ownp + row * F, own);
 #pragma unroll
-    for (int f = 0; f < F; ++f) {
-      gs[f] += me_src ? own[f] : 0.f;
-      gt[f] += me_src ? 0.f : own[f];
+      for (int f = 0; f < F; ++f) {
+        gs[f] += me_src ? own[f] : 0.f;
+        gt[f] += me_src ? 0.f : own[f];
+      }
     }
-    mh_store<F>(gHs + row * F, gs);
-    mh_store<F>(gHt + row * F, gt);
+    if (gHs) mh_store<F>(gHs + row * F, gs);
+    if (gHt) mh_store<F>(gHt + row * F, gt);
   }
 }
 
@@ -364,14 +372,14 @@ static long long mh_dst_max_warps() { return (long long)kNumSMs * kMhDstMaxCtasP
   } while (0)
 
 int launch_gatv2_heads_fwd(const int* rowptr, const int* col, const uint8_t* dst_is_src, const float* Hs, const float* Ht,
-                           const float* af_t2s, const float* af_s2t, float slope, long long n, int heads, int c,
+                           const float* af_t2s, const float* af_s2t, float slope, long long n, long long row_off, int heads, int c,
                            float* out, float* row_max, float* row_sum, cudaStream_t stream) {
   if (n <= 0) return BGNN_OK;
   if (!gatv2_heads_supported(heads, c)) return BGNN_ERR_UNSUPPORTED;
   const long long blocks = (n * MH_ES + MH_THREADS - 1) / MH_THREADS;
 #define CALL(H_, C_)                                                                                             \
   gatv2_heads_fwd_kernel<H_, C_><<<(unsigned)blocks, MH_THREADS, 0, stream>>>(rowptr, col, dst_is_src, Hs, Ht, af_t2s, \
-                                                                              af_s2t, slope, n, out, row_max, row_sum)
+                                                                              af_s2t, slope, n, row_off, out, row_max, row_sum)
   MH_DISPATCH(CALL);
 #undef CALL
   BGNN_LAUNCH_CHECK();
@@ -385,10 +393,11 @@ size_t gatv2_heads_bwd_workspace_bytes(long long n, long long e, int heads, int 
 }
 
 template <int HD, int C>
-static int mh_launch_dst(long long n, int& nwarps, cudaStream_t stream, const int* rowptr, const int* col,
+static int mh_launch_dst(long long n, long long row_off, int& nwarps, cudaStream_t stream, const int* rowptr, const int* col,
                          const int* csr_to_csc, const uint8_t* dst_is_src, const float* Hs, const float* Ht,
                          const float* af_t2s, const float* af_s2t, float slope, const float* out, const float* row_max,
                          const float* row_sum, const float* gout, float* gHs, float* gHt, unsigned* erec, float* part) {
+  if (n <= 0) { nwarps = 0; return BGNN_OK; }        // a rank that owns no destination row
   auto kern = gatv2_heads_bwd_dst_kernel<HD, C>;
   static int occ = 0;
   if (occ == 0) {
@@ -402,17 +411,18 @@ static int mh_launch_dst(long long n, int& nwarps, cudaStream_t stream, const in
   if (ctas > (long long)kNumSMs * occ) ctas = (long long)kNumSMs * occ;
   nwarps = (int)(ctas * WPC);
   kern<<<(unsigned)ctas, kMhDstThreads, 0, stream>>>(rowptr, col, csr_to_csc, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n,
-                                                     out, row_max, row_sum, gout, gHs, gHt, erec, part);
+                                                     row_off, out, row_max, row_sum, gout, gHs, gHt, erec, part);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }
 
 int launch_gatv2_heads_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csr_to_csc,
                            long long e, const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
-                           const float* af_s2t, float slope, long long n, int heads, int c, const float* out,
+                           const float* af_s2t, float slope, long long n, long long row_off, long long n_src, int heads, int c,
+                           const float* out,
                            const float* row_max, const float* row_sum, const float* gout, float* gHs, float* gHt,
                            float* g_af_t2s, float* g_af_s2t, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  if (n <= 0) return BGNN_OK;
+  if (n_src <= 0) return BGNN_OK;
   if (!gatv2_heads_supported(heads, c)) return BGNN_ERR_UNSUPPORTED;
   const int f = heads * c;
   Workspace w(ws, ws_bytes);
@@ -421,17 +431,17 @@ int launch_gatv2_heads_bwd(const int* rowptr, const int* col, const int* t_rowpt
   if (!w.ok()) return BGNN_ERR_WORKSPACE;
   int nparts = 0, rc = BGNN_OK;
 #define CALL(H_, C_)                                                                                                \
-  rc = mh_launch_dst<H_, C_>(n, nparts, stream, rowptr, col, csr_to_csc, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, out, \
+  rc = mh_launch_dst<H_, C_>(n, row_off, nparts, stream, rowptr, col, csr_to_csc, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, out, \
                              row_max, row_sum, gout, gHs, gHt, erec, part)
   MH_DISPATCH(CALL);
 #undef CALL
   if (rc != BGNN_OK) return rc;
   mh_reduce_partials_kernel<<<2 * f, 256, 0, stream>>>(part, nparts, 2 * f, g_af_t2s, g_af_s2t, f);
   BGNN_LAUNCH_CHECK();
-  const long long blocks = (n * MH_ES + MH_THREADS - 1) / MH_THREADS;
+  const long long blocks = (n_src * MH_ES + MH_THREADS - 1) / MH_THREADS;
 #define CALL(H_, C_)                                                                                                \
   gatv2_heads_bwd_src_kernel<H_, C_><<<(unsigned)blocks, MH_THREADS, 0, stream>>>(t_rowptr, t_col, dst_is_src, af_t2s, \
-                                                                                  af_s2t, slope, n, erec, gout, gHs, gHt)
+                                                                                  af_s2t, slope, n_src, row_off, n, erec, gout, gHs, gHt)
   MH_DISPATCH(CALL);
 #undef CALL
   BGNN_LAUNCH_CHECK();

@@ -76,19 +76,19 @@ int launch_rows_by_degree(const int* rowptr, long long n, int min_degree, int* o
 
 // spmm_csr.cu
 int launch_spmm_csr(const int* rowptr, const int* col, const float* edge_w, const float* gather_scale,
-                    const float* out_scale, const float* X, long long n_rows, int f, int reduce_mean, float* Y,
-                    cudaStream_t stream);
+                    const float* out_scale, const float* X, long long ldx, long long n_rows, int f, int reduce_mean, float* Y,
+                    long long ldy, cudaStream_t stream);
 
 // gatv2_fused.cu
 int launch_gatv2_fwd(const int* rowptr, const int* col, const int* order, const uint8_t* dst_is_src, const float* Hs, const float* Ht,
-                     const float* af_t2s, const float* af_s2t, float slope, long long n, int c, float* out,
-                     float* row_max, float* row_sum, cudaStream_t stream);
+                     const float* af_t2s, const float* af_s2t, float slope, long long n, long long row_off, int c, float* out,
+                     float* row_max, float* row_sum, float* score, int score_only, cudaStream_t stream);
 size_t gatv2_bwd_workspace_bytes(long long n, long long e, int c);
 int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csr_to_csc,
                      const int* order, const int* t_order, long long e, const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
-                     const float* af_s2t, float slope, long long n, int c, const float* out, const float* row_max,
-                     const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
-                     float* g_af_s2t, void* ws, size_t ws_bytes, cudaStream_t stream);
+                     const float* af_s2t, float slope, long long n, long long row_off, long long n_src, int c, const float* out,
+                     const float* row_max, const float* row_sum, const float* score, const float* gout, float* gHs, float* gHt,
+                     float* g_af_t2s, float* g_af_s2t, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // adapted_transform.cu
 int launch_adapted_transform_fwd(const float* P, const uint8_t* is_src, const float* wd, const float* kg, const float* bias,
@@ -101,13 +101,13 @@ int launch_adapted_transform_bwd(const float* gHs, const float* gHt, const float
 // gatv2_heads.cu: 2-3 narrow aggregations over the same graph in one pass
 bool gatv2_heads_supported(int heads, int c);
 int launch_gatv2_heads_fwd(const int* rowptr, const int* col, const uint8_t* dst_is_src, const float* Hs, const float* Ht,
-                           const float* af_t2s, const float* af_s2t, float slope, long long n, int heads, int c,
+                           const float* af_t2s, const float* af_s2t, float slope, long long n, long long row_off, int heads, int c,
                            float* out, float* row_max, float* row_sum, cudaStream_t stream);
 size_t gatv2_heads_bwd_workspace_bytes(long long n, long long e, int heads, int c);
 int launch_gatv2_heads_bwd(const int* rowptr, const int* col, const int* t_rowptr, const int* t_col, const int* csr_to_csc,
                            long long e, const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
-                           const float* af_s2t, float slope, long long n, int heads, int c, const float* out,
-                           const float* row_max, const float* row_sum, const float* gout, float* gHs, float* gHt,
+                           const float* af_s2t, float slope, long long n, long long row_off, long long n_src, int heads, int c,
+                           const float* out, const float* row_max, const float* row_sum, const float* gout, float* gHs, float* gHt,
                            float* g_af_t2s, float* g_af_s2t, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // adapted_skinny.cu
@@ -158,6 +158,10 @@ int launch_bn_relu_fwd(const float* x, long long n, int c, const float* w, const
                        float* running_mean, float* running_var, int relu, float* y, float* stats, void* ws, size_t ws_bytes,
                        cudaStream_t stream);
 int launch_bn_relu_apply(const float* x, long long n, int c, const float* stats, int relu, float* y, cudaStream_t stream);
+int launch_bn_relu_bwd_reduce(const float* gy, const float* x, long long n, int c, const float* stats, int relu, float* gwb,
+                              void* ws, size_t ws_bytes, cudaStream_t stream);
+int launch_bn_relu_bwd_apply(const float* gy, const float* x, long long n, int c, const float* stats, int relu,
+                             const float* coef, float* gx, cudaStream_t stream);
 int launch_bn_relu_bwd(const float* gy, const float* x, long long n, int c, const float* stats, int relu, float* gx, float* gwb,
                        void* ws, size_t ws_bytes, cudaStream_t stream);
 

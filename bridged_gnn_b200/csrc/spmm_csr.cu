@@ -18,7 +18,8 @@ template <int VEC, int G, int CH>
 __global__ void __launch_bounds__(256)
 spmm_csr_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ edge_w,
                 const float* __restrict__ gather_scale, const float* __restrict__ out_scale,
-                const float* __restrict__ X, long long n_rows, int f, int reduce_mean, float* __restrict__ Y) {
+                const float* __restrict__ X, long long ldx, long long n_rows, int f, int reduce_mean, float* __restrict__ Y,
+                long long ldy) {
   const int lane_g = threadIdx.x % G;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
   if (row >= n_rows) return;   // whole groups exit together
@@ -47,7 +48,7 @@ spmm_csr_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
       if (gather_scale && j[u] >= 0) w[u] *= __ldg(gather_scale + j[u]);
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch)
-        x[u][ch] = ld_chunk<VEC>(X + (long long)(j[u] < 0 ? 0 : j[u]) * f + (ch * G + lane_g) * VEC, cok[ch] && j[u] >= 0);
+        x[u][ch] = ld_chunk<VEC>(X + (long long)(j[u] < 0 ? 0 : j[u]) * ldx + (ch * G + lane_g) * VEC, cok[ch] && j[u] >= 0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -62,7 +63,7 @@ spmm_csr_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
   for (int ch = 0; ch < CH; ++ch) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[ch].v[i] *= s;
-    st_chunk<VEC>(Y + row * f + (ch * G + lane_g) * VEC, acc[ch], cok[ch]);
+    st_chunk<VEC>(Y + row * ldy + (ch * G + lane_g) * VEC, acc[ch], cok[ch]);
   }
 }
 
@@ -70,7 +71,8 @@ spmm_csr_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
 __global__ void __launch_bounds__(256)
 spmm_csr_generic_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ edge_w,
                         const float* __restrict__ gather_scale, const float* __restrict__ out_scale,
-                        const float* __restrict__ X, long long n_rows, int f, int reduce_mean, float* __restrict__ Y) {
+                        const float* __restrict__ X, long long ldx, long long n_rows, int f, int reduce_mean,
+                        float* __restrict__ Y, long long ldy) {
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_rows) return;
@@ -84,28 +86,30 @@ spmm_csr_generic_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
       int j = __ldg(col + e);
       float w = edge_w ? __ldg(edge_w + e) : 1.f;
       if (gather_scale) w *= __ldg(gather_scale + j);
-      if (c < f) acc = fmaf(w, __ldg(X + (long long)j * f + c), acc);
+      if (c < f) acc = fmaf(w, __ldg(X + (long long)j * ldx + c), acc);
     }
-    if (c < f) Y[row * f + c] = acc * s;
+    if (c < f) Y[row * ldy + c] = acc * s;
   }
 }
 
 int launch_spmm_csr(const int* rowptr, const int* col, const float* edge_w, const float* gather_scale,
-                    const float* out_scale, const float* X, long long n_rows, int f, int reduce_mean, float* Y,
-                    cudaStream_t stream) {
+                    const float* out_scale, const float* X, long long ldx, long long n_rows, int f, int reduce_mean, float* Y,
+                    long long ldy, cudaStream_t stream) {
   if (n_rows <= 0 || f <= 0) return BGNN_OK;
   int vec, g, ch;
-  if (!pick_row_config(f, vec, g, ch)) {
+  // 128-bit loads need 16-byte aligned rows: bases and strides (a column panel of a wider matrix qualifies)
+  const bool aligned = ldx % 4 == 0 && ldy % 4 == 0 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0;
+  if (!pick_row_config(f, vec, g, ch) || (vec == 4 && !aligned)) {
     long long blocks = (n_rows * 32 + 255) / 256;
     spmm_csr_generic_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rowptr, col, edge_w, gather_scale, out_scale, X,
-                                                                    n_rows, f, reduce_mean, Y);
+                                                                    ldx, n_rows, f, reduce_mean, Y, ldy);
     BGNN_LAUNCH_CHECK();
     return BGNN_OK;
   }
   long long blocks = (n_rows * g + 255) / 256;
 #define CALL(V, G_, C_)                                                                                          \
   spmm_csr_kernel<V, G_, C_><<<(unsigned)blocks, 256, 0, stream>>>(rowptr, col, edge_w, gather_scale, out_scale, \
-                                                                     X, n_rows, f, reduce_mean, Y)
+                                                                     X, ldx, n_rows, f, reduce_mean, Y, ldy)
   BGNN_ROW_DISPATCH(vec, g, ch, CALL);
 #undef CALL
   BGNN_LAUNCH_CHECK();

@@ -13,22 +13,28 @@ from .. import ops
 from ..data import add_self_loops, remove_self_loops
 
 
-def bn_relu(bn, x):
-    """relu(bn(x)) (models/KTGNN.py:425-429); plain nn.BatchNorm1d on the GPU goes through the fused two-pass kernels,
-    anything else (SyncBatchNorm of the partitioned path, CPU, other dtypes) through the module itself."""
+def bn_relu(bn, x, part=None):
+    """relu(bn(x)) (models/KTGNN.py:425-429); plain nn.BatchNorm1d on the GPU goes through the fused two-pass kernels
+    -- with the batch statistics combined over the ranks of ``part`` (a ``dist.DstPartition``) when x is row-partitioned
+    -- anything else (SyncBatchNorm, CPU, other dtypes) through the module itself."""
     if type(bn) is nn.BatchNorm1d and ops.batch_norm_relu_supported(x, bn):
+        if part is not None and part.world > 1 and bn.training:
+            return ops.batch_norm_relu_dist(x, bn, part.group, part.r1 - part.r0)
         return ops.batch_norm_relu(x, bn)
+    if part is not None and part.world > 1 and bn.training and type(bn) is nn.BatchNorm1d:
+        raise RuntimeError("row-partitioned BatchNorm1d on this input needs torch.nn.SyncBatchNorm "
+                           "(convert_sync_batchnorm) or an fp32 CUDA input of a supported width")
     return F.relu(bn(x))
 
 
-def run_sequential(seq, x):
+def run_sequential(seq, x, part=None):
     """``seq(x)`` for an nn.Sequential, with every BatchNorm1d -> ReLU pair taken by ``bn_relu``
     (clf_transformer, models/KTGNN.py:363-366)."""
     mods = list(seq)
     i = 0
     while i < len(mods):
         if isinstance(mods[i], nn.modules.batchnorm._BatchNorm) and i + 1 < len(mods) and type(mods[i + 1]) is nn.ReLU:
-            x = bn_relu(mods[i], x)
+            x = bn_relu(mods[i], x, part)
             i += 2
         else:
             x = mods[i](x)
@@ -190,46 +196,55 @@ class AdaptedConv(nn.Module):
             h_s, h_t = ops.adapted_transform(p, wd, k_g, self._dst_is_src(c), b2)   # biases, gates, rank-1 corrections
         return h_s, h_t, a_t2s, a_s2t, cp
 
-    def _forward_partitioned(self, x, edge_index, central_mask, part):
-        """Destination-partitioned forward: domain means by all-reduce, node-wise transforms on
-        the local rows, all-gather of H (dense halo), fused aggregation over the local destination rows;
-        autograd turns the all-gather into the reduce-scatter of dH."""
+    def _local_masks(self, central_mask, part):
+        """(is_src of this rank's rows uint8 [n_loc], global is_src uint8 [n_pad], (1/Ns, 1/Nt)), cached per mask."""
+        def build(cm):
+            glob = part.pad_rows(self._dst_is_src(cm)[: part.n])
+            return part.local_rows(glob[: part.n]).contiguous(), glob.contiguous(), self._domain_counts(cm[: part.n])
+        return part.local_cached(("masks", id(self)), central_mask, build)
+
+    def node_part_partitioned(self, x, central_mask, part):
+        """Node-wise half for this rank's rows of a row-partitioned x: the two domain means are all-reduced, the rest
+        is the single-GPU code on the local rows (padding rows count as target-domain rows; nothing reads them)."""
         from .. import dist as bdist
-        if self.root_weight or self.normalize:
-            raise NotImplementedError("partitioned AdaptedConv supports root_weight=False, normalize=False (all recipes)")
-        d, co = x.shape[1], self.out_channels
-        c_loc = part.local_rows(central_mask[: part.n].to(x.dtype))           # [n_loc] (padding rows: 0)
-        valid = part.local_rows(torch.ones(part.n, dtype=x.dtype, device=x.device))
-        n_s = central_mask[: part.n].sum().clamp(min=1).to(x.dtype)
-        n_t = (part.n - central_mask[: part.n].sum()).clamp(min=1).to(x.dtype)
-        is_src_loc = part.local_rows(self._dst_is_src(central_mask)[: part.n])
+        d = x.shape[1]
+        is_src_loc, _, inv_counts = self._local_masks(central_mask, part)
         if x.is_cuda and x.dtype == torch.float32 and ops.domain_colsum_supported(d):
-            # padding rows of x are zero, so it does not matter which domain they are counted in
-            local = ops.domain_means(x, is_src_loc, torch.stack((1.0 / n_s, 1.0 / n_t)))
+            local = ops.domain_means(x, is_src_loc, inv_counts)       # padding rows of x are zero
         else:
-            local = torch.stack((c_loc / n_s, (valid - c_loc) / n_t), 0) @ x   # [2, n_loc] x [n_loc, d]
+            cf = is_src_loc.to(x.dtype)
+            valid = part.local_rows(torch.ones(part.n, dtype=x.dtype, device=x.device))
+            local = torch.stack((cf * inv_counts[0], (valid - cf) * inv_counts[1]), 0) @ x
         means = bdist.all_reduce_sum_autograd(local, part.group)
         delta = means[0:1] - means[1:2]
         w_s, w_t, b_s, b_t, a_t2s, a_s2t, cp = self._padded_params()
         w_cat = torch.cat((w_s, w_t, self.a_g_s2t.weight[:, :d], self.a_g_t2s.weight[:, :d]), 0)
         k_g = torch.stack(((self.a_g_s2t.weight[:, d:] * delta).sum(), (self.a_g_t2s.weight[:, d:] * delta).sum()))
         wd = delta @ torch.cat((w_s, w_t), 0).t()
-        # node-wise transform of the local rows with the same fused kernels as the single-GPU path (padding rows
-        # count as target-domain rows there; nothing reads them and their gradients are zero)
-        b_cat = None if b_s is None else torch.cat((b_s, b_t, b_s.new_zeros(2)))
-        if x.is_cuda and x.dtype == torch.float32 and ops.adapted_skinny_supported(cp, d):
+        b2 = None if b_s is None else torch.cat((b_s, b_t))
+        on_gpu = x.is_cuda and x.dtype == torch.float32
+        if on_gpu and ops.adapted_skinny_supported(cp, d):
+            b_cat = None if b_s is None else torch.cat((b_s, b_t, b_s.new_zeros(2)))
             h_s, h_t = ops.adapted_skinny(x, w_cat, b_cat, wd, k_g, is_src_loc)
-        elif x.is_cuda and x.dtype == torch.float32 and ops.adapted_wide_supported(cp, d):
-            b2 = None if b_s is None else torch.cat((b_s, b_t))
+        elif on_gpu and ops.adapted_wide_supported(cp, d):
             h_s, h_t = ops.adapted_wide(x, w_cat, b2, wd, k_g, is_src_loc)
         else:
-            b2 = None if b_s is None else torch.cat((b_s, b_t))
             h_s, h_t = ops.adapted_transform(x @ w_cat.t(), wd, k_g, is_src_loc, b2)
-        H_s = bdist.all_gather_rows_autograd(h_s, part.group)                  # [n_pad, cp]
-        H_t = bdist.all_gather_rows_autograd(h_t, part.group)
-        graph = ops.cached_graph(edge_index, part.n_pad)
-        out = ops.gat_aggregate(H_s, H_t, a_t2s, a_s2t, graph, self._dst_is_src(central_mask), self.negative_slope)
-        return out[part.r0:part.r0 + part.n_loc, :co]
+        return h_s, h_t, a_t2s, a_s2t, cp
+
+    def _forward_partitioned(self, x, edge_index, central_mask, part):
+        """Destination-partitioned forward: node-wise transforms on the local rows, domain-aware halo
+        exchange of H (a rank receives lin_s(.) of all nodes only if it owns source-domain destinations, lin_t(.) only
+        if it owns target-domain ones), fused aggregation over the LOCAL destination rows; autograd turns the exchange
+        into the transposed one for dH."""
+        from .. import dist as bdist
+        if self.root_weight or self.normalize:
+            raise NotImplementedError("partitioned AdaptedConv supports root_weight=False, normalize=False (all recipes)")
+        h_s, h_t, a_t2s, a_s2t, cp = self.node_part_partitioned(x, central_mask, part)
+        H_s, H_t = bdist.halo_exchange(h_s, h_t, part, central_mask)            # [n_pad, cp] each, or None
+        _, is_src_glob, _ = self._local_masks(central_mask, part)
+        out = ops.gat_aggregate(H_s, H_t, a_t2s, a_s2t, part.graph(edge_index), is_src_glob, self.negative_slope)
+        return out[:, : self.out_channels] if cp != self.out_channels else out
 
     def __repr__(self):
         return "{}({}, {})".format(self.__class__.__name__, self.in_channels, self.out_channels)
@@ -241,7 +256,7 @@ def adapted_convs_shared_graph(convs, xs, edge_index, edge_index1, edge_index2, 
     one by one, the (lin_s, lin_t) outputs are laid side by side and a single multi-head kernel walks the edges."""
     c = central_mask
     widths = {conv.out_channels for conv in convs}
-    ok = (part is None and len(widths) == 1 and len(convs) in (2, 3) and all(torch.is_tensor(x) and x.is_cuda for x in xs)
+    ok = (len(widths) == 1 and len(convs) in (2, 3) and all(torch.is_tensor(x) and x.is_cuda for x in xs)
           and not any(conv.root_weight or conv.normalize for conv in convs)
           and len({conv.negative_slope for conv in convs}) == 1)
     order = list(range(len(convs)))
@@ -261,6 +276,10 @@ def adapted_convs_shared_graph(convs, xs, edge_index, edge_index1, edge_index2, 
                 sub = idxs[j: j + 2]
                 if ops.adapted_skinny_group_supported(x, cp, len(sub)):
                     d = x.shape[1]
+                    if part is not None:
+                        is_src_rows, _, inv_counts = convs[sub[0]]._local_masks(c, part)
+                    else:
+                        is_src_rows, inv_counts = convs[sub[0]]._dst_is_src(c), convs[sub[0]]._domain_counts(c)
                     hp = []
                     for i in sub:
                         w_s, w_t, b_s, b_t, _, _, _ = convs[i]._padded_params()
@@ -268,13 +287,14 @@ def adapted_convs_shared_graph(convs, xs, edge_index, edge_index1, edge_index2, 
                         hp.append((torch.cat((w_s, w_t, a1[:, :d], a2[:, :d]), 0),
                                    None if b_s is None else torch.cat((b_s, b_t, b_s.new_zeros(2))),
                                    torch.cat((a1[:, d:], a2[:, d:]), 0)))
-                    h_s, h_t = ops.adapted_skinny_group(x, convs[sub[0]]._dst_is_src(c), convs[sub[0]]._domain_counts(c), hp)
+                    h_s, h_t = ops.adapted_skinny_group(x, is_src_rows, inv_counts, hp,
+                                                        group=None if part is None or part.world == 1 else part.group)
                     hs.append(h_s)
                     ht.append(h_t)
                 else:
-                    means = convs[sub[0]].domain_means(x, c)
+                    means = None if part is not None else convs[sub[0]].domain_means(x, c)
                     for i in sub:
-                        p = convs[i].node_part(x, c, means)
+                        p = convs[i].node_part_partitioned(x, c, part) if part is not None else convs[i].node_part(x, c, means)
                         hs.append(p[0])
                         ht.append(p[1])
                 for i in sub:
@@ -284,9 +304,15 @@ def adapted_convs_shared_graph(convs, xs, edge_index, edge_index1, edge_index2, 
                     order.append(i)
     if not ok:
         return [conv(x, edge_index, edge_index1, edge_index2, c, part=part) for conv, x in zip(convs, xs)]
-    graph = ops.cached_graph(edge_index, xs[0].shape[0])
-    out = ops.gat_aggregate_heads(torch.cat(hs, 1), torch.cat(ht, 1), torch.cat(af1), torch.cat(af2), graph,
-                                  convs[0]._dst_is_src(c), convs[0].negative_slope, len(convs))
+    hs_all, ht_all = torch.cat(hs, 1), torch.cat(ht, 1)
+    if part is not None:
+        from .. import dist as bdist
+        hs_all, ht_all = bdist.halo_exchange(hs_all, ht_all, part, c)      # every head's operands in ONE exchange
+        graph, is_src = part.graph(edge_index), convs[0]._local_masks(c, part)[1]
+    else:
+        graph, is_src = ops.cached_graph(edge_index, xs[0].shape[0]), convs[0]._dst_is_src(c)
+    out = ops.gat_aggregate_heads(hs_all, ht_all, torch.cat(af1), torch.cat(af2), graph, is_src, convs[0].negative_slope,
+                                  len(convs))
     co = convs[0].out_channels
     res = [None] * len(convs)
     for pos, i in enumerate(order):                 # heads were laid out group by group
@@ -341,7 +367,7 @@ class _KTGNNBase(nn.Module):
                                       "(padding rows would enter the batch statistics)")
         for ind in range(n_convs):
             x = self.convs[ind](x, ei, ei1, ei2, c, part=part)
-            x = bn_relu(self.bns[ind], x) if self.use_bn else F.relu(x)
+            x = bn_relu(self.bns[ind], x, part) if self.use_bn else F.relu(x)
             x = F.dropout(x, p=self.dropout, training=self.training)
         return x
 
@@ -372,7 +398,8 @@ class KTGNN_no_complement(_KTGNNBase):
         """``data.part`` (a ``dist.DstPartition``), if present, selects the destination-partitioned multi-GPU
         forward: ``data.x`` = this rank's rows [n_loc, F], ``data.edge_index`` = this rank's incoming edges
         AFTER graph_partition's self-loop rewrite (global ids), ``data.central_mask`` = padded global mask.
-        BatchNorm layers must then be SyncBatchNorm (``torch.nn.SyncBatchNorm.convert_sync_batchnorm``)."""
+        BatchNorm1d layers combine their batch statistics over the ranks (``ops.batch_norm_relu_dist``); call
+        ``part.sync_grads(model)`` after ``backward()``."""
         part = getattr(data, "part", None)
         if part is not None:
             ei1 = ei2 = None
@@ -382,7 +409,7 @@ class KTGNN_no_complement(_KTGNNBase):
         c = data.central_mask
         x = self._hidden(data.x, ei, ei1, ei2, c, len(self.convs), part)
         logits_base, logits_trans, logits_target = adapted_convs_shared_graph(
-            (self.clf_base, self.clf_target, self.clf_target), (x, run_sequential(self.clf_transformer, x), x), ei, ei1, ei2, c, part)
+            (self.clf_base, self.clf_target, self.clf_target), (x, run_sequential(self.clf_transformer, x, part), x), ei, ei1, ei2, c, part)
         return F.log_softmax(logits_base, 1), F.log_softmax(logits_target, 1), F.log_softmax(logits_trans, 1), None
 
 

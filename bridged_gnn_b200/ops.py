@@ -203,12 +203,23 @@ def rows_by_degree(rowptr, n, min_degree=0):
 class CSRGraph:
     """Destination-major CSR of an edge list plus, lazily, the CSR of the transposed graph (needed by
     the backward passes).  Built once per graph and cached by the layers, where the reference rebuilds
-    a SparseTensor on every forward (models/backbones.py:464)."""
+    a SparseTensor on every forward (models/backbones.py:464).
 
-    def __init__(self, edge_index, num_nodes):
+    Destination-partitioned (multi-GPU) form: ``n_rows`` / ``row_off`` say that the edge list holds only the edges
+    whose destination lies in [row_off, row_off + n_rows) (global ids).  Rows are then LOCAL (0 .. n_rows-1), column
+    entries stay global (0 .. n-1), and the transposed CSR has n rows (every source) with local destination entries."""
+
+    def __init__(self, edge_index, num_nodes, n_rows=None, row_off=0):
         self.n = int(num_nodes)
+        self.n_src = self.n
+        self.n_rows = self.n if n_rows is None else int(n_rows)
+        self.row_off = int(row_off)
         self.edge_index = edge_index
-        self.rowptr, self.col, self.perm, self.e = edges_to_csr(edge_index[0], edge_index[1], self.n)
+        self._dst = edge_index[1] if self.row_off == 0 else edge_index[1] - self.row_off
+        rowptr, self.col, self.perm, self.e = edges_to_csr(edge_index[0], self._dst, self.n)
+        if self.e and self.n_rows < self.n and int(rowptr[self.n_rows]) != self.e:
+            raise IndexError("edge_index holds destinations outside [%d, %d)" % (self.row_off, self.row_off + self.n_rows))
+        self.rowptr = rowptr[: self.n_rows + 1]
         self._t = None
         self._deg = None
         self._csr_to_csc = None
@@ -218,7 +229,7 @@ class CSRGraph:
     @property
     def t(self):
         if self._t is None:
-            self._t = edges_to_csr(self.edge_index[1], self.edge_index[0], self.n)[:3]
+            self._t = edges_to_csr(self._dst, self.edge_index[0], self.n)[:3]
         return self._t
 
     @property
@@ -239,7 +250,7 @@ class CSRGraph:
         if c < WIDE_ROW:
             return None
         if self._order is None:
-            self._order = rows_by_degree(self.rowptr, self.n, 0)
+            self._order = rows_by_degree(self.rowptr, self.n_rows, 0)
         return self._order
 
     def t_order(self, c=WIDE_ROW):
@@ -265,36 +276,41 @@ class CSRGraph:
     @property
     def deg(self):
         if self._deg is None:
-            self._deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.float32)
+            self._deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.float32)     # [n_rows]
         return self._deg
 
 
 _graph_cache = {}
 
 
-def cached_graph(edge_index, num_nodes):
-    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device))
+def cached_graph(edge_index, num_nodes, n_rows=None, row_off=0):
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device),
+           n_rows, row_off)
     g = _graph_cache.get(key)
     if g is None:
         if len(_graph_cache) >= 4:      # a handful of live graphs; each entry pins its edge list and two CSRs
             _graph_cache.pop(next(iter(_graph_cache)))
-        g = CSRGraph(edge_index, num_nodes)
+        g = CSRGraph(edge_index, num_nodes, n_rows, row_off)
         _graph_cache[key] = g
     return g
 
 
 # ----------------------------------------------------------------------------------- SpMM
-def _spmm_raw(rowptr, col, X, n_rows, reduce_mean=False, edge_w=None, gather_scale=None, out_scale=None):
+def _spmm_raw(rowptr, col, X, n_rows, reduce_mean=False, edge_w=None, gather_scale=None, out_scale=None, out=None):
+    """X [*, f] and ``out`` [n_rows, f] may be column panels (row-strided views) of wider matrices."""
     lib = _lib.load()
-    X = X.contiguous()
-    f = X.shape[1]
-    Y = torch.empty((n_rows, f), dtype=torch.float32, device=X.device)
     f32 = torch.float32
+    if X.stride(1) != 1:
+        X = X.contiguous()
+    f = X.shape[1]
+    Y = torch.empty((n_rows, f), dtype=f32, device=X.device) if out is None else out
+    if X.dtype != f32 or Y.dtype != f32 or not X.is_cuda or Y.stride(1) != 1:
+        raise TypeError("spmm needs fp32 CUDA matrices with unit column stride")
     with _lib.call("bgnn_spmm_csr_f32"):
-        _lib.check(lib.bgnn_spmm_csr_f32(_lib.ptr(rowptr, torch.int32), _lib.ptr(col, torch.int32),
-                                         _lib.ptr(edge_w, f32, True), _lib.ptr(gather_scale, f32, True),
-                                         _lib.ptr(out_scale, f32, True), _lib.ptr(X, f32), n_rows, f, int(reduce_mean),
-                                         _lib.ptr(Y), _lib.stream(X.device)))
+        _lib.check(lib.bgnn_spmm_csr_ld_f32(_lib.ptr(rowptr, torch.int32), _lib.ptr(col, torch.int32),
+                                            _lib.ptr(edge_w, f32, True), _lib.ptr(gather_scale, f32, True),
+                                            _lib.ptr(out_scale, f32, True), X.data_ptr(), X.stride(0), n_rows, f,
+                                            int(reduce_mean), Y.data_ptr(), Y.stride(0), _lib.stream(X.device)))
     return Y
 
 
@@ -304,7 +320,7 @@ class _SpmmFn(torch.autograd.Function):
         ctx.graph, ctx.reduce, ctx.edge_weight = graph, reduce, edge_weight
         ctx.gather_scale, ctx.out_scale = gather_scale, out_scale
         ew = None if edge_weight is None else edge_weight[graph.perm].contiguous()
-        return _spmm_raw(graph.rowptr, graph.col, X.to(torch.float32), graph.n, reduce == "mean", ew, gather_scale,
+        return _spmm_raw(graph.rowptr, graph.col, X.to(torch.float32), graph.n_rows, reduce == "mean", ew, gather_scale,
                          out_scale)
 
     @staticmethod
@@ -332,50 +348,69 @@ def spmm(graph, X, reduce="sum", edge_weight=None, gather_scale=None, out_scale=
 
 
 # ----------------------------------------------------------------------------------- fused AdaptedConv aggregation
+def _pick(Hs, Ht):
+    """(Hs, Ht) with a missing one replaced by the other as a never-read stand-in (a destination-partitioned rank that
+    owns no destination row of a domain is given no H of that domain)."""
+    if Hs is None and Ht is None:
+        raise ValueError("at least one of Hs, Ht is needed")
+    return (Ht if Hs is None else Hs), (Hs if Ht is None else Ht)
+
+
 class _GatAggFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope):
         lib = _lib.load()
         f32 = torch.float32
+        has = (Hs is not None, Ht is not None)
+        Hs, Ht = _pick(Hs, Ht)
         Hs, Ht = Hs.to(f32).contiguous(), Ht.to(f32).contiguous()
         a1, a2 = af_t2s.to(f32).contiguous().view(-1), af_s2t.to(f32).contiguous().view(-1)
-        n, c = Hs.shape
+        c = Hs.shape[1]
+        if Hs.shape[0] != graph.n_src or Ht.shape[0] != graph.n_src:
+            raise ValueError("H must have one row per node of the graph (%d)" % graph.n_src)
+        n = graph.n_rows
         dev = Hs.device
         out = torch.empty((n, c), dtype=f32, device=dev)
         row_max = torch.empty((n,), dtype=f32, device=dev)
         row_sum = torch.empty((n,), dtype=f32, device=dev)
-        with _lib.call("bgnn_gatv2_fwd_ord_f32", "bgnn_gatv2_fwd_f32[c=%d]" % c):
-            _lib.check(lib.bgnn_gatv2_fwd_ord_f32(_lib.ptr(graph.rowptr), _lib.ptr(graph.col),
-                                              _lib.ptr(graph.order(c), torch.int32, True),
-                                              _lib.ptr(dst_is_src, torch.uint8), _lib.ptr(Hs), _lib.ptr(Ht),
-                                              _lib.ptr(a1), _lib.ptr(a2), float(slope), n, c, _lib.ptr(out),
-                                              _lib.ptr(row_max), _lib.ptr(row_sum), _lib.stream(dev)))
-        ctx.save_for_backward(Hs, Ht, a1, a2, out, row_max, row_sum)
-        ctx.graph, ctx.dst_is_src, ctx.slope = graph, dst_is_src, float(slope)
+        # training: the per-edge scores stay for the backward (4 B per edge instead of a recomputation per edge)
+        keep = any(ctx.needs_input_grad[:4])
+        score = torch.empty((max(graph.e, 1),), dtype=f32, device=dev) if keep else None
+        with _lib.call("bgnn_gatv2_fwd_part_f32", "bgnn_gatv2_fwd_f32[c=%d]" % c):
+            _lib.check(lib.bgnn_gatv2_fwd_part_f32(_lib.ptr(graph.rowptr), _lib.ptr(graph.col),
+                                                   _lib.ptr(graph.order(c), torch.int32, True),
+                                                   _lib.ptr(dst_is_src, torch.uint8), _lib.ptr(Hs), _lib.ptr(Ht),
+                                                   _lib.ptr(a1), _lib.ptr(a2), float(slope), n, graph.row_off, c,
+                                                   _lib.ptr(out), _lib.ptr(row_max), _lib.ptr(row_sum),
+                                                   _lib.ptr(score, allow_none=True), _lib.stream(dev)))
+        ctx.save_for_backward(Hs, Ht, a1, a2, out, row_max, row_sum, score)
+        ctx.graph, ctx.dst_is_src, ctx.slope, ctx.has = graph, dst_is_src, float(slope), has
         ctx.a_shapes = (af_t2s.shape, af_s2t.shape)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         lib = _lib.load()
-        Hs, Ht, a1, a2, out, row_max, row_sum = ctx.saved_tensors
+        Hs, Ht, a1, a2, out, row_max, row_sum, score = ctx.saved_tensors
         g = ctx.graph
         t_rowptr, t_col, _ = g.t
-        n, c = Hs.shape
+        c = Hs.shape[1]
         dev = Hs.device
         gout = gout.to(torch.float32).contiguous()
-        gHs, gHt = torch.empty_like(Hs), torch.empty_like(Ht)
+        gHs = torch.empty_like(Hs) if ctx.has[0] else None
+        gHt = torch.empty_like(Ht) if ctx.has[1] else None
         ga1, ga2 = torch.empty_like(a1), torch.empty_like(a2)
-        ws = _lib.workspace(lib.bgnn_gatv2_bwd_workspace_bytes(n, g.e, c), dev)
-        with _lib.call("bgnn_gatv2_bwd_ord_f32", "bgnn_gatv2_bwd_f32[c=%d]" % c):
-            _lib.check(lib.bgnn_gatv2_bwd_ord_f32(_lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(t_rowptr), _lib.ptr(t_col),
-                                              _lib.ptr(g.csr_to_csc, torch.int32), _lib.ptr(g.order(c), torch.int32, True),
-                                              _lib.ptr(g.t_order(c), torch.int32, True), g.e,
-                                              _lib.ptr(ctx.dst_is_src), _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(a1),
-                                              _lib.ptr(a2), ctx.slope, n, c, _lib.ptr(out), _lib.ptr(row_max),
-                                              _lib.ptr(row_sum), _lib.ptr(gout), _lib.ptr(gHs), _lib.ptr(gHt),
-                                              _lib.ptr(ga1), _lib.ptr(ga2), _lib.ptr(ws), ws.numel(),
-                                              _lib.stream(dev)))
+        ws = _lib.workspace(lib.bgnn_gatv2_bwd_workspace_bytes(g.n_src, g.e, c), dev)
+        with _lib.call("bgnn_gatv2_bwd_part_f32", "bgnn_gatv2_bwd_f32[c=%d]" % c):
+            _lib.check(lib.bgnn_gatv2_bwd_part_f32(_lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(t_rowptr), _lib.ptr(t_col),
+                                                   _lib.ptr(g.csr_to_csc, torch.int32), _lib.ptr(g.order(c), torch.int32, True),
+                                                   _lib.ptr(g.t_order(c), torch.int32, True), g.e,
+                                                   _lib.ptr(ctx.dst_is_src), _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(a1),
+                                                   _lib.ptr(a2), ctx.slope, g.n_rows, g.row_off, g.n_src, c, _lib.ptr(out),
+                                                   _lib.ptr(row_max), _lib.ptr(row_sum), _lib.ptr(score, allow_none=True),
+                                                   _lib.ptr(gout), _lib.ptr(gHs, allow_none=True),
+                                                   _lib.ptr(gHt, allow_none=True), _lib.ptr(ga1), _lib.ptr(ga2), _lib.ptr(ws),
+                                                   ws.numel(), _lib.stream(dev)))
         return gHs, gHt, ga1.view(ctx.a_shapes[0]), ga2.view(ctx.a_shapes[1]), None, None, None
 
 
@@ -383,7 +418,11 @@ def gat_aggregate(Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope=0.1):
     """Edge part of AdaptedConv (models/KTGNN.py:292-305 + message :317-319) as one fused kernel per
     direction of autograd: scores a.leaky_relu(H[src]+H[dst]), softmax over each destination's incoming
     edges (PyG softmax, +1e-16), weighted sum of H[src]; (H, a) = (Hs, af_t2s) for destinations in the
-    source domain, (Ht, af_s2t) otherwise.  dst_is_src: uint8 [n]."""
+    source domain, (Ht, af_s2t) otherwise.  dst_is_src: uint8 [n].
+
+    With a destination-partitioned ``graph`` (``CSRGraph(..., n_rows, row_off)``) Hs / Ht / dst_is_src cover ALL nodes,
+    the result the rank's own ``n_rows`` destination rows; Hs or Ht may be None on a rank without destination rows of
+    that domain."""
     return _GatAggFn.apply(Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope)
 
 
@@ -392,21 +431,24 @@ class _GatHeadsFn(torch.autograd.Function):
     def forward(ctx, Hs, Ht, af_t2s, af_s2t, graph, dst_is_src, slope, heads):
         lib = _lib.load()
         f32 = torch.float32
+        has = (Hs is not None, Ht is not None)
+        Hs, Ht = _pick(Hs, Ht)
         Hs, Ht = Hs.to(f32).contiguous(), Ht.to(f32).contiguous()
         a1, a2 = af_t2s.to(f32).contiguous().view(-1), af_s2t.to(f32).contiguous().view(-1)
-        n, f = Hs.shape
+        f = Hs.shape[1]
         c = f // heads
+        n = graph.n_rows
         dev = Hs.device
         out = torch.empty((n, f), dtype=f32, device=dev)
         row_max = torch.empty((n, heads), dtype=f32, device=dev)
         row_sum = torch.empty((n, heads), dtype=f32, device=dev)
-        with _lib.call("bgnn_gatv2_heads_fwd_f32", "bgnn_gatv2_heads_fwd_f32[%dx%d]" % (heads, c)):
-            _lib.check(lib.bgnn_gatv2_heads_fwd_f32(_lib.ptr(graph.rowptr), _lib.ptr(graph.col),
-                                                    _lib.ptr(dst_is_src, torch.uint8), _lib.ptr(Hs), _lib.ptr(Ht),
-                                                    _lib.ptr(a1), _lib.ptr(a2), float(slope), n, heads, c, _lib.ptr(out),
-                                                    _lib.ptr(row_max), _lib.ptr(row_sum), _lib.stream(dev)))
+        with _lib.call("bgnn_gatv2_heads_fwd_part_f32", "bgnn_gatv2_heads_fwd_f32[%dx%d]" % (heads, c)):
+            _lib.check(lib.bgnn_gatv2_heads_fwd_part_f32(_lib.ptr(graph.rowptr), _lib.ptr(graph.col),
+                                                         _lib.ptr(dst_is_src, torch.uint8), _lib.ptr(Hs), _lib.ptr(Ht),
+                                                         _lib.ptr(a1), _lib.ptr(a2), float(slope), n, graph.row_off, heads, c,
+                                                         _lib.ptr(out), _lib.ptr(row_max), _lib.ptr(row_sum), _lib.stream(dev)))
         ctx.save_for_backward(Hs, Ht, a1, a2, out, row_max, row_sum)
-        ctx.graph, ctx.dst_is_src, ctx.slope, ctx.heads = graph, dst_is_src, float(slope), heads
+        ctx.graph, ctx.dst_is_src, ctx.slope, ctx.heads, ctx.has = graph, dst_is_src, float(slope), heads, has
         ctx.a_shapes = (af_t2s.shape, af_s2t.shape)
         return out
 
@@ -416,20 +458,23 @@ class _GatHeadsFn(torch.autograd.Function):
         Hs, Ht, a1, a2, out, row_max, row_sum = ctx.saved_tensors
         g, heads = ctx.graph, ctx.heads
         t_rowptr, t_col, _ = g.t
-        n, f = Hs.shape
+        f = Hs.shape[1]
         c = f // heads
         dev = Hs.device
         gout = gout.to(torch.float32).contiguous()
-        gHs, gHt = torch.empty_like(Hs), torch.empty_like(Ht)
+        gHs = torch.empty_like(Hs) if ctx.has[0] else None
+        gHt = torch.empty_like(Ht) if ctx.has[1] else None
         ga1, ga2 = torch.empty_like(a1), torch.empty_like(a2)
-        ws = _lib.workspace(lib.bgnn_gatv2_heads_bwd_workspace_bytes(n, g.e, heads, c), dev)
-        with _lib.call("bgnn_gatv2_heads_bwd_f32", "bgnn_gatv2_heads_bwd_f32[%dx%d]" % (heads, c)):
-            _lib.check(lib.bgnn_gatv2_heads_bwd_f32(_lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(t_rowptr), _lib.ptr(t_col),
-                                                    _lib.ptr(g.csr_to_csc, torch.int32), g.e, _lib.ptr(ctx.dst_is_src),
-                                                    _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(a1), _lib.ptr(a2), ctx.slope, n,
-                                                    heads, c, _lib.ptr(out), _lib.ptr(row_max), _lib.ptr(row_sum),
-                                                    _lib.ptr(gout), _lib.ptr(gHs), _lib.ptr(gHt), _lib.ptr(ga1),
-                                                    _lib.ptr(ga2), _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+        ws = _lib.workspace(lib.bgnn_gatv2_heads_bwd_workspace_bytes(g.n_src, g.e, heads, c), dev)
+        with _lib.call("bgnn_gatv2_heads_bwd_part_f32", "bgnn_gatv2_heads_bwd_f32[%dx%d]" % (heads, c)):
+            _lib.check(lib.bgnn_gatv2_heads_bwd_part_f32(_lib.ptr(g.rowptr), _lib.ptr(g.col), _lib.ptr(t_rowptr), _lib.ptr(t_col),
+                                                         _lib.ptr(g.csr_to_csc, torch.int32), g.e, _lib.ptr(ctx.dst_is_src),
+                                                         _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(a1), _lib.ptr(a2), ctx.slope,
+                                                         g.n_rows, g.row_off, g.n_src, heads, c, _lib.ptr(out),
+                                                         _lib.ptr(row_max), _lib.ptr(row_sum), _lib.ptr(gout),
+                                                         _lib.ptr(gHs, allow_none=True), _lib.ptr(gHt, allow_none=True),
+                                                         _lib.ptr(ga1), _lib.ptr(ga2), _lib.ptr(ws), ws.numel(),
+                                                         _lib.stream(dev)))
         return gHs, gHt, ga1.view(ctx.a_shapes[0]), ga2.view(ctx.a_shapes[1]), None, None, None, None
 
 
@@ -818,6 +863,95 @@ def batch_norm_relu(x, bn, relu=True):
     return y
 
 
+class _BnReluDistFn(torch.autograd.Function):
+    """BatchNorm1d (+ ReLU), training mode, over a node-feature matrix whose ROWS are partitioned over the ranks of
+    ``group``: every rank reduces its own rows with the library's kernels, the per-rank (count, mean, variance) are
+    combined exactly (Chan et al.'s pairwise update, in double) after one all-gather of 2c+1 numbers per rank, and the
+    normalisation uses the global statistics.  Backward: per-rank column sums, one all-reduce of 2c numbers, one apply
+    pass.  Replaces torch.nn.SyncBatchNorm + ReLU in the destination-partitioned KT-GNN."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu, group, n_rows):
+        import torch.distributed as dist
+        lib = _lib.load()
+        f32, f64 = torch.float32, torch.float64
+        x = x.to(f32).contiguous()
+        c = x.shape[1]
+        n_loc = int(n_rows)                     # real rows of this rank (padding rows, if any, follow them)
+        dev = x.device
+        world = dist.get_world_size(group)
+        stats_loc = torch.empty((4 * c,), dtype=f32, device=dev)
+        ws = _lib.workspace(lib.bgnn_bn_relu_workspace_bytes(c), dev)
+        with _lib.call("bgnn_bn_relu_fwd_f32", "bgnn_bn_relu_stats_f32"):
+            _lib.check(lib.bgnn_bn_relu_fwd_f32(_lib.ptr(x), n_loc, c, None, None, 0.0, 0.0, None, None, 0, None,
+                                                _lib.ptr(stats_loc), _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+        mine = torch.empty((2 * c + 1,), dtype=f64, device=dev)
+        mine[0] = float(n_loc)
+        mine[1:c + 1] = stats_loc[:c].to(f64)
+        mine[c + 1:] = stats_loc[c:2 * c].to(f64).pow(-2)          # eps = 0 above: invstd^-2 is the biased variance
+        if n_loc == 0:
+            mine[1:] = 0.0
+        allr = torch.empty((world, 2 * c + 1), dtype=f64, device=dev)
+        dist.all_gather_into_tensor(allr, mine.view(1, -1), group=group)
+        cnt, mean_r, var_r = allr[:, :1], allr[:, 1:c + 1], allr[:, c + 1:]
+        n_tot = cnt.sum()
+        mean = (cnt * mean_r).sum(0) / n_tot
+        var = (cnt * (var_r + (mean_r - mean).pow(2))).sum(0) / n_tot
+        invstd = (var + eps).rsqrt()
+        w = torch.ones(c, dtype=f64, device=dev) if weight is None else weight.detach().to(f64)
+        b = torch.zeros(c, dtype=f64, device=dev) if bias is None else bias.detach().to(f64)
+        stats = torch.cat((mean, invstd, w * invstd, b)).to(f32).contiguous()
+        if running_mean is not None:
+            running_mean.mul_(1.0 - momentum).add_((momentum * mean).to(running_mean.dtype))
+            unbiased = var * (n_tot / (n_tot - 1).clamp(min=1.0))
+            running_var.mul_(1.0 - momentum).add_((momentum * unbiased).to(running_var.dtype))
+        y = torch.empty_like(x)
+        with _lib.call("bgnn_bn_relu_apply_f32"):
+            _lib.check(lib.bgnn_bn_relu_apply_f32(_lib.ptr(x), x.shape[0], c, _lib.ptr(stats), int(relu), _lib.ptr(y),
+                                                  _lib.stream(dev)))
+        ctx.save_for_backward(x, stats, n_tot)
+        ctx.meta = (int(relu), weight is not None, bias is not None, group, n_loc)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        import torch.distributed as dist
+        lib = _lib.load()
+        x, stats, n_tot = ctx.saved_tensors
+        relu, has_w, has_b, group, n_loc = ctx.meta
+        f32 = torch.float32
+        gy = gy.to(f32).contiguous()
+        c = x.shape[1]
+        dev = x.device
+        gwb = torch.empty((2 * c,), dtype=f32, device=dev)          # this rank's (d weight | d bias)
+        ws = _lib.workspace(lib.bgnn_bn_relu_workspace_bytes(c), dev)
+        with _lib.call("bgnn_bn_relu_bwd_reduce_f32"):
+            _lib.check(lib.bgnn_bn_relu_bwd_reduce_f32(_lib.ptr(gy), _lib.ptr(x), n_loc, c, _lib.ptr(stats), relu, _lib.ptr(gwb),
+                                                       _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+        tot = gwb.to(torch.float64)
+        dist.all_reduce(tot, group=group)
+        coef = (torch.cat((tot[c:], tot[:c])) / n_tot).to(f32).contiguous()      # (mean g | mean g xhat) over all rows
+        gx = torch.zeros_like(x) if n_loc < x.shape[0] else torch.empty_like(x)
+        with _lib.call("bgnn_bn_relu_bwd_apply_f32"):
+            _lib.check(lib.bgnn_bn_relu_bwd_apply_f32(_lib.ptr(gy), _lib.ptr(x), n_loc, c, _lib.ptr(stats), relu, _lib.ptr(coef),
+                                                      _lib.ptr(gx), _lib.stream(dev)))
+        # parameter gradients stay per rank: the caller sums them over ranks with every other parameter gradient
+        return gx, (gwb[:c] if has_w else None), (gwb[c:] if has_b else None), None, None, None, None, None, None, None
+
+
+def batch_norm_relu_dist(x, bn, group, n_rows=None, relu=True):
+    """relu(bn(x)) in training mode for x row-partitioned over ``group`` (see _BnReluDistFn).  ``n_rows``: real rows of
+    this rank when x carries padding rows at the end (they come out as relu(bn(0)) and get zero gradient)."""
+    if not bn.training:
+        return batch_norm_relu(x, bn, relu)
+    track = bn.track_running_stats and bn.running_mean is not None
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return _BnReluDistFn.apply(x, bn.weight, bn.bias, bn.running_mean if track else None, bn.running_var if track else None,
+                               bn.momentum if bn.momentum is not None else 0.0, bn.eps, relu, group,
+                               x.shape[0] if n_rows is None else n_rows)
+
+
 # ----------------------------------------------------------------------------------- narrow AdaptedConv transform
 class _AdaptedSkinnyFn(torch.autograd.Function):
     @staticmethod
@@ -883,7 +1017,7 @@ class _SkinnyGroupFn(torch.autograd.Function):
     accumulation pass per consumer."""
 
     @staticmethod
-    def forward(ctx, x, is_src, inv_counts, heads, *params):
+    def forward(ctx, x, is_src, inv_counts, heads, group, *params):
         lib = _lib.load()
         f32 = torch.float32
         x = x.to(f32).contiguous()
@@ -899,6 +1033,9 @@ class _SkinnyGroupFn(torch.autograd.Function):
         with _lib.call("bgnn_domain_colsum_f32"):
             _lib.check(lib.bgnn_domain_colsum_f32(_lib.ptr(x), _lib.ptr(is_src, torch.uint8), n, d, _lib.ptr(sums),
                                                   _lib.ptr(wsp), wsp.numel(), _lib.stream(dev)))
+        if group is not None:      # rows partitioned over ranks: the domain sums are global
+            import torch.distributed as dist
+            dist.all_reduce(sums, group=group)
         means = sums * inv_counts.view(2, 1)
         delta = means[0] - means[1]                                        # [d]
         wcat = torch.cat(ws_, 0).contiguous()                              # [heads*o, d]
@@ -927,14 +1064,14 @@ class _SkinnyGroupFn(torch.autograd.Function):
                                                                  c, heads, _lib.ptr(Hs), _lib.ptr(Ht), _lib.ptr(gates),
                                                                  _lib.stream(dev)))
         ctx.save_for_backward(x, wcat, atail, wd, gates, is_src, delta, inv_counts)
-        ctx.meta = (heads, c, d, has_bias)
+        ctx.meta = (heads, c, d, has_bias, group)
         return Hs, Ht
 
     @staticmethod
     def backward(ctx, gHs, gHt):
         lib = _lib.load()
         x, wcat, atail, wd, gates, is_src, delta, inv_counts = ctx.saved_tensors
-        heads, c, d, has_bias = ctx.meta
+        heads, c, d, has_bias, group = ctx.meta
         f32 = torch.float32
         gHs, gHt = gHs.to(f32).contiguous(), gHt.to(f32).contiguous()
         n, dev, o = x.shape[0], x.device, 2 * c + 2
@@ -949,6 +1086,10 @@ class _SkinnyGroupFn(torch.autograd.Function):
         w3, a3 = wcat.view(heads, o, d), atail.view(heads, 2, d)
         # wd_h = W_h[:2c] delta, kg_h = A_h delta  ->  d delta, and through the two means into every row of x
         g_delta = torch.einsum("hj,hjd->d", g_wd, w3[:, : 2 * c, :]) + torch.einsum("hk,hkd->d", g_kg, a3)
+        if group is not None:      # Delta is a function of EVERY rank's rows: its gradient is the sum over ranks
+            import torch.distributed as dist
+            g_delta = g_delta.contiguous()
+            dist.all_reduce(g_delta, group=group)
         gm = torch.stack((g_delta * inv_counts[0], -g_delta * inv_counts[1])).contiguous()
         gx = torch.empty_like(x)
         red = torch.empty((heads * (o * d + o + 2 * c),), dtype=f32, device=dev)
@@ -961,7 +1102,7 @@ class _SkinnyGroupFn(torch.autograd.Function):
         g_w[:, : 2 * c, :] += g_wd.unsqueeze(2) * delta.view(1, 1, d)       # wd = W[:2c] delta
         colsum = red[heads * o * d: heads * o * d + heads * o].view(heads, o)
         g_a = g_kg.unsqueeze(2) * delta.view(1, 1, d)                       # [heads, 2, d]
-        out = [gx, None, None, None]
+        out = [gx, None, None, None, None]
         for h in range(heads):
             g_b = None
             if has_bias[h]:
@@ -977,15 +1118,17 @@ def adapted_skinny_group_supported(x, c, heads):
             and domain_colsum_supported(x.shape[1]))
 
 
-def adapted_skinny_group(x, is_src, inv_counts, head_params):
+def adapted_skinny_group(x, is_src, inv_counts, head_params, group=None):
     """Node-wise part (models/KTGNN.py:275-284) of 1 or 2 narrow AdaptedConvs over the SAME input x, domain means
     included.  ``head_params``: per head (w_cat [2c+2, d] = [W_s; W_t; a_g_s2t[:d]; a_g_t2s[:d]], b_cat [2c+2] or
     None, a_tail [2, d] = [a_g_s2t[d:]; a_g_t2s[d:]]); ``inv_counts`` = (1/Ns, 1/Nt).  Returns (Hs, Ht), each
-    [n, heads*c] with the heads side by side.  Differentiable in x and every parameter."""
+    [n, heads*c] with the heads side by side.  Differentiable in x and every parameter.  ``group``: x holds this
+    rank's rows of a row-partitioned matrix (inv_counts are then the GLOBAL domain sizes); the parameter gradients
+    returned are this rank's share."""
     flat = []
     for w, b, a in head_params:
         flat += [w, b, a]
-    return _SkinnyGroupFn.apply(x, is_src, inv_counts, len(head_params), *flat)
+    return _SkinnyGroupFn.apply(x, is_src, inv_counts, len(head_params), group, *flat)
 
 
 class _DomainMeansFn(torch.autograd.Function):

@@ -129,6 +129,13 @@ int bgnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* ed
                       const float* out_scale, const float* X, int64_t n_rows, int f, int reduce_mean, float* Y,
                       void* stream);
 
+/* The same with row strides (elements) of X and Y, so that a column panel of a wider matrix is addressed in place:
+ * the destination-partitioned multi-GPU path gathers X panel by panel and runs this on panel p while panel p+1 is
+ * still on the wire.  128-bit loads need ldx, ldy multiples of 4 and 16-byte aligned bases. */
+int bgnn_spmm_csr_ld_f32(const int32_t* rowptr, const int32_t* col, const float* edge_w, const float* gather_scale,
+                         const float* out_scale, const float* X, int64_t ldx, int64_t n_rows, int f, int reduce_mean,
+                         float* Y, int64_t ldy, void* stream);
+
 /* Fused AdaptedConv aggregation (models/KTGNN.py:292-305, message :317-319; PyG softmax +
  * propagate underneath).  Per destination row i: (H, a) = (Hs, af_t2s) if dst_is_src[i] else
  * (Ht, af_s2t); score_j = a . leaky_relu(H[j] + H[i], slope); out[i] = sum_j softmax_j(score) H[j].
@@ -142,10 +149,21 @@ int bgnn_gatv2_fwd_f32(const int32_t* rowptr, const int32_t* col, const uint8_t*
  * bgnn_rows_by_degree gives "longest rows first", which removes the tail a hub row of a kNN graph otherwise
  * forms and evens out the rows that share a warp.  Rows shorter than min_degree keep their natural order after
  * the long ones (use that for narrow feature rows, whose row-level accesses should stay coalesced; 0 = full
- * sort).  Results do not depend on the order. */
+ * sort).  Forward results do not depend on the order; in the backward the longest rows of an order get a whole warp
+ * each (their edges are split over several lane groups), which changes the fp32 summation order of those rows'
+ * gradients -- every order gives run-to-run reproducible results. */
 int bgnn_gatv2_fwd_ord_f32(const int32_t* rowptr, const int32_t* col, const int32_t* row_order, const uint8_t* dst_is_src,
                            const float* Hs, const float* Ht, const float* af_t2s, const float* af_s2t, float slope,
                            int64_t n, int c, float* out, float* row_max, float* row_sum, void* stream);
+/* Training / destination-partitioned form of the forward.  n_rows destination rows with LOCAL ids 0..n_rows-1 (rowptr,
+ * row_order, out, row_max, row_sum) whose global node id is row + row_off; Hs, Ht and dst_is_src are indexed by
+ * GLOBAL node id (col entries are global ids).  score [e] (CSR edge order) or NULL: the per-edge attention scores
+ * a . leaky_relu(H[src] + H[dst]), kept for bgnn_gatv2_bwd_part_f32 so that the backward never recomputes them.
+ * Single GPU: row_off = 0. */
+int bgnn_gatv2_fwd_part_f32(const int32_t* rowptr, const int32_t* col, const int32_t* row_order, const uint8_t* dst_is_src,
+                            const float* Hs, const float* Ht, const float* af_t2s, const float* af_s2t, float slope,
+                            int64_t n_rows, int64_t row_off, int c, float* out, float* row_max, float* row_sum, float* score,
+                            void* stream);
 size_t bgnn_rows_by_degree_workspace_bytes(int64_t n);
 int bgnn_rows_by_degree(const int32_t* rowptr, int64_t n, int min_degree, int32_t* order, void* workspace,
                         size_t workspace_bytes, void* stream);
@@ -170,6 +188,20 @@ int bgnn_gatv2_bwd_ord_f32(const int32_t* rowptr, const int32_t* col, const int3
                            const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
                            float* g_af_s2t, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward with the forward's scores and the destination-partitioned layout: (rowptr, col) has n_rows local destination
+ * rows, (t_rowptr, t_col) n_src source rows (all nodes) whose entries are LOCAL destination ids; gout, out, row_max,
+ * row_sum are local, Hs, Ht, dst_is_src, gHs, gHt global ([n_src, c]; the destination-side part of local row r lands at
+ * r + row_off).  score [e] from bgnn_gatv2_fwd_part_f32, or NULL (recomputed by one extra sweep).  gHs or gHt may be
+ * NULL on a rank that owns no destination row of that domain (nothing would be written but zeros).  The workspace is
+ * sized by bgnn_gatv2_bwd_workspace_bytes(n_src, e, c).  Single GPU: row_off = 0, n_src = n_rows. */
+int bgnn_gatv2_bwd_part_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
+                            const int32_t* csr_to_csc, const int32_t* row_order, const int32_t* t_row_order, int64_t e,
+                            const uint8_t* dst_is_src, const float* Hs, const float* Ht, const float* af_t2s,
+                            const float* af_s2t, float slope, int64_t n_rows, int64_t row_off, int64_t n_src, int c,
+                            const float* out, const float* row_max, const float* row_sum, const float* score,
+                            const float* gout, float* gHs, float* gHt, float* g_af_t2s, float* g_af_s2t, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* Two or three NARROW aggregations (heads) over the same graph in one pass -- KT-GNN's classifier convs
  * clf_base(x), clf_target(clf_transformer(x)), clf_target(x) (models/KTGNN.py:432-434).  Hs, Ht, out, gout, gHs,
  * gHt are [n, heads*c] with head h in columns h*c .. h*c+c-1; af_*, g_af_* are [heads*c]; row_max / row_sum are
@@ -187,6 +219,17 @@ int bgnn_gatv2_heads_bwd_f32(const int32_t* rowptr, const int32_t* col, const in
                              int c, const float* out, const float* row_max, const float* row_sum, const float* gout,
                              float* gHs, float* gHt, float* g_af_t2s, float* g_af_s2t, void* workspace,
                              size_t workspace_bytes, void* stream);
+
+/* Destination-partitioned forms (see bgnn_gatv2_fwd_part_f32 / bgnn_gatv2_bwd_part_f32 for the index conventions). */
+int bgnn_gatv2_heads_fwd_part_f32(const int32_t* rowptr, const int32_t* col, const uint8_t* dst_is_src, const float* Hs,
+                                  const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n_rows,
+                                  int64_t row_off, int heads, int c, float* out, float* row_max, float* row_sum, void* stream);
+int bgnn_gatv2_heads_bwd_part_f32(const int32_t* rowptr, const int32_t* col, const int32_t* t_rowptr, const int32_t* t_col,
+                                  const int32_t* csr_to_csc, int64_t e, const uint8_t* dst_is_src, const float* Hs,
+                                  const float* Ht, const float* af_t2s, const float* af_s2t, float slope, int64_t n_rows,
+                                  int64_t row_off, int64_t n_src, int heads, int c, const float* out, const float* row_max,
+                                  const float* row_sum, const float* gout, float* gHs, float* gHt, float* g_af_t2s,
+                                  float* g_af_s2t, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Node-wise epilogue of AdaptedConv's domain-shift transform (models/KTGNN.py:275-284).  The host computes
  * P [n, 2c+2] = x [W_s; W_t; a_g_s2t[:D]; a_g_t2s[:D]]^T, wd [2c] = [W_s Delta; W_t Delta] and
@@ -282,6 +325,14 @@ int bgnn_bn_relu_fwd_f32(const float* x, int64_t n, int c, const float* weight, 
 int bgnn_bn_relu_apply_f32(const float* x, int64_t n, int c, const float* stats, int relu, float* y, void* stream);
 int bgnn_bn_relu_bwd_f32(const float* gy, const float* x, int64_t n, int c, const float* stats, int relu, float* gx,
                          float* gwb, void* workspace, size_t workspace_bytes, void* stream);
+/* Multi-GPU (rows partitioned over ranks): bgnn_bn_relu_fwd_f32 with y = NULL yields this rank's (mean, invstd) only;
+ * the host combines the ranks' statistics, and bgnn_bn_relu_apply_f32 normalises with the global ones.  Backward in two
+ * halves around an all-reduce: _reduce gives this rank's gwb [2c] = (sum g xhat | sum g) under the global statistics,
+ * _apply takes coef [2c] = (mean g | mean g xhat) over the rows of all ranks. */
+int bgnn_bn_relu_bwd_reduce_f32(const float* gy, const float* x, int64_t n, int c, const float* stats, int relu, float* gwb,
+                                void* workspace, size_t workspace_bytes, void* stream);
+int bgnn_bn_relu_bwd_apply_f32(const float* gy, const float* x, int64_t n, int c, const float* stats, int relu,
+                               const float* coef, float* gx, void* stream);
 
 /* The narrow transform for `heads` (1 or 2) convs that read the SAME x (the classifier heads clf_base / clf_target,
  * models/KTGNN.py:432-434): parameters stacked per head (wcat [heads*(2c+2), d], bias [heads*(2c+2)] or NULL,

@@ -79,17 +79,27 @@ def _mp_worker(rank, world, port, ret):
     from bridged_gnn_b200.models import KTGNN_no_complement, graph_partition
     from oracle import mp_oracle as mo
 
-    # CUDA operators -> oracle on the CPU (test infrastructure, as in tests/test_host_logic.py)
+    # CUDA operators -> oracle on the CPU (test infrastructure, as in tests/test_host_logic.py).  The fakes follow the
+    # partitioned calling convention: H over all nodes (None for an operand this rank never reads), result = the
+    # rank's own destination rows.
     class FakeGraph:
-        def __init__(self, ei, n):
-            self.edge_index, self.n = ei, n
-    ops.cached_graph = lambda ei, n: FakeGraph(ei, n)
+        def __init__(self, ei, n, n_rows=None, row_off=0):
+            self.edge_index, self.n, self.n_src = ei, n, n
+            self.n_rows, self.row_off = (n if n_rows is None else n_rows), row_off
+    ops.cached_graph = lambda ei, n, n_rows=None, row_off=0: FakeGraph(ei, n, n_rows, row_off)
 
     def gat(Hs, Ht, a1, a2, graph, dst_is_src, slope=0.1):
         cm = dst_is_src.bool()
         ei = graph.edge_index
         m1 = cm[ei[1]]
-        return mo.adapted_conv_aggregate(Hs, Ht, ei[:, m1], ei[:, ~m1], cm, a1.view(-1), a2.view(-1), slope)
+        if Hs is None:
+            assert not bool(m1.any())          # no source-domain destination on this rank
+            Hs = torch.zeros_like(Ht)
+        if Ht is None:
+            assert bool(m1.all())
+            Ht = torch.zeros_like(Hs)
+        full = mo.adapted_conv_aggregate(Hs, Ht, ei[:, m1], ei[:, ~m1], cm, a1.view(-1), a2.view(-1), slope)
+        return full[graph.row_off: graph.row_off + graph.n_rows]
     ops.gat_aggregate = gat
     ops.adapted_transform = mo.adapted_transform_epilogue
 
@@ -155,3 +165,50 @@ def test_two_rank_partitioned_ktgnn_matches_single_rank():
             assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-7, key
         assert gerr < 5e-5
         assert abs(ltot - lref) < 1e-5 * max(1.0, abs(lref))
+
+
+# ------------------------------------------------------------------ domain-aware halo exchange
+def _halo_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from bridged_gnn_b200 import dist as bd
+    n, ns, c = 12, 8, 3                      # 8 source + 4 target nodes over 3 ranks: ranks 0, 1 source-only, rank 2 target-only
+    cm = torch.arange(n) < ns
+    part = bd.DstPartition(n)
+    needs = part.needs(cm)
+    g = torch.Generator().manual_seed(5)
+    h_s_all, h_t_all = torch.randn(n, c, generator=g), torch.randn(n, c, generator=g)
+    w_s, w_t = torch.randn(world, n, c, generator=g), torch.randn(world, n, c, generator=g)     # per-rank loss weights
+    h_s = part.local_rows(h_s_all).requires_grad_(True)
+    h_t = part.local_rows(h_t_all).requires_grad_(True)
+    H_s, H_t = bd.halo_exchange(h_s, h_t, part, cm)
+    ok = True
+    loss = h_s.sum() * 0.0
+    if needs[rank][0]:
+        ok &= torch.equal(H_s, h_s_all)
+        loss = loss + (H_s * w_s[rank]).sum()
+    else:
+        ok &= H_s is None
+    if needs[rank][1]:
+        ok &= torch.equal(H_t, h_t_all)
+        loss = loss + (H_t * w_t[rank]).sum()
+    else:
+        ok &= H_t is None
+    loss.backward()
+    want_s = sum(w_s[r] for r in range(world) if needs[r][0])[part.r0:part.r1]
+    want_t = sum(w_t[r] for r in range(world) if needs[r][1])[part.r0:part.r1]
+    ret[rank] = (bool(ok), needs, float((h_s.grad - want_s).abs().max()), float((h_t.grad - want_t).abs().max()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_sends_each_operand_only_where_it_is_read():
+    port = 33500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_halo_worker, args=(3, port, ret), nprocs=3, join=True)
+    for r in range(3):
+        ok, needs, es, et = ret[r]
+        assert needs == ((True, False), (True, False), (False, True))
+        assert ok and es < 1e-6 and et < 1e-6

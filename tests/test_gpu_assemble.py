@@ -106,7 +106,7 @@ def test_quantile_matches_torch(n):
     g = torch.Generator().manual_seed(n)
     v = torch.sigmoid(torch.randn(n, generator=g))
     if n > 100:
-        v[torch.randint(0, n, (n // 3,), generator=g)] = v[0]     # a large tied group
+        v[torch.randint(0, n, (n // 3,), generator=g)] = float(v[0])     # a large tied group
         v[::17] *= -1.0                                           # negative keys
     vd = v.to(DEV)
     for q in (0.0, 0.1, 0.25, 0.5, 0.9, 1.0):

@@ -146,15 +146,29 @@ def test_fb_cosine_head_matches_reference(fb_build, algo):
     with torch.no_grad():
         u_src, u_tar = head.cosine_operand(z_src), head.cosine_operand(z_tar)
     idx, val, gap, stats = ops.knn_cosine(u_tar, u_src, 50, algo=algo)
+    # The node-wise operands u come out of torch's cuBLAS here and out of MKL in the oracle: the two GEMM chains differ
+    # in the last bits run to run (first call of a shape in a process, heuristics), and u_src / u_tar of this
+    # checkpoint are nearly parallel, which amplifies that.  So (1) the operands must agree to 1e-4 relative, (2) the
+    # KERNEL is held to the tight bar against the oracle evaluated on the very operands it was given, and (3) against
+    # the reference's own lists the window is the near-tie window of the operand noise.
+    with torch.no_grad():
+        u_src_c, u_tar_c = head.cpu().cosine_operand(T(g["z_src"])), head.cosine_operand(T(g["z_tar"]))
+        head.cuda()
+    for a, b in ((u_src, u_src_c), (u_tar, u_tar_c)):
+        assert float((a.cpu() - b).abs().max()) <= 1e-4 * float(b.abs().max())
+
+    def sim_from_u(udb, uq):
+        pairs = bo.pair_enumeration(torch.arange(udb.shape[0]).unsqueeze(-1), torch.arange(uq.shape[0]).unsqueeze(-1)).t()
+        return torch.sigmoid(torch.nn.CosineSimilarity(dim=1)(udb[pairs[0]], uq[pairs[1]])).view(-1, udb.shape[0])
+    _check_against_full(sim_from_u(u_src.cpu(), u_tar.cpu()), idx, val, 50, label="fb cross " + algo)
     full = bo.full_sim_matrix(T(g["z_src"]), T(g["z_tar"]), W, "cosine")
-    _check_against_full(full, idx, val, 50, label="fb cross " + algo)
+    _check_against_full(full, idx, val, 50, tol_val=2e-5, label="fb cross (reference operands) " + algo, near_tie=2e-5)
     ref_sets = [set(r.tolist()) for r in g["cross_idx"]]
-    tie_rows = set(torch.nonzero(bo.near_tie_rows(full, 50, NEAR_TIE)).view(-1).tolist())
+    tie_rows = set(torch.nonzero(bo.near_tie_rows(full, 50, 2e-5)).view(-1).tolist())
     differ = {r for r in range(400) if ref_sets[r] != set(idx[r].tolist())}
     assert differ <= tie_rows
     idx, val, gap, _ = ops.knn_cosine(u_tar, u_tar, 5, algo=algo)
-    fullw = bo.full_sim_matrix(T(g["z_tar"]), T(g["z_tar"]), W, "cosine")
-    _check_against_full(fullw, idx, val, 5, label="fb within " + algo)
+    _check_against_full(sim_from_u(u_tar.cpu(), u_tar.cpu()), idx, val, 5, label="fb within " + algo)
 
 
 # ------------------------------------------------------------------ seeded random inputs vs the oracle

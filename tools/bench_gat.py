@@ -22,7 +22,12 @@ def main():
     y = torch.cat((y_s, y_t))
     rnd = bench.make_random_edges(y, bench.RAND_EDGES_PER_NODE, bench.HOMOPHILY, dev)
     tar = torch.arange(ns, n, device=dev).repeat_interleave(bench.K_CROSS)
-    src = torch.randint(0, ns, (tar.numel(),), device=dev)
+    if os.environ.get("BGNN_RANDOM_KNN"):
+        src = torch.randint(0, ns, (tar.numel(),), device=dev)
+    else:      # the bench graph itself: real kNN edges (hub rows, in-degree up to ~1800)
+        u_s, u_t, _, _ = bench.make_sync_embeddings(ns, nt, bench.DIM, dev)
+        src = ops.knn_cosine(u_t, u_s, bench.K_CROSS)[0].reshape(-1)
+        del u_s, u_t
     ei = to_undirected(torch.cat((rnd, torch.stack((src, tar))), 1), n)
     cm = torch.zeros(n, dtype=torch.bool, device=dev)
     cm[:ns] = True

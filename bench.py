@@ -11,8 +11,15 @@ Workload (BASELINE.json configs[3]): synthetic Sync-RD_intra-and-i
   phase B  message passing: one KT-GNN (2 layers, hidden 64) training forward + backward over
            the bridged graph (random edges U kNN edges, undirected, self loops)             -> value, GEdges/s
 A "step" is one phase-B pass; `value` = E_mp * 8 conv passes (4 forward + 4 backward) / step time.
-Multi-GPU (torchrun): weak scaling, every rank owns its own 2^20-node shard (target rows are sharded
-for the build, the kNN lists are all-gathered with NCCL); value sums the ranks' edges over the max time.
+Multi-GPU (torchrun): the headline line is weak scaling -- every rank owns its own 2^20-node replica and `value` sums
+the ranks' edges over the max time.  Beside it, at N > 1 the line carries the paths that really shard:
+  `sharded_build_1m`  ONE sync-1M build with the target rows split over the ranks + NCCL all-gather (verified bit for
+                      bit against the 1-GPU lists)
+  `partitioned_1m`    ONE sync-1M KT-GNN step with the destination rows partitioned over the ranks (domain-aware halo
+                      exchange of H, rank-combined BatchNorm), against the 1-GPU step of the same graph
+  `sync16m`           BASELINE configs[4]: 2^24 nodes, dim 256, k_cross 32 -- row-sharded build, partitioned KT-GNN
+                      step and the panel-pipelined partitioned SpMM (F = 256); also run at N = 1 when it fits
+At N = 1 the line also carries `spmm` (K2 at F = 64 / 128 / 256), `addrelu` (K1b) and `configs_1_3` (office / fb).
 
 --impl reference times the oracle restatement of the reference's own op sequence on the host CPU
 (PyG-free port; the reference itself needs torch_geometric, which is not installable here) on a
@@ -35,6 +42,14 @@ if ROOT not in sys.path:
 NS, NT, DIM, K_CROSS, N_CLASS, HIDDEN = 786432, 262144, 128, 20, 2, 64
 RAND_EDGES_PER_NODE, HOMOPHILY = 5, 0.7
 METRIC = "bridged-graph kNN build ms & KT-GNN message-passing GEdges/s"
+# identical in both arms (the driver compares it): only what names the workload
+CONFIG = {"workload": "sync-1M per GPU (BASELINE configs[3]): Ns=%d Nt=%d dim=%d k_cross=%d classes=%d hidden=%d; "
+                      "step = KT-GNN train fwd+bwd (4 AdaptedConv fwd + 4 bwd) over the bridged graph (5N random 70%%-homophily "
+                      "edges U kNN edges, undirected, self loops)" % (NS, NT, DIM, K_CROSS, N_CLASS, HIDDEN),
+          "conv_passes_per_step": 8,
+          "l2": "inputs exceed L2 (features 537 MB, db 403 MB of fp32)"}
+# BASELINE configs[4]
+NS16, NT16, DIM16, K16 = 12582912, 4194304, 256, 32
 
 
 # ----------------------------------------------------------------------------- synthetic workload
@@ -214,89 +229,409 @@ def _init_ktgnn_params(f_in, n_class, hidden):
 
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args):
+    """The reference's CPU path (oracle port: torch_geometric is not installable) on the box's host cores.
+    Every step is a BOUNDED SAMPLE of the workload: the same generator at N = 2^18 nodes (a quarter of the nodes, same
+    degree distribution), one KT-GNN training forward + backward; `value` is per-edge throughput, so it is comparable
+    with the GPU arm's.  K steps are really run (after W warm-up steps)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t_all = time.perf_counter()
-    # one bounded sample per step (N = 2^18 nodes, ~3 s each on 16 cores), at most 3 steps; then 48 kNN rows (~8 s)
-    mp_runs = [cpu_mp_sample(n_nodes=1 << 18, reps=1) for _ in range(max(1, min(args.steps, 3)))]
-    mp = max(mp_runs, key=lambda r: r["value"])
+    n_nodes = 1 << 18
+    K, W = max(1, args.steps), max(0, args.warmup)
+    # keep the whole run within a few minutes: a step takes ~2.5 s on 16 cores
+    budget_steps = 60
+    if K + W > budget_steps:
+        W = min(W, 3)
+        K = max(1, budget_steps - W)
+    runs = [cpu_mp_sample(n_nodes=n_nodes, reps=1) for _ in range(W + K)]
+    timed = runs[W:]
+    secs = sum(r["seconds"] for r in timed) / len(timed)
+    e_mp = timed[0]["value"] * timed[0]["seconds"] * 1e9 / 8
+    value = e_mp * 8 / secs / 1e9
     knn = cpu_knn_sample(rows=48)
+    sample = "%d timed steps (+%d warm-up) of: %s" % (len(timed), W, timed[0]["sample"].replace(", best of 1", ""))
     line = {
-        "impl": "reference", "metric": METRIC, "value": mp["value"], "unit": "GEdges/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mp["seconds"] * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "sync-1M (configs[3]) sampled for the CPU", "mp_sample": mp["sample"],
-                   "knn_sample": knn["sample"]},
-        "cpu_baseline": {"value": mp["value"], "unit": "GEdges/s", "cores": mp["cores"], "kind": "port",
-                         "sample": mp["sample"]},
-        "e2e": {"value": mp["value"], "unit": "GEdges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GEdges/s", "n_gpus": args.gpus,
+        "steps": len(timed), "warmup": W, "ms_per_step": secs * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+        "cpu_baseline": {"value": value, "unit": "GEdges/s", "cores": timed[0]["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "GEdges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "knn_build": {"ms": knn["ms_full_build_extrapolated"], "gpairs_per_s": knn["gpairs_per_s"], "cores": knn["cores"],
                       "sample": knn["sample"], "note": "ms extrapolated linearly in rows from the sample"},
-        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
+        "requested": {"steps": args.steps, "warmup": args.warmup}, "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import torch.distributed as dist
-    from bridged_gnn_b200 import _lib, ops
-    from bridged_gnn_b200 import dist as bdist
-    from bridged_gnn_b200.data import Data, to_undirected
-    from bridged_gnn_b200.models import KTGNN_no_complement
+class Ctx:
+    """Process-wide state of the GPU arm: device, ranks, timing helpers."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU oracle)")
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.load()
-    peaks = load_peaks()
-    K, W = args.steps, max(args.warmup, 3)
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU oracle)")
+        self.dev = torch.device("cuda", self.local)
+        torch.cuda.set_device(self.dev)
+        if self.world > 1:
+            import datetime
+            # a rank that fails must not leave the others waiting in a collective for NCCL's default 10 minutes
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=300))
+        self.K, self.W = args.steps, max(args.warmup, 3)
+        self.args = args
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(fn, steps, warm):
+    def sum_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t)
+        return float(t.item())
+
+    def timed(self, fn, steps, warm):
+        """ms per call: `warm` untimed calls, then `steps` calls between barrier + synchronize, CUDA events on the
+        launching stream, max over ranks."""
         for _ in range(warm):
             fn()
-        barrier()
+        self.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(steps):
             fn()
         b.record()
-        barrier()
-        return max_over_ranks(a.elapsed_time(b)) / steps
+        self.barrier()
+        return self.max_over_ranks(a.elapsed_time(b)) / steps
 
-    # ---- data: every rank owns one sync-1M shard (weak scaling); the source set is shared -------------
+    def timed_once(self, fn):
+        """(ms, result) of ONE call (for calls that take seconds: the caller warms the kernels up on a slice)."""
+        self.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        self.barrier()
+        return self.max_over_ranks(a.elapsed_time(b)), out
+
+
+def nll_weighted(y, mask):
+    """nll_loss(out[mask], y[mask]) (main_graph_knowledge_transfer.py:57-59) as gather * mask / count: no boolean-mask
+    compaction and none of ATen's single-block nll_loss reductions (0.5 ms each at 1 M rows)."""
+    w = mask.to(torch.float32) / mask.sum()
+    y_col = y.unsqueeze(1)
+
+    def nll(lp):
+        return -(lp.gather(1, y_col).squeeze(1) * w).sum()
+    return nll
+
+
+def gat_bytes(e_mp, n, c, bwd):
+    """Algorithmic bytes of one launch of the fused AdaptedConv aggregation."""
+    fwd_b = e_mp * (4 + 4 * c) + n * (4 + 4 * c + 4 * c + 1 + 8)
+    rec = 16 if c <= 64 else 8 + 4 * ((c + 31) // 32)
+    # pass A: col + H[src] gather + record write; pass B: t_col + slot map + record + gout[dst] gather; 7 row-sized node passes
+    bwd_b = e_mp * (4 + 4 * c + rec) + e_mp * (8 + rec + 4 * c) + n * 7 * 4 * c
+    return bwd_b if bwd else fwd_b
+
+
+def measure_spmm(cx, graph, n, peaks):
+    """K2: CSR SpMM mean, forward and backward (= the same kernel on the transposed CSR), on the bench graph
+    at F = 64 / 128 / 256.  Two byte models: the per-edge one, E (4 + 4F) + N (4 + 4F) -- the contract for graphs whose X
+    does not fit L2 -- and the compulsory one, 8 N F + 4 E, reached only if every row of X were fetched once."""
+    from bridged_gnn_b200 import ops
+    out = {}
+    e = graph.e
+    _ = graph.t
+    for f in (64, 128, 256):
+        x = torch.randn(n, f, device=cx.dev, requires_grad=True)
+        gy = torch.randn(n, f, device=cx.dev)
+        fwd = cx.timed(lambda: ops.spmm(graph, x.detach(), "mean"), 5, 3)
+        y = ops.spmm(graph, x, "mean")
+
+        def bwd_only():
+            x.grad = None
+            y.backward(gy, retain_graph=True)
+        bwd = cx.timed(bwd_only, 5, 3)
+        per_edge = e * (4 + 4 * f) + n * (4 + 4 * f)
+        comp = 8 * n * f + 4 * e
+        out["F=%d" % f] = {"fwd_ms": fwd, "bwd_ms": bwd, "gedges_per_s_fwd": e / fwd / 1e6,
+                           "per_edge_model": {"bytes": per_edge, "fwd_gbs": per_edge / fwd / 1e6, "fwd_frac": per_edge / fwd / 1e6 / peaks["hbm_gbs"],
+                                              "bwd_gbs": per_edge / bwd / 1e6, "bwd_frac": per_edge / bwd / 1e6 / peaks["hbm_gbs"]},
+                           "compulsory_model": {"bytes": comp, "fwd_gbs": comp / fwd / 1e6, "fwd_frac": comp / fwd / 1e6 / peaks["hbm_gbs"]}}
+        del x, gy, y
+    out["note"] = ("X of the bench graph is 268 / 537 / 1074 MB against 126 MB of L2: part of the gather is served by L2, so the "
+                   "per-edge model can exceed the DRAM peak; peak = %.0f GB/s (%s)" % (peaks["hbm_gbs"], peaks["source"]))
+    return out
+
+
+def measure_addrelu(cx):
+    """K1b: the add-ReLU head on CUDA cores: 3 Nq Ndb H lane-ops against 148 SM x 128 lanes x f_SM."""
+    from bridged_gnn_b200 import ops
+    g = torch.Generator(device=cx.dev).manual_seed(3)
+    h, k = 128, 20
+    w2 = torch.randn(h, generator=g, device=cx.dev) * 0.1
+    res = {}
+    for name, nq, ndb, steps in (("config1_cross_591x2817", 591, 2817, 20), ("sync1m_quarter_65536x786432", 65536, NS, 1)):
+        uq, udb = torch.randn(nq, h, generator=g, device=cx.dev), torch.randn(ndb, h, generator=g, device=cx.dev)
+        if steps == 1:
+            ops.knn_addrelu(uq[:4096], udb, w2, 0.1, k)                      # warm-up on a slice
+            ms = cx.timed(lambda: ops.knn_addrelu(uq, udb, w2, 0.1, k), 1, 0)
+        else:
+            ms = cx.timed(lambda: ops.knn_addrelu(uq, udb, w2, 0.1, k), steps, 3)
+        lane_ops = 3.0 * nq * ndb * h
+        res[name] = {"ms": ms, "gpairs_per_s": nq * ndb / ms / 1e6, "lane_tops": lane_ops / ms / 1e9,
+                     "frac_of_37.2T_lane_ops": lane_ops / ms / 1e9 / 37.2}
+        del uq, udb
+    res["note"] = "ceiling 148 SM x 128 lanes x 1.965 GHz = 37.2 T lane-ops/s (add, max, fma per pair and hidden unit)"
+    return res
+
+
+def measure_small_configs(cx):
+    """Wall time of BASELINE configs[0..2] (launch-latency bound; parity is in tests/): office A->D build through the
+    reference entry points, one office KT-GNN epoch eager and as CUDA graphs, fb-shaped build + steps."""
+    import numpy as np
+    from bridged_gnn_b200 import ops
+    from bridged_gnn_b200.data import Data, to_undirected
+    from bridged_gnn_b200.main_bridged_graph import add_topk_sim_cross_domain_edges, add_topk_sim_within_domain_edges
+    from bridged_gnn_b200.main_graph_knowledge_transfer import GraphedEpoch, get_each_clf_res, test, train
+    from bridged_gnn_b200.models import Adversarial_Learner_v2, GraphSAGE, KTGNN_no_complement
+    dev, out = cx.dev, {}
+    path = os.path.join(ROOT, "tests", "golden", "office_a2d_build.npz")
+    if os.path.exists(path):
+        g = np.load(path)
+        T = torch.from_numpy
+        ns = 2817
+        x, y, cm = T(g["x"]).to(dev), T(g["y"]).to(dev), T(g["central_mask"]).to(dev)
+        src = Data(x=x[:ns].contiguous(), y=y[:ns], edge_index=torch.zeros((2, 0), dtype=torch.long, device=dev))
+        tar = Data(x=x[ns:].contiguous(), y=y[ns:], edge_index=torch.zeros((2, 0), dtype=torch.long, device=dev))
+        sim = Adversarial_Learner_v2(src, tar, dim_hidden=128, num_layer=2, source_clf=True, use_norm=True, norm_mode="None",
+                                     norm_scale=1.0, backbone="mlp", sim_mode="mlp")
+        sim.load_state_dict({k[5:]: T(g[k]) for k in g.files if k.startswith("ckpt.")}, strict=False)
+        sim = sim.to(dev).eval()
+
+        def build():
+            add_topk_sim_cross_domain_edges(src, tar, sim, k=20, verbose=False)
+            add_topk_sim_within_domain_edges(src, sim, k=3, domain="source", verbose=False)
+            add_topk_sim_within_domain_edges(tar, sim, k=3, domain="target", verbose=False)
+        out["config1_office_build"] = {"ms": cx.timed(build, 5, 3), "what": "cross k=20 (591 x 2817) + within-source k=3 (2817^2) + "
+                                       "within-target k=3 (591^2), embeddings, mlp head, coalesce and the copies to the host included",
+                                       "reference_cpu_s": "4.7-5.6 (cross) + 19.2 (within-source), SURVEY 6"}
+        ei = to_undirected(T(g["edge_index"]).to(dev), x.shape[0])
+        data = Data(x=x, edge_index=ei, y=y, central_mask=cm, train_mask=T(g["train_mask"]).to(dev), val_mask=T(g["val_mask"]).to(dev),
+                    test_mask=T(g["test_mask"]).to(dev))
+        torch.manual_seed(0)
+        model = KTGNN_no_complement(256, 31, 2, 64, root_weight=False, use_bn=True, dim_share=256).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-3)
+
+        def epoch_eager():
+            train(data, model, opt, gnn="KTGNN")
+            test(data, model, gnn="KTGNN")
+            get_each_clf_res(data, model)
+        eager = cx.timed(epoch_eager, 10, 3)
+        ge = GraphedEpoch(data, model, opt)
+
+        def epoch_graphed():
+            ge.train_step()
+            ge.evaluate()
+        graphed = cx.timed(epoch_graphed, 10, 3)
+        out["config2_office_ktgnn_epoch"] = {"eager_ms": eager, "cuda_graph_ms": graphed, "E_mp": 37522,
+                                             "what": "train step + test + get_each_clf_res (main_graph_knowledge_transfer.py:219-227), "
+                                                     "device-side F1 included; the reference's AdaptedConv forward alone takes ~110 ms on 8 CPU cores"}
+    # config 3: fb_hamilton2caltech shapes (data not shipped: seeded stand-ins), cosine head d = 128, k = 50
+    g3 = torch.Generator(device=dev).manual_seed(0)
+    ns, nt, din = 2314, 769, 1685
+    u_s, u_t = torch.randn(ns, 128, generator=g3, device=dev), torch.randn(nt, 128, generator=g3, device=dev)
+    out["config3_fb_build_kernel"] = {"ms": cx.timed(lambda: ops.knn_cosine(u_t, u_s, 50), 20, 3), "what": "769 x 2314, d=128, k=50 (CUDA-core sweep: too small for tcgen05)"}
+    n = ns + nt
+    xf = torch.zeros(n, din, device=dev)
+    xf.scatter_(1, torch.randint(0, din, (n, 6), generator=g3, device=dev), 1.0)
+    ei = to_undirected(torch.randint(0, n, (2, 113000), generator=g3, device=dev), n)
+    y3 = torch.randint(0, 2, (n,), generator=g3, device=dev)
+    cm3 = torch.arange(n, device=dev) < ns
+    d3 = Data(x=xf, edge_index=ei, y=y3, central_mask=cm3, train_mask=torch.ones(n, dtype=torch.bool, device=dev))
+    torch.manual_seed(0)
+    kt = KTGNN_no_complement(din, 2, 2, 64, root_weight=False, use_bn=True, dim_share=din).to(dev)
+    sg = GraphSAGE(type("D", (), {"num_features": din, "num_classes": 2})(), layer_num=2, hidden=64).to(dev)
+    o1, o2 = torch.optim.Adam(kt.parameters(), lr=1e-3), torch.optim.Adam(sg.parameters(), lr=1e-3)
+    out["config3_fb_train_step"] = {"ktgnn_ms": cx.timed(lambda: train(d3, kt, o1, gnn="KTGNN"), 10, 3),
+                                    "graphsage_no_dtc_ms": cx.timed(lambda: train(d3, sg, o2, gnn="GraphSAGE"), 10, 3),
+                                    "what": "N=3083, F=1685 one-hot-like, E=%d undirected; optimiser step included" % ei.shape[1]}
+    return out
+
+
+def build_bridged_graph(idx, y, ns, n, dev, seed):
+    """Bridged graph of the synthetic configs: 5N random 70 %-homophily edges U kNN (source, target) edges, undirected."""
+    from bridged_gnn_b200 import dist as bdist
+    from bridged_gnn_b200.data import to_undirected
+    rnd = make_random_edges(y, RAND_EDGES_PER_NODE, HOMOPHILY, dev, seed=seed)
+    cross = bdist.edges_from_topk(idx) + torch.tensor([[0], [ns]], device=dev)
+    return to_undirected(torch.cat((rnd, cross), 1), n)
+
+
+def partitioned_step_fn(cx, model, x_full_fn, ei_u, cm, y, part):
+    """(train_step, data_loc) of the destination-partitioned KT-GNN on this rank's rows."""
+    from bridged_gnn_b200.data import Data
+    from bridged_gnn_b200.models import graph_partition
+    _, _, ei_all = graph_partition(ei_u, cm)
+    ei_loc = part.local_edges(ei_all)
+    del ei_all
+    data_loc = Data(x=x_full_fn(part.r0, part.r1), edge_index=ei_loc, central_mask=part.pad_rows(cm), part=part)
+    tm_loc, y_loc = part.local_rows(cm), part.local_rows(y)          # train mask = the source nodes, as in the headline
+    w = tm_loc.to(torch.float32) / cm.sum()
+    y_col = y_loc.unsqueeze(1)
+
+    def nll(lp):
+        return -(lp.gather(1, y_col).squeeze(1) * w).sum()
+
+    def train_step():
+        model.zero_grad(set_to_none=True)
+        lb, lt, ltt, _ = model(data_loc)
+        loss = nll(lb) + nll(lt) + nll(ltt)
+        loss.backward()
+        part.sync_grads(model)
+        return loss
+    return train_step, data_loc
+
+
+def run_sync16m(cx, peaks):
+    """BASELINE configs[4]: N = 2^24 nodes (12 582 912 source + 4 194 304 target), dim 256, k_cross 32.
+    Row-sharded build (source set replicated, target rows split, lists all-gathered), then message passing on the
+    destination-partitioned bridged graph: one KT-GNN training step (F_in 256, hidden 64) and the SAGE-style mean SpMM at
+    F = 256 with the column-panel pipelined halo.  Strong scaling: the problem is fixed, N ranks share it."""
+    from bridged_gnn_b200 import dist as bdist
+    from bridged_gnn_b200 import ops
+    from bridged_gnn_b200.models import KTGNN_no_complement
+    dev, world, rank = cx.dev, cx.world, cx.rank
+    res = {"workload": "sync-16M (BASELINE configs[4]): Ns=%d Nt=%d dim=%d k_cross=%d" % (NS16, NT16, DIM16, K16), "scaling": "strong"}
+    free, total = torch.cuda.mem_get_info()
+    res["hbm_free_gb_at_start"] = round(free / 2**30, 1)
+    if free < 120 * 2**30:
+        res["skipped"] = "needs ~110 GB of free HBM per GPU"
+        return res
+    u_src, u_tar, y_src, y_tar = make_sync_embeddings(NS16, NT16, DIM16, dev, seed=0)
+    s, e = bdist.row_shard(NT16, rank, world)
+    # ---- build -------------------------------------------------------------------------------------------------
+    def build():
+        idx, val, gap, stats = ops.knn_cosine(u_tar[s:e], u_src, K16, algo="f16")
+        if world > 1:
+            idx = bdist.all_gather_rows(idx, NT16)
+            val = bdist.all_gather_rows(val, NT16)
+        return idx, val, stats
+    ops.knn_cosine(u_tar[s:s + 8192], u_src, K16, algo="f16")            # warm-up on a slice (the full build takes seconds)
+    ms, (idx, val, stats) = cx.timed_once(build)
+    flops = 2.0 * NT16 * NS16 * DIM16
+    res["knn_build"] = {"ms": ms, "tflops_all_gpus": flops / ms / 1e9, "frac_of_bf16_peak_per_gpu": flops / ms / 1e9 / world / peaks["bf16_tflops"],
+                        "gpairs_per_s": NT16 * NS16 / ms / 1e6, "rows_per_rank": e - s, "exact_fallback_rows_this_rank": int(stats[0]),
+                        "timed": "1 build after a warm-up on 8192 rows"}
+    # sampled rows of the gathered lists against the exact CUDA-core sweep on this rank (rows of OTHER ranks too)
+    rows = torch.arange(rank, NT16, NT16 // 256, device=dev)[:256]
+    i0, v0, _, _ = ops.knn_cosine(u_tar[rows], u_src, K16, algo="simt")
+    res["knn_build"]["gathered_lists_match_exact_sweep_on_256_sampled_rows"] = bool(torch.equal(idx[rows], i0) and torch.equal(val[rows], v0))
+    del val, i0, v0
+    # ---- bridged graph ---------------------------------------------------------------------------------------------
+    n = NS16 + NT16
+    y = torch.cat((y_src, y_tar))
+    ei_u = build_bridged_graph(idx, y, NS16, n, dev, seed=1)
+    del idx
+    cm = torch.arange(n, device=dev) < NS16
+    part = bdist.DstPartition(n)
+
+    def x_rows(r0, r1):      # rows [r0, r1) of cat(u_src, u_tar) without materialising the concatenation
+        parts = []
+        if r0 < NS16:
+            parts.append(u_src[r0:min(r1, NS16)])
+        if r1 > NS16:
+            parts.append(u_tar[max(r0, NS16) - NS16:r1 - NS16])
+        return torch.cat(parts, 0).contiguous() if len(parts) > 1 else parts[0].contiguous()
+    torch.manual_seed(0)
+    model = KTGNN_no_complement(DIM16, N_CLASS, 2, HIDDEN, root_weight=False, use_bn=True, dim_share=DIM16, dropout=0.0).to(dev)
+    model.train()
+    if world > 1:
+        step, data_loc = partitioned_step_fn(cx, model, x_rows, ei_u, cm, y, part)
+        e_mp = cx.sum_over_ranks(float(data_loc.edge_index.shape[1]))
+    else:
+        from bridged_gnn_b200.data import Data
+        data_loc = Data(x=x_rows(0, n), edge_index=ei_u, y=y, central_mask=cm)
+        nll = nll_weighted(y, cm)
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            lb, lt, ltt, _ = model(data_loc)
+            loss = nll(lb) + nll(lt) + nll(ltt)
+            loss.backward()
+            return loss
+        step()
+        e_mp = float(model.edge_index.shape[1])
+    del u_src, u_tar
+    torch.cuda.empty_cache()
+    ms = cx.timed(step, 3, 2)
+    res["ktgnn_step"] = {"ms": ms, "gedges_per_s": e_mp * 8 / ms / 1e6, "E_mp": int(e_mp), "loss": cx.sum_over_ranks(float(step())),
+                         "what": "KT-GNN (F_in 256, hidden 64, 2 classes) train fwd+bwd%s" % (
+                             ", destination-partitioned: domain-aware halo exchange, rank-combined BatchNorm, one flat gradient all-reduce" if world > 1 else "")}
+    # ---- SpMM F = 256 (SAGE / GCN aggregation of configs[4]) ---------------------------------------------------------
+    if world > 1:
+        graph = part.graph(data_loc.edge_index)
+        x_loc = data_loc.x
+        t_pipe = cx.timed(lambda: bdist.partitioned_spmm(graph, x_loc, part, "mean", panels=4), 3, 2)
+        t_mono = cx.timed(lambda: bdist.partitioned_spmm(graph, x_loc, part, "mean", panels=1), 3, 2)
+        full = torch.empty((part.n_pad, DIM16), device=dev)
+        t_kernel = cx.timed(lambda: ops._spmm_raw(graph.rowptr, graph.col, full, graph.n_rows, True), 3, 2)
+        del full
+        res["spmm_f256"] = {"ms_panel_pipelined": t_pipe, "ms_single_all_gather": t_mono, "ms_local_kernel_only": t_kernel,
+                            "gedges_per_s": e_mp / t_pipe / 1e6, "halo_bytes_received_per_rank": (part.n_pad - part.n_loc) * DIM16 * 4,
+                            "what": "mean aggregation of X [N, 256] over the partitioned graph: NCCL all-gather of X in 4 column panels, "
+                                    "the gather kernel of panel p overlapping the transfer of panels p+1.."}
+    else:
+        graph = ops.cached_graph(model.edge_index, n)
+        x_all = data_loc.x
+        t = cx.timed(lambda: ops.spmm(graph, x_all, "mean"), 3, 2)
+        b = e_mp * (4 + 4 * DIM16) + n * (4 + 4 * DIM16)
+        res["spmm_f256"] = {"ms": t, "gedges_per_s": e_mp / t / 1e6, "per_edge_model_gbs": b / t / 1e6, "frac_of_hbm_peak": b / t / 1e6 / peaks["hbm_gbs"]}
+    return res
+
+
+def run_ours(args):
+    from bridged_gnn_b200 import _lib, ops
+    from bridged_gnn_b200 import dist as bdist
+    from bridged_gnn_b200.data import Data
+    from bridged_gnn_b200.models import KTGNN_no_complement
+
+    cx = Ctx(args)
+    dist, dev, rank, world = cx.dist, cx.dev, cx.rank, cx.world
+    _lib.load()
+    peaks = load_peaks()
+    K, W = cx.K, cx.W
+    timed = cx.timed
+
+    # ---- data: every rank owns one sync-1M replica (weak scaling); the source set is shared -------------
     u_src, u_tar, y_src, y_tar = make_sync_embeddings(NS, NT, DIM, dev, seed=0, tar_seed=100 + rank)
     u_src_h, u_tar_h = u_src.cpu().pin_memory(), u_tar.cpu().pin_memory()
 
     # ---- phase A: bridged-graph build ------------------------------------------------------------------
     def build(us, ut):
         idx, val, gap, stats = ops.knn_cosine(ut, us, K_CROSS, normalize=True, apply_sigmoid=True, algo=args.knn_algo)
-        if world > 1:   # per-shard kNN lists -> every rank (one NCCL all-gather each, over NVLink)
+        if world > 1:   # per-replica kNN lists -> every rank (one NCCL all-gather each, over NVLink)
             bdist.all_gather_rows(idx, NT * world)
             bdist.all_gather_rows(val, NT * world)
-        edges = bdist.edges_from_topk(idx)       # this rank's shard of the edge list (local target ids)
+        edges = bdist.edges_from_topk(idx)       # this rank's edge list (local target ids)
         return idx, val, gap, stats, edges
 
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(cx.local)
     clocks.start()
     launches0 = _lib.launches
     _lib.start_timing()
@@ -332,27 +667,37 @@ def run_ours(args):
                                                   if half_rate else " dense bf16 == fp16 rate of tcgen05 kind::f16"),
                 "algorithmic_flops_per_launch": flops}
 
+    # ---- N > 1: ONE sync-1M build, target rows sharded over the ranks, lists all-gathered and VERIFIED ----
+    sharded = None
+    idx_global = None
+    if world > 1:
+        u_tar0 = u_tar if rank == 0 else make_sync_embeddings(NS, NT, DIM, dev, seed=0, tar_seed=100)[1]
+        y_tar0 = y_tar if rank == 0 else make_sync_embeddings(NS, NT, DIM, dev, seed=0, tar_seed=100)[3]
+        local_fn = lambda q, db, k: ops.knn_cosine(q, db, k, algo=args.knn_algo)[:3]        # noqa: E731
+        sh_ms = timed(lambda: bdist.sharded_topk(u_tar0, u_src, K_CROSS, local_fn), K, W)
+        idx_global, val_global, _ = bdist.sharded_topk(u_tar0, u_src, K_CROSS, local_fn)
+        ok = torch.tensor([1.0], device=dev)
+        if rank == 0:      # rank 0's own replica IS this problem: the 1-GPU lists are at hand
+            ok[0] = float(torch.equal(idx_global, idx) and torch.equal(val_global, val))
+        dist.broadcast(ok, 0)
+        sharded = {"ms": sh_ms, "speedup_vs_1gpu_build": knn_ms / sh_ms, "rows_per_rank": NT // world,
+                   "gathered_lists_bit_identical_to_1gpu": bool(ok.item()),
+                   "what": "262 144 target rows split over %d ranks, source set replicated, idx + val all-gathered" % world}
+        del val_global
+
     # ---- phase B: message passing over the bridged graph ------------------------------------------------
     n = NS + NT
     y = torch.cat((y_src, y_tar), 0)
-    rnd = make_random_edges(y, RAND_EDGES_PER_NODE, HOMOPHILY, dev, seed=1 + rank)
-    cross = cross_edges + torch.tensor([[0], [NS]], device=dev)
-    ei = to_undirected(torch.cat((rnd, cross), 1), n)
+    ei = build_bridged_graph(idx, y, NS, n, dev, seed=1 + rank)
     cm = torch.zeros(n, dtype=torch.bool, device=dev)
     cm[:NS] = True
     data = Data(x=torch.cat((u_src, u_tar), 0).contiguous(), edge_index=ei, y=y, central_mask=cm)
-    del rnd, cross, cross_edges, idx, val
+    del cross_edges, idx, val
     torch.manual_seed(0)
     model = KTGNN_no_complement(DIM, N_CLASS, 2, HIDDEN, root_weight=False, use_bn=True, dim_share=DIM,
                                 need_complement=False, dropout=0.0).to(dev)
     model.train()
-    # == nll_loss(out[train_mask], y[train_mask]) (main_graph_knowledge_transfer.py:57-59) as gather * mask / count:
-    # no boolean-mask compaction, and none of ATen's single-block nll_loss reductions (0.5 ms each at 1 M rows)
-    w_train = cm.to(torch.float32) / cm.sum()
-    y_col = y.unsqueeze(1)
-
-    def nll(lp, _unused=None):
-        return -(lp.gather(1, y_col).squeeze(1) * w_train).sum()
+    nll = nll_weighted(y, cm)
 
     def train_step():
         model.zero_grad(set_to_none=True)
@@ -365,7 +710,7 @@ def run_ours(args):
         with torch.no_grad():
             return model(data)
 
-    train_step()                       # builds + caches partition / CSR / transposed CSR
+    loss0 = float(train_step())        # builds + caches partition / CSR / transposed CSR
     e_mp = int(model.edge_index.shape[1])
     deg = torch.bincount(model.edge_index[1], minlength=n)
     deg_stats = {"mean": float(deg.float().mean()), "p99": int(torch.quantile(deg[::64].float(), 0.99)), "max": int(deg.max())}
@@ -376,26 +721,23 @@ def run_ours(args):
     mp_launches = (_lib.launches - launches0) * K // (K + W)
     fwd_ms = timed(fwd_step, K, W)
     clk = clocks.stop()
-    total_edges = e_mp * world
-    if world > 1:
-        t = torch.tensor([e_mp], device=dev, dtype=torch.float64)
-        dist.all_reduce(t)
-        total_edges = float(t.item())
+    total_edges = cx.sum_over_ranks(float(e_mp))
     value = total_edges * 8 / (step_ms * 1e-3) / 1e9
 
-    # e2e: host buffers in, log-probs out, through the public model API (fresh tensors -> CSR rebuilt too)
-    x_h, ei_h, cm_h = data.x.cpu().pin_memory(), ei.cpu().pin_memory(), cm.cpu().pin_memory()
-    h2d = x_h.numel() * 4 + ei_h.numel() * 8 + cm_h.numel()
-    d2h = 3 * n * N_CLASS * 4
+    # e2e: host buffers in, log-probs out, through the public model API (fresh tensors -> CSR rebuilt too).  The edge
+    # list crosses PCIe as int32 (node ids < 2^31; widened to the int64 the PyG-style API takes on the device).
+    x_h, ei_h, cm_h = data.x.cpu().pin_memory(), ei.to(torch.int32).cpu().pin_memory(), cm.cpu().pin_memory()
+    h2d = x_h.numel() * 4 + ei_h.numel() * 4 + cm_h.numel()
+    d2h = 3 * n * N_CLASS * 4 + 4
 
     copy_stream = torch.cuda.Stream(device=dev)
     out_h = [torch.empty((n, N_CLASS), dtype=torch.float32).pin_memory() for _ in range(3)]
     loss_h = torch.empty((), dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        # the graph goes first; the features (61 % of the bytes) follow on a second stream while the graph is
+        # the graph goes first; the features (75 % of the bytes) follow on a second stream while the graph is
         # partitioned and its CSR / transposed CSR / row orders are built (model.prepare_graph needs no features)
-        d = Data(x=None, edge_index=ei_h.to(dev, non_blocking=True), central_mask=cm_h.to(dev, non_blocking=True))
+        d = Data(x=None, edge_index=ei_h.to(dev, non_blocking=True).to(torch.int64), central_mask=cm_h.to(dev, non_blocking=True))
         copy_stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(copy_stream):
             d.x = x_h.to(dev, non_blocking=True)
@@ -415,14 +757,10 @@ def run_ours(args):
         return out_h, float(loss_h)
     e2e_ms = timed(e2e_step, max(3, K // 2), 6)   # fresh tensors every step: the caching allocator keeps growing for ~5 steps
     e2e_value = total_edges * 8 / (e2e_ms * 1e-3) / 1e9
+    model.edge_index = None
+    train_step()                       # back on the resident graph
 
     # roofline of the dominant message-passing kernel (largest share of the step among our kernels)
-    def gat_bytes(c, bwd):
-        fwd_b = e_mp * (4 + 4 * c) + n * (4 + 4 * c + 4 * c + 1 + 8)
-        rec = 16 if c <= 64 else 8 + 4 * ((c + 31) // 32)
-        # pass A: col + H[src] gather + record write; pass B: t_col + slot map + record + gout[dst] gather; 7 row-sized node passes
-        bwd_b = e_mp * (4 + 4 * c + rec) + e_mp * (8 + rec + 4 * c) + n * 7 * 4 * c
-        return bwd_b if bwd else fwd_b
     shares = {k: v[1] / (K + W) for k, v in mp_calls.items()}       # ms per step (events span warm-up + timed steps)
     top = max(shares, key=shares.get) if shares else None
     roof = None
@@ -430,12 +768,71 @@ def run_ours(args):
         c = int(top.split("c=")[1].rstrip("]")) if "c=" in top else HIDDEN
         calls_per_step = mp_calls[top][0] / (K + W)
         dur_ms = shares[top] / max(calls_per_step, 1e-9)
-        b = gat_bytes(c, "bwd" in top)
+        b = gat_bytes(e_mp, n, c, "bwd" in top)
         roof = {"bound": "hbm", "achieved": b / (dur_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": b / (dur_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get(top, {}).get("bytes"),
                 "traffic_source": traffic.get(top, {}).get("source"), "kernel": top,
                 "avg_launch_ms": dur_ms, "share_of_step": shares[top] / step_ms, "algorithmic_bytes_per_launch": b,
                 "peak_source": peaks["source"], "kernel_ms_per_step": {k: round(v, 4) for k, v in shares.items()}}
+
+    extras = {}
+    if world == 1 and not args.no_extras:
+        for name, fn in (("spmm", lambda: measure_spmm(cx, ops.cached_graph(model.edge_index, n), n, peaks)),
+                         ("addrelu", lambda: measure_addrelu(cx))):
+            try:
+                extras[name] = fn()
+            except Exception as ex:      # an auxiliary measurement must not cost the headline line
+                extras[name] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
+            torch.cuda.empty_cache()
+
+    # ---- N > 1: ONE sync-1M KT-GNN step, destination rows partitioned over the ranks ----------------------
+    partitioned = None
+    if world > 1:
+        try:
+            y0 = torch.cat((y_src, y_tar0), 0)
+            x0 = data.x if rank == 0 else torch.cat((u_src, u_tar0), 0)
+            ei0 = ei if rank == 0 else build_bridged_graph(idx_global, y0, NS, n, dev, seed=1)
+            part = bdist.DstPartition(n)
+            torch.manual_seed(0)
+            pmodel = KTGNN_no_complement(DIM, N_CLASS, 2, HIDDEN, root_weight=False, use_bn=True, dim_share=DIM,
+                                         need_complement=False, dropout=0.0).to(dev)
+            pmodel.train()
+            pstep, pdata = partitioned_step_fn(cx, pmodel, lambda r0, r1: x0[r0:r1].contiguous(), ei0, cm, y0, part)
+            ploss = pstep().detach().clone()
+            dist.all_reduce(ploss)
+            ref = torch.tensor([loss0], device=dev)
+            dist.broadcast(ref, 0)      # rank 0's replica is this very graph and model initialisation
+            p_ms = timed(pstep, K, W)
+            ref_step = torch.tensor([step_ms], device=dev)
+            e0 = torch.tensor([float(e_mp)], device=dev)
+            dist.broadcast(e0, 0)
+            partitioned = {"ms_per_step": p_ms, "one_gpu_ms_per_step": step_ms, "ratio_to_1gpu_step": p_ms / step_ms,
+                           "gedges_per_s": float(e0) * 8 / p_ms / 1e6, "loss_partitioned": float(ploss), "loss_1gpu": float(ref),
+                           "loss_rel_err": abs(float(ploss) - float(ref)) / max(abs(float(ref)), 1e-12),
+                           "edges_this_rank": int(pdata.edge_index.shape[1]), "halo": "domain-aware point-to-point exchange of H",
+                           "what": "the 2^20-node graph of rank 0 with destination rows split over %d ranks: strong scaling of ONE step" % world}
+            del pmodel, pdata, x0, ei0
+        except Exception as ex:
+            partitioned = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
+        torch.cuda.empty_cache()
+
+    # ---- configs[4] ------------------------------------------------------------------------------------------
+    sync16m = None
+    if not args.no_sync16m:
+        del data, model, u_src, u_tar, x_h, ei_h, u_src_h, u_tar_h, ei
+        torch.cuda.empty_cache()
+        try:
+            sync16m = run_sync16m(cx, peaks)
+        except Exception as ex:
+            sync16m = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
+            # every rank must leave the collective sequence together: a failure on one rank ends the run for all
+        torch.cuda.empty_cache()
+
+    if world == 1 and not args.no_extras:      # last: CUDA-graph capture lives here
+        try:
+            extras["configs_1_3"] = measure_small_configs(cx)
+        except Exception as ex:
+            extras["configs_1_3"] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
 
     if rank == 0:
         cpu = cpu_mp_sample() if world == 1 and not args.no_cpu_baseline else None
@@ -443,12 +840,9 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "GEdges/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": "sync-1M per GPU (BASELINE configs[3]): Ns=%d Nt=%d dim=%d k_cross=%d classes=%d hidden=%d"
-                                   % (NS, NT, DIM, K_CROSS, N_CLASS, HIDDEN),
-                       "E_mp": e_mp, "in_degree": deg_stats, "conv_passes_per_step": 8, "step": "KT-GNN train fwd+bwd (4 AdaptedConv fwd + 4 bwd)",
-                       "l2": "inputs exceed L2 (features %.0f MB, db %.0f MB)" % (n * DIM * 4 / 1e6, NS * DIM * 4 / 1e6),
-                       "knn_algo": args.knn_algo, "parallelism": "row-sharded x%d" % world},
+            "data": "synthetic", "config": CONFIG,
+            "run": {"E_mp": e_mp, "in_degree": deg_stats, "knn_algo": args.knn_algo, "parallelism": "replicas x%d (headline); "
+                    "row-sharded build / destination-partitioned step in sharded_build_1m, partitioned_1m, sync16m" % world},
             "fwd_only": {"ms": fwd_ms, "gedges_per_s": total_edges * 4 / (fwd_ms * 1e-3) / 1e9},
             "e2e": {"value": e2e_value, "unit": "GEdges/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
@@ -461,6 +855,13 @@ def run_ours(args):
                           "cpu_baseline": cpu_knn, "gpu_launches": knn_launches},
             "cpu_baseline": cpu, "gpu_launches": mp_launches, "clocks": clk,
         }
+        if sharded is not None:
+            line["sharded_build_1m"] = sharded
+        if partitioned is not None:
+            line["partitioned_1m"] = partitioned
+        if sync16m is not None:
+            line["sync16m"] = sync16m
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -474,6 +875,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--knn-algo", dest="knn_algo", default="f16", choices=["f16", "tc3", "tc1", "simt"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the SpMM / add-ReLU / configs 1-3 blocks (N = 1)")
+    ap.add_argument("--no-sync16m", dest="no_sync16m", action="store_true", help="skip BASELINE configs[4]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -285,6 +285,17 @@ class Ctx:
         self.K, self.W = args.steps, max(args.warmup, 3)
         self.args = args
 
+    def hp_group(self):
+        """All ranks on a communicator whose NCCL kernels run on a HIGH-PRIORITY stream: the exchanges of the partitioned
+        paths then make progress while a gather kernel fills the SMs (tools/dist_spmm_check.py: the column-panel
+        pipeline overlaps only with it)."""
+        if self.world == 1:
+            return None
+        if getattr(self, "_hp", None) is None:
+            opts = self.dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            self._hp = self.dist.new_group(pg_options=opts)
+        return self._hp
+
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
@@ -483,11 +494,15 @@ def build_bridged_graph(idx, y, ns, n, dev, seed):
     return to_undirected(torch.cat((rnd, cross), 1), n)
 
 
-def partitioned_step_fn(cx, model, x_full_fn, ei_u, cm, y, part):
-    """(train_step, data_loc) of the destination-partitioned KT-GNN on this rank's rows."""
+def partitioned_step_fn(cx, model, x_full_fn, ei_u, cm, y):
+    """(train_step, data_loc, part) of the destination-partitioned KT-GNN on this rank's rows.  The row blocks are cut
+    at equal incoming-EDGE counts (target rows carry ~1.8x the edges of source rows in these graphs)."""
+    from bridged_gnn_b200 import dist as bdist
     from bridged_gnn_b200.data import Data
     from bridged_gnn_b200.models import graph_partition
     _, _, ei_all = graph_partition(ei_u, cm)
+    n = cm.shape[0]
+    part = bdist.DstPartition(n, cx.hp_group(), bounds=bdist.DstPartition.balanced_bounds(ei_all[1], n, cx.world))
     ei_loc = part.local_edges(ei_all)
     del ei_all
     data_loc = Data(x=x_full_fn(part.r0, part.r1), edge_index=ei_loc, central_mask=part.pad_rows(cm), part=part)
@@ -505,7 +520,7 @@ def partitioned_step_fn(cx, model, x_full_fn, ei_u, cm, y, part):
         loss.backward()
         part.sync_grads(model)
         return loss
-    return train_step, data_loc
+    return train_step, data_loc, part
 
 
 def run_sync16m(cx, peaks):
@@ -549,7 +564,6 @@ def run_sync16m(cx, peaks):
     ei_u = build_bridged_graph(idx, y, NS16, n, dev, seed=1)
     del idx
     cm = torch.arange(n, device=dev) < NS16
-    part = bdist.DstPartition(n)
 
     def x_rows(r0, r1):      # rows [r0, r1) of cat(u_src, u_tar) without materialising the concatenation
         parts = []
@@ -562,8 +576,9 @@ def run_sync16m(cx, peaks):
     model = KTGNN_no_complement(DIM16, N_CLASS, 2, HIDDEN, root_weight=False, use_bn=True, dim_share=DIM16, dropout=0.0).to(dev)
     model.train()
     if world > 1:
-        step, data_loc = partitioned_step_fn(cx, model, x_rows, ei_u, cm, y, part)
+        step, data_loc, part = partitioned_step_fn(cx, model, x_rows, ei_u, cm, y)
         e_mp = cx.sum_over_ranks(float(data_loc.edge_index.shape[1]))
+        res["row_blocks"] = {"bounds": part.bounds, "edges_this_rank": int(data_loc.edge_index.shape[1]), "needs_Hs_Ht_per_rank": part.needs(data_loc.central_mask)}
     else:
         from bridged_gnn_b200.data import Data
         data_loc = Data(x=x_rows(0, n), edge_index=ei_u, y=y, central_mask=cm)
@@ -585,8 +600,15 @@ def run_sync16m(cx, peaks):
                              ", destination-partitioned: domain-aware halo exchange, rank-combined BatchNorm, one flat gradient all-reduce" if world > 1 else "")}
     # ---- SpMM F = 256 (SAGE / GCN aggregation of configs[4]) ---------------------------------------------------------
     if world > 1:
-        graph = part.graph(data_loc.edge_index)
-        x_loc = data_loc.x
+        # equal row blocks here: the panels are all-gathered
+        from bridged_gnn_b200.models import graph_partition
+        upart = bdist.DstPartition(n, cx.hp_group())
+        del data_loc, model, step
+        torch.cuda.empty_cache()
+        ei_loc = upart.local_edges(graph_partition(ei_u, cm)[2])
+        part = upart
+        graph = part.graph(ei_loc)
+        x_loc = torch.randn(part.n_loc, DIM16, device=dev)        # (the features themselves were freed with the embeddings)
         t_pipe = cx.timed(lambda: bdist.partitioned_spmm(graph, x_loc, part, "mean", panels=4), 3, 2)
         t_mono = cx.timed(lambda: bdist.partitioned_spmm(graph, x_loc, part, "mean", panels=1), 3, 2)
         full = torch.empty((part.n_pad, DIM16), device=dev)
@@ -759,6 +781,17 @@ def run_ours(args):
     e2e_value = total_edges * 8 / (e2e_ms * 1e-3) / 1e9
     model.edge_index = None
     train_step()                       # back on the resident graph
+    # the same step replayed as one CUDA graph (bridged_gnn_b200.graphs.GraphedStep): reported beside the eager headline
+    graphed = None
+    try:
+        from bridged_gnn_b200.graphs import GraphedStep
+        gstep = GraphedStep(train_step)
+        g_ms = timed(gstep, K, W)
+        graphed = {"ms_per_step": g_ms, "gedges_per_s": total_edges * 8 / (g_ms * 1e-3) / 1e9, "loss": float(gstep()), "eager_loss": loss0}
+        del gstep
+    except Exception as ex:
+        graphed = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+    torch.cuda.empty_cache()
 
     # roofline of the dominant message-passing kernel (largest share of the step among our kernels)
     shares = {k: v[1] / (K + W) for k, v in mp_calls.items()}       # ms per step (events span warm-up + timed steps)
@@ -792,24 +825,55 @@ def run_ours(args):
             y0 = torch.cat((y_src, y_tar0), 0)
             x0 = data.x if rank == 0 else torch.cat((u_src, u_tar0), 0)
             ei0 = ei if rank == 0 else build_bridged_graph(idx_global, y0, NS, n, dev, seed=1)
-            part = bdist.DstPartition(n)
             torch.manual_seed(0)
             pmodel = KTGNN_no_complement(DIM, N_CLASS, 2, HIDDEN, root_weight=False, use_bn=True, dim_share=DIM,
                                          need_complement=False, dropout=0.0).to(dev)
             pmodel.train()
-            pstep, pdata = partitioned_step_fn(cx, pmodel, lambda r0, r1: x0[r0:r1].contiguous(), ei0, cm, y0, part)
+            pstep, pdata, part = partitioned_step_fn(cx, pmodel, lambda r0, r1: x0[r0:r1].contiguous(), ei0, cm, y0)
             ploss = pstep().detach().clone()
             dist.all_reduce(ploss)
             ref = torch.tensor([loss0], device=dev)
             dist.broadcast(ref, 0)      # rank 0's replica is this very graph and model initialisation
             p_ms = timed(pstep, K, W)
+            # the same step replayed as ONE CUDA graph (NCCL exchanges included): removes the host's issue time, which
+            # does not shrink with the number of ranks
+            graphed_ms, graph_err = None, None
+            try:
+                from bridged_gnn_b200.graphs import GraphedStep
+                gstep = GraphedStep(pstep)
+                gl = gstep().detach().clone()
+                dist.all_reduce(gl)
+                graphed_ms = timed(gstep, K, W)
+                graph_loss = float(gl)
+            except Exception as ex:
+                import traceback
+                graph_err = "%s: %s || %s" % (type(ex).__name__, str(ex)[:200], " | ".join(
+                    ln.strip() for ln in traceback.format_exc().splitlines() if "File" in ln)[-900:])
+            # where the step goes: our kernels (CUDA events around every C-ABI call), the host's issue time (a step
+            # enqueued without synchronising), the rest = NCCL exchanges + torch glue
+            _lib.start_timing()
+            for _ in range(3):
+                pstep()
+            pk = _lib.stop_timing()
+            kernel_ms = sum(v[1] for v in pk.values()) / 3
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                pstep()
+            host_ms = (time.perf_counter() - t0) / 3 * 1e3
+            torch.cuda.synchronize()
             ref_step = torch.tensor([step_ms], device=dev)
             e0 = torch.tensor([float(e_mp)], device=dev)
             dist.broadcast(e0, 0)
             partitioned = {"ms_per_step": p_ms, "one_gpu_ms_per_step": step_ms, "ratio_to_1gpu_step": p_ms / step_ms,
+                           "cuda_graph_ms_per_step": graphed_ms, "cuda_graph_ratio_to_1gpu_step": (graphed_ms / step_ms) if graphed_ms else None,
+                           "cuda_graph_loss": graph_loss if graphed_ms else None, "cuda_graph_error": graph_err,
                            "gedges_per_s": float(e0) * 8 / p_ms / 1e6, "loss_partitioned": float(ploss), "loss_1gpu": float(ref),
                            "loss_rel_err": abs(float(ploss) - float(ref)) / max(abs(float(ref)), 1e-12),
-                           "edges_this_rank": int(pdata.edge_index.shape[1]), "halo": "domain-aware point-to-point exchange of H",
+                           "edges_this_rank": int(pdata.edge_index.shape[1]), "row_bounds": part.bounds,
+                           "halo": "domain-aware point-to-point exchange of H; row blocks cut at equal edge counts",
+                           "rank0_kernel_ms_per_step": kernel_ms, "rank0_host_issue_ms_per_step": host_ms,
+                           "rank0_kernels": {k: round(v[1] / 3, 3) for k, v in pk.items()},
                            "what": "the 2^20-node graph of rank 0 with destination rows split over %d ranks: strong scaling of ONE step" % world}
             del pmodel, pdata, x0, ei0
         except Exception as ex:
@@ -844,6 +908,7 @@ def run_ours(args):
             "run": {"E_mp": e_mp, "in_degree": deg_stats, "knn_algo": args.knn_algo, "parallelism": "replicas x%d (headline); "
                     "row-sharded build / destination-partitioned step in sharded_build_1m, partitioned_1m, sync16m" % world},
             "fwd_only": {"ms": fwd_ms, "gedges_per_s": total_edges * 4 / (fwd_ms * 1e-3) / 1e9},
+            "step_cuda_graph": graphed,
             "e2e": {"value": e2e_value, "unit": "GEdges/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "roofline": roof,
@@ -862,9 +927,15 @@ def run_ours(args):
         if sync16m is not None:
             line["sync16m"] = sync16m
         line.update(extras)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL work captured in CUDA graphs makes ProcessGroupNCCL's teardown wait for minutes (measured: the process
+        # sat in destroy_process_group until the launcher's timeout): leave together, without the teardown
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -136,22 +136,24 @@ class _HaloExchange(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h_s, h_t, part, needs):
-        rank, world, n_loc = part.rank, part.world, part.n_loc
+        rank, world = part.rank, part.world
         ctx.part, ctx.needs, ctx.shape = part, needs, tuple(h_s.shape[1:])
         h = (h_s.contiguous(), h_t.contiguous())
         outs, p2p = [], []
         for d in (0, 1):
             if needs[rank][d]:
                 H = h[d].new_empty((part.n_pad,) + ctx.shape)
-                H[rank * n_loc:(rank + 1) * n_loc] = h[d]
+                b0, b1 = part.block(rank)
+                H[b0:b1] = h[d]
                 for j in range(world):
-                    if j != rank:
-                        p2p.append(dist.P2POp(dist.irecv, H[j * n_loc:(j + 1) * n_loc], part.global_rank(j), group=part.group))
+                    if j != rank and part.block_rows(j):
+                        j0, j1 = part.block(j)
+                        p2p.append(dist.P2POp(dist.irecv, H[j0:j1], part.global_rank(j), group=part.group))
                 outs.append(H)
             else:
                 outs.append(None)
             for j in range(world):
-                if j != rank and needs[j][d]:
+                if j != rank and needs[j][d] and part.block_rows(rank):
                     p2p.append(dist.P2POp(dist.isend, h[d], part.global_rank(j), group=part.group))
         _exchange(p2p)
         return tuple(outs)
@@ -159,7 +161,9 @@ class _HaloExchange(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_s, g_t):
         part, needs = ctx.part, ctx.needs
-        rank, world, n_loc = part.rank, part.world, part.n_loc
+        rank, world = part.rank, part.world
+        my0, my1 = part.block(rank)
+        n_mine = my1 - my0
         ref = g_s if g_s is not None else g_t
         g, p2p, stage = [], [], [None, None]
         for d, gd in enumerate((g_s, g_t)):
@@ -167,27 +171,28 @@ class _HaloExchange(torch.autograd.Function):
                 # an operand this rank received but whose gradient autograd did not produce counts as zero
                 gd = ref.new_zeros((part.n_pad,) + ctx.shape) if gd is None else gd.contiguous()
                 for i in range(world):
-                    if i != rank:
-                        p2p.append(dist.P2POp(dist.isend, gd[i * n_loc:(i + 1) * n_loc], part.global_rank(i), group=part.group))
+                    if i != rank and part.block_rows(i):
+                        i0, i1 = part.block(i)
+                        p2p.append(dist.P2POp(dist.isend, gd[i0:i1], part.global_rank(i), group=part.group))
             else:
                 gd = None
             g.append(gd)
             senders = [j for j in range(world) if j != rank and needs[j][d]]
-            if senders:
-                stage[d] = ref.new_empty((len(senders), n_loc) + ctx.shape)
+            if senders and n_mine:
+                stage[d] = ref.new_empty((len(senders), n_mine) + ctx.shape)
                 for k, j in enumerate(senders):
                     p2p.append(dist.P2POp(dist.irecv, stage[d][k], part.global_rank(j), group=part.group))
         _exchange(p2p)
         res = []
         for d in (0, 1):
-            acc = None if g[d] is None else g[d][rank * n_loc:(rank + 1) * n_loc]
+            acc = None if g[d] is None else g[d][my0:my1]
             if stage[d] is not None:
                 recv = stage[d].sum(0) if stage[d].shape[0] > 1 else stage[d][0]
                 acc = recv if acc is None else acc + recv
             elif acc is not None:
                 acc = acc.clone()
             if acc is None:           # no rank aggregated with this operand: zero gradient
-                acc = ref.new_zeros((n_loc,) + ctx.shape)
+                acc = ref.new_zeros((n_mine,) + ctx.shape)
             res.append(acc)
         return res[0], res[1], None, None
 
@@ -199,37 +204,79 @@ def halo_exchange(h_s, h_t, part, central_mask):
 
 
 class DstPartition:
-    """1-D partition of the node set by destination rows for message passing: rank r owns the
-    contiguous rows [r*n_loc, (r+1)*n_loc) of a node set padded to a multiple of the world size, keeps the
-    edges whose destination it owns (global source ids), and needs H of the other nodes for the gather."""
+    """1-D partition of the node set by destination rows for message passing: rank r owns a contiguous
+    block of rows, keeps the edges whose destination it owns (global source ids), and needs H of the other nodes for
+    the gather.
 
-    def __init__(self, num_nodes, group=None):
+    Default: equal blocks of ``n_loc`` rows over a node set padded to ``n_pad = world * n_loc`` (what the all-gather
+    based paths need).  With ``bounds`` (world + 1 increasing row offsets, 0 .. num_nodes; ``balanced_bounds`` cuts at
+    equal EDGE counts) the blocks differ in size, nothing is padded, and the exchanges are point-to-point."""
+
+    def __init__(self, num_nodes, group=None, bounds=None):
+        if group is None and dist.is_available() and dist.is_initialized():
+            group = dist.group.WORLD       # a concrete group: `None` means "not partitioned" to the operators
         self.group = group
         self.rank, self.world = _world(group)
         self.n = int(num_nodes)
-        self.n_loc = (self.n + self.world - 1) // self.world
-        self.n_pad = self.n_loc * self.world
-        self.r0 = self.rank * self.n_loc
-        self.r1 = min(self.n, self.r0 + self.n_loc)
+        if bounds is None:
+            self.uniform = True
+            self.n_loc = (self.n + self.world - 1) // self.world
+            self.n_pad = self.n_loc * self.world
+            self.bounds = [r * self.n_loc for r in range(self.world + 1)]
+            self.r0 = self.rank * self.n_loc
+            self.r1 = min(self.n, self.r0 + self.n_loc)
+        else:
+            bounds = [int(b) for b in bounds]
+            if len(bounds) != self.world + 1 or bounds[0] != 0 or bounds[-1] != self.n or any(b1 < b0 for b0, b1 in zip(bounds, bounds[1:])):
+                raise ValueError("bounds must be world + 1 non-decreasing offsets from 0 to num_nodes")
+            self.uniform = False
+            self.bounds = bounds
+            self.n_pad = self.n
+            self.r0, self.r1 = bounds[self.rank], bounds[self.rank + 1]
+            self.n_loc = self.r1 - self.r0
         self._needs = None
         self._loc = {}
 
+    def block(self, r):
+        """[start, end) of rank r's block in the (padded) global row space."""
+        return self.bounds[r], self.bounds[r + 1]
+
+    def block_rows(self, r):
+        return self.bounds[r + 1] - self.bounds[r]
+
+    @staticmethod
+    def balanced_bounds(dst, num_nodes, world):
+        """Row offsets that give every rank the same number of incoming EDGES (+- one row): cut points of the cumulative
+        in-degree.  ``dst``: destination ids of the edge list (device tensor).  One host read of world - 1 numbers."""
+        deg = torch.bincount(dst, minlength=num_nodes)
+        cum = torch.cumsum(deg, 0)
+        targets = (torch.arange(1, world, device=dst.device, dtype=torch.float64) * (float(dst.numel()) / world)).to(cum.dtype)
+        cuts = (torch.searchsorted(cum, targets) + 1).clamp(max=num_nodes).tolist()
+        b = [0] + cuts + [int(num_nodes)]
+        for i in range(1, len(b)):
+            b[i] = max(b[i], b[i - 1])
+        return b
+
     def global_rank(self, r):
-        return r if self.group is None else dist.get_global_rank(self.group, r)
+        return r if self.group is None or self.group is dist.group.WORLD else dist.get_global_rank(self.group, r)
 
     def needs(self, central_mask):
         """needs[r] = (rank r owns a source-domain row, rank r owns a target-domain row), for every rank: computed
         once per mask (one host read of 2 * world flags)."""
         key = (central_mask, central_mask._version)
         if self._needs is None or self._needs[0][0] is not central_mask or self._needs[0][1] != central_mask._version:
-            c = self.pad_rows(central_mask[: self.n].to(torch.int64)).view(self.world, self.n_loc)
-            valid = self.pad_rows(torch.ones(self.n, dtype=torch.int64, device=central_mask.device)).view(self.world, self.n_loc)
-            flags = torch.stack((c.sum(1) > 0, (valid - c).sum(1) > 0), 1).tolist()
-            self._needs = (key, tuple((bool(a), bool(b)) for a, b in flags))
+            cs = torch.zeros(self.n + 1, dtype=torch.int64, device=central_mask.device)
+            cs[1:] = torch.cumsum(central_mask[: self.n].to(torch.int64), 0)
+            ends = torch.tensor([min(b, self.n) for b in self.bounds], device=central_mask.device)
+            src_cnt = (cs[ends[1:]] - cs[ends[:-1]]).tolist()              # source-domain rows per rank
+            rows = (ends[1:] - ends[:-1]).tolist()
+            self._needs = (key, tuple((s_ > 0, r_ - s_ > 0) for s_, r_ in zip(src_cnt, rows)))
         return self._needs[1]
 
     def local_rows(self, t):
-        """Rows of a global per-node tensor owned by this rank, zero padded to n_loc."""
+        """Rows of a global per-node tensor owned by this rank (zero padded to n_loc in the equal-block layout)."""
+        if not self.uniform:
+            return t[self.r0:self.r1].contiguous()
         out = t.new_zeros((self.n_loc,) + tuple(t.shape[1:]))
         if self.r1 > self.r0:
             out[: self.r1 - self.r0] = t[self.r0:self.r1]
@@ -276,26 +323,81 @@ class DstPartition:
             off += k
 
 
-def partitioned_spmm(graph, x_loc, part, reduce="mean", panels=4):
+class _PeerPanels:
+    """Persistent symmetric-memory buffer [panels, n_pad, w] of one partitioned SpMM shape: every rank can write into
+    every other rank's copy over NVLink with plain device-to-device copies, which run on the COPY ENGINES -- no SM is
+    taken from the gather kernel that runs at the same time, and a pair of B200s moves 760 GB/s this way against
+    465 GB/s for NCCL's all-gather (tools/dist_bw_check.py)."""
+
+    def __init__(self, part, panels, w, device):
+        import torch.distributed._symmetric_memory as symm
+        self.buf = symm.empty((panels, part.n_pad, w), dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, part.group)
+        self.peers = [self.hdl.get_buffer(part.global_rank(j), (panels, part.n_pad, w), torch.float32) for j in range(part.world)]
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
+        self.events = [torch.cuda.Event() for _ in range(panels)]
+
+
+def _peer_panels(part, panels, w, device):
+    key = ("spmm_panels", panels, w, str(device))
+    if key not in part._loc:
+        try:
+            part._loc[key] = _PeerPanels(part, panels, w, device)
+        except Exception as ex:             # no symmetric memory on this system / backend: NCCL all-gather instead
+            part._loc[key] = ex
+    v = part._loc[key]
+    return None if isinstance(v, Exception) else v
+
+
+def partitioned_spmm(graph, x_loc, part, reduce="mean", panels=4, transport="auto"):
     """Y_loc = reduce_{j -> i} X[j] for this rank's destination rows when X is row-partitioned too (config 5: the
     SAGE / GCN aggregation of a graph too large for one GPU).  The dense halo -- every rank needs (nearly) all rows of
-    X, kNN edges have no locality -- is gathered COLUMN PANEL by column panel: all panel all-gathers are queued on the
-    NCCL stream up front and the SpMM of panel p starts as soon as panel p has landed, so the transfer of panels
-    p+1.. overlaps the gather kernel of panel p.  Forward only (inference / diagnostics)."""
+    X, kNN edges have no locality -- moves COLUMN PANEL by column panel, and the gather kernel of panel p runs while
+    panels p+1.. are still on the wire.
+
+    transport "peer" (default on NVLink systems): every rank pushes its rows of a panel straight into the other ranks'
+    symmetric-memory buffers (copy engines, no SMs), a device-side barrier per panel tells the consumers it has landed.
+    transport "nccl": one NCCL all-gather per panel, all queued up front on the communicator's stream (give the group a
+    high-priority stream, otherwise the all-gather kernels wait behind the gather kernel's CTAs).
+    Forward only (inference / diagnostics)."""
     from . import ops
+    if not part.uniform:
+        raise ValueError("partitioned_spmm works on equal row blocks: use the default (equal-block) DstPartition")
     f = x_loc.shape[1]
     panels = max(1, min(panels, f // 4 if f >= 4 else 1))
-    bounds = [(f * p // panels) // 4 * 4 for p in range(panels)] + [f]
+    while f % panels or (f // panels) % 4:
+        panels -= 1                               # equal panel widths, 16-byte aligned rows
+    w = f // panels
     y = torch.empty((graph.n_rows, f), dtype=torch.float32, device=x_loc.device)
+    pp = _peer_panels(part, panels, w, x_loc.device) if (transport in ("auto", "peer") and x_loc.is_cuda and part.world > 1) else None
+    if transport == "peer" and pp is None:
+        raise RuntimeError("symmetric memory is not available for this process group")
+    if pp is not None:
+        cur = torch.cuda.current_stream(x_loc.device)
+        srcs = [x_loc[:, p * w:(p + 1) * w].contiguous() for p in range(panels)]
+        pp.stream.wait_stream(cur)
+        with torch.cuda.stream(pp.stream):
+            pp.hdl.barrier()                      # every rank is done with the previous contents of the buffers
+            for p in range(panels):
+                for j in range(part.world):       # own copy last: the remote ones are the long ones
+                    dst = pp.peers[(part.rank + 1 + j) % part.world]
+                    dst[p, part.r0:part.r0 + part.n_loc].copy_(srcs[p], non_blocking=True)
+                pp.hdl.barrier()                  # panel p has landed everywhere
+                pp.events[p].record(pp.stream)
+        for p in range(panels):
+            cur.wait_event(pp.events[p])
+            ops._spmm_raw(graph.rowptr, graph.col, pp.buf[p], graph.n_rows, reduce == "mean", out=y[:, p * w:(p + 1) * w])
+        for t in srcs:
+            t.record_stream(pp.stream)
+        pp.stream.wait_stream(cur)                # the next call's first barrier comes after this call's last kernel
+        return y
     works, bufs = [], []
     for p in range(panels):
-        lo, hi = bounds[p], bounds[p + 1]
-        src = x_loc[:, lo:hi].contiguous()
-        buf = src.new_empty((part.n_pad, hi - lo))
+        src = x_loc[:, p * w:(p + 1) * w].contiguous()
+        buf = src.new_empty((part.n_pad, w))
         works.append(dist.all_gather_into_tensor(buf, src, group=part.group, async_op=True))
         bufs.append(buf)
     for p in range(panels):
-        lo, hi = bounds[p], bounds[p + 1]
         works[p].wait()
-        ops._spmm_raw(graph.rowptr, graph.col, bufs[p], graph.n_rows, reduce == "mean", out=y[:, lo:hi])
+        ops._spmm_raw(graph.rowptr, graph.col, bufs[p], graph.n_rows, reduce == "mean", out=y[:, p * w:(p + 1) * w])
     return y

@@ -885,12 +885,11 @@ class _BnReluDistFn(torch.autograd.Function):
         with _lib.call("bgnn_bn_relu_fwd_f32", "bgnn_bn_relu_stats_f32"):
             _lib.check(lib.bgnn_bn_relu_fwd_f32(_lib.ptr(x), n_loc, c, None, None, 0.0, 0.0, None, None, 0, None,
                                                 _lib.ptr(stats_loc), _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
-        mine = torch.empty((2 * c + 1,), dtype=f64, device=dev)
-        mine[0] = float(n_loc)
-        mine[1:c + 1] = stats_loc[:c].to(f64)
-        mine[c + 1:] = stats_loc[c:2 * c].to(f64).pow(-2)          # eps = 0 above: invstd^-2 is the biased variance
+        cnt0 = torch.full((1,), float(n_loc), dtype=f64, device=dev)
         if n_loc == 0:
-            mine[1:] = 0.0
+            mine = torch.zeros((2 * c + 1,), dtype=f64, device=dev)
+        else:                                    # eps = 0 above: invstd^-2 is the biased variance
+            mine = torch.cat((cnt0, stats_loc[:c].to(f64), stats_loc[c:2 * c].to(f64).pow(-2)))
         allr = torch.empty((world, 2 * c + 1), dtype=f64, device=dev)
         dist.all_gather_into_tensor(allr, mine.view(1, -1), group=group)
         cnt, mean_r, var_r = allr[:, :1], allr[:, 1:c + 1], allr[:, c + 1:]

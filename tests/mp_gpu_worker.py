@@ -34,7 +34,7 @@ def main():
         assert torch.equal(idx, i0) and torch.equal(val, v0) and torch.equal(gap, g0), "sharded kNN differs from 1-GPU"
 
     # ---- (b) partitioned KT-GNN -------------------------------------------------------------------------------
-    for n, ns, f_in, n_class in ((4096, 3072, 128, 2), (2048, 1024, 64, 3)):
+    for n, ns, f_in, n_class, balanced in ((4096, 3072, 128, 2, False), (2048, 1024, 64, 3, False), (4096, 3072, 128, 2, True)):
         x = torch.randn(n, f_in, generator=g, device=dev)
         y = torch.randint(0, n_class, (n,), generator=g, device=dev)
         ei = to_undirected(torch.randint(0, n, (2, 12 * n), generator=g, device=dev), n)
@@ -50,8 +50,8 @@ def main():
         cnt = int(tm.sum())
         out_r = ref(Data(x=x, edge_index=ei, central_mask=cm))
         (sum(nll(o[tm], y[tm], reduction="sum") for o in out_r[:3]) / cnt).backward()
-        part = bd.DstPartition(n)
         _, _, ei_all = graph_partition(ei, cm)
+        part = bd.DstPartition(n, bounds=bd.DstPartition.balanced_bounds(ei_all[1], n, world) if balanced else None)
         data_loc = Data(x=part.local_rows(x), edge_index=part.local_edges(ei_all), central_mask=part.pad_rows(cm), part=part)
         out = mod(data_loc)
         tm_loc, y_loc = part.local_rows(tm), part.local_rows(y)
@@ -75,13 +75,16 @@ def main():
     ei = to_undirected(torch.randint(0, n, (2, 10 * n), generator=g, device=dev), n)
     part = bd.DstPartition(n)
     full = ops.spmm(ops.CSRGraph(ei, n), X, reduce="mean")
-    y_loc = bd.partitioned_spmm(part.graph(part.local_edges(ei)), part.local_rows(X), part, reduce="mean", panels=4)
-    assert torch.equal(y_loc, full[part.r0:part.r1]), "partitioned SpMM differs from 1-GPU"
+    for transport in ("nccl", "peer", "peer"):       # (twice over peer memory: the buffers are reused across calls)
+        y_loc = bd.partitioned_spmm(part.graph(part.local_edges(ei)), part.local_rows(X), part, reduce="mean", panels=4,
+                                    transport=transport)
+        assert torch.equal(y_loc, full[part.r0:part.r1]), "partitioned SpMM (%s) differs from 1-GPU" % transport
     dist.barrier()
     torch.cuda.synchronize()
     if rank == 0:
         print("MP_GPU_OK world=%d" % world, flush=True)
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)      # (symmetric-memory handles and NCCL teardown: leave without the slow destructors)
 
 
 if __name__ == "__main__":

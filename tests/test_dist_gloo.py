@@ -67,7 +67,7 @@ def test_row_shard_partitions_exactly():
 
 
 # ------------------------------------------------------------------ destination-partitioned message passing
-def _mp_worker(rank, world, port, ret):
+def _mp_worker(rank, world, port, balanced, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, ROOT)
@@ -110,9 +110,16 @@ def _mp_worker(rank, world, port, ret):
     ei_u = T(gm["edge_index_undirected"])
     n = x.shape[0]
     sd = {k[len("ktgnn.sd."):]: T(v) for k, v in gm.items() if k.startswith("ktgnn.sd.")}
-    part = bd.DstPartition(n)
     _, _, ei_all = graph_partition(ei_u, cm)
+    # equal row blocks, or blocks cut at equal incoming-edge counts (unequal sizes, point-to-point exchanges only)
+    part = bd.DstPartition(n, bounds=bd.DstPartition.balanced_bounds(ei_all[1], n, world) if balanced else None)
     data_loc = Data(x=part.local_rows(x), edge_index=part.local_edges(ei_all), central_mask=part.pad_rows(cm), part=part)
+
+    def gather_rows(t):          # this rank's rows into place, summed over ranks (blocks may differ in size)
+        out = t.new_zeros((n,) + tuple(t.shape[1:]))
+        out[part.r0:part.r1] = t[: part.r1 - part.r0]
+        dist.all_reduce(out)
+        return out
 
     # (1) eval forward == reference logits
     model = KTGNN_no_complement(256, 31, 2, 64, root_weight=False, use_bn=True, dim_share=256)
@@ -120,7 +127,7 @@ def _mp_worker(rank, world, port, ret):
     model.eval()
     with torch.no_grad():
         lb, lt, ltt, _ = model(data_loc)
-    full = [bd.all_gather_rows(t[: part.r1 - part.r0].contiguous(), n) for t in (lb, lt, ltt)]
+    full = [gather_rows(t) for t in (lb, lt, ltt)]
 
     # (2) train-mode gradients (no BatchNorm: SyncBatchNorm is CUDA-only) == single-process gradients
     torch.manual_seed(0)
@@ -151,12 +158,13 @@ def _mp_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_two_rank_partitioned_ktgnn_matches_single_rank():
+@pytest.mark.parametrize("balanced", [False, True])
+def test_two_rank_partitioned_ktgnn_matches_single_rank(balanced):
     import numpy as np
-    port = 31500 + (os.getpid() % 2000)
+    port = 31500 + (os.getpid() % 2000) + (7 if balanced else 0)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_mp_worker, args=(2, port, ret), nprocs=2, join=True)
+    mp.spawn(_mp_worker, args=(2, port, balanced, ret), nprocs=2, join=True)
     gm = dict(np.load(os.path.join(ROOT, "tests", "golden", "office_a2d_mp.npz")))
     for r in (0, 1):
         full, gerr, ltot, lref = ret[r]

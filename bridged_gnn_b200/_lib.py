@@ -59,6 +59,7 @@ SIGNATURES = {
     "bgnn_adapted_skinny_bwd_workspace_bytes": (_sz, [_i32, _i32]),
     "bgnn_adapted_skinny_bwd_f32": (_i32, [_vp] * 7 + [_i64, _i32, _i32] + [_vp] * 3 + [_sz, _vp]),
     "bgnn_rowpanel_gemm_supported": (_i32, [_i32, _i32, _i32]),
+    "bgnn_rowpanel_gemm_act_f32": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _vp, _i32, _vp]),
     "bgnn_rowpanel_gemm_f32": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _vp]),
     "bgnn_adapted_transform_bwd_gates_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "bgnn_wgrad_gemm_cat_f32": (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _sz, _vp]),
@@ -144,7 +145,7 @@ KERNELS_PER_CALL = {"bgnn_knn_cosine_f32": 13, "bgnn_knn_cosine_eps_f32": 13, "b
                     "bgnn_gatv2_heads_fwd_part_f32": 1, "bgnn_gatv2_heads_bwd_part_f32": 3, "bgnn_spmm_csr_ld_f32": 1,
                     "bgnn_bn_relu_bwd_reduce_f32": 2, "bgnn_bn_relu_bwd_apply_f32": 1, "bgnn_rows_by_degree": 1,
                     "bgnn_adapted_transform_fwd_f32": 1, "bgnn_adapted_transform_bwd_f32": 2,
-                    "bgnn_gatv2_heads_fwd_f32": 1, "bgnn_gatv2_heads_bwd_f32": 3, "bgnn_adapted_skinny_fwd_f32": 1, "bgnn_adapted_skinny_bwd_f32": 2, "bgnn_domain_colsum_f32": 2, "bgnn_rowpanel_gemm_f32": 1, "bgnn_tf32_planes_f32": 1, "bgnn_adapted_skinny_heads_tc_fwd_f32": 1, "bgnn_wgrad_gemm_cat_f32": 2, "bgnn_adapted_transform_bwd_gates_f32": 2, "bgnn_adapted_skinny_heads_fwd_f32": 1, "bgnn_adapted_skinny_heads_pre_f32": 2,
+                    "bgnn_gatv2_heads_fwd_f32": 1, "bgnn_gatv2_heads_bwd_f32": 3, "bgnn_adapted_skinny_fwd_f32": 1, "bgnn_adapted_skinny_bwd_f32": 2, "bgnn_domain_colsum_f32": 2, "bgnn_rowpanel_gemm_f32": 1, "bgnn_rowpanel_gemm_act_f32": 1, "bgnn_tf32_planes_f32": 1, "bgnn_adapted_skinny_heads_tc_fwd_f32": 1, "bgnn_wgrad_gemm_cat_f32": 2, "bgnn_adapted_transform_bwd_gates_f32": 2, "bgnn_adapted_skinny_heads_fwd_f32": 1, "bgnn_adapted_skinny_heads_pre_f32": 2,
                     "bgnn_adapted_skinny_heads_bwd_f32": 2, "bgnn_bn_relu_fwd_f32": 3, "bgnn_bn_relu_apply_f32": 1, "bgnn_bn_relu_bwd_f32": 3, "bgnn_wgrad_gemm_f32": 2,
                     "bgnn_adapted_wide_fwd_f32": 1}
 launches = 0          # running count of kernels launched through the C ABI

@@ -486,13 +486,19 @@ int bgnn_domain_colsum_f32(const float* x, const uint8_t* is_src, int64_t n, int
 
 int bgnn_rowpanel_gemm_supported(int k, int ld_a, int no) { return rowpanel_gemm_supported(k, ld_a, no) ? 1 : 0; }
 
-int bgnn_rowpanel_gemm_f32(const float* A, int64_t n, int k, int ld_a, const float* b_hi, const float* b_lo,
-                           const float* bias, int no, float* Y, int ldy, void* stream) {
-  if (n < 0 || k <= 0 || no <= 0 || ld_a < k || ldy < no) return BGNN_ERR_INVALID_ARG;
+int bgnn_rowpanel_gemm_act_f32(const float* A, int64_t n, int k, int ld_a, const float* b_hi, const float* b_lo,
+                               const float* scale, const float* bias, int act, const float* res, int ld_res, int no,
+                               float* Y, int ldy, void* stream) {
+  if (n < 0 || k <= 0 || no <= 0 || ld_a < k || ldy < no || act < 0 || act > 2 || (res && ld_res < no)) return BGNN_ERR_INVALID_ARG;
   if (n > 0 && (!A || !b_hi || !b_lo || !Y)) return BGNN_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo)) & 15)
     return BGNN_ERR_INVALID_ARG;
-  return launch_rowpanel_gemm(A, n, k, ld_a, b_hi, b_lo, bias, no, Y, ldy, (cudaStream_t)stream);
+  return launch_rowpanel_gemm(A, n, k, ld_a, b_hi, b_lo, scale, bias, act, res, ld_res, no, Y, ldy, (cudaStream_t)stream);
+}
+
+int bgnn_rowpanel_gemm_f32(const float* A, int64_t n, int k, int ld_a, const float* b_hi, const float* b_lo,
+                           const float* bias, int no, float* Y, int ldy, void* stream) {
+  return bgnn_rowpanel_gemm_act_f32(A, n, k, ld_a, b_hi, b_lo, nullptr, bias, 0, nullptr, 0, no, Y, ldy, stream);
 }
 
 int bgnn_adapted_wide_supported(int c, int d) { return adapted_wide_supported(c, d) ? 1 : 0; }

@@ -130,8 +130,9 @@ int launch_domain_colsum(const float* x, const uint8_t* is_src, long long n, int
 
 // rowpanel_gemm_sm100.cu
 bool rowpanel_gemm_supported(int k, int ld_a, int no);
-int launch_rowpanel_gemm(const float* A, long long n, int k, int ld_a, const float* bhi, const float* blo, const float* bias,
-                         int no, float* Y, int ldy, cudaStream_t stream);
+int launch_rowpanel_gemm(const float* A, long long n, int k, int ld_a, const float* bhi, const float* blo, const float* scale,
+                         const float* bias, int act, const float* res, int ld_res, int no, float* Y, int ldy,
+                         cudaStream_t stream);
 int launch_tf32_planes(const float* w, int rows, int cols, long long stride_r, long long stride_c, int rows_p, int cols_p, float* hi,
                        float* lo, cudaStream_t stream);
 bool adapted_wide_supported(int c, int d);

@@ -56,6 +56,12 @@ struct RgEpi {                 // EPI 1: AdaptedConv node-wise epilogue (adapted
   float* gates;                // [n, 2]  (EPI 2: [n, heads * 2])
   int c;
   int heads;                   // EPI 2: narrow convs side by side, columns h * (2c+2) + [0, 2c+2) of the accumulator
+  // EPI 0 (plain Linear): y = act(acc * scale[col] + bias[col]) + res[row, col] -- eval-mode BatchNorm folded into
+  // (scale, bias), ReLU / Tanh and a residual applied to the accumulator tile (the embedding producers of the build)
+  const float* scale;          // [no] or null
+  const float* res;            // [n, ld_res] or null
+  int ld_res;
+  int act;                     // 0 none, 1 relu, 2 tanh
 };
 
 // Epilogue store of one 32 x 32 block: the thread <-> row registers go through a 4 KB per-warp staging tile (16-byte
@@ -252,9 +258,25 @@ rowpanel_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int c0 = 0; c0 < nop; c0 += 32) {
           tc_ld32(taddr0 + (uint32_t)c0, r);
           tc_wait_ld();
+          if (ep.scale) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) r[k] *= (c0 + k < no) ? __ldg(ep.scale + c0 + k) : 1.f;
+          }
           if (ep.bias) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) r[k] += (c0 + k < no) ? __ldg(ep.bias + c0 + k) : 0.f;
+          }
+          if (ep.act == 1) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) r[k] = fmaxf(r[k], 0.f);
+          } else if (ep.act == 2) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) r[k] = tanhf(r[k]);
+          }
+          if (ep.res && row_ok) {
+            const float* rp = ep.res + row * ep.ld_res + c0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) r[k] += (c0 + k < no) ? __ldg(rp + k) : 0.f;
           }
           rg_store_block(stg, r, lane, Y, row0, n, ldy, c0, no);
         }
@@ -383,10 +405,15 @@ static int rg_launch(const float* A, long long n, int k, int ld_a, const float* 
   return BGNN_OK;
 }
 
-int launch_rowpanel_gemm(const float* A, long long n, int k, int ld_a, const float* bhi, const float* blo, const float* bias,
-                         int no, float* Y, int ldy, cudaStream_t stream) {
+int launch_rowpanel_gemm(const float* A, long long n, int k, int ld_a, const float* bhi, const float* blo, const float* scale,
+                         const float* bias, int act, const float* res, int ld_res, int no, float* Y, int ldy,
+                         cudaStream_t stream) {
   RgEpi ep = {};
   ep.bias = bias;
+  ep.scale = scale;
+  ep.act = act;
+  ep.res = res;
+  ep.ld_res = ld_res;
   return rg_launch<0>(A, n, k, ld_a, bhi, blo, no, Y, ldy, ep, stream);
 }
 

@@ -13,7 +13,15 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
 from .backbones import SAGEConv
+
+
+def _bn_fold(bn):
+    """(scale, shift) of an eval-mode BatchNorm1d in float64: y = x * scale + shift."""
+    f64 = torch.float64
+    s = bn.weight.detach().to(f64) / torch.sqrt(bn.running_var.to(f64) + bn.eps)
+    return s, bn.bias.detach().to(f64) - bn.running_mean.to(f64) * s
 
 
 class PairNorm(nn.Module):
@@ -63,9 +71,17 @@ class MLP(nn.Module):
             self.norm = PairNorm(norm_mode, norm_scale)
 
     def forward(self, x, edge_index=None):
+        last = len(self.layers) - 1
+        plain_norm = not self.use_norm or self.norm.mode == "None"
         for ind, layer in enumerate(self.layers):
+            if not self.training and not torch.is_grad_enabled() and ops.dense_supported(x, layer.in_features, layer.out_features) \
+                    and (ind == last or plain_norm):
+                # inference on the device (the bridged-graph build): one tcgen05 row-panel GEMM per layer, bias and
+                # ReLU applied to the accumulator tile
+                x = ops.rowpanel_gemm(x, layer.weight, layer.bias, act=None if ind == last else "relu")
+                continue
             x = layer(x)
-            if ind != len(self.layers) - 1:
+            if ind != last:
                 if self.use_norm:
                     x = self.norm(x)
                 x = F.dropout(F.relu(x), p=0.5, training=self.training)
@@ -135,7 +151,19 @@ class Similar_v2(nn.Module):
         return F.log_softmax(self.lin_clf(F.dropout(F.relu(z), p=self.dropout, training=self.training)), dim=-1)
 
     def cosine_operand(self, z):
-        """Node-wise vector fed to CosineSimilarity (:125-128, :946-948)."""
+        """Node-wise vector fed to CosineSimilarity (:125-128, :946-948): u = z' + biasatt(z'), z' = lin_self(z).
+        Inference on the device: four row-panel GEMMs -- the two eval-mode BatchNorms folded into the first layer's
+        weights (float64 fold of the 64 x h matrix) and epilogue scale / shift, Tanh and the residual fused."""
+        bn1, lin1, bn2, _, lin2 = self.lin_self
+        if (not self.training and not torch.is_grad_enabled() and ops.dense_supported(z, lin1.in_features, lin1.out_features)
+                and lin1.bias is None and lin2.bias is None):
+            s1, t1 = _bn_fold(bn1)
+            s2, t2 = _bn_fold(bn2)
+            w1 = lin1.weight.detach().to(torch.float64)
+            y1 = ops.rowpanel_gemm(z, (w1 * s1).float(), bias=((w1 @ t1) * s2 + t2).float(), scale=s2.float(), act="tanh")
+            zz = ops.rowpanel_gemm(y1, lin2.weight)
+            b1 = ops.rowpanel_gemm(zz, self.biasatt[0].weight, self.biasatt[0].bias, act="tanh")
+            return ops.rowpanel_gemm(b1, self.biasatt[2].weight, self.biasatt[2].bias, res=zz)
         zz = self.lin_self(z)
         return zz + self.biasatt(zz)
 
@@ -148,15 +176,21 @@ class Similar_v2(nn.Module):
         bn1, lin1, bn2, _, lin2 = self.lin_self
         d = z_db.shape[1]
         f64 = torch.float64
-        s1 = bn1.weight.to(f64) / torch.sqrt(bn1.running_var.to(f64) + bn1.eps)
-        t1 = bn1.bias.to(f64) - bn1.running_mean.to(f64) * s1
-        s2 = bn2.weight.to(f64) / torch.sqrt(bn2.running_var.to(f64) + bn2.eps)
-        t2 = bn2.bias.to(f64) - bn2.running_mean.to(f64) * s2
-        W = lin1.weight.to(f64)
+        s1, t1 = _bn_fold(bn1)
+        s2, t2 = _bn_fold(bn2)
+        W = lin1.weight.detach().to(f64)
         Wa, Wb = W[:, :d], W[:, d:]
-        U_db = ((z_db.to(f64) * s1[:d] + t1[:d]) @ Wa.t()) * s2
-        U_q = ((z_q.to(f64) * s1[d:] + t1[d:]) @ Wb.t() + lin1.bias.to(f64)) * s2 + t2
-        return U_db.float().contiguous(), U_q.float().contiguous(), lin2.weight.view(-1).float(), float(lin2.bias.item())
+        # everything that is not an [N, d] operand is folded in float64 on the 128 x d weight blocks:
+        #   U_db = z_db (s2 (.) Wa (.) s1a)^T + s2 (.) (Wa t1a),   U_q = z_q (s2 (.) Wb (.) s1b)^T + s2 (.) (Wb t1b + b1) + t2
+        w_db, b_db = (Wa * s1[:d]) * s2[:, None], (Wa @ t1[:d]) * s2
+        w_q, b_q = (Wb * s1[d:]) * s2[:, None], (Wb @ t1[d:] + lin1.bias.detach().to(f64)) * s2 + t2
+        w2, b2 = lin2.weight.detach().view(-1).float(), float(lin2.bias.item())
+        if ops.dense_supported(z_db, d, lin1.out_features) and ops.dense_supported(z_q, d, lin1.out_features):
+            # the two [N, d] x [d, 128] products on the tensor cores (3 x TF32, fp32-grade), bias in the epilogue
+            return (ops.rowpanel_gemm(z_db, w_db.float(), b_db.float()), ops.rowpanel_gemm(z_q, w_q.float(), b_q.float()), w2, b2)
+        U_db = z_db.to(f64) @ w_db.t() + b_db
+        U_q = z_q.to(f64) @ w_q.t() + b_q
+        return U_db.float().contiguous(), U_q.float().contiguous(), w2, b2
 
 
 class Similar(Similar_v2):
@@ -193,8 +227,15 @@ class Source_Learner_v2(nn.Module):
 
 class _TargetBase(nn.Module):
     def encode(self, data):
-        """models/models.py:735-739 / 1092-1096."""
-        h0 = self.equavilent_trans_layer(data.x)
+        """models/models.py:735-739 / 1092-1096.  Inference on the device: Linear + Tanh of equavilent_trans_layer as one
+        row-panel GEMM (PairNorm mode 'None' is the identity)."""
+        lin, norm, _ = self.equavilent_trans_layer
+        x = data.x
+        if (not self.training and not torch.is_grad_enabled() and norm.mode == "None"
+                and ops.dense_supported(x, lin.in_features, lin.out_features)):
+            h0 = ops.rowpanel_gemm(x, lin.weight, lin.bias, act="tanh")
+        else:
+            h0 = self.equavilent_trans_layer(x)
         return self.encoder(h0, getattr(data, "edge_index", None)), h0
 
 

@@ -573,10 +573,15 @@ def rowpanel_gemm_supported(k, ld_a, no):
     return bool(_lib.load().bgnn_rowpanel_gemm_supported(int(k), int(ld_a), int(no)))
 
 
-def rowpanel_gemm(A, B, bias=None):
-    """A [n, k] @ B [no, k]^T (+ bias [no]) on the tcgen05 tensor cores with fp32-grade accuracy (3 x TF32; A is split on chip and
-    streamed from HBM once).  Stands in for the fp32 SIMT GEMMs of AdaptedConv's node-wise part
-    (models/KTGNN.py:277-284).  A may be a row-strided view (stride % 4 == 0).  Not differentiable."""
+_ACTS = {None: 0, "none": 0, "relu": 1, "tanh": 2}
+
+
+def rowpanel_gemm(A, B, bias=None, scale=None, act=None, res=None):
+    """act(A [n, k] @ B [no, k]^T * scale + bias) + res on the tcgen05 tensor cores with fp32-grade accuracy (3 x TF32; A is
+    split on chip and streamed from HBM once), the epilogue applied to the accumulator tile.  Stands in for the fp32 SIMT
+    GEMMs of AdaptedConv's node-wise part (models/KTGNN.py:277-284) and, with the epilogue, for the dense layers of the
+    embedding producers (models/models.py:852-893, 70-99, 1092-1096).  scale / bias [no]; act None | "relu" | "tanh";
+    res [n, no].  A may be a row-strided view (stride % 4 == 0).  Not differentiable."""
     lib = _lib.load()
     f32 = torch.float32
     A = A.detach().to(f32)
@@ -588,12 +593,23 @@ def rowpanel_gemm(A, B, bias=None):
     no = B.shape[0]
     hi, lo = tf32_planes(B)
     b_c = None if bias is None else bias.detach().to(f32).contiguous()
+    s_c = None if scale is None else scale.detach().to(f32).contiguous()
+    r_c = None if res is None else res.detach().to(f32).contiguous()
+    if r_c is not None and tuple(r_c.shape) != (n, no):
+        raise ValueError("res must be [n, no]")
     Y = torch.empty((n, no), dtype=f32, device=A.device)
     with _lib.call("bgnn_rowpanel_gemm_f32"):
         _lib.ptr(A[:1])          # device / dtype checks; A itself may be a row-strided view
-        _lib.check(lib.bgnn_rowpanel_gemm_f32(A.data_ptr(), n, k, max(A.stride(0), k + (-k) % 4), _lib.ptr(hi), _lib.ptr(lo),
-                                              _lib.ptr(b_c, f32, True), no, _lib.ptr(Y), no, _lib.stream(A.device)))
+        _lib.check(lib.bgnn_rowpanel_gemm_act_f32(A.data_ptr(), n, k, max(A.stride(0), k + (-k) % 4), _lib.ptr(hi), _lib.ptr(lo),
+                                                  _lib.ptr(s_c, f32, True), _lib.ptr(b_c, f32, True), _ACTS[act],
+                                                  _lib.ptr(r_c, f32, True), no, no, _lib.ptr(Y), no, _lib.stream(A.device)))
     return Y
+
+
+def dense_supported(x, in_features, out_features):
+    """Whether ``rowpanel_gemm`` takes a dense layer [*, in] -> [*, out] on this input (fp32 CUDA matrix, widths <= 256)."""
+    return (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and not os.environ.get("BGNN_NO_WIDE")
+            and rowpanel_gemm_supported(in_features, in_features + (-in_features) % 4, out_features))
 
 
 def _tma_rows(t):

@@ -283,6 +283,14 @@ int bgnn_domain_colsum_f32(const float* x, const uint8_t* is_src, int64_t n, int
 int bgnn_rowpanel_gemm_supported(int k, int ld_a, int no);
 int bgnn_rowpanel_gemm_f32(const float* A, int64_t n, int k, int ld_a, const float* b_hi, const float* b_lo,
                            const float* bias, int no, float* Y, int ldy, void* stream);
+/* The same with an epilogue on the accumulator tile:  Y = act(A . B^T * scale + bias) + res.  scale, bias [no] or NULL;
+ * act 0 none, 1 ReLU, 2 tanh; res [n, no] (row stride ld_res) or NULL.  One launch per dense layer of the embedding
+ * producers that feed the build -- eval-mode BatchNorm folded into (scale, bias), the activation and the residual of
+ * u = z' + biasatt(z') fused: models/models.py:852-893 (MLP), :70-99 / :124-127 (lin_self, biasatt), :1092-1096
+ * (equavilent_trans_layer + Tanh). */
+int bgnn_rowpanel_gemm_act_f32(const float* A, int64_t n, int k, int ld_a, const float* b_hi, const float* b_lo,
+                               const float* scale, const float* bias, int act, const float* res, int ld_res, int no,
+                               float* Y, int ldy, void* stream);
 /* The same contraction for a WIDE AdaptedConv (c % 32 == 0, 2c+2 <= 256, d % 4 == 0, d <= 256) with the node-wise
  * epilogue of bgnn_adapted_transform_fwd_f32 fused in: x [n,d] is read once, P is never written.
  * wcat_hi / wcat_lo: planes of [W_s; W_t; a_g_s2t[:d]; a_g_t2s[:d]] as above; bias [2c] or NULL. */

@@ -201,3 +201,52 @@ def test_edge_ids_out_of_range_raise():
         ops.coalesce(torch.tensor([[0, -1], [1, 0]], device=DEV), 4)
     g = ops.CSRGraph(torch.tensor([[0, 1, 3, 2], [1, 2, 0, 0]], device=DEV), 4)       # n = 2^nb: the parking row is unused
     assert g.rowptr.tolist() == [0, 2, 3, 4, 4] and g.col.tolist() == [2, 3, 0, 1]
+
+
+# ------------------------------------------------------------------ f3: embedding producers on the row-panel GEMM
+@pytest.mark.parametrize("n,k,no,act", [(1000, 128, 128, "relu"), (4099, 256, 128, "tanh"), (777, 64, 64, None), (300, 100, 36, "tanh")])
+def test_rowpanel_gemm_epilogue_matches_float64(n, k, no, act):
+    """act(A B^T * scale + bias) + res: the epilogue of bgnn_rowpanel_gemm_act_f32 against float64."""
+    from bridged_gnn_b200 import ops
+    g = torch.Generator().manual_seed(n + k)
+    A, B = torch.randn(n, k, generator=g), torch.randn(no, k, generator=g) * 0.2
+    scale, bias, res = torch.rand(no, generator=g) + 0.5, torch.randn(no, generator=g), torch.randn(n, no, generator=g)
+    ref = A.double() @ B.double().t() * scale.double() + bias.double()
+    ref = torch.relu(ref) if act == "relu" else (torch.tanh(ref) if act == "tanh" else ref)
+    ref = ref + res.double()
+    got = ops.rowpanel_gemm(A.to(DEV), B.to(DEV), bias.to(DEV), scale=scale.to(DEV), act=act, res=res.to(DEV)).cpu()
+    assert float((got - ref.float()).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_embedding_producers_match_reference(office_build, fb_build):
+    """The dense layers in front of the kNN sweep (MLP backbone, equavilent_trans_layer + Tanh, lin_self / biasatt with
+    eval-mode BatchNorm folded, the mlp head's node-wise operands) through the fused row-panel GEMMs: within 1e-5
+    relative of the reference's embeddings (golden z_src / z_tar) and of the same modules evaluated by torch on the CPU."""
+    from bridged_gnn_b200.models import Similar
+    g = office_build
+    src, tar = _data(g)
+    model = _office_model(g, src, tar)
+    with torch.no_grad():
+        z_src, z_tar = model.embed_source(src), model.embed_target(tar)
+    for got, key in ((z_src, "z_src"), (z_tar, "z_tar")):
+        want = T(g[key])
+        assert float((got.cpu() - want).abs().max()) <= 1e-5 * float(want.abs().max()), key
+    # mlp head operands: device fold + tensor-core GEMM vs the float64 fold on the CPU
+    head = model.source_learner.sim_net
+    with torch.no_grad():
+        U_db, U_q, w2, b2 = head.mlp_operands(z_src, z_tar)
+        head_c = type(head)(128, 31, mode="mlp")
+        head_c.load_state_dict({k: v.cpu() for k, v in head.state_dict().items()})
+        Uc_db, Uc_q, _, _ = head_c.eval().mlp_operands(T(g["z_src"]), T(g["z_tar"]))
+    for a, b in ((U_db, Uc_db), (U_q, Uc_q)):
+        assert float((a.cpu() - b).abs().max()) <= 1e-5 * float(b.abs().max())
+    # cosine head (fb checkpoint): fused chain vs the module's own layers on the CPU
+    W = sub_state(fb_build, "ckpt.")
+    head = Similar(64, 2)
+    head.load_state_dict({k[len("source_learner.sim_net."):]: v for k, v in W.items()})
+    head.eval()
+    z = T(fb_build["z_src"])
+    with torch.no_grad():
+        want = head.cosine_operand(z)
+        got = head.to(DEV).cosine_operand(z.to(DEV)).cpu()
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())

@@ -360,7 +360,14 @@ bool gatv2_heads_supported(int heads, int c) { return (heads == 2 || heads == 3)
 
 constexpr int kMhDstThreads = 128;
 constexpr int kMhDstMaxCtasPerSm = 16;
-static long long mh_dst_max_warps() { return (long long)kNumSMs * kMhDstMaxCtasPerSm * (kMhDstThreads / 32); }
+// Pass A takes one row SET (4 rows) per warp, CTAs scheduled by the hardware: with a static round-robin over resident
+// warps, the warp that drew a hub row (1800 edges = 220 serial steps of its 8 lanes) kept its other 70 sets waiting
+// behind it and set the duration of the launch (profiles/r02n_gat_ncu.txt: 1.0 ms at 18 % DRAM utilisation).
+static long long mh_dst_warps(long long n) {
+  const long long nsets = (n + (32 / MH_ES) - 1) / (32 / MH_ES);
+  const long long ctas = (nsets + (kMhDstThreads / 32) - 1) / (kMhDstThreads / 32);
+  return (ctas < 1 ? 1 : ctas) * (kMhDstThreads / 32);
+}
 
 #define MH_DISPATCH(CALL)                                                                  \
   do {                                                                                     \
@@ -388,7 +395,7 @@ int launch_gatv2_heads_fwd(const int* rowptr, const int* col, const uint8_t* dst
 
 size_t gatv2_heads_bwd_workspace_bytes(long long n, long long e, int heads, int c) {
   if (!gatv2_heads_supported(heads, c)) return 0;
-  return align_up((size_t)mh_dst_max_warps() * 2 * heads * c * sizeof(float), 256) +
+  return align_up((size_t)mh_dst_warps(n) * 2 * heads * c * sizeof(float), 256) +
          align_up((size_t)e * MH_REC_WORDS * sizeof(unsigned), 256) + 1024;
 }
 
@@ -408,7 +415,7 @@ static int mh_launch_dst(long long n, long long row_off, int& nwarps, cudaStream
   constexpr int WPC = kMhDstThreads / 32;
   const long long nsets = (n + (32 / MH_ES) - 1) / (32 / MH_ES);
   long long ctas = (nsets + WPC - 1) / WPC;
-  if (ctas > (long long)kNumSMs * occ) ctas = (long long)kNumSMs * occ;
+  (void)occ;
   nwarps = (int)(ctas * WPC);
   kern<<<(unsigned)ctas, kMhDstThreads, 0, stream>>>(rowptr, col, csr_to_csc, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n,
                                                      row_off, out, row_max, row_sum, gout, gHs, gHt, erec, part);
@@ -426,7 +433,7 @@ int launch_gatv2_heads_bwd(const int* rowptr, const int* col, const int* t_rowpt
   if (!gatv2_heads_supported(heads, c)) return BGNN_ERR_UNSUPPORTED;
   const int f = heads * c;
   Workspace w(ws, ws_bytes);
-  float* part = w.take<float>(mh_dst_max_warps() * 2 * f);
+  float* part = w.take<float>(mh_dst_warps(n_src) * 2 * f);
   unsigned* erec = w.take<unsigned>((size_t)e * MH_REC_WORDS);
   if (!w.ok()) return BGNN_ERR_WORKSPACE;
   int nparts = 0, rc = BGNN_OK;

@@ -502,7 +502,9 @@ def partitioned_step_fn(cx, model, x_full_fn, ei_u, cm, y):
     from bridged_gnn_b200.models import graph_partition
     _, _, ei_all = graph_partition(ei_u, cm)
     n = cm.shape[0]
-    part = bdist.DstPartition(n, cx.hp_group(), bounds=bdist.DstPartition.balanced_bounds(ei_all[1], n, cx.world))
+    n_src_nodes = int(cm.sum())
+    prefix = n_src_nodes if bool(cm[:n_src_nodes].all()) else None
+    part = bdist.DstPartition(n, cx.hp_group(), bounds=bdist.DstPartition.balanced_bounds(ei_all[1], n, cx.world, n_prefix=prefix))
     ei_loc = part.local_edges(ei_all)
     del ei_all
     data_loc = Data(x=x_full_fn(part.r0, part.r1), edge_index=ei_loc, central_mask=part.pad_rows(cm), part=part)

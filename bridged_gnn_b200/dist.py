@@ -245,20 +245,47 @@ class DstPartition:
         return self.bounds[r + 1] - self.bounds[r]
 
     @staticmethod
-    def balanced_bounds(dst, num_nodes, world, row_weight=12.0):
+    def balanced_bounds(dst, num_nodes, world, row_weight=12.0, n_prefix=None, pure_slack=1.12):
         """Row offsets that give every rank the same WORK (+- one row): cut points of the cumulative cost
         ``in-degree + row_weight`` per row.  The aggregation kernels cost per edge, the node-wise dense layers per row;
         measured on the sync-1M KT-GNN step one row costs about as much as 12 edges (6.6 ms of aggregation for 2.2e7
         edges, 3.7 ms of dense kernels for 1e6 rows).  ``dst``: destination ids of the edge list (device tensor).
-        One host read of world - 1 numbers."""
+
+        ``n_prefix``: number of source-domain nodes when they form a prefix of the id order (merge_graphs puts them
+        first).  A rank whose block straddles the domain boundary needs BOTH halo operands -- twice the exchange of every
+        other rank, on the critical path.  So the ranks are also split between the two domains in proportion to the
+        domains' work, each domain cut evenly among its ranks, and that domain-pure partition is taken when its heaviest
+        rank is within ``pure_slack`` of the plainly balanced one.  One host read of a few numbers."""
         cost = torch.bincount(dst, minlength=num_nodes).to(torch.float64) + float(row_weight)
         cum = torch.cumsum(cost, 0)
-        targets = torch.arange(1, world, device=dst.device, dtype=torch.float64) * (cum[-1] / world)
-        cuts = (torch.searchsorted(cum, targets) + 1).clamp(max=num_nodes).tolist()
-        b = [0] + cuts + [int(num_nodes)]
-        for i in range(1, len(b)):
-            b[i] = max(b[i], b[i - 1])
-        return b
+
+        def cuts_of(lo, hi, parts):         # parts - 1 interior cut points of rows [lo, hi) at equal cost
+            if parts <= 1:
+                return []
+            base = cum[lo - 1] if lo > 0 else cum.new_zeros(())
+            total = cum[hi - 1] - base
+            targets = base + torch.arange(1, parts, device=dst.device, dtype=torch.float64) * (total / parts)
+            return (torch.searchsorted(cum, targets) + 1).clamp(min=lo, max=hi).tolist()
+
+        def finish(cuts):
+            b = [0] + [int(c) for c in cuts] + [int(num_nodes)]
+            for i in range(1, len(b)):
+                b[i] = max(b[i], b[i - 1])
+            return b
+
+        plain = finish(cuts_of(0, num_nodes, world))
+        if n_prefix is None or world < 2 or not (0 < n_prefix < num_nodes):
+            return plain
+
+        def heaviest(b):
+            ends = torch.tensor(b, device=dst.device)
+            c0 = torch.cat((cum.new_zeros(1), cum))[ends]
+            return float((c0[1:] - c0[:-1]).max())
+        w_src = float(cum[n_prefix - 1])
+        w_all = float(cum[-1])
+        r_src = min(world - 1, max(1, int(round(world * w_src / w_all))))
+        pure = finish(cuts_of(0, n_prefix, r_src) + [n_prefix] + cuts_of(n_prefix, num_nodes, world - r_src))
+        return pure if heaviest(pure) <= pure_slack * heaviest(plain) else plain
 
     def global_rank(self, r):
         return r if self.group is None or self.group is dist.group.WORLD else dist.get_global_rank(self.group, r)

@@ -208,15 +208,44 @@ int launch_gatv2_fwd(const int* rowptr, const int* col, const int* order, const 
 // the bits of a lane are packed by one funnel shift per feature.  U edges are in flight per group; warps are
 // persistent over a static round-robin of row sets (no CTA barrier: a long row delays only its own warp, and the
 // d a_f summation order stays fixed).
-template <int VEC, int G, int CH, int U, int MINB, int ES>
-__global__ void __launch_bounds__(128, MINB)
-gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ csr_to_csc,
-                     const int* __restrict__ order, const uint8_t* __restrict__ dst_is_src, const float* __restrict__ Hs, const float* __restrict__ Ht,
-                     const float* __restrict__ af_t2s, const float* __restrict__ af_s2t, float slope, long long n, long long slot_off,
-                     long long row_off, int c, int cw, const float* __restrict__ out, const float* __restrict__ row_max,
-                     const float* __restrict__ row_sum, const float* __restrict__ score, const float* __restrict__ gout,
-                     float* __restrict__ gHs, float* __restrict__ gHt, unsigned* __restrict__ erec, unsigned* __restrict__ emask,
-                     float* __restrict__ ga_part) {
+struct BwdDstParams {
+  const int *rowptr, *col, *csr_to_csc, *order;
+  const uint8_t* dst_is_src;
+  const float *Hs, *Ht, *af_t2s, *af_s2t;
+  float slope;
+  long long row_off;
+  int c, cw;
+  const float *out, *row_max, *row_sum, *score, *gout;
+  float *gHs, *gHt;
+  unsigned *erec, *emask;
+};
+
+// The slots [slot_off, slot_off + n) of the row order, processed by the warps wid = 0 .. nwarps-1 of a launch (or of a
+// part of one); s_ga: the CTA's [2 * EPL][128] scratch columns.
+template <int VEC, int G, int CH, int U, int ES>
+__device__ __forceinline__ void bwd_dst_rows(const BwdDstParams& P, long long n, long long slot_off, long long wid, long long nwarps,
+                                             float (*s_ga)[128], float* __restrict__ ga_part) {
+  const int* __restrict__ rowptr = P.rowptr;
+  const int* __restrict__ col = P.col;
+  const int* __restrict__ csr_to_csc = P.csr_to_csc;
+  const int* __restrict__ order = P.order;
+  const uint8_t* __restrict__ dst_is_src = P.dst_is_src;
+  const float* __restrict__ Hs = P.Hs;
+  const float* __restrict__ Ht = P.Ht;
+  const float* __restrict__ af_t2s = P.af_t2s;
+  const float* __restrict__ af_s2t = P.af_s2t;
+  const float slope = P.slope;
+  const long long row_off = P.row_off;
+  const int c = P.c, cw = P.cw;
+  const float* __restrict__ out = P.out;
+  const float* __restrict__ row_max = P.row_max;
+  const float* __restrict__ row_sum = P.row_sum;
+  const float* __restrict__ score = P.score;
+  const float* __restrict__ gout = P.gout;
+  float* __restrict__ gHs = P.gHs;
+  float* __restrict__ gHt = P.gHt;
+  unsigned* __restrict__ erec = P.erec;
+  unsigned* __restrict__ emask = P.emask;
   // ES > 1: ES groups of G lanes share a row and split its EDGES (group s takes edges s, s + ES, ...).  Used for
   // narrow rows (G == 1: consecutive lanes read consecutive col entries) and for the HUB rows of wide ones (the
   // longest rows of the degree order get a whole warp each, so that a 2000-edge row is not one group's serial loop).
@@ -230,14 +259,11 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
   const int sub = (lane / G) % ES;                 // which share of the row's edges
   const unsigned gmask = group_mask<G>(lane);
   const unsigned rmask = group_mask<RL>(lane);
-  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int col0 = lane_g * EPL;
   const float oms = 1.f - slope;
   bool cok[CH];
-  // running d a_f sums of this lane, per destination domain: thread-private columns of shared memory
+  // s_ga: running d a_f sums of this lane, per destination domain: thread-private columns of shared memory
   // (kept out of the register file; touched once per ROW)
-  __shared__ float s_ga[2 * EPL][128];
 #pragma unroll
   for (int ch = 0; ch < CH; ++ch) cok[ch] = col0 + ch * VEC < c;
 #pragma unroll
@@ -402,6 +428,30 @@ gatv2_bwd_dst_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
       ga_part[wid * 2 * c + c + cc] = vt;
     }
   }
+}
+
+template <int VEC, int G, int CH, int U, int MINB, int ES>
+__global__ void __launch_bounds__(128, MINB)
+gatv2_bwd_dst_kernel(const BwdDstParams P, long long n, long long slot_off, float* __restrict__ ga_part) {
+  __shared__ float s_ga[2 * VEC * CH][128];
+  bwd_dst_rows<VEC, G, CH, U, ES>(P, n, slot_off, (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5),
+                                  (long long)gridDim.x * (blockDim.x >> 5), s_ga, ga_part);
+}
+
+// One launch for a degree-ordered graph: the first hub_ctas CTAs take the n_hub longest rows with a WARP per row (32 / G
+// groups split the edges), the others the remaining rows with a group per row.  The hub CTAs start first and are done
+// long before the launch ends, so the longest row costs nothing on top (as a launch of its own it took 0.18 ms).
+template <int VEC, int G, int CH, int U, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+gatv2_bwd_dst_hub_kernel(const BwdDstParams P, long long n, long long n_hub, int hub_ctas, float* __restrict__ ga_part) {
+  __shared__ float s_ga[2 * VEC * CH][128];
+  const long long wpc = blockDim.x >> 5;
+  if ((int)blockIdx.x < hub_ctas)
+    bwd_dst_rows<VEC, G, CH, U, 32 / G>(P, n_hub, 0, (long long)blockIdx.x * wpc + (threadIdx.x >> 5), (long long)hub_ctas * wpc,
+                                        s_ga, ga_part);
+  else
+    bwd_dst_rows<VEC, G, CH, U, 1>(P, n - n_hub, n_hub, (long long)(blockIdx.x - hub_ctas) * wpc + (threadIdx.x >> 5),
+                                   (long long)(gridDim.x - hub_ctas) * wpc, s_ga, ga_part + (size_t)hub_ctas * wpc * 2 * P.c);
 }
 
 // Row mapping of pass A: 128-bit loads when c % 4 == 0 (64-bit for other even widths, scalar otherwise), 8
@@ -630,15 +680,8 @@ size_t gatv2_bwd_workspace_bytes(long long n, long long e, int c) {
 }
 
 struct BwdDstArgs {
-  const int *rowptr, *col, *csr_to_csc, *order;
-  const uint8_t* dst_is_src;
-  const float *Hs, *Ht, *af_t2s, *af_s2t;
-  float slope;
-  long long n, slot_off, row_off;
-  int c, cw;
-  const float *out, *row_max, *row_sum, *score, *gout;
-  float *gHs, *gHt;
-  unsigned *erec, *emask;
+  BwdDstParams p;
+  long long n, slot_off;
   float* part;
 };
 
@@ -656,9 +699,33 @@ static int launch_bwd_dst_cfg(const BwdDstArgs& a, int& nwarps_out, cudaStream_t
   long long ctas = (nsets + WPC - 1) / WPC;
   if (ctas > (long long)kNumSMs * occ) ctas = (long long)kNumSMs * occ;
   nwarps_out = (int)(ctas * WPC);
-  kern<<<(unsigned)ctas, kBwdDstThreads, 0, stream>>>(a.rowptr, a.col, a.csr_to_csc, a.order, a.dst_is_src, a.Hs, a.Ht, a.af_t2s,
-                                                      a.af_s2t, a.slope, a.n, a.slot_off, a.row_off, a.c, a.cw, a.out, a.row_max, a.row_sum,
-                                                      a.score, a.gout, a.gHs, a.gHt, a.erec, a.emask, a.part);
+  kern<<<(unsigned)ctas, kBwdDstThreads, 0, stream>>>(a.p, a.n, a.slot_off, a.part);
+  BGNN_LAUNCH_CHECK();
+  return BGNN_OK;
+}
+
+// hub rows + the rest in one launch (see gatv2_bwd_dst_hub_kernel)
+template <int VEC, int G, int CH, int U, int MINB>
+static int launch_bwd_dst_merged(const BwdDstArgs& a, long long n_hub, int& nwarps_out, cudaStream_t stream) {
+  auto kern = gatv2_bwd_dst_hub_kernel<VEC, G, CH, U, MINB>;
+  static int occ = 0;
+  if (occ == 0) {
+    int o = 0;
+    BGNN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kBwdDstThreads, 0));
+    occ = o < 1 ? 1 : (o > kBwdDstMaxCtasPerSm ? kBwdDstMaxCtasPerSm : o);
+  }
+  constexpr int WPC = kBwdDstThreads / 32;
+  const long long resident = (long long)kNumSMs * occ;
+  // the hub rows hold a few per cent of the edges: a few per cent of the resident CTAs walk them (a warp per row,
+  // longest first), so that the slots they free early are few
+  long long hub_ctas = (n_hub + WPC - 1) / WPC;
+  if (hub_ctas > resident / 24) hub_ctas = resident / 24 > 0 ? resident / 24 : 1;
+  const long long nsets = (a.n - n_hub + (32 / G) - 1) / (32 / G);
+  long long main_ctas = (nsets + WPC - 1) / WPC;
+  if (main_ctas > resident - hub_ctas) main_ctas = resident - hub_ctas;
+  if (main_ctas < 1) main_ctas = 1;
+  nwarps_out = (int)((hub_ctas + main_ctas) * WPC);
+  kern<<<(unsigned)(hub_ctas + main_ctas), kBwdDstThreads, 0, stream>>>(a.p, a.n, n_hub, (int)hub_ctas, a.part);
   BGNN_LAUNCH_CHECK();
   return BGNN_OK;
 }
@@ -684,16 +751,33 @@ static int launch_bwd_dst(const BwdDstArgs& a, int& nwarps_out, cudaStream_t str
   }
 }
 
-// The longest rows of the degree order, one WARP per row (ES = 32 / G groups split the row's edges).
+// Degree-ordered graph, rows of 2..16 lanes: the longest rows get a WARP each (ES = 32 / G groups split the row's edges)
+// inside the same launch.  BGNN_GAT_HUBS=separate keeps the two-launch form for A/B measurements.
 template <int VEC, int G, int CH>
-static int launch_bwd_dst_hubs(const BwdDstArgs& a, int& nwarps_out, cudaStream_t stream) {
+static int launch_bwd_dst_hubs(const BwdDstArgs& a, long long n_hub, int& nwarps_out, cudaStream_t stream) {
   if constexpr (G > 1 && G < 32) {
     constexpr int EPL = VEC * CH;
+    static const bool separate = getenv("BGNN_GAT_HUBS") && getenv("BGNN_GAT_HUBS")[0] == 's';
+    if (!separate) return launch_bwd_dst_merged<VEC, G, CH, 2, (EPL > 8) ? 3 : 6>(a, n_hub, nwarps_out, stream);
+    BwdDstArgs h = a;
+    h.n = n_hub;
+    int nh = 0, nr = 0;
     // 4 edges in flight per group: the single longest row bounds this launch
-    return launch_bwd_dst_cfg<VEC, G, CH, (EPL > 8) ? 2 : 4, (EPL > 8) ? 3 : 4, 32 / G>(a, nwarps_out, stream);
+    int rc = launch_bwd_dst_cfg<VEC, G, CH, (EPL > 8) ? 2 : 4, (EPL > 8) ? 3 : 4, 32 / G>(h, nh, stream);
+    if (rc != BGNN_OK) return rc;
+    BwdDstArgs r = a;
+    r.n = a.n - n_hub;
+    r.slot_off = n_hub;
+    r.part = a.part + (size_t)nh * 2 * a.p.c;
+    if (r.n > 0) {
+      rc = launch_bwd_dst<VEC, G, CH>(r, nr, stream);
+      if (rc != BGNN_OK) return rc;
+    }
+    nwarps_out = nh + nr;
+    return BGNN_OK;
   } else {
     nwarps_out = 0;
-    return BGNN_OK;
+    return BGNN_ERR_UNSUPPORTED;
   }
 }
 
@@ -718,14 +802,14 @@ static int dispatch_bwd_dst(int g, int ch, const BwdDstArgs& a, int& nwarps_out,
 }
 
 template <int VEC>
-static int dispatch_bwd_dst_hubs(int g, const BwdDstArgs& a, int& nwarps_out, cudaStream_t stream) {
+static int dispatch_bwd_dst_hubs(int g, const BwdDstArgs& a, long long n_hub, int& nwarps_out, cudaStream_t stream) {
   constexpr int CHW = 8 / VEC;
   switch (g) {
-    case 2: return launch_bwd_dst_hubs<VEC, 2, CHW>(a, nwarps_out, stream);
-    case 4: return launch_bwd_dst_hubs<VEC, 4, CHW>(a, nwarps_out, stream);
-    case 8: return launch_bwd_dst_hubs<VEC, 8, CHW>(a, nwarps_out, stream);
-    case 16: return launch_bwd_dst_hubs<VEC, 16, CHW>(a, nwarps_out, stream);
-    default: nwarps_out = 0; return BGNN_OK;
+    case 2: return launch_bwd_dst_hubs<VEC, 2, CHW>(a, n_hub, nwarps_out, stream);
+    case 4: return launch_bwd_dst_hubs<VEC, 4, CHW>(a, n_hub, nwarps_out, stream);
+    case 8: return launch_bwd_dst_hubs<VEC, 8, CHW>(a, n_hub, nwarps_out, stream);
+    case 16: return launch_bwd_dst_hubs<VEC, 16, CHW>(a, n_hub, nwarps_out, stream);
+    default: nwarps_out = 0; return BGNN_ERR_UNSUPPORTED;
   }
 }
 
@@ -789,30 +873,24 @@ int launch_gatv2_bwd(const int* rowptr, const int* col, const int* t_rowptr, con
   }
   int npa = 0, npb = 0;
   if (n > 0) {
-    BwdDstArgs a{rowptr, col, csr_to_csc, order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, n, 0, row_off, c, cw,
-                 out, row_max, row_sum, score, gout, gHs, gHt, erec, emask, part};
+    BwdDstArgs a;
+    a.p = BwdDstParams{rowptr, col, csr_to_csc, order, dst_is_src, Hs, Ht, af_t2s, af_s2t, slope, row_off, c, cw,
+                       out, row_max, row_sum, score, gout, gHs, gHt, erec, emask};
+    a.n = n;
+    a.slot_off = 0;
+    a.part = part;
     // the head of the degree order: one warp per row, so that a hub row is not a single group's serial loop
     const long long n_hub = (order && dg >= 2 && dg <= 16) ? (n < kHubRows ? n : kHubRows) : 0;
-    if (n_hub > 0) {
-      a.n = n_hub;
-      int nh = 0;
-      const int rc = dvec == 4 ? dispatch_bwd_dst_hubs<4>(dg, a, nh, stream)
-                   : dvec == 2 ? dispatch_bwd_dst_hubs<2>(dg, a, nh, stream)
-                               : dispatch_bwd_dst_hubs<1>(dg, a, nh, stream);
-      if (rc != BGNN_OK) return rc;
-      npa = nh;
-    }
-    if (n > n_hub) {
-      a.n = n - n_hub;
-      a.slot_off = n_hub;
-      a.part = part + (size_t)npa * 2 * c;
-      int nr = 0;
-      const int rc = dvec == 4 ? dispatch_bwd_dst<4>(dg, dch, a, nr, stream)
-                   : dvec == 2 ? dispatch_bwd_dst<2>(dg, dch, a, nr, stream)
-                               : dispatch_bwd_dst<1>(dg, dch, a, nr, stream);
-      if (rc != BGNN_OK) return rc;
-      npa += nr;
-    }
+    int rc;
+    if (n_hub > 0 && n > n_hub)
+      rc = dvec == 4 ? dispatch_bwd_dst_hubs<4>(dg, a, n_hub, npa, stream)
+         : dvec == 2 ? dispatch_bwd_dst_hubs<2>(dg, a, n_hub, npa, stream)
+                     : dispatch_bwd_dst_hubs<1>(dg, a, n_hub, npa, stream);
+    else
+      rc = dvec == 4 ? dispatch_bwd_dst<4>(dg, dch, a, npa, stream)
+         : dvec == 2 ? dispatch_bwd_dst<2>(dg, dch, a, npa, stream)
+                     : dispatch_bwd_dst<1>(dg, dch, a, npa, stream);
+    if (rc != BGNN_OK) return rc;
   }
   float* part_b = part + (size_t)npa * 2 * c;
   int rcb = BGNN_OK;

@@ -116,3 +116,33 @@ def test_dense_kernels_reject_invalid_arguments(lib):
     assert lib.bgnn_bn_relu_fwd_f32(null, 4, 8, null, null, 1e-5, 0.1, null, null, 1, null, null, null, 0, null) == -1
     assert lib.bgnn_adapted_wide_fwd_f32(null, 4, 8, null, null, 32, null, null, null, null, null, null, null, null) == -1
     assert lib.bgnn_tf32_planes_f32(null, 4, 4, 4, 1, 16, 32, null, null, null) == -1
+
+
+def test_round2_entry_points_reject_invalid_arguments(lib):
+    """Host-side validation of the entry points added in round 2 (no launch happens on these paths)."""
+    null = ctypes.c_void_p(None)
+    nan = float("nan")
+    # kNN with the epsilon epilogue: NULL inputs / k > ndb
+    assert lib.bgnn_knn_cosine_eps_f32(null, 4, null, 4, 8, 2, 1, 1, 0, nan, null, null, null, null, null, null, 0, null) == -1
+    assert lib.bgnn_knn_addrelu_eps_f32(null, 4, null, 4, 8, null, 0.0, 9, 1, 0.5, null, null, null, null, null, 0, null) == -1
+    # quantile: empty input, rank out of range, weight outside [0, 1]
+    assert lib.bgnn_quantile_workspace_bytes() >= 1024
+    assert lib.bgnn_quantile_f32(null, 0, 0, 0.0, null, null, 0, null) == -1
+    one = ctypes.c_void_p(16)          # a non-NULL pointer that is never dereferenced on these paths
+    assert lib.bgnn_quantile_f32(one, 10, 10, 0.0, one, one, 4096, null) == -1
+    assert lib.bgnn_quantile_f32(one, 10, 3, 1.5, one, one, 4096, null) == -1
+    assert lib.bgnn_quantile_f32(one, 10, 3, 0.5, one, null, 0, null) == -2          # workspace
+    assert lib.bgnn_edge_validity_f32(null, null, 5, null, null, null, null, null, null, null, null, null, null, 8, 0.0, null, one, null) == -1
+    # destination-partitioned aggregation: the local rows must lie inside the node range
+    assert lib.bgnn_gatv2_fwd_part_f32(null, null, null, null, null, null, null, null, 0.1, 4, -1, 8, null, null, null, null, null) == -1
+    assert lib.bgnn_gatv2_bwd_part_f32(*([null] * 7), 0, *([null] * 5), 0.1, 8, 4, 10, 8, *([null] * 10), 0, null) == -1     # 4 + 8 > 10
+    assert lib.bgnn_gatv2_heads_bwd_part_f32(*([null] * 5), 0, *([null] * 5), 0.1, 8, 4, 10, 3, 2, *([null] * 9), 0, null) == -1
+    # row-panel GEMM epilogue: unknown activation, residual narrower than the output
+    assert lib.bgnn_rowpanel_gemm_act_f32(one, 4, 8, 8, one, one, null, null, 3, null, 0, 8, one, 8, null) == -1
+    assert lib.bgnn_rowpanel_gemm_act_f32(one, 4, 8, 8, one, one, null, null, 1, one, 4, 8, one, 8, null) == -1
+    # strided SpMM: strides shorter than the width
+    assert lib.bgnn_spmm_csr_ld_f32(one, one, null, null, null, one, 4, 10, 8, 0, one, 8, null) == -1
+    assert lib.bgnn_bn_relu_bwd_apply_f32(null, null, 4, 8, null, 1, null, null, null) == -1
+    # the backward workspace now also holds scores and per-CTA partials of pass B: grows with n and e
+    a, b = lib.bgnn_gatv2_bwd_workspace_bytes(1000, 20000, 64), lib.bgnn_gatv2_bwd_workspace_bytes(2000, 40000, 64)
+    assert b > a > 20000 * 20

@@ -38,8 +38,9 @@ struct TcPlan {
   int kc;            // candidates kept per (row, list)
   int stages;        // slots of the TMA->MMA operand ring
   int kps;           // f16 sweep: k-blocks (64 features) per ring slot; 1 elsewhere
-  int nlists;        // lists per row = nsplit
+  int nlists;        // lists per row (nsplit; f16 sweep: ew * nsplit)
   int pair;          // f16 sweep: CTA pairs (cluster of 2, cta_group::2) sharing every db tile
+  int ew;            // f16 sweep: epilogue warps per TMEM lane quarter = lists per (row, split): 2 or 4
 };
 TcPlan tc_plan(int nq, int ndb, int d, int k, int passes);
 int launch_knn_cosine_tc(const float* qhi, const float* qlo, int nq, const float* dhi, const float* dlo, int ndb, int d,

@@ -13,14 +13,15 @@
 // them exactly in fp32 with the reference fmaf chain, selects under the parity key and certifies the row
 // against (largest discarded approximate score + delta); uncertified rows are redone exactly on CUDA cores.
 //
-// CTA = 10 warps, one (128-query block, db split) work unit, 1 CTA / SM:
+// CTA = 2 + 4*EW warps (EW = epilogue warps per TMEM lane quarter: 4, or 2 for CTA pairs / the seed sweep), one
+// (128-query block, db split) work unit, 1 CTA / SM:
 //   warp 0     TMA producer: the query block A [128 x dpad] once (resident), then a ring of B k-blocks
 //              [BN x 64] fp16, SWIZZLE_128B
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer; 128 x BN fp32 accumulator,
 //              double-buffered in TMEM: the epilogue of tile t overlaps the MMAs of tile t+1
-//   warps 2-9  epilogue: two warps per TMEM lane quarter, each taking every other 32-column chunk;
+//   warps 2..   epilogue: EW warps per TMEM lane quarter, each taking every EW-th 32-column chunk;
 //              thread <-> query row, running-threshold test on registers, rare insertion into a
-//              thread-private list in shared memory
+//              thread-private list in shared memory (one list per row and epilogue warp of the quarter)
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdio.h>
@@ -35,12 +36,14 @@ namespace bgnn {
 constexpr int F16_BM = 128;
 constexpr int F16_BK = 64;                          // fp16 elements per k-block = 128 B = one swizzle row
 constexpr int F16_UMMA_K = 16;
-constexpr int F16_THREADS = 320;
+constexpr int f16_threads(int ew) { return (2 + 4 * ew) * 32; }   // producer + MMA issuer + 4*EW epilogue warps
 constexpr int F16_A_KBLOCK = F16_BM * F16_BK * 2;   // 16 KB
 constexpr int F16_SMEM_MAX = 232448;
-constexpr int F16_SMEM_FIXED = 1024 + 512 + 1024;   // alignment slack + barriers / tmem slot + shared thresholds
+constexpr int f16_smem_fixed(int ew) { return 1024 + 512 + ew * F16_BM * 4; }   // alignment slack + barriers / tmem slot + shared thresholds
 constexpr int F16_FCAP = 4;                         // pending candidates per (row, epilogue warp) before a drain
-constexpr int F16_FIFO_BYTES = 2 * F16_FCAP * F16_BM * 8;
+// EW = 2: the pending FIFOs live in shared memory; EW = 4: two pending candidates per thread in registers (the
+// shared memory goes to the four lists per row)
+constexpr int f16_fifo_bytes(int ew) { return ew == 2 ? 2 * F16_FCAP * F16_BM * 8 : 0; }
 constexpr int F16_DRAIN_TILES = 8;                  // all lanes drain together every so many tiles
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -113,7 +116,9 @@ struct EpiState {
   int cnt;      // heap fill
   int fcnt;     // pending FIFO fill
   float lthr;   // worst kept heap value (-inf until the heap is full)
-  float thr;    // threshold the thread filters with = max(own heap, partner heap, seed), slightly stale
+  float thr;    // threshold the thread filters with = max(own heap, partner heaps, seed), slightly stale
+  float f0v, f1v;   // register FIFO (REGF): up to two pending candidates
+  int f0i, f1i;
 };
 struct EpiAddr {                // shared-window byte addresses of this thread's columns
   uint32_t val, idx;            // heap [kc][128]
@@ -122,15 +127,26 @@ struct EpiAddr {                // shared-window byte addresses of this thread's
   int kc;
 };
 
-// FIFO -> heap (FIFO order = index order, which the heap's tie rule relies on)
+// FIFO -> heap (FIFO order = index order, which the heap's tie rule relies on).  An unsorted list with a tracked minimum
+// (two stores + one pass over the kc values per insertion) was measured slower than the heap's sift-down: the pass is
+// kc / 4 dependent rounds of shared-memory loads at one or two active lanes (drains 289 -> 346 cycles per tile, r02x).
+template <bool REGF>
 static __device__ __noinline__ EpiState epi_drain(EpiState e, EpiAddr a) {
   ListState st;
   st.cnt = e.cnt;
   st.thr = e.lthr;
-  for (int s = 0; s < e.fcnt; ++s) {
-    const float v = lds_f32(a.fv + s * (F16_BM * 4));
-    const int j = lds_s32(a.fi + s * (F16_BM * 4));
-    if (v > st.thr) list_push(a.val, a.idx, F16_BM * 4, a.kc, st, v, j);
+  if (REGF) {
+    for (int s = 0; s < e.fcnt; ++s) {
+      const float v = s == 0 ? e.f0v : e.f1v;
+      const int j = s == 0 ? e.f0i : e.f1i;
+      if (v > st.thr) list_push(a.val, a.idx, F16_BM * 4, a.kc, st, v, j);
+    }
+  } else {
+    for (int s = 0; s < e.fcnt; ++s) {
+      const float v = lds_f32(a.fv + s * (F16_BM * 4));
+      const int j = lds_s32(a.fi + s * (F16_BM * 4));
+      if (v > st.thr) list_push(a.val, a.idx, F16_BM * 4, a.kc, st, v, j);
+    }
   }
   e.cnt = st.cnt;
   e.lthr = st.thr;
@@ -141,8 +157,10 @@ static __device__ __noinline__ EpiState epi_drain(EpiState e, EpiAddr a) {
 }
 
 // queue every column of one group of 8 that beats the threshold, in index order
+template <bool REGF>
 static __device__ __noinline__ EpiState epi_scan8(EpiState e, EpiAddr a, int jbase, float v0, float v1, float v2,
                                                   float v3, float v4, float v5, float v6, float v7) {
+  constexpr int FCAP = REGF ? 2 : F16_FCAP;
   const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
   int last = -1;
   while (true) {
@@ -156,10 +174,14 @@ static __device__ __noinline__ EpiState epi_scan8(EpiState e, EpiAddr a, int jba
       cnt += p ? 1 : 0;
     }
     if (cc < 0) break;
-    if (e.fcnt == F16_FCAP) e = epi_drain(e, a);
+    if (e.fcnt == FCAP) e = epi_drain<REGF>(e, a);
     if (cv > e.thr) {                               // the drain may have raised the threshold
-      sts_f32(a.fv + e.fcnt * (F16_BM * 4), cv);
-      sts_s32(a.fi + e.fcnt * (F16_BM * 4), jbase + cc);
+      if (REGF) {
+        if (e.fcnt == 0) { e.f0v = cv; e.f0i = jbase + cc; } else { e.f1v = cv; e.f1i = jbase + cc; }
+      } else {
+        sts_f32(a.fv + e.fcnt * (F16_BM * 4), cv);
+        sts_s32(a.fi + e.fcnt * (F16_BM * 4), jbase + cc);
+      }
       ++e.fcnt;
     }
     if (cnt == 1) break;
@@ -173,13 +195,21 @@ static __device__ __noinline__ EpiState epi_scan8(EpiState e, EpiAddr a, int jba
 // shared-memory fill rate per SM halve; both bounded the single-CTA kernel (profiles/README.md, r01g).
 // MODE: 0 = sweep, 1 = seed sweep over the db sample (segment maxima only), 2 = sweep with the BGNN_F16_DBG
 // bottleneck experiments / wait-cycle instrumentation compiled in (tools/diag_knn_*.sh).
-template <int BN, bool PAIR, int MODE>
-__global__ void __launch_bounds__(F16_THREADS, 1)
+// EW: epilogue warps per TMEM lane quarter = lists per (row, db split).  The epilogue is bound by the LATENCY of its
+// rare paths (one lane of 32 walks the hit path while the tile's other rows wait: 24 % of the warps' time; the heap
+// drains: 14 %; profiles/r02w_knn_f16_ncu.txt).  EW = 4 halves the columns, the registers and the hit probability per
+// warp and puts four epilogue warps on every scheduler, but the hits per warp only drop by a fifth and the tcgen05.ld's
+// contend: measured equal to EW = 2 (42.2 vs 42.6 ms), kept as an experiment (BGNN_F16_EW=4).
+template <int BN, bool PAIR, int MODE, int EW>
+__global__ void __launch_bounds__(f16_threads(EW), 1)
 knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
                       int nq, int ndb, int kblocks, int tiles_total, int tiles_per_split, int kc, int stages, int kps,
                       const float* __restrict__ thr_init, float* __restrict__ cand_val, int* __restrict__ cand_idx,
                       int seed_segs, int dbg_arg) {
   constexpr bool SEED = MODE == 1;
+  constexpr bool REGF = EW == 4;                   // pending candidates in registers
+  static_assert(EW == 2 || EW == 4, "two or four epilogue warps per lane quarter");
+  static_assert(BN % (32 * EW) == 0, "every epilogue warp takes whole 32-column chunks");
   const int dbg = (MODE == 2) ? dbg_arg : 0;       // folds every experiment branch away outside MODE 2
   constexpr int B_ROWS = PAIR ? BN / 2 : BN;     // db rows of a tile this CTA loads
   constexpr int B_STAGE = B_ROWS * F16_BK * 2;
@@ -189,12 +219,13 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* a_base = smem;                                          // kblocks * 16 KB, resident
   unsigned char* b_base = a_base + (size_t)kblocks * F16_A_KBLOCK;       // stages * B_STAGE ring
-  float* lval = reinterpret_cast<float*>(b_base + (size_t)stages * kps * B_STAGE);   // [2][kc][128]
-  int* lidx = reinterpret_cast<int*>(lval + (size_t)2 * kc * F16_BM);           // [2][kc][128]
-  float* ffv = reinterpret_cast<float*>(lidx + (size_t)2 * kc * F16_BM);     // [2][FCAP][128] pending values
-  int* ffi = reinterpret_cast<int*>(ffv + 2 * F16_FCAP * F16_BM);             // [2][FCAP][128] pending indices
-  float* thr_sh = reinterpret_cast<float*>(ffi + 2 * F16_FCAP * F16_BM);      // [2][128] list thresholds, shared by the warp pair
-  uint64_t* bars = reinterpret_cast<uint64_t*>(thr_sh + 2 * F16_BM);
+  constexpr int FIFO_ELEMS = REGF ? 0 : 2 * F16_FCAP * F16_BM;
+  float* lval = reinterpret_cast<float*>(b_base + (size_t)stages * kps * B_STAGE);   // [EW][kc][128]
+  int* lidx = reinterpret_cast<int*>(lval + (size_t)EW * kc * F16_BM);          // [EW][kc][128]
+  float* ffv = reinterpret_cast<float*>(lidx + (size_t)EW * kc * F16_BM);    // [2][FCAP][128] pending values (EW = 2)
+  int* ffi = reinterpret_cast<int*>(ffv + FIFO_ELEMS);                        // [2][FCAP][128] pending indices (EW = 2)
+  float* thr_sh = reinterpret_cast<float*>(ffi + FIFO_ELEMS);                 // [EW][128] list thresholds, shared by the warps of a quarter
+  uint64_t* bars = reinterpret_cast<uint64_t*>(thr_sh + EW * F16_BM);
   uint64_t* full_bar = bars;                      // [stages]
   uint64_t* empty_bar = bars + stages;            // [stages]
   uint64_t* tfull_bar = bars + 2 * stages;               // [NBUF]
@@ -212,7 +243,7 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    for (int b = 0; b < NBUF; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), PAIR ? 16 : 8); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), (PAIR ? 8 : 4) * EW); }
     mbar_init(smem_u32(a_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -324,19 +355,20 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   } else {
     // ===================== epilogue: thread <-> query row, warp pair <-> lane quarter =====================
     const int quarter = warp & 3;                  // TMEM lanes this warp may read: 32*quarter ..
-    const int half = (warp - 2) >> 2;              // which of the two warps of the quarter
+    const int half = (warp - 2) >> 2;              // which of the EW warps of the quarter
     const int r_in_tile = quarter * 32 + lane;
     const bool row_ok = q0 + r_in_tile < nq;
     float* my_val = lval + (size_t)half * kc * F16_BM + r_in_tile;
     int* my_idx = lidx + (size_t)half * kc * F16_BM + r_in_tile;
     const uint32_t my_val_s = smem_addr(my_val), my_idx_s = smem_addr(my_idx);
-    // The two warps of a lane quarter keep separate lists for the same rows but share their thresholds:
-    // a column is kept only if it beats max(own, partner) threshold.  Sound for the certification in
-    // knn_select.cu: every column either warp discards scores <= the larger of the two final list minima.
-    const uint32_t my_thr_s = smem_addr(thr_sh + half * F16_BM + r_in_tile);
-    const uint32_t other_thr_s = smem_addr(thr_sh + (half ^ 1) * F16_BM + r_in_tile);
+    // The EW warps of a lane quarter keep separate lists for the same rows but share their thresholds:
+    // a column is kept only if it beats the largest of the row's list thresholds.  Sound for the certification in
+    // knn_select.cu: every column any warp discards scores <= the largest of the final minima of the FULL lists
+    // (a threshold is published only once its list is full, and thresholds only rise).
+    const uint32_t row_thr_s = smem_addr(thr_sh + r_in_tile);        // + l * 512: list l of this row
+    const uint32_t my_thr_s = row_thr_s + (uint32_t)(half * F16_BM * 4);
     sts_f32(my_thr_s, -INFINITY);
-    asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * EW) : "memory");     // epilogue warps only
     // effective threshold = max(own list, partner list, seed): the seed is a score that at least kSeedKc db
     // rows of a sample reach (knn_seed_thr_kernel), so the lists skip most of their start-up insertions
     EpiState es;
@@ -344,6 +376,8 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     es.fcnt = 0;
     es.lthr = -INFINITY;
     es.thr = (thr_init && row_ok) ? __ldg(thr_init + q0 + r_in_tile) : -INFINITY;
+    es.f0v = es.f1v = 0.f;
+    es.f0i = es.f1i = 0;
     // Heap insertions are deferred: a column that beats the threshold is appended to a small per-thread
     // FIFO (two stores), and the FIFOs are drained into the heaps by ALL lanes of the warp together every
     // F16_DRAIN_TILES tiles (or by one lane alone when its FIFO is full).  In steady state a chunk holds a
@@ -353,8 +387,8 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     EpiAddr ea;
     ea.val = my_val_s;
     ea.idx = my_idx_s;
-    ea.fv = smem_addr(ffv + (size_t)half * F16_FCAP * F16_BM + r_in_tile);
-    ea.fi = smem_addr(ffi + (size_t)half * F16_FCAP * F16_BM + r_in_tile);
+    ea.fv = REGF ? 0u : smem_addr(ffv + (size_t)half * F16_FCAP * F16_BM + r_in_tile);
+    ea.fi = REGF ? 0u : smem_addr(ffi + (size_t)half * F16_FCAP * F16_BM + r_in_tile);
     ea.thr = my_thr_s;
     ea.kc = kc;
     float seg_max = -INFINITY, seed_min = INFINITY;   // seed mode only (see below)
@@ -364,15 +398,17 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const int seg_tiles = SEED ? max(1, ntiles / max(seed_segs, 1)) : 0;
     int seg_left = seg_tiles, segs_done = 0;
     int drain_left = F16_DRAIN_TILES;
-    long long w_tfull = 0, w_ld = 0, w_proc = 0, e_start = clock64();
+    long long w_tfull = 0, w_ld = 0, w_proc = 0, w_drain = 0, w_hit = 0, e_start = clock64();
+    int n_hit_tiles = 0;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t % NBUF;
       const uint32_t tph = (uint32_t)(t / NBUF) & 1u;
+      long long c0 = (dbg & 8) ? clock64() : 0;
       if (!SEED && --drain_left == 0) {
         drain_left = F16_DRAIN_TILES;
-        if (__any_sync(0xffffffffu, es.fcnt > 0)) es = epi_drain(es, ea);
+        if (__any_sync(0xffffffffu, es.fcnt > 0)) es = epi_drain<REGF>(es, ea);
       }
-      long long c0 = (dbg & 8) ? clock64() : 0;
+      if (dbg & 8) { const long long c1 = clock64(); w_drain += c1 - c0; c0 = c1; }
       mbar_wait(smem_u32(&tfull_bar[buf]), tph);
       if (dbg & 8) { const long long c1 = clock64(); w_tfull += c1 - c0; c0 = c1; }
       tc_fence_after();
@@ -389,10 +425,10 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       // All of this warp's chunks of the tile (half, half+2, ...) are pulled into registers up front and the
       // TMEM buffer goes straight back to the MMA issuer: how long the selection below takes (it varies a lot
       // from warp to warp and tile to tile) no longer decides when the MMAs of tile t+2 may start.
-      constexpr int NCH = BN / 64;                  // chunks per warp per tile
+      constexpr int NCH = BN / (32 * EW);           // chunks per warp per tile
       float rr[NCH][32];
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) tc_ld32(taddr0 + (uint32_t)((half + 2 * i) * 32), rr[i]);
+      for (int i = 0; i < NCH; ++i) tc_ld32(taddr0 + (uint32_t)((half + EW * i) * 32), rr[i]);
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
@@ -404,23 +440,27 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #pragma unroll
         for (int i = 0; i < NCH; ++i)
 #pragma unroll
-          for (int c = 0; c < 32; ++c) rr[i][c] = (db0 + (half + 2 * i) * 32 + c < ndb) ? rr[i][c] : -INFINITY;
+          for (int c = 0; c < 32; ++c) rr[i][c] = (db0 + (half + EW * i) * 32 + c < ndb) ? rr[i][c] : -INFINITY;
       }
       if (!(dbg & 1)) {
-        // group maxima of ALL chunks first (3-input maxima, 4 instructions per group of 8, independent of each
-        // other), then one test per tile; a hit hands the groups concerned to the out-of-line scan
-        float gm[NCH][4];
+        // chunk maxima first (3-input maxima, 4 instructions per group of 8, independent of each other), then one
+        // test per tile.  Only the chunk maxima stay live: a hit recomputes the group maxima of the chunks concerned
+        // (kept per group they cost 8-16 registers, which the compiler spilled on every tile).
+        float cm[NCH];
 #pragma unroll
-        for (int i = 0; i < NCH; ++i)
+        for (int i = 0; i < NCH; ++i) {
+          float gmx[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const float m012 = max3f(rr[i][g * 8 + 0], rr[i][g * 8 + 1], rr[i][g * 8 + 2]);
             const float m345 = max3f(rr[i][g * 8 + 3], rr[i][g * 8 + 4], rr[i][g * 8 + 5]);
-            gm[i][g] = max3f(m012, m345, fmaxf(rr[i][g * 8 + 6], rr[i][g * 8 + 7]));
+            gmx[g] = max3f(m012, m345, fmaxf(rr[i][g * 8 + 6], rr[i][g * 8 + 7]));
           }
-        float mx = max3f(gm[0][0], gm[0][1], fmaxf(gm[0][2], gm[0][3]));
+          cm[i] = max3f(gmx[0], gmx[1], fmaxf(gmx[2], gmx[3]));
+        }
+        float mx = cm[0];
 #pragma unroll
-        for (int i = 1; i < NCH; ++i) mx = fmaxf(mx, max3f(gm[i][0], gm[i][1], fmaxf(gm[i][2], gm[i][3])));
+        for (int i = 1; i < NCH; ++i) mx = fmaxf(mx, cm[i]);
         if (SEED) {
           seg_max = fmaxf(seg_max, mx);
           if (--seg_left == 0) {                     // a segment is complete (tiles past the last full one are ignored)
@@ -429,50 +469,62 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             seg_max = -INFINITY;
           }
         } else {
-          es.thr = fmaxf(es.thr, lds_f32(other_thr_s));
+#pragma unroll
+          for (int l = 0; l < EW; ++l) es.thr = fmaxf(es.thr, lds_f32(row_thr_s + (uint32_t)(l * F16_BM * 4)));
+          const long long ch0 = (dbg & 8) ? clock64() : 0;
+          if ((dbg & 8) && __any_sync(0xffffffffu, row_ok && mx > es.thr)) ++n_hit_tiles;
           if (row_ok && mx > es.thr) {
 #pragma unroll
-            for (int i = 0; i < NCH; ++i)
+            for (int i = 0; i < NCH; ++i) {
+              if (!(cm[i] > es.thr)) continue;
 #pragma unroll
-              for (int g = 0; g < 4; ++g)
-                if (gm[i][g] > es.thr) {
+              for (int g = 0; g < 4; ++g) {
+                // The copies are made opaque to the compiler INSIDE the branch: without that it if-converts the
+                // select chains of all groups of a tile into every hit (290 instructions per hit at one active
+                // lane, profiles/r01p_knn_f16_ncu.txt)
+                float v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { v[c] = rr[i][g * 8 + c]; asm volatile("" : "+f"(v[c])); }
+                const float gmax = max3f(max3f(v[0], v[1], v[2]), max3f(v[3], v[4], v[5]), fmaxf(v[6], v[7]));
+                if (gmax > es.thr) {
                   // the usual case inline: exactly one column of the group beats the threshold -- it is the
-                  // group maximum, only its position is missing -- and the FIFO has room.  The copies below are
-                  // made opaque to the compiler INSIDE the branch: without that it if-converts the select chains
-                  // of all 16 groups of a tile into every hit (290 instructions per hit at one active lane,
-                  // profiles/r01p_knn_f16_ncu.txt)
-                  float v[8];
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) { v[c] = rr[i][g * 8 + c]; asm volatile("" : "+f"(v[c])); }
+                  // group maximum, only its position is missing -- and the FIFO has room
                   int first = 8, last = -1;
 #pragma unroll
                   for (int c = 7; c >= 0; --c) first = (v[c] > es.thr) ? c : first;
 #pragma unroll
                   for (int c = 0; c < 8; ++c) last = (v[c] > es.thr) ? c : last;
-                  const int jb = db0 + (half + 2 * i) * 32 + g * 8;
-                  if (first == last && es.fcnt < F16_FCAP) {
-                    sts_f32(ea.fv + es.fcnt * (F16_BM * 4), gm[i][g]);
-                    sts_s32(ea.fi + es.fcnt * (F16_BM * 4), jb + first);
+                  const int jb = db0 + (half + EW * i) * 32 + g * 8;
+                  if (first == last && es.fcnt < (REGF ? 2 : F16_FCAP)) {
+                    if (REGF) {
+                      if (es.fcnt == 0) { es.f0v = gmax; es.f0i = jb + first; } else { es.f1v = gmax; es.f1i = jb + first; }
+                    } else {
+                      sts_f32(ea.fv + es.fcnt * (F16_BM * 4), gmax);
+                      sts_s32(ea.fi + es.fcnt * (F16_BM * 4), jb + first);
+                    }
                     ++es.fcnt;
                   } else {
-                    es = epi_scan8(es, ea, jb, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+                    es = epi_scan8<REGF>(es, ea, jb, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
                   }
                 }
+              }
+            }
           }
+          if (dbg & 8) { __syncwarp(); w_hit += clock64() - ch0; }
         }
       }
       if (dbg & 8) w_proc += clock64() - c0;
     }
     if ((dbg & 8) && blockIdx.x < 1 && blockIdx.y == 0 && lane == 0)
-      printf("cta %d epilogue warp %d: total %lld cyc, waiting for a tile %lld, tmem loads %lld, selection %lld (%d tiles)\n",
-             (int)blockIdx.x, warp, clock64() - e_start, w_tfull, w_ld, w_proc, ntiles);
+      printf("cta %d epilogue warp %d: total %lld cyc, waiting for a tile %lld, tmem loads %lld, selection %lld (of which hit path %lld in %d tiles), drains %lld (%d tiles)\n",
+             (int)blockIdx.x, warp, clock64() - e_start, w_tfull, w_ld, w_proc, w_hit, n_hit_tiles, w_drain, ntiles);
     if (SEED) {
       // one value per (list, row): -inf when this CTA saw no complete segment
-      if (row_ok) cand_val[((long long)split * 2 + half) * nq + (q0 + r_in_tile)] = (seed_min < INFINITY) ? seed_min : -INFINITY;
+      if (row_ok) cand_val[((long long)split * EW + half) * nq + (q0 + r_in_tile)] = (seed_min < INFINITY) ? seed_min : -INFINITY;
     } else {
-    es = epi_drain(es, ea);
+    es = epi_drain<REGF>(es, ea);
     if (row_ok) {
-      const long long base = (((long long)split * 2 + half) * nq + (q0 + r_in_tile)) * kc;
+      const long long base = (((long long)split * EW + half) * nq + (q0 + r_in_tile)) * kc;
       for (int s = 0; s < kc; ++s) {
         const bool f = s < es.cnt;
         cand_val[base + s] = f ? my_val[s * F16_BM] : -INFINITY;
@@ -509,40 +561,77 @@ static int make_map_f16(CUtensorMap* m, const void* base, long long rows, int ld
   return r == CUDA_SUCCESS ? BGNN_OK : BGNN_ERR_DRIVER;
 }
 
-// Work decomposition: kc nominees per (row, half-list) next to the resident query block and the B ring.
+// List length for EW lists per (row, split).  The lists of a row cover disjoint column classes (32-column chunks dealt
+// round-robin to the EW warps), so the row's best k + 1 columns spread over them like Binomial(k + 1, 1 / EW) unless the
+// db order correlates with the chunk pattern; a list that would have to hold more than kc of them makes the row fail
+// certification (knn_select.cu) and the row is redone exactly -- correct, but slow when there are many.  kc is the
+// smallest length whose overflow probability per row stays below `target` (EW = 2 keeps k + 4 >= k + 1: no overflow).
+static int f16_list_len(int k, int ew, double target) {
+  const int n = k + 1;
+  if (ew == 2) return (k + 4 + 3) / 4 * 4;
+  const double p = 1.0 / ew;
+  for (int kc = (n + ew - 1) / ew; kc < n; ++kc) {
+    // P(X > kc), X ~ Binomial(n, p)
+    double tail = 0.0, term = 1.0;
+    for (int x = 0; x < n; ++x) term *= (1.0 - p);               // P(X = 0)
+    double px = term;
+    for (int x = 0; x <= n; ++x) {
+      if (x > kc) tail += px;
+      px = px * (double)(n - x) / (double)(x + 1) * p / (1.0 - p);
+    }
+    if (ew * tail <= target) return kc;
+  }
+  return n;
+}
+
+// Work decomposition: kc nominees per (row, list) next to the resident query block and the B ring.
 TcPlan tc_plan_f16(int nq, int ndb, int d, int k, int kc_fixed) {
   TcPlan p;
   p.bn = 0;
+  p.ew = 2;
   const int ldh = (d + F16_BK - 1) / F16_BK * F16_BK;
-  int kc = kc_fixed > 0 ? kc_fixed : (k + 4 + 3) / 4 * 4;
-  p.kc = kc;
   const int a_bytes = (ldh / F16_BK) * F16_A_KBLOCK;
-  const int list_bytes = 2 * kc * F16_BM * 8 + F16_FIFO_BYTES;
   static const int force_bn = getenv("BGNN_F16_BN") ? atoi(getenv("BGNN_F16_BN")) : 0;   // tuning experiments
-  static const int pair_env = getenv("BGNN_F16_PAIR") ? atoi(getenv("BGNN_F16_PAIR")) : 0;   // measured slower
+  // CTA pairs by default: every db tile crosses L2 -> shared memory once per 256 query rows instead of once per 128
+  // (the single-CTA sweep without its epilogue stops at 69 % of the tensor pipe = the chip's ~6300 B/clk L2 throughput;
+  // pairs reach 75 %), BGNN_F16_PAIR=0 switches them off.  BGNN_F16_EW=4: four epilogue warps / lists per lane quarter
+  // (single CTAs only) -- measured equal to two (42.2 vs 42.6 ms) and the shorter lists fail certification more often.
+  static const int pair_env = getenv("BGNN_F16_PAIR") ? atoi(getenv("BGNN_F16_PAIR")) : 1;
+  static const int force_ew = getenv("BGNN_F16_EW") ? atoi(getenv("BGNN_F16_EW")) : 0;       // 2 | 4
   const int qblocks = (nq + F16_BM - 1) / F16_BM;
-  p.pair = (pair_env && qblocks >= 2) ? 1 : 0;
-  for (int bn = (force_bn == 128 ? 128 : 256); bn >= 128; bn >>= 1) {
-    const int stage_bytes = (p.pair ? bn / 2 : bn) * F16_BK * 2;
-    const int units = (F16_SMEM_MAX - F16_SMEM_FIXED - a_bytes - list_bytes) / stage_bytes;   // k-blocks that fit
-    if (units < 3) continue;
-    // one barrier per slot of kps k-blocks: as many k-blocks of a tile per slot as still leave >= 2 slots
-    const int kblocks = ldh / F16_BK;
-    int kps = kblocks;
-    while (kps > 1 && (kblocks % kps != 0 || units / kps < 2)) --kps;
-    p.bn = bn;
-    p.kps = kps;
-    p.stages = min(units / kps, 8);
-    break;
+  p.pair = (pair_env && force_ew != 4 && qblocks >= 2) ? 1 : 0;
+  const int ew_first = (force_ew == 4 && kc_fixed == 0) ? 4 : 2;
+  for (int ew = ew_first; ew >= 2 && p.bn == 0; ew -= 2) {
+    // expected uncertified rows of the whole call <= ~1.5 (a handful go through knn_exact_rows at ~0.2 ms each)
+    const double target = fmin(6e-6, 1.5 / (double)(nq > 0 ? nq : 1));
+    const int kc = kc_fixed > 0 ? kc_fixed : f16_list_len(k, ew, target);
+    const int list_bytes = ew * kc * F16_BM * 8 + f16_fifo_bytes(ew);
+    for (int bn = (force_bn == 128 ? 128 : 256); bn >= 128; bn >>= 1) {
+      if (bn % (32 * ew) != 0) continue;
+      const int stage_bytes = (p.pair ? bn / 2 : bn) * F16_BK * 2;
+      const int units = (F16_SMEM_MAX - f16_smem_fixed(ew) - a_bytes - list_bytes) / stage_bytes;   // k-blocks that fit
+      if (units < 3) continue;
+      // one barrier per slot of kps k-blocks: as many k-blocks of a tile per slot as still leave >= 2 slots
+      const int kblocks = ldh / F16_BK;
+      int kps = kblocks;
+      while (kps > 1 && (kblocks % kps != 0 || units / kps < 2)) --kps;
+      p.bn = bn;
+      p.kps = kps;
+      p.stages = min(units / kps, 8);
+      p.kc = kc;
+      p.ew = ew;
+      break;
+    }
   }
   if (p.bn == 0) return p;                                  // caller falls back to another sweep
+  const int kc = p.kc;
   const int tiles = (ndb + p.bn - 1) / p.bn;
   int ns = (2 * kNumSMs + qblocks - 1) / qblocks;            // fill the machine when nq is small
-  ns = max(1, min(min(ns, tiles), min(8, BGNN_MERGE_MAX_CAND / (2 * kc))));
+  ns = max(1, min(min(ns, tiles), min(8, BGNN_MERGE_MAX_CAND / (p.ew * kc))));
   if (ns < 1) { p.bn = 0; return p; }
   p.tiles_per_split = (tiles + ns - 1) / ns;
   p.nsplit = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.nlists = 2 * p.nsplit;
+  p.nlists = p.ew * p.nsplit;
   if (p.nlists * kc > BGNN_MERGE_MAX_CAND) p.bn = 0;
   return p;
 }
@@ -552,7 +641,7 @@ static int f16_dbg_env() {
   return dbg;
 }
 
-template <int BN, bool PAIR, int MODE>
+template <int BN, bool PAIR, int MODE, int EW>
 static int launch_f16_cfg(const void* qh, int nq, const void* dh, int ndb, int ldh, const TcPlan& plan,
                           const float* thr_init, float* cand_val, int* cand_idx, int seed_segs, cudaStream_t stream) {
   CUtensorMap mq, md;
@@ -561,17 +650,17 @@ static int launch_f16_cfg(const void* qh, int nq, const void* dh, int ndb, int l
   if ((rc = make_map_f16(&mq, qh, nq, ldh, F16_BM)) != BGNN_OK) return rc;
   if ((rc = make_map_f16(&md, dh, ndb, ldh, B_ROWS)) != BGNN_OK) return rc;
   const int kblocks = ldh / F16_BK;
-  const size_t smem = F16_SMEM_FIXED + (size_t)kblocks * F16_A_KBLOCK + (size_t)plan.stages * plan.kps * B_ROWS * F16_BK * 2 +
-                      (size_t)2 * plan.kc * F16_BM * 8 + F16_FIFO_BYTES;
+  const size_t smem = f16_smem_fixed(EW) + (size_t)kblocks * F16_A_KBLOCK + (size_t)plan.stages * plan.kps * B_ROWS * F16_BK * 2 +
+                      (size_t)EW * plan.kc * F16_BM * 8 + f16_fifo_bytes(EW);
   if (smem > (size_t)F16_SMEM_MAX || plan.stages < 2 || plan.kps < 1 || kblocks % plan.kps != 0) return BGNN_ERR_UNSUPPORTED;
-  auto kern = knn_cosine_f16_kernel<BN, PAIR, MODE>;
+  auto kern = knn_cosine_f16_kernel<BN, PAIR, MODE, EW>;
   BGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = (ndb + BN - 1) / BN;
   const int qblocks = (nq + F16_BM - 1) / F16_BM;
   const int dbg = f16_dbg_env();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(PAIR ? (qblocks + 1) / 2 * 2 : qblocks, plan.nsplit);   // a pair = two neighbouring query blocks
-  cfg.blockDim = dim3(F16_THREADS);
+  cfg.blockDim = dim3(f16_threads(EW));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -591,11 +680,18 @@ static int launch_f16_any(const void* qh, int nq, const void* dh, int ndb, int l
   if (nq <= 0) return BGNN_OK;
   if (ldh % F16_BK != 0) return BGNN_ERR_INVALID_ARG;
   const int mode = seed_segs > 0 ? 1 : (f16_dbg_env() ? 2 : 0);
-#define F16_GO(BN_, PAIR_, MODE_) \
-  launch_f16_cfg<BN_, PAIR_, MODE_>(qh, nq, dh, ndb, ldh, plan, thr_init, cand_val, cand_idx, seed_segs, stream)
-#define F16_GO_MODE(BN_, PAIR_) (mode == 1 ? F16_GO(BN_, PAIR_, 1) : mode == 2 ? F16_GO(BN_, PAIR_, 2) : F16_GO(BN_, PAIR_, 0))
-  if (plan.bn == 256) return plan.pair ? F16_GO_MODE(256, true) : F16_GO_MODE(256, false);
-  if (plan.bn == 128) return plan.pair ? F16_GO_MODE(128, true) : F16_GO_MODE(128, false);
+#define F16_GO(BN_, PAIR_, MODE_, EW_) \
+  launch_f16_cfg<BN_, PAIR_, MODE_, EW_>(qh, nq, dh, ndb, ldh, plan, thr_init, cand_val, cand_idx, seed_segs, stream)
+#define F16_GO_MODE(BN_, PAIR_, EW_) \
+  (mode == 1 ? F16_GO(BN_, PAIR_, 1, EW_) : mode == 2 ? F16_GO(BN_, PAIR_, 2, EW_) : F16_GO(BN_, PAIR_, 0, EW_))
+  if (plan.ew == 4) {                                  // single CTAs only (tc_plan_f16)
+    if (plan.pair) return BGNN_ERR_UNSUPPORTED;
+    if (plan.bn == 256) return F16_GO_MODE(256, false, 4);
+    if (plan.bn == 128) return F16_GO_MODE(128, false, 4);
+  } else if (plan.ew == 2) {
+    if (plan.bn == 256) return plan.pair ? F16_GO_MODE(256, true, 2) : F16_GO_MODE(256, false, 2);
+    if (plan.bn == 128) return plan.pair ? F16_GO_MODE(128, true, 2) : F16_GO_MODE(128, false, 2);
+  }
 #undef F16_GO_MODE
 #undef F16_GO
   return BGNN_ERR_UNSUPPORTED;

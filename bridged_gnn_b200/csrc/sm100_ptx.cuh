@@ -89,8 +89,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Remote arrive WITHOUT cluster-scope release semantics: `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front
+// of the arrive (~1000 cycles per call, measured as the "tmem loads" wait of the pair epilogue).  What the hand-back of a
+// TMEM accumulator has to order are tcgen05.ld's, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync do; no
+// generic-proxy data travels with this signal (the same form CUTLASS' ClusterBarrier::arrive(cta_id) uses).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA load into this CTA's shared memory whose completion bytes are counted on a barrier that may live in the
 // peer CTA of the pair (shared::cluster address)

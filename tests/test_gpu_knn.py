@@ -209,6 +209,37 @@ def test_tensor_core_path_is_bit_identical_to_cuda_core_path(algo, nq, ndb, d, k
     assert int(st[0]) <= nq
 
 
+_VARIANT_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from bridged_gnn_b200 import ops
+g = torch.Generator().manual_seed(21)
+for nq, ndb, d, k in ((700, 9000, 128, 20), (1000, 70000, 256, 32), (129, 5000, 96, 8)):
+    cent = torch.randn(16, d, generator=g)
+    q = (cent[torch.randint(0, 16, (nq,), generator=g)] + 0.7 * torch.randn(nq, d, generator=g)).cuda()
+    db = (cent[torch.randint(0, 16, (ndb,), generator=g)] + 0.7 * torch.randn(ndb, d, generator=g)).cuda()
+    i0, v0, g0, _ = ops.knn_cosine(q, db, k, algo="simt")
+    i1, v1, g1, st = ops.knn_cosine(q, db, k, algo="f16")
+    assert torch.equal(i0, i1) and torch.equal(v0, v1) and torch.equal(g0, g1), (nq, ndb, d, k)
+    print("ok", nq, ndb, d, k, "fallback rows", int(st[0]))
+"""
+
+
+@pytest.mark.parametrize("env", [{"BGNN_F16_PAIR": "0"}, {"BGNN_F16_EW": "4"}, {"BGNN_F16_PAIR": "0", "BGNN_F16_BN": "128"}])
+def test_f16_sweep_variants_are_bit_identical(env):
+    """The fp16 sweep's shape knobs are read once per process: single CTAs instead of CTA pairs (cta_group::2), four
+    epilogue warps / lists per TMEM lane quarter, 128-column tiles.  Every variant must return the CUDA-core result."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT % root], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 3
+
+
 @pytest.mark.parametrize("algo", ["tc3", "f16"])
 @pytest.mark.parametrize("n_hard", [1, 5, 8, 9, 40])
 def test_uncertified_rows_few_and_many_take_the_exact_path(algo, n_hard):

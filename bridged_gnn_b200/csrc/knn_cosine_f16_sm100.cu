@@ -127,9 +127,55 @@ struct EpiAddr {                // shared-window byte addresses of this thread's
   int kc;
 };
 
-// FIFO -> heap (FIFO order = index order, which the heap's tie rule relies on).  An unsorted list with a tracked minimum
-// (two stores + one pass over the kc values per insertion) was measured slower than the heap's sift-down: the pass is
-// kc / 4 dependent rounds of shared-memory loads at one or two active lanes (drains 289 -> 346 cycles per tile, r02x).
+// Nominee heap: a binary min-heap on the APPROXIMATE score alone (root = worst kept nominee).  The shared list_push of
+// common.cuh orders by the parity key (value desc, index asc), which the exact CUDA-core sweep needs; here the lists only
+// nominate -- the threshold test is strict, an evicted nominee scores no more than the list's new minimum either way, and
+// knn_select.cu re-scores and orders exactly -- so the index compare, and with it most of the dependent instructions of a
+// sift level, can go: at one or two active lanes a level cost ~185 cycles (2300 cycles per drain, profiles/r02w).
+// Both children's values AND indices are loaded together (one shared-memory round trip per level), and the new root is
+// tracked in a register instead of being read back.  An unsorted list with a tracked minimum (two stores + one pass
+// over the kc values per insertion) was measured slower than a heap (kc / 4 dependent rounds of loads, r02x).
+__device__ __forceinline__ void nominee_push(uint32_t val, uint32_t idx, int kc, ListState& st, float v, int j) {
+  constexpr uint32_t SB = F16_BM * 4;               // byte stride between the slots of a thread's column
+  int pos;
+  float root = v;
+  if (st.cnt < kc) {
+    pos = st.cnt++;
+    while (pos > 0) {                               // sift up: a parent must not score more than its children
+      const int par = (pos - 1) >> 1;
+      const float pv = lds_f32(val + par * SB);
+      const int pi = lds_s32(idx + par * SB);
+      if (!(v < pv)) break;
+      sts_f32(val + pos * SB, pv);
+      sts_s32(idx + pos * SB, pi);
+      pos = par;
+    }
+    sts_f32(val + pos * SB, v);
+    sts_s32(idx + pos * SB, j);
+    if (st.cnt == kc) st.thr = lds_f32(val);
+    return;
+  }
+  pos = 0;                                          // replace the root, sift down
+  while (true) {
+    const int l = 2 * pos + 1;
+    if (l >= kc) break;
+    const int r = min(l + 1, kc - 1);               // == l when there is no right child
+    const float lv = lds_f32(val + l * SB), rv = lds_f32(val + r * SB);
+    const int li = lds_s32(idx + l * SB), ri = lds_s32(idx + r * SB);
+    const bool right = rv < lv;
+    const float cv = right ? rv : lv;
+    if (!(cv < v)) break;
+    if (pos == 0) root = cv;
+    sts_f32(val + pos * SB, cv);
+    sts_s32(idx + pos * SB, right ? ri : li);
+    pos = right ? r : l;
+  }
+  sts_f32(val + pos * SB, v);
+  sts_s32(idx + pos * SB, j);
+  st.thr = root;
+}
+
+// FIFO -> heap
 template <bool REGF>
 static __device__ __noinline__ EpiState epi_drain(EpiState e, EpiAddr a) {
   ListState st;
@@ -139,13 +185,13 @@ static __device__ __noinline__ EpiState epi_drain(EpiState e, EpiAddr a) {
     for (int s = 0; s < e.fcnt; ++s) {
       const float v = s == 0 ? e.f0v : e.f1v;
       const int j = s == 0 ? e.f0i : e.f1i;
-      if (v > st.thr) list_push(a.val, a.idx, F16_BM * 4, a.kc, st, v, j);
+      if (v > st.thr) nominee_push(a.val, a.idx, a.kc, st, v, j);
     }
   } else {
     for (int s = 0; s < e.fcnt; ++s) {
       const float v = lds_f32(a.fv + s * (F16_BM * 4));
       const int j = lds_s32(a.fi + s * (F16_BM * 4));
-      if (v > st.thr) list_push(a.val, a.idx, F16_BM * 4, a.kc, st, v, j);
+      if (v > st.thr) nominee_push(a.val, a.idx, a.kc, st, v, j);
     }
   }
   e.cnt = st.cnt;
@@ -489,13 +535,14 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 if (gmax > es.thr) {
                   // the usual case inline: exactly one column of the group beats the threshold -- it is the
                   // group maximum, only its position is missing -- and the FIFO has room
-                  int first = 8, last = -1;
+                  // count and position in one sum (3-input adds, depth 2) instead of two chains of 8 dependent selects
+                  int tk[8];
 #pragma unroll
-                  for (int c = 7; c >= 0; --c) first = (v[c] > es.thr) ? c : first;
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) last = (v[c] > es.thr) ? c : last;
+                  for (int c = 0; c < 8; ++c) tk[c] = (v[c] > es.thr) ? (0x100 | c) : 0;
+                  const int pk = (tk[0] + tk[1] + tk[2]) + (tk[3] + tk[4] + tk[5]) + (tk[6] + tk[7]);
+                  const int first = pk & 0xff;       // the column's position when exactly one beats the threshold
                   const int jb = db0 + (half + EW * i) * 32 + g * 8;
-                  if (first == last && es.fcnt < (REGF ? 2 : F16_FCAP)) {
+                  if ((pk >> 8) == 1 && es.fcnt < (REGF ? 2 : F16_FCAP)) {
                     if (REGF) {
                       if (es.fcnt == 0) { es.f0v = gmax; es.f0i = jb + first; } else { es.f1v = gmax; es.f1i = jb + first; }
                     } else {

@@ -8,6 +8,12 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..data import add_self_loops, remove_self_loops
+from .KTGNN import NodeLinear
+
+
+def _linear(x, weight):
+    """x W^T on the library's row-panel GEMM when the shape is one it takes (fp32 CUDA, widths <= 256), else ATen."""
+    return ops.linear(x, weight, None) if ops.linear_supported(x, weight) else F.linear(x, weight)
 
 
 class SAGEConv(nn.Module):
@@ -16,9 +22,9 @@ class SAGEConv(nn.Module):
     def __init__(self, in_channels, out_channels, root_weight=True, bias=True):
         super().__init__()
         self.in_channels, self.out_channels, self.root_weight = in_channels, out_channels, root_weight
-        self.lin_l = nn.Linear(in_channels, out_channels, bias=bias)
+        self.lin_l = NodeLinear(in_channels, out_channels, bias=bias)
         if root_weight:
-            self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+            self.lin_r = NodeLinear(in_channels, out_channels, bias=False)
 
     def reset_parameters(self):
         self.lin_l.reset_parameters()
@@ -30,7 +36,7 @@ class SAGEConv(nn.Module):
         if self.in_channels > self.out_channels:
             # mean aggregation commutes with the linear map: transform first, gather the narrower rows
             # (e.g. 1685 -> 64 one-hot inputs of the fb graphs: 26x less gather traffic)
-            out = ops.spmm(graph, torch.nn.functional.linear(x, self.lin_l.weight), "mean")
+            out = ops.spmm(graph, _linear(x, self.lin_l.weight), "mean")
             if self.lin_l.bias is not None:
                 out = out + self.lin_l.bias          # lin_l(mean) = W mean + b also for rows without in-edges
         else:
@@ -46,7 +52,7 @@ class GCNConv(nn.Module):
     def __init__(self, in_channels, out_channels, bias=True):
         super().__init__()
         self.in_channels, self.out_channels = in_channels, out_channels
-        self.lin = nn.Linear(in_channels, out_channels, bias=False)
+        self.lin = NodeLinear(in_channels, out_channels, bias=False)
         self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
         self._key, self._graph, self._dis = None, None, None
         self.reset_parameters()

@@ -61,18 +61,24 @@ knn_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ can
                  float delta, const float* __restrict__ seed_thr, const int* __restrict__ row_list,
                  const int* __restrict__ row_count, int few_rows, long long* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ out_gap,
                  int* __restrict__ fb_rows, int* __restrict__ fb_count, float eps, int* __restrict__ out_count) {
-  __shared__ float sv[MG_WARPS][MG_MAXC];
-  __shared__ int si[MG_WARPS][MG_MAXC];
-  extern __shared__ __align__(16) float sqrow[];  // [MG_WARPS][ld] when rescoring
+  // dynamic shared memory, sized for THIS call's lists (a fixed [MG_MAXC] per warp held the kernel at 5 CTAs per SM):
+  // per warp `cap` values, `cap` ids, `cap` 16-bit slots of the nominees that are re-scored; then [MG_WARPS][ld] query
+  // rows when rescoring
+  extern __shared__ __align__(16) float mg_smem[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cap = (nlists * kc + 31) / 32 * 32;
+  float* sv_all = mg_smem;
+  int* si_all = reinterpret_cast<int*>(sv_all + MG_WARPS * cap);
+  unsigned short* skl_all = reinterpret_cast<unsigned short*>(si_all + MG_WARPS * cap);
+  float* sqrow = reinterpret_cast<float*>(skl_all + MG_WARPS * cap);   // 16-byte aligned: cap is a multiple of 32
   const int nrows = row_list ? min(__ldg(row_count), nq) : nq;
   if (row_list && nrows <= few_rows) return;        // a handful of rows went through knn_exact_rows_kernel
   const long long r = (long long)blockIdx.x * MG_WARPS + wid;
   if (r >= nrows) return;
   const long long row = row_list ? (long long)row_list[r] : r;
   const int total = nlists * kc;
-  float* v = sv[wid];
-  int* ix = si[wid];
+  float* v = sv_all + wid * cap;
+  int* ix = si_all + wid * cap;
   // Largest approximate score any list may have discarded: a full list dropped only columns scoring
   // <= its minimum; a list that is not full kept every column of its split.
   // A seeded sweep additionally dropped every column scoring <= the row's seed threshold.
@@ -94,12 +100,49 @@ knn_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ can
   }
   __syncwarp();
   if (rescore) {
+    // Nominees that cannot reach the first k + 1 places are not re-scored.  With T = the (k+1)-th largest APPROXIMATE
+    // score of the row's nominees, a nominee below T - 2 delta scores, exactly, less than T - delta, which each of the
+    // k + 1 nominees at or above T reaches: it is strictly behind k + 1 others whatever the exact values are.  `lo`
+    // (bisection, count(v >= lo) >= k + 1 throughout) stands in for T; about half of the nominees go (the lists keep
+    // k + 4 each, the union needs k + 1), and the survivors are dealt round-robin to the lanes.
+    unsigned short* kl = skl_all + wid * cap;
+    if (delta >= 0.f) {
+      float vmin = INFINITY, vmax = -INFINITY;
+      int nvalid = 0;
+      for (int c = lane; c < total; c += 32)
+        if (ix[c] >= 0) { vmin = fminf(vmin, v[c]); vmax = fmaxf(vmax, v[c]); ++nvalid; }
+      vmin = -warp_max(-vmin);
+      vmax = warp_max(vmax);
+      nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+      if (nvalid > k + 1) {
+        float lo = vmin, hi = vmax;
+        for (int it = 0; it < 10; ++it) {
+          const float mid = 0.5f * (lo + hi);
+          int cnt = 0;
+          for (int c = lane; c < total; c += 32) cnt += (ix[c] >= 0 && v[c] >= mid) ? 1 : 0;
+          cnt = __reduce_add_sync(0xffffffffu, cnt);
+          if (cnt >= k + 1) lo = mid; else hi = mid;
+        }
+        // 1e-6 more: two raw scores that close may round to the same sigmoid, where the index would decide
+        const float cut = lo - 2.f * delta - 1e-6f;
+        for (int c = lane; c < total; c += 32)
+          if (ix[c] >= 0 && v[c] < cut) ix[c] = -1;
+      }
+    }
+    int nkept = 0;
+    for (int c0 = 0; c0 < total; c0 += 32) {
+      const int c = c0 + lane;
+      const bool keep = c < total && ix[c] >= 0;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) kl[nkept + __popc(m & ((1u << lane) - 1u))] = (unsigned short)c;
+      nkept += __popc(m);
+    }
     float* qr = sqrow + (size_t)wid * ld;
     for (int c = lane; c < ld; c += 32) qr[c] = qhi[row * ld + c] + (qlo ? qlo[row * ld + c] : 0.f);
     __syncwarp();
-    for (int c = lane; c < total; c += 32) {
+    for (int r = lane; r < nkept; r += 32) {
+      const int c = kl[r];
       const int j = ix[c];
-      if (j < 0) continue;
       const float4* ph = reinterpret_cast<const float4*>(dhi + (long long)j * ld);
       const float4* pl = dlo ? reinterpret_cast<const float4*>(dlo + (long long)j * ld) : nullptr;
       float acc = 0.f;
@@ -181,7 +224,10 @@ int launch_knn_merge(const float* cand_val, const int* cand_idx, int nlists, int
   if (nq <= 0) return BGNN_OK;
   if (nlists * kc > MG_MAXC) return BGNN_ERR_UNSUPPORTED;
   if (rescore && (ld % 4 != 0 || d % 4 != 0)) return BGNN_ERR_INVALID_ARG;
-  size_t dyn = rescore ? (size_t)MG_WARPS * ld * sizeof(float) : 0;
+  const size_t cap = (size_t)(nlists * kc + 31) / 32 * 32;
+  size_t dyn = MG_WARPS * cap * (sizeof(float) + sizeof(int) + sizeof(unsigned short)) +
+               (rescore ? (size_t)MG_WARPS * ld * sizeof(float) : 0);
+  if (dyn > 48 * 1024) BGNN_CUDA_TRY(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   knn_merge_kernel<<<(nq + MG_WARPS - 1) / MG_WARPS, MG_WARPS * 32, dyn, stream>>>(
       cand_val, cand_idx, nlists, kc, nq, k, rescore, qhi, qlo, dhi, dlo, d, ld, apply_sigmoid, delta, seed_thr,
       row_list, row_count, few_rows, out_idx, out_val, out_gap, fb_rows, fb_count, eps, out_count);

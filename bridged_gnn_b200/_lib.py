@@ -35,6 +35,8 @@ SIGNATURES = {
     "bgnn_edge_validity_f32": (_i32, [_vp, _vp, _i64] + [_vp] * 10 + [_i32, _f32, _vp, _vp, _vp]),
     "bgnn_edges_to_csr_workspace_bytes": (_sz, [_i64]),
     "bgnn_edges_to_csr": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bgnn_graph_prepare_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "bgnn_graph_prepare": (_i32, [_vp, _vp, _i64, _i64, _i32] + [_vp] * 9 + [_sz, _vp]),
     "bgnn_spmm_csr_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "bgnn_spmm_csr_ld_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),
     "bgnn_gatv2_fwd_part_f32": (_i32, [_vp] * 8 + [_f32, _i64, _i64, _i32] + [_vp] * 5),
@@ -140,7 +142,7 @@ def workspace(nbytes, device):
 # kernels launched per C-ABI call (hand-written kernels of this library only; CUB's sort/scan inside
 # bgnn_edges_to_csr are not counted)
 KERNELS_PER_CALL = {"bgnn_knn_cosine_f32": 13, "bgnn_knn_cosine_eps_f32": 13, "bgnn_knn_addrelu_eps_f32": 2, "bgnn_knn_cosine_f32[simt]": 4, "bgnn_knn_addrelu_f32": 2,
-                    "bgnn_edges_to_csr": 4, "bgnn_quantile_f32": 11, "bgnn_edge_validity_f32": 2, "bgnn_spmm_csr_f32": 1, "bgnn_gatv2_fwd_f32": 1, "bgnn_gatv2_bwd_f32": 3,
+                    "bgnn_edges_to_csr": 4, "bgnn_graph_prepare": 8, "bgnn_quantile_f32": 11, "bgnn_edge_validity_f32": 2, "bgnn_spmm_csr_f32": 1, "bgnn_gatv2_fwd_f32": 1, "bgnn_gatv2_bwd_f32": 3,
                     "bgnn_gatv2_fwd_ord_f32": 1, "bgnn_gatv2_bwd_ord_f32": 3, "bgnn_gatv2_fwd_part_f32": 1, "bgnn_gatv2_bwd_part_f32": 3,
                     "bgnn_gatv2_heads_fwd_part_f32": 1, "bgnn_gatv2_heads_bwd_part_f32": 3, "bgnn_spmm_csr_ld_f32": 1,
                     "bgnn_bn_relu_bwd_reduce_f32": 2, "bgnn_bn_relu_bwd_apply_f32": 1, "bgnn_rows_by_degree": 1,

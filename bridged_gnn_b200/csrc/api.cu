@@ -288,6 +288,23 @@ int bgnn_edges_to_csr(const int64_t* src, const int64_t* dst, int64_t e, int64_t
                              (long long*)e_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t bgnn_graph_prepare_workspace_bytes(int64_t e, int64_t n, int rewrite_self_loops) {
+  return (e < 0 || n < 0) ? 0 : graph_prepare_workspace_bytes(e, n, rewrite_self_loops);
+}
+
+int bgnn_graph_prepare(const int64_t* src, const int64_t* dst, int64_t e, int64_t n, int rewrite_self_loops,
+                       int32_t* rowptr, int32_t* col, int32_t* t_rowptr, int32_t* t_col, int32_t* csr_to_csc,
+                       int32_t* order, int32_t* t_order, int64_t* e_out, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  if (e < 0 || n < 0 || !rowptr || !e_out || (e > 0 && (!src || !dst))) return BGNN_ERR_INVALID_ARG;
+  const int64_t m = e + (rewrite_self_loops ? n : 0);
+  if (m > 0 && !col) return BGNN_ERR_INVALID_ARG;
+  if (m > 0 && (!workspace || workspace_bytes < graph_prepare_workspace_bytes(e, n, rewrite_self_loops))) return BGNN_ERR_WORKSPACE;
+  return launch_graph_prepare((const long long*)src, (const long long*)dst, e, n, rewrite_self_loops, rowptr, col, t_rowptr,
+                              t_col, csr_to_csc, order, t_order, (long long*)e_out, workspace, workspace_bytes,
+                              (cudaStream_t)stream);
+}
+
 int bgnn_spmm_csr_ld_f32(const int32_t* rowptr, const int32_t* col, const float* edge_w, const float* gather_scale,
                          const float* out_scale, const float* X, int64_t ldx, int64_t n_rows, int f, int reduce_mean,
                          float* Y, int64_t ldy, void* stream) {

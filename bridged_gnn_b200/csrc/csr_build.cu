@@ -127,6 +127,152 @@ int launch_edges_to_csr(const long long* src, const long long* dst, long long e,
   return BGNN_OK;
 }
 
+// ---- one-call graph preparation of the aggregation kernels ---------------------------------------------------
+// Everything KT-GNN's forward / backward need from a NEW edge list, straight from the caller's edge_index:
+//   * the self-loop rewrite of graph_partition (models/KTGNN.py:385-398: remove_self_loops, then add_self_loops)
+//     happens while the sort keys are made -- an edge with src == dst is parked behind the last row like an invalid
+//     one, and n keys (v, v) are appended -- so no filtered / concatenated copy of the edge list is ever written;
+//   * destination-major CSR: ONE keys-only radix sort of (dst, src) (no permutation back to the input is needed: the
+//     aggregation has no per-edge inputs);
+//   * transposed CSR + the CSR -> CSC slot map: a STABLE sort of the CSR-ordered edges on the source bits alone
+//     (half the radix passes of a second full sort; entries of a source row stay in destination order), whose
+//     payload -- the CSR position -- is the slot map;
+//   * both processing orders (rows by descending degree).
+// 168 B of sort traffic per edge against 288 B for two full pair sorts, and none of the index / cat / nonzero
+// passes of the host-side partition (2 of the 6.3 ms a new 2.1e7-edge graph cost, tools/profile_e2e.py).
+__global__ void prep_keys_kernel(const long long* __restrict__ src, const long long* __restrict__ dst, long long e,
+                                 long long n, int nb, int rewrite, unsigned long long* __restrict__ keys,
+                                 unsigned long long* __restrict__ bad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long m = e + (rewrite ? n : 0);
+  if (i >= m) return;
+  unsigned long long k;
+  if (i < e) {
+    long long s = src[i], d = dst[i];
+    if (s < 0 || s >= n || d < 0 || d >= n) {
+      atomicAdd(bad, 1ull);
+      s = 0;
+      d = n;
+    } else if (rewrite && s == d) {                  // a self loop of the input: dropped (re-added below)
+      s = 0;
+      d = n;
+    }
+    k = ((unsigned long long)d << nb) | (unsigned long long)s;
+  } else {
+    const unsigned long long v = (unsigned long long)(i - e);
+    k = (v << nb) | v;
+  }
+  keys[i] = k;
+}
+
+// col of the CSR, keys (src, dst) of the transposed sort with the CSR position as payload; parked entries keep
+// source n (behind the last transposed row)
+__global__ void prep_split_kernel(const unsigned long long* __restrict__ keys, long long m, long long n, int nb,
+                                  int* __restrict__ col, unsigned long long* __restrict__ tkeys,
+                                  unsigned int* __restrict__ vals) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const unsigned long long k = keys[i], mask = (1ull << nb) - 1ull;
+  const unsigned long long d = k >> nb, s = k & mask;
+  col[i] = (int)s;
+  if (tkeys) {
+    tkeys[i] = d >= (unsigned long long)n ? ((unsigned long long)n << nb) : ((s << nb) | d);
+    vals[i] = (unsigned int)i;
+  }
+}
+
+// rowptr[r] = first position whose row field (key >> nb) is >= r, r = 0..n; count = rowptr[n] (parked entries follow)
+__global__ void prep_rowptr_kernel(const unsigned long long* __restrict__ keys, long long m, long long n, int nb,
+                                   int* __restrict__ rowptr, long long* __restrict__ count) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n) return;
+  long long lo = 0, hi = m;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((long long)(keys[mid] >> nb) < r) lo = mid + 1; else hi = mid;
+  }
+  rowptr[r] = (int)lo;
+  if (r == n && count) *count = lo;
+}
+
+__global__ void prep_transposed_kernel(const unsigned long long* __restrict__ tkeys, const unsigned int* __restrict__ vals,
+                                       long long m, long long n, int nb, int* __restrict__ t_col,
+                                       int* __restrict__ csr_to_csc) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  const unsigned long long k = tkeys[q];
+  if ((k >> nb) >= (unsigned long long)n) return;    // parked
+  t_col[q] = (int)(k & ((1ull << nb) - 1ull));
+  csr_to_csc[vals[q]] = (int)q;
+}
+
+static size_t prep_sort_temp_bytes(long long m) {
+  size_t a = 0, b = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, a, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, m);
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const unsigned int*)nullptr, (unsigned int*)nullptr, m);
+  return a > b ? a : b;
+}
+
+size_t graph_prepare_workspace_bytes(long long e, long long n, int rewrite) {
+  const long long m = e + (rewrite ? n : 0);
+  if (m <= 0) return 256;
+  const size_t deg = rows_by_degree_workspace_bytes(n);
+  return (size_t)m * (8 + 8 + 4 + 4) + prep_sort_temp_bytes(m) + deg + 8 * 256;
+}
+
+int launch_graph_prepare(const long long* src, const long long* dst, long long e, long long n, int rewrite, int* rowptr,
+                         int* col, int* t_rowptr, int* t_col, int* csr_to_csc, int* order, int* t_order, long long* e_out,
+                         void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const long long m = e + (rewrite ? n : 0);
+  if (n < 0 || e < 0 || n >= (1ll << 31) || m >= (1ll << 31)) return BGNN_ERR_INVALID_ARG;
+  if ((t_rowptr != nullptr) != (t_col != nullptr) || (t_col != nullptr) != (csr_to_csc != nullptr)) return BGNN_ERR_INVALID_ARG;
+  if (t_order && !t_rowptr) return BGNN_ERR_INVALID_ARG;
+  const int T = 256;
+  if (m == 0) {
+    zero_rowptr_kernel<<<(unsigned)((n + 1 + T - 1) / T), T, 0, stream>>>(n, rowptr, e_out);
+    BGNN_LAUNCH_CHECK();
+    if (t_rowptr) BGNN_CUDA_TRY(cudaMemsetAsync(t_rowptr, 0, (size_t)(n + 1) * sizeof(int), stream));
+    return BGNN_OK;
+  }
+  Workspace w(ws, ws_bytes);
+  auto* k0 = w.take<unsigned long long>(m);
+  auto* k1 = w.take<unsigned long long>(m);
+  auto* v0 = w.take<unsigned int>(m);
+  auto* v1 = w.take<unsigned int>(m);
+  const size_t tb = prep_sort_temp_bytes(m);
+  auto* temp = w.take<char>(tb);
+  const size_t db = rows_by_degree_workspace_bytes(n);
+  auto* dws = w.take<char>(db);
+  if (!w.ok()) return BGNN_ERR_WORKSPACE;
+  const unsigned blocks = (unsigned)((m + T - 1) / T), rblocks = (unsigned)((n + 1 + T - 1) / T);
+  int nb = 1;
+  while ((1ll << nb) < n) ++nb;
+  zero_bad_kernel<<<1, 1, 0, stream>>>(e_out);
+  BGNN_LAUNCH_CHECK();
+  prep_keys_kernel<<<blocks, T, 0, stream>>>(src, dst, e, n, nb, rewrite, k0, reinterpret_cast<unsigned long long*>(e_out + 1));
+  BGNN_LAUNCH_CHECK();
+  size_t tbv = tb;
+  BGNN_CUDA_TRY(cub::DeviceRadixSort::SortKeys(temp, tbv, k0, k1, m, 0, 2 * nb + 1, stream));
+  prep_rowptr_kernel<<<rblocks, T, 0, stream>>>(k1, m, n, nb, rowptr, e_out);
+  BGNN_LAUNCH_CHECK();
+  prep_split_kernel<<<blocks, T, 0, stream>>>(k1, m, n, nb, col, t_col ? k0 : nullptr, v0);
+  BGNN_LAUNCH_CHECK();
+  int rc;
+  if (order && (rc = launch_rows_by_degree(rowptr, n, 0, order, dws, db, stream)) != BGNN_OK) return rc;
+  if (t_col) {
+    tbv = tb;
+    // stable: within a source row the CSR order (dst ascending) survives; source n (parked) needs bit 2 nb
+    BGNN_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, tbv, k0, k1, v0, v1, m, nb, 2 * nb + 1, stream));
+    prep_rowptr_kernel<<<rblocks, T, 0, stream>>>(k1, m, n, nb, t_rowptr, nullptr);
+    BGNN_LAUNCH_CHECK();
+    prep_transposed_kernel<<<blocks, T, 0, stream>>>(k1, v1, m, n, nb, t_col, csr_to_csc);
+    BGNN_LAUNCH_CHECK();
+    if (t_order && (rc = launch_rows_by_degree(t_rowptr, n, 0, t_order, dws, db, stream)) != BGNN_OK) return rc;
+  }
+  return BGNN_OK;
+}
+
 // ---- rows by descending degree ---------------------------------------------------------------------------
 // The row-parallel gather kernels take an optional processing order: longest rows first, so that a hub row of
 // a kNN graph starts at once instead of forming the tail of the launch, and rows sharing a warp have similar

@@ -71,6 +71,11 @@ size_t csr_build_workspace_bytes(long long e);
 int launch_edges_to_csr(const long long* src, const long long* dst, long long e, long long n, int dedup, int* rowptr,
                         int* col, long long* perm, long long* e_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+size_t graph_prepare_workspace_bytes(long long e, long long n, int rewrite);
+int launch_graph_prepare(const long long* src, const long long* dst, long long e, long long n, int rewrite, int* rowptr,
+                         int* col, int* t_rowptr, int* t_col, int* csr_to_csc, int* order, int* t_order, long long* e_out,
+                         void* ws, size_t ws_bytes, cudaStream_t stream);
+
 size_t rows_by_degree_workspace_bytes(long long n);
 int launch_rows_by_degree(const int* rowptr, long long n, int min_degree, int* order, void* ws, size_t ws_bytes,
                           cudaStream_t stream);

@@ -338,23 +338,71 @@ class _KTGNNBase(nn.Module):
             raise NotImplementedError("need_complement=True is not part of the accelerated hot path")
         self.cached_edges, self.dropout, self.use_bn, self.need_complement = cached_edges, dropout, use_bn, False
         self.convs, self.bns = nn.ModuleList(), nn.ModuleList()
-        self.edge_index1 = self.edge_index2 = self.edge_index = None
+        self._ei = None          # (edge_index1, edge_index2, edge_index) of graph_partition, cached (cached_edges)
+        self._fast = None        # (CSRGraph.prepared, data.edge_index, data.central_mask): the graph the kernels use
 
     graph_partition = staticmethod(graph_partition)
+
+    # The reference caches graph_partition's three edge lists as attributes (models/KTGNN.py:385-398).  On the GPU the
+    # aggregation never reads them -- the CSR comes straight from data.edge_index (``_graph``) -- so they are
+    # materialised on first access only; assigning None to ``edge_index`` announces a new graph, as in the reference.
+    def _materialize(self):
+        if self._ei is None and self._fast is not None:
+            graph, ei_in, cm = self._fast
+            self._ei = graph_partition(ei_in, cm)
+            ops.register_graph(self._ei[2], cm.shape[0], graph)     # cached_graph(self.edge_index, n) is this graph
+        return self._ei
+
+    @property
+    def edge_index(self):
+        t = self._materialize()
+        return None if t is None else t[2]
+
+    @edge_index.setter
+    def edge_index(self, value):
+        if value is not None:
+            raise AttributeError("edge_index is derived from data.edge_index; assign None to drop the cached graph")
+        self._ei = self._fast = None
+
+    @property
+    def edge_index1(self):
+        t = self._materialize()
+        return None if t is None else t[0]
+
+    @property
+    def edge_index2(self):
+        t = self._materialize()
+        return None if t is None else t[1]
 
     def _edges(self, data):
         if not self.cached_edges:
             return graph_partition(data.edge_index, data.central_mask)
-        if self.edge_index is None:
-            self.edge_index1, self.edge_index2, self.edge_index = graph_partition(data.edge_index, data.central_mask)
-        return self.edge_index1, self.edge_index2, self.edge_index
+        if self._ei is None and self._fast is None:
+            self._ei = graph_partition(data.edge_index, data.central_mask)
+        return self._materialize()
+
+    def _graph(self, data):
+        """(edge_index1, edge_index2, graph) for the convs.  CUDA + cached_edges: ``graph`` is a ``CSRGraph.prepared`` built
+        by ONE library call from ``data.edge_index`` (self-loop rewrite inside the key construction, transposed CSR by
+        a stable sort on the source bits, slot map, row orders) and the two partitioned lists stay None -- the kernels
+        pick the branch per destination row from ``central_mask``.  Otherwise: graph_partition's tensors."""
+        ei_in = data.edge_index
+        if not (self.cached_edges and torch.is_tensor(ei_in) and ei_in.is_cuda and ei_in.dtype == torch.int64):
+            return self._edges(data)
+        training = self.training and torch.is_grad_enabled()
+        if self._fast is None or (training and self._fast[0]._t is None):
+            if self._ei is not None:        # the partition was materialised before (CPU-style use): keep using it
+                return self._ei
+            g = ops.CSRGraph.prepared(ei_in, data.central_mask.shape[0], rewrite_self_loops=True, training=training)
+            self._fast = (g, ei_in, data.central_mask)
+        return None, None, self._fast[0]
 
     def prepare_graph(self, data):
         """Everything of a forward / backward pass that depends on the graph alone (models/KTGNN.py:385-398
-        graph_partition, then the CSR, transposed CSR and row orders of the aggregation kernels), cached for the
-        calls that follow.  ``data`` needs ``edge_index`` and ``central_mask`` only: a serving loop can call this
-        while ``data.x`` is still being copied to the device on another stream."""
-        _, _, ei = self._edges(data)
+        graph_partition's self-loop rewrite, then the CSR, transposed CSR and row orders of the aggregation kernels),
+        cached for the calls that follow.  ``data`` needs ``edge_index`` and ``central_mask`` only: a serving loop can
+        call this while ``data.x`` is still being copied to the device on another stream."""
+        _, _, ei = self._graph(data)
         ops.cached_graph(ei, data.central_mask.shape[0]).prepare(training=self.training and torch.is_grad_enabled())
         for conv in list(self.convs) + [m for m in self.children() if isinstance(m, AdaptedConv)]:
             conv._dst_is_src(data.central_mask)
@@ -391,7 +439,7 @@ class KTGNN_no_complement(_KTGNNBase):
                                              NodeLinear(hidden, hidden))
 
     def get_emb(self, data):
-        ei1, ei2, ei = self._edges(data)
+        ei1, ei2, ei = self._graph(data)
         return self._hidden(data.x, ei, ei1, ei2, data.central_mask, len(self.convs))
 
     def forward(self, data):
@@ -405,7 +453,7 @@ class KTGNN_no_complement(_KTGNNBase):
             ei1 = ei2 = None
             ei = data.edge_index
         else:
-            ei1, ei2, ei = self._edges(data)
+            ei1, ei2, ei = self._graph(data)
         c = data.central_mask
         x = self._hidden(data.x, ei, ei1, ei2, c, len(self.convs), part)
         logits_base, logits_trans, logits_target = adapted_convs_shared_graph(
@@ -429,11 +477,11 @@ class KTGNN_noDTC(_KTGNNBase):
                     self.bns.append(nn.BatchNorm1d(hidden))
 
     def get_emb(self, data):
-        ei1, ei2, ei = self._edges(data)
+        ei1, ei2, ei = self._graph(data)
         return self._hidden(data.x, ei, ei1, ei2, data.central_mask, len(self.convs) - 1)
 
     def forward(self, data):
-        ei1, ei2, ei = self._edges(data)
+        ei1, ei2, ei = self._graph(data)
         c = data.central_mask
         x = self._hidden(data.x, ei, ei1, ei2, c, len(self.convs) - 1)
         x = self.convs[-1](x, ei, ei1, ei2, c)

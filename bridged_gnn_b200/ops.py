@@ -226,9 +226,58 @@ class CSRGraph:
         self._order = None
         self._t_order = None
 
+    @classmethod
+    def prepared(cls, edge_index, num_nodes, rewrite_self_loops=True, training=True):
+        """CSR, transposed CSR, CSR -> CSC slot map and both processing orders of a NEW edge list in one library call
+        (``bgnn_graph_prepare``).  ``rewrite_self_loops``: graph_partition's ``add_self_loops(remove_self_loops(.))``
+        (models/KTGNN.py:385-398) happens inside the key construction, so no filtered / concatenated copy of the edge
+        list is made.  The result equals ``CSRGraph(graph_partition(edge_index, mask)[2], n)`` after ``prepare()``,
+        except that ``perm`` (the map back to an input edge list) is None: the aggregation has no per-edge inputs."""
+        lib = _lib.load()
+        if not edge_index.is_cuda or edge_index.dtype != torch.int64:
+            raise TypeError("CSRGraph.prepared needs an int64 CUDA edge_index")
+        n, e = int(num_nodes), int(edge_index.shape[1])
+        dev = edge_index.device
+        src, dst = edge_index[0].contiguous(), edge_index[1].contiguous()
+        cap = max(e + (n if rewrite_self_loops else 0), 1)
+        i32 = torch.int32
+        g = cls.__new__(cls)
+        g.n = g.n_src = g.n_rows = n
+        g.row_off = 0
+        g.edge_index, g._dst, g.perm = None, None, None
+        rowptr = torch.empty((n + 1,), dtype=i32, device=dev)
+        col = torch.empty((cap,), dtype=i32, device=dev)
+        order = torch.empty((n,), dtype=i32, device=dev)
+        t_rowptr = t_col = c2c = t_order = None
+        if training:
+            t_rowptr = torch.empty((n + 1,), dtype=i32, device=dev)
+            t_col = torch.empty((cap,), dtype=i32, device=dev)
+            c2c = torch.empty((cap,), dtype=i32, device=dev)
+            t_order = torch.empty((n,), dtype=i32, device=dev)
+        e_out = torch.zeros((2,), dtype=torch.int64, device=dev)
+        ws = _lib.workspace(lib.bgnn_graph_prepare_workspace_bytes(e, n, int(rewrite_self_loops)), dev)
+        with _lib.call("bgnn_graph_prepare"):
+            _lib.check(lib.bgnn_graph_prepare(_lib.ptr(src, torch.int64) if e else None, _lib.ptr(dst, torch.int64) if e else None,
+                                              e, n, int(rewrite_self_loops), _lib.ptr(rowptr), _lib.ptr(col),
+                                              _lib.ptr(t_rowptr, allow_none=True), _lib.ptr(t_col, allow_none=True),
+                                              _lib.ptr(c2c, allow_none=True), _lib.ptr(order), _lib.ptr(t_order, allow_none=True),
+                                              _lib.ptr(e_out), _lib.ptr(ws), ws.numel(), _lib.stream(dev)))
+        ne, bad = e_out.tolist()      # one sync per graph build
+        if bad:
+            raise IndexError("edge_index holds %d edge(s) with a node id outside [0, %d)" % (bad, n))
+        g.e = int(ne)
+        g.rowptr, g.col = rowptr, col[: max(g.e, 1)]
+        g._t = (t_rowptr, t_col[: max(g.e, 1)], None) if training else None
+        g._csr_to_csc = c2c[: max(g.e, 1)] if training else None
+        g._order, g._t_order = order, t_order
+        g._deg = None
+        return g
+
     @property
     def t(self):
         if self._t is None:
+            if self.edge_index is None:
+                raise RuntimeError("this graph was prepared without its transposed CSR (training=False)")
             self._t = edges_to_csr(self._dst, self.edge_index[0], self.n)[:3]
         return self._t
 
@@ -283,9 +332,24 @@ class CSRGraph:
 _graph_cache = {}
 
 
+def _graph_key(edge_index, num_nodes, n_rows=None, row_off=0):
+    return (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device),
+            n_rows, row_off)
+
+
+def register_graph(edge_index, num_nodes, graph):
+    """Makes ``cached_graph(edge_index, num_nodes)`` return ``graph`` (a CSRGraph built by other means for this very
+    edge list, e.g. ``CSRGraph.prepared`` of the un-partitioned list)."""
+    if len(_graph_cache) >= 4:
+        _graph_cache.pop(next(iter(_graph_cache)))
+    graph._pinned_edges = edge_index          # the key holds an address: keep the tensor alive with the entry
+    _graph_cache[_graph_key(edge_index, num_nodes)] = graph
+
+
 def cached_graph(edge_index, num_nodes, n_rows=None, row_off=0):
-    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device),
-           n_rows, row_off)
+    if isinstance(edge_index, CSRGraph):
+        return edge_index
+    key = _graph_key(edge_index, num_nodes, n_rows, row_off)
     g = _graph_cache.get(key)
     if g is None:
         if len(_graph_cache) >= 4:      # a handful of live graphs; each entry pins its edge list and two CSRs

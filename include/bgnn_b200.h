@@ -118,6 +118,23 @@ int bgnn_edges_to_csr(const int64_t* src, const int64_t* dst, int64_t e, int64_t
                       int32_t* col, int64_t* perm, int64_t* e_out, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* One-call graph preparation of the aggregation kernels, straight from the caller's edge_index.
+ * Replaces KTGNN.graph_partition's self-loop rewrite (models/KTGNN.py:385-398: remove_self_loops + add_self_loops;
+ * the split by destination domain needs no edge copy here, the kernels pick the branch per destination row) and the
+ * per-forward SparseTensor build (models/backbones.py:464).  rewrite_self_loops != 0: input edges with src == dst are
+ * dropped and one (v, v) per node is added.  Capacity of col / t_col / csr_to_csc: e + (rewrite_self_loops ? n : 0).
+ *   rowptr [n+1], col            destination-major CSR (rows sorted by destination, then source)
+ *   t_rowptr [n+1], t_col        CSR of the transposed graph (rows = sources, entries = destinations, ascending)
+ *   csr_to_csc                   slot of every CSR edge in the transposed CSR       (the three: all NULL or none)
+ *   order, t_order [n]           rows by descending in- / out-degree (bgnn_rows_by_degree(.., 0)); either may be NULL
+ *   e_out [2] int64              [0] = edges kept, [1] = input edges with a node id outside [0, n) (parked, unread)
+ * Identical to bgnn_edges_to_csr on the rewritten edge list and on its transpose. */
+size_t bgnn_graph_prepare_workspace_bytes(int64_t e, int64_t n, int rewrite_self_loops);
+int bgnn_graph_prepare(const int64_t* src, const int64_t* dst, int64_t e, int64_t n, int rewrite_self_loops,
+                       int32_t* rowptr, int32_t* col, int32_t* t_rowptr, int32_t* t_col, int32_t* csr_to_csc,
+                       int32_t* order, int32_t* t_order, int64_t* e_out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* ---- message passing ------------------------------------------------------------------------
  *
  * CSR SpMM:  Y[i,:] = out_scale[i] * (1/deg_i if reduce_mean) * sum_e edge_w[e] * gather_scale[col[e]] * X[col[e],:]

@@ -56,6 +56,81 @@ def test_coalesce_matches_pyg_semantics(n, e):
     assert torch.equal(to_undirected(ei.cuda(), n).cpu(), mo.to_undirected(ei, n))
 
 
+@pytest.mark.parametrize("n,e,training", [(1, 0, True), (10, 0, True), (7, 30, True), (1000, 20000, True),
+                                          (1024, 30000, False), (3408, 37522, True), (100000, 1 << 20, True)])
+def test_graph_prepare_equals_partition_then_csr(n, e, training):
+    """bgnn_graph_prepare (self-loop rewrite inside the key construction, keys-only sort, transposed CSR by a stable
+    sort on the source bits, slot map, row orders) against the path it replaces: graph_partition's
+    add_self_loops(remove_self_loops(.)) on the host, then two full CSR builds -- every array bit for bit."""
+    ops = _ops()
+    from bridged_gnn_b200.models import graph_partition
+    ei = _rand_graph(n, e, 5).cuda()
+    if e:
+        ei[1, : e // 8] = ei[0, : e // 8]                      # plenty of self loops in the input
+        ei[:, e // 8: e // 4] = ei[:, : e // 4 - e // 8]       # and duplicate edges (kept, like the reference)
+    cm = torch.zeros(n, dtype=torch.bool, device="cuda")
+    cm[: n * 3 // 4] = True
+    ref = ops.CSRGraph(graph_partition(ei, cm)[2], n).prepare(training=training)
+    g = ops.CSRGraph.prepared(ei, n, rewrite_self_loops=True, training=training)
+    assert g.e == ref.e and g.n == ref.n and g.n_rows == ref.n_rows
+    assert torch.equal(g.rowptr, ref.rowptr) and torch.equal(g.col, ref.col)
+    assert torch.equal(g.order(), ref.order())
+    if training:
+        assert torch.equal(g.t[0], ref.t[0]) and torch.equal(g.t[1], ref.t[1])
+        assert torch.equal(g.csr_to_csc, ref.csr_to_csc)
+        assert torch.equal(g.t_order(), ref.t_order())
+    else:
+        assert g._t is None
+    # without the rewrite it is a plain CSR build of the list as given
+    g2 = ops.CSRGraph.prepared(ei, n, rewrite_self_loops=False, training=True)
+    ref2 = ops.CSRGraph(ei, n).prepare(training=True)
+    assert g2.e == ref2.e and torch.equal(g2.rowptr, ref2.rowptr) and torch.equal(g2.col[: g2.e], ref2.col[: g2.e])
+    assert torch.equal(g2.t[0], ref2.t[0]) and torch.equal(g2.t[1][: g2.e], ref2.t[1][: g2.e])
+    if e:
+        bad = ei.clone()
+        bad[0, 0] = n
+        with pytest.raises(IndexError):
+            ops.CSRGraph.prepared(bad, n)
+
+
+def test_ktgnn_fast_graph_path_matches_partitioned_lists():
+    """On the GPU the model builds its graph with ONE library call from data.edge_index; the reference's cached
+    edge_index1 / edge_index2 / edge_index attributes are materialised on first access, are graph_partition's, and
+    map to the very graph the kernels used."""
+    ops = _ops()
+    from bridged_gnn_b200.data import Data
+    from bridged_gnn_b200.models import KTGNN_no_complement, graph_partition
+    n = 3000
+    g = torch.Generator().manual_seed(9)
+    ei = torch.randint(0, n, (2, 40000), generator=g).cuda()
+    cm = (torch.arange(n) < 2000).cuda()
+    x = torch.randn(n, 64, generator=g).cuda()
+    data = Data(x=x, edge_index=ei, central_mask=cm)
+    torch.manual_seed(0)
+    model = KTGNN_no_complement(64, 3, 2, 32, root_weight=False, use_bn=True, dim_share=64, dropout=0.0).cuda().train()
+    out = model(data)
+    assert model._ei is None and model._fast is not None          # nothing was partitioned on the host
+    fast = model._fast[0]
+    e1, e2, e = graph_partition(ei, cm)
+    assert torch.equal(model.edge_index1, e1) and torch.equal(model.edge_index2, e2) and torch.equal(model.edge_index, e)
+    assert ops.cached_graph(model.edge_index, n) is fast
+    sum(o.sum() for o in out[:3]).backward()
+    g_fast = [p.grad.clone() for p in model.parameters()]
+    # the same step over the partitioned lists (the path of a CPU-style caller): identical graph, identical numbers
+    model.zero_grad()
+    model.edge_index = None
+    model._ei = (e1, e2, e)
+    out2 = model(data)
+    assert model._fast is None
+    for a, b in zip(out[:3], out2[:3]):
+        assert torch.equal(a, b)
+    sum(o.sum() for o in out2[:3]).backward()
+    for a, p in zip(g_fast, model.parameters()):
+        assert torch.equal(a, p.grad)
+    with pytest.raises(AttributeError):
+        model.edge_index = e
+
+
 def test_office_undirected_and_partition(office_build, office_mp):
     from bridged_gnn_b200.data import to_undirected
     from bridged_gnn_b200.models import graph_partition

@@ -146,3 +146,11 @@ def test_round2_entry_points_reject_invalid_arguments(lib):
     # the backward workspace now also holds scores and per-CTA partials of pass B: grows with n and e
     a, b = lib.bgnn_gatv2_bwd_workspace_bytes(1000, 20000, 64), lib.bgnn_gatv2_bwd_workspace_bytes(2000, 40000, 64)
     assert b > a > 20000 * 20
+    # one-call graph preparation: NULL edge list with e > 0, the three transposed outputs all or none, workspace
+    assert lib.bgnn_graph_prepare_workspace_bytes(37522, 3408, 1) > (37522 + 3408) * 24
+    assert lib.bgnn_graph_prepare_workspace_bytes(-1, 3408, 1) == 0
+    assert lib.bgnn_graph_prepare(null, null, 5, 10, 1, one, one, null, null, null, null, null, one, one, 1 << 20, null) == -1
+    assert lib.bgnn_graph_prepare(one, one, 5, 10, 1, one, one, one, null, null, null, null, one, one, 1 << 20, null) == -1
+    assert lib.bgnn_graph_prepare(one, one, 5, 10, 1, one, one, null, null, null, null, one, one, one, 1 << 20, null) == -1
+    assert lib.bgnn_graph_prepare(one, one, 5, 10, 1, one, one, null, null, null, null, null, one, one, 64, null) == -2
+

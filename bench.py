@@ -668,13 +668,32 @@ def run_ours(args):
 
     edges_h = torch.empty(tuple(cross_edges.shape), dtype=cross_edges.dtype).pin_memory()
 
+    # Serving-loop pipeline, as in the message-passing e2e below: the copy engine brings in the embeddings of build i+1
+    # while build i runs (one input copy and one result copy per build, all inside the timed region).
+    knn_copy_stream = torch.cuda.Stream(device=dev)
+
+    def issue_embeddings():
+        with torch.cuda.stream(knn_copy_stream):
+            us, ut = u_src_h.to(dev, non_blocking=True), u_tar_h.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(knn_copy_stream)
+        return us, ut, ev
+    knn_pending = [issue_embeddings()]
+
     def build_e2e():
-        us, ut = u_src_h.to(dev, non_blocking=True), u_tar_h.to(dev, non_blocking=True)
+        cur = torch.cuda.current_stream(dev)
+        us, ut, ev = knn_pending.pop()
+        knn_pending.append(issue_embeddings())
+        cur.wait_event(ev)
+        for t in (us, ut):
+            t.record_stream(cur)
         out = build(us, ut)
         edges_h.copy_(out[4], non_blocking=True)      # the edge list lands in a pinned host buffer
-        torch.cuda.current_stream(dev).synchronize()
+        cur.synchronize()
         return edges_h
     knn_e2e_ms = timed(build_e2e, max(3, K // 2), 3)
+    knn_copy_stream.synchronize()
+    del knn_pending
     calls, tot = knn_calls.get("bgnn_knn_cosine_f32", (1, 0.0))
     knn_call_ms = tot / max(calls, 1)
     flops = 2.0 * NT * NS * DIM

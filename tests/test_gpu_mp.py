@@ -946,6 +946,30 @@ def test_sage_backward_matches_oracle(office_mp, office_build):
         assert relclose(p.grad, P[k].grad, 2e-5), k
 
 
+def test_gcn_backward_matches_oracle(office_mp, office_build):
+    """GCNNet training gradients (scaled SpMM backward over the transposed CSR, NodeLinear weight gradients) against
+    autograd through the oracle's restatement of GCNConv (models/backbones.py:269-277, PyG gcn_norm)."""
+    import types
+    from bridged_gnn_b200.models import GCNNet
+    m = office_mp
+    data = _office_data(office_build, office_mp)
+    ds = types.SimpleNamespace(num_features=256, num_classes=31)
+    gcn = GCNNet(ds, layer_num=2, hidden=64)
+    sd = sub_state(m, "gcn.sd.")
+    gcn.load_state_dict(sd)
+    gcn.cuda().eval()        # dropout off; no BatchNorm in GCNNet, so eval == train numerically
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x, ei = T(office_build["x"]), T(m["edge_index_undirected"])
+    lp_ref = mo.gcn_net(x, ei, P)
+    tm, y = T(office_build["train_mask"]), T(office_build["y"])
+    torch.nn.functional.nll_loss(lp_ref[tm], y[tm]).backward()
+    lp = gcn(data)
+    assert relclose(lp, lp_ref.detach())
+    torch.nn.functional.nll_loss(lp[data.train_mask], data.y[data.train_mask]).backward()
+    for k, p in gcn.named_parameters():
+        assert relclose(p.grad, P[k].grad, 2e-5), k
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_large_graph_properties():
     """Config-4-sized aggregation (2^20 nodes, ~1.6e7 edges): constant features must aggregate to the

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(f16_threads(EW), 1)
 knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
                       int nq, int ndb, int kblocks, int tiles_total, int tiles_per_split, int kc, int stages, int kps,
                       const float* __restrict__ thr_init, float* __restrict__ cand_val, int* __restrict__ cand_idx,
-                      int seed_segs, int dbg_arg) {
+                      int seed_segs, int dbg_arg, int drain_tiles) {
   constexpr bool SEED = MODE == 1;
   constexpr bool REGF = EW == 4;                   // pending candidates in registers
   static_assert(EW == 2 || EW == 4, "two or four epilogue warps per lane quarter");
@@ -443,7 +443,7 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // is all the seed has to guarantee -- maxima only instead of a top-k.
     const int seg_tiles = SEED ? max(1, ntiles / max(seed_segs, 1)) : 0;
     int seg_left = seg_tiles, segs_done = 0;
-    int drain_left = F16_DRAIN_TILES;
+    int drain_left = drain_tiles;
     long long w_tfull = 0, w_ld = 0, w_proc = 0, w_drain = 0, w_hit = 0, e_start = clock64();
     int n_hit_tiles = 0;
     for (int t = 0; t < ntiles; ++t) {
@@ -451,7 +451,7 @@ knn_cosine_f16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       const uint32_t tph = (uint32_t)(t / NBUF) & 1u;
       long long c0 = (dbg & 8) ? clock64() : 0;
       if (!SEED && --drain_left == 0) {
-        drain_left = F16_DRAIN_TILES;
+        drain_left = drain_tiles;
         if (__any_sync(0xffffffffu, es.fcnt > 0)) es = epi_drain<REGF>(es, ea);
       }
       if (dbg & 8) { const long long c1 = clock64(); w_drain += c1 - c0; c0 = c1; }
@@ -705,6 +705,7 @@ static int launch_f16_cfg(const void* qh, int nq, const void* dh, int ndb, int l
   const int tiles = (ndb + BN - 1) / BN;
   const int qblocks = (nq + F16_BM - 1) / F16_BM;
   const int dbg = f16_dbg_env();
+  static const int drain = getenv("BGNN_F16_DRAIN") ? max(1, atoi(getenv("BGNN_F16_DRAIN"))) : F16_DRAIN_TILES;   // tuning experiments
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(PAIR ? (qblocks + 1) / 2 * 2 : qblocks, plan.nsplit);   // a pair = two neighbouring query blocks
   cfg.blockDim = dim3(f16_threads(EW));
@@ -718,7 +719,7 @@ static int launch_f16_cfg(const void* qh, int nq, const void* dh, int ndb, int l
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   BGNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mq, md, nq, ndb, kblocks, tiles, plan.tiles_per_split, plan.kc, plan.stages,
-                                   plan.kps, thr_init, cand_val, cand_idx, seed_segs, dbg));
+                                   plan.kps, thr_init, cand_val, cand_idx, seed_segs, dbg, drain));
   return BGNN_OK;
 }
 

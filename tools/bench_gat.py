@@ -34,6 +34,10 @@ def main():
     _, _, eall = graph_partition(ei, cm)
     graph = ops.CSRGraph(eall, n)
     _ = graph.t, graph.csr_to_csc
+    if os.environ.get("BGNN_HACK_SEQ_RECORDS"):
+        # timing experiment only (results are garbage): pass A writes its per-edge records in CSR order instead of
+        # scattering them to their transposed-CSR slots -- what does the scatter cost?  (profiles/r03k)
+        graph._csr_to_csc = torch.arange(graph.e, dtype=torch.int32, device=dev)
     e = graph.e
     cm8 = cm.to(torch.uint8)
     peak = bench.load_peaks()["hbm_gbs"]

@@ -21,7 +21,7 @@ if has launches; then
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --no-sync16m > $O/${T}_ncu_launches.log 2>&1
 fi
 if has gat; then
-  ncu --set full --import-source on --clock-control none -k 'regex:gatv2_(heads_)?(fwd|bwd_dst|bwd_src)_kernel' -c 7 -o $O/${T}_prof_gat \
+  ncu --set full --import-source on --clock-control none -k 'regex:gatv2_(heads_)?(fwd|bwd_dst|bwd_dst_hub|bwd_src)_kernel' -c 6 -o $O/${T}_prof_gat \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras --no-sync16m > $O/${T}_ncu_gat.log 2>&1
 fi
 if has dense; then
